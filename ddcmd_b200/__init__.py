@@ -1,0 +1,295 @@
+"""ddcmd_b200 - B200-native Martini MD step behind ddcMD's object-database API.
+
+Python here is plumbing only (ctypes over the C-ABI in include/ddcmd_b200.h and the plain-C
+host layer in include/ddcmd_b200_host.h); the product is libddcmd_b200.so.  There is no CPU
+path: compute calls raise when no sm_100 device is present.
+
+Reference-facing names are kept: ``simulate_init`` (src/simulate.c:104), ``ddcenergy``
+(src/ddcenergy.c:160), ``nglf`` (src/nglf.c:67), ``eval_energyInfo`` (src/energyInfo.c:75),
+``constructList`` (src/nlistGPU.h:184).
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+from . import build as _build
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_lib = None
+
+
+class Params(C.Structure):
+    _fields_ = [("h", C.c_double * 9), ("pbc", C.c_int), ("updateRate", C.c_int), ("rmax", C.c_double),
+                ("deltaR", C.c_double), ("minBoxSide", C.c_double), ("keR", C.c_double), ("krf", C.c_double),
+                ("crf", C.c_double), ("center", C.c_double * 3), ("nConstraints", C.c_int), ("device", C.c_int)]
+
+
+class EType(C.Structure):
+    _fields_ = [("eion", C.c_double), ("rk", C.c_double), ("virial", C.c_double * 6), ("tion", C.c_double * 6),
+                ("sion", C.c_double * 6), ("pion", C.c_double), ("temperature", C.c_double), ("number", C.c_double),
+                ("volume", C.c_double), ("eLJ", C.c_double), ("eEle", C.c_double), ("eBond", C.c_double),
+                ("eAngle", C.c_double), ("eTorsion", C.c_double), ("eImproper", C.c_double), ("eRestraint", C.c_double),
+                ("molVirial", C.c_double * 3), ("molPressure", C.c_double * 3), ("pMolecular", C.c_double),
+                ("loop", C.c_int64), ("time", C.c_double), ("nMolecules", C.c_int64), ("nPairsListed", C.c_int64)]
+
+
+_P = C.POINTER
+
+
+class DeckStruct(C.Structure):
+    _fields_ = [("dt", C.c_double), ("time", C.c_double), ("loop", C.c_int64), ("maxloop", C.c_int64),
+                ("printrate", C.c_int), ("deltaloop", C.c_int), ("snapshotrate", C.c_int), ("checkpointrate", C.c_int),
+                ("params", Params), ("ddc_lx", C.c_int), ("ddc_ly", C.c_int), ("ddc_lz", C.c_int),
+                ("rcoulomb", C.c_double), ("epsilon_r", C.c_double), ("epsilon_rf", C.c_double), ("rmax4all", C.c_double),
+                ("excludePotentialTerm", C.c_int), ("potentialShift", C.c_int),
+                ("kB", C.c_double), ("ke", C.c_double), ("lengthPerAngstrom", C.c_double), ("energyPerKJmol", C.c_double),
+                ("massPerAmu", C.c_double), ("pressurePerBar", C.c_double), ("timePerFs", C.c_double),
+                ("printMolecularPressure", C.c_int),
+                ("nspecies", C.c_int), ("speciesName", _P(C.c_char_p)), ("specLJ", _P(C.c_int)),
+                ("specCharge", _P(C.c_double)), ("specMass", _P(C.c_double)), ("specMolType", _P(C.c_int)),
+                ("specResidue", _P(C.c_int)), ("specAtom", _P(C.c_int)),
+                ("ntypes", C.c_int), ("ljEps", _P(C.c_double)), ("ljSigma", _P(C.c_double)), ("ljShift", _P(C.c_double)),
+                ("nMolTypes", C.c_int), ("molTypeNSpecies", _P(C.c_int)), ("molTypeResidue", _P(C.c_int)),
+                ("molTypeOwnerOffset", _P(C.c_int)), ("bpairOffset", _P(C.c_int)), ("bpairI", _P(C.c_int)), ("bpairJ", _P(C.c_int)),
+                ("n", C.c_int64), ("gid", _P(C.c_uint64)), ("species", _P(C.c_int)),
+                ("rx", _P(C.c_double)), ("ry", _P(C.c_double)), ("rz", _P(C.c_double)),
+                ("vx", _P(C.c_double)), ("vy", _P(C.c_double)), ("vz", _P(C.c_double)),
+                ("nTerms", C.c_int64), ("termKind", _P(C.c_int)), ("termIdx", _P(C.c_int)), ("termParm", _P(C.c_double)),
+                ("nRestraints", C.c_int64), ("restrBead", _P(C.c_int)), ("restrFrac0", _P(C.c_double)),
+                ("restrKb", _P(C.c_double)), ("restrFc", _P(C.c_double)), ("restrOrigin", C.c_int),
+                ("nMol", C.c_int64), ("nMolTotal", C.c_int64), ("molOffset", _P(C.c_int64)), ("molBeads", _P(C.c_int))]
+
+
+class DdcError(RuntimeError):
+    pass
+
+
+def lib():
+    """Load libddcmd_b200.so (building it in-tree with nvcc when sources are newer)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    path = os.path.join(_HERE, "libddcmd_b200.so")
+    if _build.needs_build():
+        try:
+            _build.build()
+        except Exception as e:  # a prebuilt .so that travelled with the snapshot is still usable
+            if not os.path.exists(path):
+                raise DdcError("libddcmd_b200.so is missing and could not be built: %s" % e)
+    L = C.CDLL(path)
+    vp, i32, i64, dbl = C.c_void_p, C.c_int, C.c_int64, C.c_double
+    pd, pi = _P(C.c_double), _P(C.c_int)
+    sig = {
+        "ddcb200_lastError": (C.c_char_p, []),
+        "ddcb200_deviceCount": (i32, []),
+        "ddcb200_create": (i32, [_P(Params), _P(vp)]),
+        "ddcb200_destroy": (None, [vp]),
+        "ddcb200_sync": (i32, [vp]),
+        "ddcb200_martiniNonBondParms": (i32, [vp, i32, pd, pd, pd]),
+        "ddcb200_setSpecies": (i32, [vp, i32, pi, pd, pd]),
+        "ddcb200_setBeads": (i32, [vp, i64, _P(C.c_uint64), pi]),
+        "ddcb200_setExclusions": (i32, [vp, i32, pi, pi, pi, pi, pi]),
+        "ddcb200_martiniBondParms": (i32, [vp, i64, pi, pi, pd]),
+        "ddcb200_setRestraints": (i32, [vp, i64, pi, pd, pd, pd, i32]),
+        "ddcb200_setMolecules": (i32, [vp, i64, _P(C.c_int64), pi, i64]),
+        "ddcb200_sendState": (i32, [vp, i64, pi, pd, pd, pd, pd, pd, pd, i64, dbl]),
+        "ddcb200_numLocal": (i64, [vp]),
+        "ddcb200_getLocalBeads": (i32, [vp, pi]),
+        "ddcb200_getState": (i32, [vp] + [pd] * 9),
+        "ddcb200_constructList": (i32, [vp]),
+        "ddcb200_ddcenergy": (i32, [vp, i32]),
+        "ddcb200_nglf": (i32, [vp, i32, dbl]),
+        "ddcb200_energyInfo": (i32, [vp, dbl, _P(EType)]),
+        "ddcb200_getCells": (i32, [vp, pi, pi, pd]),
+        "ddcb200_getPairs": (i64, [vp, i64, pi, pi, pi]),
+        "ddcb200_profile": (i32, [vp, i32]),
+        "ddcb200_profileRead": (i32, [vp, pd, _P(C.c_int64), i32]),
+        "ddcb200_ncclUniqueId": (i32, [C.c_char_p]),
+        "ddcb200_ddcInit": (i32, [vp, i32, i32, i32, i32, i32, C.c_char_p]),
+        "ddcb200_deckLoad": (i32, [C.c_char_p, C.c_char_p, C.c_char_p, _P(_P(DeckStruct))]),
+        "ddcb200_deckFree": (None, [_P(DeckStruct)]),
+        "ddcb200_lastHostError": (C.c_char_p, []),
+        "ddcb200_simulateBind": (i32, [_P(DeckStruct), i32, _P(vp)]),
+        "ddcb200_printinfoLine": (i32, [_P(DeckStruct), _P(EType), C.c_char_p, C.c_size_t]),
+        "ddcb200_unitsConvert": (dbl, [dbl, C.c_char_p, C.c_char_p]),
+    }
+    for name, (res, args) in sig.items():
+        f = getattr(L, name)
+        f.restype = res
+        f.argtypes = args
+    _lib = L
+    return L
+
+
+EXPORTS = ["ddcb200_lastError", "ddcb200_deviceCount", "ddcb200_create", "ddcb200_destroy", "ddcb200_sync",
+           "ddcb200_martiniNonBondParms", "ddcb200_setSpecies", "ddcb200_setBeads", "ddcb200_setExclusions",
+           "ddcb200_martiniBondParms", "ddcb200_setRestraints", "ddcb200_setMolecules", "ddcb200_sendState",
+           "ddcb200_numLocal", "ddcb200_getLocalBeads", "ddcb200_getState", "ddcb200_constructList", "ddcb200_ddcenergy",
+           "ddcb200_nglf", "ddcb200_energyInfo", "ddcb200_getCells", "ddcb200_getPairs", "ddcb200_profile",
+           "ddcb200_profileRead", "ddcb200_ncclUniqueId", "ddcb200_ddcInit", "ddcb200_deckLoad", "ddcb200_deckFree",
+           "ddcb200_lastHostError", "ddcb200_simulateBind", "ddcb200_printinfoLine", "ddcb200_unitsConvert"]
+
+
+def _arr(ptr, n, dtype):
+    if n == 0:
+        return np.zeros(0, dtype)
+    return np.ctypeslib.as_array(ptr, shape=(n,)).view(dtype)
+
+
+def units_convert(value, frm, to):
+    """units_convert (src/units.c:515-551); None = internal units."""
+    return lib().ddcb200_unitsConvert(value, frm.encode() if frm else None, to.encode() if to else None)
+
+
+class Deck:
+    """Parsed object database of one Martini deck (object.data + restart + parm files + atoms#)."""
+
+    def __init__(self, object_file, restart_file=None, simulate_name=None):
+        L = lib()
+        p = _P(DeckStruct)()
+        rc = L.ddcb200_deckLoad(os.fsencode(object_file), os.fsencode(restart_file) if restart_file else None,
+                                simulate_name.encode() if simulate_name else None, C.byref(p))
+        if rc != 0:
+            raise DdcError(L.ddcb200_lastHostError().decode())
+        self._p = p
+        self.s = p.contents
+
+    def __del__(self):
+        if getattr(self, "_p", None) is not None and _lib is not None:
+            _lib.ddcb200_deckFree(self._p)
+            self._p = None
+
+    # numpy views (valid while the Deck lives)
+    @property
+    def n(self):
+        return int(self.s.n)
+
+    def array(self, name):
+        s = self.s
+        n, ns, nt, nm = int(s.n), int(s.nspecies), int(s.ntypes), int(s.nMolTypes)
+        table = {
+            "gid": (s.gid, n, np.uint64), "species": (s.species, n, np.int32),
+            "rx": (s.rx, n, np.float64), "ry": (s.ry, n, np.float64), "rz": (s.rz, n, np.float64),
+            "vx": (s.vx, n, np.float64), "vy": (s.vy, n, np.float64), "vz": (s.vz, n, np.float64),
+            "specLJ": (s.specLJ, ns, np.int32), "specCharge": (s.specCharge, ns, np.float64),
+            "specMass": (s.specMass, ns, np.float64), "specMolType": (s.specMolType, ns, np.int32),
+            "specResidue": (s.specResidue, ns, np.int32), "specAtom": (s.specAtom, ns, np.int32),
+            "ljEps": (s.ljEps, nt * nt, np.float64), "ljSigma": (s.ljSigma, nt * nt, np.float64),
+            "ljShift": (s.ljShift, nt * nt, np.float64),
+            "molTypeNSpecies": (s.molTypeNSpecies, nm, np.int32), "bpairOffset": (s.bpairOffset, nm + 1, np.int32),
+            "termKind": (s.termKind, int(s.nTerms), np.int32), "termIdx": (s.termIdx, 4 * int(s.nTerms), np.int32),
+            "termParm": (s.termParm, 3 * int(s.nTerms), np.float64),
+            "molOffset": (s.molOffset, int(s.nMol) + 1, np.int64),
+            "restrBead": (s.restrBead, int(s.nRestraints), np.int32),
+        }
+        if name == "bpairI" or name == "bpairJ":
+            nb = int(self.array("bpairOffset")[-1])
+            return _arr(getattr(s, name), nb, np.int32)
+        if name == "molBeads":
+            return _arr(s.molBeads, int(self.array("molOffset")[-1]), np.int32)
+        ptr, cnt, dt = table[name]
+        return _arr(ptr, cnt, dt)
+
+    @property
+    def species_names(self):
+        return [self.s.speciesName[i].decode() for i in range(int(self.s.nspecies))]
+
+
+class Simulate:
+    """simulate_init + the simulateMaster loop pieces, on one GPU.
+
+    ``nglf(nsteps)`` is the reference's ``eval_integrator`` called nsteps times; ``energyInfo()``
+    is ``kinetic_terms`` + ``eval_energyInfo`` (+ molecular pressure).
+    """
+
+    def __init__(self, deck, device=0):
+        L = lib()
+        if L.ddcb200_deviceCount() <= 0:
+            raise DdcError("no CUDA device: ddcmd_b200 has no CPU path")
+        self.deck = deck
+        self.ctx = C.c_void_p()
+        rc = L.ddcb200_simulateBind(deck._p, device, C.byref(self.ctx))
+        if rc != 0:
+            raise DdcError(L.ddcb200_lastHostError().decode())
+        self.dt = deck.s.dt
+
+    def close(self):
+        if getattr(self, "ctx", None) is not None and self.ctx.value and _lib is not None:
+            _lib.ddcb200_destroy(self.ctx)
+            self.ctx = C.c_void_p()
+
+    def __del__(self):
+        self.close()
+
+    def _ck(self, rc):
+        if rc != 0:
+            raise DdcError(lib().ddcb200_lastError().decode())
+
+    def constructList(self):
+        self._ck(lib().ddcb200_constructList(self.ctx))
+
+    def ddcenergy(self, e_eval_flag=1):
+        self._ck(lib().ddcb200_ddcenergy(self.ctx, int(e_eval_flag)))
+
+    def nglf(self, nsteps=1, dt=None):
+        self._ck(lib().ddcb200_nglf(self.ctx, int(nsteps), float(self.dt if dt is None else dt)))
+
+    def sync(self):
+        self._ck(lib().ddcb200_sync(self.ctx))
+
+    def energyInfo(self):
+        e = EType()
+        self._ck(lib().ddcb200_energyInfo(self.ctx, float(self.deck.s.kB), C.byref(e)))
+        return e
+
+    def sendState(self, rx, ry, rz, vx, vy, vz, loop=0, time=0.0):
+        a = [np.ascontiguousarray(x, np.float64) for x in (rx, ry, rz, vx, vy, vz)]
+        pd = _P(C.c_double)
+        self._ck(lib().ddcb200_sendState(self.ctx, a[0].size, None, *[x.ctypes.data_as(pd) for x in a], int(loop), float(time)))
+
+    def getState(self):
+        n = int(lib().ddcb200_numLocal(self.ctx))
+        out = np.empty((9, n), np.float64)
+        pd = _P(C.c_double)
+        self._ck(lib().ddcb200_getState(self.ctx, *[out[k].ctypes.data_as(pd) for k in range(9)]))
+        return dict(zip(("rx", "ry", "rz", "vx", "vy", "vz", "fx", "fy", "fz"), out))
+
+    def getCells(self):
+        n = int(lib().ddcb200_numLocal(self.ctx))
+        cell = np.empty(n, np.int32)
+        dims = (C.c_int * 3)()
+        geom = (C.c_double * 9)()
+        self._ck(lib().ddcb200_getCells(self.ctx, cell.ctypes.data_as(_P(C.c_int)), dims, geom))
+        return cell, np.array(dims[:]), np.array(geom[:])
+
+    def getPairs(self):
+        L = lib()
+        n = int(L.ddcb200_getPairs(self.ctx, 0, None, None, None))
+        if n < 0:
+            self._ck(n)
+        bi, bj, pr = (np.empty(n, np.int32) for _ in range(3))
+        pi = _P(C.c_int)
+        L.ddcb200_getPairs(self.ctx, n, bi.ctypes.data_as(pi), bj.ctypes.data_as(pi), pr.ctypes.data_as(pi))
+        return bi, bj, pr
+
+    def profile(self, enable=True):
+        self._ck(lib().ddcb200_profile(self.ctx, int(enable)))
+
+    def profileRead(self, reset=True):
+        ms = (C.c_double * 8)()
+        ln = (C.c_int64 * 8)()
+        self._ck(lib().ddcb200_profileRead(self.ctx, ms, ln, int(reset)))
+        names = ("integrate", "pair", "bonded", "list", "reduce", "halo")
+        return {k: (ms[i], int(ln[i])) for i, k in enumerate(names)}
+
+    def printinfo(self, e=None):
+        e = e or self.energyInfo()
+        buf = C.create_string_buffer(512)
+        lib().ddcb200_printinfoLine(self.deck._p, C.byref(e), buf, 512)
+        return buf.value.decode()
+
+
+def simulate_init(object_file, restart_file=None, device=0, simulate_name=None):
+    """Mirror of simulate_init(NULL, name, comm) (src/simulate.c:104) for a Martini deck."""
+    return Simulate(Deck(object_file, restart_file, simulate_name), device)

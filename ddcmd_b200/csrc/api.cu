@@ -1,0 +1,899 @@
+// api.cu - C-ABI of the B200-native Martini MD step (include/ddcmd_b200.h): host
+// orchestration of the kernels in cells.cuh / pair.cuh / bonded.cuh / integrate.cuh.
+// There is no CPU path: every compute entry point requires a CUDA device.
+#include "engine.cuh"
+#include "cells.cuh"
+#include "pair.cuh"
+#include "bonded.cuh"
+#include "integrate.cuh"
+#include <math.h>
+#include <string.h>
+#include <algorithm>
+#include <map>
+
+static thread_local std::string g_err;
+static int fail(int code, const std::string &msg)
+{
+    g_err = msg;
+    return code;
+}
+#define CK(call)                                                                                         \
+    do                                                                                                   \
+    {                                                                                                    \
+        cudaError_t e__ = (call);                                                                        \
+        if (e__ != cudaSuccess)                                                                          \
+            return fail(DDCB200_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e__));          \
+    } while (0)
+#define CKL(what)                                                                                        \
+    do                                                                                                   \
+    {                                                                                                    \
+        cudaError_t e__ = cudaGetLastError();                                                            \
+        if (e__ != cudaSuccess)                                                                          \
+            return fail(DDCB200_ERR_CUDA, std::string(what) + ": " + cudaGetErrorString(e__));           \
+    } while (0)
+
+extern "C" const char *ddcb200_lastError(void) { return g_err.c_str(); }
+
+extern "C" int ddcb200_deviceCount(void)
+{
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess)
+    {
+        cudaGetLastError();
+        return 0;
+    }
+    return n;
+}
+
+// ---- profiling helpers ----------------------------------------------------------------
+struct ProfScope
+{
+    ddcb200_ctx *c;
+    int slot;
+    cudaEvent_t a = nullptr, b = nullptr;
+    ProfScope(ddcb200_ctx *ctx, int s) : c(ctx), slot(s)
+    {
+        c->profLaunch[slot]++;
+        if (!c->prof) return;
+        auto get = [&]() {
+            cudaEvent_t e;
+            if (!c->evPool.empty())
+            {
+                e = c->evPool.back();
+                c->evPool.pop_back();
+            }
+            else
+                cudaEventCreate(&e);
+            return e;
+        };
+        a = get();
+        b = get();
+        cudaEventRecord(a, c->stream);
+    }
+    ~ProfScope()
+    {
+        if (!a) return;
+        cudaEventRecord(b, c->stream);
+        c->pending.push_back({a, b, slot});
+    }
+};
+
+// ---- box constants, in the reference's operation order ---------------------------------
+static int setupBox(ddcb200_ctx *c)
+{
+    const ddcb200_params &p = c->prm;
+    const double *h = p.h;
+    const double eps = 1e-10;   // orthorhombicBox(), src/preduce.c:483-494
+    if (fabs(h[1]) > eps || fabs(h[2]) > eps || fabs(h[3]) > eps || fabs(h[5]) > eps || fabs(h[6]) > eps || fabs(h[7]) > eps)
+        return fail(DDCB200_ERR_ARG, "only ORTHORHOMBIC boxes are supported");
+    if (p.pbc != 7) return fail(DDCB200_ERR_ARG, "only pbc=7 is supported");
+    BoxConst &b = c->box;
+    const double xx = h[0], xy = h[1], xz = h[2], yx = h[3], yy = h[4], yz = h[5], zx = h[6], zy = h[7], zz = h[8];
+    // matinv, src/three_algebra.c:37-64
+    const double d00 = yy * zz - yz * zy, d11 = zz * xx - zx * xz, d22 = xx * yy - xy * yx;
+    const double d01 = yz * zx - yx * zz, d12 = zx * xy - zy * xx, d20 = xy * yz - xz * yy;
+    const double d02 = yx * zy - zx * yy, d10 = zy * xz - xy * zz, d21 = xz * yx - yz * xx;
+    const double det = xx * d00 + xy * d01 + xz * d02;
+    b.hinv[0] = d00 / det; b.hinv[4] = d11 / det; b.hinv[8] = d22 / det;
+    b.hinv[1] = d10 / det; b.hinv[3] = d01 / det; b.hinv[2] = d20 / det;
+    b.hinv[6] = d02 / det; b.hinv[5] = d21 / det; b.hinv[7] = d12 / det;
+    b.volume = det;
+    b.hxx = xx; b.hyy = yy; b.hzz = zz;
+    b.hhx = 0.5 * xx; b.hhy = 0.5 * yy; b.hhz = 0.5 * zz;
+    b.cx = p.center[0]; b.cy = p.center[1]; b.cz = p.center[2];
+    // box_get_minspan, src/box.c:213-227
+    static const double lv[13][3] = {{0, 0, 1}, {0, 1, 0}, {1, 0, 0}, {0, 1, 1}, {1, 0, 1}, {1, 1, 0}, {1, 1, 1},
+                                     {0, 1, -1}, {1, 0, -1}, {1, -1, 0}, {1, 1, -1}, {1, -1, 1}, {-1, 1, 0}};
+    double r2min = 0;
+    for (int i = 0; i < 13; i++)
+    {
+        const double rx = xx * lv[i][0] + xy * lv[i][1] + xz * lv[i][2];
+        const double ry = yx * lv[i][0] + yy * lv[i][1] + yz * lv[i][2];
+        const double rz = zx * lv[i][0] + zy * lv[i][1] + zz * lv[i][2];
+        const double r2 = rx * rx + ry * ry + rz * rz;
+        if (i == 0 || r2 < r2min) r2min = r2;
+    }
+    const double minspan = sqrt(r2min);
+    b.R2cut = 0.25 * minspan * minspan;
+    const double rl = p.rmax + p.deltaR;
+    b.rlist2 = rl * rl;                     // src/pairlist.c:226
+    b.rc2 = p.rmax * p.rmax;                // SQ(parms->rmax), src/bioMartini.c:1002
+    b.rcutGeom = rl > p.minBoxSide ? rl : p.minBoxSide;
+    // computeBoxSpan, src/geom.c:478-511
+    {
+        const double a0[3] = {xx, yx, zx}, a1[3] = {xy, yy, zy}, a2[3] = {xz, yz, zz};
+        auto dot = [](const double *u, const double *v) { return u[0] * v[0] + u[1] * v[1] + u[2] * v[2]; };
+        auto cross = [](const double *u, const double *v, double *w) {
+            w[0] = u[1] * v[2] - u[2] * v[1];
+            w[1] = u[2] * v[0] - u[0] * v[2];
+            w[2] = u[0] * v[1] - u[1] * v[0];
+        };
+        const double l0 = sqrt(dot(a0, a0)), l1 = sqrt(dot(a1, a1)), l2 = sqrt(dot(a2, a2));
+        double n0[3], n1[3], n2[3];
+        cross(a1, a2, n0);
+        cross(a2, a0, n1);
+        cross(a0, a1, n2);
+        const double s0 = 1.0 / (l1 * l2), s1 = 1.0 / (l2 * l0), s2 = 1.0 / (l0 * l1);
+        for (int k = 0; k < 3; k++)
+        {
+            n0[k] *= s0;
+            n1[k] *= s1;
+            n2[k] *= s2;
+        }
+        const double bd[3] = {a0[0] + a1[0] + a2[0], a0[1] + a1[1] + a2[1], a0[2] + a1[2] + a2[2]};
+        b.spanx = fabs(dot(n0, bd));
+        b.spany = fabs(dot(n1, bd));
+        b.spanz = fabs(dot(n2, bd));
+    }
+    // ordering bins (not part of parity): edges relative to cutoff and skin
+    {
+        const double f[NBINS - 1] = {-0.25, -0.125, 0.0, 0.125, 0.25, 0.375, 0.625};
+        for (int k = 0; k < NBINS - 1; k++)
+        {
+            const double r = p.rmax + f[k] * p.deltaR;
+            b.binEdge2[k] = r * r;
+        }
+    }
+    PairConst &pc = c->pc;
+    pc.rc2 = b.rc2; pc.R2cut = b.R2cut;
+    pc.hxx = b.hxx; pc.hyy = b.hyy; pc.hzz = b.hzz;
+    pc.hhx = b.hhx; pc.hhy = b.hhy; pc.hhz = b.hhz;
+    pc.keR = p.keR; pc.krf = p.krf; pc.crf = p.crf;
+    pc.ntypes = c->ntypes;
+    return DDCB200_OK;
+}
+
+extern "C" int ddcb200_create(const ddcb200_params *p, ddcb200_ctx **out)
+{
+    if (!p || !out) return fail(DDCB200_ERR_ARG, "null argument");
+    int ndev = ddcb200_deviceCount();
+    if (ndev <= 0) return fail(DDCB200_ERR_NODEVICE, "no CUDA device: ddcmd_b200 has no CPU path");
+    if (p->device < 0 || p->device >= ndev) return fail(DDCB200_ERR_ARG, "bad device ordinal");
+    CK(cudaSetDevice(p->device));
+    cudaDeviceProp prop;
+    CK(cudaGetDeviceProperties(&prop, p->device));
+    if (prop.major < 10) return fail(DDCB200_ERR_NODEVICE, std::string("device ") + prop.name + " is not sm_100 class");
+    ddcb200_ctx *c = new ddcb200_ctx();
+    c->prm = *p;
+    c->device = p->device;
+    c->numSM = prop.multiProcessorCount;
+    int rc = setupBox(c);
+    if (rc != DDCB200_OK)
+    {
+        delete c;
+        return rc;
+    }
+    CK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    CK(cudaMalloc((void **)&c->grid, sizeof(GridDev)));
+    CK(cudaMemset(c->grid, 0, sizeof(GridDev)));
+    CK(cudaMallocHost((void **)&c->gridHost, sizeof(GridDev)));
+    CK(cudaMalloc((void **)&c->acc, ACC_N * sizeof(double)));
+    CK(cudaMemset(c->acc, 0, ACC_N * sizeof(double)));
+    CK(cudaMallocHost((void **)&c->accHost, ACC_N * sizeof(double)));
+    *out = c;
+    return DDCB200_OK;
+}
+
+extern "C" void ddcb200_destroy(ddcb200_ctx *c)
+{
+    if (!c) return;
+    cudaSetDevice(c->device);
+    cudaStreamSynchronize(c->stream);
+    c->ljTab.release(); c->shiftTab.release(); c->qTab.release(); c->massOfBead.release(); c->wOfBead.release();
+    c->gidOfBead.release(); c->molTypeOfBead.release(); c->molTypeSingle.release(); c->bpairOffset.release();
+    c->bpairKey.release(); c->termsBead.release(); c->termsSlot.release(); c->restrBead.release(); c->restrSlot.release();
+    c->restrParm.release(); c->molOffset.release(); c->molBeads.release();
+    for (int k = 0; k < 2; k++)
+    {
+        c->pos4[k].release();
+        c->beadOfSlot[k].release();
+        for (int a = 0; a < 3; a++) c->vel[k][a].release();
+    }
+    for (int a = 0; a < 3; a++) c->frc[a].release();
+    c->slotOfBead.release(); c->cellOfSlot[0].release(); c->cellOfSlot[1].release(); c->rank0.release(); c->cellCount.release();
+    c->cellStart.release(); c->member.release(); c->perm.release(); c->mmPartial.release(); c->nbrRaw.release();
+    c->nbr.release(); c->nbrCount.release(); c->pairPartial.release(); c->bondPartial.release(); c->kinPartial.release();
+    c->colMap.release(); c->stage.release(); c->stageI.release();
+    for (auto &pe : c->pending)
+    {
+        cudaEventDestroy(pe.a);
+        cudaEventDestroy(pe.b);
+    }
+    for (auto e : c->evPool) cudaEventDestroy(e);
+    if (c->grid) cudaFree(c->grid);
+    if (c->gridHost) cudaFreeHost(c->gridHost);
+    if (c->acc) cudaFree(c->acc);
+    if (c->accHost) cudaFreeHost(c->accHost);
+    if (c->stream) cudaStreamDestroy(c->stream);
+    delete c;
+}
+
+extern "C" int ddcb200_sync(ddcb200_ctx *c)
+{
+    if (!c) return fail(DDCB200_ERR_ARG, "null ctx");
+    CK(cudaSetDevice(c->device));
+    CK(cudaStreamSynchronize(c->stream));
+    return DDCB200_OK;
+}
+
+extern "C" int ddcb200_martiniNonBondParms(ddcb200_ctx *c, int ntypes, const double *eps, const double *sigma, const double *shift)
+{
+    if (!c || ntypes <= 0 || ntypes > 255 || !eps || !sigma || !shift) return fail(DDCB200_ERR_ARG, "bad LJ table");
+    CK(cudaSetDevice(c->device));
+    std::vector<double2> t((size_t)ntypes * ntypes);
+    for (int k = 0; k < ntypes * ntypes; k++)
+    {
+        const double s2 = sigma[k] * sigma[k], s6 = s2 * s2 * s2;
+        t[k].x = 4.0 * eps[k] * s6;
+        t[k].y = 4.0 * eps[k] * s6 * s6;
+    }
+    CK(c->ljTab.ensure(t.size()));
+    CK(c->shiftTab.ensure(t.size()));
+    CK(cudaMemcpy(c->ljTab.p, t.data(), t.size() * sizeof(double2), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(c->shiftTab.p, shift, t.size() * sizeof(double), cudaMemcpyHostToDevice));
+    c->ntypes = ntypes;
+    c->pc.ntypes = ntypes;
+    return DDCB200_OK;
+}
+
+extern "C" int ddcb200_setSpecies(ddcb200_ctx *c, int nspecies, const int *ljType, const double *charge, const double *mass)
+{
+    if (!c || nspecies <= 0 || !ljType || !charge || !mass) return fail(DDCB200_ERR_ARG, "bad species table");
+    c->nspecies = nspecies;
+    c->hSpecLJ.assign(ljType, ljType + nspecies);
+    c->hSpecQ.assign(charge, charge + nspecies);
+    c->hSpecMass.assign(mass, mass + nspecies);
+    c->hQtab.clear();
+    c->hSpecQi.resize(nspecies);
+    for (int s = 0; s < nspecies; s++)
+    {
+        if (ljType[s] < 0 || ljType[s] > 254) return fail(DDCB200_ERR_ARG, "LJ type out of range");
+        size_t k = 0;
+        for (; k < c->hQtab.size(); k++)
+            if (c->hQtab[k] == charge[s]) break;
+        if (k == c->hQtab.size()) c->hQtab.push_back(charge[s]);
+        if (k > 255) return fail(DDCB200_ERR_CAPACITY, "more than 256 distinct charges");
+        c->hSpecQi[s] = (int)k;
+    }
+    CK(cudaSetDevice(c->device));
+    std::vector<double> q(256, 0.0);
+    std::copy(c->hQtab.begin(), c->hQtab.end(), q.begin());
+    CK(c->qTab.ensure(256));
+    CK(cudaMemcpy(c->qTab.p, q.data(), 256 * sizeof(double), cudaMemcpyHostToDevice));
+    return DDCB200_OK;
+}
+
+static int uploadBeadTables(ddcb200_ctx *c)
+{
+    const int64_t n = c->nGlobal;
+    std::vector<uint64_t> w((size_t)n);
+    std::vector<double> m((size_t)n);
+    std::vector<int> mt((size_t)n, -1);
+    for (int64_t i = 0; i < n; i++)
+    {
+        const int s = c->hSpecies[(size_t)i];
+        if (s < 0 || s >= c->nspecies) return fail(DDCB200_ERR_ARG, "species index out of range");
+        w[(size_t)i] = packW(c->hSpecLJ[s], c->hSpecQi[s], (uint32_t)i);
+        m[(size_t)i] = c->hSpecMass[s];
+        if (!c->hMolTypeOfSpecies.empty()) mt[(size_t)i] = c->hMolTypeOfSpecies[s];
+    }
+    CK(c->wOfBead.ensure((size_t)n));
+    CK(c->massOfBead.ensure((size_t)n));
+    CK(c->gidOfBead.ensure((size_t)n));
+    CK(c->molTypeOfBead.ensure((size_t)n));
+    CK(c->slotOfBead.ensure((size_t)n));
+    CK(cudaMemcpy(c->wOfBead.p, w.data(), n * sizeof(uint64_t), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(c->massOfBead.p, m.data(), n * sizeof(double), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(c->gidOfBead.p, c->hGid.data(), n * sizeof(uint64_t), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(c->molTypeOfBead.p, mt.data(), n * sizeof(int), cudaMemcpyHostToDevice));
+    CK(cudaMemset(c->slotOfBead.p, 0xff, n * sizeof(int)));
+    return DDCB200_OK;
+}
+
+extern "C" int ddcb200_setBeads(ddcb200_ctx *c, int64_t nGlobal, const uint64_t *gid, const int *species)
+{
+    if (!c || nGlobal <= 0 || nGlobal >= (1ll << 27) || !gid || !species) return fail(DDCB200_ERR_ARG, "bad bead table");
+    if (c->nspecies == 0) return fail(DDCB200_ERR_STATE, "setSpecies must precede setBeads");
+    CK(cudaSetDevice(c->device));
+    c->nGlobal = nGlobal;
+    c->hGid.assign(gid, gid + nGlobal);
+    c->hSpecies.assign(species, species + nGlobal);
+    return uploadBeadTables(c);
+}
+
+extern "C" int ddcb200_setExclusions(ddcb200_ctx *c, int nMolTypes, const int *molTypeOfSpecies, const int *molTypeNSpecies,
+                                     const int *bpairOffset, const int *bpairI, const int *bpairJ)
+{
+    if (!c || nMolTypes <= 0 || !molTypeOfSpecies || !molTypeNSpecies || !bpairOffset) return fail(DDCB200_ERR_ARG, "bad exclusion tables");
+    if (c->nspecies == 0) return fail(DDCB200_ERR_STATE, "setSpecies must precede setExclusions");
+    CK(cudaSetDevice(c->device));
+    c->nMolTypes = nMolTypes;
+    c->hMolTypeOfSpecies.assign(molTypeOfSpecies, molTypeOfSpecies + c->nspecies);
+    c->hMolTypeNSpecies.assign(molTypeNSpecies, molTypeNSpecies + nMolTypes);
+    std::vector<int> single(nMolTypes), off(nMolTypes + 1, 0);
+    std::vector<uint32_t> keys;
+    for (int m = 0; m < nMolTypes; m++)
+    {
+        single[m] = molTypeNSpecies[m] <= 1 ? 1 : 0;
+        std::vector<uint32_t> k;
+        for (int e = bpairOffset[m]; e < bpairOffset[m + 1]; e++)
+        {
+            const uint32_t a = (uint32_t)bpairI[e] & 0xffffu, b = (uint32_t)bpairJ[e] & 0xffffu;
+            k.push_back((std::min(a, b) << 16) | std::max(a, b));
+        }
+        std::sort(k.begin(), k.end());
+        k.erase(std::unique(k.begin(), k.end()), k.end());
+        off[m] = (int)keys.size();
+        keys.insert(keys.end(), k.begin(), k.end());
+    }
+    off[nMolTypes] = (int)keys.size();
+    CK(c->molTypeSingle.ensure(nMolTypes));
+    CK(c->bpairOffset.ensure(nMolTypes + 1));
+    CK(c->bpairKey.ensure(keys.size() + 1));
+    CK(cudaMemcpy(c->molTypeSingle.p, single.data(), nMolTypes * sizeof(int), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(c->bpairOffset.p, off.data(), (nMolTypes + 1) * sizeof(int), cudaMemcpyHostToDevice));
+    if (!keys.empty()) CK(cudaMemcpy(c->bpairKey.p, keys.data(), keys.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
+    c->haveExcl = true;
+    if (c->nGlobal > 0) return uploadBeadTables(c);
+    return DDCB200_OK;
+}
+
+extern "C" int ddcb200_martiniBondParms(ddcb200_ctx *c, int64_t nTerms, const int *kind, const int *idx, const double *parm)
+{
+    if (!c || nTerms < 0 || (nTerms > 0 && (!kind || !idx || !parm))) return fail(DDCB200_ERR_ARG, "bad bonded terms");
+    CK(cudaSetDevice(c->device));
+    std::vector<Term> t((size_t)nTerms);
+    for (int64_t k = 0; k < nTerms; k++)
+    {
+        Term &tm = t[(size_t)k];
+        tm.i = idx[4 * k]; tm.j = idx[4 * k + 1]; tm.k = idx[4 * k + 2]; tm.l = idx[4 * k + 3];
+        tm.p0 = parm[3 * k]; tm.p1 = parm[3 * k + 1]; tm.p2 = parm[3 * k + 2];
+        tm.kind = kind[k]; tm.pad = 0;
+        if (tm.kind < 0 || tm.kind > 5) return fail(DDCB200_ERR_ARG, "unknown bonded term kind");
+        const int need = tm.kind == 0 ? 2 : (tm.kind <= 3 ? 3 : 4);
+        const int ids[4] = {tm.i, tm.j, tm.k, tm.l};
+        for (int a = 0; a < need; a++)
+            if (ids[a] < 0 || (c->nGlobal > 0 && ids[a] >= c->nGlobal)) return fail(DDCB200_ERR_ARG, "bonded term bead index out of range");
+        if (need < 3) tm.k = -1;
+        if (need < 4) tm.l = -1;
+    }
+    // one formula per warp: sort by kind (stable, keeps the caller's order inside a kind)
+    std::stable_sort(t.begin(), t.end(), [](const Term &a, const Term &b) { return a.kind < b.kind; });
+    c->nTerms = nTerms;
+    CK(c->termsBead.ensure((size_t)nTerms + 1));
+    CK(c->termsSlot.ensure((size_t)nTerms + 1));
+    if (nTerms) CK(cudaMemcpy(c->termsBead.p, t.data(), nTerms * sizeof(Term), cudaMemcpyHostToDevice));
+    c->listValid = false;
+    return DDCB200_OK;
+}
+
+extern "C" int ddcb200_setRestraints(ddcb200_ctx *c, int64_t n, const int *bead, const double *frac0, const double *kb,
+                                     const double *fc, int origin)
+{
+    if (!c || n < 0 || (n > 0 && (!bead || !frac0 || !kb || !fc))) return fail(DDCB200_ERR_ARG, "bad restraints");
+    CK(cudaSetDevice(c->device));
+    std::vector<double> p((size_t)n * 7);
+    for (int64_t k = 0; k < n; k++)
+    {
+        for (int a = 0; a < 3; a++)
+        {
+            p[7 * k + a] = frac0[3 * k + a];
+            p[7 * k + 4 + a] = fc[3 * k + a];
+        }
+        p[7 * k + 3] = kb[k];
+    }
+    c->nRestr = n;
+    c->restrOrigin = origin;
+    CK(c->restrBead.ensure((size_t)n + 1));
+    CK(c->restrSlot.ensure((size_t)n + 1));
+    CK(c->restrParm.ensure((size_t)n * 7 + 1));
+    if (n)
+    {
+        CK(cudaMemcpy(c->restrBead.p, bead, n * sizeof(int), cudaMemcpyHostToDevice));
+        CK(cudaMemcpy(c->restrParm.p, p.data(), n * 7 * sizeof(double), cudaMemcpyHostToDevice));
+    }
+    c->listValid = false;
+    return DDCB200_OK;
+}
+
+extern "C" int ddcb200_setMolecules(ddcb200_ctx *c, int64_t nMol, const int64_t *molOffset, const int *molBeads, int64_t nMolTotal)
+{
+    if (!c || nMol < 0 || (nMol > 0 && (!molOffset || !molBeads))) return fail(DDCB200_ERR_ARG, "bad molecule table");
+    CK(cudaSetDevice(c->device));
+    c->nMol = nMol;
+    c->nMolTotal = nMolTotal;
+    if (nMol)
+    {
+        CK(c->molOffset.ensure((size_t)nMol + 1));
+        CK(c->molBeads.ensure((size_t)molOffset[nMol] + 1));
+        CK(cudaMemcpy(c->molOffset.p, molOffset, (nMol + 1) * sizeof(int64_t), cudaMemcpyHostToDevice));
+        CK(cudaMemcpy(c->molBeads.p, molBeads, molOffset[nMol] * sizeof(int), cudaMemcpyHostToDevice));
+    }
+    return DDCB200_OK;
+}
+
+static int ensureState(ddcb200_ctx *c, int64_t nIon)
+{
+    const int64_t nPad = ((nIon + TILE - 1) / TILE) * TILE;
+    for (int k = 0; k < 2; k++)
+    {
+        CK(c->pos4[k].ensure((size_t)nPad));
+        CK(c->beadOfSlot[k].ensure((size_t)nPad));
+        CK(c->cellOfSlot[k].ensure((size_t)nPad));
+        for (int a = 0; a < 3; a++) CK(c->vel[k][a].ensure((size_t)nPad));
+    }
+    for (int a = 0; a < 3; a++) CK(c->frc[a].ensure((size_t)nPad));
+    CK(c->rank0.ensure((size_t)nPad));
+    CK(c->member.ensure((size_t)nPad));
+    CK(c->perm.ensure((size_t)nPad));
+    CK(c->cellCount.ensure((size_t)nIon + 8));
+    CK(c->cellStart.ensure((size_t)nIon + 8));
+    CK(c->nbrCount.ensure((size_t)nPad));
+    CK(c->mmPartial.ensure(6 * 1024));
+    const size_t tiles = (size_t)(nPad / TILE);
+    CK(c->pairPartial.ensure(tiles * 8 + 8));
+    CK(c->kinPartial.ensure(tiles * 7 + 8));
+    c->nPad = nPad;
+    return DDCB200_OK;
+}
+
+extern "C" int ddcb200_sendState(ddcb200_ctx *c, int64_t nLocal, const int *bead, const double *rx, const double *ry, const double *rz,
+                                 const double *vx, const double *vy, const double *vz, int64_t loop, double time)
+{
+    if (!c || nLocal <= 0 || !rx || !ry || !rz || !vx || !vy || !vz) return fail(DDCB200_ERR_ARG, "bad state");
+    if (c->nGlobal == 0) return fail(DDCB200_ERR_STATE, "setBeads must precede sendState");
+    if (nLocal > c->nGlobal) return fail(DDCB200_ERR_ARG, "nLocal exceeds the bead table");
+    CK(cudaSetDevice(c->device));
+    int rc = ensureState(c, nLocal);
+    if (rc) return rc;
+    c->nLocal = nLocal;
+    c->nIon = nLocal;
+    c->hLocalBeads.resize((size_t)nLocal);
+    for (int64_t i = 0; i < nLocal; i++) c->hLocalBeads[(size_t)i] = bead ? bead[i] : (int)i;
+    CK(c->stage.ensure((size_t)nLocal * 9));
+    CK(c->stageI.ensure((size_t)nLocal));
+    const double *src[6] = {rx, ry, rz, vx, vy, vz};
+    for (int a = 0; a < 6; a++)
+        CK(cudaMemcpyAsync(c->stage.p + (size_t)a * nLocal, src[a], nLocal * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    CK(cudaMemcpyAsync(c->stageI.p, c->hLocalBeads.data(), nLocal * sizeof(int), cudaMemcpyHostToDevice, c->stream));
+    CK(cudaMemsetAsync(c->slotOfBead.p, 0xff, c->nGlobal * sizeof(int), c->stream));
+    const int cur = c->cur;
+    const int blocks = (int)((nLocal + 255) / 256);
+    const double *s = c->stage.p;
+    k_upload_state<<<blocks, 256, 0, c->stream>>>((int)nLocal, c->stageI.p, s, s + nLocal, s + 2 * nLocal, s + 3 * nLocal, s + 4 * nLocal,
+                                                  s + 5 * nLocal, c->wOfBead.p, c->pos4[cur].p, c->vel[cur][0].p, c->vel[cur][1].p,
+                                                  c->vel[cur][2].p, c->beadOfSlot[cur].p, c->slotOfBead.p);
+    CKL("k_upload_state");
+    c->loop = loop;
+    c->time = time;
+    c->listValid = false;
+    c->forcesValid = false;
+    c->energyValid = false;
+    return DDCB200_OK;
+}
+
+extern "C" int64_t ddcb200_numLocal(ddcb200_ctx *c) { return c ? c->nLocal : 0; }
+
+extern "C" int ddcb200_getLocalBeads(ddcb200_ctx *c, int *bead)
+{
+    if (!c || !bead) return fail(DDCB200_ERR_ARG, "null argument");
+    std::copy(c->hLocalBeads.begin(), c->hLocalBeads.end(), bead);
+    return DDCB200_OK;
+}
+
+extern "C" int ddcb200_getState(ddcb200_ctx *c, double *rx, double *ry, double *rz, double *vx, double *vy, double *vz,
+                                double *fx, double *fy, double *fz)
+{
+    if (!c) return fail(DDCB200_ERR_ARG, "null ctx");
+    if (c->nLocal == 0) return fail(DDCB200_ERR_STATE, "no state");
+    CK(cudaSetDevice(c->device));
+    const int64_t n = c->nLocal;
+    const int cur = c->cur;
+    CK(c->stage.ensure((size_t)n * 9));
+    const int blocks = (int)((n + 255) / 256);
+    k_download_state<<<blocks, 256, 0, c->stream>>>((int)n, c->stageI.p, c->slotOfBead.p, c->pos4[cur].p, c->vel[cur][0].p,
+                                                    c->vel[cur][1].p, c->vel[cur][2].p, c->frc[0].p, c->frc[1].p, c->frc[2].p, c->stage.p);
+    CKL("k_download_state");
+    double *dst[9] = {rx, ry, rz, vx, vy, vz, fx, fy, fz};
+    for (int a = 0; a < 9; a++)
+        if (dst[a]) CK(cudaMemcpyAsync(dst[a], c->stage.p + (size_t)a * n, n * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    return DDCB200_OK;
+}
+
+// ---- list build -------------------------------------------------------------------------
+extern "C" int ddcb200_constructList(ddcb200_ctx *c)
+{
+    if (!c) return fail(DDCB200_ERR_ARG, "null ctx");
+    if (c->nLocal == 0) return fail(DDCB200_ERR_STATE, "no state");
+    if (c->ntypes == 0) return fail(DDCB200_ERR_STATE, "martiniNonBondParms not called");
+    CK(cudaSetDevice(c->device));
+    ProfScope ps(c, PROF_LIST);
+    const int nIon = (int)c->nIon, nLocal = (int)c->nLocal, nPad = (int)c->nPad;
+    const int cur = c->cur, nxt = cur ^ 1;
+    cudaStream_t st = c->stream;
+    const int maxCells = nIon + 4;
+    const int mmBlocks = std::min(1024, (nIon + 255) / 256);
+    k_minmax_partial<<<mmBlocks, 256, 0, st>>>(c->pos4[cur].p, nIon, c->box, c->mmPartial.p);
+    k_grid_setup<<<1, 32, 0, st>>>(c->mmPartial.p, mmBlocks, nIon, c->box, c->grid, maxCells);
+    CK(cudaMemsetAsync(c->cellCount.p, 0, (size_t)(nIon + 8) * sizeof(int), st));
+    const int nb = (nIon + 255) / 256;
+    k_cell_count<<<nb, 256, 0, st>>>(c->pos4[cur].p, nIon, c->box, c->grid, c->cellOfSlot[cur].p, c->rank0.p, c->cellCount.p);
+    k_cell_scan<<<1, 1024, 0, st>>>(c->cellCount.p, c->cellStart.p, c->grid);
+    k_cell_scatter<<<nb, 256, 0, st>>>(nIon, c->cellOfSlot[cur].p, c->rank0.p, c->cellStart.p, c->member.p);
+    k_cell_rank<<<nb, 256, 0, st>>>(nIon, c->cellOfSlot[cur].p, c->beadOfSlot[cur].p, c->cellStart.p, c->member.p, c->perm.p);
+    k_gather<<<nb, 256, 0, st>>>(nIon, c->perm.p, c->cellOfSlot[cur].p, c->cellOfSlot[nxt].p, c->pos4[cur].p, c->pos4[nxt].p,
+                                 c->vel[cur][0].p, c->vel[cur][1].p, c->vel[cur][2].p, c->vel[nxt][0].p, c->vel[nxt][1].p,
+                                 c->vel[nxt][2].p, c->beadOfSlot[cur].p, c->beadOfSlot[nxt].p, c->slotOfBead.p, nLocal);
+    CKL("cell sort");
+    c->cur = nxt;
+
+    if (c->nbrCap == 0) c->nbrCap = 176;
+    for (int attempt = 0; attempt < 4; attempt++)
+    {
+        CK(c->nbrRaw.ensure((size_t)c->nbrCap * nPad));
+        CK(c->nbr.ensure((size_t)c->nbrCap * nPad));
+        k_nbr_raw<<<nPad / 128, 128, 0, st>>>(nLocal, nIon, nPad, c->pos4[nxt].p, c->cellOfSlot[nxt].p, c->cellStart.p, c->box, c->grid,
+                                             c->nbrCap, c->nbrRaw.p, c->nbrCount.p, c->beadOfSlot[nxt].p, c->gidOfBead.p,
+                                             c->molTypeOfBead.p, c->molTypeSingle.p, c->bpairOffset.p, c->bpairKey.p, c->haveExcl ? 1 : 0);
+        CKL("k_nbr_raw");
+        CK(cudaMemcpyAsync(c->gridHost, c->grid, sizeof(GridDev), cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+        if (c->gridHost->error & 2) return fail(DDCB200_ERR_CAPACITY, "cell grid larger than the bead count bound");
+        if (!(c->gridHost->error & 1)) break;
+        // a row overflowed: grow and redo the raw pass
+        c->nbrCap = (int)(c->gridHost->maxCount * 1.25) + 8;
+        CK(cudaMemsetAsync(&c->grid->error, 0, sizeof(int), st));
+        CK(cudaMemsetAsync(&c->grid->maxCount, 0, sizeof(int), st));
+        CK(cudaMemsetAsync(&c->grid->totalEntries, 0, sizeof(unsigned long long), st));
+        if (attempt == 3) return fail(DDCB200_ERR_CAPACITY, "neighbor list capacity could not be satisfied");
+    }
+    k_nbr_order<<<nPad / 128, 128, 0, st>>>(nLocal, nPad, c->nbrCap, c->nbrRaw.p, c->nbrCount.p, c->nbr.p);
+    CKL("k_nbr_order");
+    if (c->nTerms)
+    {
+        k_terms_remap<<<(int)((c->nTerms + 255) / 256), 256, 0, st>>>(c->nTerms, c->termsBead.p, c->termsSlot.p, c->slotOfBead.p);
+        CKL("k_terms_remap");
+    }
+    if (c->nRestr)
+    {
+        k_restr_remap<<<(int)((c->nRestr + 255) / 256), 256, 0, st>>>(c->nRestr, c->restrBead.p, c->restrSlot.p, c->slotOfBead.p);
+        CKL("k_restr_remap");
+    }
+    c->listValid = true;
+    c->lastBuildLoop = c->loop;
+    c->nPairsListed = (int64_t)(c->gridHost->totalEntries / 2);
+    return DDCB200_OK;
+}
+
+// ---- force evaluation -------------------------------------------------------------------
+static int reduceCols(ddcb200_ctx *c, const double *partial, int nblocks, int ncol, const int *map)
+{
+    // column map lives in a small device table: [0..7] pair, [8..18] bonded, [19..25] kinetic
+    k_reduce_cols<<<ncol, 256, 0, c->stream>>>(partial, nblocks, ncol, map, c->acc, 1);
+    CKL("k_reduce_cols");
+    return DDCB200_OK;
+}
+
+static int ensureColMap(ddcb200_ctx *c)
+{
+    if (c->colMap.p) return DDCB200_OK;
+    const int m[26] = {ACC_ELJ, ACC_EELE, ACC_VXX, ACC_VYY, ACC_VZZ, ACC_VXY, ACC_VXZ, ACC_VYZ,
+                       ACC_VXX, ACC_VYY, ACC_VZZ, ACC_VXY, ACC_VXZ, ACC_VYZ, ACC_EBOND, ACC_EANGLE, ACC_ETORS, ACC_EIMPR, ACC_EREST,
+                       ACC_RK, ACC_TXX, ACC_TYY, ACC_TZZ, ACC_TXY, ACC_TXZ, ACC_TYZ};
+    CK(c->colMap.ensure(32));
+    CK(cudaMemcpy(c->colMap.p, m, sizeof(m), cudaMemcpyHostToDevice));
+    return DDCB200_OK;
+}
+
+extern "C" int ddcb200_ddcenergy(ddcb200_ctx *c, int withEnergy)
+{
+    if (!c) return fail(DDCB200_ERR_ARG, "null ctx");
+    if (c->nLocal == 0) return fail(DDCB200_ERR_STATE, "no state");
+    if (c->ntypes == 0) return fail(DDCB200_ERR_STATE, "martiniNonBondParms not called");
+    CK(cudaSetDevice(c->device));
+    int rc = ensureColMap(c);
+    if (rc) return rc;
+    // evalUpdateFlag, src/ddcUpdateAll.c:64-71
+    const bool due = c->prm.updateRate > 0 && (c->loop % c->prm.updateRate) == 0 && c->lastBuildLoop != c->loop;
+    if (!c->listValid || due)
+    {
+        rc = ddcb200_constructList(c);
+        if (rc) return rc;
+    }
+    cudaStream_t st = c->stream;
+    const int cur = c->cur;
+    const int nLocal = (int)c->nLocal, nPad = (int)c->nPad;
+    const int tiles = nPad / TILE;
+    if (withEnergy) CK(cudaMemsetAsync(c->acc, 0, ACC_N * sizeof(double), st));
+    {
+        ProfScope ps(c, PROF_PAIR);
+        const size_t smem = (size_t)c->ntypes * c->ntypes * (sizeof(double2) + sizeof(double)) + 256 * sizeof(double);
+        if (withEnergy)
+            k_pair<true><<<tiles, TILE, smem, st>>>(nLocal, nPad, c->pos4[cur].p, c->nbr.p, c->nbrCount.p, c->ljTab.p, c->shiftTab.p,
+                                                    c->qTab.p, c->pc, c->frc[0].p, c->frc[1].p, c->frc[2].p, c->pairPartial.p);
+        else
+            k_pair<false><<<tiles, TILE, smem, st>>>(nLocal, nPad, c->pos4[cur].p, c->nbr.p, c->nbrCount.p, c->ljTab.p, c->shiftTab.p,
+                                                     c->qTab.p, c->pc, c->frc[0].p, c->frc[1].p, c->frc[2].p, c->pairPartial.p);
+        CKL("k_pair");
+    }
+    const int64_t nb = c->nTerms + c->nRestr;
+    int bBlocks = 0;
+    if (nb > 0)
+    {
+        ProfScope ps(c, PROF_BONDED);
+        bBlocks = (int)((nb + BONDED_THREADS - 1) / BONDED_THREADS);
+        CK(c->bondPartial.ensure((size_t)bBlocks * BONDED_ACC + 8));
+        if (withEnergy)
+            k_bonded<true><<<bBlocks, BONDED_THREADS, 0, st>>>(c->nTerms, c->termsSlot.p, c->nRestr, c->restrSlot.p, c->restrParm.p,
+                                                               c->restrOrigin, c->pos4[cur].p, c->pc, c->frc[0].p, c->frc[1].p,
+                                                               c->frc[2].p, c->bondPartial.p);
+        else
+            k_bonded<false><<<bBlocks, BONDED_THREADS, 0, st>>>(c->nTerms, c->termsSlot.p, c->nRestr, c->restrSlot.p, c->restrParm.p,
+                                                                c->restrOrigin, c->pos4[cur].p, c->pc, c->frc[0].p, c->frc[1].p,
+                                                                c->frc[2].p, c->bondPartial.p);
+        CKL("k_bonded");
+    }
+    if (withEnergy)
+    {
+        ProfScope ps(c, PROF_REDUCE);
+        rc = reduceCols(c, c->pairPartial.p, tiles, 8, c->colMap.p);
+        if (rc) return rc;
+        if (bBlocks)
+        {
+            rc = reduceCols(c, c->bondPartial.p, bBlocks, BONDED_ACC, c->colMap.p + 8);
+            if (rc) return rc;
+        }
+    }
+    c->forcesValid = true;
+    c->energyValid = withEnergy != 0;
+    c->kineticValid = false;
+    return DDCB200_OK;
+}
+
+template <int MODE>
+static int launchIntegrate(ddcb200_ctx *c, double halfDt2, double halfDt1, double dt)
+{
+    ProfScope ps(c, PROF_INTEGRATE);
+    const int cur = c->cur;
+    const int tiles = (int)(c->nPad / TILE);
+    k_integrate<MODE><<<tiles, TILE, 0, c->stream>>>((int)c->nLocal, c->pos4[cur].p, c->vel[cur][0].p, c->vel[cur][1].p, c->vel[cur][2].p,
+                                                     c->frc[0].p, c->frc[1].p, c->frc[2].p, c->massOfBead.p, halfDt2, halfDt1, dt, c->pc,
+                                                     c->kinPartial.p);
+    CKL("k_integrate");
+    return DDCB200_OK;
+}
+
+static int kineticTerms(ddcb200_ctx *c)
+{
+    // kinetic_terms alone (src/energy.c:48-163), e.g. after the first energy call
+    int rc = launchIntegrate<INT_KE>(c, 0, 0, 0);
+    if (rc) return rc;
+    ProfScope ps(c, PROF_REDUCE);
+    return reduceCols(c, c->kinPartial.p, (int)(c->nPad / TILE), 7, c->colMap.p + 19);
+}
+
+extern "C" int ddcb200_nglf(ddcb200_ctx *c, int nsteps, double dt)
+{
+    if (!c || nsteps < 0) return fail(DDCB200_ERR_ARG, "bad arguments");
+    if (c->nLocal == 0) return fail(DDCB200_ERR_STATE, "no state");
+    CK(cudaSetDevice(c->device));
+    int rc;
+    if (!c->forcesValid)
+    {
+        // firstEnergyCall (src/masters.c:579-620)
+        rc = ddcb200_ddcenergy(c, nsteps == 0 ? 1 : 0);
+        if (rc) return rc;
+    }
+    const double half = 0.5 * dt;
+    for (int s = 0; s < nsteps; s++)
+    {
+        // kick2 of the previous step is fused with kick1+drift of this one
+        if (s == 0) rc = launchIntegrate<INT_KICK1_DRIFT>(c, 0.0, half, dt);
+        else rc = launchIntegrate<INT_KICK2 | INT_KICK1_DRIFT>(c, half, half, dt);
+        if (rc) return rc;
+        c->loop++;
+        c->time += dt;
+        rc = ddcb200_ddcenergy(c, s == nsteps - 1 ? 1 : 0);
+        if (rc) return rc;
+    }
+    if (nsteps > 0)
+    {
+        rc = launchIntegrate<INT_KICK2 | INT_KE>(c, half, 0.0, 0.0);
+        if (rc) return rc;
+        ProfScope ps(c, PROF_REDUCE);
+        rc = reduceCols(c, c->kinPartial.p, (int)(c->nPad / TILE), 7, c->colMap.p + 19);
+        if (rc) return rc;
+        c->kineticValid = true;
+    }
+    return DDCB200_OK;
+}
+
+extern "C" int ddcb200_energyInfo(ddcb200_ctx *c, double kB, ddcb200_etype *out)
+{
+    if (!c || !out) return fail(DDCB200_ERR_ARG, "null argument");
+    if (!c->energyValid) return fail(DDCB200_ERR_STATE, "no energy evaluation is current (call ddcenergy(1) or nglf)");
+    CK(cudaSetDevice(c->device));
+    int rc;
+    if (!c->kineticValid)
+    {
+        rc = kineticTerms(c);
+        if (rc) return rc;
+        c->kineticValid = true;
+    }
+    cudaStream_t st = c->stream;
+    CK(cudaMemsetAsync(c->acc + ACC_MVX, 0, 3 * sizeof(double), st));
+    if (c->nMol > 0)
+    {
+        const int cur = c->cur;
+        k_mol_virial<<<(int)((c->nMol + 255) / 256), 256, 0, st>>>(c->nMol, c->molOffset.p, c->molBeads.p, c->slotOfBead.p, c->pos4[cur].p,
+                                                                   c->frc[0].p, c->frc[1].p, c->frc[2].p, c->massOfBead.p, c->pc,
+                                                                   c->acc + ACC_MVX);
+        CKL("k_mol_virial");
+    }
+    CK(cudaMemcpyAsync(c->accHost, c->acc, ACC_N * sizeof(double), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    const double *a = c->accHost;
+    memset(out, 0, sizeof(*out));
+    out->eLJ = a[ACC_ELJ]; out->eEle = a[ACC_EELE];
+    out->eBond = a[ACC_EBOND]; out->eAngle = a[ACC_EANGLE]; out->eTorsion = a[ACC_ETORS]; out->eImproper = a[ACC_EIMPR];
+    out->eRestraint = a[ACC_EREST];
+    out->eion = (a[ACC_ELJ] + a[ACC_EELE]) + (a[ACC_EBOND] + a[ACC_EANGLE] + a[ACC_ETORS] + a[ACC_EIMPR]) + a[ACC_EREST];
+    out->rk = a[ACC_RK];
+    for (int k = 0; k < 6; k++)
+    {
+        out->virial[k] = a[ACC_VXX + k];
+        out->tion[k] = a[ACC_TXX + k];
+    }
+    // eval_energyInfo, src/energyInfo.c:75-113
+    out->number = (double)c->nLocal;
+    out->volume = c->box.volume;
+    for (int k = 0; k < 6; k++) out->sion[k] = -(out->virial[k] + out->tion[k]) / out->volume;
+    out->pion = -(out->sion[0] + out->sion[1] + out->sion[2]) / 3.0;
+    out->temperature = 2.0 * out->rk / (3.0 * out->number - c->prm.nConstraints);
+    // molecularPressure, src/molecularPressure.c:57-67
+    for (int k = 0; k < 3; k++)
+    {
+        out->molVirial[k] = out->virial[k] + a[ACC_MVX + k];
+        out->molPressure[k] = (out->molVirial[k] + (double)c->nMolTotal * kB * out->temperature) / out->volume;
+    }
+    out->pMolecular = (out->molPressure[0] + out->molPressure[1] + out->molPressure[2]) / 3.0;
+    out->loop = c->loop;
+    out->time = c->time;
+    out->nMolecules = c->nMolTotal;
+    out->nPairsListed = c->nPairsListed;
+    return DDCB200_OK;
+}
+
+// ---- parity hooks -------------------------------------------------------------------------
+extern "C" int ddcb200_getCells(ddcb200_ctx *c, int *cellOfBead, int dims[3], double geom[9])
+{
+    if (!c || !cellOfBead) return fail(DDCB200_ERR_ARG, "null argument");
+    if (!c->listValid) return fail(DDCB200_ERR_STATE, "no list built");
+    CK(cudaSetDevice(c->device));
+    const int n = (int)c->nIon;
+    std::vector<int> cell(n), bead(n);
+    CK(cudaStreamSynchronize(c->stream));
+    CK(cudaMemcpy(cell.data(), c->cellOfSlot[c->cur].p, n * sizeof(int), cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(bead.data(), c->beadOfSlot[c->cur].p, n * sizeof(int), cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(c->gridHost, c->grid, sizeof(GridDev), cudaMemcpyDeviceToHost));
+    std::map<int, int> pos;
+    for (size_t i = 0; i < c->hLocalBeads.size(); i++) pos[c->hLocalBeads[i]] = (int)i;
+    for (int s = 0; s < n; s++)
+    {
+        auto it = pos.find(bead[s]);
+        if (it != pos.end()) cellOfBead[it->second] = cell[s];
+    }
+    if (dims)
+        for (int a = 0; a < 3; a++) dims[a] = c->gridHost->n[a];
+    if (geom)
+        for (int a = 0; a < 3; a++)
+        {
+            geom[a] = c->gridHost->mn[a];
+            geom[3 + a] = c->gridHost->mx[a];
+            geom[6 + a] = c->gridHost->d[a];
+        }
+    return DDCB200_OK;
+}
+
+extern "C" int64_t ddcb200_getPairs(ddcb200_ctx *c, int64_t capacity, int *beadI, int *beadJ, int *pruned)
+{
+    if (!c) return fail(DDCB200_ERR_ARG, "null ctx");
+    if (!c->listValid) return fail(DDCB200_ERR_STATE, "no list built");
+    if (cudaSetDevice(c->device) != cudaSuccess) return fail(DDCB200_ERR_CUDA, "cudaSetDevice");
+    const int n = (int)c->nLocal, nPad = (int)c->nPad;
+    std::vector<int> cnt(n), bead((size_t)c->nIon);
+    cudaStreamSynchronize(c->stream);
+    if (cudaMemcpy(cnt.data(), c->nbrCount.p, n * sizeof(int), cudaMemcpyDeviceToHost) != cudaSuccess ||
+        cudaMemcpy(bead.data(), c->beadOfSlot[c->cur].p, c->nIon * sizeof(int), cudaMemcpyDeviceToHost) != cudaSuccess)
+        return fail(DDCB200_ERR_CUDA, "getPairs copy");
+    int maxc = 0;
+    for (int i = 0; i < n; i++) maxc = std::max(maxc, cnt[i]);
+    std::vector<uint32_t> rows((size_t)maxc * nPad);
+    if (maxc && cudaMemcpy(rows.data(), c->nbr.p, rows.size() * sizeof(uint32_t), cudaMemcpyDeviceToHost) != cudaSuccess)
+        return fail(DDCB200_ERR_CUDA, "getPairs copy");
+    int64_t np = 0;
+    for (int i = 0; i < n; i++)
+        for (int k = 0; k < cnt[i]; k++)
+        {
+            const uint32_t e = rows[(size_t)k * nPad + i];
+            const int j = (int)(e & 0x07ffffffu);
+            const int bi = bead[i], bj = bead[j];
+            if (c->hGid[bi] < c->hGid[bj])
+            {
+                if (np < capacity && beadI && beadJ)
+                {
+                    beadI[np] = bi;
+                    beadJ[np] = bj;
+                    if (pruned) pruned[np] = (e & EXCL_BIT) ? 1 : 0;
+                }
+                np++;
+            }
+        }
+    return np;
+}
+
+extern "C" int ddcb200_profile(ddcb200_ctx *c, int enable)
+{
+    if (!c) return fail(DDCB200_ERR_ARG, "null ctx");
+    c->prof = enable != 0;
+    return DDCB200_OK;
+}
+
+extern "C" int ddcb200_profileRead(ddcb200_ctx *c, double ms[8], int64_t launches[8], int reset)
+{
+    if (!c) return fail(DDCB200_ERR_ARG, "null ctx");
+    CK(cudaSetDevice(c->device));
+    CK(cudaStreamSynchronize(c->stream));
+    for (auto &pe : c->pending)
+    {
+        float t = 0;
+        cudaEventElapsedTime(&t, pe.a, pe.b);
+        c->profMs[pe.slot] += t;
+        c->evPool.push_back(pe.a);
+        c->evPool.push_back(pe.b);
+    }
+    c->pending.clear();
+    for (int k = 0; k < PROF_N; k++)
+    {
+        if (ms) ms[k] = c->profMs[k];
+        if (launches) launches[k] = c->profLaunch[k];
+        if (reset)
+        {
+            c->profMs[k] = 0;
+            c->profLaunch[k] = 0;
+        }
+    }
+    return DDCB200_OK;
+}
+
+extern "C" int ddcb200_ncclUniqueId(unsigned char id[128])
+{
+    (void)id;
+    return fail(DDCB200_ERR_NCCL, "multi-GPU path not built yet");
+}
+extern "C" int ddcb200_ddcInit(ddcb200_ctx *c, int rank, int nranks, int lx, int ly, int lz, const unsigned char id[128])
+{
+    (void)c; (void)rank; (void)nranks; (void)lx; (void)ly; (void)lz; (void)id;
+    return fail(DDCB200_ERR_NCCL, "multi-GPU path not built yet");
+}

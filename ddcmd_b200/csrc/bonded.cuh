@@ -1,0 +1,276 @@
+// bonded.cuh - all Martini bonded terms and position restraints in ONE kernel over a
+// kind-sorted term list: harmonic bonds, harmonic / cosine / restricted-bending angles,
+// proper torsions, harmonic impropers.
+//
+// Replaces charmmConvalent + connectiveEnergy + res*Sorted (src/bioCharmmCovalent.c:95-251,
+// src/bioCharmmCovalentEnergies.c:266-351,754-794, src/bioCharmmCovalentEnergiesSorted.c)
+// and bondedGPU.cu's seven kernels, and restraint() (src/restraint.c:259-361).
+// Terms are sorted by kind on the host, so a warp runs one formula; indices are slot
+// indices refreshed at every list build.
+#pragma once
+#include "engine.cuh"
+
+struct V3
+{
+    double x, y, z;
+};
+__device__ __forceinline__ V3 vsub(const double4 a, const double4 b) { return V3{a.x - b.x, a.y - b.y, a.z - b.z}; }
+__device__ __forceinline__ double vdot(V3 a, V3 b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
+__device__ __forceinline__ V3 vcross(V3 a, V3 b) { return V3{a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x}; }
+__device__ __forceinline__ V3 vscale(V3 a, double s) { return V3{a.x * s, a.y * s, a.z * s}; }
+__device__ __forceinline__ V3 vaxpy(double s, V3 a, V3 b) { return V3{s * a.x + b.x, s * a.y + b.y, s * a.z + b.z}; }
+
+__device__ __forceinline__ V3 minImage(V3 d, const PairConst &pc)
+{
+    // nearestImage == Preduce for an orthorhombic box (src/preduce.c:449-470): d -= h*rint(d/h)
+    d.x -= pc.hxx * rint(d.x / pc.hxx);
+    d.y -= pc.hyy * rint(d.y / pc.hyy);
+    d.z -= pc.hzz * rint(d.z / pc.hzz);
+    return d;
+}
+
+__device__ __forceinline__ void addForce(double *fx, double *fy, double *fz, int s, V3 f)
+{
+    atomicAdd(fx + s, f.x);
+    atomicAdd(fy + s, f.y);
+    atomicAdd(fz + s, f.z);
+}
+
+// bioDihedralFast (src/bioCharmmCovalentEnergies.c:266-351): angle, sin, d(cos)/dr and the
+// geometric virial factor.
+__device__ __forceinline__ void dihedral(V3 vij, V3 vjk, V3 vkl, double &ang, double &sinX, V3 &dI, V3 &dJ, V3 &dK, V3 &dL, double vir[6])
+{
+    const double eps = 1e-12;
+    const double a2 = vdot(vij, vij), b2 = vdot(vjk, vjk), c2 = vdot(vkl, vkl);
+    const double ab = vdot(vij, vjk), bc = vdot(vjk, vkl), ac = vdot(vij, vkl);
+    const double f = ab * bc - ac * b2;
+    const double g1 = a2 * b2 - ab * ab + eps;
+    const double g2 = b2 * c2 - bc * bc + eps;
+    const double y = 1.0 / sqrt(g1 * g2);
+    double x = y * f;
+    const double xab = y * bc + x / g1 * ab;
+    const double xbc = y * ab + x / g2 * bc;
+    const double xac = -y * b2;
+    const double xaa = -0.5 * x * b2 / g1;
+    const double xcc = -0.5 * x * b2 / g2;
+    const double xbb = -y * ac - 0.5 * x * (a2 / g1 + c2 / g2);
+    V3 ca = vscale(vjk, xab);
+    ca = vaxpy(xac, vkl, ca);
+    ca = vaxpy(2.0 * xaa, vij, ca);
+    V3 cb = vscale(vij, xab);
+    cb = vaxpy(xbc, vkl, cb);
+    cb = vaxpy(2.0 * xbb, vjk, cb);
+    V3 cc = vscale(vjk, xbc);
+    cc = vaxpy(xac, vij, cc);
+    cc = vaxpy(2.0 * xcc, vkl, cc);
+    const V3 m = vcross(vij, vjk), n = vcross(vjk, vkl), mxn = vcross(m, n);
+    const double sign = (vdot(vjk, mxn) < 0.0) ? -1.0 : 1.0;
+    x = fmax(fmin(x, 1.0), -1.0);
+    ang = sign * acos(x);
+    sinX = sin(ang);
+    dI = ca;
+    dJ = V3{cb.x - ca.x, cb.y - ca.y, cb.z - ca.z};
+    dK = V3{cc.x - cb.x, cc.y - cb.y, cc.z - cb.z};
+    dL = V3{-cc.x, -cc.y, -cc.z};
+    vir[0] = -(ca.x * vij.x + cb.x * vjk.x + cc.x * vkl.x);   // xx
+    vir[1] = -(ca.y * vij.y + cb.y * vjk.y + cc.y * vkl.y);   // yy
+    vir[2] = -(ca.z * vij.z + cb.z * vjk.z + cc.z * vkl.z);   // zz
+    vir[3] = -(ca.x * vij.y + cb.x * vjk.y + cc.x * vkl.y);   // xy
+    vir[4] = -(ca.x * vij.z + cb.x * vjk.z + cc.x * vkl.z);   // xz
+    vir[5] = -(ca.y * vij.z + cb.y * vjk.z + cc.y * vkl.z);   // yz
+}
+
+#define BONDED_THREADS 128
+#define BONDED_ACC 11   // 0..5 virial (xx yy zz xy xz yz), 6 bond, 7 angle, 8 torsion, 9 improper, 10 restraint
+
+template <bool ENERGY>
+__global__ void __launch_bounds__(BONDED_THREADS)
+k_bonded(int64_t nTerms, const Term *__restrict__ terms, int64_t nRestr, const int *__restrict__ restrSlot,
+         const double *__restrict__ restrParm, int restrOrigin, const double4 *__restrict__ pos, PairConst pc,
+         double *__restrict__ fx, double *__restrict__ fy, double *__restrict__ fz, double *__restrict__ partial)
+{
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    double acc[BONDED_ACC];
+#pragma unroll
+    for (int a = 0; a < BONDED_ACC; a++) acc[a] = 0.0;
+
+    if (t < nTerms)
+    {
+        const Term tm = terms[t];
+        if (tm.i >= 0)
+        {
+            if (tm.kind == 0)
+            {
+                // resBondSorted (src/bioCharmmCovalentEnergiesSorted.c:18-116)
+                const V3 b = minImage(vsub(pos[tm.i], pos[tm.j]), pc);
+                const double len = sqrt(vdot(b, b));
+                const double dl = len - tm.p1;
+                const double kf = -2.0 * tm.p0 * dl / len;
+                const V3 f = vscale(b, kf);
+                addForce(fx, fy, fz, tm.i, f);
+                addForce(fx, fy, fz, tm.j, V3{-f.x, -f.y, -f.z});
+                if (ENERGY)
+                {
+                    acc[6] = tm.p0 * dl * dl;
+                    acc[0] = f.x * b.x; acc[1] = f.y * b.y; acc[2] = f.z * b.z;
+                    acc[3] = f.x * b.y; acc[4] = f.x * b.z; acc[5] = f.y * b.z;
+                }
+            }
+            else if (tm.kind <= 3)
+            {
+                // resAngleSorted / resAngleCosineSorted / resAngleRestrainSorted (:118-487)
+                const double4 pj = pos[tm.j];
+                const V3 vij = minImage(vsub(pos[tm.i], pj), pc), vkj = minImage(vsub(pos[tm.k], pj), pc);
+                const double bij = sqrt(vdot(vij, vij)), bkj = sqrt(vdot(vkj, vkj));
+                const V3 uij = vscale(vij, 1.0 / bij), ukj = vscale(vkj, 1.0 / bkj);
+                const double c = vdot(uij, ukj);
+                double coef, e;
+                if (tm.kind == 1)
+                {
+                    const double a = acos(c), da = a - tm.p1;
+                    e = tm.p0 * da * da;
+                    coef = 2.0 * tm.p0 * da / sin(a);
+                }
+                else if (tm.kind == 2)
+                {
+                    const double da = c - tm.p1;
+                    e = tm.p0 * da * da;
+                    coef = -2.0 * tm.p0 * da;
+                }
+                else
+                {
+                    const double s2 = 1.0 - c * c, da = c - tm.p1;
+                    e = tm.p0 * da * da / s2;
+                    coef = -2.0 * tm.p0 * da * (1.0 - c * tm.p1) / (s2 * s2);
+                }
+                const double ci = coef / bij, ck = coef / bkj;
+                const V3 fi = V3{ci * (ukj.x - uij.x * c), ci * (ukj.y - uij.y * c), ci * (ukj.z - uij.z * c)};
+                const V3 fk = V3{ck * (uij.x - ukj.x * c), ck * (uij.y - ukj.y * c), ck * (uij.z - ukj.z * c)};
+                addForce(fx, fy, fz, tm.i, fi);
+                addForce(fx, fy, fz, tm.k, fk);
+                addForce(fx, fy, fz, tm.j, V3{-(fi.x + fk.x), -(fi.y + fk.y), -(fi.z + fk.z)});
+                if (ENERGY)
+                {
+                    acc[7] = e;
+                    acc[0] = fi.x * vij.x + fk.x * vkj.x; acc[1] = fi.y * vij.y + fk.y * vkj.y; acc[2] = fi.z * vij.z + fk.z * vkj.z;
+                    acc[3] = fi.x * vij.y + fk.x * vkj.y; acc[4] = fi.x * vij.z + fk.x * vkj.z; acc[5] = fi.y * vij.z + fk.y * vkj.z;
+                }
+            }
+            else
+            {
+                // resTorsionSorted / resImproperSorted (:577-848)
+                const double4 pI = pos[tm.i], pJ = pos[tm.j], pK = pos[tm.k], pL = pos[tm.l];
+                const V3 vij = minImage(vsub(pI, pJ), pc), vjk = minImage(vsub(pJ, pK), pc), vkl = minImage(vsub(pK, pL), pc);
+                double ang, sinX, vir[6];
+                V3 dI, dJ, dK, dL;
+                dihedral(vij, vjk, vkl, ang, sinX, dI, dJ, dK, dL, vir);
+                double kf, e;
+                if (tm.kind == 4)
+                {
+                    const double kchi = tm.p0, delta = tm.p1, n = tm.p2;
+                    e = kchi * (1.0 + cos(n * ang - delta));
+                    if (fabs(sinX) > 1e-8) kf = kchi * n * sin(n * ang - delta) / sinX;
+                    else
+                    {
+                        const double nX2 = (n * ang) * (n * ang), X2 = ang * ang;
+                        const double num = 1 - nX2 / 6 + nX2 * nX2 / 120 - nX2 * nX2 * nX2 / 5040 + nX2 * nX2 * nX2 * nX2 / 362880 - nX2 * nX2 * nX2 * nX2 * nX2 / 39916800;
+                        const double den = 1 - X2 / 6 + X2 * X2 / 120 - X2 * X2 * X2 / 5040 + X2 * X2 * X2 * X2 / 362880 - X2 * X2 * X2 * X2 * X2 / 39916800;
+                        const double ratio = n * num / den;
+                        kf = (delta > 3.12413936106985) ? -kchi * n * ratio : kchi * n * ratio;
+                    }
+                }
+                else
+                {
+                    const double kpsi = tm.p0, psi0 = tm.p1;
+                    double d = ang - psi0;
+                    if (d < -M_PI) d += 2 * M_PI;
+                    else if (d > M_PI) d -= 2 * M_PI;
+                    e = kpsi * d * d;
+                    if (fabs(sinX) > 1e-8) kf = -2.0 * kpsi * d / sinX;
+                    else
+                    {
+                        const double X2 = ang * ang;
+                        kf = -2.0 * kpsi / (1 - X2 / 6 + X2 * X2 / 120 - X2 * X2 * X2 / 5040 + X2 * X2 * X2 * X2 / 362880 - X2 * X2 * X2 * X2 * X2 / 39916800);
+                    }
+                }
+                addForce(fx, fy, fz, tm.i, vscale(dI, -kf));
+                addForce(fx, fy, fz, tm.j, vscale(dJ, -kf));
+                addForce(fx, fy, fz, tm.k, vscale(dK, -kf));
+                addForce(fx, fy, fz, tm.l, vscale(dL, -kf));
+                if (ENERGY)
+                {
+                    acc[tm.kind == 4 ? 8 : 9] = e;
+#pragma unroll
+                    for (int a = 0; a < 6; a++) acc[a] = vir[a] * kf;
+                }
+            }
+        }
+    }
+    else if (t - nTerms < nRestr)
+    {
+        // restraint (src/restraint.c:287-357)
+        const int64_t r = t - nTerms;
+        const int s = restrSlot[r];
+        if (s >= 0)
+        {
+            const double *p = restrParm + 7 * r;
+            double x0 = p[0] * pc.hxx, y0 = p[1] * pc.hyy, z0 = p[2] * pc.hzz;
+            if (restrOrigin == 0)
+            {
+                x0 -= pc.hxx / 2.0;
+                y0 -= pc.hyy / 2.0;
+                z0 -= pc.hzz / 2.0;
+            }
+            const double kb = p[3];
+            const double4 ps = pos[s];
+            V3 d = V3{ps.x - x0, ps.y - y0, ps.z - z0};
+            if ((p[4] > 0 && fabs(d.x) > pc.hhx) || (p[5] > 0 && fabs(d.y) > pc.hhy) || (p[6] > 0 && fabs(d.z) > pc.hhz)) d = minImage(d, pc);
+            const V3 cd = V3{p[4] * d.x, p[5] * d.y, p[6] * d.z};
+            const V3 f = vscale(cd, -2.0 * kb);
+            addForce(fx, fy, fz, s, f);
+            if (ENERGY)
+            {
+                acc[10] = kb * (cd.x * d.x + cd.y * d.y + cd.z * d.z);
+                acc[0] = f.x * cd.x; acc[1] = f.y * cd.y; acc[2] = f.z * cd.z;
+                acc[3] = f.x * cd.y; acc[4] = f.x * cd.z; acc[5] = f.y * cd.z;
+            }
+        }
+    }
+
+    if (ENERGY)
+    {
+        __shared__ double red[BONDED_ACC][BONDED_THREADS / 32];
+#pragma unroll
+        for (int a = 0; a < BONDED_ACC; a++)
+        {
+            double v = acc[a];
+            for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+            if ((threadIdx.x & 31) == 0) red[a][threadIdx.x >> 5] = v;
+        }
+        __syncthreads();
+        if (threadIdx.x < BONDED_ACC)
+        {
+            double v = 0.0;
+            for (int w = 0; w < BONDED_THREADS / 32; w++) v += red[threadIdx.x][w];
+            partial[(size_t)blockIdx.x * BONDED_ACC + threadIdx.x] = v;
+        }
+    }
+}
+
+// refresh slot indices of the bonded terms and restraints after a re-sort
+__global__ void k_terms_remap(int64_t nTerms, const Term *__restrict__ in, Term *__restrict__ out, const int *__restrict__ slotOfBead)
+{
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= nTerms) return;
+    Term tm = in[t];
+    tm.i = slotOfBead[tm.i];
+    tm.j = slotOfBead[tm.j];
+    if (tm.k >= 0) tm.k = slotOfBead[tm.k];
+    if (tm.l >= 0) tm.l = slotOfBead[tm.l];
+    out[t] = tm;
+}
+__global__ void k_restr_remap(int64_t n, const int *__restrict__ bead, int *__restrict__ slot, const int *__restrict__ slotOfBead)
+{
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t < n) slot[t] = slotOfBead[bead[t]];
+}

@@ -1,0 +1,193 @@
+// engine.cuh - device data model of the B200-native Martini MD step.
+//
+// Layout in HBM (see DESIGN.md "Data layout"):
+//   * "slot" order = beads sorted by (reference GeomBox cell, input index); rebuilt with the
+//     neighbor list every DDC updateRate steps.  All per-step streams are in slot order so a
+//     warp touches consecutive memory.
+//   * pos4[slot] = {x, y, z, w}: 32-byte records so one j-bead is one DRAM/L2 sector; w carries
+//     packed ints (LJ type, charge index, input index) reinterpreted as a double.
+//   * vel / frc are SoA (3 arrays each).
+//   * neighbor list: full (both directions) per-bead list, transposed (entry k of slot i at
+//     k*nPad + i) so a warp reads 32 consecutive ints; entries are ordered by build-time
+//     distance so the lanes of a warp leave the cutoff sphere together.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string>
+#include <vector>
+#include "../../include/ddcmd_b200.h"
+
+#define TILE 128           // beads per CTA in the per-step kernels
+#define NBINS 8            // build-time distance bins used to order each bead's list
+#define EXCL_BIT 0x80000000u
+
+struct BoxConst
+{
+    double hxx, hyy, hzz;      // box edges
+    double hhx, hhy, hhz;      // 0.5*h (PreduceOrthorhombicB7_OneLatticeReduction, src/preduce.c:147-160)
+    double hinv[9];            // matinv cofactor inverse (src/three_algebra.c:37-64)
+    double cx, cy, cz;         // GeomBox centre
+    double R2cut;              // 0.25*minspan^2 (src/pairlist.c:227)
+    double rlist2;             // (rcut0+deltaR)^2 (src/pairlist.c:226)
+    double rc2;                // rmax^2
+    double rcutGeom;           // max(rcut0+deltaR, minBoxSide)
+    double spanx, spany, spanz;  // computeBoxSpan (src/geom.c:478-511)
+    double binEdge2[NBINS - 1];  // r^2 edges of the ordering bins
+    double volume;
+};
+
+struct GridDev
+{
+    double mn[3], mx[3], d[3];
+    int n[3];
+    int ncell;
+    int error;       // sticky error flags (bit0: neighbor capacity overflow, bit1: cell overflow)
+    int maxCount;    // max full-list length over beads
+    unsigned long long totalEntries;
+};
+
+struct PairConst
+{
+    double rc2, R2cut, hxx, hyy, hzz, hhx, hhy, hhz;
+    double keR, krf, crf;
+    int ntypes;
+};
+
+// packed w of pos4: [0,8) LJ type, [8,16) charge index, [32,64) input (bead) index
+__host__ __device__ inline uint64_t packW(int lj, int qi, uint32_t bead) { return (uint64_t)(lj & 0xff) | ((uint64_t)(qi & 0xff) << 8) | ((uint64_t)bead << 32); }
+
+struct Term
+{
+    int i, j, k, l;
+    double p0, p1, p2;
+    int kind, pad;
+};
+
+enum { PROF_INTEGRATE = 0, PROF_PAIR, PROF_BONDED, PROF_LIST, PROF_REDUCE, PROF_HALO, PROF_N = 8 };
+enum { ACC_ELJ = 0, ACC_EELE, ACC_VXX, ACC_VYY, ACC_VZZ, ACC_VXY, ACC_VXZ, ACC_VYZ,
+       ACC_EBOND, ACC_EANGLE, ACC_ETORS, ACC_EIMPR, ACC_EREST, ACC_RK,
+       ACC_TXX, ACC_TYY, ACC_TZZ, ACC_TXY, ACC_TXZ, ACC_TYZ, ACC_MVX, ACC_MVY, ACC_MVZ, ACC_N = 24 };
+
+template <typename T>
+struct DevBuf
+{
+    T *p = nullptr;
+    size_t cap = 0;
+    cudaError_t ensure(size_t n)
+    {
+        if (n <= cap) return cudaSuccess;
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+        size_t want = n + n / 8 + 256;
+        cudaError_t e = cudaMalloc((void **)&p, want * sizeof(T));
+        if (e == cudaSuccess) cap = want;
+        return e;
+    }
+    void release()
+    {
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+    }
+};
+
+struct ddcb200_ctx
+{
+    ddcb200_params prm;
+    BoxConst box;
+    PairConst pc;
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    int numSM = 148;
+
+    // static tables
+    int ntypes = 0;
+    DevBuf<double2> ljTab;        // {c6, c12} = {4 eps sigma^6, 4 eps sigma^12}
+    DevBuf<double> shiftTab;
+    int nspecies = 0;
+    std::vector<int> hSpecLJ, hSpecQi;
+    std::vector<double> hSpecQ, hSpecMass, hQtab;
+    DevBuf<double> qTab;          // unique charges
+    DevBuf<double> massOfBead;    // by input index  (mass)
+    DevBuf<uint64_t> wOfBead;     // packed w by input index
+    DevBuf<uint64_t> gidOfBead;
+    std::vector<uint64_t> hGid;
+    std::vector<int> hSpecies;
+    int64_t nGlobal = 0;
+
+    // exclusions
+    int nMolTypes = 0;
+    std::vector<int> hMolTypeOfSpecies, hMolTypeNSpecies;
+    DevBuf<int> molTypeOfBead;    // -1: none
+    DevBuf<int> molTypeSingle;    // per mol type: 1 if nSpecies == 1
+    DevBuf<int> bpairOffset;
+    DevBuf<uint32_t> bpairKey;    // sorted (min<<16|max) keys per mol type
+    bool haveExcl = false;
+
+    // bonded terms (input-index form and slot form)
+    int64_t nTerms = 0;
+    DevBuf<Term> termsBead, termsSlot;
+    int64_t nRestr = 0;
+    DevBuf<int> restrBead, restrSlot;
+    DevBuf<double> restrParm;     // 7 doubles: frac0[3], kb, fc[3]
+    int restrOrigin = 0;
+
+    // molecules (molecular virial)
+    int64_t nMol = 0, nMolTotal = 0;
+    DevBuf<int64_t> molOffset;
+    DevBuf<int> molBeads;
+
+    // dynamic state, slot order (double buffered for the re-sort)
+    int64_t nLocal = 0, nIon = 0, nPad = 0;
+    DevBuf<double4> pos4[2];
+    DevBuf<double> vel[2][3];
+    DevBuf<double> frc[3];
+    DevBuf<int> beadOfSlot[2];
+    int cur = 0;
+    DevBuf<int> slotOfBead;       // input index -> slot (-1 if absent)
+    std::vector<int> hLocalBeads; // order of sendState
+
+    // cells
+    DevBuf<int> cellOfSlot[2], rank0, cellCount, cellStart, member, perm;
+    DevBuf<double> mmPartial;
+    GridDev *grid = nullptr;      // device
+    GridDev *gridHost = nullptr;  // pinned
+
+    // neighbor list
+    DevBuf<uint32_t> nbrRaw, nbr;
+    DevBuf<int> nbrCount;
+    int nbrCap = 0;               // entries per bead allocated
+    bool listValid = false;
+    int64_t lastBuildLoop = -1;
+
+    // accumulators
+    DevBuf<double> pairPartial, bondPartial, kinPartial;   // per-CTA partial sums
+    DevBuf<int> colMap;           // partial column -> acc slot
+    double *acc = nullptr;        // device ACC_N
+    double *accHost = nullptr;    // pinned
+    bool energyValid = false, kineticValid = false;
+    int64_t nPairsListed = 0;
+    DevBuf<double> stage;         // H2D / D2H staging in caller order
+    DevBuf<int> stageI;
+
+    int64_t loop = 0;
+    double time = 0.0;
+    bool forcesValid = false;
+    bool pendingKick2 = false;
+    double pendingDt = 0.0;
+
+    // profiling
+    bool prof = false;
+    double profMs[PROF_N] = {0};
+    int64_t profLaunch[PROF_N] = {0};
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    struct PendingEv { cudaEvent_t a, b; int slot; };
+    std::vector<PendingEv> pending;
+    std::vector<cudaEvent_t> evPool;
+
+    // multi-GPU
+    int rank = 0, nranks = 1;
+    void *nccl = nullptr;
+};

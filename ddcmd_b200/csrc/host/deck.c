@@ -1,0 +1,944 @@
+/* deck.c - ddcMD object-database front end for the Martini MD step (plain C host code).
+ *
+ * Mirrors, for the subset of objects a Martini deck uses, the reference's init chain:
+ *   simulate_init (src/simulate.c:104-297) -> system_init (src/system.c:79-217)
+ *   -> moleculeClassInit/moleculeInit/species_init (src/molecule.c:20-58,212-241, src/species.c:20-40)
+ *   -> box_init (src/box.c:50-87) -> collection read (src/collection_read.c:86-170)
+ *   -> martini_parms (src/bioMartini.c:1210-1353): mmff_init (src/bioMMFF.c:236-273),
+ *      genMartiniConn (:567-838), genMartiniBondPair (:135-282), martiniLJ_parms (:868-950)
+ *   -> restraint_parms (src/restraint.c:200-257) -> neighbor_init (src/neighbor.c:34-56)
+ *   -> nglf_parms -> ddc_init (src/ddc.c:40-120)
+ * and flattens the per-residue templates into per-bead term lists, which is what
+ * charmmResidues + connectiveEnergy rebuild every step on the CPU (src/bioCharmmCovalent.c:48-93).
+ */
+#include "host.h"
+#include "../../../include/ddcmd_b200_host.h"
+#include <ctype.h>
+#include <math.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+static char g_hostErr[1024];
+const char *ddcb200_lastHostError(void) { return g_hostErr; }
+static int herr(const char *fmt, ...)
+{
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_hostErr, sizeof g_hostErr, fmt, ap);
+    va_end(ap);
+    return -1;
+}
+
+double ddcb200_unitsConvert(double value, const char *from, const char *to) { return hu_convert(value, from, to); }
+
+/* ---- MMFF tree (reference src/bioMMFF.h:4-218) ----------------------------------------------- */
+typedef struct { int atomI, atomJ, func; char typeI[32], typeJ[32]; double kb, b0; } H_BOND;
+typedef struct { int atomI, atomJ, atomK, func; double ktheta, theta0; } H_ANGLE;
+typedef struct { int atomI, atomJ, atomK, atomL, func, n; double kchi, delta; } H_TORS;
+typedef struct { int atomI, atomJ, valid; } H_PAIR;
+typedef struct { char name[32], type[32]; int atomID, typeID; double charge; } H_ATOM;
+typedef struct
+{
+    char objName[64], resName[32];
+    int resID, nAtoms, nBonds, nAngles, nTors, nExcl, nCons;
+    H_ATOM *atoms;
+    H_BOND *bonds;
+    H_ANGLE *angles;
+    H_TORS *tors;
+    H_PAIR *excl, *cons;
+    int nBpair;
+    int *bpI, *bpJ;
+} H_RESI;
+
+typedef struct
+{
+    int nResi, nTypes;
+    H_RESI *resi;
+    int *typeID;           /* atomTypes[i]->atomTypeID */
+    char (*typeName)[32];
+} H_MMFF;
+
+#define NEED(o, what, name) do { if (!(o)) return herr("object %s %s not found", name, what); } while (0)
+
+static int loadResi(ODB *db, const char *name, H_RESI *r)
+{
+    const ODB_OBJECT *o = odb_find(db, name, "RESIPARMS");
+    NEED(o, "RESIPARMS", name);
+    memset(r, 0, sizeof *r);
+    snprintf(r->objName, sizeof r->objName, "%s", name);
+    char *s;
+    odb_getString(o, "resName", &s, "NoName");
+    snprintf(r->resName, sizeof r->resName, "%s", s);
+    free(s);
+    odb_getInts(o, "resID", &r->resID, 1, "0");
+    char **groups;
+    int ng = odb_getStrings(o, "groupList", &groups, NULL);
+    if (ng <= 0) return herr("RESIPARMS %s has no groupList", name);
+    int cap = 0;
+    for (int g = 0; g < ng; g++)
+    {
+        const ODB_OBJECT *go = odb_find(db, groups[g], "GROUPPARMS");
+        NEED(go, "GROUPPARMS", groups[g]);
+        char **an;
+        int na = odb_getStrings(go, "atomList", &an, NULL);
+        for (int a = 0; a < na; a++)
+        {
+            const ODB_OBJECT *ao = odb_find(db, an[a], "ATOMPARMS");
+            NEED(ao, "ATOMPARMS", an[a]);
+            if (r->nAtoms == cap)
+            {
+                cap = cap ? 2 * cap : 16;
+                r->atoms = (H_ATOM *)realloc(r->atoms, cap * sizeof(H_ATOM));
+            }
+            H_ATOM *at = &r->atoms[r->nAtoms++];
+            memset(at, 0, sizeof *at);
+            odb_getString(ao, "atomName", &s, "NoName");
+            snprintf(at->name, sizeof at->name, "%s", s);
+            free(s);
+            odb_getString(ao, "atomType", &s, "NoType");
+            snprintf(at->type, sizeof at->type, "%s", s);
+            free(s);
+            odb_getInts(ao, "atomID", &at->atomID, 1, "0");
+            odb_getInts(ao, "atomTypeID", &at->typeID, 1, "0");
+            if (odb_getWithUnits(ao, "charge", &at->charge, 1, "0.0", "i*t", NULL) < 0) return herr("bad charge unit in %s", an[a]);
+        }
+        odb_freeStrings(an, na);
+    }
+    odb_freeStrings(groups, ng);
+
+    char **names;
+    int n = odb_getStrings(o, "bondList", &names, NULL);
+    r->nBonds = n;
+    r->bonds = (H_BOND *)calloc(n > 0 ? n : 1, sizeof(H_BOND));
+    for (int i = 0; i < n; i++)
+    {
+        const ODB_OBJECT *b = odb_find(db, names[i], "BONDPARMS");
+        NEED(b, "BONDPARMS", names[i]);
+        H_BOND *h = &r->bonds[i];
+        odb_getInts(b, "atomI", &h->atomI, 1, "0");
+        odb_getInts(b, "atomJ", &h->atomJ, 1, "0");
+        odb_getInts(b, "func", &h->func, 1, "1");
+        odb_getString(b, "atomTypeI", &s, "NoType"); snprintf(h->typeI, 32, "%s", s); free(s);
+        odb_getString(b, "atomTypeJ", &s, "NoType"); snprintf(h->typeJ, 32, "%s", s); free(s);
+        if (odb_getWithUnits(b, "kb", &h->kb, 1, "0.0", "kJ*mol^-1*nm^-2", NULL) < 0) return herr("bad kb unit in %s", names[i]);
+        if (odb_getWithUnits(b, "b0", &h->b0, 1, "0.0", "nm", NULL) < 0) return herr("bad b0 unit in %s", names[i]);
+    }
+    odb_freeStrings(names, n);
+
+    n = odb_getStrings(o, "angleList", &names, NULL);
+    r->nAngles = n;
+    r->angles = (H_ANGLE *)calloc(n > 0 ? n : 1, sizeof(H_ANGLE));
+    for (int i = 0; i < n; i++)
+    {
+        const ODB_OBJECT *b = odb_find(db, names[i], "ANGLEPARMS");
+        NEED(b, "ANGLEPARMS", names[i]);
+        H_ANGLE *h = &r->angles[i];
+        odb_getInts(b, "atomI", &h->atomI, 1, "0");
+        odb_getInts(b, "atomJ", &h->atomJ, 1, "0");
+        odb_getInts(b, "atomK", &h->atomK, 1, "0");
+        odb_getInts(b, "func", &h->func, 1, "1");
+        if (odb_getWithUnits(b, "ktheta", &h->ktheta, 1, "0.0", "kJ*mol^-1", NULL) < 0) return herr("bad ktheta unit in %s", names[i]);
+        odb_getDoubles(b, "theta0", &h->theta0, 1, "0");
+    }
+    odb_freeStrings(names, n);
+
+    n = odb_getStrings(o, "dihedralList", &names, NULL);
+    r->nTors = n;
+    r->tors = (H_TORS *)calloc(n > 0 ? n : 1, sizeof(H_TORS));
+    for (int i = 0; i < n; i++)
+    {
+        const ODB_OBJECT *b = odb_find(db, names[i], "TORSPARMS");
+        NEED(b, "TORSPARMS", names[i]);
+        H_TORS *h = &r->tors[i];
+        odb_getInts(b, "atomI", &h->atomI, 1, "0");
+        odb_getInts(b, "atomJ", &h->atomJ, 1, "0");
+        odb_getInts(b, "atomK", &h->atomK, 1, "0");
+        odb_getInts(b, "atomL", &h->atomL, 1, "0");
+        odb_getInts(b, "func", &h->func, 1, "1");
+        odb_getInts(b, "n", &h->n, 1, "1");
+        if (odb_getWithUnits(b, "kchi", &h->kchi, 1, "0.0", "kJ*mol^-1", NULL) < 0) return herr("bad kchi unit in %s", names[i]);
+        odb_getDoubles(b, "delta", &h->delta, 1, "0");
+    }
+    odb_freeStrings(names, n);
+
+    n = odb_getStrings(o, "exclusionList", &names, NULL);
+    r->nExcl = n;
+    r->excl = (H_PAIR *)calloc(n > 0 ? n : 1, sizeof(H_PAIR));
+    for (int i = 0; i < n; i++)
+    {
+        const ODB_OBJECT *b = odb_find(db, names[i], "EXCLUDEPARMS");
+        NEED(b, "EXCLUDEPARMS", names[i]);
+        odb_getInts(b, "atomI", &r->excl[i].atomI, 1, "0");
+        odb_getInts(b, "atomJ", &r->excl[i].atomJ, 1, "0");
+        r->excl[i].valid = 1;
+    }
+    odb_freeStrings(names, n);
+
+    /* constraintList -> CONSLISTPARMS{constraintSubList} -> CONSPARMS (valid iff func==1, src/bioMMFF.c:66-82) */
+    n = odb_getStrings(o, "constraintList", &names, NULL);
+    int ccap = 0;
+    for (int i = 0; i < n; i++)
+    {
+        const ODB_OBJECT *cl = odb_find(db, names[i], "CONSLISTPARMS");
+        NEED(cl, "CONSLISTPARMS", names[i]);
+        char **sub;
+        int ns = odb_getStrings(cl, "constraintSubList", &sub, NULL);
+        for (int k = 0; k < ns; k++)
+        {
+            const ODB_OBJECT *b = odb_find(db, sub[k], "CONSPARMS");
+            NEED(b, "CONSPARMS", sub[k]);
+            if (r->nCons == ccap)
+            {
+                ccap = ccap ? 2 * ccap : 16;
+                r->cons = (H_PAIR *)realloc(r->cons, ccap * sizeof(H_PAIR));
+            }
+            H_PAIR *h = &r->cons[r->nCons++];
+            int func;
+            odb_getInts(b, "atomI", &h->atomI, 1, "0");
+            odb_getInts(b, "atomJ", &h->atomJ, 1, "0");
+            odb_getInts(b, "func", &func, 1, "1");
+            h->valid = (func == 1);
+        }
+        odb_freeStrings(sub, ns);
+    }
+    odb_freeStrings(names, n);
+    return 0;
+}
+
+static int samePair(int a, int b, int c, int d) { return (a == c && b == d) || (a == d && b == c); }
+
+/* validateExclusions + genMartiniBondPair (src/bioMartini.c:54-282) */
+static void buildBpairs(H_RESI *r)
+{
+    for (int e = 0; e < r->nExcl; e++)
+        for (int i = 0; i < r->nBonds; i++)
+            if (r->bonds[i].func == 1 && samePair(r->excl[e].atomI, r->excl[e].atomJ, r->bonds[i].atomI, r->bonds[i].atomJ))
+            {
+                r->excl[e].valid = 0;
+                break;
+            }
+    for (int c = 0; c < r->nCons; c++)
+    {
+        if (!r->cons[c].valid) continue;
+        for (int i = 0; i < r->nBonds; i++)
+            if (r->bonds[i].func == 1 && samePair(r->cons[c].atomI, r->cons[c].atomJ, r->bonds[i].atomI, r->bonds[i].atomJ))
+            {
+                r->cons[c].valid = 0;
+                break;
+            }
+        for (int e = 0; e < r->nExcl; e++)
+            if (r->excl[e].valid && samePair(r->cons[c].atomI, r->cons[c].atomJ, r->excl[e].atomI, r->excl[e].atomJ))
+            {
+                r->cons[c].valid = 0;
+                break;
+            }
+    }
+    int n = 0;
+    for (int i = 0; i < r->nBonds; i++) n += r->bonds[i].func == 1;
+    for (int e = 0; e < r->nExcl; e++) n += r->excl[e].valid;
+    for (int c = 0; c < r->nCons; c++) n += r->cons[c].valid;
+    r->bpI = (int *)calloc(n > 0 ? n : 1, sizeof(int));
+    r->bpJ = (int *)calloc(n > 0 ? n : 1, sizeof(int));
+    r->nBpair = 0;
+    for (int i = 0; i < r->nBonds; i++)
+        if (r->bonds[i].func == 1) { r->bpI[r->nBpair] = r->bonds[i].atomI; r->bpJ[r->nBpair++] = r->bonds[i].atomJ; }
+    for (int e = 0; e < r->nExcl; e++)
+        if (r->excl[e].valid) { r->bpI[r->nBpair] = r->excl[e].atomI; r->bpJ[r->nBpair++] = r->excl[e].atomJ; }
+    for (int c = 0; c < r->nCons; c++)
+        if (r->cons[c].valid) { r->bpI[r->nBpair] = r->cons[c].atomI; r->bpJ[r->nBpair++] = r->cons[c].atomJ; }
+}
+
+static void freeMMFF(H_MMFF *m)
+{
+    for (int i = 0; i < m->nResi; i++)
+    {
+        H_RESI *r = &m->resi[i];
+        free(r->atoms); free(r->bonds); free(r->angles); free(r->tors); free(r->excl); free(r->cons); free(r->bpI); free(r->bpJ);
+    }
+    free(m->resi); free(m->typeID); free(m->typeName);
+}
+
+/* ---- atoms file (VARRECORDASCII, src/collection_read.c:86-170) ---------------------------------- */
+typedef struct { const char *name; int index; } NameIdx;
+static int cmpName(const void *a, const void *b) { return strcmp(((const NameIdx *)a)->name, ((const NameIdx *)b)->name); }
+
+static int readAtoms(const char *path, int64_t size, ddcb200_deck *d, NameIdx *sortedSpecies, int nspecies, int64_t *filled)
+{
+    FILE *f = fopen(path, "rb");
+    if (!f) return herr("cannot open atoms file %s", path);
+    fseek(f, 0, SEEK_END);
+    long sz = ftell(f);
+    fseek(f, 0, SEEK_SET);
+    char *text = (char *)malloc((size_t)sz + 1);
+    size_t got = fread(text, 1, (size_t)sz, f);
+    fclose(f);
+    text[got] = 0;
+    char *p = strchr(text, '}');
+    if (!p) { free(text); return herr("atoms file %s has no FILEHEADER", path); }
+    /* header checks: ASCII variable records with the standard field list */
+    {
+        ODB *hdb = odb_new();
+        char save = p[1];
+        p[1] = 0;
+        odb_compileString(hdb, text);
+        p[1] = save;
+        if (hdb->n > 0)
+        {
+            char *dt = NULL;
+            odb_getString(&hdb->obj[0], "datatype", &dt, "VARRECORDASCII");
+            int bad = strcmp(dt, "VARRECORDASCII") != 0 && strcmp(dt, "FIXRECORDASCII") != 0;
+            free(dt);
+            char **fn;
+            int nf = odb_getStrings(&hdb->obj[0], "field_names", &fn, "id class type group rx ry rz vx vy vz");
+            const char *want[10] = {"id", "class", "type", "group", "rx", "ry", "rz", "vx", "vy", "vz"};
+            if (nf < 10) bad = 1;
+            for (int i = 0; i < 10 && i < nf; i++) bad |= strcmp(fn[i], want[i]) != 0;
+            odb_freeStrings(fn, nf);
+            if (bad) { odb_free(hdb); free(text); return herr("atoms file %s: only ASCII records 'id class type group rx ry rz vx vy vz' are supported", path); }
+        }
+        odb_free(hdb);
+    }
+    p++;
+    const double lc = hu_convert(1.0, "l", NULL), tc = hu_convert(1.0, "t", NULL);
+    const double vc = lc / tc;   /* src/collection_read.c:94-96 */
+    int64_t i = *filled;
+    while (i < size)
+    {
+        while (*p && isspace((unsigned char)*p)) p++;
+        if (!*p) break;
+        char *end;
+        uint64_t gid = strtoull(p, &end, 10);
+        if (end == p) { free(text); return herr("atoms file %s: bad record %lld", path, (long long)i); }
+        p = end;
+        char cls[64], type[64], group[64];
+        int used = 0;
+        if (sscanf(p, "%63s %63s %63s%n", cls, type, group, &used) != 3) { free(text); return herr("atoms file %s: short record %lld", path, (long long)i); }
+        p += used;
+        NameIdx key = {type, 0};
+        NameIdx *hit = (NameIdx *)bsearch(&key, sortedSpecies, nspecies, sizeof(NameIdx), cmpName);
+        if (!hit) { free(text); return herr("atoms file %s: unknown species %s", path, type); }
+        double v[6];
+        for (int k = 0; k < 6; k++)
+        {
+            v[k] = strtod(p, &end);
+            if (end == p) { free(text); return herr("atoms file %s: bad number in record %lld", path, (long long)i); }
+            p = end;
+        }
+        while (*p && *p != '\n') p++;   /* ignore trailing fields (random state, group data) */
+        d->gid[i] = gid;
+        d->species[i] = hit->index;
+        d->rx[i] = lc * v[0]; d->ry[i] = lc * v[1]; d->rz[i] = lc * v[2];
+        d->vx[i] = vc * v[3]; d->vy[i] = vc * v[4]; d->vz[i] = vc * v[5];
+        i++;
+    }
+    *filled = i;
+    free(text);
+    return 0;
+}
+
+/* ---- helpers ------------------------------------------------------------------------------------ */
+static char *dirOf(const char *path)
+{
+    const char *s = strrchr(path, '/');
+    if (!s) return strdup(".");
+    size_t n = (size_t)(s - path);
+    char *d = (char *)malloc(n + 1);
+    memcpy(d, path, n);
+    d[n] = 0;
+    return d;
+}
+static char *joinPath(const char *dir, const char *file)
+{
+    if (file[0] == '/') return strdup(file);
+    size_t n = strlen(dir) + strlen(file) + 2;
+    char *p = (char *)malloc(n);
+    snprintf(p, n, "%s/%s", dir, file);
+    return p;
+}
+static double ljShift(double sigma, double eps, double rcut)
+{
+    /* CGLennardJones_setShift, src/bioMartini.c:840-848 */
+    double sr = sigma / rcut, s2 = sr * sr, s4 = s2 * s2, s6 = s4 * s2, s12 = s6 * s6;
+    return (-4.0 * eps * (s12 - s6));
+}
+
+typedef struct { uint64_t gid; int64_t idx; } GidIdx;
+static int cmpGid(const void *a, const void *b)
+{
+    uint64_t x = ((const GidIdx *)a)->gid, y = ((const GidIdx *)b)->gid;
+    return x < y ? -1 : (x > y ? 1 : 0);
+}
+
+void ddcb200_deckFree(ddcb200_deck *d)
+{
+    if (!d) return;
+    for (int i = 0; i < d->nspecies; i++) free(d->speciesName[i]);
+    free(d->speciesName); free(d->specLJ); free(d->specCharge); free(d->specMass); free(d->specMolType);
+    free(d->specResidue); free(d->specAtom); free(d->ljEps); free(d->ljSigma); free(d->ljShift);
+    free(d->molTypeNSpecies); free(d->molTypeResidue); free(d->molTypeOwnerOffset); free(d->bpairOffset); free(d->bpairI); free(d->bpairJ);
+    free(d->gid); free(d->species); free(d->rx); free(d->ry); free(d->rz); free(d->vx); free(d->vy); free(d->vz);
+    free(d->termKind); free(d->termIdx); free(d->termParm);
+    free(d->restrBead); free(d->restrFrac0); free(d->restrKb); free(d->restrFc);
+    free(d->molOffset); free(d->molBeads);
+    free(d);
+}
+
+#define FAIL(...) do { rc = herr(__VA_ARGS__); goto done; } while (0)
+
+int ddcb200_deckLoad(const char *objectFile, const char *restartFile, const char *simulateName, ddcb200_deck **out)
+{
+    int rc = 0;
+    hu_init();
+    if (!objectFile || !out) return herr("null argument");
+    ODB *db = odb_new();
+    ddcb200_deck *d = (ddcb200_deck *)calloc(1, sizeof(ddcb200_deck));
+    H_MMFF mm;
+    memset(&mm, 0, sizeof mm);
+    char *dir = dirOf(objectFile);
+    NameIdx *sorted = NULL;
+    GidIdx *order = NULL;
+    char **molNames = NULL;
+    int nMolNames = 0;
+
+    if (odb_compileFile(db, objectFile)) FAIL("%s", db->err);
+    {
+        char *rpath = restartFile ? strdup(restartFile) : joinPath(dir, "restart");
+        FILE *t = fopen(rpath, "rb");
+        if (t)
+        {
+            fclose(t);
+            if (odb_compileFile(db, rpath)) { free(rpath); FAIL("%s", db->err); }
+        }
+        else if (restartFile) { free(rpath); FAIL("cannot open restart file %s", restartFile); }
+        free(rpath);
+    }
+    const ODB_OBJECT *sim = odb_find(db, simulateName ? simulateName : "simulate", "SIMULATE");
+    if (!sim) FAIL("SIMULATE object %s not found", simulateName ? simulateName : "simulate");
+    char *sysName = NULL, *intName = NULL, *ddcName = NULL, *piName = NULL, *s = NULL;
+    odb_getString(sim, "system", &sysName, NULL);
+    odb_getString(sim, "integrator", &intName, NULL);
+    odb_getString(sim, "ddc", &ddcName, "ddc");
+    odb_getString(sim, "printinfo", &piName, "printinfo");
+    if (!sysName || !intName) FAIL("SIMULATE needs system and integrator keywords");
+    odb_getI64(sim, "loop", &d->loop, "0");
+    odb_getI64(sim, "maxloop", &d->maxloop, "0");
+    odb_getInts(sim, "printrate", &d->printrate, 1, "5");
+    odb_getInts(sim, "deltaloop", &d->deltaloop, 1, "-1");
+    odb_getInts(sim, "snapshotrate", &d->snapshotrate, 1, "100");
+    odb_getInts(sim, "checkpointrate", &d->checkpointrate, 1, "1000");
+    if (odb_getWithUnits(sim, "time", &d->time, 1, "0.0", "t", NULL) < 0) FAIL("bad time unit");
+    if (odb_getWithUnits(sim, "dt", &d->dt, 1, "1.0", "t", NULL) < 0) FAIL("bad dt unit");
+
+    /* INTEGRATOR: only NGLF (src/integrator.c:59-64); GROUPs: only FREE (src/group.c:78-82) */
+    const ODB_OBJECT *integ = odb_find(db, intName, "INTEGRATOR");
+    if (!integ) FAIL("INTEGRATOR %s not found", intName);
+    odb_getString(integ, "type", &s, "");
+    if (strcmp(s, "NGLF") != 0) { char t[64]; snprintf(t, 64, "%s", s); free(s); FAIL("INTEGRATOR type %s is not supported (only NGLF)", t); }
+    free(s);
+
+    const ODB_OBJECT *sys = odb_find(db, sysName, "SYSTEM");
+    if (!sys) FAIL("SYSTEM %s not found", sysName);
+    {
+        char **gn;
+        int ng = odb_getStrings(sys, "groups", &gn, NULL);
+        for (int g = 0; g < ng; g++)
+        {
+            const ODB_OBJECT *go = odb_find(db, gn[g], "GROUP");
+            if (!go) { odb_freeStrings(gn, ng); FAIL("GROUP %s not found", gn[g]); }
+            odb_getString(go, "type", &s, "");
+            int ok = strcmp(s, "FREE") == 0;
+            free(s);
+            if (!ok) { odb_freeStrings(gn, ng); FAIL("GROUP type other than FREE is not supported"); }
+        }
+        odb_freeStrings(gn, ng);
+    }
+    odb_getInts(sys, "nConstraints", &d->params.nConstraints, 1, "0");
+
+    /* BOX */
+    char *boxName = NULL, *nbrName = NULL, *colName = NULL, *mcName = NULL;
+    odb_getString(sys, "box", &boxName, NULL);
+    odb_getString(sys, "neighbor", &nbrName, NULL);
+    odb_getString(sys, "collection", &colName, NULL);
+    odb_getString(sys, "moleculeClass", &mcName, "NONE");
+    if (!boxName || !nbrName || !colName) FAIL("SYSTEM needs box, neighbor and collection");
+    const ODB_OBJECT *box = odb_find(db, boxName, "BOX");
+    if (!box) FAIL("BOX %s not found", boxName);
+    if (odb_getWithUnits(box, "h", d->params.h, 9, "1 0 0 0 1 0 0 0 1", "l", NULL) < 0) FAIL("bad box unit");
+    odb_getInts(box, odb_has(box, "bndcdn") ? "bndcdn" : "pbc", &d->params.pbc, 1, "7");
+    const ODB_OBJECT *nbr = odb_find(db, nbrName, "NEIGHBOR");
+    if (!nbr) FAIL("NEIGHBOR %s not found", nbrName);
+    if (odb_getWithUnits(nbr, "deltaR", &d->params.deltaR, 1, "0", "l", NULL) < 0) FAIL("bad deltaR unit");
+    if (odb_getWithUnits(nbr, "minBoxSide", &d->params.minBoxSide, 1, "0", "l", NULL) < 0) FAIL("bad minBoxSide unit");
+    const ODB_OBJECT *ddc = odb_find(db, ddcName, "DDC");
+    if (ddc)
+    {
+        odb_getInts(ddc, "updateRate", &d->params.updateRate, 1, "0");
+        odb_getInts(ddc, "lx", &d->ddc_lx, 1, "0");
+        odb_getInts(ddc, "ly", &d->ddc_ly, 1, "0");
+        odb_getInts(ddc, "lz", &d->ddc_lz, 1, "0");
+    }
+    if (d->params.updateRate <= 0) FAIL("DDC updateRate=0 (displacement-triggered rebuild) is not supported; set updateRate>0");
+    const ODB_OBJECT *pi = odb_find(db, piName, "PRINTINFO");
+    if (pi) odb_getInts(pi, "printMolecularPressure", &d->printMolecularPressure, 1, "0");
+
+    /* MOLECULECLASS -> MOLECULE -> SPECIES */
+    if (strcmp(mcName, "NONE") == 0) FAIL("SYSTEM without moleculeClass is not supported (Martini decks define one)");
+    const ODB_OBJECT *mc = odb_find(db, mcName, "MOLECULECLASS");
+    if (!mc) FAIL("MOLECULECLASS %s not found", mcName);
+    nMolNames = odb_getStrings(mc, "molecules", &molNames, NULL);
+    if (nMolNames <= 0) FAIL("MOLECULECLASS has no molecules");
+    d->nMolTypes = nMolNames;
+    d->molTypeNSpecies = (int *)calloc(nMolNames, sizeof(int));
+    d->molTypeResidue = (int *)calloc(nMolNames, sizeof(int));
+    d->molTypeOwnerOffset = (int *)calloc(nMolNames, sizeof(int));
+    int spCap = 0;
+    for (int m = 0; m < nMolNames; m++)
+    {
+        const ODB_OBJECT *mo = odb_find(db, molNames[m], "MOLECULE");
+        if (!mo) FAIL("MOLECULE %s not found", molNames[m]);
+        char **sn, *owner = NULL;
+        int ns = odb_getStrings(mo, "species", &sn, NULL);
+        if (ns <= 0) FAIL("MOLECULE %s has no species", molNames[m]);
+        odb_getString(mo, "ownershipSpecies", &owner, "$NONE$");
+        d->molTypeNSpecies[m] = ns;
+        d->molTypeOwnerOffset[m] = 0;
+        for (int k = 0; k < ns; k++)
+        {
+            const ODB_OBJECT *so = odb_find(db, sn[k], "SPECIES");
+            if (!so) FAIL("SPECIES %s not found", sn[k]);
+            if (d->nspecies == spCap)
+            {
+                spCap = spCap ? 2 * spCap : 64;
+                d->speciesName = (char **)realloc(d->speciesName, spCap * sizeof(char *));
+                d->specLJ = (int *)realloc(d->specLJ, spCap * sizeof(int));
+                d->specCharge = (double *)realloc(d->specCharge, spCap * sizeof(double));
+                d->specMass = (double *)realloc(d->specMass, spCap * sizeof(double));
+                d->specMolType = (int *)realloc(d->specMolType, spCap * sizeof(int));
+                d->specResidue = (int *)realloc(d->specResidue, spCap * sizeof(int));
+                d->specAtom = (int *)realloc(d->specAtom, spCap * sizeof(int));
+            }
+            const int idx = d->nspecies++;
+            d->speciesName[idx] = strdup(sn[k]);
+            d->specMolType[idx] = m;
+            if (odb_getWithUnits(so, "mass", &d->specMass[idx], 1, "1.0", "m", NULL) < 0) FAIL("bad mass unit in SPECIES %s", sn[k]);
+            if (odb_getWithUnits(so, "charge", &d->specCharge[idx], 1, "0.0", "i*t", NULL) < 0) FAIL("bad charge unit in SPECIES %s", sn[k]);
+            if (strcmp(sn[k], owner) == 0) d->molTypeOwnerOffset[m] = k;
+        }
+        free(owner);
+        odb_freeStrings(sn, ns);
+    }
+
+    /* POTENTIALs */
+    {
+        char **pn;
+        int np = odb_getStrings(sys, "potential", &pn, NULL);
+        int haveMartini = 0;
+        for (int k = 0; k < np; k++)
+        {
+            const ODB_OBJECT *po = odb_find(db, pn[k], "POTENTIAL");
+            if (!po) { odb_freeStrings(pn, np); FAIL("POTENTIAL %s not found", pn[k]); }
+            char *type = NULL, *parmfile = NULL;
+            odb_getString(po, "type", &type, "");
+            if (strcmp(type, "MARTINI") == 0)
+            {
+                haveMartini = 1;
+                odb_getString(po, "parmfile", &parmfile, "martini.data");
+                char *pp = joinPath(dir, parmfile);
+                int e = odb_compileFile(db, pp);
+                free(pp);
+                if (e) { free(type); free(parmfile); odb_freeStrings(pn, np); FAIL("%s", db->err); }
+                odb_getInts(po, "excludePotentialTerm", &d->excludePotentialTerm, 1, "0");
+                odb_getInts(po, "potential-shift", &d->potentialShift, 1, "1");
+                double cutoff;
+                if (odb_getWithUnits(po, "cutoff", &cutoff, 1, "11.0", "Angstrom", NULL) < 0 ||
+                    odb_getWithUnits(po, "rmax4all", &d->rmax4all, 1, "11.0", "Angstrom", NULL) < 0 ||
+                    odb_getWithUnits(po, "rcoulomb", &d->rcoulomb, 1, "11.0", "Angstrom", NULL) < 0)
+                { free(type); free(parmfile); odb_freeStrings(pn, np); FAIL("bad unit in POTENTIAL %s", pn[k]); }
+                odb_getDoubles(po, "epsilon_r", &d->epsilon_r, 1, "15.0");
+                odb_getDoubles(po, "epsilon_rf", &d->epsilon_rf, 1, "-1.0");
+                d->params.rmax = cutoff;
+                /* src/bioMartini.c:1234-1245 */
+                const double irc = 1.0 / d->rcoulomb, irc3 = irc * irc * irc;
+                if (d->epsilon_rf != -1.0)
+                {
+                    d->params.krf = (d->epsilon_rf - d->epsilon_r) / (2 * d->epsilon_rf + d->epsilon_r) * irc3;
+                    d->params.crf = 3 * (d->epsilon_rf) / (2 * d->epsilon_rf + d->epsilon_r) * irc;
+                }
+                else
+                {
+                    d->params.krf = 0.5 * irc3;
+                    d->params.crf = 1.5 * irc;
+                }
+                if (d->params.rmax > d->rmax4all) d->rmax4all = d->params.rmax;
+                if (d->rcoulomb > d->rmax4all) d->rmax4all = d->rcoulomb;
+                d->params.keR = hu_ke() / d->epsilon_r;
+            }
+            else if (strcmp(type, "RESTRAINT") == 0)
+            {
+                odb_getString(po, "parmfile", &parmfile, "restraint.data");
+                char *pp = joinPath(dir, parmfile);
+                int e = odb_compileFile(db, pp);
+                free(pp);
+                if (e) { free(type); free(parmfile); odb_freeStrings(pn, np); FAIL("%s", db->err); }
+            }
+            else
+            {
+                char t[64];
+                snprintf(t, 64, "%s", type);
+                free(type); free(parmfile); odb_freeStrings(pn, np);
+                FAIL("POTENTIAL type %s is not supported (MARTINI, RESTRAINT)", t);
+            }
+            free(type);
+            free(parmfile);
+        }
+        odb_freeStrings(pn, np);
+        if (!haveMartini) FAIL("no POTENTIAL of type MARTINI in SYSTEM");
+    }
+
+    /* MMFF (mmff_init, src/bioMMFF.c:236-273) */
+    {
+        const ODB_OBJECT *mo = odb_find(db, "martini", "MMFF");
+        if (!mo) FAIL("MMFF object 'martini' not found in the parmfile");
+        char **rn, **tn, **ln;
+        int nr = odb_getStrings(mo, "resiParms", &rn, NULL);
+        int nt = odb_getStrings(mo, "atomTypeList", &tn, NULL);
+        int nl = odb_getStrings(mo, "ljParms", &ln, NULL);
+        if (nr <= 0 || nt <= 0) FAIL("MMFF needs resiParms and atomTypeList");
+        mm.nResi = nr;
+        mm.resi = (H_RESI *)calloc(nr, sizeof(H_RESI));
+        for (int i = 0; i < nr; i++)
+        {
+            if (loadResi(db, rn[i], &mm.resi[i])) { rc = -1; goto done; }
+            buildBpairs(&mm.resi[i]);
+        }
+        mm.nTypes = nt;
+        mm.typeID = (int *)calloc(nt, sizeof(int));
+        mm.typeName = (char(*)[32])calloc(nt, 32);
+        for (int i = 0; i < nt; i++)
+        {
+            const ODB_OBJECT *to = odb_find(db, tn[i], "MASSPARMS");
+            if (!to) FAIL("MASSPARMS %s not found", tn[i]);
+            odb_getInts(to, "atomTypeID", &mm.typeID[i], 1, "0");
+            odb_getString(to, "atomType", &s, "NoType");
+            snprintf(mm.typeName[i], 32, "%s", s);
+            free(s);
+            if (mm.typeID[i] < 0 || mm.typeID[i] >= nt) FAIL("MASSPARMS %s: atomTypeID out of range", tn[i]);
+        }
+        d->ntypes = nt;
+        d->ljEps = (double *)calloc((size_t)nt * nt, sizeof(double));
+        d->ljSigma = (double *)calloc((size_t)nt * nt, sizeof(double));
+        d->ljShift = (double *)calloc((size_t)nt * nt, sizeof(double));
+        for (int k = 0; k < nt * nt; k++) d->ljSigma[k] = 1.0;
+        for (int i = 0; i < nl; i++)
+        {
+            const ODB_OBJECT *lo = odb_find(db, ln[i], "LJPARMS");
+            if (!lo) FAIL("LJPARMS %s not found", ln[i]);
+            int a, b;
+            double sigma, eps;
+            odb_getInts(lo, "indexI", &a, 1, "0");
+            odb_getInts(lo, "indexJ", &b, 1, "0");
+            if (odb_getWithUnits(lo, "sigma", &sigma, 1, "1.0", "nm", NULL) < 0 || odb_getWithUnits(lo, "eps", &eps, 1, "0.0", "kJ*mol^-1", NULL) < 0)
+                FAIL("bad unit in LJPARMS %s", ln[i]);
+            if (a < 0 || a >= nt || b < 0 || b >= nt) FAIL("LJPARMS %s: index out of range", ln[i]);
+            const double sh = d->potentialShift ? ljShift(sigma, eps, d->params.rmax) : 0.0;
+            d->ljEps[a + b * nt] = d->ljEps[b + a * nt] = eps;
+            d->ljSigma[a + b * nt] = d->ljSigma[b + a * nt] = sigma;
+            d->ljShift[a + b * nt] = d->ljShift[b + a * nt] = sh;
+        }
+        odb_freeStrings(rn, nr);
+        odb_freeStrings(tn, nt);
+        odb_freeStrings(ln, nl);
+    }
+
+    /* species -> residue / atom / LJ type (src/bioMartini.c:1274-1308, :952-987) */
+    for (int sp = 0; sp < d->nspecies; sp++)
+    {
+        const char *nm = d->speciesName[sp];
+        const char *x = strchr(nm, 'x');
+        if (!x) FAIL("species name %s is not of the form <RES>x<ATOM>", nm);
+        char res[64];
+        snprintf(res, sizeof res, "%.*s", (int)(x - nm), nm);
+        int ri = -1, ai = -1;
+        for (int r = 0; r < mm.nResi && ri < 0; r++)
+            if (strcmp(mm.resi[r].resName, res) == 0)
+                for (int a = 0; a < mm.resi[r].nAtoms; a++)
+                    if (strcmp(mm.resi[r].atoms[a].name, x + 1) == 0) { ri = r; ai = a; break; }
+        if (ri < 0) FAIL("species %s: no residue/atom in the MMFF", nm);
+        d->specResidue[sp] = ri;
+        d->specAtom[sp] = ai;
+        const int tid = mm.resi[ri].atoms[ai].typeID;
+        if (tid < 0 || tid >= mm.nTypes) FAIL("species %s: atomTypeID out of range", nm);
+        d->specLJ[sp] = mm.typeID[tid];   /* massParms[atomTypeID]->atmTypeID, src/bioMartini.c:634,980 */
+    }
+    /* molecule type -> residue of its ownership species (reOrgPairs, src/bioMartini.c:1416-1423) */
+    {
+        int base = 0, total = 0;
+        d->bpairOffset = (int *)calloc(d->nMolTypes + 1, sizeof(int));
+        for (int m = 0; m < d->nMolTypes; m++)
+        {
+            d->molTypeResidue[m] = d->specResidue[base + d->molTypeOwnerOffset[m]];
+            total += mm.resi[d->molTypeResidue[m]].nBpair;
+            base += d->molTypeNSpecies[m];
+        }
+        d->bpairI = (int *)calloc(total > 0 ? total : 1, sizeof(int));
+        d->bpairJ = (int *)calloc(total > 0 ? total : 1, sizeof(int));
+        int k = 0;
+        for (int m = 0; m < d->nMolTypes; m++)
+        {
+            d->bpairOffset[m] = k;
+            const H_RESI *r = &mm.resi[d->molTypeResidue[m]];
+            for (int b = 0; b < r->nBpair; b++) { d->bpairI[k] = r->bpI[b]; d->bpairJ[k++] = r->bpJ[b]; }
+        }
+        d->bpairOffset[d->nMolTypes] = k;
+    }
+
+    /* COLLECTION */
+    {
+        const ODB_OBJECT *co = odb_find(db, colName, "COLLECTION");
+        if (!co) FAIL("COLLECTION %s not found", colName);
+        int64_t size = 0;
+        odb_getI64(co, "size", &size, "0");
+        char *files = NULL;
+        odb_getString(co, "files", &files, NULL);
+        if (size <= 0 || !files) FAIL("COLLECTION needs size and files");
+        d->n = size;
+        d->gid = (uint64_t *)calloc(size, sizeof(uint64_t));
+        d->species = (int *)calloc(size, sizeof(int));
+        d->rx = (double *)calloc(size, sizeof(double)); d->ry = (double *)calloc(size, sizeof(double)); d->rz = (double *)calloc(size, sizeof(double));
+        d->vx = (double *)calloc(size, sizeof(double)); d->vy = (double *)calloc(size, sizeof(double)); d->vz = (double *)calloc(size, sizeof(double));
+        sorted = (NameIdx *)calloc(d->nspecies, sizeof(NameIdx));
+        for (int i = 0; i < d->nspecies; i++) { sorted[i].name = d->speciesName[i]; sorted[i].index = i; }
+        qsort(sorted, d->nspecies, sizeof(NameIdx), cmpName);
+        int64_t filled = 0;
+        for (int fi = 0; fi < 4096 && filled < size; fi++)
+        {
+            char fn[1024];
+            snprintf(fn, sizeof fn, "%s%06d", files, fi);
+            char *pp = joinPath(dir, fn);
+            FILE *t = fopen(pp, "rb");
+            if (!t) { free(pp); break; }
+            fclose(t);
+            int e = readAtoms(pp, size, d, sorted, d->nspecies, &filled);
+            free(pp);
+            if (e) { free(files); rc = -1; goto done; }
+        }
+        free(files);
+        if (filled != size) FAIL("COLLECTION size=%lld but %lld records were read", (long long)size, (long long)filled);
+    }
+
+    /* flatten bonded terms: walk residues in gid order (charmmResidues, src/bioCharmmCovalent.c:48-93) */
+    {
+        const int64_t n = d->n;
+        order = (GidIdx *)malloc((size_t)n * sizeof(GidIdx));
+        for (int64_t i = 0; i < n; i++) { order[i].gid = d->gid[i]; order[i].idx = i; }
+        qsort(order, (size_t)n, sizeof(GidIdx), cmpGid);
+        const uint64_t molResMask = 0xffffffffffff0000ull;
+        const int ex = d->excludePotentialTerm;
+        for (int pass = 0; pass < 2; pass++)
+        {
+            int64_t nt = 0, nm = 0, nmb = 0, nmt = 0;
+            for (int64_t a = 0; a < n;)
+            {
+                int64_t b = a;
+                while (b < n && (order[b].gid & molResMask) == (order[a].gid & molResMask)) b++;
+                const int sp0 = d->species[order[a].idx];
+                const int ri = d->specResidue[sp0];
+                const H_RESI *r = &mm.resi[ri];
+                if (b - a != r->nAtoms) FAIL("residue instance at gid %llu has %lld beads, template %s has %d (incomplete residues are not supported)",
+                                             (unsigned long long)order[a].gid, (long long)(b - a), r->resName, r->nAtoms);
+                for (int64_t k = a; k < b; k++)
+                {
+                    const int sp = d->species[order[k].idx];
+                    if (d->specResidue[sp] != ri || d->specAtom[sp] != (int)(k - a))
+                        FAIL("bead gid %llu: species %s is not atom %d of residue %s", (unsigned long long)order[k].gid, d->speciesName[sp], (int)(k - a), r->resName);
+                    if ((int)(order[k].gid & 0xffffull) != (int)(k - a))
+                        FAIL("bead gid %llu: low 16 bits must equal the atom offset %d in residue %s", (unsigned long long)order[k].gid, (int)(k - a), r->resName);
+                }
+#define BEAD(off) ((int)order[a + (off)].idx)
+#define CHECKOFF(off) do { if ((off) < 0 || (off) >= r->nAtoms) FAIL("term atom offset %d outside residue %s", (off), r->resName); } while (0)
+                if (!(ex & 1))
+                    for (int t = 0; t < r->nBonds; t++)
+                    {
+                        /* every bond in bondList is evaluated (resBondSorted loops the whole sorted list); Martini constraints
+                         * (func != 1 bonds are still harmonic here, as in genMartiniConn which copies all of bondList) */
+                        CHECKOFF(r->bonds[t].atomI); CHECKOFF(r->bonds[t].atomJ);
+                        if (pass)
+                        {
+                            /* sortBondList swaps so that atmI < atmJ (src/bioCharmmParms.c:2147-2190) */
+                            int ia = r->bonds[t].atomI, ja = r->bonds[t].atomJ;
+                            if (ia > ja) { int tmp = ia; ia = ja; ja = tmp; }
+                            d->termKind[nt] = 0;
+                            d->termIdx[4 * nt] = BEAD(ia); d->termIdx[4 * nt + 1] = BEAD(ja); d->termIdx[4 * nt + 2] = -1; d->termIdx[4 * nt + 3] = -1;
+                            d->termParm[3 * nt] = r->bonds[t].kb; d->termParm[3 * nt + 1] = r->bonds[t].b0; d->termParm[3 * nt + 2] = 0;
+                        }
+                        nt++;
+                    }
+                for (int t = 0; t < r->nAngles; t++)
+                {
+                    const H_ANGLE *h = &r->angles[t];
+                    int kind = h->func == 1 ? 1 : (h->func == 2 ? 2 : (h->func == 10 ? 3 : -1));
+                    if (kind < 0) continue;   /* genMartiniConn keeps only func 1, 2, 10 (src/bioMartini.c:662-754) */
+                    if ((kind == 1 && (ex & 2)) || (kind == 2 && (ex & 4)) || (kind == 3 && (ex & 256))) continue;
+                    CHECKOFF(h->atomI); CHECKOFF(h->atomJ); CHECKOFF(h->atomK);
+                    if (pass)
+                    {
+                        d->termKind[nt] = kind;
+                        d->termIdx[4 * nt] = BEAD(h->atomI); d->termIdx[4 * nt + 1] = BEAD(h->atomJ); d->termIdx[4 * nt + 2] = BEAD(h->atomK); d->termIdx[4 * nt + 3] = -1;
+                        d->termParm[3 * nt] = h->ktheta; d->termParm[3 * nt + 1] = h->theta0; d->termParm[3 * nt + 2] = 0;
+                    }
+                    nt++;
+                }
+                for (int t = 0; t < r->nTors; t++)
+                {
+                    const H_TORS *h = &r->tors[t];
+                    int kind = h->func == 1 ? 4 : (h->func == 2 ? 5 : -1);
+                    if (kind < 0) continue;
+                    if ((kind == 4 && (ex & 16)) || (kind == 5 && (ex & 32))) continue;
+                    CHECKOFF(h->atomI); CHECKOFF(h->atomJ); CHECKOFF(h->atomK); CHECKOFF(h->atomL);
+                    if (pass)
+                    {
+                        d->termKind[nt] = kind;
+                        d->termIdx[4 * nt] = BEAD(h->atomI); d->termIdx[4 * nt + 1] = BEAD(h->atomJ); d->termIdx[4 * nt + 2] = BEAD(h->atomK); d->termIdx[4 * nt + 3] = BEAD(h->atomL);
+                        d->termParm[3 * nt] = h->kchi; d->termParm[3 * nt + 1] = h->delta; d->termParm[3 * nt + 2] = (double)h->n;
+                    }
+                    nt++;
+                }
+                /* molecule bookkeeping (moleculeScanState, src/molecule.c:118-211): one molecule per (gid>>32) */
+                {
+                    const int mt = d->specMolType[sp0];
+                    const int ownerOff = d->molTypeOwnerOffset[mt];
+                    nmt++;   /* every residue instance holds its molecule's ownership bead in a Martini deck */
+                    if (d->molTypeNSpecies[mt] > 1)
+                    {
+                        if (pass)
+                        {
+                            d->molOffset[nm] = nmb;
+                            d->molBeads[nmb] = BEAD(ownerOff);
+                            int64_t w = nmb + 1;
+                            for (int k = 0; k < r->nAtoms; k++)
+                                if (k != ownerOff) d->molBeads[w++] = BEAD(k);
+                        }
+                        nm++;
+                        nmb += r->nAtoms;
+                    }
+                }
+                a = b;
+            }
+            if (!pass)
+            {
+                d->nTerms = nt;
+                d->termKind = (int *)calloc(nt > 0 ? nt : 1, sizeof(int));
+                d->termIdx = (int *)calloc(nt > 0 ? 4 * nt : 1, sizeof(int));
+                d->termParm = (double *)calloc(nt > 0 ? 3 * nt : 1, sizeof(double));
+                d->nMol = nm;
+                d->nMolTotal = nmt;
+                d->molOffset = (int64_t *)calloc(nm + 1, sizeof(int64_t));
+                d->molBeads = (int *)calloc(nmb > 0 ? nmb : 1, sizeof(int));
+            }
+            else d->molOffset[nm] = nmb;
+        }
+    }
+
+    /* RESTRAINTLIST (src/restraint.c:25-80,164-198) */
+    {
+        const ODB_OBJECT *ro = odb_find(db, "restraint", "RESTRAINTLIST");
+        if (ro)
+        {
+            odb_getInts(ro, "origin", &d->restrOrigin, 1, "0");
+            char **rn;
+            int nr = odb_getStrings(ro, "restraintList", &rn, NULL);
+            d->restrBead = (int *)calloc(nr > 0 ? nr : 1, sizeof(int));
+            d->restrFrac0 = (double *)calloc(nr > 0 ? 3 * nr : 1, sizeof(double));
+            d->restrKb = (double *)calloc(nr > 0 ? nr : 1, sizeof(double));
+            d->restrFc = (double *)calloc(nr > 0 ? 3 * nr : 1, sizeof(double));
+            int64_t k = 0;
+            for (int i = 0; i < nr; i++)
+            {
+                const ODB_OBJECT *po = odb_find(db, rn[i], "RESTRAINTPARMS");
+                if (!po) { odb_freeStrings(rn, nr); FAIL("RESTRAINTPARMS %s not found", rn[i]); }
+                int64_t gid = 0;
+                odb_getI64(po, "gid", &gid, "0");
+                GidIdx key = {(uint64_t)gid, 0};
+                GidIdx *hit = (GidIdx *)bsearch(&key, order, (size_t)d->n, sizeof(GidIdx), cmpGid);
+                if (!hit) continue;   /* restraintMap stays -1: no bead with that gid */
+                d->restrBead[k] = (int)hit->idx;
+                int fc[3];
+                odb_getInts(po, "fcx", &fc[0], 1, "0");
+                odb_getInts(po, "fcy", &fc[1], 1, "0");
+                odb_getInts(po, "fcz", &fc[2], 1, "0");
+                odb_getDoubles(po, "x0", &d->restrFrac0[3 * k], 1, "0");
+                odb_getDoubles(po, "y0", &d->restrFrac0[3 * k + 1], 1, "0");
+                odb_getDoubles(po, "z0", &d->restrFrac0[3 * k + 2], 1, "0");
+                for (int a = 0; a < 3; a++) d->restrFc[3 * k + a] = fc[a];
+                if (odb_getWithUnits(po, "kb", &d->restrKb[k], 1, "0.0", "kJ*mol^-1*nm^-2", NULL) < 0) { odb_freeStrings(rn, nr); FAIL("bad kb unit in %s", rn[i]); }
+                k++;
+            }
+            d->nRestraints = k;
+            odb_freeStrings(rn, nr);
+        }
+    }
+
+    d->kB = hu_kB();
+    d->ke = hu_ke();
+    d->lengthPerAngstrom = hu_convert(1.0, "Angstrom", NULL);
+    d->energyPerKJmol = hu_convert(1.0, "kJ/mol", NULL);
+    d->massPerAmu = hu_convert(1.0, "amu", NULL);
+    d->pressurePerBar = hu_convert(1.0, "bar", NULL);
+    d->timePerFs = hu_convert(1.0, "fs", NULL);
+    d->params.center[0] = d->params.center[1] = d->params.center[2] = 0.0;
+    d->params.device = 0;
+
+done:
+    free(sysName); free(intName); free(ddcName); free(piName);
+    free(boxName); free(nbrName); free(colName); free(mcName);
+    odb_freeStrings(molNames, nMolNames);
+    free(sorted);
+    free(order);
+    free(dir);
+    freeMMFF(&mm);
+    odb_free(db);
+    if (rc)
+    {
+        ddcb200_deckFree(d);
+        return rc;
+    }
+    *out = d;
+    return 0;
+}
+
+int ddcb200_simulateBind(const ddcb200_deck *d, int device, ddcb200_ctx **out)
+{
+    if (!d || !out) return herr("null argument");
+    ddcb200_params p = d->params;
+    p.device = device;
+    ddcb200_ctx *c = NULL;
+    int rc = ddcb200_create(&p, &c);
+    if (rc) return herr("ddcb200_create: %s", ddcb200_lastError());
+#define TRY(call) do { rc = (call); if (rc) { herr(#call ": %s", ddcb200_lastError()); ddcb200_destroy(c); return rc; } } while (0)
+    TRY(ddcb200_martiniNonBondParms(c, d->ntypes, d->ljEps, d->ljSigma, d->ljShift));
+    TRY(ddcb200_setSpecies(c, d->nspecies, d->specLJ, d->specCharge, d->specMass));
+    if ((d->excludePotentialTerm & 128) != 0) { herr("excludePotentialTerm nonBondMask is not supported"); ddcb200_destroy(c); return -1; }
+    TRY(ddcb200_setExclusions(c, d->nMolTypes, d->specMolType, d->molTypeNSpecies, d->bpairOffset, d->bpairI, d->bpairJ));
+    TRY(ddcb200_setBeads(c, d->n, d->gid, d->species));
+    TRY(ddcb200_martiniBondParms(c, d->nTerms, d->termKind, d->termIdx, d->termParm));
+    TRY(ddcb200_setRestraints(c, d->nRestraints, d->restrBead, d->restrFrac0, d->restrKb, d->restrFc, d->restrOrigin));
+    TRY(ddcb200_setMolecules(c, d->nMol, d->molOffset, d->molBeads, d->nMolTotal));
+    TRY(ddcb200_sendState(c, d->n, NULL, d->rx, d->ry, d->rz, d->vx, d->vy, d->vz, d->loop, d->time));
+#undef TRY
+    *out = c;
+    return 0;
+}
+
+int ddcb200_printinfoLine(const ddcb200_deck *d, const ddcb200_etype *e, char *buf, size_t len)
+{
+    /* printinfoA, src/printinfo.c:125-232 with PRINTINFO units ns / kJ/mol / K / bar / Ang^3 / Ang */
+    const double n = e->number;
+    const double cE = hu_convert(1.0, NULL, "kJ/mol"), cT = hu_convert(1.0, NULL, "K"), cP = hu_convert(1.0, NULL, "bar");
+    const double cV = hu_convert(1.0, NULL, "Ang^3"), cL = hu_convert(1.0, NULL, "Ang"), ct = hu_convert(1.0, NULL, "ns");
+    const double pressure = d->printMolecularPressure ? e->pMolecular : e->pion;
+    return snprintf(buf, len, "%012lld %16.6f %18.12f %18.12f %18.12f %18.8f %18.12f %18.12f %15.8f %15.8f %15.8f",
+                    (long long)e->loop, ct * e->time, cE * ((e->eion + e->rk) / n), cE * (e->rk / n), cE * (e->eion / n),
+                    cT * e->temperature, cP * pressure, cV * e->volume / n, cL * d->params.h[0], cL * d->params.h[4], cL * d->params.h[8]);
+}

@@ -1,0 +1,144 @@
+// pair.cuh - Martini non-bonded pair force: shifted Lennard-Jones + reaction-field Coulomb,
+// with the reaction-field-only treatment of pruned (excluded) intramolecular pairs.
+//
+// Replaces martiniNonBond + martiniIntraMoleReaction (src/bioMartini.c:989-1208) and
+// nlistGPU.cu's evalList5.  One thread per bead walks its full (both-direction) list, so
+// forces need no atomics and the summation order is fixed: results are bitwise
+// reproducible run to run.  Energies and the virial are halved per visit.
+//
+// fp64 throughout.  The summation order differs from the CPU path's linked-list order, so
+// parity is to tolerance (forces 1e-6, energy 1e-9 relative), not bitwise.
+#pragma once
+#include "engine.cuh"
+
+template <bool ENERGY>
+__global__ void __launch_bounds__(TILE)
+k_pair(int nLocal, int nPad, const double4 *__restrict__ pos, const uint32_t *__restrict__ nbr, const int *__restrict__ count,
+       const double2 *__restrict__ ljTab, const double *__restrict__ shiftTab, const double *__restrict__ qTab, PairConst pc,
+       double *__restrict__ fx, double *__restrict__ fy, double *__restrict__ fz, double *__restrict__ accPartial)
+{
+    extern __shared__ double2 sLJ[];           // ntypes*ntypes {c6,c12}
+    double *sQ = (double *)(sLJ + pc.ntypes * pc.ntypes);   // 256 charges
+    double *sShift = sQ + 256;                              // ntypes*ntypes, ENERGY only
+    for (int k = threadIdx.x; k < pc.ntypes * pc.ntypes; k += blockDim.x)
+    {
+        sLJ[k] = ljTab[k];
+        if (ENERGY) sShift[k] = shiftTab[k];
+    }
+    for (int k = threadIdx.x; k < 256; k += blockDim.x) sQ[k] = qTab[k];
+    __syncthreads();
+
+    const int i = blockIdx.x * TILE + threadIdx.x;
+    const bool live = i < nLocal;
+    const int ii = live ? i : 0;
+    const double4 pi = pos[ii];
+    const uint64_t wi = (uint64_t)__double_as_longlong(pi.w);
+    const int ti = (int)(wi & 0xff);
+    const double qi = sQ[(wi >> 8) & 0xff];
+    const double kqi = pc.keR * qi;
+    const double2 *ljRow = sLJ + ti * pc.ntypes;
+    int n = live ? count[ii] : 0;
+    int nmax = n;
+    for (int o = 16; o > 0; o >>= 1) nmax = max(nmax, __shfl_xor_sync(0xffffffffu, nmax, o));
+
+    double fxi = 0.0, fyi = 0.0, fzi = 0.0;
+    double eLJ = 0.0, eEle = 0.0, vxx = 0.0, vyy = 0.0, vzz = 0.0, vxy = 0.0, vxz = 0.0, vyz = 0.0;
+
+    const uint32_t *row = nbr + ii;
+    uint32_t eNext = (0 < n) ? row[0] : 0u;
+    for (int k = 0; k < nmax; k++)
+    {
+        const uint32_t e = eNext;
+        if (k + 1 < n) eNext = row[(size_t)(k + 1) * nPad];
+        const bool valid = k < n;
+        const int j = valid ? (int)(e & 0x07ffffffu) : ii;
+        const double4 pj = pos[j];
+        double x = pi.x - pj.x, y = pi.y - pj.y, z = pi.z - pj.z;
+        double r2 = x * x + y * y + z * z;
+        if (r2 > pc.R2cut)
+        {
+            // nearestImage_fast: one lattice reduction per component (src/preduce.c:147-160)
+            if (x > pc.hhx) x -= pc.hxx;
+            if (x < -pc.hhx) x += pc.hxx;
+            if (y > pc.hhy) y -= pc.hyy;
+            if (y < -pc.hhy) y += pc.hyy;
+            if (z > pc.hhz) z -= pc.hzz;
+            if (z < -pc.hhz) z += pc.hzz;
+            r2 = x * x + y * y + z * z;
+        }
+        const bool in = valid && (r2 < pc.rc2);
+        if (__any_sync(0xffffffffu, in))
+        {
+            const uint64_t wj = (uint64_t)__double_as_longlong(pj.w);
+            const bool excl = (e & EXCL_BIT) != 0u;
+            const double kqij = kqi * sQ[(wj >> 8) & 0xff];
+            const double r2s = in ? r2 : 1.0;
+            double dvdr, vlj = 0.0, vele = 0.0;
+            const double ir2 = 1.0 / r2s;
+            {
+                // Lennard-Jones: 4 eps (s12 - s6) + shift ; dvdr = 24 eps (s6 - 2 s12)/r^2 (src/bioMartini.c:1073-1080)
+                const double2 cc = ljRow[wj & 0xff];
+                const double ir6 = ir2 * ir2 * ir2;
+                const double a6 = excl ? 0.0 : cc.x * ir6;
+                const double a12 = excl ? 0.0 : cc.y * ir6 * ir6;
+                dvdr = 6.0 * (a6 - 2.0 * a12) * ir2;
+                if (ENERGY) vlj = excl ? 0.0 : (a12 - a6) + sShift[ti * pc.ntypes + (int)(wj & 0xff)];
+            }
+            if (__any_sync(0xffffffffu, in && kqij != 0.0))
+            {
+                // reaction field (src/bioMartini.c:1082-1085); pruned pairs keep only krf r^2 - crf (:1172-1174)
+                const double ir = excl ? 0.0 : sqrt(ir2);
+                dvdr += kqij * (2.0 * pc.krf - ir2 * ir);
+                if (ENERGY) vele = kqij * (ir + pc.krf * r2s - pc.crf);
+            }
+            if (!in)
+            {
+                dvdr = 0.0;
+                vlj = 0.0;
+                vele = 0.0;
+            }
+            const double fxij = -dvdr * x, fyij = -dvdr * y, fzij = -dvdr * z;
+            fxi += fxij;
+            fyi += fyij;
+            fzi += fzij;
+            if (ENERGY)
+            {
+                eLJ += vlj;
+                eEle += vele;
+                vxx += fxij * x;
+                vyy += fyij * y;
+                vzz += fzij * z;
+                vxy += fxij * y;
+                vxz += fxij * z;
+                vyz += fyij * z;
+            }
+        }
+    }
+    if (live)
+    {
+        fx[i] = fxi;
+        fy[i] = fyi;
+        fz[i] = fzi;
+    }
+    if (ENERGY)
+    {
+        // every pair is visited from both ends: halve.  Self term -0.5 q_i^2 keR crf (src/bioMartini.c:1031-1035)
+        double v[8] = {0.5 * eLJ, 0.5 * eEle + (live ? -0.5 * qi * qi * pc.keR * pc.crf : 0.0),
+                       0.5 * vxx, 0.5 * vyy, 0.5 * vzz, 0.5 * vxy, 0.5 * vxz, 0.5 * vyz};
+        __shared__ double red[8][TILE / 32];
+#pragma unroll
+        for (int a = 0; a < 8; a++)
+        {
+            double t = v[a];
+            for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+            if ((threadIdx.x & 31) == 0) red[a][threadIdx.x >> 5] = t;
+        }
+        __syncthreads();
+        if (threadIdx.x < 8)
+        {
+            double t = 0.0;
+            for (int w = 0; w < TILE / 32; w++) t += red[threadIdx.x][w];
+            accPartial[(size_t)blockIdx.x * 8 + threadIdx.x] = t;
+        }
+    }
+}

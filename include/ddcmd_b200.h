@@ -1,0 +1,175 @@
+/* ddcmd_b200.h - C-ABI of the B200-native Martini MD step (drop-in for ddcMD's GPU seam).
+ *
+ * Every entry point is extern "C", takes plain pointers and sizes, and returns an int
+ * status (0 = ok, <0 = error; text via ddcb200_lastError()).  No CPU fallback exists:
+ * every compute entry point fails with DDCB200_ERR_NODEVICE when no sm_100 device is
+ * usable.  All floating point is fp64 in ddcMD internal units (bohr, fs, Rydberg-ish
+ * energy, src/ddcMD.c:71); host arrays are in the caller's bead
+ * order ("input order", the order of STATE arrays, src/state.h:7-27).
+ *
+ * Each function cites the reference interface it replaces.  INTEGRATION.md shows the
+ * few lines a ddcMD maintainer adds to martini_parms()/nglf_parms() to bind them.
+ */
+#ifndef DDCMD_B200_H
+#define DDCMD_B200_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DDCB200_OK 0
+#define DDCB200_ERR_ARG (-1)
+#define DDCB200_ERR_NODEVICE (-2)
+#define DDCB200_ERR_CUDA (-3)
+#define DDCB200_ERR_STATE (-4)
+#define DDCB200_ERR_CAPACITY (-5)
+#define DDCB200_ERR_NCCL (-6)
+
+typedef struct ddcb200_ctx ddcb200_ctx;
+
+/* Box, neighbor and non-bonded constants.
+ * Replaces: BOX{h,pbc} (src/box.c:50-87), NEIGHBOR{deltaR,minBoxSide} (src/neighbor.c:50-54),
+ * DDC{updateRate} (src/ddc.c:61-117), and the CHARMMPOT_PARMS scalars filled by
+ * martini_parms (src/bioMartini.c:1210-1245): rmax, krf, crf, ke/epsilon_r. */
+typedef struct ddcb200_params
+{
+    double h[9];          /* box matrix, row major xx xy xz yx .. zz; must be orthorhombic */
+    int pbc;              /* boundary bits, only 7 (xyz periodic) is supported */
+    int updateRate;       /* DDC updateRate: rebuild cells+lists when loop % updateRate == 0 */
+    double rmax;          /* potential cutoff (POTENTIAL cutoff, 11 Angstrom) */
+    double deltaR;        /* NEIGHBOR deltaR (skin) */
+    double minBoxSide;    /* NEIGHBOR minBoxSide */
+    double keR;           /* ke / epsilon_r */
+    double krf, crf;      /* reaction-field constants */
+    double center[3];     /* domain centre used by GeomBox (src/geom.c:335-340); 0 for one domain */
+    int nConstraints;     /* SYSTEM nConstraints (temperature denominator, src/energyInfo.c:112) */
+    int device;           /* CUDA device ordinal */
+} ddcb200_params;
+
+/* ETYPE subset (src/energyInfo.h:18-40) after eval_energyInfo (src/energyInfo.c:75-148),
+ * plus bioEnergies-style term sums and the molecular-pressure tensor
+ * (src/molecularPressure.c:22-67, src/printinfo.c:233-240). Symmetric tensors: xx yy zz xy xz yz. */
+typedef struct ddcb200_etype
+{
+    double eion;            /* potential energy */
+    double rk;              /* kinetic energy */
+    double virial[6];
+    double tion[6];         /* sum m v_a v_b */
+    double sion[6];         /* -(virial+tion)/V */
+    double pion;            /* -tr(sion)/3 */
+    double temperature;     /* 2 rk / (3 N - nConstraints), internal units */
+    double number;          /* beads */
+    double volume;
+    double eLJ, eEle, eBond, eAngle, eTorsion, eImproper, eRestraint;
+    double molVirial[3];    /* virial diag after molecular correction */
+    double molPressure[3];  /* (molVirial + Nmol kB T)/V, diag */
+    double pMolecular;      /* trace/3 of the above */
+    int64_t loop;
+    double time;
+    int64_t nMolecules;
+    int64_t nPairsListed;   /* half-list pair count, == nbr->npairs of the reference */
+} ddcb200_etype;
+
+const char *ddcb200_lastError(void);
+int ddcb200_deviceCount(void);
+
+/* Replaces accelerator_init + allocSendGPUState/allocGPUBoxInfo (src/accelerator.c:21,
+ * src/system.c:183-184). */
+int ddcb200_create(const ddcb200_params *p, ddcb200_ctx **out);
+void ddcb200_destroy(ddcb200_ctx *ctx);
+int ddcb200_sync(ddcb200_ctx *ctx);
+
+/* Replaces martiniNonBondGPUParms (src/bioMartiniGPU.h:8; table built by martiniLJ_parms,
+ * src/bioMartini.c:868-950).  eps/sigma/shift are ntypes*ntypes, symmetric. */
+int ddcb200_martiniNonBondParms(ddcb200_ctx *ctx, int ntypes, const double *eps, const double *sigma, const double *shift);
+
+/* Per-species constants (SPECIES objects + getCGLJindexbySpecie, src/bioMartini.c:952-987):
+ * LJ type, charge, mass, and the molecule type of each species. */
+int ddcb200_setSpecies(ddcb200_ctx *ctx, int nspecies, const int *ljType, const double *charge, const double *mass);
+
+/* Static per-bead identity, in input order: gid label (src/bioGid.h:13-23) and species
+ * index.  nGlobal beads in total (all ranks hold the full static table). */
+int ddcb200_setBeads(ddcb200_ctx *ctx, int64_t nGlobal, const uint64_t *gid, const int *species);
+
+/* Exclusion ("bpair") tables consumed by the list build, replacing reOrgPairs
+ * (src/bioMartini.c:1392-1485): for every bead the index of its molecule type, and per
+ * molecule type either "single species" (all intra-molecule pairs pruned) or a list of
+ * (atomI, atomJ) keys built by genMartiniBondPair (src/bioMartini.c:135-282).
+ * bpairOffset has nMolTypes+1 entries into bpairI/bpairJ. */
+int ddcb200_setExclusions(ddcb200_ctx *ctx, int nMolTypes, const int *molTypeOfSpecies, const int *molTypeNSpecies,
+                          const int *bpairOffset, const int *bpairI, const int *bpairJ);
+
+/* Replaces martiniBondGPUParms (src/bioMartiniGPU.h:9): flattened bonded terms, bead
+ * indices in input order.  kind: 0 bond kb(b-b0)^2 (resBondSorted), 1 harmonic angle,
+ * 2 cosine angle, 3 restricted-bending angle, 4 proper torsion, 5 improper
+ * (src/bioCharmmCovalentEnergiesSorted.c).  idx is 4 ints per term (unused = -1);
+ * parm is 3 doubles per term: (k, x0, n). */
+int ddcb200_martiniBondParms(ddcb200_ctx *ctx, int64_t nTerms, const int *kind, const int *idx, const double *parm);
+
+/* Position restraints (src/restraint.c:259-361): bead index, fractional reference point
+ * (x0,y0,z0 of RESTRAINTPARMS, scaled by the box edge at evaluation time; origin==0 shifts by
+ * -L/2 as the reference does), kb, and per-axis factors fc (3 per restraint). */
+int ddcb200_setRestraints(ddcb200_ctx *ctx, int64_t n, const int *bead, const double *frac0, const double *kb, const double *fc,
+                          int origin);
+
+/* Molecule membership for the molecular virial (moleculeScanState, src/molecule.c:118-211):
+ * molOffset has nMol+1 entries into molBeads (bead indices, input order); only
+ * multi-bead molecules need to be listed.  nMolTotal counts every molecule. */
+int ddcb200_setMolecules(ddcb200_ctx *ctx, int64_t nMol, const int64_t *molOffset, const int *molBeads, int64_t nMolTotal);
+
+/* Replaces sendGPUState + sendForceVelocityToGPU (src/gpuMemUtils.h:19-29): positions and
+ * velocities of the nLocal beads this context owns; bead[] gives their input-order index
+ * (NULL = 0..nLocal-1). */
+int ddcb200_sendState(ddcb200_ctx *ctx, int64_t nLocal, const int *bead, const double *rx, const double *ry, const double *rz,
+                      const double *vx, const double *vy, const double *vz, int64_t loop, double time);
+
+/* Replaces sendPosnToHost / sendForceVelocityToHost.  Any pointer may be NULL.  Output is
+ * ordered like the bead[] array returned by ddcb200_getLocalBeads (for one context that
+ * never migrates beads: the order given to sendState). */
+int64_t ddcb200_numLocal(ddcb200_ctx *ctx);
+int ddcb200_getLocalBeads(ddcb200_ctx *ctx, int *bead);
+int ddcb200_getState(ddcb200_ctx *ctx, double *rx, double *ry, double *rz, double *vx, double *vy, double *vz,
+                     double *fx, double *fy, double *fz);
+
+/* Replaces constructList(SYSTEM*, double rcut) (src/nlistGPU.h:184) = GeomBox + pairlist1 +
+ * reOrgPairs of the CPU path (src/geom.c:311-383, src/pairlist.c:205-314). */
+int ddcb200_constructList(ddcb200_ctx *ctx);
+
+/* Replaces ddcenergy(ddc, sys, e_eval_flag) with eval_potential = martiniGPU1
+ * (src/ddcenergy.c:160-238, src/bioMartini.cu:146): rebuilds the list when due, zeroes and
+ * evaluates non-bonded + bonded (+restraint) forces at the current positions.
+ * withEnergy != 0 also accumulates energies and the virial. */
+int ddcb200_ddcenergy(ddcb200_ctx *ctx, int withEnergy);
+
+/* Replaces nglfGPU / nglf (src/nglfGPU.h:16, src/nglf.c:67-112) called nsteps times:
+ * velocity-Verlet with the FREE group update (src/free.c:13-28); the last step is an
+ * energy step so ddcb200_energyInfo is valid afterwards. */
+int ddcb200_nglf(ddcb200_ctx *ctx, int nsteps, double dt);
+
+/* Replaces sendForceEnergyToHost + kinetic_terms + eval_energyInfo
+ * (src/pairProcessGPU.cu:1556, src/energy.c:48-163, src/energyInfo.c:75-148) and
+ * molecularPressure (src/molecularPressure.c:57-67). kB in internal units. */
+int ddcb200_energyInfo(ddcb200_ctx *ctx, double kB, ddcb200_etype *out);
+
+/* Parity hooks: cell index of every local bead in the reference's GeomBox numbering
+ * (src/geom.c:386-454), the grid {nx,ny,nz}, geom = {min[3], max[3], d[3]} in normalised
+ * coordinates; and the half list as (beadI, beadJ, pruned) triples with gid_I < gid_J. */
+int ddcb200_getCells(ddcb200_ctx *ctx, int *cellOfBead, int dims[3], double geom[9]);
+int64_t ddcb200_getPairs(ddcb200_ctx *ctx, int64_t capacity, int *beadI, int *beadJ, int *pruned);
+
+/* Timing aid for bench.py: device time (ms) spent in each kernel family since the last
+ * reset, measured with CUDA events on the launching stream when profiling is enabled.
+ * slots: 0 integrate, 1 pair, 2 bonded, 3 list build, 4 reductions, 5 halo. */
+int ddcb200_profile(ddcb200_ctx *ctx, int enable);
+int ddcb200_profileRead(ddcb200_ctx *ctx, double ms[8], int64_t launches[8], int reset);
+
+/* ---- multi-GPU (ddc-style spatial decomposition, src/ddcUpdate.c, src/ddcAssignment.c) ---- */
+int ddcb200_ncclUniqueId(unsigned char id[128]);
+int ddcb200_ddcInit(ddcb200_ctx *ctx, int rank, int nranks, int lx, int ly, int lz, const unsigned char id[128]);
+
+#ifdef __cplusplus
+}
+#endif
+#endif
