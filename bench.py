@@ -1,0 +1,243 @@
+#!/usr/bin/env python
+"""bench.py - Martini MD steps/s on B200 (BASELINE.json metric), one JSON line on stdout.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload NAME]
+
+A "step" is one nglf velocity-Verlet MD step (dt = 20 fs) of the synthetic Martini membrane
+named in config.workload: list rebuild every 20 steps, non-bonded + bonded forces,
+integrate.  `value` = steps/s with the state resident in HBM, timed with CUDA events on the
+stream the kernels are launched on; `e2e` = the same through the reference-facing call
+sequence with HOST buffers (sendState H2D from pinned memory, then nglf(1) + energyInfo D2H
+every step = the shipped deck's printrate=1, then getState D2H).  The `roofline` object is
+for the dominant kernel (k_pair); `cpu_baseline` times the UNMODIFIED reference CPU path
+(oracle/_ref) on a bounded sample of the same membrane.
+
+--impl reference times only the reference CPU path (no GPU work).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+DT_FS = 20.0
+DECK_CACHE = os.environ.get("DDCB200_DECK_CACHE", "/tmp/ddcb200_decks")
+CPU_SAMPLE = dict(lx=400.0, ly=400.0, lz=130.0, seed=3)     # ~140k beads of the same membrane recipe
+
+
+def log(*a):
+    print(*a, file=sys.stderr, flush=True)
+
+
+def get_deck(name, kwargs=None):
+    from ddcmd_b200 import synth
+    path = os.path.join(DECK_CACHE, name)
+    if not os.path.exists(os.path.join(path, "snapshot.mem", "atoms#000000")):
+        t = time.time()
+        s = synth.make_membrane(**kwargs) if kwargs else synth.make(name)
+        s.write_deck(path)
+        log("[bench] generated deck %s: %d beads in %.1fs" % (name, s.n, time.time() - t))
+    return path
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
+
+    def __init__(self, device=0):
+        super().__init__(daemon=True)
+        self.device = device
+        self.samples = []
+        self.stop_flag = False
+        self.proc = None
+
+    def run(self):
+        q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.device), "--query-gpu=" + q, "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            for line in self.proc.stdout:
+                if self.stop_flag:
+                    break
+                self.samples.append([x.strip() for x in line.split(",")])
+        except Exception:
+            pass
+
+    def finish(self):
+        self.stop_flag = True
+        if self.proc:
+            self.proc.terminate()
+        sm, mx, reasons = [], 0.0, set()
+        for s in self.samples:
+            try:
+                sm.append(float(s[1]))
+                mx = max(mx, float(s[2]))
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), s[4:8]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+            except Exception:
+                pass
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx or None, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        return json.load(open(p)).get("hbm_gbs", 6650.0), "measured"
+    return 6650.0, "fallback"
+
+
+def run_reference(workload_n, steps, warmup):
+    """Reference CPU path (oracle/_ref/ref_dump = the unmodified ddcMD objects) on the bounded sample."""
+    ref = os.path.join(ROOT, "oracle", "_ref", "ref_dump")
+    if not os.path.exists(ref):
+        raise RuntimeError("oracle/_ref/ref_dump is missing (run oracle/build_ref.sh in the build container)")
+    from refdump import read_records
+    path = get_deck("cpu_sample", CPU_SAMPLE)
+    out = os.path.join(path, "_bench.bin")
+    n_steps = max(2, steps + warmup)
+    t = time.time()
+    subprocess.check_call(["bash", "-c", "ulimit -s unlimited; exec '%s' '%s' %d 0 light" % (ref, out, n_steps)], cwd=path,
+                          stdout=open(os.path.join(path, "_bench.log"), "w"), stderr=subprocess.STDOUT)
+    wall_total = time.time() - t
+    r = read_records(out)
+    wall = r["wall"]
+    n_sample = int(r["nion"][0])
+    w = min(warmup, len(wall) - 1)
+    t_timed = wall[-1] - (wall[w - 1] if w > 0 else 0.0)
+    k = len(wall) - w
+    sps_sample = k / t_timed
+    return {"steps_per_s_sample": sps_sample, "n_sample": n_sample, "steps_timed": k, "wall_total_s": wall_total,
+            "value": sps_sample * n_sample / workload_n, "us_per_bead_step": 1e6 * t_timed / k / n_sample}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=20)
+    ap.add_argument("--impl", default="ours")
+    ap.add_argument("--workload", default="membrane_1m")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    from ddcmd_b200 import synth
+    desc = synth.CONFIGS[args.workload][1]
+    config = {"workload": "%s: %s; NGLF dt=20fs, cutoff 11 A + 4 A skin, rebuild every 20 steps" % (args.workload, desc),
+              "l2": "inputs larger than L2 (neighbor list >= 4 B x 106 entries per bead)"}
+
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        n_full = synth.make_membrane(**dict(synth.CONFIGS[args.workload][0], lx=40.0, ly=40.0)).n  # density probe only
+        kw = synth.CONFIGS[args.workload][0]
+        n_full = int(round(n_full * (kw["lx"] * kw["ly"]) / (40.0 * 40.0)))   # beads scale with membrane area
+        r = run_reference(n_full, max(2, min(args.steps, 40)), min(args.warmup, 5))
+        line = {"impl": "reference", "metric": "Martini MD steps/s (20 fs)", "value": r["value"], "unit": "steps/s", "n_gpus": args.gpus,
+                "steps": r["steps_timed"], "warmup": min(args.warmup, 5), "ms_per_step": 1e3 / r["value"], "higher_is_better": True,
+                "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config,
+                "cpu_baseline": {"value": r["value"], "unit": "steps/s", "cores": 1, "kind": "reference",
+                                 "sample": "%d-bead patch of the same membrane recipe, %d steps of oracle/_ref (unmodified ddcMD CPU path, single-rank MPI shim); "
+                                           "steps/s scaled by bead count to the %d-bead workload (cost is linear in beads: %.2f us/bead-step)" % (
+                                               r["n_sample"], r["steps_timed"], n_full, r["us_per_bead_step"])},
+                "e2e": {"value": r["value"], "unit": "steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                "ns_per_day": r["value"] * DT_FS * 86400 * 1e-6}
+        print(json.dumps(line))
+        return
+
+    import ddcmd_b200 as dd
+    if world > 1:
+        raise SystemExit("bench.py: the multi-GPU (ddc halo over NCCL) path is not wired into bench yet")
+    K, W = args.steps, max(3, args.warmup)
+    deck_path = get_deck(args.workload)
+    t = time.time()
+    deck = dd.Deck(os.path.join(deck_path, "object.data"))
+    n = deck.n
+    log("[bench] deck parsed: %d beads, %d bonded terms in %.1fs" % (n, deck.s.nTerms, time.time() - t))
+    sim = dd.Simulate(deck, device=0)
+
+    # ---- device-resident throughput ------------------------------------------------------
+    sim.nglf(W)
+    sim.sync()
+    l0 = sim.kernelLaunches()
+    clocks = ClockSampler(0)
+    clocks.start()
+    time.sleep(0.3)
+    sim.timerRecord(0)
+    sim.nglf(K)
+    sim.timerRecord(1)
+    sim.sync()
+    ms = sim.timerElapsed(0, 1)
+    launches = sim.kernelLaunches() - l0
+    clk = clocks.finish()
+    e = sim.energyInfo()
+    sps = K / (ms * 1e-3)
+    log("[bench] %d steps in %.2f ms -> %.1f steps/s; T=%.1f K" % (K, ms, sps, e.temperature / dd.units_convert(1.0, "K", None)))
+
+    # ---- per-kernel device time (CUDA events around every launch) --------------------------
+    sim.profile(True)
+    sim.profileRead(reset=True)
+    KP = 40
+    sim.nglf(KP)
+    prof = sim.profileRead(reset=True)
+    sim.profile(False)
+    pair_ms = prof["pair"][0] / max(1, prof["pair"][1])
+    total_prof = sum(v[0] for v in prof.values())
+    p_full = 2 * int(e.nPairsListed)
+    alg_bytes = n * (32 + 24) + 4 * p_full       # pos4 read + force write + list entries
+    peak, peak_kind = measured_peaks()
+    achieved = alg_bytes / (pair_ms * 1e-3) / 1e9
+    roofline = {"bound": "hbm", "kernel": "k_pair", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": None, "peak_kind": peak_kind, "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms": pair_ms,
+                "kernel_share_of_step": prof["pair"][0] / total_prof,
+                "per_kernel_ms_per_step": {k: v[0] / KP for k, v in prof.items()}}
+
+    # ---- end to end through the reference-facing calls with host buffers ---------------------
+    import torch
+    st = sim.getState()
+    pinned = torch.empty((6, n), dtype=torch.float64).pin_memory()
+    host = pinned.numpy()
+    for k, name in enumerate(("rx", "ry", "rz", "vx", "vy", "vz")):
+        host[k] = st[name]
+    KE = min(K, 100)
+    sim.sync()
+    t0 = time.perf_counter()
+    sim.sendState(host[0], host[1], host[2], host[3], host[4], host[5], loop=int(e.loop), time=float(e.time))
+    for _ in range(KE):
+        sim.nglf(1)
+        ee = sim.energyInfo()
+    st2 = sim.getState()
+    t1 = time.perf_counter()
+    e2e_sps = KE / (t1 - t0)
+    e2e = {"value": e2e_sps, "unit": "steps/s", "h2d_bytes_per_step": 6 * 8 * n / KE, "d2h_bytes_per_step": 9 * 8 * n / KE + 24 * 8,
+           "steps": KE, "note": "sendState(H2D, pinned) + per step [nglf(1) + energyInfo D2H] (printrate=1) + getState(D2H)"}
+
+    cpu = None
+    if not args.no_cpu_baseline:
+        try:
+            r = run_reference(n, 30, 5)
+            cpu = {"value": r["value"], "unit": "steps/s", "cores": 1, "kind": "reference",
+                   "sample": "%d-bead patch of the same membrane recipe, %d steps of oracle/_ref (unmodified ddcMD CPU path); scaled by bead count to %d beads "
+                             "(%.2f us/bead-step)" % (r["n_sample"], r["steps_timed"], n, r["us_per_bead_step"])}
+        except Exception as ex:  # the baseline is reported, never required for the GPU number
+            cpu = {"value": None, "unit": "steps/s", "cores": 1, "kind": "reference", "sample": "failed: %s" % ex}
+
+    line = {"metric": "Martini MD steps/s (20 fs)", "value": sps, "unit": "steps/s", "n_gpus": 1, "steps": K, "warmup": W,
+            "ms_per_step": ms / K, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
+            "data": "synthetic", "config": dict(config, beads=n, bonded_terms=int(deck.s.nTerms), pairs_listed=int(e.nPairsListed)),
+            "ns_per_day": sps * DT_FS * 86400 * 1e-6, "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e,
+            "gpu_launches": int(launches), "clocks": clk}
+    print(json.dumps(line))
+
+
+if __name__ == "__main__":
+    main()

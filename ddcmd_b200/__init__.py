@@ -105,6 +105,9 @@ def lib():
         "ddcb200_getPairs": (i64, [vp, i64, pi, pi, pi]),
         "ddcb200_profile": (i32, [vp, i32]),
         "ddcb200_profileRead": (i32, [vp, pd, _P(C.c_int64), i32]),
+        "ddcb200_timerRecord": (i32, [vp, i32]),
+        "ddcb200_timerElapsed": (i32, [vp, i32, i32, pd]),
+        "ddcb200_kernelLaunches": (i64, [vp]),
         "ddcb200_ncclUniqueId": (i32, [C.c_char_p]),
         "ddcb200_ddcInit": (i32, [vp, i32, i32, i32, i32, i32, C.c_char_p]),
         "ddcb200_deckLoad": (i32, [C.c_char_p, C.c_char_p, C.c_char_p, _P(_P(DeckStruct))]),
@@ -127,7 +130,7 @@ EXPORTS = ["ddcb200_lastError", "ddcb200_deviceCount", "ddcb200_create", "ddcb20
            "ddcb200_martiniBondParms", "ddcb200_setRestraints", "ddcb200_setMolecules", "ddcb200_sendState",
            "ddcb200_numLocal", "ddcb200_getLocalBeads", "ddcb200_getState", "ddcb200_constructList", "ddcb200_ddcenergy",
            "ddcb200_nglf", "ddcb200_energyInfo", "ddcb200_getCells", "ddcb200_getPairs", "ddcb200_profile",
-           "ddcb200_profileRead", "ddcb200_ncclUniqueId", "ddcb200_ddcInit", "ddcb200_deckLoad", "ddcb200_deckFree",
+           "ddcb200_profileRead", "ddcb200_timerRecord", "ddcb200_timerElapsed", "ddcb200_kernelLaunches", "ddcb200_ncclUniqueId", "ddcb200_ddcInit", "ddcb200_deckLoad", "ddcb200_deckFree",
            "ddcb200_lastHostError", "ddcb200_simulateBind", "ddcb200_printinfoLine", "ddcb200_unitsConvert"]
 
 
@@ -282,6 +285,17 @@ class Simulate:
         self._ck(lib().ddcb200_profileRead(self.ctx, ms, ln, int(reset)))
         names = ("integrate", "pair", "bonded", "list", "reduce", "halo")
         return {k: (ms[i], int(ln[i])) for i, k in enumerate(names)}
+
+    def timerRecord(self, which):
+        self._ck(lib().ddcb200_timerRecord(self.ctx, int(which)))
+
+    def timerElapsed(self, a, b):
+        ms = C.c_double()
+        self._ck(lib().ddcb200_timerElapsed(self.ctx, int(a), int(b), C.byref(ms)))
+        return ms.value
+
+    def kernelLaunches(self):
+        return int(lib().ddcb200_kernelLaunches(self.ctx))
 
     def printinfo(self, e=None):
         e = e or self.energyInfo()

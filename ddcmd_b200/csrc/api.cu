@@ -27,10 +27,14 @@ static int fail(int code, const std::string &msg)
 #define CKL(what)                                                                                        \
     do                                                                                                   \
     {                                                                                                    \
+        c->kernelLaunches += launchesOf(what);                                                           \
         cudaError_t e__ = cudaGetLastError();                                                            \
         if (e__ != cudaSuccess)                                                                          \
             return fail(DDCB200_ERR_CUDA, std::string(what) + ": " + cudaGetErrorString(e__));           \
     } while (0)
+
+// number of kernels launched before each CKL() checkpoint (for the bench's gpu_launches count)
+static int launchesOf(const char *what) { return strcmp(what, "cell sort") == 0 ? 7 : 1; }
 
 extern "C" const char *ddcb200_lastError(void) { return g_err.c_str(); }
 
@@ -852,6 +856,28 @@ extern "C" int64_t ddcb200_getPairs(ddcb200_ctx *c, int64_t capacity, int *beadI
         }
     return np;
 }
+
+extern "C" int ddcb200_timerRecord(ddcb200_ctx *c, int which)
+{
+    if (!c || which < 0 || which > 3) return fail(DDCB200_ERR_ARG, "bad timer slot");
+    CK(cudaSetDevice(c->device));
+    if (!c->timer[which]) CK(cudaEventCreate(&c->timer[which]));
+    CK(cudaEventRecord(c->timer[which], c->stream));
+    return DDCB200_OK;
+}
+
+extern "C" int ddcb200_timerElapsed(ddcb200_ctx *c, int from, int to, double *ms)
+{
+    if (!c || !ms || from < 0 || from > 3 || to < 0 || to > 3 || !c->timer[from] || !c->timer[to]) return fail(DDCB200_ERR_ARG, "bad timer slot");
+    CK(cudaSetDevice(c->device));
+    CK(cudaEventSynchronize(c->timer[to]));
+    float t = 0;
+    CK(cudaEventElapsedTime(&t, c->timer[from], c->timer[to]));
+    *ms = t;
+    return DDCB200_OK;
+}
+
+extern "C" int64_t ddcb200_kernelLaunches(ddcb200_ctx *c) { return c ? c->kernelLaunches : 0; }
 
 extern "C" int ddcb200_profile(ddcb200_ctx *c, int enable)
 {

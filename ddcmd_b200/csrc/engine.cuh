@@ -187,6 +187,9 @@ struct ddcb200_ctx
     std::vector<PendingEv> pending;
     std::vector<cudaEvent_t> evPool;
 
+    cudaEvent_t timer[4] = {nullptr, nullptr, nullptr, nullptr};
+    int64_t kernelLaunches = 0;
+
     // multi-GPU
     int rank = 0, nranks = 1;
     void *nccl = nullptr;

@@ -378,8 +378,8 @@ moleculeClass MOLECULECLASS { molecules = %s; }
         return path
 
 
-def make_membrane(lx=150.0, ly=150.0, lz=110.0, seed=1, protein_beads=0, temperature=250.0, lipid_mix=True, ions=True):
-    """Bilayer in the xy plane (centre z=0) + water (10% antifreeze) + ions (+ optional protein-like chain).
+def make_membrane(lx=150.0, ly=150.0, lz=110.0, seed=1, protein_beads=0, temperature=240.0, lipid_mix=True, ions=True):
+    """Bilayer in the xy plane (centre z=0) + water (5% antifreeze) + ions (+ optional protein-like chain).
     ~0.0083 beads/A^3.  lx, ly are rounded so the lipid lattice tiles the box exactly."""
     rng = np.random.default_rng(seed)
     s = 5.657                               # chain-site spacing: 64 A^2 per lipid
@@ -413,18 +413,20 @@ def make_membrane(lx=150.0, ly=150.0, lz=110.0, seed=1, protein_beads=0, tempera
                 kind = R_POPE if (lipid_mix and (ix * 7 + iy * 3) % 4 == 0) else R_POPC
                 mol_res.append(kind)
                 chunks.append(c)
-    # water lattice in |z| > zwat
-    a = 4.95
-    wx, wy = int(lx / a), int(ly / a)
+    # water on an fcc lattice (nearest-neighbour distance ~5.5 A => ~0.0085 beads/A^3, every neighbour just
+    # outside the LJ minimum of sigma = 4.7 A) in |z| > zwat
+    nn = 5.5
+    a = nn * math.sqrt(2.0)
+    wx, wy = max(1, int(round(lx / a))), max(1, int(round(ly / a)))
     ax, ay = lx / wx, ly / wy
-    nzw = int((lz / 2 - zwat) / a)
-    az = (lz / 2 - zwat) / nzw
-    gx = -lx / 2 + (np.arange(wx) + 0.5) * ax
-    gy = -ly / 2 + (np.arange(wy) + 0.5) * ay
-    gz = zwat + (np.arange(nzw) + 0.25) * az
-    gz = np.concatenate([gz, -gz])
-    W = np.stack(np.meshgrid(gx, gy, gz, indexing="ij"), -1).reshape(-1, 3)
-    W += rng.uniform(-0.35, 0.35, W.shape)
+    nzw = max(1, int(round((lz / 2 - zwat - 1.0) / a)))
+    az = (lz / 2 - zwat - 1.0) / nzw
+    basis = np.array([[0.0, 0.0, 0.0], [0.5, 0.5, 0.0], [0.5, 0.0, 0.5], [0.0, 0.5, 0.5]])
+    cells = np.stack(np.meshgrid(np.arange(wx), np.arange(wy), np.arange(nzw), indexing="ij"), -1).reshape(-1, 1, 3)
+    frac = (cells + basis[None, :, :]).reshape(-1, 3)
+    Wup = np.stack([-lx / 2 + (frac[:, 0] + 0.25) * ax, -ly / 2 + (frac[:, 1] + 0.25) * ay, zwat + 1.5 + frac[:, 2] * az], 1)
+    W = np.concatenate([Wup, Wup * np.array([1.0, 1.0, -1.0])])
+    W += rng.uniform(-0.15, 0.15, W.shape)
     if prot_coords is not None:
         # drop water sites within 4.6 A of any protein bead (coarse grid search)
         from scipy.spatial import cKDTree
@@ -432,7 +434,7 @@ def make_membrane(lx=150.0, ly=150.0, lz=110.0, seed=1, protein_beads=0, tempera
         W = W[near == 0]
     kinds = np.full(len(W), R_W)
     u = rng.random(len(W))
-    kinds[u < 0.10] = R_WF
+    kinds[u < 0.05] = R_WF
     if ions:
         nion = max(1, len(W) // 184)
         idx = rng.choice(len(W), 2 * nion, replace=False)
@@ -475,8 +477,8 @@ CONFIGS = {
     "ras_small": (dict(lx=136.0, ly=68.0, lz=160.0, seed=2, protein_beads=120), "small bilayer + protein-like chain (~12k beads), test size"),
     "popc_100k": (dict(lx=300.0, ly=300.0, lz=130.0, seed=1), "POPC/POPE bilayer + water, ~100k beads"),
     "ras_140k": (dict(lx=340.0, ly=340.0, lz=150.0, seed=2, protein_beads=350), "RAS-like protein chain over a mixed membrane, ~140k beads"),
-    "membrane_1m": (dict(lx=950.0, ly=950.0, lz=130.0, seed=3), "multi-lipid membrane, ~1M beads"),
-    "membrane_10m": (dict(lx=3000.0, ly=3000.0, lz=130.0, seed=3), "multi-lipid membrane, ~10M beads"),
+    "membrane_1m": (dict(lx=1060.0, ly=1060.0, lz=130.0, seed=3), "multi-lipid membrane, ~1M beads"),
+    "membrane_10m": (dict(lx=3352.0, ly=3352.0, lz=130.0, seed=3), "multi-lipid membrane, ~10M beads"),
 }
 
 

@@ -165,6 +165,13 @@ int64_t ddcb200_getPairs(ddcb200_ctx *ctx, int64_t capacity, int *beadI, int *be
 int ddcb200_profile(ddcb200_ctx *ctx, int enable);
 int ddcb200_profileRead(ddcb200_ctx *ctx, double ms[8], int64_t launches[8], int reset);
 
+/* CUDA-event stopwatch on the context's own stream (torch.cuda.Event would only see torch's
+ * stream): record slot 0..3, elapsed ms between two recorded slots; and the number of kernels
+ * this context has launched so far. */
+int ddcb200_timerRecord(ddcb200_ctx *ctx, int which);
+int ddcb200_timerElapsed(ddcb200_ctx *ctx, int from, int to, double *ms);
+int64_t ddcb200_kernelLaunches(ddcb200_ctx *ctx);
+
 /* ---- multi-GPU (ddc-style spatial decomposition, src/ddcUpdate.c, src/ddcAssignment.c) ---- */
 int ddcb200_ncclUniqueId(unsigned char id[128]);
 int ddcb200_ddcInit(ddcb200_ctx *ctx, int rank, int nranks, int lx, int ly, int lz, const unsigned char id[128]);

@@ -11,7 +11,8 @@
  * firstEnergyCall, then calls eval_integrator nsteps times.
  *
  * Usage (cwd = deck directory with object.data + restart):
- *     ref_dump <out.bin> [nsteps] [full_dump_every]
+ *     ref_dump <out.bin> [nsteps] [full_dump_every] [light]
+ * "light" (any 4th argument) skips the per-bead and pair-list records: timing runs.
  *
  * Output: sequence of records  name[32] | dtype char ('d','q','i') | pad[7] |
  * count u64 | payload.  Read by tests/refdump.py.
@@ -54,6 +55,7 @@ double units_convert(double value, const char *from, const char *to);
 static FILE *out;
 static int nsteps = 0;
 static int dump_every = 0;
+static int light = 0;
 
 static void rec(const char *name, char dtype, const void *data, uint64_t count)
 {
@@ -186,13 +188,16 @@ static void dumpMaster(void *parms, MPI_Comm comm)
         rec("species_names", 'q', buf, nq);
         free(buf);
     }
-    dump_state("s0_", sys);
+    if (!light) dump_state("s0_", sys);
     dump_energy("s0_", sys);
-    dump_neighbor(sys);
+    if (!light) dump_neighbor(sys);
+    rec_i("npairs0", (int)sys->neighbor->npairs);
 
     if (nsteps > 0)
     {
         double *trace = malloc(sizeof(double) * 16 * (size_t)nsteps);
+        double *wall = malloc(sizeof(double) * (size_t)nsteps);
+        const double t0 = MPI_Wtime();
         for (int s = 0; s < nsteps; s++)
         {
             simulate->integrator->eval_integrator(simulate->ddc, simulate, simulate->integrator->parms);
@@ -205,6 +210,7 @@ static void dumpMaster(void *parms, MPI_Comm comm)
             t[8] = e->virial.xy; t[9] = e->virial.xz; t[10] = e->virial.yz;
             t[11] = e->tion.xx; t[12] = e->tion.yy; t[13] = e->tion.zz;
             t[14] = (double)sys->neighbor->npairs; t[15] = (double)sys->neighbor->lastUpdate;
+            wall[s] = MPI_Wtime() - t0;
             if (dump_every > 0 && (s + 1) % dump_every == 0 && s + 1 < nsteps)
             {
                 char pre[32];
@@ -213,8 +219,10 @@ static void dumpMaster(void *parms, MPI_Comm comm)
             }
         }
         rec("trace", 'd', trace, 16 * (uint64_t)nsteps);
+        rec("wall", 'd', wall, (uint64_t)nsteps);
         free(trace);
-        dump_state("sN_", sys);
+        free(wall);
+        if (!light) dump_state("sN_", sys);
         dump_energy("sN_", sys);
     }
     fclose(out);
@@ -231,6 +239,7 @@ int main(int argc, char *argv[])
     if (!out) { perror(argv[1]); return 2; }
     if (argc > 2) nsteps = atoi(argv[2]);
     if (argc > 3) dump_every = atoi(argv[3]);
+    if (argc > 4) light = 1;
     char *fake_argv[2] = {argv[0], NULL};
     int fake_argc = 1;
     mpiStartUp(fake_argc, fake_argv);
