@@ -287,11 +287,11 @@ static int readAtoms(const char *path, int64_t size, ddcb200_deck *d, NameIdx *s
         if (hdb->n > 0)
         {
             char *dt = NULL;
-            odb_getString(&hdb->obj[0], "datatype", &dt, "VARRECORDASCII");
+            odb_getString(hdb->obj[0], "datatype", &dt, "VARRECORDASCII");
             int bad = strcmp(dt, "VARRECORDASCII") != 0 && strcmp(dt, "FIXRECORDASCII") != 0;
             free(dt);
             char **fn;
-            int nf = odb_getStrings(&hdb->obj[0], "field_names", &fn, "id class type group rx ry rz vx vy vz");
+            int nf = odb_getStrings(hdb->obj[0], "field_names", &fn, "id class type group rx ry rz vx vy vz");
             const char *want[10] = {"id", "class", "type", "group", "rx", "ry", "rz", "vx", "vy", "vz"};
             if (nf < 10) bad = 1;
             for (int i = 0; i < 10 && i < nf; i++) bad |= strcmp(fn[i], want[i]) != 0;
@@ -312,10 +312,17 @@ static int readAtoms(const char *path, int64_t size, ddcb200_deck *d, NameIdx *s
         uint64_t gid = strtoull(p, &end, 10);
         if (end == p) { free(text); return herr("atoms file %s: bad record %lld", path, (long long)i); }
         p = end;
-        char cls[64], type[64], group[64];
-        int used = 0;
-        if (sscanf(p, "%63s %63s %63s%n", cls, type, group, &used) != 3) { free(text); return herr("atoms file %s: short record %lld", path, (long long)i); }
-        p += used;
+        /* class, species ("type") and group names: manual tokens (sscanf would strlen the whole file per record) */
+        char *tok[3];
+        for (int k = 0; k < 3; k++)
+        {
+            while (*p == ' ' || *p == '\t') p++;
+            tok[k] = p;
+            while (*p && !isspace((unsigned char)*p)) p++;
+            if (p == tok[k]) { free(text); return herr("atoms file %s: short record %lld", path, (long long)i); }
+            if (*p) *p++ = 0;
+        }
+        const char *type = tok[1];
         NameIdx key = {type, 0};
         NameIdx *hit = (NameIdx *)bsearch(&key, sortedSpecies, nspecies, sizeof(NameIdx), cmpName);
         if (!hit) { free(text); return herr("atoms file %s: unknown species %s", path, type); }

@@ -17,7 +17,7 @@ typedef struct
 } ODB_OBJECT;
 typedef struct
 {
-    ODB_OBJECT *obj;
+    ODB_OBJECT **obj; /* stable addresses: callers keep pointers while more files are compiled */
     int n, cap;
     char err[512];
 } ODB;

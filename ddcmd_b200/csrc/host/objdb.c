@@ -37,9 +37,10 @@ void odb_free(ODB *db)
     if (!db) return;
     for (int i = 0; i < db->n; i++)
     {
-        free(db->obj[i].name);
-        free(db->obj[i].cls);
-        free(db->obj[i].value);
+        free(db->obj[i]->name);
+        free(db->obj[i]->cls);
+        free(db->obj[i]->value);
+        free(db->obj[i]);
     }
     free(db->obj);
     free(db);
@@ -48,21 +49,22 @@ void odb_free(ODB *db)
 static int addObject(ODB *db, const char *name, const char *cls, const char *value)
 {
     for (int i = 0; i < db->n; i++)
-        if (strcmp(db->obj[i].name, name) == 0 && strcmp(db->obj[i].cls, cls) == 0)
+        if (strcmp(db->obj[i]->name, name) == 0 && strcmp(db->obj[i]->cls, cls) == 0)
         {
-            size_t a = strlen(db->obj[i].value), b = strlen(value);
-            db->obj[i].value = (char *)realloc(db->obj[i].value, a + b + 2);
-            memcpy(db->obj[i].value + a, value, b + 1);
+            size_t a = strlen(db->obj[i]->value), b = strlen(value);
+            db->obj[i]->value = (char *)realloc(db->obj[i]->value, a + b + 2);
+            memcpy(db->obj[i]->value + a, value, b + 1);
             return 0;
         }
     if (db->n == db->cap)
     {
         db->cap = db->cap ? 2 * db->cap : 64;
-        db->obj = (ODB_OBJECT *)realloc(db->obj, db->cap * sizeof(ODB_OBJECT));
+        db->obj = (ODB_OBJECT **)realloc(db->obj, db->cap * sizeof(ODB_OBJECT *));
     }
-    db->obj[db->n].name = xstrdup(name);
-    db->obj[db->n].cls = xstrdup(cls);
-    db->obj[db->n].value = xstrdup(value);
+    db->obj[db->n] = (ODB_OBJECT *)malloc(sizeof(ODB_OBJECT));
+    db->obj[db->n]->name = xstrdup(name);
+    db->obj[db->n]->cls = xstrdup(cls);
+    db->obj[db->n]->value = xstrdup(value);
     db->n++;
     return 0;
 }
@@ -164,7 +166,7 @@ int odb_compileFile(ODB *db, const char *path)
 const ODB_OBJECT *odb_find(const ODB *db, const char *name, const char *cls)
 {
     for (int i = 0; i < db->n; i++)
-        if (strcmp(db->obj[i].name, name) == 0 && strcmp(db->obj[i].cls, cls) == 0) return &db->obj[i];
+        if (strcmp(db->obj[i]->name, name) == 0 && strcmp(db->obj[i]->cls, cls) == 0) return db->obj[i];
     return NULL;
 }
 
