@@ -408,6 +408,9 @@ int ddcb200_deckLoad(const char *objectFile, const char *restartFile, const char
     GidIdx *order = NULL;
     char **molNames = NULL;
     int nMolNames = 0;
+    /* everything `done:` frees is initialised before the first FAIL */
+    char *sysName = NULL, *intName = NULL, *ddcName = NULL, *piName = NULL, *s = NULL;
+    char *boxName = NULL, *nbrName = NULL, *colName = NULL, *mcName = NULL;
 
     if (odb_compileFile(db, objectFile)) FAIL("%s", db->err);
     {
@@ -423,7 +426,6 @@ int ddcb200_deckLoad(const char *objectFile, const char *restartFile, const char
     }
     const ODB_OBJECT *sim = odb_find(db, simulateName ? simulateName : "simulate", "SIMULATE");
     if (!sim) FAIL("SIMULATE object %s not found", simulateName ? simulateName : "simulate");
-    char *sysName = NULL, *intName = NULL, *ddcName = NULL, *piName = NULL, *s = NULL;
     odb_getString(sim, "system", &sysName, NULL);
     odb_getString(sim, "integrator", &intName, NULL);
     odb_getString(sim, "ddc", &ddcName, "ddc");
@@ -464,7 +466,6 @@ int ddcb200_deckLoad(const char *objectFile, const char *restartFile, const char
     odb_getInts(sys, "nConstraints", &d->params.nConstraints, 1, "0");
 
     /* BOX */
-    char *boxName = NULL, *nbrName = NULL, *colName = NULL, *mcName = NULL;
     odb_getString(sys, "box", &boxName, NULL);
     odb_getString(sys, "neighbor", &nbrName, NULL);
     odb_getString(sys, "collection", &colName, NULL);

@@ -1,0 +1,148 @@
+"""CPU-side tests (no GPU): the C-ABI library loads and exports every symbol the headers
+declare, the host C object-database front end reproduces what the reference's own init chain
+produced for the same decks (tests/golden/*/ref.npz, written by oracle/_ref/ref_dump), and
+compute entry points fail loudly without a device (there is no CPU fallback).
+"""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+import ddcmd_b200 as dd
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+DECKS = ["waterbox", "popc_small", "ras_small"]
+
+
+def _declared(header):
+    src = open(os.path.join(ROOT, "include", header)).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(ddcb200_[A-Za-z0-9]+)\s*\(", src)))
+
+
+def test_abi_exports_every_declared_symbol():
+    L = dd.lib()
+    names = _declared("ddcmd_b200.h") + _declared("ddcmd_b200_host.h")
+    assert len(names) >= 30
+    for n in names:
+        assert hasattr(L, n), "libddcmd_b200.so does not export %s" % n
+    # and the Python table binds exactly the declared set
+    assert sorted(dd.EXPORTS) == sorted(names)
+
+
+def test_abi_struct_sizes_match_header():
+    # compile-time layout probe: a tiny C program prints sizeof() of the public structs
+    import subprocess
+    import tempfile
+    with tempfile.TemporaryDirectory() as td:
+        src = os.path.join(td, "sz.c")
+        open(src, "w").write('#include <stdio.h>\n#include "ddcmd_b200_host.h"\nint main(){printf("%zu %zu %zu\\n",'
+                             'sizeof(ddcb200_params),sizeof(ddcb200_etype),sizeof(ddcb200_deck));return 0;}\n')
+        exe = os.path.join(td, "sz")
+        subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), src, "-o", exe])
+        a, b, c = map(int, subprocess.check_output([exe]).split())
+    assert (a, b, c) == (C.sizeof(dd.Params), C.sizeof(dd.EType), C.sizeof(dd.DeckStruct))
+
+
+@pytest.mark.parametrize("name", DECKS)
+def test_deck_matches_reference_init(golden_dir, name):
+    ref = np.load(os.path.join(golden_dir, name, "ref.npz"))
+    deck = dd.Deck(os.path.join(golden_dir, name, "object.data"))
+    n = int(ref["nion"][0])
+    assert deck.n == n
+    # collection_read: labels, species, positions, velocities bit for bit (input order = reference order at np=1)
+    assert np.array_equal(deck.array("gid"), ref["s0_label"])
+    assert np.array_equal(deck.array("species"), ref["s0_species"])
+    for k in ("rx", "ry", "rz", "vx", "vy", "vz"):
+        assert np.array_equal(deck.array(k), ref["s0_" + k]), k
+    # species table: names in creation order, masses, charges
+    names = ref["species_names"].tobytes().split(b"\0")[0].decode().split()
+    assert deck.species_names == names
+    assert np.array_equal(deck.array("specMass"), ref["species_mass"])
+    assert np.array_equal(deck.array("specCharge")[deck.array("species")], ref["s0_q"])
+    # box, units, MARTINI scalars
+    assert np.array_equal(np.array(deck.s.params.h[:]), ref["h"])
+    un = ref["units"]   # 1 internal in Angstrom, kJ/mol, amu, bar, K ; ke ; kB ; fs
+    assert deck.s.lengthPerAngstrom == pytest.approx(1.0 / un[0], rel=1e-15)
+    assert deck.s.energyPerKJmol == pytest.approx(1.0 / un[1], rel=1e-15)
+    assert deck.s.massPerAmu == pytest.approx(1.0 / un[2], rel=1e-15)
+    assert deck.s.pressurePerBar == pytest.approx(1.0 / un[3], rel=1e-15)
+    assert deck.s.ke == un[5] and deck.s.kB == un[6]
+    mp = ref["martini_parms"]   # rmax rcoulomb epsilon_r epsilon_rf krf crf
+    assert deck.s.params.rmax == mp[0] and deck.s.rcoulomb == mp[1]
+    assert deck.s.epsilon_r == mp[2] and deck.s.epsilon_rf == mp[3]
+    assert deck.s.params.krf == mp[4] and deck.s.params.crf == mp[5]
+    assert deck.s.dt == ref["dt"][0]
+
+
+def test_units_convert_known_values():
+    # SURVEY.md Appendix B (src/units.c:450-486 with CODATA 2014)
+    assert dd.units_convert(1.0, "Angstrom", None) == pytest.approx(1.8897261254578, rel=1e-12)
+    assert dd.units_convert(1.0, "kJ/mol", None) == pytest.approx(7.61759769773e-4, rel=1e-10)
+    assert dd.units_convert(1.0, "amu", None) == pytest.approx(2.13314461, rel=1e-8)
+    assert dd.units_convert(1.0, "bar", None) == pytest.approx(6.79786195e-9, rel=1e-8)
+    assert dd.units_convert(11.0, "Angstrom", "nm") == pytest.approx(1.1, rel=1e-14)
+
+
+def test_bonded_term_tables(golden_dir):
+    deck = dd.Deck(os.path.join(golden_dir, "ras_small", "object.data"))
+    kind = deck.array("termKind")
+    idx = deck.array("termIdx").reshape(-1, 4)
+    assert set(np.unique(kind)) <= {0, 1, 2, 3, 4, 5}
+    assert (kind == 0).sum() > 0 and (kind == 2).sum() > 0 and (kind >= 4).sum() > 0
+    need = np.where(kind == 0, 2, np.where(kind <= 3, 3, 4))
+    for a in range(4):
+        used = need > a
+        assert np.all(idx[used, a] >= 0) and np.all(idx[used, a] < deck.n)
+    # every term lives inside one molecule (ddcRule MARTINI keeps molecules whole)
+    gid = deck.array("gid")
+    mol = (gid >> np.uint64(32)).astype(np.int64)
+    for a in range(1, 4):
+        used = need > a
+        assert np.array_equal(mol[idx[used, 0]], mol[idx[used, a]])
+    # exclusion keys exist for multi-species molecule types
+    off = deck.array("bpairOffset")
+    assert off[-1] > 0 and np.all(np.diff(off) >= 0)
+
+
+def test_waterbox_has_no_terms_and_single_species_molecules(golden_dir):
+    deck = dd.Deck(os.path.join(golden_dir, "waterbox", "object.data"))
+    assert deck.s.nTerms == 0 and deck.n == 6173
+    assert np.all(deck.array("molTypeNSpecies") == 1)
+    assert deck.s.params.updateRate == 20
+
+
+def test_deck_errors_are_reported(tmp_path):
+    with pytest.raises(dd.DdcError):
+        dd.Deck(str(tmp_path / "missing_object.data"))
+    bad = tmp_path / "object.data"
+    bad.write_text("simulate SIMULATE { type = MD; system=nosuch; }\n")
+    with pytest.raises(dd.DdcError):
+        dd.Deck(str(bad))
+
+
+def test_no_device_is_a_loud_error(golden_dir):
+    L = dd.lib()
+    if L.ddcb200_deviceCount() > 0:
+        pytest.skip("a CUDA device is present")
+    deck = dd.Deck(os.path.join(golden_dir, "waterbox", "object.data"))
+    with pytest.raises(dd.DdcError, match="no CUDA device|no CPU path"):
+        dd.Simulate(deck)
+    ctx = C.c_void_p()
+    p = dd.Params()
+    rc = L.ddcb200_create(C.byref(p), C.byref(ctx))
+    assert rc == -2 and b"no CPU path" in L.ddcb200_lastError()
+
+
+def test_product_does_not_reference_the_oracle():
+    """The product path may not import, link or execute anything under oracle/."""
+    pkg = os.path.join(ROOT, "ddcmd_b200")
+    for root, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".c", ".h", ".cu", ".cuh")):
+                txt = open(os.path.join(root, f)).read()
+                # prose may mention the oracle; code may not name it in a string literal, import or include
+                bad = re.findall(r"""["'][^"'\n]*(?:oracle|ref_dump|_ref)[^"'\n]*["']|import\s+oracle|from\s+oracle|#include\s*[<"][^>"]*oracle""", txt)
+                assert not bad, (os.path.join(root, f), bad)
