@@ -11,6 +11,15 @@
 #pragma once
 #include "engine.cuh"
 
+// One 256-bit load per j-bead: pos4 records are 32-byte aligned, so the whole record is one
+// L1/L2 sector and one LSU request (LDG.E.256, sm_100 only) instead of two 128-bit requests.
+__device__ __forceinline__ double4 ldPos(const double4 *p)
+{
+    double4 r;
+    asm volatile("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(r.x), "=d"(r.y), "=d"(r.z), "=d"(r.w) : "l"(p));
+    return r;
+}
+
 template <bool ENERGY>
 __global__ void __launch_bounds__(TILE)
 k_pair(int nLocal, int nPad, const double4 *__restrict__ pos, const uint32_t *__restrict__ nbr, const int *__restrict__ count,
@@ -31,7 +40,7 @@ k_pair(int nLocal, int nPad, const double4 *__restrict__ pos, const uint32_t *__
     const int i = blockIdx.x * TILE + threadIdx.x;
     const bool live = i < nLocal;
     const int ii = live ? i : 0;
-    const double4 pi = pos[ii];
+    const double4 pi = ldPos(pos + ii);
     const uint64_t wi = (uint64_t)__double_as_longlong(pi.w);
     const int ti = (int)(wi & 0xff);
     const double qi = sQ[(wi >> 8) & 0xff];
@@ -44,15 +53,20 @@ k_pair(int nLocal, int nPad, const double4 *__restrict__ pos, const uint32_t *__
     double fxi = 0.0, fyi = 0.0, fzi = 0.0;
     double eLJ = 0.0, eEle = 0.0, vxx = 0.0, vyy = 0.0, vzz = 0.0, vxy = 0.0, vxz = 0.0, vyz = 0.0;
 
+    // software pipeline: entry k+2 and position k+1 are in flight while pair k is computed
     const uint32_t *row = nbr + ii;
-    uint32_t eNext = (0 < n) ? row[0] : 0u;
+    uint32_t eCur = (0 < n) ? row[0] : (uint32_t)ii;
+    uint32_t eNext = (1 < n) ? row[(size_t)nPad] : (uint32_t)ii;
+    double4 pNext = ldPos(pos + (eCur & 0x07ffffffu));
     for (int k = 0; k < nmax; k++)
     {
-        const uint32_t e = eNext;
-        if (k + 1 < n) eNext = row[(size_t)(k + 1) * nPad];
+        const uint32_t e = eCur;
+        const double4 pj = pNext;
+        eCur = eNext;
+        pNext = ldPos(pos + (eCur & 0x07ffffffu));
+        if (k + 2 < n) eNext = row[(size_t)(k + 2) * nPad];
+        else eNext = (uint32_t)ii;
         const bool valid = k < n;
-        const int j = valid ? (int)(e & 0x07ffffffu) : ii;
-        const double4 pj = pos[j];
         double x = pi.x - pj.x, y = pi.y - pj.y, z = pi.z - pj.z;
         double r2 = x * x + y * y + z * z;
         if (r2 > pc.R2cut)
@@ -74,7 +88,9 @@ k_pair(int nLocal, int nPad, const double4 *__restrict__ pos, const uint32_t *__
             const double kqij = kqi * sQ[(wj >> 8) & 0xff];
             const double r2s = in ? r2 : 1.0;
             double dvdr, vlj = 0.0, vele = 0.0;
-            const double ir2 = 1.0 / r2s;
+            // one reciprocal square root serves both terms (the reference takes sqrt(1/r2), src/bioMartini.c:1068)
+            const double ir1 = rsqrt(r2s);
+            const double ir2 = ir1 * ir1;
             {
                 // Lennard-Jones: 4 eps (s12 - s6) + shift ; dvdr = 24 eps (s6 - 2 s12)/r^2 (src/bioMartini.c:1073-1080)
                 const double2 cc = ljRow[wj & 0xff];
@@ -87,7 +103,7 @@ k_pair(int nLocal, int nPad, const double4 *__restrict__ pos, const uint32_t *__
             if (__any_sync(0xffffffffu, in && kqij != 0.0))
             {
                 // reaction field (src/bioMartini.c:1082-1085); pruned pairs keep only krf r^2 - crf (:1172-1174)
-                const double ir = excl ? 0.0 : sqrt(ir2);
+                const double ir = excl ? 0.0 : ir1;
                 dvdr += kqij * (2.0 * pc.krf - ir2 * ir);
                 if (ENERGY) vele = kqij * (ir + pc.krf * r2s - pc.crf);
             }
