@@ -34,7 +34,7 @@ static int fail(int code, const std::string &msg)
     } while (0)
 
 // number of kernels launched before each CKL() checkpoint (for the bench's gpu_launches count)
-static int launchesOf(const char *what) { return strcmp(what, "cell sort") == 0 ? 7 : 1; }
+static int launchesOf(const char *what) { return strcmp(what, "cell sort") == 0 ? 7 : 1; }   // minmax, grid, count, scan, scatter, rank, gather
 
 extern "C" const char *ddcb200_lastError(void) { return g_err.c_str(); }
 
@@ -156,6 +156,7 @@ static int setupBox(ddcb200_ctx *c)
         {
             const double r = p.rmax + f[k] * p.deltaR;
             b.binEdge2[k] = r * r;
+            c->pc.binEdge[k] = r * (1.0 - 1e-12);   // r_build >= sqrt(binEdge2) >= this
         }
     }
     PairConst &pc = c->pc;
@@ -163,6 +164,7 @@ static int setupBox(ddcb200_ctx *c)
     pc.hxx = b.hxx; pc.hyy = b.hyy; pc.hzz = b.hzz;
     pc.hhx = b.hhx; pc.hhy = b.hhy; pc.hhz = b.hhz;
     pc.keR = p.keR; pc.krf = p.krf; pc.crf = p.crf;
+    pc.rmax = p.rmax;
     pc.ntypes = c->ntypes;
     return DDCB200_OK;
 }
@@ -194,6 +196,8 @@ extern "C" int ddcb200_create(const ddcb200_params *p, ddcb200_ctx **out)
     CK(cudaMalloc((void **)&c->acc, ACC_N * sizeof(double)));
     CK(cudaMemset(c->acc, 0, ACC_N * sizeof(double)));
     CK(cudaMallocHost((void **)&c->accHost, ACC_N * sizeof(double)));
+    CK(cudaMalloc((void **)&c->dmax2, sizeof(unsigned long long)));
+    CK(cudaMemset(c->dmax2, 0, sizeof(unsigned long long)));
     *out = c;
     return DDCB200_OK;
 }
@@ -218,6 +222,9 @@ extern "C" void ddcb200_destroy(ddcb200_ctx *c)
     c->cellStart.release(); c->member.release(); c->perm.release(); c->mmPartial.release(); c->nbrRaw.release();
     c->nbr.release(); c->nbrCount.release(); c->pairPartial.release(); c->bondPartial.release(); c->kinPartial.release();
     c->colMap.release(); c->stage.release(); c->stageI.release();
+    c->orderKey.release(); c->pos32.release(); c->nbrRawCount.release(); c->nbrCum.release();
+    for (int a = 0; a < 3; a++) c->posBuild[a].release();
+    if (c->dmax2) cudaFree(c->dmax2);
     for (auto &pe : c->pending)
     {
         cudaEventDestroy(pe.a);
@@ -297,7 +304,7 @@ static int uploadBeadTables(ddcb200_ctx *c)
     {
         const int s = c->hSpecies[(size_t)i];
         if (s < 0 || s >= c->nspecies) return fail(DDCB200_ERR_ARG, "species index out of range");
-        w[(size_t)i] = packW(c->hSpecLJ[s], c->hSpecQi[s], (uint32_t)i);
+        w[(size_t)i] = packW(c->hSpecLJ[s], c->hSpecQi[s], (uint32_t)(c->hGid[(size_t)i] >> 32), (uint32_t)i);
         m[(size_t)i] = c->hSpecMass[s];
         if (!c->hMolTypeOfSpecies.empty()) mt[(size_t)i] = c->hMolTypeOfSpecies[s];
     }
@@ -453,6 +460,11 @@ static int ensureState(ddcb200_ctx *c, int64_t nIon)
     CK(c->cellCount.ensure((size_t)nIon + 8));
     CK(c->cellStart.ensure((size_t)nIon + 8));
     CK(c->nbrCount.ensure((size_t)nPad));
+    CK(c->nbrRawCount.ensure((size_t)nPad));
+    CK(c->nbrCum.ensure((size_t)nPad * NBINS));
+    CK(c->orderKey.ensure((size_t)nPad));
+    CK(c->pos32.ensure((size_t)nPad));
+    for (int a = 0; a < 3; a++) CK(c->posBuild[a].ensure((size_t)nPad));
     CK(c->mmPartial.ensure(6 * 1024));
     const size_t tiles = (size_t)(nPad / TILE);
     CK(c->pairPartial.ensure(tiles * 8 + 8));
@@ -542,38 +554,48 @@ extern "C" int ddcb200_constructList(ddcb200_ctx *c)
     k_grid_setup<<<1, 32, 0, st>>>(c->mmPartial.p, mmBlocks, nIon, c->box, c->grid, maxCells);
     CK(cudaMemsetAsync(c->cellCount.p, 0, (size_t)(nIon + 8) * sizeof(int), st));
     const int nb = (nIon + 255) / 256;
-    k_cell_count<<<nb, 256, 0, st>>>(c->pos4[cur].p, nIon, c->box, c->grid, c->cellOfSlot[cur].p, c->rank0.p, c->cellCount.p);
+    k_cell_count<<<nb, 256, 0, st>>>(c->pos4[cur].p, nIon, c->box, c->grid, c->cellOfSlot[cur].p, c->rank0.p, c->cellCount.p,
+                                     c->beadOfSlot[cur].p, c->orderKey.p);
     k_cell_scan<<<1, 1024, 0, st>>>(c->cellCount.p, c->cellStart.p, c->grid);
     k_cell_scatter<<<nb, 256, 0, st>>>(nIon, c->cellOfSlot[cur].p, c->rank0.p, c->cellStart.p, c->member.p);
-    k_cell_rank<<<nb, 256, 0, st>>>(nIon, c->cellOfSlot[cur].p, c->beadOfSlot[cur].p, c->cellStart.p, c->member.p, c->perm.p);
+    k_cell_rank<<<nb, 256, 0, st>>>(nIon, c->cellOfSlot[cur].p, c->orderKey.p, c->cellStart.p, c->member.p, c->perm.p);
     k_gather<<<nb, 256, 0, st>>>(nIon, c->perm.p, c->cellOfSlot[cur].p, c->cellOfSlot[nxt].p, c->pos4[cur].p, c->pos4[nxt].p,
                                  c->vel[cur][0].p, c->vel[cur][1].p, c->vel[cur][2].p, c->vel[nxt][0].p, c->vel[nxt][1].p,
-                                 c->vel[nxt][2].p, c->beadOfSlot[cur].p, c->beadOfSlot[nxt].p, c->slotOfBead.p, nLocal);
+                                 c->vel[nxt][2].p, c->beadOfSlot[cur].p, c->beadOfSlot[nxt].p, c->slotOfBead.p, nLocal,
+                                 c->pos32.p, c->posBuild[0].p, c->posBuild[1].p, c->posBuild[2].p);
     CKL("cell sort");
     c->cur = nxt;
+    CK(cudaMemsetAsync(c->dmax2, 0, sizeof(unsigned long long), st));
 
+    // fp32 candidate filter: margin covers the rounding of box-sized coordinates (and the image shift) to fp32
+    const double Lmax = std::max(c->box.hxx, std::max(c->box.hyy, c->box.hzz));
+    const double rl = sqrt(c->box.rlist2);
+    const double margin = std::max(1e-3, 64.0 * 1.1920929e-7 * 1.5 * Lmax / rl);
+    const float rl2f = (float)(c->box.rlist2 * (1.0 + margin));
     if (c->nbrCap == 0) c->nbrCap = 176;
     for (int attempt = 0; attempt < 4; attempt++)
     {
         CK(c->nbrRaw.ensure((size_t)c->nbrCap * nPad));
         CK(c->nbr.ensure((size_t)c->nbrCap * nPad));
-        k_nbr_raw<<<nPad / 128, 128, 0, st>>>(nLocal, nIon, nPad, c->pos4[nxt].p, c->cellOfSlot[nxt].p, c->cellStart.p, c->box, c->grid,
-                                             c->nbrCap, c->nbrRaw.p, c->nbrCount.p, c->beadOfSlot[nxt].p, c->gidOfBead.p,
-                                             c->molTypeOfBead.p, c->molTypeSingle.p, c->bpairOffset.p, c->bpairKey.p, c->haveExcl ? 1 : 0);
-        CKL("k_nbr_raw");
+        k_nbr_filter<<<nPad / 128, 128, 0, st>>>(nLocal, nPad, c->pos32.p, c->cellOfSlot[nxt].p, c->cellStart.p, c->box, rl2f, c->grid,
+                                                c->nbrCap, c->nbrRaw.p, c->nbrRawCount.p);
+        CKL("k_nbr_filter");
+        k_nbr_exact<<<nPad / 128, 128, 0, st>>>(nLocal, nPad, c->nbrCap, c->pos4[nxt].p, c->box, c->grid, c->nbrRaw.p, c->nbrRawCount.p,
+                                               c->nbr.p, c->nbrCount.p, c->nbrCum.p, c->gidOfBead.p, c->molTypeOfBead.p,
+                                               c->molTypeSingle.p, c->bpairOffset.p, c->bpairKey.p, c->haveExcl ? 1 : 0);
+        CKL("k_nbr_exact");
         CK(cudaMemcpyAsync(c->gridHost, c->grid, sizeof(GridDev), cudaMemcpyDeviceToHost, st));
         CK(cudaStreamSynchronize(st));
         if (c->gridHost->error & 2) return fail(DDCB200_ERR_CAPACITY, "cell grid larger than the bead count bound");
         if (!(c->gridHost->error & 1)) break;
-        // a row overflowed: grow and redo the raw pass
-        c->nbrCap = (int)(c->gridHost->maxCount * 1.25) + 8;
+        // a candidate row overflowed: grow and redo both passes
+        if (attempt == 3) return fail(DDCB200_ERR_CAPACITY, "neighbor list capacity could not be satisfied");
+        c->nbrCap = (int)(c->gridHost->maxRaw * 1.25) + 8;
         CK(cudaMemsetAsync(&c->grid->error, 0, sizeof(int), st));
         CK(cudaMemsetAsync(&c->grid->maxCount, 0, sizeof(int), st));
+        CK(cudaMemsetAsync(&c->grid->maxRaw, 0, sizeof(int), st));
         CK(cudaMemsetAsync(&c->grid->totalEntries, 0, sizeof(unsigned long long), st));
-        if (attempt == 3) return fail(DDCB200_ERR_CAPACITY, "neighbor list capacity could not be satisfied");
     }
-    k_nbr_order<<<nPad / 128, 128, 0, st>>>(nLocal, nPad, c->nbrCap, c->nbrRaw.p, c->nbrCount.p, c->nbr.p);
-    CKL("k_nbr_order");
     if (c->nTerms)
     {
         k_terms_remap<<<(int)((c->nTerms + 255) / 256), 256, 0, st>>>(c->nTerms, c->termsBead.p, c->termsSlot.p, c->slotOfBead.p);
@@ -634,10 +656,10 @@ extern "C" int ddcb200_ddcenergy(ddcb200_ctx *c, int withEnergy)
         ProfScope ps(c, PROF_PAIR);
         const size_t smem = (size_t)c->ntypes * c->ntypes * (sizeof(double2) + sizeof(double)) + 256 * sizeof(double);
         if (withEnergy)
-            k_pair<true><<<tiles, TILE, smem, st>>>(nLocal, nPad, c->pos4[cur].p, c->nbr.p, c->nbrCount.p, c->ljTab.p, c->shiftTab.p,
+            k_pair<true><<<tiles, TILE, smem, st>>>(nLocal, nPad, c->pos4[cur].p, c->nbr.p, c->nbrCum.p, c->dmax2, c->ljTab.p, c->shiftTab.p,
                                                     c->qTab.p, c->pc, c->frc[0].p, c->frc[1].p, c->frc[2].p, c->pairPartial.p);
         else
-            k_pair<false><<<tiles, TILE, smem, st>>>(nLocal, nPad, c->pos4[cur].p, c->nbr.p, c->nbrCount.p, c->ljTab.p, c->shiftTab.p,
+            k_pair<false><<<tiles, TILE, smem, st>>>(nLocal, nPad, c->pos4[cur].p, c->nbr.p, c->nbrCum.p, c->dmax2, c->ljTab.p, c->shiftTab.p,
                                                      c->qTab.p, c->pc, c->frc[0].p, c->frc[1].p, c->frc[2].p, c->pairPartial.p);
         CKL("k_pair");
     }
@@ -683,7 +705,7 @@ static int launchIntegrate(ddcb200_ctx *c, double halfDt2, double halfDt1, doubl
     const int tiles = (int)(c->nPad / TILE);
     k_integrate<MODE><<<tiles, TILE, 0, c->stream>>>((int)c->nLocal, c->pos4[cur].p, c->vel[cur][0].p, c->vel[cur][1].p, c->vel[cur][2].p,
                                                      c->frc[0].p, c->frc[1].p, c->frc[2].p, c->massOfBead.p, halfDt2, halfDt1, dt, c->pc,
-                                                     c->kinPartial.p);
+                                                     c->kinPartial.p, c->posBuild[0].p, c->posBuild[1].p, c->posBuild[2].p, c->dmax2);
     CKL("k_integrate");
     return DDCB200_OK;
 }

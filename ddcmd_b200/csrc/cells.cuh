@@ -86,22 +86,23 @@ __global__ void k_minmax_partial(const double4 *__restrict__ pos, int n, BoxCons
     }
 }
 
-// ---- 2. grid parameters (geomMethodDefault, src/geom.c:537-583), one thread ------------
+// ---- 2. grid parameters (geomMethodDefault, src/geom.c:537-583), one warp ---------------
 __global__ void k_grid_setup(const double *__restrict__ partial, int nblocks, int nion, BoxConst b, GridDev *g, int maxCells)
 {
-    if (threadIdx.x != 0 || blockIdx.x != 0) return;
-    double mn[3], mx[3];
-    for (int a = 0; a < 3; a++)
-    {
-        mn[a] = partial[a];
-        mx[a] = partial[3 + a];
-    }
-    for (int k = 1; k < nblocks; k++)
+    double mn[3] = {1e300, 1e300, 1e300}, mx[3] = {-1e300, -1e300, -1e300};
+    for (int k = threadIdx.x; k < nblocks; k += 32)
         for (int a = 0; a < 3; a++)
         {
             mn[a] = fmin(mn[a], partial[k * 6 + a]);
             mx[a] = fmax(mx[a], partial[k * 6 + 3 + a]);
         }
+    for (int a = 0; a < 3; a++)
+        for (int o = 16; o > 0; o >>= 1)
+        {
+            mn[a] = fmin(mn[a], __shfl_xor_sync(0xffffffffu, mn[a], o));
+            mx[a] = fmax(mx[a], __shfl_xor_sync(0xffffffffu, mx[a], o));
+        }
+    if (threadIdx.x != 0) return;
     const double span[3] = {b.spanx, b.spany, b.spanz};
     double ext[3], nn[3];
     for (int a = 0; a < 3; a++)
@@ -128,33 +129,45 @@ __global__ void k_grid_setup(const double *__restrict__ partial, int nblocks, in
     g->ncell = g->n[0] * g->n[1] * g->n[2];
     if (g->ncell > maxCells) g->error |= 2;
     g->maxCount = 0;
+    g->maxRaw = 0;
     g->totalEntries = 0ull;
 }
 
-__device__ __forceinline__ int cellIndexOf(const double4 p, const BoxConst &b, const GridDev &g)
+__device__ __forceinline__ int spread2(int v) { return (v & 1) | ((v & 2) << 2); }   // bits 0,1 -> bits 0,3
+
+__device__ __forceinline__ int cellIndexOf(const double4 p, const BoxConst &b, const GridDev &g, int &subKey)
 {
     // GeomDenseBox second loop, src/geom.c:428-441
     double ux, uy, uz;
     normCoord(p, b, ux, uy, uz);
-    int ix = (int)__ddiv_rn(__dadd_rn(ux, -g.mn[0]), g.d[0]);
-    int iy = (int)__ddiv_rn(__dadd_rn(uy, -g.mn[1]), g.d[1]);
-    int iz = (int)__ddiv_rn(__dadd_rn(uz, -g.mn[2]), g.d[2]);
+    const double qx = __ddiv_rn(__dadd_rn(ux, -g.mn[0]), g.d[0]);
+    const double qy = __ddiv_rn(__dadd_rn(uy, -g.mn[1]), g.d[1]);
+    const double qz = __ddiv_rn(__dadd_rn(uz, -g.mn[2]), g.d[2]);
+    int ix = (int)qx, iy = (int)qy, iz = (int)qz;
     ix = max(min(ix, g.n[0] - 1), 0);
     iy = max(min(iy, g.n[1] - 1), 0);
     iz = max(min(iz, g.n[2] - 1), 0);
+    // 4x4x4 sub-cells in Morton order: only the slot order inside a cell depends on it (locality of the
+    // per-step gathers), never a parity-visible quantity
+    const int sx = max(min((int)((qx - ix) * 4.0), 3), 0), sy = max(min((int)((qy - iy) * 4.0), 3), 0),
+              sz = max(min((int)((qz - iz) * 4.0), 3), 0);
+    subKey = spread2(sx) | (spread2(sy) << 1) | (spread2(sz) << 2);
     return ix + g.n[0] * (iy + g.n[1] * iz);
 }
 
 // ---- 3. count beads per cell -----------------------------------------------------------
 __global__ void k_cell_count(const double4 *__restrict__ pos, int n, BoxConst b, const GridDev *__restrict__ gp,
-                             int *__restrict__ cellOf, int *__restrict__ rank0, int *__restrict__ cellCount)
+                             int *__restrict__ cellOf, int *__restrict__ rank0, int *__restrict__ cellCount,
+                             const int *__restrict__ beadOfSlot, uint64_t *__restrict__ orderKey)
 {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     GridDev g = *gp;
     if (g.error & 2) return;
-    int c = cellIndexOf(pos[i], b, g);
+    int sub;
+    int c = cellIndexOf(pos[i], b, g, sub);
     cellOf[i] = c;
+    orderKey[i] = ((uint64_t)sub << 32) | (uint32_t)beadOfSlot[i];
     rank0[i] = atomicAdd(&cellCount[c], 1);
 }
 
@@ -186,7 +199,7 @@ __global__ void k_cell_scan(const int *__restrict__ cnt, int *__restrict__ start
     if (threadIdx.x == blockDim.x - 1) start[n] = sums[threadIdx.x];
 }
 
-// ---- 5/6. deterministic order inside a cell: by input (bead) index ---------------------
+// ---- 5/6. deterministic order inside a cell: by (sub-cell Morton key, input bead index) -----
 __global__ void k_cell_scatter(int n, const int *__restrict__ cellOf, const int *__restrict__ rank0,
                                const int *__restrict__ cellStart, int *__restrict__ member)
 {
@@ -195,16 +208,16 @@ __global__ void k_cell_scatter(int n, const int *__restrict__ cellOf, const int 
     member[cellStart[cellOf[i]] + rank0[i]] = i;
 }
 
-__global__ void k_cell_rank(int n, const int *__restrict__ cellOf, const int *__restrict__ beadOfSlot,
+__global__ void k_cell_rank(int n, const int *__restrict__ cellOf, const uint64_t *__restrict__ orderKey,
                             const int *__restrict__ cellStart, const int *__restrict__ member, int *__restrict__ perm)
 {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const int c = cellOf[i];
     const int lo = cellStart[c], hi = cellStart[c + 1];
-    const int me = beadOfSlot[i];
+    const uint64_t me = orderKey[i];
     int r = 0;
-    for (int k = lo; k < hi; k++) r += (beadOfSlot[member[k]] < me) ? 1 : 0;
+    for (int k = lo; k < hi; k++) r += (orderKey[member[k]] < me) ? 1 : 0;
     perm[lo + r] = i;
 }
 
@@ -213,12 +226,18 @@ __global__ void k_gather(int n, const int *__restrict__ perm, const int *__restr
                          const double4 *__restrict__ posOld, double4 *__restrict__ posNew,
                          const double *__restrict__ vxo, const double *__restrict__ vyo, const double *__restrict__ vzo,
                          double *__restrict__ vxn, double *__restrict__ vyn, double *__restrict__ vzn,
-                         const int *__restrict__ beadOld, int *__restrict__ beadNew, int *__restrict__ slotOfBead, int nLocal)
+                         const int *__restrict__ beadOld, int *__restrict__ beadNew, int *__restrict__ slotOfBead, int nLocal,
+                         float4 *__restrict__ pos32, double *__restrict__ bx, double *__restrict__ by, double *__restrict__ bz)
 {
     int s = blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= n) return;
     const int o = perm[s];
-    posNew[s] = posOld[o];
+    const double4 p = posOld[o];
+    posNew[s] = p;
+    pos32[s] = make_float4((float)p.x, (float)p.y, (float)p.z, 0.0f);   // candidate filter of the list build
+    bx[s] = p.x;                                                        // build-time positions: displacement bound
+    by[s] = p.y;
+    bz[s] = p.z;
     cellNew[s] = cellOld[o];
     const int bead = beadOld[o];
     beadNew[s] = bead;
@@ -230,15 +249,89 @@ __global__ void k_gather(int n, const int *__restrict__ perm, const int *__restr
     (void)nLocal;
 }
 
-// ---- 8. raw neighbor pass ---------------------------------------------------------------
-// One thread per slot; visits the <=27 periodic neighbour cells (deduplicated when a grid
-// dimension has fewer than 3 cells) and applies pairlist1's test bit for bit.
-__device__ __forceinline__ bool isPruned(int si, int sj, const int *__restrict__ beadOfSlot, const uint64_t *__restrict__ gid,
+// ---- 8. candidate pass (fp32, conservative) ----------------------------------------------
+// One thread per local slot walks the <=27 periodic neighbour cells and keeps every j whose
+// single-precision distance is below (rcut+skin)^2 times a safety margin covering the fp32
+// rounding of the coordinates.  It only shrinks the work of the exact pass below; every list
+// decision is taken there in fp64 with the reference's own arithmetic.
+__global__ void __launch_bounds__(128)
+k_nbr_filter(int nLocal, int nPad, const float4 *__restrict__ pos32, const int *__restrict__ cellOf,
+             const int *__restrict__ cellStart, BoxConst b, float rl2f, GridDev *gp, int cap, uint32_t *__restrict__ raw,
+             int *__restrict__ rawCount)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    int cnt = 0;
+    if (i < nLocal)
+    {
+        const int nx = gp->n[0], ny = gp->n[1], nz = gp->n[2];
+        const float Lx = (float)b.hxx, Ly = (float)b.hyy, Lz = (float)b.hzz;
+        const float hx2 = 0.5f * Lx, hy2 = 0.5f * Ly, hz2 = 0.5f * Lz;
+        // with >= 3 cells along an axis a wrapped stencil cell has ONE possible image: shift it;
+        // with fewer the stencil is deduplicated and each pair takes its nearest image
+        const bool px = nx < 3, py = ny < 3, pz = nz < 3;
+        const float4 pi = pos32[i];
+        const int c = cellOf[i];
+        const int cx = c % nx, cy = (c / nx) % ny, cz = c / (nx * ny);
+        const int lx = nx >= 3 ? -1 : 0, hx = nx >= 2 ? 1 : 0;
+        const int ly = ny >= 3 ? -1 : 0, hy = ny >= 2 ? 1 : 0;
+        const int lz = nz >= 3 ? -1 : 0, hz = nz >= 2 ? 1 : 0;
+        for (int dz = lz; dz <= hz; dz++)
+        {
+            int az = cz + dz;
+            float sz = 0.0f;
+            if (az < 0) { az += nz; sz = -Lz; }
+            else if (az >= nz) { az -= nz; sz = Lz; }
+            const float bz = pz ? pi.z : pi.z - sz;
+            for (int dy = ly; dy <= hy; dy++)
+            {
+                int ay = cy + dy;
+                float sy = 0.0f;
+                if (ay < 0) { ay += ny; sy = -Ly; }
+                else if (ay >= ny) { ay -= ny; sy = Ly; }
+                const float by = py ? pi.y : pi.y - sy;
+                for (int dx = lx; dx <= hx; dx++)
+                {
+                    int ax = cx + dx;
+                    float sx = 0.0f;
+                    if (ax < 0) { ax += nx; sx = -Lx; }
+                    else if (ax >= nx) { ax -= nx; sx = Lx; }
+                    const float bx = px ? pi.x : pi.x - sx;
+                    const int cc = ax + nx * (ay + ny * az);
+                    const int lo = cellStart[cc], hi = cellStart[cc + 1];
+                    for (int j = lo; j < hi; j++)
+                    {
+                        const float4 pj = pos32[j];
+                        float x = bx - pj.x, y = by - pj.y, z = bz - pj.z;
+                        if (px) { if (x > hx2) x -= Lx; if (x < -hx2) x += Lx; }
+                        if (py) { if (y > hy2) y -= Ly; if (y < -hy2) y += Ly; }
+                        if (pz) { if (z > hz2) z -= Lz; if (z < -hz2) z += Lz; }
+                        const float r2 = x * x + y * y + z * z;
+                        if (r2 < rl2f && j != i)
+                        {
+                            if (cnt < cap) raw[(size_t)cnt * nPad + i] = (uint32_t)j;
+                            cnt++;
+                        }
+                    }
+                }
+            }
+        }
+        rawCount[i] = cnt;
+    }
+    int m = cnt;
+    for (int o = 16; o > 0; o >>= 1) m = max(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if ((threadIdx.x & 31) == 0 && m > 0)
+    {
+        atomicMax(&gp->maxRaw, m);
+        if (m > cap) atomicOr(&gp->error, 1);
+    }
+}
+
+// ---- 9. exact pass: pairlist1's test bit for bit, reOrgPairs' pruning, distance-bin order ----
+__device__ __forceinline__ bool isPruned(int bi, int bj, const uint64_t *__restrict__ gid,
                                          const int *__restrict__ molTypeOfBead, const int *__restrict__ molTypeSingle,
                                          const int *__restrict__ bpairOffset, const uint32_t *__restrict__ bpairKey)
 {
     // reOrgPairs, src/bioMartini.c:1426-1464
-    const int bi = beadOfSlot[si], bj = beadOfSlot[sj];
     const uint64_t gi = gid[bi], gj = gid[bj];
     if ((gi >> 32) != (gj >> 32)) return false;
     // the reference takes the molecule type of the bead that owns the pair (smaller gid)
@@ -259,101 +352,107 @@ __device__ __forceinline__ bool isPruned(int si, int sj, const int *__restrict__
     return false;
 }
 
+__device__ __forceinline__ double4 ldPos256(const double4 *p)
+{
+    double4 r;
+    asm volatile("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(r.x), "=d"(r.y), "=d"(r.z), "=d"(r.w) : "l"(p));
+    return r;
+}
+
+#define RAW_REJECT 0xffffffffu
+
+// Eight 16-bit per-bin counters in two 64-bit words: bins 0-3 in A, 4-7 in B.
 __global__ void __launch_bounds__(128)
-k_nbr_raw(int nLocal, int nIon, int nPad, const double4 *__restrict__ pos, const int *__restrict__ cellOf,
-          const int *__restrict__ cellStart, BoxConst b, GridDev *gp, int cap, uint32_t *__restrict__ raw,
-          int *__restrict__ count, const int *__restrict__ beadOfSlot, const uint64_t *__restrict__ gid,
-          const int *__restrict__ molTypeOfBead, const int *__restrict__ molTypeSingle, const int *__restrict__ bpairOffset,
-          const uint32_t *__restrict__ bpairKey, int haveExcl)
+k_nbr_exact(int nLocal, int nPad, int cap, const double4 *__restrict__ pos, BoxConst b, GridDev *gp, uint32_t *__restrict__ raw,
+            const int *__restrict__ rawCount, uint32_t *__restrict__ out, int *__restrict__ count, uint16_t *__restrict__ cum,
+            const uint64_t *__restrict__ gid, const int *__restrict__ molTypeOfBead, const int *__restrict__ molTypeSingle,
+            const int *__restrict__ bpairOffset, const uint32_t *__restrict__ bpairKey, int haveExcl)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= nIon) return;
-    const int nx = gp->n[0], ny = gp->n[1], nz = gp->n[2];
-    const double4 pi = pos[i];
-    const int c = cellOf[i];
-    const int cx = c % nx, cy = (c / nx) % ny, cz = c / (nx * ny);
-    // only local beads own list rows; ghost rows stay empty (multi-GPU)
-    int cnt = 0;
+    int total = 0;
     if (i < nLocal)
     {
-        const int lx = nx >= 3 ? -1 : 0, hx = nx >= 2 ? 1 : 0;
-        const int ly = ny >= 3 ? -1 : 0, hy = ny >= 2 ? 1 : 0;
-        const int lz = nz >= 3 ? -1 : 0, hz = nz >= 2 ? 1 : 0;
-        for (int dz = lz; dz <= hz; dz++)
-            for (int dy = ly; dy <= hy; dy++)
-                for (int dx = lx; dx <= hx; dx++)
-                {
-                    int ax = cx + dx, ay = cy + dy, az = cz + dz;
-                    ax = ax < 0 ? ax + nx : (ax >= nx ? ax - nx : ax);
-                    ay = ay < 0 ? ay + ny : (ay >= ny ? ay - ny : ay);
-                    az = az < 0 ? az + nz : (az >= nz ? az - nz : az);
-                    const int cc = ax + nx * (ay + ny * az);
-                    const int lo = cellStart[cc], hi = cellStart[cc + 1];
-                    for (int j = lo; j < hi; j++)
-                    {
-                        if (j == i) continue;
-                        const double4 pj = pos[j];
-                        // pairlist1, src/pairlist.c:280-288
-                        double x = __dadd_rn(pi.x, -pj.x), y = __dadd_rn(pi.y, -pj.y), z = __dadd_rn(pi.z, -pj.z);
-                        double r2 = exactR2(x, y, z);
-                        if (r2 > b.R2cut)
-                        {
-                            wrapOnce(x, y, z, b);
-                            r2 = exactR2(x, y, z);
-                        }
-                        if (r2 < b.rlist2)
-                        {
-                            int bin = 0;
+        const int n = min(rawCount[i], cap);
+        const double4 pi = pos[i];
+        const uint64_t wi = (uint64_t)__double_as_longlong(pi.w);
+        uint64_t A = 0ull, B = 0ull;
+        uint32_t jn = (0 < n) ? raw[i] : 0u;
+        for (int k = 0; k < n; k++)
+        {
+            const uint32_t j = jn;
+            if (k + 1 < n) jn = raw[(size_t)(k + 1) * nPad + i];
+            const double4 pj = ldPos256(pos + j);
+            // pairlist1, src/pairlist.c:280-288
+            double x = __dadd_rn(pi.x, -pj.x), y = __dadd_rn(pi.y, -pj.y), z = __dadd_rn(pi.z, -pj.z);
+            double r2 = exactR2(x, y, z);
+            if (r2 > b.R2cut)
+            {
+                wrapOnce(x, y, z, b);
+                r2 = exactR2(x, y, z);
+            }
+            uint32_t ent = RAW_REJECT;
+            if (r2 < b.rlist2)
+            {
+                int bin = 0;
 #pragma unroll
-                            for (int e = 0; e < NBINS - 1; e++) bin += (r2 >= b.binEdge2[e]) ? 1 : 0;
-                            uint32_t ent = (uint32_t)j | ((uint32_t)bin << 27);
-                            if (haveExcl && isPruned(i, j, beadOfSlot, gid, molTypeOfBead, molTypeSingle, bpairOffset, bpairKey))
-                                ent |= EXCL_BIT;
-                            if (cnt < cap) raw[(size_t)cnt * nPad + i] = ent;
-                            cnt++;
-                        }
-                    }
+                for (int e = 0; e < NBINS - 1; e++) bin += (r2 >= b.binEdge2[e]) ? 1 : 0;
+                ent = j | ((uint32_t)bin << 27);
+                if (haveExcl)
+                {
+                    // same molecule? bits 16..31 of w carry the low 16 bits of gid>>32: cheap reject before the gid gathers
+                    const uint64_t wj = (uint64_t)__double_as_longlong(pj.w);
+                    if (((wi ^ wj) & 0xffff0000ull) == 0ull &&
+                        isPruned((int)(wi >> 32), (int)(wj >> 32), gid, molTypeOfBead, molTypeSingle, bpairOffset, bpairKey))
+                        ent |= EXCL_BIT;
                 }
+                const uint64_t one = 1ull << (16 * (bin & 3));
+                if (bin < 4) A += one;
+                else B += one;
+                total++;
+            }
+            raw[(size_t)k * nPad + i] = ent;
+        }
+        // exclusive prefix over the eight counters
+        const uint64_t totA = (A * 0x0001000100010001ull) >> 48;
+        uint64_t offA = A * 0x0001000100010000ull;
+        uint64_t offB = B * 0x0001000100010000ull + totA * 0x0001000100010001ull;
+        // cumulative counts at every bin boundary: entries of bins 0..bnd
+#pragma unroll
+        for (int bnd = 0; bnd < NBINS; bnd++)
+        {
+            const uint64_t off = bnd < 4 ? offA : offB, cnt = bnd < 4 ? A : B;
+            const int sh = 16 * (bnd & 3);
+            cum[(size_t)bnd * nPad + i] = (uint16_t)(((off >> sh) & 0xffffull) + ((cnt >> sh) & 0xffffull));
+        }
+        for (int k = 0; k < n; k++)
+        {
+            const uint32_t e = raw[(size_t)k * nPad + i];
+            if (e == RAW_REJECT) continue;
+            const int bin = (e >> 27) & 7;
+            const int sh = 16 * (bin & 3);
+            int dst;
+            if (bin < 4)
+            {
+                dst = (int)((offA >> sh) & 0xffffull);
+                offA += 1ull << sh;
+            }
+            else
+            {
+                dst = (int)((offB >> sh) & 0xffffull);
+                offB += 1ull << sh;
+            }
+            out[(size_t)dst * nPad + i] = (e & 0x07ffffffu) | (e & EXCL_BIT);
+        }
+        count[i] = total;
     }
-    count[i] = cnt;
-    // statistics + overflow flag
-    int m = cnt;
+    // statistics
+    int m = total;
     for (int o = 16; o > 0; o >>= 1) m = max(m, __shfl_xor_sync(0xffffffffu, m, o));
-    unsigned long long t = (unsigned long long)cnt;
+    unsigned long long t = (unsigned long long)total;
     for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
-    if ((threadIdx.x & 31) == 0)
+    if ((threadIdx.x & 31) == 0 && m > 0)
     {
         atomicMax(&gp->maxCount, m);
         atomicAdd(&gp->totalEntries, t);
-        if (m > cap) atomicOr(&gp->error, 1);
-    }
-}
-
-// ---- 9. order every row by build-time distance bin (stable within a bin) ----------------
-__global__ void __launch_bounds__(128)
-k_nbr_order(int nLocal, int nPad, int cap, const uint32_t *__restrict__ raw, const int *__restrict__ count, uint32_t *__restrict__ out)
-{
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= nLocal) return;
-    const int n = min(count[i], cap);
-    int off[NBINS];
-#pragma unroll
-    for (int k = 0; k < NBINS; k++) off[k] = 0;
-    for (int k = 0; k < n; k++)
-    {
-        const uint32_t e = raw[(size_t)k * nPad + i];
-        const int bin = (e >> 27) & 7;
-#pragma unroll
-        for (int q = 0; q < NBINS; q++) off[q] += (q > bin) ? 1 : 0;   // exclusive prefix, branch-free
-    }
-    for (int k = 0; k < n; k++)
-    {
-        const uint32_t e = raw[(size_t)k * nPad + i];
-        const int bin = (e >> 27) & 7;
-        int dst = 0;
-#pragma unroll
-        for (int q = 0; q < NBINS; q++)
-            if (q == bin) dst = off[q]++;
-        out[(size_t)dst * nPad + i] = (e & 0x07ffffffu) | (e & EXCL_BIT);
     }
 }

@@ -44,6 +44,7 @@ struct GridDev
     int ncell;
     int error;       // sticky error flags (bit0: neighbor capacity overflow, bit1: cell overflow)
     int maxCount;    // max full-list length over beads
+    int maxRaw;      // max candidate count over beads (fp32 filter pass)
     unsigned long long totalEntries;
 };
 
@@ -51,11 +52,17 @@ struct PairConst
 {
     double rc2, R2cut, hxx, hyy, hzz, hhx, hhy, hhz;
     double keR, krf, crf;
+    double rmax;
+    double binEdge[NBINS - 1];   // r edges of the build-time distance bins
     int ntypes;
 };
 
-// packed w of pos4: [0,8) LJ type, [8,16) charge index, [32,64) input (bead) index
-__host__ __device__ inline uint64_t packW(int lj, int qi, uint32_t bead) { return (uint64_t)(lj & 0xff) | ((uint64_t)(qi & 0xff) << 8) | ((uint64_t)bead << 32); }
+// packed w of pos4: [0,8) LJ type, [8,16) charge index, [16,32) low 16 bits of the molecule id (gid >> 32),
+// [32,64) input (bead) index
+__host__ __device__ inline uint64_t packW(int lj, int qi, uint32_t mol, uint32_t bead)
+{
+    return (uint64_t)(lj & 0xff) | ((uint64_t)(qi & 0xff) << 8) | ((uint64_t)(mol & 0xffff) << 16) | ((uint64_t)bead << 32);
+}
 
 struct Term
 {
@@ -151,13 +158,18 @@ struct ddcb200_ctx
 
     // cells
     DevBuf<int> cellOfSlot[2], rank0, cellCount, cellStart, member, perm;
+    DevBuf<uint64_t> orderKey;    // (sub-cell Morton key, bead) : slot order inside a cell
+    DevBuf<float4> pos32;         // fp32 copy of the build-time positions (candidate filter)
+    DevBuf<double> posBuild[3];   // build-time positions, slot order (displacement bound)
+    unsigned long long *dmax2 = nullptr;   // device: bits of max squared displacement since the build
     DevBuf<double> mmPartial;
     GridDev *grid = nullptr;      // device
     GridDev *gridHost = nullptr;  // pinned
 
     // neighbor list
     DevBuf<uint32_t> nbrRaw, nbr;
-    DevBuf<int> nbrCount;
+    DevBuf<int> nbrCount, nbrRawCount;
+    DevBuf<uint16_t> nbrCum;      // [NBINS][nPad] cumulative entries at every distance-bin boundary
     int nbrCap = 0;               // entries per bead allocated
     bool listValid = false;
     int64_t lastBuildLoop = -1;

@@ -18,10 +18,12 @@ template <int MODE>
 __global__ void __launch_bounds__(TILE)
 k_integrate(int nLocal, double4 *__restrict__ pos, double *__restrict__ vx, double *__restrict__ vy, double *__restrict__ vz,
             const double *__restrict__ fx, const double *__restrict__ fy, const double *__restrict__ fz,
-            const double *__restrict__ massOfBead, double halfDt2, double halfDt1, double dt, PairConst pc, double *__restrict__ partial)
+            const double *__restrict__ massOfBead, double halfDt2, double halfDt1, double dt, PairConst pc, double *__restrict__ partial,
+            const double *__restrict__ bx, const double *__restrict__ by, const double *__restrict__ bz, unsigned long long *__restrict__ dmax2)
 {
     const int i = blockIdx.x * TILE + threadIdx.x;
     double ke[7] = {0, 0, 0, 0, 0, 0, 0};
+    double disp2 = 0.0;
     if (i < nLocal)
     {
         double4 p = pos[i];
@@ -65,12 +67,32 @@ k_integrate(int nLocal, double4 *__restrict__ pos, double *__restrict__ vx, doub
             if (p.z > pc.hhz) p.z -= pc.hzz;
             if (p.z < -pc.hhz) p.z += pc.hzz;
             pos[i] = p;
+            // displacement since the list build (nearest image): bounds which list bins k_pair must visit
+            double dx = p.x - bx[i], dy = p.y - by[i], dz = p.z - bz[i];
+            if (dx > pc.hhx) dx -= pc.hxx;
+            if (dx < -pc.hhx) dx += pc.hxx;
+            if (dy > pc.hhy) dy -= pc.hyy;
+            if (dy < -pc.hhy) dy += pc.hyy;
+            if (dz > pc.hhz) dz -= pc.hzz;
+            if (dz < -pc.hhz) dz += pc.hzz;
+            disp2 = dx * dx + dy * dy + dz * dz;
         }
         if (MODE & (INT_KICK2 | INT_KICK1_DRIFT))
         {
             vx[i] = v0;
             vy[i] = v1;
             vz[i] = v2;
+        }
+    }
+    if (MODE & INT_KICK1_DRIFT)
+    {
+        // non-negative doubles order like their bit patterns: one integer atomicMax per warp
+        // (the running maximum is read first, so almost every warp skips the same-address atomic)
+        for (int o = 16; o > 0; o >>= 1) disp2 = fmax(disp2, __shfl_xor_sync(0xffffffffu, disp2, o));
+        if ((threadIdx.x & 31) == 0)
+        {
+            const unsigned long long bits = (unsigned long long)__double_as_longlong(disp2);
+            if (bits > *(volatile unsigned long long *)dmax2) atomicMax(dmax2, bits);
         }
     }
     if (MODE & INT_KE)

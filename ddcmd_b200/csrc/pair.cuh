@@ -20,9 +20,12 @@ __device__ __forceinline__ double4 ldPos(const double4 *p)
     return r;
 }
 
+#define PF 4   // gathers in flight per thread
+
 template <bool ENERGY>
 __global__ void __launch_bounds__(TILE)
-k_pair(int nLocal, int nPad, const double4 *__restrict__ pos, const uint32_t *__restrict__ nbr, const int *__restrict__ count,
+k_pair(int nLocal, int nPad, const double4 *__restrict__ pos, const uint32_t *__restrict__ nbr, const uint16_t *__restrict__ cum,
+       const unsigned long long *__restrict__ dmax2,
        const double2 *__restrict__ ljTab, const double *__restrict__ shiftTab, const double *__restrict__ qTab, PairConst pc,
        double *__restrict__ fx, double *__restrict__ fy, double *__restrict__ fz, double *__restrict__ accPartial)
 {
@@ -46,26 +49,47 @@ k_pair(int nLocal, int nPad, const double4 *__restrict__ pos, const uint32_t *__
     const double qi = sQ[(wi >> 8) & 0xff];
     const double kqi = pc.keR * qi;
     const double2 *ljRow = sLJ + ti * pc.ntypes;
-    int n = live ? count[ii] : 0;
+    // Rows are ordered by build-time distance bin.  A pair listed at distance r_build can only be inside the
+    // cutoff now if r_build - 2*dmax < rmax, dmax = largest displacement of any bead since the build (measured
+    // by k_integrate): bins that start beyond rmax + 2*dmax are not even loaded.  Exact, not a heuristic.
+    int binLimit = 0;
+    {
+        const double lim = (pc.rmax + 2.0 * sqrt(__longlong_as_double((long long)*dmax2))) * (1.0 + 1e-12);
+#pragma unroll
+        for (int e = 0; e < NBINS - 1; e++) binLimit += (pc.binEdge[e] < lim) ? 1 : 0;
+    }
+    int n = live ? (int)cum[(size_t)binLimit * nPad + ii] : 0;
     int nmax = n;
     for (int o = 16; o > 0; o >>= 1) nmax = max(nmax, __shfl_xor_sync(0xffffffffu, nmax, o));
 
     double fxi = 0.0, fyi = 0.0, fzi = 0.0;
     double eLJ = 0.0, eEle = 0.0, vxx = 0.0, vyy = 0.0, vzz = 0.0, vxy = 0.0, vxz = 0.0, vyz = 0.0;
 
-    // software pipeline: entry k+2 and position k+1 are in flight while pair k is computed
+    // The walk is latency-bound on the dependent chain entry -> j position (ncu: >60% of stall samples on the first
+    // use of the gathered position), so PF gathers are issued back to back before any is consumed, and the entries
+    // of the next chunk are already in flight.
     const uint32_t *row = nbr + ii;
-    uint32_t eCur = (0 < n) ? row[0] : (uint32_t)ii;
-    uint32_t eNext = (1 < n) ? row[(size_t)nPad] : (uint32_t)ii;
-    double4 pNext = ldPos(pos + (eCur & 0x07ffffffu));
-    for (int k = 0; k < nmax; k++)
+    uint32_t eNext[PF];
+#pragma unroll
+    for (int u = 0; u < PF; u++) eNext[u] = (u < n) ? row[(size_t)u * nPad] : (uint32_t)ii;
+    for (int k0 = 0; k0 < nmax; k0 += PF)
     {
-        const uint32_t e = eCur;
-        const double4 pj = pNext;
-        eCur = eNext;
-        pNext = ldPos(pos + (eCur & 0x07ffffffu));
-        if (k + 2 < n) eNext = row[(size_t)(k + 2) * nPad];
-        else eNext = (uint32_t)ii;
+        uint32_t eCur[PF];
+        double4 pCur[PF];
+#pragma unroll
+        for (int u = 0; u < PF; u++)
+        {
+            eCur[u] = eNext[u];
+            pCur[u] = ldPos(pos + (eCur[u] & 0x07ffffffu));
+        }
+#pragma unroll
+        for (int u = 0; u < PF; u++) eNext[u] = (k0 + PF + u < n) ? row[(size_t)(k0 + PF + u) * nPad] : (uint32_t)ii;
+#pragma unroll
+        for (int u = 0; u < PF; u++)
+        {
+        const int k = k0 + u;
+        const uint32_t e = eCur[u];
+        const double4 pj = pCur[u];
         const bool valid = k < n;
         double x = pi.x - pj.x, y = pi.y - pj.y, z = pi.z - pj.z;
         double r2 = x * x + y * y + z * z;
@@ -128,6 +152,7 @@ k_pair(int nLocal, int nPad, const double4 *__restrict__ pos, const uint32_t *__
                 vxz += fxij * z;
                 vyz += fyij * z;
             }
+        }
         }
     }
     if (live)
