@@ -65,6 +65,20 @@ class DdcError(RuntimeError):
     pass
 
 
+def _preload_nccl():
+    """libddcmd_b200.so needs libnccl.so.2.  When PyTorch is installed its bundled NCCL (newer than the system
+    one) must be the copy the process loads first, or a later `import torch` fails on missing symbols."""
+    try:
+        import importlib.util
+        spec = importlib.util.find_spec("nvidia.nccl")
+        if spec and spec.submodule_search_locations:
+            cand = os.path.join(list(spec.submodule_search_locations)[0], "lib", "libnccl.so.2")
+            if os.path.exists(cand):
+                C.CDLL(cand, mode=C.RTLD_GLOBAL)
+    except Exception:
+        pass   # the system libnccl.so.2 is resolved by the loader
+
+
 def lib():
     """Load libddcmd_b200.so (building it in-tree with nvcc when sources are newer)."""
     global _lib
@@ -77,6 +91,7 @@ def lib():
         except Exception as e:  # a prebuilt .so that travelled with the snapshot is still usable
             if not os.path.exists(path):
                 raise DdcError("libddcmd_b200.so is missing and could not be built: %s" % e)
+    _preload_nccl()
     L = C.CDLL(path)
     vp, i32, i64, dbl = C.c_void_p, C.c_int, C.c_int64, C.c_double
     pd, pi = _P(C.c_double), _P(C.c_int)
@@ -110,10 +125,12 @@ def lib():
         "ddcb200_kernelLaunches": (i64, [vp]),
         "ddcb200_ncclUniqueId": (i32, [C.c_char_p]),
         "ddcb200_ddcInit": (i32, [vp, i32, i32, i32, i32, i32, C.c_char_p]),
+        "ddcb200_ddcPlan": (i32, [pd, i32, i32, i32, dbl, i64, pd, pd, pd, pi, i32, pi, _P(C.c_uint32)]),
         "ddcb200_deckLoad": (i32, [C.c_char_p, C.c_char_p, C.c_char_p, _P(_P(DeckStruct))]),
         "ddcb200_deckFree": (None, [_P(DeckStruct)]),
         "ddcb200_lastHostError": (C.c_char_p, []),
         "ddcb200_simulateBind": (i32, [_P(DeckStruct), i32, _P(vp)]),
+        "ddcb200_simulateBindRank": (i32, [_P(DeckStruct), i32, i32, i32, i32, i32, i32, C.c_char_p, _P(vp)]),
         "ddcb200_printinfoLine": (i32, [_P(DeckStruct), _P(EType), C.c_char_p, C.c_size_t]),
         "ddcb200_unitsConvert": (dbl, [dbl, C.c_char_p, C.c_char_p]),
     }
@@ -130,8 +147,8 @@ EXPORTS = ["ddcb200_lastError", "ddcb200_deviceCount", "ddcb200_create", "ddcb20
            "ddcb200_martiniBondParms", "ddcb200_setRestraints", "ddcb200_setMolecules", "ddcb200_sendState",
            "ddcb200_numLocal", "ddcb200_getLocalBeads", "ddcb200_getState", "ddcb200_constructList", "ddcb200_ddcenergy",
            "ddcb200_nglf", "ddcb200_energyInfo", "ddcb200_getCells", "ddcb200_getPairs", "ddcb200_profile",
-           "ddcb200_profileRead", "ddcb200_timerRecord", "ddcb200_timerElapsed", "ddcb200_kernelLaunches", "ddcb200_ncclUniqueId", "ddcb200_ddcInit", "ddcb200_deckLoad", "ddcb200_deckFree",
-           "ddcb200_lastHostError", "ddcb200_simulateBind", "ddcb200_printinfoLine", "ddcb200_unitsConvert"]
+           "ddcb200_profileRead", "ddcb200_timerRecord", "ddcb200_timerElapsed", "ddcb200_kernelLaunches", "ddcb200_ncclUniqueId", "ddcb200_ddcInit", "ddcb200_ddcPlan", "ddcb200_deckLoad", "ddcb200_deckFree",
+           "ddcb200_lastHostError", "ddcb200_simulateBind", "ddcb200_simulateBindRank", "ddcb200_printinfoLine", "ddcb200_unitsConvert"]
 
 
 def _arr(ptr, n, dtype):
@@ -206,13 +223,18 @@ class Simulate:
     is ``kinetic_terms`` + ``eval_energyInfo`` (+ molecular pressure).
     """
 
-    def __init__(self, deck, device=0):
+    def __init__(self, deck, device=0, rank=0, nranks=1, lattice=None, nccl_id=None):
         L = lib()
         if L.ddcb200_deviceCount() <= 0:
             raise DdcError("no CUDA device: ddcmd_b200 has no CPU path")
         self.deck = deck
         self.ctx = C.c_void_p()
-        rc = L.ddcb200_simulateBind(deck._p, device, C.byref(self.ctx))
+        self.rank, self.nranks = rank, nranks
+        if nranks == 1:
+            rc = L.ddcb200_simulateBind(deck._p, device, C.byref(self.ctx))
+        else:
+            lx, ly, lz = lattice or default_lattice(nranks, [deck.s.params.h[0], deck.s.params.h[4], deck.s.params.h[8]])
+            rc = L.ddcb200_simulateBindRank(deck._p, device, rank, nranks, lx, ly, lz, bytes(nccl_id), C.byref(self.ctx))
         if rc != 0:
             raise DdcError(L.ddcb200_lastHostError().decode())
         self.dt = deck.s.dt
@@ -250,6 +272,12 @@ class Simulate:
         a = [np.ascontiguousarray(x, np.float64) for x in (rx, ry, rz, vx, vy, vz)]
         pd = _P(C.c_double)
         self._ck(lib().ddcb200_sendState(self.ctx, a[0].size, None, *[x.ctypes.data_as(pd) for x in a], int(loop), float(time)))
+
+    def getLocalBeads(self):
+        n = int(lib().ddcb200_numLocal(self.ctx))
+        bead = np.empty(n, np.int32)
+        self._ck(lib().ddcb200_getLocalBeads(self.ctx, bead.ctypes.data_as(_P(C.c_int))))
+        return bead
 
     def getState(self):
         n = int(lib().ddcb200_numLocal(self.ctx))
@@ -304,6 +332,51 @@ class Simulate:
         return buf.value.decode()
 
 
-def simulate_init(object_file, restart_file=None, device=0, simulate_name=None):
+def nccl_unique_id():
+    """128 bytes made on rank 0 (ncclGetUniqueId); distribute them to every rank before Simulate(..., nccl_id=)."""
+    buf = C.create_string_buffer(128)
+    L = lib()
+    if L.ddcb200_ncclUniqueId(buf) != 0:
+        raise DdcError(L.ddcb200_lastError().decode())
+    return buf.raw
+
+
+def default_lattice(nranks, box):
+    """DDC lx ly lz when the deck gives none: split the longest box edges first (membranes: in the plane)."""
+    lat = [1, 1, 1]
+    n = nranks
+    f = 2
+    factors = []
+    while n > 1:
+        while n % f == 0:
+            factors.append(f)
+            n //= f
+        f += 1
+    for f in sorted(factors, reverse=True):
+        a = max(range(3), key=lambda k: box[k] / lat[k])
+        lat[a] *= f
+    return tuple(lat)
+
+
+def ddc_plan(h, lattice, rlist, rx, ry, rz, rank, owner_bead=None):
+    """Host restatement of the domain classification (ddcb200_ddcPlan): returns (owner, mask)."""
+    n = len(rx)
+    a = [np.ascontiguousarray(x, np.float64) for x in (rx, ry, rz)]
+    hh = np.ascontiguousarray(h, np.float64)
+    owner = np.empty(n, np.int32)
+    mask = np.empty(n, np.uint32)
+    ob = np.ascontiguousarray(owner_bead, np.int32) if owner_bead is not None else None
+    pd, pi = _P(C.c_double), _P(C.c_int)
+    L = lib()
+    rc = L.ddcb200_ddcPlan(hh.ctypes.data_as(pd), int(lattice[0]), int(lattice[1]), int(lattice[2]), float(rlist), n,
+                           a[0].ctypes.data_as(pd), a[1].ctypes.data_as(pd), a[2].ctypes.data_as(pd),
+                           ob.ctypes.data_as(pi) if ob is not None else None, int(rank), owner.ctypes.data_as(pi),
+                           mask.ctypes.data_as(_P(C.c_uint32)))
+    if rc != 0:
+        raise DdcError(L.ddcb200_lastError().decode())
+    return owner, mask
+
+
+def simulate_init(object_file, restart_file=None, device=0, simulate_name=None, rank=0, nranks=1, lattice=None, nccl_id=None):
     """Mirror of simulate_init(NULL, name, comm) (src/simulate.c:104) for a Martini deck."""
-    return Simulate(Deck(object_file, restart_file, simulate_name), device)
+    return Simulate(Deck(object_file, restart_file, simulate_name), device, rank, nranks, lattice, nccl_id)

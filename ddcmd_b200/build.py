@@ -60,7 +60,7 @@ def build(force=False, verbose=False):
             print(" ".join(cmd))
         subprocess.check_call(cmd)
         objs.append(o)
-    cmd = [nvcc, "-shared", "-o", LIB] + objs + ["-lcudart", "-lm"]
+    cmd = [nvcc, "-shared", "-o", LIB] + objs + ["-lcudart", "-lnccl", "-lm"]
     if verbose:
         print(" ".join(cmd))
     subprocess.check_call(cmd)

@@ -6,6 +6,8 @@
 #include "pair.cuh"
 #include "bonded.cuh"
 #include "integrate.cuh"
+#include "ddc.cuh"
+#include <nccl.h>
 #include <math.h>
 #include <string.h>
 #include <algorithm>
@@ -23,6 +25,13 @@ static int fail(int code, const std::string &msg)
         cudaError_t e__ = (call);                                                                        \
         if (e__ != cudaSuccess)                                                                          \
             return fail(DDCB200_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e__));          \
+    } while (0)
+#define CKN(call)                                                                                        \
+    do                                                                                                   \
+    {                                                                                                    \
+        ncclResult_t r__ = (call);                                                                       \
+        if (r__ != ncclSuccess)                                                                          \
+            return fail(DDCB200_ERR_NCCL, std::string(#call) + ": " + ncclGetErrorString(r__));          \
     } while (0)
 #define CKL(what)                                                                                        \
     do                                                                                                   \
@@ -195,7 +204,9 @@ extern "C" int ddcb200_create(const ddcb200_params *p, ddcb200_ctx **out)
     CK(cudaMallocHost((void **)&c->gridHost, sizeof(GridDev)));
     CK(cudaMalloc((void **)&c->acc, ACC_N * sizeof(double)));
     CK(cudaMemset(c->acc, 0, ACC_N * sizeof(double)));
-    CK(cudaMallocHost((void **)&c->accHost, ACC_N * sizeof(double)));
+    CK(cudaMallocHost((void **)&c->accHost, (ACC_N + 8) * sizeof(double)));
+    CK(cudaMallocHost((void **)&c->ddcHost, 64 * sizeof(int)));
+    CK(cudaMalloc((void **)&c->ddcCounters, 8 * sizeof(int)));
     CK(cudaMalloc((void **)&c->dmax2, sizeof(unsigned long long)));
     CK(cudaMemset(c->dmax2, 0, sizeof(unsigned long long)));
     *out = c;
@@ -225,6 +236,15 @@ extern "C" void ddcb200_destroy(ddcb200_ctx *c)
     c->orderKey.release(); c->pos32.release(); c->nbrRawCount.release(); c->nbrCum.release();
     for (int a = 0; a < 3; a++) c->posBuild[a].release();
     if (c->dmax2) cudaFree(c->dmax2);
+    c->ownerBead.release(); c->gState.release(); c->ownerOfBead.release(); c->ddcMask.release(); c->ddcCnt.release();
+    c->ddcColTotal.release(); c->ddcColStart.release(); c->ddcList.release(); c->sendSlot.release(); c->recvSlot.release();
+    c->sendBuf.release(); c->recvBuf.release(); c->accG.release();
+    if (c->boxEnc) cudaFree(c->boxEnc);
+    if (c->boxes) cudaFree(c->boxes);
+    if (c->ddcCounters) cudaFree(c->ddcCounters);
+    if (c->ddcHost) cudaFreeHost(c->ddcHost);
+    if (c->boxInitHost) cudaFreeHost(c->boxInitHost);
+    if (c->nccl) ncclCommDestroy((ncclComm_t)c->nccl);
     for (auto &pe : c->pending)
     {
         cudaEventDestroy(pe.a);
@@ -433,6 +453,9 @@ extern "C" int ddcb200_setMolecules(ddcb200_ctx *c, int64_t nMol, const int64_t 
     CK(cudaSetDevice(c->device));
     c->nMol = nMol;
     c->nMolTotal = nMolTotal;
+    c->hMolOffset.assign(molOffset, molOffset + (nMol ? nMol + 1 : 0));
+    c->hMolBeads.assign(molBeads, molBeads + (nMol ? molOffset[nMol] : 0));
+    c->ownerBeadValid = false;
     if (nMol)
     {
         CK(c->molOffset.ensure((size_t)nMol + 1));
@@ -505,14 +528,42 @@ extern "C" int ddcb200_sendState(ddcb200_ctx *c, int64_t nLocal, const int *bead
     c->listValid = false;
     c->forcesValid = false;
     c->energyValid = false;
+    c->haloDirty = false;
+    c->localsDirty = false;
     return DDCB200_OK;
 }
 
-extern "C" int64_t ddcb200_numLocal(ddcb200_ctx *c) { return c ? c->nLocal : 0; }
+// After a re-domain the set of local beads has changed: list them (slot order is not meaningful to callers).
+static int refreshLocals(ddcb200_ctx *c)
+{
+    if (!c->localsDirty) return DDCB200_OK;
+    cudaStream_t st = c->stream;
+    CK(c->stageI.ensure((size_t)c->nIon));
+    CK(cudaMemsetAsync(c->ddcCounters + 4, 0, sizeof(int), st));
+    k_ddc_list_locals<<<(int)((c->nIon + 255) / 256), 256, 0, st>>>((int)c->nIon, c->pos4[c->cur].p, c->ddcCounters + 4, c->stageI.p);
+    CKL("k_ddc_list_locals");
+    CK(cudaMemcpyAsync(c->ddcHost + 4, c->ddcCounters + 4, sizeof(int), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    c->nLocal = c->ddcHost[4];
+    c->hLocalBeads.resize((size_t)c->nLocal);
+    if (c->nLocal) CK(cudaMemcpy(c->hLocalBeads.data(), c->stageI.p, c->nLocal * sizeof(int), cudaMemcpyDeviceToHost));
+    c->localsDirty = false;
+    return DDCB200_OK;
+}
+
+extern "C" int64_t ddcb200_numLocal(ddcb200_ctx *c)
+{
+    if (!c) return 0;
+    if (c->localsDirty && (cudaSetDevice(c->device) != cudaSuccess || refreshLocals(c) != DDCB200_OK)) return -1;
+    return c->nLocal;
+}
 
 extern "C" int ddcb200_getLocalBeads(ddcb200_ctx *c, int *bead)
 {
     if (!c || !bead) return fail(DDCB200_ERR_ARG, "null argument");
+    CK(cudaSetDevice(c->device));
+    int rcl = refreshLocals(c);
+    if (rcl) return rcl;
     std::copy(c->hLocalBeads.begin(), c->hLocalBeads.end(), bead);
     return DDCB200_OK;
 }
@@ -523,6 +574,8 @@ extern "C" int ddcb200_getState(ddcb200_ctx *c, double *rx, double *ry, double *
     if (!c) return fail(DDCB200_ERR_ARG, "null ctx");
     if (c->nLocal == 0) return fail(DDCB200_ERR_STATE, "no state");
     CK(cudaSetDevice(c->device));
+    int rcl = refreshLocals(c);
+    if (rcl) return rcl;
     const int64_t n = c->nLocal;
     const int cur = c->cur;
     CK(c->stage.ensure((size_t)n * 9));
@@ -537,6 +590,148 @@ extern "C" int ddcb200_getState(ddcb200_ctx *c, double *rx, double *ry, double *
     return DDCB200_OK;
 }
 
+// ---- multi-GPU: re-domain and halo (ddc.cuh) ----------------------------------------------
+static DdcGeom ddcGeomOf(const ddcb200_ctx *c)
+{
+    DdcGeom g;
+    g.nranks = c->nranks;
+    g.me = c->rank;
+    for (int a = 0; a < 3; a++) g.lat[a] = c->lat[a];
+    g.L[0] = c->box.hxx; g.L[1] = c->box.hyy; g.L[2] = c->box.hzz;
+    for (int a = 0; a < 3; a++) g.hL[a] = 0.5 * g.L[a];
+    g.rlist2 = c->box.rlist2 * (1.0 + 1e-9);
+    return g;
+}
+
+static void buildOwnerBead(const std::vector<int64_t> &molOffset, const std::vector<int> &molBeads, int64_t nGlobal, std::vector<int> &ob)
+{
+    // ddcRuleMolecule / bioMartiniRule: a molecule follows its ownership bead (first listed bead); beads of
+    // unlisted (single-bead) molecules own themselves
+    ob.resize((size_t)nGlobal);
+    for (int64_t b = 0; b < nGlobal; b++) ob[(size_t)b] = (int)b;
+    const int64_t nMol = molOffset.empty() ? 0 : (int64_t)molOffset.size() - 1;
+    for (int64_t m = 0; m < nMol; m++)
+        for (int64_t k = molOffset[m]; k < molOffset[m + 1]; k++) ob[(size_t)molBeads[(size_t)k]] = molBeads[(size_t)molOffset[m]];
+}
+
+static int ensureState(ddcb200_ctx *c, int64_t nIon);
+
+static int redomain(ddcb200_ctx *c)
+{
+    cudaStream_t st = c->stream;
+    ncclComm_t comm = (ncclComm_t)c->nccl;
+    const int64_t nG = c->nGlobal;
+    const DdcGeom g = ddcGeomOf(c);
+    const int nb = (int)((nG + 255) / 256);
+    if (!c->ownerBeadValid)
+    {
+        std::vector<int> ob;
+        buildOwnerBead(c->hMolOffset, c->hMolBeads, nG, ob);
+        CK(c->ownerBead.ensure((size_t)nG));
+        CK(cudaMemcpy(c->ownerBead.p, ob.data(), nG * sizeof(int), cudaMemcpyHostToDevice));
+        c->ownerBeadValid = true;
+    }
+    CK(c->gState.ensure((size_t)nG * 6));
+    CK(c->ownerOfBead.ensure((size_t)nG));
+    CK(c->ddcMask.ensure((size_t)nG));
+    // 1. replicate the dynamic state: scatter my beads into zeros, sum over ranks (one contributor per element)
+    const int cur = c->cur;
+    CK(cudaMemsetAsync(c->gState.p, 0, (size_t)nG * 6 * sizeof(double), st));
+    k_ddc_scatter<<<(int)((c->nIon + 255) / 256), 256, 0, st>>>((int)c->nIon, nG, c->pos4[cur].p, c->vel[cur][0].p, c->vel[cur][1].p,
+                                                                c->vel[cur][2].p, c->gState.p);
+    CKL("k_ddc_scatter");
+    CKN(ncclAllReduce(c->gState.p, c->gState.p, (size_t)nG * 6, ncclDouble, ncclSum, comm, st));
+    // 2. owners and bounding boxes, identically on every rank
+    CK(cudaMemcpyAsync(c->boxEnc, c->boxInitHost, DDC_MAXRANKS * 6 * sizeof(unsigned long long), cudaMemcpyHostToDevice, st));
+    k_ddc_owner<<<nb, 256, 0, st>>>(nG, c->gState.p, c->ownerBead.p, g, c->ownerOfBead.p, c->boxEnc);
+    CKL("k_ddc_owner");
+    k_ddc_boxes<<<1, 128, 0, st>>>(c->nranks, c->boxEnc, (DdcBoxes *)c->boxes);
+    CKL("k_ddc_boxes");
+    // 3. classify
+    CK(cudaMemsetAsync(c->ddcCounters, 0, 8 * sizeof(int), st));
+    k_ddc_mask<<<nb, 256, 0, st>>>(nG, c->gState.p, c->ownerOfBead.p, g, (const DdcBoxes *)c->boxes, c->ddcMask.p, c->ddcCounters);
+    CKL("k_ddc_mask");
+    CK(cudaMemcpyAsync(c->ddcHost, c->ddcCounters, 2 * sizeof(int), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    const int64_t nLocal = c->ddcHost[0], nGhost = c->ddcHost[1];
+    if (nLocal <= 0) return fail(DDCB200_ERR_STATE, "a rank owns no beads after the domain assignment (fewer bricks than the system can fill)");
+    int rc = ensureState(c, nLocal + nGhost);
+    if (rc) return rc;
+    c->nLocal = nLocal;
+    c->nIon = nLocal + nGhost;
+    // 4. slot arrays from the replicated state
+    CK(cudaMemsetAsync(c->slotOfBead.p, 0xff, nG * sizeof(int), st));
+    k_ddc_select<<<nb, 256, 0, st>>>(nG, c->gState.p, c->ddcMask.p, c->wOfBead.p, c->ddcCounters + 2, c->pos4[cur].p, c->vel[cur][0].p,
+                                     c->vel[cur][1].p, c->vel[cur][2].p, c->beadOfSlot[cur].p, c->slotOfBead.p);
+    CKL("k_ddc_select");
+    // 5. send / recv lists in ascending bead order: columns = [send to p (p != me)...] then [recv from p ...]
+    uint32_t colBits = 0u;
+    int ncol = 0;
+    for (int pp = 0; pp < c->nranks; pp++)
+        if (pp != c->rank) { colBits |= 1u << pp; colBits |= 1u << (16 + pp); ncol += 2; }
+    const int nUnits = (int)((nG + 31) / 32);
+    CK(c->ddcCnt.ensure((size_t)ncol * nUnits));
+    CK(c->ddcColTotal.ensure(32));
+    CK(c->ddcColStart.ensure(32));
+    k_ddc_colcount<<<nb, 256, 0, st>>>(nG, c->ddcMask.p, colBits, nUnits, c->ddcCnt.p);
+    CKL("k_ddc_colcount");
+    k_ddc_colscan<<<ncol, 1024, 0, st>>>(nUnits, c->ddcCnt.p, c->ddcColTotal.p);
+    CKL("k_ddc_colscan");
+    CK(cudaMemcpyAsync(c->ddcHost + 8, c->ddcColTotal.p, ncol * sizeof(int), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    c->hSendCount.assign(c->nranks, 0); c->hRecvCount.assign(c->nranks, 0);
+    c->hSendOff.assign(c->nranks, 0); c->hRecvOff.assign(c->nranks, 0);
+    int *colStart = c->ddcHost + 40;
+    int run = 0, col = 0;
+    for (int pp = 0; pp < c->nranks; pp++)
+        if (pp != c->rank) { c->hSendCount[pp] = c->ddcHost[8 + col]; c->hSendOff[pp] = run; colStart[col] = run; run += c->hSendCount[pp]; col++; }
+    c->nSendTot = run;
+    for (int pp = 0; pp < c->nranks; pp++)
+        if (pp != c->rank) { c->hRecvCount[pp] = c->ddcHost[8 + col]; c->hRecvOff[pp] = run - c->nSendTot; colStart[col] = run; run += c->hRecvCount[pp]; col++; }
+    c->nRecvTot = run - c->nSendTot;
+    if (c->nRecvTot != nGhost) return fail(DDCB200_ERR_STATE, "ghost count and receive lists disagree");
+    CK(cudaMemcpyAsync(c->ddcColStart.p, colStart, ncol * sizeof(int), cudaMemcpyHostToDevice, st));
+    CK(c->ddcList.ensure((size_t)run + 1));
+    CK(c->sendSlot.ensure((size_t)c->nSendTot + 1));
+    CK(c->recvSlot.ensure((size_t)c->nRecvTot + 1));
+    CK(c->sendBuf.ensure((size_t)c->nSendTot * 3 + 1));
+    CK(c->recvBuf.ensure((size_t)c->nRecvTot * 3 + 1));
+    k_ddc_colscatter<<<nb, 256, 0, st>>>(nG, c->ddcMask.p, colBits, nUnits, c->ddcCnt.p, c->ddcColStart.p, c->ddcList.p);
+    CKL("k_ddc_colscatter");
+    c->localsDirty = true;
+    return DDCB200_OK;
+}
+
+// ddcUpdate (src/ddcUpdate.c:40-88): owners send the new positions of the beads their neighbours hold as ghosts
+static int haloExchange(ddcb200_ctx *c)
+{
+    ProfScope ps(c, PROF_HALO);
+    cudaStream_t st = c->stream;
+    ncclComm_t comm = (ncclComm_t)c->nccl;
+    const int cur = c->cur;
+    if (c->nSendTot)
+    {
+        k_halo_pack<<<(c->nSendTot + 255) / 256, 256, 0, st>>>(c->nSendTot, c->sendSlot.p, c->pos4[cur].p, c->sendBuf.p);
+        CKL("k_halo_pack");
+    }
+    CKN(ncclGroupStart());
+    for (int pp = 0; pp < c->nranks; pp++)
+    {
+        if (pp == c->rank) continue;
+        if (c->hSendCount[pp]) CKN(ncclSend(c->sendBuf.p + 3 * (size_t)c->hSendOff[pp], 3 * (size_t)c->hSendCount[pp], ncclDouble, pp, comm, st));
+        if (c->hRecvCount[pp]) CKN(ncclRecv(c->recvBuf.p + 3 * (size_t)c->hRecvOff[pp], 3 * (size_t)c->hRecvCount[pp], ncclDouble, pp, comm, st));
+    }
+    CKN(ncclGroupEnd());
+    if (c->nRecvTot)
+    {
+        k_halo_unpack<<<(c->nRecvTot + 255) / 256, 256, 0, st>>>(c->nRecvTot, c->recvSlot.p, c->recvBuf.p, c->pos4[cur].p, c->posBuild[0].p,
+                                                                 c->posBuild[1].p, c->posBuild[2].p, c->pc, c->dmax2);
+        CKL("k_halo_unpack");
+    }
+    c->haloDirty = false;
+    return DDCB200_OK;
+}
+
 // ---- list build -------------------------------------------------------------------------
 extern "C" int ddcb200_constructList(ddcb200_ctx *c)
 {
@@ -545,6 +740,11 @@ extern "C" int ddcb200_constructList(ddcb200_ctx *c)
     if (c->ntypes == 0) return fail(DDCB200_ERR_STATE, "martiniNonBondParms not called");
     CK(cudaSetDevice(c->device));
     ProfScope ps(c, PROF_LIST);
+    if (c->nranks > 1)
+    {
+        int rcd = redomain(c);
+        if (rcd) return rcd;
+    }
     const int nIon = (int)c->nIon, nLocal = (int)c->nLocal, nPad = (int)c->nPad;
     const int cur = c->cur, nxt = cur ^ 1;
     cudaStream_t st = c->stream;
@@ -577,10 +777,10 @@ extern "C" int ddcb200_constructList(ddcb200_ctx *c)
     {
         CK(c->nbrRaw.ensure((size_t)c->nbrCap * nPad));
         CK(c->nbr.ensure((size_t)c->nbrCap * nPad));
-        k_nbr_filter<<<nPad / 128, 128, 0, st>>>(nLocal, nPad, c->pos32.p, c->cellOfSlot[nxt].p, c->cellStart.p, c->box, rl2f, c->grid,
+        k_nbr_filter<<<nPad / 128, 128, 0, st>>>(nIon, nPad, c->pos32.p, c->cellOfSlot[nxt].p, c->cellStart.p, c->box, rl2f, c->grid,
                                                 c->nbrCap, c->nbrRaw.p, c->nbrRawCount.p);
         CKL("k_nbr_filter");
-        k_nbr_exact<<<nPad / 128, 128, 0, st>>>(nLocal, nPad, c->nbrCap, c->pos4[nxt].p, c->box, c->grid, c->nbrRaw.p, c->nbrRawCount.p,
+        k_nbr_exact<<<nPad / 128, 128, 0, st>>>(nIon, nPad, c->nbrCap, c->pos4[nxt].p, c->box, c->grid, c->nbrRaw.p, c->nbrRawCount.p,
                                                c->nbr.p, c->nbrCount.p, c->nbrCum.p, c->gidOfBead.p, c->molTypeOfBead.p,
                                                c->molTypeSingle.p, c->bpairOffset.p, c->bpairKey.p, c->haveExcl ? 1 : 0);
         CKL("k_nbr_exact");
@@ -598,16 +798,33 @@ extern "C" int ddcb200_constructList(ddcb200_ctx *c)
     }
     if (c->nTerms)
     {
-        k_terms_remap<<<(int)((c->nTerms + 255) / 256), 256, 0, st>>>(c->nTerms, c->termsBead.p, c->termsSlot.p, c->slotOfBead.p);
+        k_terms_remap<<<(int)((c->nTerms + 255) / 256), 256, 0, st>>>(c->nTerms, c->termsBead.p, c->termsSlot.p, c->slotOfBead.p,
+                                                                      c->pos4[nxt].p);
         CKL("k_terms_remap");
     }
     if (c->nRestr)
     {
-        k_restr_remap<<<(int)((c->nRestr + 255) / 256), 256, 0, st>>>(c->nRestr, c->restrBead.p, c->restrSlot.p, c->slotOfBead.p);
+        k_restr_remap<<<(int)((c->nRestr + 255) / 256), 256, 0, st>>>(c->nRestr, c->restrBead.p, c->restrSlot.p, c->slotOfBead.p,
+                                                                      c->pos4[nxt].p);
         CKL("k_restr_remap");
+    }
+    if (c->nranks > 1)
+    {
+        if (c->nSendTot)
+        {
+            k_ddc_toslots<<<(c->nSendTot + 255) / 256, 256, 0, st>>>(c->nSendTot, c->ddcList.p, c->slotOfBead.p, c->sendSlot.p);
+            CKL("k_ddc_toslots");
+        }
+        if (c->nRecvTot)
+        {
+            k_ddc_toslots<<<(c->nRecvTot + 255) / 256, 256, 0, st>>>(c->nRecvTot, c->ddcList.p + c->nSendTot, c->slotOfBead.p, c->recvSlot.p);
+            CKL("k_ddc_toslots");
+        }
+        c->haloDirty = false;   // the replicated state carried the current positions of every ghost
     }
     c->listValid = true;
     c->lastBuildLoop = c->loop;
+    c->totalEntries = (int64_t)c->gridHost->totalEntries;
     c->nPairsListed = (int64_t)(c->gridHost->totalEntries / 2);
     return DDCB200_OK;
 }
@@ -647,9 +864,14 @@ extern "C" int ddcb200_ddcenergy(ddcb200_ctx *c, int withEnergy)
         rc = ddcb200_constructList(c);
         if (rc) return rc;
     }
+    else if (c->nranks > 1 && c->haloDirty)
+    {
+        rc = haloExchange(c);
+        if (rc) return rc;
+    }
     cudaStream_t st = c->stream;
     const int cur = c->cur;
-    const int nLocal = (int)c->nLocal, nPad = (int)c->nPad;
+    const int nLocal = (int)c->nIon, nPad = (int)c->nPad;
     const int tiles = nPad / TILE;
     if (withEnergy) CK(cudaMemsetAsync(c->acc, 0, ACC_N * sizeof(double), st));
     {
@@ -703,7 +925,8 @@ static int launchIntegrate(ddcb200_ctx *c, double halfDt2, double halfDt1, doubl
     ProfScope ps(c, PROF_INTEGRATE);
     const int cur = c->cur;
     const int tiles = (int)(c->nPad / TILE);
-    k_integrate<MODE><<<tiles, TILE, 0, c->stream>>>((int)c->nLocal, c->pos4[cur].p, c->vel[cur][0].p, c->vel[cur][1].p, c->vel[cur][2].p,
+    if (MODE & INT_KICK1_DRIFT) c->haloDirty = true;
+    k_integrate<MODE><<<tiles, TILE, 0, c->stream>>>((int)c->nIon, c->pos4[cur].p, c->vel[cur][0].p, c->vel[cur][1].p, c->vel[cur][2].p,
                                                      c->frc[0].p, c->frc[1].p, c->frc[2].p, c->massOfBead.p, halfDt2, halfDt1, dt, c->pc,
                                                      c->kinPartial.p, c->posBuild[0].p, c->posBuild[1].p, c->posBuild[2].p, c->dmax2);
     CKL("k_integrate");
@@ -777,7 +1000,17 @@ extern "C" int ddcb200_energyInfo(ddcb200_ctx *c, double kB, ddcb200_etype *out)
                                                                    c->acc + ACC_MVX);
         CKL("k_mol_virial");
     }
-    CK(cudaMemcpyAsync(c->accHost, c->acc, ACC_N * sizeof(double), cudaMemcpyDeviceToHost, st));
+    c->accHost[ACC_N] = (double)c->totalEntries;
+    CK(cudaMemcpyAsync(c->acc + ACC_NENTRIES, c->accHost + ACC_N, sizeof(double), cudaMemcpyHostToDevice, st));
+    const double *accSrc = c->acc;
+    if (c->nranks > 1)
+    {
+        // eval_energyInfo's MPI_Allreduce (src/energyInfo.c:9-63)
+        CK(c->accG.ensure(ACC_N));
+        CKN(ncclAllReduce(c->acc, c->accG.p, ACC_N, ncclDouble, ncclSum, (ncclComm_t)c->nccl, st));
+        accSrc = c->accG.p;
+    }
+    CK(cudaMemcpyAsync(c->accHost, accSrc, ACC_N * sizeof(double), cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
     const double *a = c->accHost;
     memset(out, 0, sizeof(*out));
@@ -792,7 +1025,7 @@ extern "C" int ddcb200_energyInfo(ddcb200_ctx *c, double kB, ddcb200_etype *out)
         out->tion[k] = a[ACC_TXX + k];
     }
     // eval_energyInfo, src/energyInfo.c:75-113
-    out->number = (double)c->nLocal;
+    out->number = (double)(c->nranks > 1 ? c->nGlobal : c->nLocal);
     out->volume = c->box.volume;
     for (int k = 0; k < 6; k++) out->sion[k] = -(out->virial[k] + out->tion[k]) / out->volume;
     out->pion = -(out->sion[0] + out->sion[1] + out->sion[2]) / 3.0;
@@ -807,7 +1040,7 @@ extern "C" int ddcb200_energyInfo(ddcb200_ctx *c, double kB, ddcb200_etype *out)
     out->loop = c->loop;
     out->time = c->time;
     out->nMolecules = c->nMolTotal;
-    out->nPairsListed = c->nPairsListed;
+    out->nPairsListed = (int64_t)(a[ACC_NENTRIES] / 2.0 + 0.25);
     return DDCB200_OK;
 }
 
@@ -817,6 +1050,8 @@ extern "C" int ddcb200_getCells(ddcb200_ctx *c, int *cellOfBead, int dims[3], do
     if (!c || !cellOfBead) return fail(DDCB200_ERR_ARG, "null argument");
     if (!c->listValid) return fail(DDCB200_ERR_STATE, "no list built");
     CK(cudaSetDevice(c->device));
+    int rcl = refreshLocals(c);
+    if (rcl) return rcl;
     const int n = (int)c->nIon;
     std::vector<int> cell(n), bead(n);
     CK(cudaStreamSynchronize(c->stream));
@@ -847,7 +1082,7 @@ extern "C" int64_t ddcb200_getPairs(ddcb200_ctx *c, int64_t capacity, int *beadI
     if (!c) return fail(DDCB200_ERR_ARG, "null ctx");
     if (!c->listValid) return fail(DDCB200_ERR_STATE, "no list built");
     if (cudaSetDevice(c->device) != cudaSuccess) return fail(DDCB200_ERR_CUDA, "cudaSetDevice");
-    const int n = (int)c->nLocal, nPad = (int)c->nPad;
+    const int n = (int)c->nIon, nPad = (int)c->nPad;   // ghost rows are empty
     std::vector<int> cnt(n), bead((size_t)c->nIon);
     cudaStreamSynchronize(c->stream);
     if (cudaMemcpy(cnt.data(), c->nbrCount.p, n * sizeof(int), cudaMemcpyDeviceToHost) != cudaSuccess ||
@@ -937,11 +1172,82 @@ extern "C" int ddcb200_profileRead(ddcb200_ctx *c, double ms[8], int64_t launche
 
 extern "C" int ddcb200_ncclUniqueId(unsigned char id[128])
 {
-    (void)id;
-    return fail(DDCB200_ERR_NCCL, "multi-GPU path not built yet");
+    if (!id) return fail(DDCB200_ERR_ARG, "null argument");
+    static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId is 128 bytes");
+    ncclUniqueId u;
+    CKN(ncclGetUniqueId(&u));
+    memcpy(id, &u, 128);
+    return DDCB200_OK;
 }
+
+// ddc_init (src/ddc.c:61-117: lattice lx ly lz of domain centres) + the communicator
 extern "C" int ddcb200_ddcInit(ddcb200_ctx *c, int rank, int nranks, int lx, int ly, int lz, const unsigned char id[128])
 {
-    (void)c; (void)rank; (void)nranks; (void)lx; (void)ly; (void)lz; (void)id;
-    return fail(DDCB200_ERR_NCCL, "multi-GPU path not built yet");
+    if (!c || !id || nranks < 1 || rank < 0 || rank >= nranks) return fail(DDCB200_ERR_ARG, "bad rank arguments");
+    if (nranks > DDC_MAXRANKS) return fail(DDCB200_ERR_ARG, "at most 16 ranks (one NVSwitch box)");
+    if (lx < 1 || ly < 1 || lz < 1 || lx * ly * lz != nranks) return fail(DDCB200_ERR_ARG, "DDC lx*ly*lz must equal the number of ranks");
+    if (c->nccl) return fail(DDCB200_ERR_STATE, "ddcInit called twice");
+    CK(cudaSetDevice(c->device));
+    c->rank = rank;
+    c->nranks = nranks;
+    c->lat[0] = lx; c->lat[1] = ly; c->lat[2] = lz;
+    if (nranks == 1) return DDCB200_OK;
+    ncclUniqueId u;
+    memcpy(&u, id, 128);
+    ncclComm_t comm;
+    CKN(ncclCommInitRank(&comm, nranks, u, rank));
+    c->nccl = (void *)comm;
+    CK(cudaMalloc((void **)&c->boxEnc, DDC_MAXRANKS * 6 * sizeof(unsigned long long)));
+    CK(cudaMalloc((void **)&c->boxes, sizeof(DdcBoxes)));
+    CK(cudaMallocHost((void **)&c->boxInitHost, DDC_MAXRANKS * 6 * sizeof(unsigned long long)));
+    for (int k = 0; k < DDC_MAXRANKS * 6; k++) c->boxInitHost[k] = ((k % 6) < 3) ? ~0ull : 0ull;
+    c->listValid = false;
+    return DDCB200_OK;
+}
+
+// CPU restatement of the domain classification, running the same __host__ __device__ predicates as the kernels
+// (k_ddc_owner, k_ddc_mask).  Used by the world_size-2 tests; not part of the step.
+extern "C" int ddcb200_ddcPlan(const double h[9], int lx, int ly, int lz, double rlist, int64_t nGlobal, const double *rx, const double *ry,
+                               const double *rz, const int *ownerBead, int rank, int *owner, uint32_t *mask)
+{
+    if (!h || !rx || !ry || !rz || !owner || !mask || nGlobal <= 0) return fail(DDCB200_ERR_ARG, "null argument");
+    DdcGeom g;
+    g.nranks = lx * ly * lz;
+    g.me = rank;
+    if (g.nranks < 1 || g.nranks > DDC_MAXRANKS || rank < 0 || rank >= g.nranks) return fail(DDCB200_ERR_ARG, "bad lattice or rank");
+    g.lat[0] = lx; g.lat[1] = ly; g.lat[2] = lz;
+    g.L[0] = h[0]; g.L[1] = h[4]; g.L[2] = h[8];
+    for (int a = 0; a < 3; a++) g.hL[a] = 0.5 * g.L[a];
+    g.rlist2 = rlist * rlist * (1.0 + 1e-9);
+    DdcBoxes bx;
+    for (int r = 0; r < DDC_MAXRANKS; r++)
+        for (int a = 0; a < 3; a++) { bx.lo[r][a] = 1e300; bx.hi[r][a] = -1e300; }
+    for (int64_t b = 0; b < nGlobal; b++)
+    {
+        const int ob = ownerBead ? ownerBead[b] : (int)b;
+        const int r = ddcBrickOf(rx[ob], ry[ob], rz[ob], g);
+        owner[b] = r;
+        double cc[3];
+        ddcBrickCentre(r, g, cc);
+        const double p[3] = {rx[b], ry[b], rz[b]};
+        for (int a = 0; a < 3; a++)
+        {
+            const double d = ddcMinImg(p[a] - cc[a], g.L[a], g.hL[a]);
+            if (d < bx.lo[r][a]) bx.lo[r][a] = d;
+            if (d > bx.hi[r][a]) bx.hi[r][a] = d;
+        }
+    }
+    for (int64_t b = 0; b < nGlobal; b++)
+    {
+        uint32_t m = 0u;
+        if (owner[b] == rank)
+        {
+            m = 0x80000000u;
+            for (int pp = 0; pp < g.nranks; pp++)
+                if (pp != rank && ddcNear(rx[b], ry[b], rz[b], pp, g, bx)) m |= 1u << pp;
+        }
+        else if (ddcNear(rx[b], ry[b], rz[b], rank, g, bx)) m = 1u << (16 + owner[b]);
+        mask[b] = m;
+    }
+    return DDCB200_OK;
 }

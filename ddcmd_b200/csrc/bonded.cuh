@@ -258,19 +258,32 @@ k_bonded(int64_t nTerms, const Term *__restrict__ terms, int64_t nRestr, const i
 }
 
 // refresh slot indices of the bonded terms and restraints after a re-sort
-__global__ void k_terms_remap(int64_t nTerms, const Term *__restrict__ in, Term *__restrict__ out, const int *__restrict__ slotOfBead)
+// A term is evaluated by the rank that owns its molecule (molecules are whole on their owner): terms whose
+// first bead is absent here, or present only as a ghost, are switched off (i = -1).
+__device__ __forceinline__ int ownedSlot(int bead, const int *__restrict__ slotOfBead, const double4 *__restrict__ pos)
+{
+    const int s = slotOfBead[bead];
+    if (s < 0) return -1;
+    return ((((unsigned long long)__double_as_longlong(pos[s].w)) >> 63) != 0ull) ? -1 : s;
+}
+__global__ void k_terms_remap(int64_t nTerms, const Term *__restrict__ in, Term *__restrict__ out, const int *__restrict__ slotOfBead,
+                              const double4 *__restrict__ pos)
 {
     const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= nTerms) return;
     Term tm = in[t];
-    tm.i = slotOfBead[tm.i];
-    tm.j = slotOfBead[tm.j];
-    if (tm.k >= 0) tm.k = slotOfBead[tm.k];
-    if (tm.l >= 0) tm.l = slotOfBead[tm.l];
+    tm.i = ownedSlot(tm.i, slotOfBead, pos);
+    if (tm.i >= 0)
+    {
+        tm.j = slotOfBead[tm.j];
+        if (tm.k >= 0) tm.k = slotOfBead[tm.k];
+        if (tm.l >= 0) tm.l = slotOfBead[tm.l];
+    }
     out[t] = tm;
 }
-__global__ void k_restr_remap(int64_t n, const int *__restrict__ bead, int *__restrict__ slot, const int *__restrict__ slotOfBead)
+__global__ void k_restr_remap(int64_t n, const int *__restrict__ bead, int *__restrict__ slot, const int *__restrict__ slotOfBead,
+                              const double4 *__restrict__ pos)
 {
     const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (t < n) slot[t] = slotOfBead[bead[t]];
+    if (t < n) slot[t] = ownedSlot(bead[t], slotOfBead, pos);
 }

@@ -234,7 +234,8 @@ __global__ void k_gather(int n, const int *__restrict__ perm, const int *__restr
     const int o = perm[s];
     const double4 p = posOld[o];
     posNew[s] = p;
-    pos32[s] = make_float4((float)p.x, (float)p.y, (float)p.z, 0.0f);   // candidate filter of the list build
+    // candidate filter of the list build; w = 1 marks a ghost slot (no row of its own)
+    pos32[s] = make_float4((float)p.x, (float)p.y, (float)p.z, (((unsigned long long)__double_as_longlong(p.w)) >> 63) ? 1.0f : 0.0f);
     bx[s] = p.x;                                                        // build-time positions: displacement bound
     by[s] = p.y;
     bz[s] = p.z;
@@ -255,13 +256,14 @@ __global__ void k_gather(int n, const int *__restrict__ perm, const int *__restr
 // rounding of the coordinates.  It only shrinks the work of the exact pass below; every list
 // decision is taken there in fp64 with the reference's own arithmetic.
 __global__ void __launch_bounds__(128)
-k_nbr_filter(int nLocal, int nPad, const float4 *__restrict__ pos32, const int *__restrict__ cellOf,
+k_nbr_filter(int nIon, int nPad, const float4 *__restrict__ pos32, const int *__restrict__ cellOf,
              const int *__restrict__ cellStart, BoxConst b, float rl2f, GridDev *gp, int cap, uint32_t *__restrict__ raw,
              int *__restrict__ rawCount)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     int cnt = 0;
-    if (i < nLocal)
+    const float4 pi = pos32[i < nIon ? i : 0];
+    if (i < nIon && pi.w == 0.0f)
     {
         const int nx = gp->n[0], ny = gp->n[1], nz = gp->n[2];
         const float Lx = (float)b.hxx, Ly = (float)b.hyy, Lz = (float)b.hzz;
@@ -269,7 +271,6 @@ k_nbr_filter(int nLocal, int nPad, const float4 *__restrict__ pos32, const int *
         // with >= 3 cells along an axis a wrapped stencil cell has ONE possible image: shift it;
         // with fewer the stencil is deduplicated and each pair takes its nearest image
         const bool px = nx < 3, py = ny < 3, pz = nz < 3;
-        const float4 pi = pos32[i];
         const int c = cellOf[i];
         const int cx = c % nx, cy = (c / nx) % ny, cz = c / (nx * ny);
         const int lx = nx >= 3 ? -1 : 0, hx = nx >= 2 ? 1 : 0;
@@ -315,8 +316,8 @@ k_nbr_filter(int nLocal, int nPad, const float4 *__restrict__ pos32, const int *
                 }
             }
         }
-        rawCount[i] = cnt;
     }
+    if (i < nIon) rawCount[i] = cnt;
     int m = cnt;
     for (int o = 16; o > 0; o >>= 1) m = max(m, __shfl_xor_sync(0xffffffffu, m, o));
     if ((threadIdx.x & 31) == 0 && m > 0)
@@ -363,15 +364,16 @@ __device__ __forceinline__ double4 ldPos256(const double4 *p)
 
 // Eight 16-bit per-bin counters in two 64-bit words: bins 0-3 in A, 4-7 in B.
 __global__ void __launch_bounds__(128)
-k_nbr_exact(int nLocal, int nPad, int cap, const double4 *__restrict__ pos, BoxConst b, GridDev *gp, uint32_t *__restrict__ raw,
+k_nbr_exact(int nIon, int nPad, int cap, const double4 *__restrict__ pos, BoxConst b, GridDev *gp, uint32_t *__restrict__ raw,
             const int *__restrict__ rawCount, uint32_t *__restrict__ out, int *__restrict__ count, uint16_t *__restrict__ cum,
             const uint64_t *__restrict__ gid, const int *__restrict__ molTypeOfBead, const int *__restrict__ molTypeSingle,
             const int *__restrict__ bpairOffset, const uint32_t *__restrict__ bpairKey, int haveExcl)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     int total = 0;
-    if (i < nLocal)
+    if (i < nIon)
     {
+        // ghost slots have no candidates (rawCount 0): their row stays empty
         const int n = min(rawCount[i], cap);
         const double4 pi = pos[i];
         const uint64_t wi = (uint64_t)__double_as_longlong(pi.w);
@@ -402,7 +404,7 @@ k_nbr_exact(int nLocal, int nPad, int cap, const double4 *__restrict__ pos, BoxC
                     // same molecule? bits 16..31 of w carry the low 16 bits of gid>>32: cheap reject before the gid gathers
                     const uint64_t wj = (uint64_t)__double_as_longlong(pj.w);
                     if (((wi ^ wj) & 0xffff0000ull) == 0ull &&
-                        isPruned((int)(wi >> 32), (int)(wj >> 32), gid, molTypeOfBead, molTypeSingle, bpairOffset, bpairKey))
+                        isPruned((int)((wi >> 32) & 0x7fffffffull), (int)((wj >> 32) & 0x7fffffffull), gid, molTypeOfBead, molTypeSingle, bpairOffset, bpairKey))
                         ent |= EXCL_BIT;
                 }
                 const uint64_t one = 1ull << (16 * (bin & 3));

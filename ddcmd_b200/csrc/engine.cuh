@@ -74,7 +74,7 @@ struct Term
 enum { PROF_INTEGRATE = 0, PROF_PAIR, PROF_BONDED, PROF_LIST, PROF_REDUCE, PROF_HALO, PROF_N = 8 };
 enum { ACC_ELJ = 0, ACC_EELE, ACC_VXX, ACC_VYY, ACC_VZZ, ACC_VXY, ACC_VXZ, ACC_VYZ,
        ACC_EBOND, ACC_EANGLE, ACC_ETORS, ACC_EIMPR, ACC_EREST, ACC_RK,
-       ACC_TXX, ACC_TYY, ACC_TZZ, ACC_TXY, ACC_TXZ, ACC_TYZ, ACC_MVX, ACC_MVY, ACC_MVZ, ACC_N = 24 };
+       ACC_TXX, ACC_TYY, ACC_TZZ, ACC_TXY, ACC_TXZ, ACC_TYZ, ACC_MVX, ACC_MVY, ACC_MVZ, ACC_NENTRIES, ACC_N = 24 };
 
 template <typename T>
 struct DevBuf
@@ -180,7 +180,7 @@ struct ddcb200_ctx
     double *acc = nullptr;        // device ACC_N
     double *accHost = nullptr;    // pinned
     bool energyValid = false, kineticValid = false;
-    int64_t nPairsListed = 0;
+    int64_t nPairsListed = 0, totalEntries = 0;
     DevBuf<double> stage;         // H2D / D2H staging in caller order
     DevBuf<int> stageI;
 
@@ -202,7 +202,26 @@ struct ddcb200_ctx
     cudaEvent_t timer[4] = {nullptr, nullptr, nullptr, nullptr};
     int64_t kernelLaunches = 0;
 
-    // multi-GPU
+    // multi-GPU (ddc.cuh)
     int rank = 0, nranks = 1;
-    void *nccl = nullptr;
+    int lat[3] = {1, 1, 1};
+    void *nccl = nullptr;             // ncclComm_t
+    std::vector<int64_t> hMolOffset;  // host copies of the molecule table (ownership beads)
+    std::vector<int> hMolBeads;
+    DevBuf<int> ownerBead;            // static: bead index of the ownership bead of each bead's molecule
+    bool ownerBeadValid = false;
+    DevBuf<double> gState;            // replicated x y z vx vy vz by bead index (re-domain steps only)
+    DevBuf<int> ownerOfBead;
+    DevBuf<uint32_t> ddcMask;
+    DevBuf<int> ddcCnt, ddcColTotal, ddcColStart, ddcList, sendSlot, recvSlot;
+    DevBuf<double> sendBuf, recvBuf;
+    unsigned long long *boxEnc = nullptr;   // device, DDC_MAXRANKS*6
+    void *boxes = nullptr;                  // device DdcBoxes
+    int *ddcCounters = nullptr;             // device, 8 ints
+    int *ddcHost = nullptr;                 // pinned, 64 ints
+    unsigned long long *boxInitHost = nullptr;   // pinned init pattern for boxEnc
+    std::vector<int> hSendCount, hRecvCount, hSendOff, hRecvOff;
+    int nSendTot = 0, nRecvTot = 0;
+    bool haloDirty = false, localsDirty = false;
+    DevBuf<double> accG;              // all-reduced accumulators
 };

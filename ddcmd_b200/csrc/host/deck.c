@@ -916,9 +916,14 @@ done:
     return 0;
 }
 
-int ddcb200_simulateBind(const ddcb200_deck *d, int device, ddcb200_ctx **out)
+/* One rank of nranks: push the parameters and static tables (every rank holds them), join the communicator,
+ * then hand this rank a contiguous slice of the file-order beads; the first list build re-domains them
+ * (ddcAssignment on the first call, src/ddcUpdateAll.c:81-119). */
+int ddcb200_simulateBindRank(const ddcb200_deck *d, int device, int rank, int nranks, int lx, int ly, int lz, const unsigned char *ncclId,
+                             ddcb200_ctx **out)
 {
     if (!d || !out) return herr("null argument");
+    if (nranks < 1 || rank < 0 || rank >= nranks) return herr("bad rank %d of %d", rank, nranks);
     ddcb200_params p = d->params;
     p.device = device;
     ddcb200_ctx *c = NULL;
@@ -933,10 +938,31 @@ int ddcb200_simulateBind(const ddcb200_deck *d, int device, ddcb200_ctx **out)
     TRY(ddcb200_martiniBondParms(c, d->nTerms, d->termKind, d->termIdx, d->termParm));
     TRY(ddcb200_setRestraints(c, d->nRestraints, d->restrBead, d->restrFrac0, d->restrKb, d->restrFc, d->restrOrigin));
     TRY(ddcb200_setMolecules(c, d->nMol, d->molOffset, d->molBeads, d->nMolTotal));
-    TRY(ddcb200_sendState(c, d->n, NULL, d->rx, d->ry, d->rz, d->vx, d->vy, d->vz, d->loop, d->time));
+    int64_t lo = 0, hi = d->n;
+    if (nranks > 1)
+    {
+        if (!ncclId) { herr("multi-rank bind needs the NCCL unique id"); ddcb200_destroy(c); return -1; }
+        TRY(ddcb200_ddcInit(c, rank, nranks, lx, ly, lz, ncclId));
+        lo = d->n * rank / nranks;
+        hi = d->n * (rank + 1) / nranks;
+    }
+    int *bead = NULL;
+    if (nranks > 1)
+    {
+        bead = (int *)malloc(sizeof(int) * (size_t)(hi - lo + 1));
+        for (int64_t i = lo; i < hi; i++) bead[i - lo] = (int)i;
+    }
+    rc = ddcb200_sendState(c, hi - lo, bead, d->rx + lo, d->ry + lo, d->rz + lo, d->vx + lo, d->vy + lo, d->vz + lo, d->loop, d->time);
+    free(bead);
+    if (rc) { herr("ddcb200_sendState: %s", ddcb200_lastError()); ddcb200_destroy(c); return rc; }
 #undef TRY
     *out = c;
     return 0;
+}
+
+int ddcb200_simulateBind(const ddcb200_deck *d, int device, ddcb200_ctx **out)
+{
+    return ddcb200_simulateBindRank(d, device, 0, 1, 1, 1, 1, NULL, out);
 }
 
 int ddcb200_printinfoLine(const ddcb200_deck *d, const ddcb200_etype *e, char *buf, size_t len)

@@ -16,7 +16,7 @@
 
 template <int MODE>
 __global__ void __launch_bounds__(TILE)
-k_integrate(int nLocal, double4 *__restrict__ pos, double *__restrict__ vx, double *__restrict__ vy, double *__restrict__ vz,
+k_integrate(int nIon, double4 *__restrict__ pos, double *__restrict__ vx, double *__restrict__ vy, double *__restrict__ vz,
             const double *__restrict__ fx, const double *__restrict__ fy, const double *__restrict__ fz,
             const double *__restrict__ massOfBead, double halfDt2, double halfDt1, double dt, PairConst pc, double *__restrict__ partial,
             const double *__restrict__ bx, const double *__restrict__ by, const double *__restrict__ bz, unsigned long long *__restrict__ dmax2)
@@ -24,10 +24,10 @@ k_integrate(int nLocal, double4 *__restrict__ pos, double *__restrict__ vx, doub
     const int i = blockIdx.x * TILE + threadIdx.x;
     double ke[7] = {0, 0, 0, 0, 0, 0, 0};
     double disp2 = 0.0;
-    if (i < nLocal)
+    double4 p = pos[i < nIon ? i : 0];
+    if (i < nIon && !((((uint64_t)__double_as_longlong(p.w)) >> 63)))   // ghosts are moved by their owner
     {
-        double4 p = pos[i];
-        const uint32_t bead = (uint32_t)(((uint64_t)__double_as_longlong(p.w)) >> 32);
+        const uint32_t bead = (uint32_t)((((uint64_t)__double_as_longlong(p.w)) >> 32) & 0x7fffffffull);
         const double mass = massOfBead[bead];
         double v0 = vx[i], v1 = vy[i], v2 = vz[i];
         const double f0 = fx[i], f1 = fy[i], f2 = fz[i];

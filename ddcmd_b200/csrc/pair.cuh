@@ -24,7 +24,7 @@ __device__ __forceinline__ double4 ldPos(const double4 *p)
 
 template <bool ENERGY>
 __global__ void __launch_bounds__(TILE)
-k_pair(int nLocal, int nPad, const double4 *__restrict__ pos, const uint32_t *__restrict__ nbr, const uint16_t *__restrict__ cum,
+k_pair(int nIon, int nPad, const double4 *__restrict__ pos, const uint32_t *__restrict__ nbr, const uint16_t *__restrict__ cum,
        const unsigned long long *__restrict__ dmax2,
        const double2 *__restrict__ ljTab, const double *__restrict__ shiftTab, const double *__restrict__ qTab, PairConst pc,
        double *__restrict__ fx, double *__restrict__ fy, double *__restrict__ fz, double *__restrict__ accPartial)
@@ -41,10 +41,10 @@ k_pair(int nLocal, int nPad, const double4 *__restrict__ pos, const uint32_t *__
     __syncthreads();
 
     const int i = blockIdx.x * TILE + threadIdx.x;
-    const bool live = i < nLocal;
-    const int ii = live ? i : 0;
+    const int ii = i < nIon ? i : 0;
     const double4 pi = ldPos(pos + ii);
     const uint64_t wi = (uint64_t)__double_as_longlong(pi.w);
+    const bool live = i < nIon && !(wi >> 63);   // ghost slots (bit 63 of w) own no row and receive no force here
     const int ti = (int)(wi & 0xff);
     const double qi = sQ[(wi >> 8) & 0xff];
     const double kqi = pc.keR * qi;

@@ -172,9 +172,23 @@ int ddcb200_timerRecord(ddcb200_ctx *ctx, int which);
 int ddcb200_timerElapsed(ddcb200_ctx *ctx, int from, int to, double *ms);
 int64_t ddcb200_kernelLaunches(ddcb200_ctx *ctx);
 
-/* ---- multi-GPU (ddc-style spatial decomposition, src/ddcUpdate.c, src/ddcAssignment.c) ---- */
+/* ---- multi-GPU: ddc-style spatial decomposition over the GPUs of one box, one process per GPU ----
+ * Replaces ddc_init + ddcAssignment + ddcSendRecvTables + ddcUpdate (src/ddc.c:61-117,
+ * src/ddcAssignment.c:64-107, src/ddcSendRecv.c:41-277, src/ddcUpdate.c:40-88) and the reduction of
+ * eval_energyInfo (src/energyInfo.c:9-63).  Domains are the bricks of the DDC lattice lx*ly*lz (Voronoi
+ * cells of a regular lattice of centres); a molecule follows its ownership bead (ddcRuleMolecule).
+ * Call order on every rank: create, [setters], ddcInit, sendState (any partition of the beads among the
+ * ranks), then ddcenergy / nglf / energyInfo collectively.  Rank 0 makes the id with ddcb200_ncclUniqueId
+ * and the caller distributes the 128 bytes (MPI_Bcast in ddcMD, torch.distributed in bench.py).
+ * After a re-domain step the local beads of a rank change: query numLocal / getLocalBeads / getState. */
 int ddcb200_ncclUniqueId(unsigned char id[128]);
 int ddcb200_ddcInit(ddcb200_ctx *ctx, int rank, int nranks, int lx, int ly, int lz, const unsigned char id[128]);
+
+/* Host restatement of the domain classification (same predicates as the kernels), for tests and tools:
+ * owner[b] = rank owning bead b; mask[b] for `rank`: bit 31 = mine, bit p = mine and a ghost on rank p,
+ * bit 16+p = owned by p and a ghost here.  ownerBead[b] = ownership bead of b's molecule (NULL = b). */
+int ddcb200_ddcPlan(const double h[9], int lx, int ly, int lz, double rlist, int64_t nGlobal, const double *rx, const double *ry,
+                    const double *rz, const int *ownerBead, int rank, int *owner, uint32_t *mask);
 
 #ifdef __cplusplus
 }

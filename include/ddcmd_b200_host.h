@@ -78,6 +78,11 @@ const char *ddcb200_lastHostError(void);
  * parameters, topology and state (src/simulate.c:104-297, src/masters.c:579-620). */
 int ddcb200_simulateBind(const ddcb200_deck *deck, int device, ddcb200_ctx **out);
 
+/* The same for rank `rank` of `nranks` processes (one per GPU): DDC lattice lx*ly*lz = nranks (the DDC
+ * object's lx ly lz, src/ddc.c:72-84), ncclId = the 128 bytes of ddcb200_ncclUniqueId made on rank 0. */
+int ddcb200_simulateBindRank(const ddcb200_deck *deck, int device, int rank, int nranks, int lx, int ly, int lz,
+                             const unsigned char *ncclId, ddcb200_ctx **out);
+
 /* One line of the reference's `data` file (printinfoA, src/printinfo.c:125-232): loop, time(ns),
  * Etotal, Ekin, Epot (kJ/mol per bead), T (K), P (bar; molecular if printMolecularPressure),
  * volume per bead (Ang^3), lx ly lz (Ang).  Returns the number of characters written. */

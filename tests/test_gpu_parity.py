@@ -132,3 +132,17 @@ def test_printinfo_line_matches_reference_data_file(golden_dir):
     assert abs(float(line[4]) - (-26.988954808928)) < 2e-12      # Epot
     assert abs(float(line[6]) - (-369.496497981831)) < 1e-8      # molecular pressure, bar
     assert abs(float(line[7]) - 133.942256177663) < 1e-9         # volume per bead
+
+
+@pytest.mark.parametrize("name", ["popc_small", "ras_small", "waterbox"])
+def test_two_gpus_match_reference(name):
+    """ddc decomposition over 2 GPUs (NCCL halo, re-domain every 20 steps) against the single-rank reference."""
+    import subprocess
+    import sys
+    if dd.lib().ddcb200_deviceCount() < 2:
+        pytest.skip("needs 2 GPUs")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
+           "--master-port", "29533", os.path.join(root, "tests", "mgpu_worker.py"), name]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and "MGPU_OK" in r.stdout, r.stdout[-3000:] + r.stderr[-6000:]
