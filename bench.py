@@ -95,6 +95,27 @@ def measured_peaks():
     return 6650.0, "fallback"
 
 
+def ncu_traffic(kernel):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of `kernel`, from the committed ncu --set full summary of
+    this round (profiles/*_ncu_full.txt, written by scripts/ncu_summary.py); None when no capture is committed."""
+    import glob
+    import re
+    best = None
+    for path in sorted(glob.glob(os.path.join(ROOT, "profiles", "*%s_ncu_full.txt" % kernel))):
+        rd = wr = None
+        for line in open(path):
+            m = re.match(r"\s*dram__bytes_(read|write)\.sum = ([0-9.,eE+-]+) (\w+)", line)
+            if m:
+                v = float(m.group(2).replace(",", "")) * {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}.get(m.group(3), 1.0)
+                if m.group(1) == "read" and rd is None:
+                    rd = v
+                if m.group(1) == "write" and wr is None:
+                    wr = v
+        if rd is not None and wr is not None:
+            best = {"bytes_per_launch": rd + wr, "source": os.path.relpath(path, ROOT)}
+    return best
+
+
 def run_reference(workload_n, steps, warmup):
     """Reference CPU path (oracle/_ref/ref_dump = the unmodified ddcMD objects) on the bounded sample."""
     ref = os.path.join(ROOT, "oracle", "_ref", "ref_dump")
@@ -127,6 +148,7 @@ def main():
     ap.add_argument("--impl", default="ours")
     ap.add_argument("--workload", default="membrane_1m")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--kernels-only", action="store_true", help="profiler runs: warm-up + timed steps, then exit (no e2e, no CPU baseline)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -155,33 +177,70 @@ def main():
         return
 
     import ddcmd_b200 as dd
+    dist = None
+    nccl_id = None
+    local = int(os.environ.get("LOCAL_RANK", rank))
     if world > 1:
-        raise SystemExit("bench.py: the multi-GPU (ddc halo over NCCL) path is not wired into bench yet")
+        # host-side plumbing only (barriers, the NCCL id, max over ranks): gloo.  The data path - ghost halo,
+        # re-domain, energyInfo all-reduce - is NCCL inside libddcmd_b200.so.
+        import torch
+        import torch.distributed as dist
+        dist.init_process_group("gloo")
+        ident = [dd.nccl_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(ident, src=0)
+        nccl_id = ident[0]
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+
+    def max_over_ranks(x):
+        if dist is None:
+            return x
+        t = torch.tensor([float(x)], dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t[0])
+
     K, W = args.steps, max(3, args.warmup)
+    if rank == 0:
+        deck_path = get_deck(args.workload)
+    barrier()
     deck_path = get_deck(args.workload)
     t = time.time()
     deck = dd.Deck(os.path.join(deck_path, "object.data"))
     n = deck.n
-    log("[bench] deck parsed: %d beads, %d bonded terms in %.1fs" % (n, deck.s.nTerms, time.time() - t))
-    sim = dd.Simulate(deck, device=0)
+    log("[bench] rank %d deck parsed: %d beads, %d bonded terms in %.1fs" % (rank, n, deck.s.nTerms, time.time() - t))
+    lattice = dd.default_lattice(world, [deck.s.params.h[0], deck.s.params.h[4], deck.s.params.h[8]]) if world > 1 else (1, 1, 1)
+    sim = dd.Simulate(deck, device=local, rank=rank, nranks=world, lattice=lattice, nccl_id=nccl_id)
+    config["parallelism"] = "ddc bricks %dx%dx%d, one process per GPU, ghost halo per step over NCCL" % lattice if world > 1 else "single GPU"
 
     # ---- device-resident throughput ------------------------------------------------------
     sim.nglf(W)
     sim.sync()
     l0 = sim.kernelLaunches()
-    clocks = ClockSampler(0)
+    clocks = ClockSampler(local)
     clocks.start()
     time.sleep(0.3)
+    barrier()
+    sim.sync()
     sim.timerRecord(0)
     sim.nglf(K)
     sim.timerRecord(1)
     sim.sync()
-    ms = sim.timerElapsed(0, 1)
+    barrier()
+    ms = max_over_ranks(sim.timerElapsed(0, 1))      # device time on the launching stream, max over ranks
     launches = sim.kernelLaunches() - l0
     clk = clocks.finish()
     e = sim.energyInfo()
     sps = K / (ms * 1e-3)
-    log("[bench] %d steps in %.2f ms -> %.1f steps/s; T=%.1f K" % (K, ms, sps, e.temperature / dd.units_convert(1.0, "K", None)))
+    if rank == 0:
+        log("[bench] %d steps in %.2f ms -> %.1f steps/s; T=%.1f K" % (K, ms, sps, e.temperature / dd.units_convert(1.0, "K", None)))
+
+    if args.kernels_only:
+        if rank == 0:
+            print(json.dumps({"steps_per_s": sps, "ms_per_step": ms / K, "gpu_launches": int(launches), "clocks": clk}))
+        sim.close()
+        return
 
     # ---- per-kernel device time (CUDA events around every launch) --------------------------
     sim.profile(True)
@@ -192,37 +251,49 @@ def main():
     sim.profile(False)
     pair_ms = prof["pair"][0] / max(1, prof["pair"][1])
     total_prof = sum(v[0] for v in prof.values())
-    p_full = 2 * int(e.nPairsListed)
-    alg_bytes = n * (32 + 24) + 4 * p_full       # pos4 read + force write + list entries
+    # ALGORITHMIC bytes of one k_pair launch on this rank (DESIGN.md "k_pair"): one 32-byte position record per resident
+    # bead + one 24-byte force per local bead + 4 bytes per stored list entry (full list = 2 x the half-list pairs;
+    # at N > 1 the entries are taken as evenly split over the ranks)
+    n_loc = int(sim.numLocal())
+    entries = 2 * int(e.nPairsListed) // world
+    alg_bytes = n_loc * (32 + 24) + 4 * entries
     peak, peak_kind = measured_peaks()
     achieved = alg_bytes / (pair_ms * 1e-3) / 1e9
     roofline = {"bound": "hbm", "kernel": "k_pair", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": None, "peak_kind": peak_kind, "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms": pair_ms,
+                "traffic": ncu_traffic("k_pair"), "peak_kind": peak_kind, "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms": pair_ms,
                 "kernel_share_of_step": prof["pair"][0] / total_prof,
                 "per_kernel_ms_per_step": {k: v[0] / KP for k, v in prof.items()}}
 
     # ---- end to end through the reference-facing calls with host buffers ---------------------
     import torch
     st = sim.getState()
-    pinned = torch.empty((6, n), dtype=torch.float64).pin_memory()
+    beads = sim.getLocalBeads()
+    nl = len(beads)
+    pinned = torch.empty((6, nl), dtype=torch.float64).pin_memory()
     host = pinned.numpy()
     for k, name in enumerate(("rx", "ry", "rz", "vx", "vy", "vz")):
         host[k] = st[name]
     KE = min(K, 100)
     sim.sync()
+    barrier()
     t0 = time.perf_counter()
-    sim.sendState(host[0], host[1], host[2], host[3], host[4], host[5], loop=int(e.loop), time=float(e.time))
+    sim.sendState(host[0], host[1], host[2], host[3], host[4], host[5], loop=int(e.loop), time=float(e.time),
+                  bead=beads if world > 1 else None)
     for _ in range(KE):
         sim.nglf(1)
         ee = sim.energyInfo()
     st2 = sim.getState()
+    barrier()
     t1 = time.perf_counter()
-    e2e_sps = KE / (t1 - t0)
-    e2e = {"value": e2e_sps, "unit": "steps/s", "h2d_bytes_per_step": 6 * 8 * n / KE, "d2h_bytes_per_step": 9 * 8 * n / KE + 24 * 8,
-           "steps": KE, "note": "sendState(H2D, pinned) + per step [nglf(1) + energyInfo D2H] (printrate=1) + getState(D2H)"}
+    e2e_sps = KE / max_over_ranks(t1 - t0)
+    e2e = {"value": e2e_sps, "unit": "steps/s", "h2d_bytes_per_step": 6 * 8 * n / KE, "d2h_bytes_per_step": 9 * 8 * n / KE + 24 * 8 * world,
+           "steps": KE, "note": "sendState(H2D, pinned) + per step [nglf(1) + energyInfo D2H] (printrate=1) + getState(D2H); bytes summed over ranks"}
+    sim.close()
+    if rank != 0:
+        return
 
     cpu = None
-    if not args.no_cpu_baseline:
+    if not args.no_cpu_baseline and world == 1:
         try:
             r = run_reference(n, 30, 5)
             cpu = {"value": r["value"], "unit": "steps/s", "cores": 1, "kind": "reference",
@@ -231,7 +302,7 @@ def main():
         except Exception as ex:  # the baseline is reported, never required for the GPU number
             cpu = {"value": None, "unit": "steps/s", "cores": 1, "kind": "reference", "sample": "failed: %s" % ex}
 
-    line = {"metric": "Martini MD steps/s (20 fs)", "value": sps, "unit": "steps/s", "n_gpus": 1, "steps": K, "warmup": W,
+    line = {"metric": "Martini MD steps/s (20 fs)", "value": sps, "unit": "steps/s", "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": ms / K, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
             "data": "synthetic", "config": dict(config, beads=n, bonded_terms=int(deck.s.nTerms), pairs_listed=int(e.nPairsListed)),
             "ns_per_day": sps * DT_FS * 86400 * 1e-6, "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e,

@@ -268,10 +268,16 @@ class Simulate:
         self._ck(lib().ddcb200_energyInfo(self.ctx, float(self.deck.s.kB), C.byref(e)))
         return e
 
-    def sendState(self, rx, ry, rz, vx, vy, vz, loop=0, time=0.0):
+    def sendState(self, rx, ry, rz, vx, vy, vz, loop=0, time=0.0, bead=None):
+        """bead = input-order index of each row (None: 0..n-1); on several ranks any partition of the beads works."""
         a = [np.ascontiguousarray(x, np.float64) for x in (rx, ry, rz, vx, vy, vz)]
         pd = _P(C.c_double)
-        self._ck(lib().ddcb200_sendState(self.ctx, a[0].size, None, *[x.ctypes.data_as(pd) for x in a], int(loop), float(time)))
+        b = np.ascontiguousarray(bead, np.int32) if bead is not None else None
+        self._ck(lib().ddcb200_sendState(self.ctx, a[0].size, b.ctypes.data_as(_P(C.c_int)) if b is not None else None,
+                                         *[x.ctypes.data_as(pd) for x in a], int(loop), float(time)))
+
+    def numLocal(self):
+        return int(lib().ddcb200_numLocal(self.ctx))
 
     def getLocalBeads(self):
         n = int(lib().ddcb200_numLocal(self.ctx))
