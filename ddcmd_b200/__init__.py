@@ -92,7 +92,12 @@ def lib():
             if not os.path.exists(path):
                 raise DdcError("libddcmd_b200.so is missing and could not be built: %s" % e)
     _preload_nccl()
-    L = C.CDLL(path)
+    _lib = _declare(C.CDLL(path))
+    return _lib
+
+
+def _declare(L):
+    """ctypes signatures of every entry point of include/ddcmd_b200.h and include/ddcmd_b200_host.h."""
     vp, i32, i64, dbl = C.c_void_p, C.c_int, C.c_int64, C.c_double
     pd, pi = _P(C.c_double), _P(C.c_int)
     sig = {
@@ -138,7 +143,6 @@ def lib():
         f = getattr(L, name)
         f.restype = res
         f.argtypes = args
-    _lib = L
     return L
 
 

@@ -519,7 +519,7 @@ extern "C" int ddcb200_sendState(ddcb200_ctx *c, int64_t nLocal, const int *bead
     const int cur = c->cur;
     const int blocks = (int)((nLocal + 255) / 256);
     const double *s = c->stage.p;
-    k_upload_state<<<blocks, 256, 0, c->stream>>>((int)nLocal, c->stageI.p, s, s + nLocal, s + 2 * nLocal, s + 3 * nLocal, s + 4 * nLocal,
+    LAUNCH(k_upload_state, blocks, 256, 0, c->stream)((int)nLocal, c->stageI.p, s, s + nLocal, s + 2 * nLocal, s + 3 * nLocal, s + 4 * nLocal,
                                                   s + 5 * nLocal, c->wOfBead.p, c->pos4[cur].p, c->vel[cur][0].p, c->vel[cur][1].p,
                                                   c->vel[cur][2].p, c->beadOfSlot[cur].p, c->slotOfBead.p);
     CKL("k_upload_state");
@@ -540,7 +540,7 @@ static int refreshLocals(ddcb200_ctx *c)
     cudaStream_t st = c->stream;
     CK(c->stageI.ensure((size_t)c->nIon));
     CK(cudaMemsetAsync(c->ddcCounters + 4, 0, sizeof(int), st));
-    k_ddc_list_locals<<<(int)((c->nIon + 255) / 256), 256, 0, st>>>((int)c->nIon, c->pos4[c->cur].p, c->ddcCounters + 4, c->stageI.p);
+    LAUNCH(k_ddc_list_locals, (int)((c->nIon + 255) / 256), 256, 0, st)((int)c->nIon, c->pos4[c->cur].p, c->ddcCounters + 4, c->stageI.p);
     CKL("k_ddc_list_locals");
     CK(cudaMemcpyAsync(c->ddcHost + 4, c->ddcCounters + 4, sizeof(int), cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
@@ -580,7 +580,7 @@ extern "C" int ddcb200_getState(ddcb200_ctx *c, double *rx, double *ry, double *
     const int cur = c->cur;
     CK(c->stage.ensure((size_t)n * 9));
     const int blocks = (int)((n + 255) / 256);
-    k_download_state<<<blocks, 256, 0, c->stream>>>((int)n, c->stageI.p, c->slotOfBead.p, c->pos4[cur].p, c->vel[cur][0].p,
+    LAUNCH(k_download_state, blocks, 256, 0, c->stream)((int)n, c->stageI.p, c->slotOfBead.p, c->pos4[cur].p, c->vel[cur][0].p,
                                                     c->vel[cur][1].p, c->vel[cur][2].p, c->frc[0].p, c->frc[1].p, c->frc[2].p, c->stage.p);
     CKL("k_download_state");
     double *dst[9] = {rx, ry, rz, vx, vy, vz, fx, fy, fz};
@@ -637,19 +637,19 @@ static int redomain(ddcb200_ctx *c)
     // 1. replicate the dynamic state: scatter my beads into zeros, sum over ranks (one contributor per element)
     const int cur = c->cur;
     CK(cudaMemsetAsync(c->gState.p, 0, (size_t)nG * 6 * sizeof(double), st));
-    k_ddc_scatter<<<(int)((c->nIon + 255) / 256), 256, 0, st>>>((int)c->nIon, nG, c->pos4[cur].p, c->vel[cur][0].p, c->vel[cur][1].p,
+    LAUNCH(k_ddc_scatter, (int)((c->nIon + 255) / 256), 256, 0, st)((int)c->nIon, nG, c->pos4[cur].p, c->vel[cur][0].p, c->vel[cur][1].p,
                                                                 c->vel[cur][2].p, c->gState.p);
     CKL("k_ddc_scatter");
     CKN(ncclAllReduce(c->gState.p, c->gState.p, (size_t)nG * 6, ncclDouble, ncclSum, comm, st));
     // 2. owners and bounding boxes, identically on every rank
     CK(cudaMemcpyAsync(c->boxEnc, c->boxInitHost, DDC_MAXRANKS * 6 * sizeof(unsigned long long), cudaMemcpyHostToDevice, st));
-    k_ddc_owner<<<nb, 256, 0, st>>>(nG, c->gState.p, c->ownerBead.p, g, c->ownerOfBead.p, c->boxEnc);
+    LAUNCH(k_ddc_owner, nb, 256, 0, st)(nG, c->gState.p, c->ownerBead.p, g, c->ownerOfBead.p, c->boxEnc);
     CKL("k_ddc_owner");
-    k_ddc_boxes<<<1, 128, 0, st>>>(c->nranks, c->boxEnc, (DdcBoxes *)c->boxes);
+    LAUNCH(k_ddc_boxes, 1, 128, 0, st)(c->nranks, c->boxEnc, (DdcBoxes *)c->boxes);
     CKL("k_ddc_boxes");
     // 3. classify
     CK(cudaMemsetAsync(c->ddcCounters, 0, 8 * sizeof(int), st));
-    k_ddc_mask<<<nb, 256, 0, st>>>(nG, c->gState.p, c->ownerOfBead.p, g, (const DdcBoxes *)c->boxes, c->ddcMask.p, c->ddcCounters);
+    LAUNCH(k_ddc_mask, nb, 256, 0, st)(nG, c->gState.p, c->ownerOfBead.p, g, (const DdcBoxes *)c->boxes, c->ddcMask.p, c->ddcCounters);
     CKL("k_ddc_mask");
     CK(cudaMemcpyAsync(c->ddcHost, c->ddcCounters, 2 * sizeof(int), cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
@@ -661,7 +661,7 @@ static int redomain(ddcb200_ctx *c)
     c->nIon = nLocal + nGhost;
     // 4. slot arrays from the replicated state
     CK(cudaMemsetAsync(c->slotOfBead.p, 0xff, nG * sizeof(int), st));
-    k_ddc_select<<<nb, 256, 0, st>>>(nG, c->gState.p, c->ddcMask.p, c->wOfBead.p, c->ddcCounters + 2, c->pos4[cur].p, c->vel[cur][0].p,
+    LAUNCH(k_ddc_select, nb, 256, 0, st)(nG, c->gState.p, c->ddcMask.p, c->wOfBead.p, c->ddcCounters + 2, c->pos4[cur].p, c->vel[cur][0].p,
                                      c->vel[cur][1].p, c->vel[cur][2].p, c->beadOfSlot[cur].p, c->slotOfBead.p);
     CKL("k_ddc_select");
     // 5. send / recv lists in ascending bead order: columns = [send to p (p != me)...] then [recv from p ...]
@@ -673,9 +673,9 @@ static int redomain(ddcb200_ctx *c)
     CK(c->ddcCnt.ensure((size_t)ncol * nUnits));
     CK(c->ddcColTotal.ensure(32));
     CK(c->ddcColStart.ensure(32));
-    k_ddc_colcount<<<nb, 256, 0, st>>>(nG, c->ddcMask.p, colBits, nUnits, c->ddcCnt.p);
+    LAUNCH(k_ddc_colcount, nb, 256, 0, st)(nG, c->ddcMask.p, colBits, nUnits, c->ddcCnt.p);
     CKL("k_ddc_colcount");
-    k_ddc_colscan<<<ncol, 1024, 0, st>>>(nUnits, c->ddcCnt.p, c->ddcColTotal.p);
+    LAUNCH(k_ddc_colscan, ncol, 1024, 0, st)(nUnits, c->ddcCnt.p, c->ddcColTotal.p);
     CKL("k_ddc_colscan");
     CK(cudaMemcpyAsync(c->ddcHost + 8, c->ddcColTotal.p, ncol * sizeof(int), cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
@@ -696,7 +696,7 @@ static int redomain(ddcb200_ctx *c)
     CK(c->recvSlot.ensure((size_t)c->nRecvTot + 1));
     CK(c->sendBuf.ensure((size_t)c->nSendTot * 3 + 1));
     CK(c->recvBuf.ensure((size_t)c->nRecvTot * 3 + 1));
-    k_ddc_colscatter<<<nb, 256, 0, st>>>(nG, c->ddcMask.p, colBits, nUnits, c->ddcCnt.p, c->ddcColStart.p, c->ddcList.p);
+    LAUNCH(k_ddc_colscatter, nb, 256, 0, st)(nG, c->ddcMask.p, colBits, nUnits, c->ddcCnt.p, c->ddcColStart.p, c->ddcList.p);
     CKL("k_ddc_colscatter");
     c->localsDirty = true;
     return DDCB200_OK;
@@ -711,7 +711,7 @@ static int haloExchange(ddcb200_ctx *c)
     const int cur = c->cur;
     if (c->nSendTot)
     {
-        k_halo_pack<<<(c->nSendTot + 255) / 256, 256, 0, st>>>(c->nSendTot, c->sendSlot.p, c->pos4[cur].p, c->sendBuf.p);
+        LAUNCH(k_halo_pack, (c->nSendTot + 255) / 256, 256, 0, st)(c->nSendTot, c->sendSlot.p, c->pos4[cur].p, c->sendBuf.p);
         CKL("k_halo_pack");
     }
     CKN(ncclGroupStart());
@@ -724,7 +724,7 @@ static int haloExchange(ddcb200_ctx *c)
     CKN(ncclGroupEnd());
     if (c->nRecvTot)
     {
-        k_halo_unpack<<<(c->nRecvTot + 255) / 256, 256, 0, st>>>(c->nRecvTot, c->recvSlot.p, c->recvBuf.p, c->pos4[cur].p, c->posBuild[0].p,
+        LAUNCH(k_halo_unpack, (c->nRecvTot + 255) / 256, 256, 0, st)(c->nRecvTot, c->recvSlot.p, c->recvBuf.p, c->pos4[cur].p, c->posBuild[0].p,
                                                                  c->posBuild[1].p, c->posBuild[2].p, c->pc, c->dmax2);
         CKL("k_halo_unpack");
     }
@@ -750,16 +750,16 @@ extern "C" int ddcb200_constructList(ddcb200_ctx *c)
     cudaStream_t st = c->stream;
     const int maxCells = nIon + 4;
     const int mmBlocks = std::min(1024, (nIon + 255) / 256);
-    k_minmax_partial<<<mmBlocks, 256, 0, st>>>(c->pos4[cur].p, nIon, c->box, c->mmPartial.p);
-    k_grid_setup<<<1, 32, 0, st>>>(c->mmPartial.p, mmBlocks, nIon, c->box, c->grid, maxCells);
+    LAUNCH(k_minmax_partial, mmBlocks, 256, 0, st)(c->pos4[cur].p, nIon, c->box, c->mmPartial.p);
+    LAUNCH(k_grid_setup, 1, 32, 0, st)(c->mmPartial.p, mmBlocks, nIon, c->box, c->grid, maxCells);
     CK(cudaMemsetAsync(c->cellCount.p, 0, (size_t)(nIon + 8) * sizeof(int), st));
     const int nb = (nIon + 255) / 256;
-    k_cell_count<<<nb, 256, 0, st>>>(c->pos4[cur].p, nIon, c->box, c->grid, c->cellOfSlot[cur].p, c->rank0.p, c->cellCount.p,
+    LAUNCH(k_cell_count, nb, 256, 0, st)(c->pos4[cur].p, nIon, c->box, c->grid, c->cellOfSlot[cur].p, c->rank0.p, c->cellCount.p,
                                      c->beadOfSlot[cur].p, c->orderKey.p);
-    k_cell_scan<<<1, 1024, 0, st>>>(c->cellCount.p, c->cellStart.p, c->grid);
-    k_cell_scatter<<<nb, 256, 0, st>>>(nIon, c->cellOfSlot[cur].p, c->rank0.p, c->cellStart.p, c->member.p);
-    k_cell_rank<<<nb, 256, 0, st>>>(nIon, c->cellOfSlot[cur].p, c->orderKey.p, c->cellStart.p, c->member.p, c->perm.p);
-    k_gather<<<nb, 256, 0, st>>>(nIon, c->perm.p, c->cellOfSlot[cur].p, c->cellOfSlot[nxt].p, c->pos4[cur].p, c->pos4[nxt].p,
+    LAUNCH(k_cell_scan, 1, 1024, 0, st)(c->cellCount.p, c->cellStart.p, c->grid);
+    LAUNCH(k_cell_scatter, nb, 256, 0, st)(nIon, c->cellOfSlot[cur].p, c->rank0.p, c->cellStart.p, c->member.p);
+    LAUNCH(k_cell_rank, nb, 256, 0, st)(nIon, c->cellOfSlot[cur].p, c->orderKey.p, c->cellStart.p, c->member.p, c->perm.p);
+    LAUNCH(k_gather, nb, 256, 0, st)(nIon, c->perm.p, c->cellOfSlot[cur].p, c->cellOfSlot[nxt].p, c->pos4[cur].p, c->pos4[nxt].p,
                                  c->vel[cur][0].p, c->vel[cur][1].p, c->vel[cur][2].p, c->vel[nxt][0].p, c->vel[nxt][1].p,
                                  c->vel[nxt][2].p, c->beadOfSlot[cur].p, c->beadOfSlot[nxt].p, c->slotOfBead.p, nLocal,
                                  c->pos32.p, c->posBuild[0].p, c->posBuild[1].p, c->posBuild[2].p);
@@ -777,10 +777,10 @@ extern "C" int ddcb200_constructList(ddcb200_ctx *c)
     {
         CK(c->nbrRaw.ensure((size_t)c->nbrCap * nPad));
         CK(c->nbr.ensure((size_t)c->nbrCap * nPad));
-        k_nbr_filter<<<nPad / 128, 128, 0, st>>>(nIon, nPad, c->pos32.p, c->cellOfSlot[nxt].p, c->cellStart.p, c->box, rl2f, c->grid,
+        LAUNCH(k_nbr_filter, nPad / 128, 128, 0, st)(nIon, nPad, c->pos32.p, c->cellOfSlot[nxt].p, c->cellStart.p, c->box, rl2f, c->grid,
                                                 c->nbrCap, c->nbrRaw.p, c->nbrRawCount.p);
         CKL("k_nbr_filter");
-        k_nbr_exact<<<nPad / 128, 128, 0, st>>>(nIon, nPad, c->nbrCap, c->pos4[nxt].p, c->box, c->grid, c->nbrRaw.p, c->nbrRawCount.p,
+        LAUNCH(k_nbr_exact, nPad / 128, 128, 0, st)(nIon, nPad, c->nbrCap, c->pos4[nxt].p, c->box, c->grid, c->nbrRaw.p, c->nbrRawCount.p,
                                                c->nbr.p, c->nbrCount.p, c->nbrCum.p, c->gidOfBead.p, c->molTypeOfBead.p,
                                                c->molTypeSingle.p, c->bpairOffset.p, c->bpairKey.p, c->haveExcl ? 1 : 0);
         CKL("k_nbr_exact");
@@ -798,13 +798,13 @@ extern "C" int ddcb200_constructList(ddcb200_ctx *c)
     }
     if (c->nTerms)
     {
-        k_terms_remap<<<(int)((c->nTerms + 255) / 256), 256, 0, st>>>(c->nTerms, c->termsBead.p, c->termsSlot.p, c->slotOfBead.p,
+        LAUNCH(k_terms_remap, (int)((c->nTerms + 255) / 256), 256, 0, st)(c->nTerms, c->termsBead.p, c->termsSlot.p, c->slotOfBead.p,
                                                                       c->pos4[nxt].p);
         CKL("k_terms_remap");
     }
     if (c->nRestr)
     {
-        k_restr_remap<<<(int)((c->nRestr + 255) / 256), 256, 0, st>>>(c->nRestr, c->restrBead.p, c->restrSlot.p, c->slotOfBead.p,
+        LAUNCH(k_restr_remap, (int)((c->nRestr + 255) / 256), 256, 0, st)(c->nRestr, c->restrBead.p, c->restrSlot.p, c->slotOfBead.p,
                                                                       c->pos4[nxt].p);
         CKL("k_restr_remap");
     }
@@ -812,12 +812,12 @@ extern "C" int ddcb200_constructList(ddcb200_ctx *c)
     {
         if (c->nSendTot)
         {
-            k_ddc_toslots<<<(c->nSendTot + 255) / 256, 256, 0, st>>>(c->nSendTot, c->ddcList.p, c->slotOfBead.p, c->sendSlot.p);
+            LAUNCH(k_ddc_toslots, (c->nSendTot + 255) / 256, 256, 0, st)(c->nSendTot, c->ddcList.p, c->slotOfBead.p, c->sendSlot.p);
             CKL("k_ddc_toslots");
         }
         if (c->nRecvTot)
         {
-            k_ddc_toslots<<<(c->nRecvTot + 255) / 256, 256, 0, st>>>(c->nRecvTot, c->ddcList.p + c->nSendTot, c->slotOfBead.p, c->recvSlot.p);
+            LAUNCH(k_ddc_toslots, (c->nRecvTot + 255) / 256, 256, 0, st)(c->nRecvTot, c->ddcList.p + c->nSendTot, c->slotOfBead.p, c->recvSlot.p);
             CKL("k_ddc_toslots");
         }
         c->haloDirty = false;   // the replicated state carried the current positions of every ghost
@@ -833,7 +833,7 @@ extern "C" int ddcb200_constructList(ddcb200_ctx *c)
 static int reduceCols(ddcb200_ctx *c, const double *partial, int nblocks, int ncol, const int *map)
 {
     // column map lives in a small device table: [0..7] pair, [8..18] bonded, [19..25] kinetic
-    k_reduce_cols<<<ncol, 256, 0, c->stream>>>(partial, nblocks, ncol, map, c->acc, 1);
+    LAUNCH(k_reduce_cols, ncol, 256, 0, c->stream)(partial, nblocks, ncol, map, c->acc, 1);
     CKL("k_reduce_cols");
     return DDCB200_OK;
 }
@@ -878,10 +878,10 @@ extern "C" int ddcb200_ddcenergy(ddcb200_ctx *c, int withEnergy)
         ProfScope ps(c, PROF_PAIR);
         const size_t smem = (size_t)c->ntypes * c->ntypes * (sizeof(double2) + sizeof(double)) + 256 * sizeof(double);
         if (withEnergy)
-            k_pair<true><<<tiles, TILE, smem, st>>>(nLocal, nPad, c->pos4[cur].p, c->nbr.p, c->nbrCum.p, c->dmax2, c->ljTab.p, c->shiftTab.p,
+            LAUNCH(k_pair<true>, tiles, TILE, smem, st)(nLocal, nPad, c->pos4[cur].p, c->nbr.p, c->nbrCum.p, c->dmax2, c->ljTab.p, c->shiftTab.p,
                                                     c->qTab.p, c->pc, c->frc[0].p, c->frc[1].p, c->frc[2].p, c->pairPartial.p);
         else
-            k_pair<false><<<tiles, TILE, smem, st>>>(nLocal, nPad, c->pos4[cur].p, c->nbr.p, c->nbrCum.p, c->dmax2, c->ljTab.p, c->shiftTab.p,
+            LAUNCH(k_pair<false>, tiles, TILE, smem, st)(nLocal, nPad, c->pos4[cur].p, c->nbr.p, c->nbrCum.p, c->dmax2, c->ljTab.p, c->shiftTab.p,
                                                      c->qTab.p, c->pc, c->frc[0].p, c->frc[1].p, c->frc[2].p, c->pairPartial.p);
         CKL("k_pair");
     }
@@ -893,11 +893,11 @@ extern "C" int ddcb200_ddcenergy(ddcb200_ctx *c, int withEnergy)
         bBlocks = (int)((nb + BONDED_THREADS - 1) / BONDED_THREADS);
         CK(c->bondPartial.ensure((size_t)bBlocks * BONDED_ACC + 8));
         if (withEnergy)
-            k_bonded<true><<<bBlocks, BONDED_THREADS, 0, st>>>(c->nTerms, c->termsSlot.p, c->nRestr, c->restrSlot.p, c->restrParm.p,
+            LAUNCH(k_bonded<true>, bBlocks, BONDED_THREADS, 0, st)(c->nTerms, c->termsSlot.p, c->nRestr, c->restrSlot.p, c->restrParm.p,
                                                                c->restrOrigin, c->pos4[cur].p, c->pc, c->frc[0].p, c->frc[1].p,
                                                                c->frc[2].p, c->bondPartial.p);
         else
-            k_bonded<false><<<bBlocks, BONDED_THREADS, 0, st>>>(c->nTerms, c->termsSlot.p, c->nRestr, c->restrSlot.p, c->restrParm.p,
+            LAUNCH(k_bonded<false>, bBlocks, BONDED_THREADS, 0, st)(c->nTerms, c->termsSlot.p, c->nRestr, c->restrSlot.p, c->restrParm.p,
                                                                 c->restrOrigin, c->pos4[cur].p, c->pc, c->frc[0].p, c->frc[1].p,
                                                                 c->frc[2].p, c->bondPartial.p);
         CKL("k_bonded");
@@ -926,7 +926,7 @@ static int launchIntegrate(ddcb200_ctx *c, double halfDt2, double halfDt1, doubl
     const int cur = c->cur;
     const int tiles = (int)(c->nPad / TILE);
     if (MODE & INT_KICK1_DRIFT) c->haloDirty = true;
-    k_integrate<MODE><<<tiles, TILE, 0, c->stream>>>((int)c->nIon, c->pos4[cur].p, c->vel[cur][0].p, c->vel[cur][1].p, c->vel[cur][2].p,
+    LAUNCH(k_integrate<MODE>, tiles, TILE, 0, c->stream)((int)c->nIon, c->pos4[cur].p, c->vel[cur][0].p, c->vel[cur][1].p, c->vel[cur][2].p,
                                                      c->frc[0].p, c->frc[1].p, c->frc[2].p, c->massOfBead.p, halfDt2, halfDt1, dt, c->pc,
                                                      c->kinPartial.p, c->posBuild[0].p, c->posBuild[1].p, c->posBuild[2].p, c->dmax2);
     CKL("k_integrate");
@@ -995,7 +995,7 @@ extern "C" int ddcb200_energyInfo(ddcb200_ctx *c, double kB, ddcb200_etype *out)
     if (c->nMol > 0)
     {
         const int cur = c->cur;
-        k_mol_virial<<<(int)((c->nMol + 255) / 256), 256, 0, st>>>(c->nMol, c->molOffset.p, c->molBeads.p, c->slotOfBead.p, c->pos4[cur].p,
+        LAUNCH(k_mol_virial, (int)((c->nMol + 255) / 256), 256, 0, st)(c->nMol, c->molOffset.p, c->molBeads.p, c->slotOfBead.p, c->pos4[cur].p,
                                                                    c->frc[0].p, c->frc[1].p, c->frc[2].p, c->massOfBead.p, c->pc,
                                                                    c->acc + ACC_MVX);
         CKL("k_mol_virial");

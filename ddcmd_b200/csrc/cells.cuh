@@ -355,9 +355,13 @@ __device__ __forceinline__ bool isPruned(int bi, int bj, const uint64_t *__restr
 
 __device__ __forceinline__ double4 ldPos256(const double4 *p)
 {
+#ifdef DDCB200_EMU
+    return *p;
+#else
     double4 r;
     asm volatile("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(r.x), "=d"(r.y), "=d"(r.z), "=d"(r.w) : "l"(p));
     return r;
+#endif
 }
 
 #define RAW_REJECT 0xffffffffu

@@ -99,7 +99,7 @@ HD bool ddcNear(double x, double y, double z, int r, const DdcGeom &g, const Ddc
     return e2 < g.rlist2;
 }
 
-#ifdef __CUDACC__
+#if defined(__CUDACC__) || defined(DDCB200_EMU)
 // monotone double <-> uint64 encoding for atomicMin/atomicMax
 __device__ __forceinline__ unsigned long long encOrd(double v)
 {

@@ -18,6 +18,13 @@
 #include <vector>
 #include "../../include/ddcmd_b200.h"
 
+// Kernel-launch and dynamic-shared-memory spellings.  The no-GPU test build (tests/cpu_emu, test infrastructure only)
+// compiles these sources with g++ against a shim that defines both macros itself; the product always takes this branch.
+#ifndef DDCB200_EMU
+#define LAUNCH(k, ...) k<<<__VA_ARGS__>>>
+#define EXTERN_SHARED(type, name) extern __shared__ type name[]
+#endif
+
 #define TILE 128           // beads per CTA in the per-step kernels
 #define NBINS 8            // build-time distance bins used to order each bead's list
 #define EXCL_BIT 0x80000000u

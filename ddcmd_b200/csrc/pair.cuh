@@ -15,9 +15,13 @@
 // L1/L2 sector and one LSU request (LDG.E.256, sm_100 only) instead of two 128-bit requests.
 __device__ __forceinline__ double4 ldPos(const double4 *p)
 {
+#ifdef DDCB200_EMU
+    return *p;
+#else
     double4 r;
     asm volatile("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(r.x), "=d"(r.y), "=d"(r.z), "=d"(r.w) : "l"(p));
     return r;
+#endif
 }
 
 #define PF 4   // gathers in flight per thread
@@ -29,7 +33,7 @@ k_pair(int nIon, int nPad, const double4 *__restrict__ pos, const uint32_t *__re
        const double2 *__restrict__ ljTab, const double *__restrict__ shiftTab, const double *__restrict__ qTab, PairConst pc,
        double *__restrict__ fx, double *__restrict__ fy, double *__restrict__ fz, double *__restrict__ accPartial)
 {
-    extern __shared__ double2 sLJ[];           // ntypes*ntypes {c6,c12}
+    EXTERN_SHARED(double2, sLJ);               // ntypes*ntypes {c6,c12}
     double *sQ = (double *)(sLJ + pc.ntypes * pc.ntypes);   // 256 charges
     double *sShift = sQ + 256;                              // ntypes*ntypes, ENERGY only
     for (int k = threadIdx.x; k < pc.ntypes * pc.ntypes; k += blockDim.x)

@@ -1,0 +1,70 @@
+"""Kernel-logic tests without a GPU: the product's CUDA sources compiled with g++ against tests/cpu_emu/shim (blocks
+run sequentially, threads are fibers, warp primitives and barriers are rendezvous) and run through the same C-ABI and
+the same parity assertions as tests/test_gpu_parity.py.
+
+This is TEST INFRASTRUCTURE: it checks indexing, list formats, reductions and the parity arithmetic of the kernels in
+the build container, where no GPU exists.  It says nothing about performance, and the emulated library is never
+loaded by the product (ddcmd_b200.lib() only ever opens libddcmd_b200.so, which needs a device).
+"""
+import ctypes
+import os
+import sys
+
+import numpy as np
+import pytest
+
+import ddcmd_b200 as dd
+import test_gpu_parity as tg
+
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "cpu_emu"))
+import build_emu  # noqa: E402
+
+
+@pytest.fixture(scope="module")
+def emu_handle():
+    return dd._declare(ctypes.CDLL(build_emu.build()))
+
+
+@pytest.fixture()
+def emu(emu_handle, monkeypatch):
+    dd.lib()                       # make sure the real library is what gets restored afterwards
+    monkeypatch.setattr(dd, "_lib", emu_handle)
+    return emu_handle
+
+
+SMALL = ["popc_small", "ras_small"]
+
+
+@pytest.mark.parametrize("name", tg.DECKS)
+def test_emu_cells_bit_exact(emu, golden_dir, name):
+    tg.test_cells_bit_exact(golden_dir, name)
+
+
+@pytest.mark.parametrize("name", tg.DECKS)
+def test_emu_pair_membership_bit_exact(emu, golden_dir, name):
+    tg.test_pair_membership_bit_exact(golden_dir, name)
+
+
+@pytest.mark.parametrize("name", tg.DECKS)
+def test_emu_step0_forces_energy_virial(emu, golden_dir, name):
+    tg.test_step0_forces_energy_virial(golden_dir, name)
+
+
+@pytest.mark.parametrize("name", SMALL)
+def test_emu_trajectory_40_steps(emu, golden_dir, name):
+    tg.test_trajectory_40_steps(golden_dir, name)
+
+
+def test_emu_printinfo_line(emu, golden_dir):
+    tg.test_printinfo_line_matches_reference_data_file(golden_dir)
+
+
+def test_emu_is_not_the_product():
+    """The product wrapper opens only libddcmd_b200.so; nothing under ddcmd_b200/ names the emulation."""
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    for dirpath, _, files in os.walk(os.path.join(root, "ddcmd_b200")):
+        for f in files:
+            if f.endswith((".py", ".c", ".h", ".cu", ".cuh")):
+                text = open(os.path.join(dirpath, f), errors="ignore").read()
+                assert "cpu_emu" not in text or f in ("engine.cuh",), f
+                assert "libddcmd_b200_emu" not in text, f
