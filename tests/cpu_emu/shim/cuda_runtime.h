@@ -80,7 +80,7 @@ inline double now()
 
 static inline const char *cudaGetErrorString(cudaError_t e) { return e == cudaSuccess ? "no error" : "emulated CUDA error"; }
 static inline cudaError_t cudaGetLastError() { cudaError_t e = emu::lastError(); emu::lastError() = cudaSuccess; return e; }
-static inline cudaError_t cudaGetDeviceCount(int *n) { *n = 1; return cudaSuccess; }
+static inline cudaError_t cudaGetDeviceCount(int *n) { *n = 16; return cudaSuccess; }   // every "device" is the host
 static inline cudaError_t cudaSetDevice(int) { return cudaSuccess; }
 static inline cudaError_t cudaGetDeviceProperties(cudaDeviceProp *p, int)
 {

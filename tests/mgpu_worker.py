@@ -13,6 +13,13 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 import ddcmd_b200 as dd  # noqa: E402
 
+if os.environ.get("DDCB200_TEST_EMU") == "1":
+    # no-GPU container: run the same worker on the CPU emulation of the CUDA sources (tests/cpu_emu, test infrastructure)
+    import ctypes
+    sys.path.insert(0, os.path.join(ROOT, "tests", "cpu_emu"))
+    import build_emu
+    dd._lib = dd._declare(ctypes.CDLL(build_emu.build()))
+
 
 def gather_by_bead(sim, n, keys):
     st = sim.getState()

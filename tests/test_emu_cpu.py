@@ -59,6 +59,39 @@ def test_emu_printinfo_line(emu, golden_dir):
     tg.test_printinfo_line_matches_reference_data_file(golden_dir)
 
 
+def _torchrun(nproc, port, script, *args, env=None):
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=%d" % nproc, "--master-addr", "127.0.0.1",
+           "--master-port", str(port), os.path.join(root, "tests", script)] + list(args)
+    e = dict(os.environ)
+    e.update(env or {})
+    return subprocess.run(cmd, capture_output=True, text=True, timeout=900, env=e)
+
+
+def test_emu_two_ranks_match_reference(emu_handle):
+    """The ddc decomposition (re-domain, halo lists, ghost halo per step, all-reduced energyInfo) on 2 emulated ranks,
+    NCCL replaced by a shared-memory stand-in, against the single-rank reference outputs."""
+    r = _torchrun(2, 29561, "mgpu_worker.py", "popc_small", env={"DDCB200_TEST_EMU": "1"})
+    assert r.returncode == 0 and "MGPU_OK" in r.stdout, r.stdout[-2000:] + r.stderr[-4000:]
+
+
+def test_emu_bench_contract_two_ranks(emu_handle):
+    """bench.py's multi-rank arm end to end (rank plumbing, max-over-ranks timing, one JSON line from rank 0)."""
+    import json
+    r = _torchrun(2, 29562, "emu_bench_check.py", "--gpus", "2", "--workload", "popc_small", "--steps", "3", "--warmup", "3")
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-4000:]
+    lines = [ln for ln in r.stdout.splitlines() if ln.startswith("{")]
+    assert len(lines) == 1
+    j = json.loads(lines[0])
+    for key in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "vs_baseline", "dtype",
+                "data", "config", "roofline", "cpu_baseline", "e2e", "gpu_launches", "clocks"):
+        assert key in j, key
+    assert j["n_gpus"] == 2 and j["steps"] == 3 and j["gpu_launches"] > 0
+    assert set(("bound", "achieved", "peak", "unit", "frac", "traffic")) <= set(j["roofline"])
+    assert set(("value", "unit", "h2d_bytes_per_step", "d2h_bytes_per_step")) <= set(j["e2e"])
+
+
 def test_emu_is_not_the_product():
     """The product wrapper opens only libddcmd_b200.so; nothing under ddcmd_b200/ names the emulation."""
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
