@@ -788,13 +788,13 @@ extern "C" int ddcb200_constructList(ddcb200_ctx *c)
     for (int attempt = 0; attempt < 4; attempt++)
     {
         CK(c->nbrRaw.ensure((size_t)c->nbrCap * nPad));
-        CK(c->nbr.ensure((size_t)c->nbrCap * nPad));
+        if (c->group == 1) CK(c->nbr.ensure((size_t)c->nbrCap * nPad));
         LAUNCH(k_nbr_filter, nPad / 128, 128, 0, st)(nIon, nPad, c->pos32.p, c->cellOfSlot[nxt].p, c->cellStart.p, c->box, rl2f, c->grid,
                                                 c->nbrCap, c->nbrRaw.p, c->nbrRawCount.p);
         CKL("k_nbr_filter");
         LAUNCH(k_nbr_exact, nPad / 128, 128, 0, st)(nIon, nPad, c->nbrCap, c->pos4[nxt].p, c->box, c->grid, c->nbrRaw.p, c->nbrRawCount.p,
                                                c->nbr.p, c->nbrCount.p, c->nbrCum.p, c->gidOfBead.p, c->molTypeOfBead.p,
-                                               c->molTypeSingle.p, c->bpairOffset.p, c->bpairKey.p, c->haveExcl ? 1 : 0);
+                                               c->molTypeSingle.p, c->bpairOffset.p, c->bpairKey.p, c->haveExcl ? 1 : 0, c->group == 1 ? 1 : 0);
         CKL("k_nbr_exact");
         if (c->group > 1)
         {

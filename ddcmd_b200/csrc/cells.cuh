@@ -314,6 +314,7 @@ k_nbr_filter(int nIon, int nPad, const float4 *__restrict__ pos32, const int *__
                     const float bx = px ? pi.x : pi.x - sxs[kx];
                     const int cc = ax + nx * (ay + ny * az);
                     const int lo = cellStart[cc], hi = cellStart[cc + 1];
+#pragma unroll 4
                     for (int j = lo; j < hi; j++)
                     {
                         const float4 pj = pos32[j];
@@ -380,60 +381,81 @@ __device__ __forceinline__ double4 ldPos256(const double4 *p)
 }
 
 #define RAW_REJECT 0xffffffffu
+#define EX_PF 4
 
 // Eight 16-bit per-bin counters in two 64-bit words: bins 0-3 in A, 4-7 in B.
 __global__ void __launch_bounds__(128)
 k_nbr_exact(int nIon, int nPad, int cap, const double4 *__restrict__ pos, BoxConst b, GridDev *gp, uint32_t *__restrict__ raw,
             const int *__restrict__ rawCount, uint32_t *__restrict__ out, int *__restrict__ count, uint16_t *__restrict__ cum,
             const uint64_t *__restrict__ gid, const int *__restrict__ molTypeOfBead, const int *__restrict__ molTypeSingle,
-            const int *__restrict__ bpairOffset, const uint32_t *__restrict__ bpairKey, int haveExcl)
+            const int *__restrict__ bpairOffset, const uint32_t *__restrict__ bpairKey, int haveExcl, int writeRows)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     int total = 0;
     if (i < nIon)
     {
+        bool n_done = false;
         // ghost slots have no candidates (rawCount 0): their row stays empty
         const int n = min(rawCount[i], cap);
         const double4 pi = pos[i];
         const uint64_t wi = (uint64_t)__double_as_longlong(pi.w);
         uint64_t A = 0ull, B = 0ull;
-        uint32_t jn = (0 < n) ? raw[i] : 0u;
-        for (int k = 0; k < n; k++)
+        // EX_PF candidates per trip: their entries and then their 32-byte position gathers are all issued before the
+        // first distance is computed (the walk is bound by gather latency, as in k_pair)
+        for (int k0 = 0; k0 < n; k0 += EX_PF)
         {
-            const uint32_t j = jn;
-            if (k + 1 < n) jn = raw[(size_t)(k + 1) * nPad + i];
-            const double4 pj = ldPos256(pos + j);
-            // pairlist1, src/pairlist.c:280-288
-            double x = __dadd_rn(pi.x, -pj.x), y = __dadd_rn(pi.y, -pj.y), z = __dadd_rn(pi.z, -pj.z);
-            double r2 = exactR2(x, y, z);
-            if (r2 > b.R2cut)
-            {
-                wrapOnce(x, y, z, b);
-                r2 = exactR2(x, y, z);
-            }
-            uint32_t ent = RAW_REJECT;
-            if (r2 < b.rlist2)
-            {
-                int bin = 0;
+            uint32_t jc[EX_PF];
+            double4 pc4[EX_PF];
 #pragma unroll
-                for (int e = 0; e < NBINS - 1; e++) bin += (r2 >= b.binEdge2[e]) ? 1 : 0;
-                ent = j | ((uint32_t)bin << 27);
-                if (haveExcl)
+            for (int u = 0; u < EX_PF; u++) jc[u] = (k0 + u < n) ? raw[(size_t)(k0 + u) * nPad + i] : (uint32_t)i;
+#pragma unroll
+            for (int u = 0; u < EX_PF; u++) pc4[u] = ldPos256(pos + jc[u]);
+#pragma unroll
+            for (int u = 0; u < EX_PF; u++)
+            {
+                if (k0 + u >= n) break;
+                const uint32_t j = jc[u];
+                const double4 pj = pc4[u];
+                // pairlist1, src/pairlist.c:280-288
+                double x = __dadd_rn(pi.x, -pj.x), y = __dadd_rn(pi.y, -pj.y), z = __dadd_rn(pi.z, -pj.z);
+                double r2 = exactR2(x, y, z);
+                if (r2 > b.R2cut)
                 {
-                    // same molecule? bits 16..31 of w carry the low 16 bits of gid>>32: cheap reject before the gid gathers
-                    const uint64_t wj = (uint64_t)__double_as_longlong(pj.w);
-                    if (((wi ^ wj) & 0xffff0000ull) == 0ull &&
-                        isPruned((int)((wi >> 32) & 0x7fffffffull), (int)((wj >> 32) & 0x7fffffffull), gid, molTypeOfBead, molTypeSingle, bpairOffset, bpairKey))
-                        ent |= EXCL_BIT;
+                    wrapOnce(x, y, z, b);
+                    r2 = exactR2(x, y, z);
                 }
-                const uint64_t one = 1ull << (16 * (bin & 3));
-                if (bin < 4) A += one;
-                else B += one;
-                total++;
+                uint32_t ent = RAW_REJECT;
+                if (r2 < b.rlist2)
+                {
+                    int bin = 0;
+#pragma unroll
+                    for (int e = 0; e < NBINS - 1; e++) bin += (r2 >= b.binEdge2[e]) ? 1 : 0;
+                    ent = j | ((uint32_t)bin << 27);
+                    if (haveExcl)
+                    {
+                        // same molecule? bits 16..31 of w carry the low 16 bits of gid>>32: cheap reject before the gid gathers
+                        const uint64_t wj = (uint64_t)__double_as_longlong(pj.w);
+                        if (((wi ^ wj) & 0xffff0000ull) == 0ull &&
+                            isPruned((int)((wi >> 32) & 0x7fffffffull), (int)((wj >> 32) & 0x7fffffffull), gid, molTypeOfBead, molTypeSingle, bpairOffset, bpairKey))
+                            ent |= EXCL_BIT;
+                    }
+                    const uint64_t one = 1ull << (16 * (bin & 3));
+                    if (bin < 4) A += one;
+                    else B += one;
+                    total++;
+                }
+                raw[(size_t)(k0 + u) * nPad + i] = ent;
             }
-            raw[(size_t)k * nPad + i] = ent;
+        }
+        if (!writeRows)
+        {
+            // merged group rows are built from `raw` (section 10); the per-slot rows are not needed
+            count[i] = total;
+            n_done = true;
         }
         // exclusive prefix over the eight counters
+        if (!n_done)
+        {
         const uint64_t totA = (A * 0x0001000100010001ull) >> 48;
         uint64_t offA = A * 0x0001000100010000ull;
         uint64_t offB = B * 0x0001000100010000ull + totA * 0x0001000100010001ull;
@@ -465,6 +487,7 @@ k_nbr_exact(int nIon, int nPad, int cap, const double4 *__restrict__ pos, BoxCon
             out[(size_t)dst * nPad + i] = (e & 0x07ffffffu) | (e & EXCL_BIT);
         }
         count[i] = total;
+        }
     }
     // statistics
     int m = total;
