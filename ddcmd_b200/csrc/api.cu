@@ -193,16 +193,6 @@ extern "C" int ddcb200_create(const ddcb200_params *p, ddcb200_ctx **out)
     c->prm = *p;
     c->device = p->device;
     c->numSM = prop.multiProcessorCount;
-    if (const char *g = getenv("DDCB200_GROUP"))
-    {
-        // slots per thread in the pair kernel: 1 = per-slot rows (k_pair), 2 or 4 = merged group rows (k_pair_group)
-        c->group = atoi(g);
-        if (c->group != 1 && c->group != 2 && c->group != 4)
-        {
-            delete c;
-            return fail(DDCB200_ERR_ARG, "DDCB200_GROUP must be 1, 2 or 4");
-        }
-    }
     int rc = setupBox(c);
     if (rc != DDCB200_OK)
     {
@@ -244,7 +234,6 @@ extern "C" void ddcb200_destroy(ddcb200_ctx *c)
     c->cellStart.release(); c->member.release(); c->perm.release(); c->mmPartial.release(); c->nbrRaw.release();
     c->nbr.release(); c->nbrCount.release(); c->pairPartial.release(); c->bondPartial.release(); c->kinPartial.release();
     c->colMap.release(); c->stage.release(); c->stageI.release();
-    c->nbrG.release(); c->cumG.release();
     c->orderKey.release(); c->pos32.release(); c->nbrRawCount.release(); c->nbrCum.release();
     for (int a = 0; a < 3; a++) c->posBuild[a].release();
     if (c->dmax2) cudaFree(c->dmax2);
@@ -788,32 +777,17 @@ extern "C" int ddcb200_constructList(ddcb200_ctx *c)
     for (int attempt = 0; attempt < 4; attempt++)
     {
         CK(c->nbrRaw.ensure((size_t)c->nbrCap * nPad));
-        if (c->group == 1) CK(c->nbr.ensure((size_t)c->nbrCap * nPad));
+        CK(c->nbr.ensure((size_t)c->nbrCap * nPad));
         LAUNCH(k_nbr_filter, nPad / 128, 128, 0, st)(nIon, nPad, c->pos32.p, c->cellOfSlot[nxt].p, c->cellStart.p, c->box, rl2f, c->grid,
                                                 c->nbrCap, c->nbrRaw.p, c->nbrRawCount.p);
         CKL("k_nbr_filter");
         LAUNCH(k_nbr_exact, nPad / 128, 128, 0, st)(nIon, nPad, c->nbrCap, c->pos4[nxt].p, c->box, c->grid, c->nbrRaw.p, c->nbrRawCount.p,
                                                c->nbr.p, c->nbrCount.p, c->nbrCum.p, c->gidOfBead.p, c->molTypeOfBead.p,
-                                               c->molTypeSingle.p, c->bpairOffset.p, c->bpairKey.p, c->haveExcl ? 1 : 0, c->group == 1 ? 1 : 0);
+                                               c->molTypeSingle.p, c->bpairOffset.p, c->bpairKey.p, c->haveExcl ? 1 : 0);
         CKL("k_nbr_exact");
-        if (c->group > 1)
-        {
-            // merged rows for k_pair_group, sweep 1: lengths and per-bin counts
-            const int G = c->group;
-            if ((int64_t)nPad > (1ll << (32 - 2 * G))) return fail(DDCB200_ERR_CAPACITY, "too many resident beads for this DDCB200_GROUP");
-            c->nGrp = (nIon + G - 1) / G;
-            c->nGrpPad = ((c->nGrp + TILE - 1) / TILE) * TILE;
-            CK(c->cumG.ensure((size_t)c->nGrpPad * NBINS));
-            if (G == 2)
-                LAUNCH(k_nbr_merge_count<2>, c->nGrpPad / 128, 128, 0, st)(nIon, nPad, c->nGrp, c->nGrpPad, c->nbrCap, c->nbrRaw.p, c->nbrRawCount.p, c->cumG.p, c->grid);
-            else
-                LAUNCH(k_nbr_merge_count<4>, c->nGrpPad / 128, 128, 0, st)(nIon, nPad, c->nGrp, c->nGrpPad, c->nbrCap, c->nbrRaw.p, c->nbrRawCount.p, c->cumG.p, c->grid);
-            CKL("k_nbr_merge_count");
-        }
         CK(cudaMemcpyAsync(c->gridHost, c->grid, sizeof(GridDev), cudaMemcpyDeviceToHost, st));
         CK(cudaStreamSynchronize(st));
         if (c->gridHost->error & 2) return fail(DDCB200_ERR_CAPACITY, "cell grid larger than the bead count bound");
-        if (c->gridHost->error & 4) return fail(DDCB200_ERR_CAPACITY, "merged neighbor row longer than 65535 entries");
         if (!(c->gridHost->error & 1)) break;
         // a candidate row overflowed: grow and redo both passes
         if (attempt == 3) return fail(DDCB200_ERR_CAPACITY, "neighbor list capacity could not be satisfied");
@@ -821,19 +795,7 @@ extern "C" int ddcb200_constructList(ddcb200_ctx *c)
         CK(cudaMemsetAsync(&c->grid->error, 0, sizeof(int), st));
         CK(cudaMemsetAsync(&c->grid->maxCount, 0, sizeof(int), st));
         CK(cudaMemsetAsync(&c->grid->maxRaw, 0, sizeof(int), st));
-        CK(cudaMemsetAsync(&c->grid->maxMerged, 0, sizeof(int), st));
         CK(cudaMemsetAsync(&c->grid->totalEntries, 0, sizeof(unsigned long long), st));
-    }
-    if (c->group > 1)
-    {
-        // sweep 2: place the merged entries
-        c->capG = std::max(c->gridHost->maxMerged, 1);
-        CK(c->nbrG.ensure((size_t)c->capG * c->nGrpPad));
-        if (c->group == 2)
-            LAUNCH(k_nbr_merge_place<2>, c->nGrpPad / 128, 128, 0, st)(nIon, nPad, c->nGrp, c->nGrpPad, c->nbrCap, c->capG, c->nbrRaw.p, c->nbrRawCount.p, c->cumG.p, c->nbrG.p);
-        else
-            LAUNCH(k_nbr_merge_place<4>, c->nGrpPad / 128, 128, 0, st)(nIon, nPad, c->nGrp, c->nGrpPad, c->nbrCap, c->capG, c->nbrRaw.p, c->nbrRawCount.p, c->cumG.p, c->nbrG.p);
-        CKL("k_nbr_merge_place");
     }
     if (c->nTerms)
     {
@@ -912,32 +874,16 @@ extern "C" int ddcb200_ddcenergy(ddcb200_ctx *c, int withEnergy)
     const int cur = c->cur;
     const int nLocal = (int)c->nIon, nPad = (int)c->nPad;
     const int tiles = nPad / TILE;
-    int pairTiles = tiles;
     if (withEnergy) CK(cudaMemsetAsync(c->acc, 0, ACC_N * sizeof(double), st));
     {
         ProfScope ps(c, PROF_PAIR);
         const size_t smem = (size_t)c->ntypes * c->ntypes * (sizeof(double2) + sizeof(double)) + 256 * sizeof(double);
-#define PAIR_ARGS_G nLocal, c->nGrpPad, c->pos4[cur].p, c->nbrG.p, c->cumG.p, c->dmax2, c->ljTab.p, c->shiftTab.p, c->qTab.p, c->pc, \
-                    c->frc[0].p, c->frc[1].p, c->frc[2].p, c->pairPartial.p
-        if (c->group == 2)
-        {
-            pairTiles = c->nGrpPad / TILE;
-            auto kg = withEnergy ? k_pair_group<2, true> : k_pair_group<2, false>;
-            LAUNCH(kg, pairTiles, TILE, smem, st)(PAIR_ARGS_G);
-        }
-        else if (c->group == 4)
-        {
-            pairTiles = c->nGrpPad / TILE;
-            auto kg = withEnergy ? k_pair_group<4, true> : k_pair_group<4, false>;
-            LAUNCH(kg, pairTiles, TILE, smem, st)(PAIR_ARGS_G);
-        }
-        else if (withEnergy)
+        if (withEnergy)
             LAUNCH(k_pair<true>, tiles, TILE, smem, st)(nLocal, nPad, c->pos4[cur].p, c->nbr.p, c->nbrCum.p, c->dmax2, c->ljTab.p, c->shiftTab.p,
                                                     c->qTab.p, c->pc, c->frc[0].p, c->frc[1].p, c->frc[2].p, c->pairPartial.p);
         else
             LAUNCH(k_pair<false>, tiles, TILE, smem, st)(nLocal, nPad, c->pos4[cur].p, c->nbr.p, c->nbrCum.p, c->dmax2, c->ljTab.p, c->shiftTab.p,
                                                      c->qTab.p, c->pc, c->frc[0].p, c->frc[1].p, c->frc[2].p, c->pairPartial.p);
-#undef PAIR_ARGS_G
         CKL("k_pair");
     }
     const int64_t nb = c->nTerms + c->nRestr;
@@ -960,7 +906,7 @@ extern "C" int ddcb200_ddcenergy(ddcb200_ctx *c, int withEnergy)
     if (withEnergy)
     {
         ProfScope ps(c, PROF_REDUCE);
-        rc = reduceCols(c, c->pairPartial.p, pairTiles, 8, c->colMap.p);
+        rc = reduceCols(c, c->pairPartial.p, tiles, 8, c->colMap.p);
         if (rc) return rc;
         if (bBlocks)
         {
@@ -1157,26 +1103,6 @@ extern "C" int64_t ddcb200_getPairs(ddcb200_ctx *c, int64_t capacity, int *beadI
             np++;
         }
     };
-    if (c->group > 1)
-    {
-        // the rows the force kernel actually walks: merged group rows (cells.cuh section 10)
-        const int G = c->group, JB = 32 - 2 * G, nGrp = c->nGrp, nGrpPad = c->nGrpPad;
-        std::vector<uint16_t> len((size_t)nGrpPad);
-        if (cudaMemcpy(len.data(), c->cumG.p + (size_t)(NBINS - 1) * nGrpPad, nGrpPad * sizeof(uint16_t), cudaMemcpyDeviceToHost) != cudaSuccess)
-            return fail(DDCB200_ERR_CUDA, "getPairs copy");
-        std::vector<uint32_t> rows((size_t)c->capG * nGrpPad);
-        if (cudaMemcpy(rows.data(), c->nbrG.p, rows.size() * sizeof(uint32_t), cudaMemcpyDeviceToHost) != cudaSuccess)
-            return fail(DDCB200_ERR_CUDA, "getPairs copy");
-        for (int t = 0; t < nGrp; t++)
-            for (int k = 0; k < (int)len[t]; k++)
-            {
-                const uint32_t e = rows[(size_t)k * nGrpPad + t];
-                const int j = (int)(e & ((1u << JB) - 1u));
-                for (int m = 0; m < G; m++)
-                    if ((e >> (JB + m)) & 1u) emit(G * t + m, j, ((e >> (JB + G + m)) & 1u) != 0u);
-            }
-        return np;
-    }
     int maxc = 0;
     for (int i = 0; i < n; i++) maxc = std::max(maxc, cnt[i]);
     std::vector<uint32_t> rows((size_t)maxc * nPad);

@@ -130,7 +130,6 @@ __global__ void k_grid_setup(const double *__restrict__ partial, int nblocks, in
     if (g->ncell > maxCells) g->error |= 2;
     g->maxCount = 0;
     g->maxRaw = 0;
-    g->maxMerged = 0;
     g->totalEntries = 0ull;
 }
 
@@ -251,25 +250,6 @@ __global__ void k_gather(int n, const int *__restrict__ perm, const int *__restr
     (void)nLocal;
 }
 
-// The <=3 periodic stencil coordinates of one axis (cell c of n): coordinate and the box shift that brings the
-// wrapped cell next to c, sorted by coordinate.  n >= 3: {c-1, c, c+1}; n == 2: {c, c+1}; n == 1: {c}.
-__device__ __forceinline__ void stencilAxis(int c, int n, float L, int a[3], float s[3], int &cnt)
-{
-    const int lo = n >= 3 ? -1 : 0, hi = n >= 2 ? 1 : 0;
-    cnt = 0;
-    for (int d = lo; d <= hi; d++)
-    {
-        int v = c + d;
-        float sh = 0.0f;
-        if (v < 0) { v += n; sh = -L; }
-        else if (v >= n) { v -= n; sh = L; }
-        int k = cnt++;
-        while (k > 0 && a[k - 1] > v) { a[k] = a[k - 1]; s[k] = s[k - 1]; k--; }
-        a[k] = v;
-        s[k] = sh;
-    }
-}
-
 // ---- 8. candidate pass (fp32, conservative) ----------------------------------------------
 // One thread per local slot walks the <=27 periodic neighbour cells and keeps every j whose
 // single-precision distance is below (rcut+skin)^2 times a safety margin covering the fp32
@@ -293,28 +273,32 @@ k_nbr_filter(int nIon, int nPad, const float4 *__restrict__ pos32, const int *__
         const bool px = nx < 3, py = ny < 3, pz = nz < 3;
         const int c = cellOf[i];
         const int cx = c % nx, cy = (c / nx) % ny, cz = c / (nx * ny);
-        // stencil coordinates per axis, sorted ascending, so cells are visited in ascending cell index and - slots being
-        // sorted by cell - candidates come out in ascending slot order (the group merge below relies on sorted rows)
-        int axs[3], ays[3], azs[3], nax = 0, nay = 0, naz = 0;
-        float sxs[3], sys[3], szs[3];
-        stencilAxis(cx, nx, Lx, axs, sxs, nax);
-        stencilAxis(cy, ny, Ly, ays, sys, nay);
-        stencilAxis(cz, nz, Lz, azs, szs, naz);
-        for (int kz = 0; kz < naz; kz++)
+        const int lx = nx >= 3 ? -1 : 0, hx = nx >= 2 ? 1 : 0;
+        const int ly = ny >= 3 ? -1 : 0, hy = ny >= 2 ? 1 : 0;
+        const int lz = nz >= 3 ? -1 : 0, hz = nz >= 2 ? 1 : 0;
+        for (int dz = lz; dz <= hz; dz++)
         {
-            const int az = azs[kz];
-            const float bz = pz ? pi.z : pi.z - szs[kz];
-            for (int ky = 0; ky < nay; ky++)
+            int az = cz + dz;
+            float sz = 0.0f;
+            if (az < 0) { az += nz; sz = -Lz; }
+            else if (az >= nz) { az -= nz; sz = Lz; }
+            const float bz = pz ? pi.z : pi.z - sz;
+            for (int dy = ly; dy <= hy; dy++)
             {
-                const int ay = ays[ky];
-                const float by = py ? pi.y : pi.y - sys[ky];
-                for (int kx = 0; kx < nax; kx++)
+                int ay = cy + dy;
+                float sy = 0.0f;
+                if (ay < 0) { ay += ny; sy = -Ly; }
+                else if (ay >= ny) { ay -= ny; sy = Ly; }
+                const float by = py ? pi.y : pi.y - sy;
+                for (int dx = lx; dx <= hx; dx++)
                 {
-                    const int ax = axs[kx];
-                    const float bx = px ? pi.x : pi.x - sxs[kx];
+                    int ax = cx + dx;
+                    float sx = 0.0f;
+                    if (ax < 0) { ax += nx; sx = -Lx; }
+                    else if (ax >= nx) { ax -= nx; sx = Lx; }
+                    const float bx = px ? pi.x : pi.x - sx;
                     const int cc = ax + nx * (ay + ny * az);
                     const int lo = cellStart[cc], hi = cellStart[cc + 1];
-#pragma unroll 4
                     for (int j = lo; j < hi; j++)
                     {
                         const float4 pj = pos32[j];
@@ -381,81 +365,60 @@ __device__ __forceinline__ double4 ldPos256(const double4 *p)
 }
 
 #define RAW_REJECT 0xffffffffu
-#define EX_PF 4
 
 // Eight 16-bit per-bin counters in two 64-bit words: bins 0-3 in A, 4-7 in B.
 __global__ void __launch_bounds__(128)
 k_nbr_exact(int nIon, int nPad, int cap, const double4 *__restrict__ pos, BoxConst b, GridDev *gp, uint32_t *__restrict__ raw,
             const int *__restrict__ rawCount, uint32_t *__restrict__ out, int *__restrict__ count, uint16_t *__restrict__ cum,
             const uint64_t *__restrict__ gid, const int *__restrict__ molTypeOfBead, const int *__restrict__ molTypeSingle,
-            const int *__restrict__ bpairOffset, const uint32_t *__restrict__ bpairKey, int haveExcl, int writeRows)
+            const int *__restrict__ bpairOffset, const uint32_t *__restrict__ bpairKey, int haveExcl)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     int total = 0;
     if (i < nIon)
     {
-        bool n_done = false;
         // ghost slots have no candidates (rawCount 0): their row stays empty
         const int n = min(rawCount[i], cap);
         const double4 pi = pos[i];
         const uint64_t wi = (uint64_t)__double_as_longlong(pi.w);
         uint64_t A = 0ull, B = 0ull;
-        // EX_PF candidates per trip: their entries and then their 32-byte position gathers are all issued before the
-        // first distance is computed (the walk is bound by gather latency, as in k_pair)
-        for (int k0 = 0; k0 < n; k0 += EX_PF)
+        uint32_t jn = (0 < n) ? raw[i] : 0u;
+        for (int k = 0; k < n; k++)
         {
-            uint32_t jc[EX_PF];
-            double4 pc4[EX_PF];
-#pragma unroll
-            for (int u = 0; u < EX_PF; u++) jc[u] = (k0 + u < n) ? raw[(size_t)(k0 + u) * nPad + i] : (uint32_t)i;
-#pragma unroll
-            for (int u = 0; u < EX_PF; u++) pc4[u] = ldPos256(pos + jc[u]);
-#pragma unroll
-            for (int u = 0; u < EX_PF; u++)
+            const uint32_t j = jn;
+            if (k + 1 < n) jn = raw[(size_t)(k + 1) * nPad + i];
+            const double4 pj = ldPos256(pos + j);
+            // pairlist1, src/pairlist.c:280-288
+            double x = __dadd_rn(pi.x, -pj.x), y = __dadd_rn(pi.y, -pj.y), z = __dadd_rn(pi.z, -pj.z);
+            double r2 = exactR2(x, y, z);
+            if (r2 > b.R2cut)
             {
-                if (k0 + u >= n) break;
-                const uint32_t j = jc[u];
-                const double4 pj = pc4[u];
-                // pairlist1, src/pairlist.c:280-288
-                double x = __dadd_rn(pi.x, -pj.x), y = __dadd_rn(pi.y, -pj.y), z = __dadd_rn(pi.z, -pj.z);
-                double r2 = exactR2(x, y, z);
-                if (r2 > b.R2cut)
-                {
-                    wrapOnce(x, y, z, b);
-                    r2 = exactR2(x, y, z);
-                }
-                uint32_t ent = RAW_REJECT;
-                if (r2 < b.rlist2)
-                {
-                    int bin = 0;
-#pragma unroll
-                    for (int e = 0; e < NBINS - 1; e++) bin += (r2 >= b.binEdge2[e]) ? 1 : 0;
-                    ent = j | ((uint32_t)bin << 27);
-                    if (haveExcl)
-                    {
-                        // same molecule? bits 16..31 of w carry the low 16 bits of gid>>32: cheap reject before the gid gathers
-                        const uint64_t wj = (uint64_t)__double_as_longlong(pj.w);
-                        if (((wi ^ wj) & 0xffff0000ull) == 0ull &&
-                            isPruned((int)((wi >> 32) & 0x7fffffffull), (int)((wj >> 32) & 0x7fffffffull), gid, molTypeOfBead, molTypeSingle, bpairOffset, bpairKey))
-                            ent |= EXCL_BIT;
-                    }
-                    const uint64_t one = 1ull << (16 * (bin & 3));
-                    if (bin < 4) A += one;
-                    else B += one;
-                    total++;
-                }
-                raw[(size_t)(k0 + u) * nPad + i] = ent;
+                wrapOnce(x, y, z, b);
+                r2 = exactR2(x, y, z);
             }
-        }
-        if (!writeRows)
-        {
-            // merged group rows are built from `raw` (section 10); the per-slot rows are not needed
-            count[i] = total;
-            n_done = true;
+            uint32_t ent = RAW_REJECT;
+            if (r2 < b.rlist2)
+            {
+                int bin = 0;
+#pragma unroll
+                for (int e = 0; e < NBINS - 1; e++) bin += (r2 >= b.binEdge2[e]) ? 1 : 0;
+                ent = j | ((uint32_t)bin << 27);
+                if (haveExcl)
+                {
+                    // same molecule? bits 16..31 of w carry the low 16 bits of gid>>32: cheap reject before the gid gathers
+                    const uint64_t wj = (uint64_t)__double_as_longlong(pj.w);
+                    if (((wi ^ wj) & 0xffff0000ull) == 0ull &&
+                        isPruned((int)((wi >> 32) & 0x7fffffffull), (int)((wj >> 32) & 0x7fffffffull), gid, molTypeOfBead, molTypeSingle, bpairOffset, bpairKey))
+                        ent |= EXCL_BIT;
+                }
+                const uint64_t one = 1ull << (16 * (bin & 3));
+                if (bin < 4) A += one;
+                else B += one;
+                total++;
+            }
+            raw[(size_t)k * nPad + i] = ent;
         }
         // exclusive prefix over the eight counters
-        if (!n_done)
-        {
         const uint64_t totA = (A * 0x0001000100010001ull) >> 48;
         uint64_t offA = A * 0x0001000100010000ull;
         uint64_t offB = B * 0x0001000100010000ull + totA * 0x0001000100010001ull;
@@ -487,7 +450,6 @@ k_nbr_exact(int nIon, int nPad, int cap, const double4 *__restrict__ pos, BoxCon
             out[(size_t)dst * nPad + i] = (e & 0x07ffffffu) | (e & EXCL_BIT);
         }
         count[i] = total;
-        }
     }
     // statistics
     int m = total;
@@ -499,126 +461,4 @@ k_nbr_exact(int nIon, int nPad, int cap, const double4 *__restrict__ pos, BoxCon
         atomicMax(&gp->maxCount, m);
         atomicAdd(&gp->totalEntries, t);
     }
-}
-
-// ---- 10. group rows: G consecutive slots share one merged row -------------------------------
-// k_pair_group (pair.cuh) gives every thread G consecutive slots - spatial neighbours after the cell / sub-cell sort,
-// whose lists overlap by ~75% - so one gathered j-bead serves up to G i-beads.  Its row is the sorted union of the G
-// per-slot rows with, per entry, a "listed" bit and an "excluded" bit for every member: the set of (i, j) pairs
-// evaluated is exactly the reference's list, only the storage is shared.  Entry layout (JBITS = 32 - 2G):
-//   [0, JBITS) j slot | [JBITS, JBITS+G) listed bits | [JBITS+G, 32) exclusion bits.
-// Rows are ordered by the smallest build-time distance bin over the members (same displacement-bounded walk).
-// The per-slot candidate rows left in `raw` by k_nbr_exact are in ascending slot order (k_nbr_filter visits cells in
-// ascending order), so the union is a G-way merge.
-template <int G>
-struct GroupBits
-{
-    static constexpr int JBITS = 32 - 2 * G;
-    static constexpr uint32_t JMASK = (1u << JBITS) - 1u;
-};
-
-template <int G, class F>
-__device__ __forceinline__ void mergeRows(int t, int nIon, int nPad, int cap, const uint32_t *__restrict__ raw,
-                                          const int *__restrict__ rawCount, F emit)
-{
-    int n[G], k[G];
-    uint32_t head[G];
-#pragma unroll
-    for (int m = 0; m < G; m++)
-    {
-        const int slot = G * t + m;
-        n[m] = slot < nIon ? min(rawCount[slot], cap) : 0;
-        k[m] = 0;
-        head[m] = RAW_REJECT;
-        while (k[m] < n[m] && (head[m] = raw[(size_t)k[m] * nPad + slot]) == RAW_REJECT) k[m]++;
-        if (k[m] >= n[m]) head[m] = RAW_REJECT;
-    }
-    for (;;)
-    {
-        uint32_t jmin = 0xffffffffu;
-#pragma unroll
-        for (int m = 0; m < G; m++)
-            if (head[m] != RAW_REJECT) jmin = min(jmin, head[m] & 0x07ffffffu);
-        if (jmin == 0xffffffffu) break;
-        uint32_t listed = 0u, excl = 0u;
-        int bin = NBINS;
-#pragma unroll
-        for (int m = 0; m < G; m++)
-            if (head[m] != RAW_REJECT && (head[m] & 0x07ffffffu) == jmin)
-            {
-                listed |= 1u << m;
-                if (head[m] & EXCL_BIT) excl |= 1u << m;
-                bin = min(bin, (int)((head[m] >> 27) & 7u));
-                const int slot = G * t + m;
-                k[m]++;
-                head[m] = RAW_REJECT;
-                while (k[m] < n[m] && (head[m] = raw[(size_t)k[m] * nPad + slot]) == RAW_REJECT) k[m]++;
-                if (k[m] >= n[m]) head[m] = RAW_REJECT;
-            }
-        emit(jmin, listed, excl, bin);
-    }
-}
-
-// sweep 1: entries per bin -> cumulative counts at every bin boundary, row length statistics
-template <int G>
-__global__ void __launch_bounds__(128)
-k_nbr_merge_count(int nIon, int nPad, int nGrp, int nGrpPad, int cap, const uint32_t *__restrict__ raw, const int *__restrict__ rawCount,
-                  uint16_t *__restrict__ cumG, GridDev *gp)
-{
-    const int t = blockIdx.x * blockDim.x + threadIdx.x;
-    int total = 0;
-    if (t < nGrp)
-    {
-        uint64_t A = 0ull, B = 0ull;
-        mergeRows<G>(t, nIon, nPad, cap, raw, rawCount, [&](uint32_t, uint32_t, uint32_t, int bin) {
-            const uint64_t one = 1ull << (16 * (bin & 3));
-            if (bin < 4) A += one;
-            else B += one;
-            total++;
-        });
-        const uint64_t totA = (A * 0x0001000100010001ull) >> 48;
-        const uint64_t offA = A * 0x0001000100010000ull;
-        const uint64_t offB = B * 0x0001000100010000ull + totA * 0x0001000100010001ull;
-#pragma unroll
-        for (int bnd = 0; bnd < NBINS; bnd++)
-        {
-            const uint64_t off = bnd < 4 ? offA : offB, cnt = bnd < 4 ? A : B;
-            const int sh = 16 * (bnd & 3);
-            cumG[(size_t)bnd * nGrpPad + t] = (uint16_t)(((off >> sh) & 0xffffull) + ((cnt >> sh) & 0xffffull));
-        }
-    }
-    else if (t < nGrpPad)
-    {
-#pragma unroll
-        for (int bnd = 0; bnd < NBINS; bnd++) cumG[(size_t)bnd * nGrpPad + t] = 0;
-    }
-    int m = total;
-    for (int o = 16; o > 0; o >>= 1) m = max(m, __shfl_xor_sync(0xffffffffu, m, o));
-    if ((threadIdx.x & 31) == 0 && m > 0)
-    {
-        atomicMax(&gp->maxMerged, m);
-        if (m > 65535) atomicOr(&gp->error, 4);
-    }
-}
-
-// sweep 2: place the merged entries in bin order
-template <int G>
-__global__ void __launch_bounds__(128)
-k_nbr_merge_place(int nIon, int nPad, int nGrp, int nGrpPad, int cap, int capG, const uint32_t *__restrict__ raw,
-                  const int *__restrict__ rawCount, const uint16_t *__restrict__ cumG, uint32_t *__restrict__ out)
-{
-    const int t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= nGrp) return;
-    int off[NBINS];
-    off[0] = 0;
-#pragma unroll
-    for (int bnd = 1; bnd < NBINS; bnd++) off[bnd] = cumG[(size_t)(bnd - 1) * nGrpPad + t];
-    mergeRows<G>(t, nIon, nPad, cap, raw, rawCount, [&](uint32_t j, uint32_t listed, uint32_t excl, int bin) {
-        int dst = 0;
-#pragma unroll
-        for (int bnd = 0; bnd < NBINS; bnd++)
-            if (bnd == bin) dst = off[bnd]++;
-        if (dst < capG)
-            out[(size_t)dst * nGrpPad + t] = j | (listed << GroupBits<G>::JBITS) | (excl << (GroupBits<G>::JBITS + G));
-    });
 }

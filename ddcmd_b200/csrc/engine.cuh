@@ -52,7 +52,6 @@ struct GridDev
     int error;       // sticky error flags (bit0: neighbor capacity overflow, bit1: cell overflow)
     int maxCount;    // max full-list length over beads
     int maxRaw;      // max candidate count over beads (fp32 filter pass)
-    int maxMerged;   // max merged (group) row length
     unsigned long long totalEntries;
 };
 
@@ -179,10 +178,6 @@ struct ddcb200_ctx
     DevBuf<int> nbrCount, nbrRawCount;
     DevBuf<uint16_t> nbrCum;      // [NBINS][nPad] cumulative entries at every distance-bin boundary
     int nbrCap = 0;               // entries per bead allocated
-    int group = 1;                // slots per thread in the pair kernel (1: per-slot rows; 2, 4: merged group rows)
-    DevBuf<uint32_t> nbrG;        // merged rows, transposed by group: entry k of group t at k*nGrpPad + t
-    DevBuf<uint16_t> cumG;        // [NBINS][nGrpPad]
-    int nGrp = 0, nGrpPad = 0, capG = 0;
     bool listValid = false;
     int64_t lastBuildLoop = -1;
 

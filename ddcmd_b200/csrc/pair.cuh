@@ -187,186 +187,3 @@ k_pair(int nIon, int nPad, const double4 *__restrict__ pos, const uint32_t *__re
         }
     }
 }
-
-// ---- group variant: G consecutive slots per thread, one merged row (cells.cuh section 10) ------------------
-// Same pairs, same formulas as k_pair.  Every gathered j-record serves up to G i-beads held in registers, which cuts
-// the L1 gather wavefronts - the pipe k_pair saturates (profiles/r01b_k_pair_ncu_full.txt) - by the overlap of the
-// members' lists, at the price of distance tests for (member, j) pairs only listed for another member.
-template <int G, bool ENERGY>
-__global__ void __launch_bounds__(TILE)
-k_pair_group(int nIon, int nGrpPad, const double4 *__restrict__ pos, const uint32_t *__restrict__ nbrG, const uint16_t *__restrict__ cumG,
-             const unsigned long long *__restrict__ dmax2,
-             const double2 *__restrict__ ljTab, const double *__restrict__ shiftTab, const double *__restrict__ qTab, PairConst pc,
-             double *__restrict__ fx, double *__restrict__ fy, double *__restrict__ fz, double *__restrict__ accPartial)
-{
-    constexpr int JBITS = 32 - 2 * G;
-    constexpr uint32_t JMASK = (1u << JBITS) - 1u;
-    EXTERN_SHARED(double2, sLJ);               // ntypes*ntypes {c6,c12}
-    double *sQ = (double *)(sLJ + pc.ntypes * pc.ntypes);   // 256 charges
-    double *sShift = sQ + 256;                              // ntypes*ntypes, ENERGY only
-    for (int k = threadIdx.x; k < pc.ntypes * pc.ntypes; k += blockDim.x)
-    {
-        sLJ[k] = ljTab[k];
-        if (ENERGY) sShift[k] = shiftTab[k];
-    }
-    for (int k = threadIdx.x; k < 256; k += blockDim.x) sQ[k] = qTab[k];
-    __syncthreads();
-
-    const int t = blockIdx.x * TILE + threadIdx.x;
-    double px[G], py[G], pz[G], kqi[G], qi[G];
-    int ti[G];
-    bool live[G];
-    bool anyLive = false;
-#pragma unroll
-    for (int m = 0; m < G; m++)
-    {
-        const int s = G * t + m;
-        const double4 p = ldPos(pos + (s < nIon ? s : 0));
-        const uint64_t w = (uint64_t)__double_as_longlong(p.w);
-        px[m] = p.x; py[m] = p.y; pz[m] = p.z;
-        live[m] = s < nIon && !(w >> 63);       // ghost slots own no row and receive no force here
-        anyLive = anyLive || live[m];
-        ti[m] = (int)(w & 0xff);
-        qi[m] = sQ[(w >> 8) & 0xff];
-        kqi[m] = pc.keR * qi[m];
-    }
-    int binLimit = 0;
-    {
-        const double lim = (pc.rmax + 2.0 * sqrt(__longlong_as_double((long long)*dmax2))) * (1.0 + 1e-12);
-#pragma unroll
-        for (int e = 0; e < NBINS - 1; e++) binLimit += (pc.binEdge[e] < lim) ? 1 : 0;
-    }
-    const int n = anyLive ? (int)cumG[(size_t)binLimit * nGrpPad + t] : 0;
-    int nmax = n;
-    for (int o = 16; o > 0; o >>= 1) nmax = max(nmax, __shfl_xor_sync(0xffffffffu, nmax, o));
-
-    double fxi[G], fyi[G], fzi[G];
-#pragma unroll
-    for (int m = 0; m < G; m++) fxi[m] = fyi[m] = fzi[m] = 0.0;
-    double eLJ = 0.0, eEle = 0.0, vxx = 0.0, vyy = 0.0, vzz = 0.0, vxy = 0.0, vxz = 0.0, vyz = 0.0;
-
-    // padding entry: no listed bits, a harmless in-range gather target
-    const uint32_t ePad = (uint32_t)min(G * t, nIon - 1);
-    const uint32_t *row = nbrG + t;
-    uint32_t eNext[PF];
-#pragma unroll
-    for (int u = 0; u < PF; u++) eNext[u] = (u < n) ? row[(size_t)u * nGrpPad] : ePad;
-    for (int k0 = 0; k0 < nmax; k0 += PF)
-    {
-        uint32_t eCur[PF];
-        double4 pCur[PF];
-#pragma unroll
-        for (int u = 0; u < PF; u++)
-        {
-            eCur[u] = eNext[u];
-            pCur[u] = ldPos(pos + (eCur[u] & JMASK));
-        }
-#pragma unroll
-        for (int u = 0; u < PF; u++) eNext[u] = (k0 + PF + u < n) ? row[(size_t)(k0 + PF + u) * nGrpPad] : ePad;
-#pragma unroll
-        for (int u = 0; u < PF; u++)
-        {
-            const uint32_t e = eCur[u];
-            const double4 pj = pCur[u];
-            const uint64_t wj = (uint64_t)__double_as_longlong(pj.w);
-            const int tj = (int)(wj & 0xff);
-            const double qj = sQ[(wj >> 8) & 0xff];
-#pragma unroll
-            for (int m = 0; m < G; m++)
-            {
-                const bool listed = ((e >> (JBITS + m)) & 1u) != 0u;
-                double x = px[m] - pj.x, y = py[m] - pj.y, z = pz[m] - pj.z;
-                double r2 = x * x + y * y + z * z;
-                if (r2 > pc.R2cut)
-                {
-                    // nearestImage_fast: one lattice reduction per component (src/preduce.c:147-160)
-                    if (x > pc.hhx) x -= pc.hxx;
-                    if (x < -pc.hhx) x += pc.hxx;
-                    if (y > pc.hhy) y -= pc.hyy;
-                    if (y < -pc.hhy) y += pc.hyy;
-                    if (z > pc.hhz) z -= pc.hzz;
-                    if (z < -pc.hhz) z += pc.hzz;
-                    r2 = x * x + y * y + z * z;
-                }
-                const bool in = listed && (r2 < pc.rc2);
-                if (__any_sync(0xffffffffu, in))
-                {
-                    const bool excl = ((e >> (JBITS + G + m)) & 1u) != 0u;
-                    const double kqij = kqi[m] * qj;
-                    const double r2s = in ? r2 : 1.0;
-                    double dvdr, vlj = 0.0, vele = 0.0;
-                    const double ir1 = rsqrt(r2s);
-                    const double ir2 = ir1 * ir1;
-                    {
-                        // Lennard-Jones (src/bioMartini.c:1073-1080)
-                        const double2 cc = sLJ[ti[m] * pc.ntypes + tj];
-                        const double ir6 = ir2 * ir2 * ir2;
-                        const double a6 = excl ? 0.0 : cc.x * ir6;
-                        const double a12 = excl ? 0.0 : cc.y * ir6 * ir6;
-                        dvdr = 6.0 * (a6 - 2.0 * a12) * ir2;
-                        if (ENERGY) vlj = excl ? 0.0 : (a12 - a6) + sShift[ti[m] * pc.ntypes + tj];
-                    }
-                    if (__any_sync(0xffffffffu, in && kqij != 0.0))
-                    {
-                        // reaction field (src/bioMartini.c:1082-1085); pruned pairs keep only krf r^2 - crf (:1172-1174)
-                        const double ir = excl ? 0.0 : ir1;
-                        dvdr += kqij * (2.0 * pc.krf - ir2 * ir);
-                        if (ENERGY) vele = kqij * (ir + pc.krf * r2s - pc.crf);
-                    }
-                    if (!in)
-                    {
-                        dvdr = 0.0;
-                        vlj = 0.0;
-                        vele = 0.0;
-                    }
-                    const double fxij = -dvdr * x, fyij = -dvdr * y, fzij = -dvdr * z;
-                    fxi[m] += fxij;
-                    fyi[m] += fyij;
-                    fzi[m] += fzij;
-                    if (ENERGY)
-                    {
-                        eLJ += vlj;
-                        eEle += vele;
-                        vxx += fxij * x;
-                        vyy += fyij * y;
-                        vzz += fzij * z;
-                        vxy += fxij * y;
-                        vxz += fxij * z;
-                        vyz += fyij * z;
-                    }
-                }
-            }
-        }
-    }
-#pragma unroll
-    for (int m = 0; m < G; m++)
-        if (live[m])
-        {
-            const int s = G * t + m;
-            fx[s] = fxi[m];
-            fy[s] = fyi[m];
-            fz[s] = fzi[m];
-        }
-    if (ENERGY)
-    {
-        double self = 0.0;
-#pragma unroll
-        for (int m = 0; m < G; m++) self += live[m] ? -0.5 * qi[m] * qi[m] * pc.keR * pc.crf : 0.0;
-        double v[8] = {0.5 * eLJ, 0.5 * eEle + self, 0.5 * vxx, 0.5 * vyy, 0.5 * vzz, 0.5 * vxy, 0.5 * vxz, 0.5 * vyz};
-        __shared__ double red[8][TILE / 32];
-#pragma unroll
-        for (int a = 0; a < 8; a++)
-        {
-            double r = v[a];
-            for (int o = 16; o > 0; o >>= 1) r += __shfl_xor_sync(0xffffffffu, r, o);
-            if ((threadIdx.x & 31) == 0) red[a][threadIdx.x >> 5] = r;
-        }
-        __syncthreads();
-        if (threadIdx.x < 8)
-        {
-            double r = 0.0;
-            for (int w = 0; w < TILE / 32; w++) r += red[threadIdx.x][w];
-            accPartial[(size_t)blockIdx.x * 8 + threadIdx.x] = r;
-        }
-    }
-}

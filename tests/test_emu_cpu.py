@@ -33,7 +33,6 @@ def emu(emu_handle, monkeypatch):
 
 
 SMALL = ["popc_small", "ras_small"]
-GROUPS = [2, 4]     # DDCB200_GROUP variants of the pair path (merged group rows); 1 is the default tested above
 
 
 @pytest.mark.parametrize("name", tg.DECKS)
@@ -58,28 +57,6 @@ def test_emu_trajectory_40_steps(emu, golden_dir, name):
 
 def test_emu_printinfo_line(emu, golden_dir):
     tg.test_printinfo_line_matches_reference_data_file(golden_dir)
-
-
-@pytest.mark.parametrize("group", GROUPS)
-@pytest.mark.parametrize("name", tg.DECKS)
-def test_emu_group_rows_membership_and_forces(emu, golden_dir, name, group, monkeypatch):
-    """Merged group rows (k_nbr_merge_*, k_pair_group): the pairs decoded from the rows the force kernel walks are
-    bit-exactly the reference's two lists, and forces / energies / virial meet the same bars."""
-    monkeypatch.setenv("DDCB200_GROUP", str(group))
-    tg.test_pair_membership_bit_exact(golden_dir, name)
-    tg.test_step0_forces_energy_virial(golden_dir, name)
-
-
-@pytest.mark.parametrize("group", GROUPS)
-def test_emu_group_rows_trajectory(emu, golden_dir, group, monkeypatch):
-    monkeypatch.setenv("DDCB200_GROUP", str(group))
-    tg.test_trajectory_40_steps(golden_dir, "ras_small")
-
-
-def test_emu_group_rows_two_ranks(emu_handle):
-    """Ghost slots inside groups: 2 emulated ranks with DDCB200_GROUP=4."""
-    r = _torchrun(2, 29563, "mgpu_worker.py", "ras_small", env={"DDCB200_TEST_EMU": "1", "DDCB200_GROUP": "4"})
-    assert r.returncode == 0 and "MGPU_OK" in r.stdout, r.stdout[-2000:] + r.stderr[-4000:]
 
 
 def _torchrun(nproc, port, script, *args, env=None):
