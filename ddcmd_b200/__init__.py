@@ -128,6 +128,7 @@ def _declare(L):
         "ddcb200_timerRecord": (i32, [vp, i32]),
         "ddcb200_timerElapsed": (i32, [vp, i32, i32, pd]),
         "ddcb200_kernelLaunches": (i64, [vp]),
+        "ddcb200_lastListBuild": (i64, [vp]),
         "ddcb200_ncclUniqueId": (i32, [C.c_char_p]),
         "ddcb200_ddcInit": (i32, [vp, i32, i32, i32, i32, i32, C.c_char_p]),
         "ddcb200_ddcPlan": (i32, [pd, i32, i32, i32, dbl, i64, pd, pd, pd, pi, i32, pi, _P(C.c_uint32)]),
@@ -151,7 +152,7 @@ EXPORTS = ["ddcb200_lastError", "ddcb200_deviceCount", "ddcb200_create", "ddcb20
            "ddcb200_martiniBondParms", "ddcb200_setRestraints", "ddcb200_setMolecules", "ddcb200_sendState",
            "ddcb200_numLocal", "ddcb200_getLocalBeads", "ddcb200_getState", "ddcb200_constructList", "ddcb200_ddcenergy",
            "ddcb200_nglf", "ddcb200_energyInfo", "ddcb200_getCells", "ddcb200_getPairs", "ddcb200_profile",
-           "ddcb200_profileRead", "ddcb200_timerRecord", "ddcb200_timerElapsed", "ddcb200_kernelLaunches", "ddcb200_ncclUniqueId", "ddcb200_ddcInit", "ddcb200_ddcPlan", "ddcb200_deckLoad", "ddcb200_deckFree",
+           "ddcb200_profileRead", "ddcb200_timerRecord", "ddcb200_timerElapsed", "ddcb200_kernelLaunches", "ddcb200_lastListBuild", "ddcb200_ncclUniqueId", "ddcb200_ddcInit", "ddcb200_ddcPlan", "ddcb200_deckLoad", "ddcb200_deckFree",
            "ddcb200_lastHostError", "ddcb200_simulateBind", "ddcb200_simulateBindRank", "ddcb200_printinfoLine", "ddcb200_unitsConvert"]
 
 
@@ -334,6 +335,10 @@ class Simulate:
 
     def kernelLaunches(self):
         return int(lib().ddcb200_kernelLaunches(self.ctx))
+
+    def lastListBuild(self):
+        """sys->neighbor->lastUpdate: loop of the last list build."""
+        return int(lib().ddcb200_lastListBuild(self.ctx))
 
     def printinfo(self, e=None):
         e = e or self.energyInfo()

@@ -6,6 +6,7 @@
 #include "pair.cuh"
 #include "bonded.cuh"
 #include "integrate.cuh"
+#include "nbrcheck.cuh"
 #include "ddc.cuh"
 #include <nccl.h>
 #include <math.h>
@@ -237,6 +238,8 @@ extern "C" void ddcb200_destroy(ddcb200_ctx *c)
     c->orderKey.release(); c->pos32.release(); c->nbrRawCount.release(); c->nbrCum.release();
     for (int a = 0; a < 3; a++) c->posBuild[a].release();
     if (c->dmax2) cudaFree(c->dmax2);
+    c->chk.release(); c->chkPartial.release();
+    if (c->chkHost) cudaFreeHost(c->chkHost);
     c->ownerBead.release(); c->gState.release(); c->ownerOfBead.release(); c->ddcMask.release(); c->ddcCnt.release();
     c->ddcColTotal.release(); c->ddcColStart.release(); c->ddcList.release(); c->sendSlot.release(); c->recvSlot.release();
     c->sendBuf.release(); c->recvBuf.release(); c->accG.release();
@@ -734,6 +737,7 @@ static int haloExchange(ddcb200_ctx *c)
 }
 
 // ---- list build -------------------------------------------------------------------------
+static int localSums(ddcb200_ctx *c, int atBuild);
 extern "C" int ddcb200_constructList(ddcb200_ctx *c)
 {
     if (!c) return fail(DDCB200_ERR_ARG, "null ctx");
@@ -823,6 +827,11 @@ extern "C" int ddcb200_constructList(ddcb200_ctx *c)
         }
         c->haloDirty = false;   // the replicated state carried the current positions of every ghost
     }
+    if (c->prm.updateRate == 0)
+    {
+        int rcs = localSums(c, 1);   // neighborRef: rbar at the build
+        if (rcs) return rcs;
+    }
     c->listValid = true;
     c->lastBuildLoop = c->loop;
     c->totalEntries = (int64_t)c->gridHost->totalEntries;
@@ -842,11 +851,72 @@ static int reduceCols(ddcb200_ctx *c, const double *partial, int nblocks, int nc
 static int ensureColMap(ddcb200_ctx *c)
 {
     if (c->colMap.p) return DDCB200_OK;
-    const int m[26] = {ACC_ELJ, ACC_EELE, ACC_VXX, ACC_VYY, ACC_VZZ, ACC_VXY, ACC_VXZ, ACC_VYZ,
+    const int m[32] = {ACC_ELJ, ACC_EELE, ACC_VXX, ACC_VYY, ACC_VZZ, ACC_VXY, ACC_VXZ, ACC_VYZ,
                        ACC_VXX, ACC_VYY, ACC_VZZ, ACC_VXY, ACC_VXZ, ACC_VYZ, ACC_EBOND, ACC_EANGLE, ACC_ETORS, ACC_EIMPR, ACC_EREST,
-                       ACC_RK, ACC_TXX, ACC_TYY, ACC_TZZ, ACC_TXY, ACC_TXZ, ACC_TYZ};
+                       ACC_RK, ACC_TXX, ACC_TYY, ACC_TZZ, ACC_TXY, ACC_TXZ, ACC_TYZ,
+                       0, 1, 2, 3, 4, 5};   // [26..31]: columns of the neighbor-check sums (chk, nbrcheck.cuh)
     CK(c->colMap.ensure(32));
     CK(cudaMemcpy(c->colMap.p, m, sizeof(m), cudaMemcpyHostToDevice));
+    return DDCB200_OK;
+}
+
+
+// ---- displacement-triggered rebuild (updateRate == 0): neighborRef / neighborCheck ------------
+static BoxConst checkBox(const ddcb200_ctx *c)
+{
+    // positions are taken at the image nearest to the domain centre (src/neighbor.c:220-230): the brick centre on
+    // several ranks, the GeomBox centre otherwise
+    BoxConst b = c->box;
+    if (c->nranks > 1)
+    {
+        double cc[3];
+        ddcBrickCentre(c->rank, ddcGeomOf(c), cc);
+        b.cx = cc[0]; b.cy = cc[1]; b.cz = cc[2];
+    }
+    return b;
+}
+
+static int localSums(ddcb200_ctx *c, int atBuild)
+{
+    const int tiles = (int)(c->nPad / TILE);
+    CK(c->chk.ensure(8));
+    CK(c->chkPartial.ensure((size_t)tiles * 3 + 8));
+    if (!c->chkHost) CK(cudaMallocHost((void **)&c->chkHost, 8 * sizeof(double)));
+    int rc = ensureColMap(c);
+    if (rc) return rc;
+    LAUNCH(k_nbr_rbar_partial, tiles, TILE, 0, c->stream)((int)c->nIon, c->pos4[c->cur].p, checkBox(c), c->chkPartial.p);
+    CKL("k_nbr_rbar_partial");
+    LAUNCH(k_reduce_cols, 3, 256, 0, c->stream)(c->chkPartial.p, tiles, 3, c->colMap.p + (atBuild ? 29 : 26), c->chk.p, 0);
+    CKL("k_reduce_cols");
+    return DDCB200_OK;
+}
+
+// neighborCheck (src/neighbor.c:117-208): 1 = rebuild now
+static int neighborCheck(ddcb200_ctx *c, bool *update)
+{
+    ProfScope ps(c, PROF_LIST);
+    cudaStream_t st = c->stream;
+    int rc = localSums(c, 0);
+    if (rc) return rc;
+    CK(cudaMemsetAsync(c->chk.p + 6, 0, sizeof(double), st));
+    LAUNCH(k_nbr_check, (int)(c->nPad / TILE), TILE, 0, st)((int)c->nIon, (int)c->nLocal, c->pos4[c->cur].p, c->posBuild[0].p,
+                                                             c->posBuild[1].p, c->posBuild[2].p, c->pc, c->chk.p);
+    CKL("k_nbr_check");
+    if (c->nranks > 1)   // check4updateNeighbor's MPI_Allreduce of the flags (src/ddcUpdateAll.c:48-62) = max of d^2
+        CKN(ncclAllReduce(c->chk.p + 6, c->chk.p + 6, 1, ncclDouble, ncclMax, (ncclComm_t)c->nccl, st));
+    CK(cudaMemcpyAsync(c->chkHost, c->chk.p + 6, sizeof(double), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    // box-strain term |1 - h0 hinv u| (rcut + deltaR): h0 is the box at the build; the box is constant on this path
+    const double *hi = c->box.hinv, *h = c->prm.h;
+    const double ux = hi[0] + hi[1] + hi[2], uy = hi[3] + hi[4] + hi[5], uz = hi[6] + hi[7] + hi[8];
+    const double sx = fabs(1.0 - (h[0] * ux + h[1] * uy + h[2] * uz)), sy = fabs(1.0 - (h[3] * ux + h[4] * uy + h[5] * uz)),
+                 sz = fabs(1.0 - (h[6] * ux + h[7] * uy + h[8] * uz));
+    double dmax = sx;
+    if (dmax < sy) dmax = sy;
+    if (dmax < sz) dmax = sz;
+    dmax *= c->prm.rmax + c->prm.deltaR;   // nbr->rcut[0].value + nbr->deltaR
+    dmax += 2.0 * sqrt(c->chkHost[0]);
+    *update = !(dmax < c->prm.deltaR);
     return DDCB200_OK;
 }
 
@@ -859,15 +929,20 @@ extern "C" int ddcb200_ddcenergy(ddcb200_ctx *c, int withEnergy)
     int rc = ensureColMap(c);
     if (rc) return rc;
     // evalUpdateFlag, src/ddcUpdateAll.c:64-71
-    const bool due = c->prm.updateRate > 0 && (c->loop % c->prm.updateRate) == 0 && c->lastBuildLoop != c->loop;
+    bool due = c->prm.updateRate > 0 && (c->loop % c->prm.updateRate) == 0 && c->lastBuildLoop != c->loop;
+    if (c->listValid && !due && c->nranks > 1 && c->haloDirty)
+    {
+        rc = haloExchange(c);
+        if (rc) return rc;
+    }
+    if (c->listValid && c->prm.updateRate == 0 && c->lastBuildLoop != c->loop)
+    {
+        rc = neighborCheck(c, &due);
+        if (rc) return rc;
+    }
     if (!c->listValid || due)
     {
         rc = ddcb200_constructList(c);
-        if (rc) return rc;
-    }
-    else if (c->nranks > 1 && c->haloDirty)
-    {
-        rc = haloExchange(c);
         if (rc) return rc;
     }
     cudaStream_t st = c->stream;
@@ -1138,6 +1213,8 @@ extern "C" int ddcb200_timerElapsed(ddcb200_ctx *c, int from, int to, double *ms
 }
 
 extern "C" int64_t ddcb200_kernelLaunches(ddcb200_ctx *c) { return c ? c->kernelLaunches : 0; }
+
+extern "C" int64_t ddcb200_lastListBuild(ddcb200_ctx *c) { return c ? c->lastBuildLoop : -1; }
 
 extern "C" int ddcb200_profile(ddcb200_ctx *c, int enable)
 {

@@ -180,6 +180,9 @@ struct ddcb200_ctx
     int nbrCap = 0;               // entries per bead allocated
     bool listValid = false;
     int64_t lastBuildLoop = -1;
+    // displacement-triggered rebuild (updateRate == 0, nbrcheck.cuh)
+    DevBuf<double> chk, chkPartial;   // chk: 3 sums now, 3 sums at the build, bits of max d^2
+    double *chkHost = nullptr;        // pinned
 
     // accumulators
     DevBuf<double> pairPartial, bondPartial, kinPartial;   // per-CTA partial sums

@@ -487,7 +487,7 @@ int ddcb200_deckLoad(const char *objectFile, const char *restartFile, const char
         odb_getInts(ddc, "ly", &d->ddc_ly, 1, "0");
         odb_getInts(ddc, "lz", &d->ddc_lz, 1, "0");
     }
-    if (d->params.updateRate <= 0) FAIL("DDC updateRate=0 (displacement-triggered rebuild) is not supported; set updateRate>0");
+    if (d->params.updateRate < 0) FAIL("DDC updateRate must be >= 0");
     const ODB_OBJECT *pi = odb_find(db, piName, "PRINTINFO");
     if (pi) odb_getInts(pi, "printMolecularPressure", &d->printMolecularPressure, 1, "0");
 

@@ -37,7 +37,7 @@ typedef struct ddcb200_params
 {
     double h[9];          /* box matrix, row major xx xy xz yx .. zz; must be orthorhombic */
     int pbc;              /* boundary bits, only 7 (xyz periodic) is supported */
-    int updateRate;       /* DDC updateRate: rebuild cells+lists when loop % updateRate == 0 */
+    int updateRate;       /* DDC updateRate: rebuild cells+lists when loop % updateRate == 0; 0 = when displacements demand it */
     double rmax;          /* potential cutoff (POTENTIAL cutoff, 11 Angstrom) */
     double deltaR;        /* NEIGHBOR deltaR (skin) */
     double minBoxSide;    /* NEIGHBOR minBoxSide */
@@ -171,6 +171,11 @@ int ddcb200_profileRead(ddcb200_ctx *ctx, double ms[8], int64_t launches[8], int
 int ddcb200_timerRecord(ddcb200_ctx *ctx, int which);
 int ddcb200_timerElapsed(ddcb200_ctx *ctx, int from, int to, double *ms);
 int64_t ddcb200_kernelLaunches(ddcb200_ctx *ctx);
+
+/* Loop index of the last cell sort + list build = sys->neighbor->lastUpdate (src/ddcUpdateAll.c:135).  With DDC
+ * updateRate = 0 the build is displacement-triggered: neighborRef + neighborCheck (src/neighbor.c:117-246) through
+ * check4updateNeighbor / evalUpdateFlag (src/ddcUpdateAll.c:48-71). */
+int64_t ddcb200_lastListBuild(ddcb200_ctx *ctx);
 
 /* ---- multi-GPU: ddc-style spatial decomposition over the GPUs of one box, one process per GPU ----
  * Replaces ddc_init + ddcAssignment + ddcSendRecvTables + ddcUpdate (src/ddc.c:61-117,

@@ -27,7 +27,7 @@ typedef struct { char internal[128]; } ncclUniqueId;
 typedef int ncclResult_t;
 enum { ncclSuccess = 0, ncclSystemError = 2, ncclInvalidUsage = 5 };
 enum ncclDataType_t { ncclDouble = 8 };
-enum ncclRedOp_t { ncclSum = 0 };
+enum ncclRedOp_t { ncclSum = 0, ncclMax = 2 };
 
 namespace emu
 {
@@ -88,7 +88,7 @@ static inline ncclResult_t ncclCommDestroy(ncclComm_t c)
     free(c);
     return ncclSuccess;
 }
-static inline ncclResult_t ncclAllReduce(const void *src, void *dst, size_t count, ncclDataType_t, ncclRedOp_t, ncclComm_t c, cudaStream_t)
+static inline ncclResult_t ncclAllReduce(const void *src, void *dst, size_t count, ncclDataType_t, ncclRedOp_t op, ncclComm_t c, cudaStream_t)
 {
     if (count * 8 > c->slot) return ncclInvalidUsage;
     memcpy(emu::ncclSlot(c, c->rank), src, count * 8);
@@ -96,8 +96,12 @@ static inline ncclResult_t ncclAllReduce(const void *src, void *dst, size_t coun
     double *d = (double *)dst;
     for (size_t k = 0; k < count; k++)
     {
-        double s = 0.0;
-        for (int r = 0; r < c->nranks; r++) s += ((const double *)emu::ncclSlot(c, r))[k];
+        double s = op == ncclMax ? -1e308 : 0.0;
+        for (int r = 0; r < c->nranks; r++)
+        {
+            const double v = ((const double *)emu::ncclSlot(c, r))[k];
+            s = op == ncclMax ? (v > s ? v : s) : s + v;
+        }
         d[k] = s;
     }
     emu::ncclBarrier(c);

@@ -59,6 +59,12 @@ def test_emu_printinfo_line(emu, golden_dir):
     tg.test_printinfo_line_matches_reference_data_file(golden_dir)
 
 
+def test_emu_displacement_triggered_rebuild(emu, golden_dir, tmp_path):
+    """DDC updateRate = 0: rebuild loops, pair counts and energies against the reference's trace (k_nbr_rbar_partial, k_nbr_check)."""
+    import test_zzzz_ur0 as tu
+    tu.check_ur0(golden_dir, "popc_small", tmp_path, 40)
+
+
 def _torchrun(nproc, port, script, *args, env=None):
     import subprocess
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
