@@ -58,7 +58,15 @@ class DeckStruct(C.Structure):
                 ("nTerms", C.c_int64), ("termKind", _P(C.c_int)), ("termIdx", _P(C.c_int)), ("termParm", _P(C.c_double)),
                 ("nRestraints", C.c_int64), ("restrBead", _P(C.c_int)), ("restrFrac0", _P(C.c_double)),
                 ("restrKb", _P(C.c_double)), ("restrFc", _P(C.c_double)), ("restrOrigin", C.c_int),
-                ("nMol", C.c_int64), ("nMolTotal", C.c_int64), ("molOffset", _P(C.c_int64)), ("molBeads", _P(C.c_int))]
+                ("nMol", C.c_int64), ("nMolTotal", C.c_int64), ("molOffset", _P(C.c_int64)), ("molBeads", _P(C.c_int)),
+                ("integratorType", C.c_int), ("ncT", C.c_double), ("ncP0", C.c_double), ("ncBeta", C.c_double),
+                ("ncTauBarostat", C.c_double), ("ncIsotropic", C.c_int),
+                ("nGroups", C.c_int), ("groupName", _P(C.c_char_p)), ("groupType", _P(C.c_int)), ("groupTeq", _P(C.c_double)),
+                ("groupTau", _P(C.c_double)), ("groupVcm", _P(C.c_double)), ("groupOfBead", _P(C.c_ubyte)),
+                ("haveRandom", C.c_int), ("randomSeed", C.c_uint64), ("rngState", _P(C.c_uint64)), ("rngMult", _P(C.c_uint32)),
+                ("rngPrime", _P(C.c_uint32)),
+                ("nCons", C.c_int64), ("consAtomOffset", _P(C.c_int64)), ("consPairOffset", _P(C.c_int64)),
+                ("consAtomBead", _P(C.c_int)), ("consPairA", _P(C.c_int)), ("consPairB", _P(C.c_int)), ("consPairDist", _P(C.c_double))]
 
 
 class DdcError(RuntimeError):
@@ -121,6 +129,14 @@ def _declare(L):
         "ddcb200_ddcenergy": (i32, [vp, i32]),
         "ddcb200_nglf": (i32, [vp, i32, dbl]),
         "ddcb200_energyInfo": (i32, [vp, dbl, _P(EType)]),
+        "ddcb200_setGroups": (i32, [vp, i32, pi, pd, pd, pd, i64, _P(C.c_ubyte)]),
+        "ddcb200_setRandom": (i32, [vp, i64, _P(C.c_uint64), _P(C.c_uint32), _P(C.c_uint32)]),
+        "ddcb200_getRandom": (i32, [vp, i64, _P(C.c_uint64)]),
+        "ddcb200_setConstraints": (i32, [vp, i64, _P(C.c_int64), pi, _P(C.c_int64), pi, pi, pd]),
+        "ddcb200_nglfconstraintParms": (i32, [vp, dbl, dbl, dbl, dbl]),
+        "ddcb200_nglfconstraint": (i32, [vp, i32, dbl]),
+        "ddcb200_getBox": (i32, [vp, pd]),
+        "ddcb200_constraintFailures": (i64, [vp]),
         "ddcb200_getCells": (i32, [vp, pi, pi, pd]),
         "ddcb200_getPairs": (i64, [vp, i64, pi, pi, pi]),
         "ddcb200_profile": (i32, [vp, i32]),
@@ -151,7 +167,8 @@ EXPORTS = ["ddcb200_lastError", "ddcb200_deviceCount", "ddcb200_create", "ddcb20
            "ddcb200_martiniNonBondParms", "ddcb200_setSpecies", "ddcb200_setBeads", "ddcb200_setExclusions",
            "ddcb200_martiniBondParms", "ddcb200_setRestraints", "ddcb200_setMolecules", "ddcb200_sendState",
            "ddcb200_numLocal", "ddcb200_getLocalBeads", "ddcb200_getState", "ddcb200_constructList", "ddcb200_ddcenergy",
-           "ddcb200_nglf", "ddcb200_energyInfo", "ddcb200_getCells", "ddcb200_getPairs", "ddcb200_profile",
+           "ddcb200_nglf", "ddcb200_energyInfo", "ddcb200_setGroups", "ddcb200_setRandom", "ddcb200_getRandom", "ddcb200_setConstraints",
+           "ddcb200_nglfconstraintParms", "ddcb200_nglfconstraint", "ddcb200_getBox", "ddcb200_constraintFailures", "ddcb200_getCells", "ddcb200_getPairs", "ddcb200_profile",
            "ddcb200_profileRead", "ddcb200_timerRecord", "ddcb200_timerElapsed", "ddcb200_kernelLaunches", "ddcb200_lastListBuild", "ddcb200_ncclUniqueId", "ddcb200_ddcInit", "ddcb200_ddcPlan", "ddcb200_deckLoad", "ddcb200_deckFree",
            "ddcb200_lastHostError", "ddcb200_simulateBind", "ddcb200_simulateBindRank", "ddcb200_printinfoLine", "ddcb200_unitsConvert"]
 
@@ -207,7 +224,15 @@ class Deck:
             "termParm": (s.termParm, 3 * int(s.nTerms), np.float64),
             "molOffset": (s.molOffset, int(s.nMol) + 1, np.int64),
             "restrBead": (s.restrBead, int(s.nRestraints), np.int32),
+            "groupOfBead": (s.groupOfBead, n if s.groupOfBead else 0, np.uint8),
+            "rngState": (s.rngState, n if s.rngState else 0, np.uint64), "rngMult": (s.rngMult, n if s.rngState else 0, np.uint32),
+            "rngPrime": (s.rngPrime, n if s.rngState else 0, np.uint32),
+            "consAtomOffset": (s.consAtomOffset, int(s.nCons) + 1, np.int64), "consPairOffset": (s.consPairOffset, int(s.nCons) + 1, np.int64),
         }
+        if name in ("consAtomBead",):
+            return _arr(s.consAtomBead, int(self.array("consAtomOffset")[-1]), np.int32)
+        if name in ("consPairA", "consPairB", "consPairDist"):
+            return _arr(getattr(s, name), int(self.array("consPairOffset")[-1]), np.float64 if name == "consPairDist" else np.int32)
         if name == "bpairI" or name == "bpairJ":
             nb = int(self.array("bpairOffset")[-1])
             return _arr(getattr(s, name), nb, np.int32)
@@ -264,6 +289,31 @@ class Simulate:
 
     def nglf(self, nsteps=1, dt=None):
         self._ck(lib().ddcb200_nglf(self.ctx, int(nsteps), float(self.dt if dt is None else dt)))
+
+    def nglfconstraint(self, nsteps=1, dt=None):
+        """nglfconstraint (src/nglfconstraint.c:510-574) called nsteps times."""
+        self._ck(lib().ddcb200_nglfconstraint(self.ctx, int(nsteps), float(self.dt if dt is None else dt)))
+
+    def eval_integrator(self, nsteps=1, dt=None):
+        """simulate->integrator->eval_integrator (src/masters.c:445): the INTEGRATOR object of the deck decides."""
+        if int(self.deck.s.integratorType) == 1:
+            self.nglfconstraint(nsteps, dt)
+        else:
+            self.nglf(nsteps, dt)
+
+    def getBox(self):
+        h = np.empty(9, np.float64)
+        self._ck(lib().ddcb200_getBox(self.ctx, h.ctypes.data_as(_P(C.c_double))))
+        return h
+
+    def getRandom(self):
+        """current per-bead LCG64 states, input order"""
+        st = np.empty(self.deck.n, np.uint64)
+        self._ck(lib().ddcb200_getRandom(self.ctx, st.size, st.ctypes.data_as(_P(C.c_uint64))))
+        return st
+
+    def constraintFailures(self):
+        return int(lib().ddcb200_constraintFailures(self.ctx))
 
     def sync(self):
         self._ck(lib().ddcb200_sync(self.ctx))

@@ -7,6 +7,7 @@
 #include "bonded.cuh"
 #include "integrate.cuh"
 #include "nbrcheck.cuh"
+#include "nglfcons.cuh"
 #include "ddc.cuh"
 #include <nccl.h>
 #include <math.h>
@@ -177,6 +178,12 @@ static int setupBox(ddcb200_ctx *c)
     pc.keR = p.keR; pc.krf = p.krf; pc.crf = p.crf;
     pc.rmax = p.rmax;
     pc.ntypes = c->ntypes;
+    // barostat: the box may have changed since the list was built (hBuild = 0 before the first build)
+    {
+        const double ex = c->hBuild[0] != 0.0 ? xx - c->hBuild[0] : 0.0, ey = c->hBuild[1] != 0.0 ? yy - c->hBuild[1] : 0.0,
+                     ez = c->hBuild[2] != 0.0 ? zz - c->hBuild[2] : 0.0;
+        pc.listSlack = sqrt(ex * ex + ey * ey + ez * ez);
+    }
     return DDCB200_OK;
 }
 
@@ -238,6 +245,9 @@ extern "C" void ddcb200_destroy(ddcb200_ctx *c)
     c->orderKey.release(); c->pos32.release(); c->nbrRawCount.release(); c->nbrCum.release();
     for (int a = 0; a < 3; a++) c->posBuild[a].release();
     if (c->dmax2) cudaFree(c->dmax2);
+    c->groupOfBead.release(); c->rngState.release(); c->rngMP.release(); c->consAtomOff.release(); c->consAtomBead.release();
+    c->consPairOff.release(); c->consPairA.release(); c->consPairB.release(); c->consPairDist.release();
+    if (c->consFlag) cudaFree(c->consFlag);
     c->chk.release(); c->chkPartial.release();
     if (c->chkHost) cudaFreeHost(c->chkHost);
     c->ownerBead.release(); c->gState.release(); c->ownerOfBead.release(); c->ddcMask.release(); c->ddcCnt.release();
@@ -833,6 +843,8 @@ extern "C" int ddcb200_constructList(ddcb200_ctx *c)
         if (rcs) return rcs;
     }
     c->listValid = true;
+    c->hBuild[0] = c->box.hxx; c->hBuild[1] = c->box.hyy; c->hBuild[2] = c->box.hzz;
+    c->pc.listSlack = 0.0;
     c->lastBuildLoop = c->loop;
     c->totalEntries = (int64_t)c->gridHost->totalEntries;
     c->nPairsListed = (int64_t)(c->gridHost->totalEntries / 2);
@@ -906,8 +918,11 @@ static int neighborCheck(ddcb200_ctx *c, bool *update)
         CKN(ncclAllReduce(c->chk.p + 6, c->chk.p + 6, 1, ncclDouble, ncclMax, (ncclComm_t)c->nccl, st));
     CK(cudaMemcpyAsync(c->chkHost, c->chk.p + 6, sizeof(double), cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
-    // box-strain term |1 - h0 hinv u| (rcut + deltaR): h0 is the box at the build; the box is constant on this path
-    const double *hi = c->box.hinv, *h = c->prm.h;
+    // box-strain term |1 - h0 hinv u| (rcut + deltaR): h0 is the box at the build (it only differs under the barostat)
+    const double *hi = c->box.hinv;
+    double h[9];
+    memcpy(h, c->prm.h, sizeof(h));
+    if (c->hBuild[0] != 0.0) { h[0] = c->hBuild[0]; h[4] = c->hBuild[1]; h[8] = c->hBuild[2]; }
     const double ux = hi[0] + hi[1] + hi[2], uy = hi[3] + hi[4] + hi[5], uz = hi[6] + hi[7] + hi[8];
     const double sx = fabs(1.0 - (h[0] * ux + h[1] * uy + h[2] * uz)), sy = fabs(1.0 - (h[3] * ux + h[4] * uy + h[5] * uz)),
                  sz = fabs(1.0 - (h[6] * ux + h[7] * uy + h[8] * uz));
@@ -1018,10 +1033,14 @@ static int kineticTerms(ddcb200_ctx *c)
     return reduceCols(c, c->kinPartial.p, (int)(c->nPad / TILE), 7, c->colMap.p + 19);
 }
 
+static int nglfcSteps(ddcb200_ctx *c, int nsteps, double dt, const bool baro, const bool cons);
 extern "C" int ddcb200_nglf(ddcb200_ctx *c, int nsteps, double dt)
 {
     if (!c || nsteps < 0) return fail(DDCB200_ERR_ARG, "bad arguments");
     if (c->nLocal == 0) return fail(DDCB200_ERR_STATE, "no state");
+    // nglf calls every bead's group->velocityUpdate (src/nglf.c:75,104): with a LANGEVIN group the step is the
+    // NGLFCONSTRAINT pass without barostat and constraints
+    if (c->anyLangevin) return nglfcSteps(c, nsteps, dt, false, false);
     CK(cudaSetDevice(c->device));
     int rc;
     if (!c->forcesValid)
@@ -1054,18 +1073,9 @@ extern "C" int ddcb200_nglf(ddcb200_ctx *c, int nsteps, double dt)
     return DDCB200_OK;
 }
 
-extern "C" int ddcb200_energyInfo(ddcb200_ctx *c, double kB, ddcb200_etype *out)
+// molecular virial correction + (several ranks) the all-reduce + the copy of the accumulators to pinned host memory
+static int fetchAccumulators(ddcb200_ctx *c)
 {
-    if (!c || !out) return fail(DDCB200_ERR_ARG, "null argument");
-    if (!c->energyValid) return fail(DDCB200_ERR_STATE, "no energy evaluation is current (call ddcenergy(1) or nglf)");
-    CK(cudaSetDevice(c->device));
-    int rc;
-    if (!c->kineticValid)
-    {
-        rc = kineticTerms(c);
-        if (rc) return rc;
-        c->kineticValid = true;
-    }
     cudaStream_t st = c->stream;
     CK(cudaMemsetAsync(c->acc + ACC_MVX, 0, 3 * sizeof(double), st));
     if (c->nMol > 0)
@@ -1088,6 +1098,23 @@ extern "C" int ddcb200_energyInfo(ddcb200_ctx *c, double kB, ddcb200_etype *out)
     }
     CK(cudaMemcpyAsync(c->accHost, accSrc, ACC_N * sizeof(double), cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
+    return DDCB200_OK;
+}
+
+extern "C" int ddcb200_energyInfo(ddcb200_ctx *c, double kB, ddcb200_etype *out)
+{
+    if (!c || !out) return fail(DDCB200_ERR_ARG, "null argument");
+    if (!c->energyValid) return fail(DDCB200_ERR_STATE, "no energy evaluation is current (call ddcenergy(1) or nglf)");
+    CK(cudaSetDevice(c->device));
+    int rc;
+    if (!c->kineticValid)
+    {
+        rc = kineticTerms(c);
+        if (rc) return rc;
+        c->kineticValid = true;
+    }
+    rc = fetchAccumulators(c);
+    if (rc) return rc;
     const double *a = c->accHost;
     memset(out, 0, sizeof(*out));
     out->eLJ = a[ACC_ELJ]; out->eEle = a[ACC_EELE];
@@ -1118,6 +1145,309 @@ extern "C" int ddcb200_energyInfo(ddcb200_ctx *c, double kB, ddcb200_etype *out)
     out->nMolecules = c->nMolTotal;
     out->nPairsListed = (int64_t)(a[ACC_NENTRIES] / 2.0 + 0.25);
     return DDCB200_OK;
+}
+
+// ---- NGLFCONSTRAINT: groups, per-bead random streams, constraints, barostat (nglfcons.cuh) ---------------------
+extern "C" int ddcb200_setGroups(ddcb200_ctx *c, int ngroups, const int *type, const double *kBT, const double *tau, const double *vcm,
+                                 int64_t nGlobal, const unsigned char *groupOfBead)
+{
+    if (!c || ngroups < 1 || !type) return fail(DDCB200_ERR_ARG, "bad arguments");
+    if (ngroups > MAXGROUPS) return fail(DDCB200_ERR_CAPACITY, "more than 8 GROUP objects");
+    CK(cudaSetDevice(c->device));
+    c->anyLangevin = false;
+    for (int g = 0; g < ngroups; g++)
+    {
+        if (type[g] != GROUP_FREE && type[g] != GROUP_LANGEVIN) return fail(DDCB200_ERR_ARG, "GROUP type must be FREE (0) or LANGEVIN (1)");
+        c->groupType[g] = type[g];
+        c->groupKBT[g] = kBT ? kBT[g] : 0.0;
+        c->groupTau[g] = tau ? tau[g] : 1.0;
+        for (int a = 0; a < 3; a++) c->groupVcm[g][a] = vcm ? vcm[3 * g + a] : 0.0;
+        if (type[g] == GROUP_LANGEVIN)
+        {
+            if (!(c->groupTau[g] > 0.0)) return fail(DDCB200_ERR_ARG, "LANGEVIN group needs tau > 0");
+            c->anyLangevin = true;
+        }
+    }
+    c->nGroups = ngroups;
+    if (groupOfBead)
+    {
+        if (c->nGlobal == 0 || nGlobal != c->nGlobal) return fail(DDCB200_ERR_STATE, "setGroups: call setBeads first (bead count differs)");
+        for (int64_t i = 0; i < nGlobal; i++)
+            if (groupOfBead[i] >= ngroups) return fail(DDCB200_ERR_ARG, "group index out of range");
+        CK(c->groupOfBead.ensure((size_t)nGlobal));
+        CK(cudaMemcpy(c->groupOfBead.p, groupOfBead, (size_t)nGlobal, cudaMemcpyHostToDevice));
+    }
+    else
+        c->groupOfBead.release();
+    return DDCB200_OK;
+}
+
+extern "C" int ddcb200_setRandom(ddcb200_ctx *c, int64_t nGlobal, const uint64_t *state, const uint32_t *multID, const uint32_t *prime)
+{
+    if (!c || !state || !multID || !prime) return fail(DDCB200_ERR_ARG, "null argument");
+    if (c->nGlobal == 0 || nGlobal != c->nGlobal) return fail(DDCB200_ERR_STATE, "setRandom: call setBeads first (bead count differs)");
+    CK(cudaSetDevice(c->device));
+    std::vector<uint2> mp((size_t)nGlobal);
+    for (int64_t i = 0; i < nGlobal; i++)
+    {
+        // lcg64_checkValue (src/lcg64.c:110-120)
+        if (multID[i] > 2 || state[i] == 0 || (prime[i] & 1u) == 0) return fail(DDCB200_ERR_ARG, "bad LCG64 state (multID > 2, state 0 or even prime)");
+        mp[(size_t)i] = make_uint2(multID[i], prime[i]);
+    }
+    CK(c->rngState.ensure((size_t)nGlobal));
+    CK(c->rngMP.ensure((size_t)nGlobal));
+    CK(cudaMemcpy(c->rngState.p, state, (size_t)nGlobal * sizeof(uint64_t), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(c->rngMP.p, mp.data(), (size_t)nGlobal * sizeof(uint2), cudaMemcpyHostToDevice));
+    c->haveRandom = true;
+    return DDCB200_OK;
+}
+
+extern "C" int ddcb200_getRandom(ddcb200_ctx *c, int64_t nGlobal, uint64_t *state)
+{
+    if (!c || !state) return fail(DDCB200_ERR_ARG, "null argument");
+    if (!c->haveRandom || nGlobal != c->nGlobal) return fail(DDCB200_ERR_STATE, "no random state of that size");
+    CK(cudaSetDevice(c->device));
+    CK(cudaStreamSynchronize(c->stream));
+    CK(cudaMemcpy(state, c->rngState.p, (size_t)nGlobal * sizeof(uint64_t), cudaMemcpyDeviceToHost));
+    return DDCB200_OK;
+}
+
+extern "C" int ddcb200_setConstraints(ddcb200_ctx *c, int64_t nCons, const int64_t *atomOffset, const int *atomBead, const int64_t *pairOffset,
+                                      const int *pairA, const int *pairB, const double *pairDist)
+{
+    if (!c || nCons < 0) return fail(DDCB200_ERR_ARG, "bad arguments");
+    CK(cudaSetDevice(c->device));
+    c->nCons = 0;
+    if (nCons == 0) return DDCB200_OK;
+    if (!atomOffset || !atomBead || !pairOffset || !pairA || !pairB || !pairDist) return fail(DDCB200_ERR_ARG, "null argument");
+    if (c->nGlobal == 0) return fail(DDCB200_ERR_STATE, "setConstraints: call setBeads first");
+    if (nCons > 0x7fffffff || atomOffset[nCons] > 0x7fffffff || pairOffset[nCons] > 0x7fffffff) return fail(DDCB200_ERR_CAPACITY, "too many constraints");
+    std::vector<int> ao((size_t)nCons + 1), po((size_t)nCons + 1);
+    std::vector<char> seen((size_t)c->nGlobal, 0);
+    for (int64_t k = 0; k <= nCons; k++)
+    {
+        ao[(size_t)k] = (int)atomOffset[k];
+        po[(size_t)k] = (int)pairOffset[k];
+    }
+    for (int64_t k = 0; k < nCons; k++)
+    {
+        const int na = ao[(size_t)k + 1] - ao[(size_t)k], np = po[(size_t)k + 1] - po[(size_t)k];
+        if (na < 0 || np < 0) return fail(DDCB200_ERR_ARG, "constraint offsets must not decrease");
+        if (na > CONS_MAXATOM || np > CONS_MAXPAIR) return fail(DDCB200_ERR_CAPACITY, "constraint cluster larger than 32 atoms / 48 pairs");
+        for (int a = ao[(size_t)k]; a < ao[(size_t)k + 1]; a++)
+        {
+            const int b = atomBead[a];
+            if (b < 0 || b >= c->nGlobal) return fail(DDCB200_ERR_ARG, "constraint bead index out of range");
+            if (seen[(size_t)b]) return fail(DDCB200_ERR_ARG, "constraint clusters must be disjoint (a bead is in two clusters)");
+            seen[(size_t)b] = 1;
+        }
+        for (int q = po[(size_t)k]; q < po[(size_t)k + 1]; q++)
+        {
+            if (pairA[q] < 0 || pairA[q] >= na || pairB[q] < 0 || pairB[q] >= na || pairA[q] == pairB[q])
+                return fail(DDCB200_ERR_ARG, "constraint pair index outside its cluster");
+            if (!(pairDist[q] > 0.0)) return fail(DDCB200_ERR_ARG, "constraint distance must be positive");
+        }
+    }
+    const size_t nA = (size_t)ao[(size_t)nCons], nP = (size_t)po[(size_t)nCons];
+    CK(c->consAtomOff.ensure((size_t)nCons + 1));
+    CK(c->consPairOff.ensure((size_t)nCons + 1));
+    CK(c->consAtomBead.ensure(nA + 1));
+    CK(c->consPairA.ensure(nP + 1));
+    CK(c->consPairB.ensure(nP + 1));
+    CK(c->consPairDist.ensure(nP + 1));
+    CK(cudaMemcpy(c->consAtomOff.p, ao.data(), ((size_t)nCons + 1) * sizeof(int), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(c->consPairOff.p, po.data(), ((size_t)nCons + 1) * sizeof(int), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(c->consAtomBead.p, atomBead, nA * sizeof(int), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(c->consPairA.p, pairA, nP * sizeof(int), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(c->consPairB.p, pairB, nP * sizeof(int), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(c->consPairDist.p, pairDist, nP * sizeof(double), cudaMemcpyHostToDevice));
+    if (!c->consFlag)
+    {
+        CK(cudaMalloc((void **)&c->consFlag, sizeof(int)));
+        CK(cudaMemset(c->consFlag, 0, sizeof(int)));
+    }
+    c->nCons = (int)nCons;
+    return DDCB200_OK;
+}
+
+extern "C" int ddcb200_nglfconstraintParms(ddcb200_ctx *c, double kBT, double P0, double beta, double tauBarostat)
+{
+    if (!c) return fail(DDCB200_ERR_ARG, "null ctx");
+    if (beta > 0.0 && !(tauBarostat > 0.0)) return fail(DDCB200_ERR_ARG, "barostat (beta > 0) needs tauBarostat > 0");
+    c->ncKBT = kBT;
+    c->ncP0 = P0;
+    c->ncBeta = beta;
+    c->ncTau = tauBarostat;
+    return DDCB200_OK;
+}
+
+extern "C" int ddcb200_getBox(ddcb200_ctx *c, double h[9])
+{
+    if (!c || !h) return fail(DDCB200_ERR_ARG, "null argument");
+    memcpy(h, c->prm.h, 9 * sizeof(double));
+    return DDCB200_OK;
+}
+
+static GroupTab groupTabOf(const ddcb200_ctx *c)
+{
+    GroupTab g;
+    memset(&g, 0, sizeof(g));
+    g.n = c->nGroups;
+    for (int k = 0; k < MAXGROUPS; k++)
+    {
+        g.type[k] = c->groupType[k];
+        g.kBT[k] = c->groupKBT[k];
+        g.tau[k] = c->groupTau[k] > 0.0 ? c->groupTau[k] : 1.0;
+        g.vcx[k] = c->groupVcm[k][0];
+        g.vcy[k] = c->groupVcm[k][1];
+        g.vcz[k] = c->groupVcm[k][2];
+    }
+    return g;
+}
+
+template <int MODE>
+static int launchNglfc(ddcb200_ctx *c, double halfDt, double dt, const double scale[3])
+{
+    ProfScope ps(c, PROF_INTEGRATE);
+    const int cur = c->cur;
+    const int tiles = (int)(c->nPad / TILE);
+    if (MODE & (NC_DRIFT | NC_SCALE)) c->haloDirty = true;
+    LAUNCH(k_nglfc<MODE>, tiles, TILE, 0, c->stream)((int)c->nIon, c->pos4[cur].p, c->vel[cur][0].p, c->vel[cur][1].p, c->vel[cur][2].p,
+                                                 c->frc[0].p, c->frc[1].p, c->frc[2].p, c->massOfBead.p, c->groupOfBead.p, c->rngState.p,
+                                                 c->rngMP.p, groupTabOf(c), halfDt, dt, scale[0], scale[1], scale[2], c->pc, c->kinPartial.p,
+                                                 c->posBuild[0].p, c->posBuild[1].p, c->posBuild[2].p, c->dmax2);
+    CKL("k_nglfc");
+    return DDCB200_OK;
+}
+
+template <bool FRONT>
+static int launchConstraint(ddcb200_ctx *c, double dt)
+{
+    ProfScope ps(c, PROF_INTEGRATE);
+    const int cur = c->cur;
+    LAUNCH(k_constraint<FRONT>, (c->nCons + 63) / 64, 64, 0, c->stream)(c->nCons, c->consAtomOff.p, c->consAtomBead.p, c->consPairOff.p,
+                                                                    c->consPairA.p, c->consPairB.p, c->consPairDist.p, c->slotOfBead.p,
+                                                                    c->pos4[cur].p, c->vel[cur][0].p, c->vel[cur][1].p, c->vel[cur][2].p,
+                                                                    c->massOfBead.p, dt, c->pc, c->box.hinv[0], c->box.hinv[4], c->box.hinv[8],
+                                                                    c->consFlag);
+    CKL("k_constraint");
+    return DDCB200_OK;
+}
+
+// changeVolume (src/nglfconstraint.c:64-84) on molecularPressure (src/molecularPressure.c:57-67): new box, and the
+// diagonal of hfac = h_new h_old^-1 that adjustPosn applies to the positions (updateH0, src/box.c:40-48)
+static int barostat(ddcb200_ctx *c, double dt, double scale[3])
+{
+    int rc = fetchAccumulators(c);
+    if (rc) return rc;
+    const double *a = c->accHost;
+    const double vol = c->box.volume;
+    const double nkT = (double)c->nMolTotal * c->ncKBT;
+    double pxx = (a[ACC_VXX] + a[ACC_MVX]) + nkT, pyy = (a[ACC_VYY] + a[ACC_MVY]) + nkT, pzz = (a[ACC_VZZ] + a[ACC_MVZ]) + nkT;
+    pxx /= vol; pyy /= vol; pzz /= vol;       // SMATNORM
+    pxx -= c->ncP0; pyy -= c->ncP0; pzz -= c->ncP0;
+    const double btt = c->ncBeta * dt / c->ncTau;
+    const double Pxx = 0.5 * (pxx + pyy), Pzz = pzz;     // semi-isotropic: x and y share the mean in-plane pressure
+    const double lx = cbrt(1.0 + Pxx * btt), ly = cbrt(1.0 + Pxx * btt), lz = cbrt(1.0 + Pzz * btt);
+    const double hi[3] = {c->box.hinv[0], c->box.hinv[4], c->box.hinv[8]};   // inverse of the old box
+    double *h = c->prm.h;
+    const double hn[3] = {lx * h[0], ly * h[4], lz * h[8]};
+    scale[0] = hn[0] * hi[0]; scale[1] = hn[1] * hi[1]; scale[2] = hn[2] * hi[2];
+    if (fabs(scale[0] - 1.0) <= 1e-14 && fabs(scale[1] - 1.0) <= 1e-14 && fabs(scale[2] - 1.0) <= 1e-14)
+        scale[0] = scale[1] = scale[2] = 1.0;     // matrix_equal_tol(hfac, I, 1e-14)
+    h[0] = hn[0]; h[4] = hn[1]; h[8] = hn[2];
+    return setupBox(c);
+}
+
+static int nglfcSteps(ddcb200_ctx *c, int nsteps, double dt, const bool baro, const bool cons)
+{
+    if (!c || nsteps < 0) return fail(DDCB200_ERR_ARG, "bad arguments");
+    if (c->nLocal == 0) return fail(DDCB200_ERR_STATE, "no state");
+    if (c->nranks > 1) return fail(DDCB200_ERR_STATE, "LANGEVIN groups / nglfconstraint run on one GPU in this version (per-bead random streams and the box are not exchanged)");
+    if (c->anyLangevin && !c->haveRandom) return fail(DDCB200_ERR_STATE, "LANGEVIN groups need the per-bead random state (setRandom)");
+    CK(cudaSetDevice(c->device));
+    int rc;
+    if (!c->forcesValid || (baro && nsteps > 0 && !c->energyValid))
+    {
+        // firstEnergyCall (src/masters.c:579-620); the barostat needs the virial of the current forces
+        rc = ddcb200_ddcenergy(c, 1);
+        if (rc) return rc;
+    }
+    const double half = 0.5 * dt;
+    double scale[3] = {1.0, 1.0, 1.0};
+    for (int s = 0; s < nsteps; s++)
+    {
+        if (baro)
+        {
+            rc = barostat(c, dt, scale);
+            if (rc) return rc;
+        }
+        if (!cons)
+        {
+            // one pass: BACK update of the previous step (inside this call), barostat scaling, FRONT update, drift
+            if (s == 0) rc = baro ? launchNglfc<NC_SCALE | NC_FRONT | NC_DRIFT>(c, half, dt, scale) : launchNglfc<NC_FRONT | NC_DRIFT>(c, half, dt, scale);
+            else rc = baro ? launchNglfc<NC_BACK | NC_SCALE | NC_FRONT | NC_DRIFT>(c, half, dt, scale)
+                           : launchNglfc<NC_BACK | NC_FRONT | NC_DRIFT>(c, half, dt, scale);
+            if (rc) return rc;
+        }
+        else
+        {
+            rc = baro ? launchNglfc<NC_SCALE | NC_FRONT>(c, half, dt, scale) : launchNglfc<NC_FRONT>(c, half, dt, scale);
+            if (rc) return rc;
+            rc = launchConstraint<true>(c, dt);
+            if (rc) return rc;
+            rc = launchNglfc<NC_DRIFT>(c, half, dt, scale);
+            if (rc) return rc;
+        }
+        c->loop++;
+        c->time += dt;
+        const bool last = s == nsteps - 1;
+        rc = ddcb200_ddcenergy(c, (baro || last) ? 1 : 0);
+        if (rc) return rc;
+        if (cons)
+        {
+            rc = launchNglfc<NC_BACK>(c, half, dt, scale);
+            if (rc) return rc;
+            rc = launchConstraint<false>(c, dt);
+            if (rc) return rc;
+        }
+        else if (last)
+        {
+            rc = launchNglfc<NC_BACK | NC_KE>(c, half, dt, scale);
+            if (rc) return rc;
+        }
+    }
+    if (nsteps > 0)
+    {
+        if (cons)
+        {
+            rc = launchNglfc<NC_KE>(c, half, dt, scale);
+            if (rc) return rc;
+        }
+        ProfScope ps(c, PROF_REDUCE);
+        rc = reduceCols(c, c->kinPartial.p, (int)(c->nPad / TILE), 7, c->colMap.p + 19);
+        if (rc) return rc;
+        c->kineticValid = true;
+    }
+    return DDCB200_OK;
+}
+
+extern "C" int ddcb200_nglfconstraint(ddcb200_ctx *c, int nsteps, double dt)
+{
+    if (!c) return fail(DDCB200_ERR_ARG, "null ctx");
+    return nglfcSteps(c, nsteps, dt, c->ncBeta > 0.0, c->nCons > 0);
+}
+
+// number of constraint clusters that hit the iteration cap since the context was created (the reference prints
+// "too many contraint iterations" and continues, src/nglfconstraint.c:246)
+extern "C" int64_t ddcb200_constraintFailures(ddcb200_ctx *c)
+{
+    if (!c || !c->consFlag) return 0;
+    int v = 0;
+    cudaSetDevice(c->device);
+    cudaStreamSynchronize(c->stream);
+    cudaMemcpy(&v, c->consFlag, sizeof(int), cudaMemcpyDeviceToHost);
+    return v;
 }
 
 // ---- parity hooks -------------------------------------------------------------------------

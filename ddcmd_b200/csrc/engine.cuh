@@ -61,6 +61,7 @@ struct PairConst
     double keR, krf, crf;
     double rmax;
     double binEdge[NBINS - 1];   // r edges of the build-time distance bins
+    double listSlack;            // |h - h_build| (barostat): added to the displacement bound of the list walk; 0 for a fixed box
     int ntypes;
 };
 
@@ -234,4 +235,20 @@ struct ddcb200_ctx
     int nSendTot = 0, nRecvTot = 0;
     bool haloDirty = false, localsDirty = false;
     DevBuf<double> accG;              // all-reduced accumulators
+
+    // NGLFCONSTRAINT (nglfcons.cuh): groups, per-bead LCG64 streams, constraint clusters, barostat
+    int nGroups = 1;
+    int groupType[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    double groupKBT[8] = {0}, groupTau[8] = {0}, groupVcm[8][3] = {{0}};
+    bool anyLangevin = false;
+    DevBuf<unsigned char> groupOfBead;   // by input index; null = every bead in group 0
+    DevBuf<uint64_t> rngState;           // by input index
+    DevBuf<uint2> rngMP;                 // {multID, prime}
+    bool haveRandom = false;
+    int nCons = 0;
+    DevBuf<int> consAtomOff, consAtomBead, consPairOff, consPairA, consPairB;
+    DevBuf<double> consPairDist;
+    int *consFlag = nullptr;             // device: clusters that hit the iteration cap
+    double ncKBT = 0.0, ncP0 = 0.0, ncBeta = 0.0, ncTau = 0.0;   // nglfconstraint_parms: kB*T, P0, beta, tauBarostat
+    double hBuild[3] = {0, 0, 0};        // box edges at the last list build (nbr->h0, src/neighbor.c:231)
 };

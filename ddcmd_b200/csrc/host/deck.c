@@ -37,12 +37,12 @@ double ddcb200_unitsConvert(double value, const char *from, const char *to) { re
 typedef struct { int atomI, atomJ, func; char typeI[32], typeJ[32]; double kb, b0; } H_BOND;
 typedef struct { int atomI, atomJ, atomK, func; double ktheta, theta0; } H_ANGLE;
 typedef struct { int atomI, atomJ, atomK, atomL, func, n; double kchi, delta; } H_TORS;
-typedef struct { int atomI, atomJ, valid; } H_PAIR;
+typedef struct { int atomI, atomJ, valid, list; double r0; } H_PAIR;   /* list, r0: constraints only */
 typedef struct { char name[32], type[32]; int atomID, typeID; double charge; } H_ATOM;
 typedef struct
 {
     char objName[64], resName[32];
-    int resID, nAtoms, nBonds, nAngles, nTors, nExcl, nCons;
+    int resID, nAtoms, nBonds, nAngles, nTors, nExcl, nCons, nConsLists;
     H_ATOM *atoms;
     H_BOND *bonds;
     H_ANGLE *angles;
@@ -200,9 +200,12 @@ static int loadResi(ODB *db, const char *name, H_RESI *r)
             odb_getInts(b, "atomJ", &h->atomJ, 1, "0");
             odb_getInts(b, "func", &func, 1, "1");
             h->valid = (func == 1);
+            h->list = i;
+            if (odb_getWithUnits(b, "r0", &h->r0, 1, "0.0", "nm", NULL) < 0) return herr("bad r0 unit in CONSPARMS %s", sub[k]);
         }
         odb_freeStrings(sub, ns);
     }
+    r->nConsLists = n > 0 ? n : 0;
     odb_freeStrings(names, n);
     return 0;
 }
@@ -264,7 +267,7 @@ static void freeMMFF(H_MMFF *m)
 typedef struct { const char *name; int index; } NameIdx;
 static int cmpName(const void *a, const void *b) { return strcmp(((const NameIdx *)a)->name, ((const NameIdx *)b)->name); }
 
-static int readAtoms(const char *path, int64_t size, ddcb200_deck *d, NameIdx *sortedSpecies, int nspecies, int64_t *filled)
+static int readAtoms(const char *path, int64_t size, ddcb200_deck *d, NameIdx *sortedSpecies, int nspecies, int64_t *filled, int *randomMissing)
 {
     FILE *f = fopen(path, "rb");
     if (!f) return herr("cannot open atoms file %s", path);
@@ -296,6 +299,12 @@ static int readAtoms(const char *path, int64_t size, ddcb200_deck *d, NameIdx *s
             if (nf < 10) bad = 1;
             for (int i = 0; i < 10 && i < nf; i++) bad |= strcmp(fn[i], want[i]) != 0;
             odb_freeStrings(fn, nf);
+            {
+                char *rnd = NULL;
+                odb_getString(hdb->obj[0], "random", &rnd, "NotSet");
+                if (strcmp(rnd, "NONE") == 0) *randomMissing = 1;   /* hasRandomField == No (src/collection_read.c:103-109) */
+                free(rnd);
+            }
             if (bad) { odb_free(hdb); free(text); return herr("atoms file %s: only ASCII records 'id class type group rx ry rz vx vy vz' are supported", path); }
         }
         odb_free(hdb);
@@ -323,6 +332,14 @@ static int readAtoms(const char *path, int64_t size, ddcb200_deck *d, NameIdx *s
             if (*p) *p++ = 0;
         }
         const char *type = tok[1];
+        if (d->groupOfBead)
+        {
+            int gi = -1;
+            for (int g = 0; g < d->nGroups; g++)
+                if (strcmp(d->groupName[g], tok[2]) == 0) { gi = g; break; }
+            if (gi < 0) { herr("atoms file %s: record %lld names GROUP %s, which SYSTEM groups does not list", path, (long long)i, tok[2]); free(text); return -1; }
+            d->groupOfBead[i] = (unsigned char)gi;
+        }
         NameIdx key = {type, 0};
         NameIdx *hit = (NameIdx *)bsearch(&key, sortedSpecies, nspecies, sizeof(NameIdx), cmpName);
         if (!hit) { free(text); return herr("atoms file %s: unknown species %s", path, type); }
@@ -333,7 +350,22 @@ static int readAtoms(const char *path, int64_t size, ddcb200_deck *d, NameIdx *s
             if (end == p) { free(text); return herr("atoms file %s: bad number in record %lld", path, (long long)i); }
             p = end;
         }
-        while (*p && *p != '\n') p++;   /* ignore trailing fields (random state, group data) */
+        if (d->rngState && !*randomMissing)
+        {
+            /* lcg64_parse (src/lcg64.c:87-94): "%llx %u %x"; one unparsable record makes every bead use the default */
+            unsigned long long st;
+            unsigned mult, prime;
+            int used = 0;
+            char *eol = p;
+            while (*eol && *eol != '\n') eol++;
+            const char save = *eol;
+            *eol = 0;
+            const int cnt = sscanf(p, "%llx %u %x%n", &st, &mult, &prime, &used);
+            *eol = save;
+            if (cnt != 3 || prime == 0 || mult > 2) *randomMissing = 1;
+            else { d->rngState[i] = st; d->rngMult[i] = mult; d->rngPrime[i] = prime; }
+        }
+        while (*p && *p != '\n') p++;   /* ignore the remaining fields (group data) */
         d->gid[i] = gid;
         d->species[i] = hit->index;
         d->rx[i] = lc * v[0]; d->ry[i] = lc * v[1]; d->rz[i] = lc * v[2];
@@ -378,6 +410,74 @@ static int cmpGid(const void *a, const void *b)
     return x < y ? -1 : (x > y ? 1 : 0);
 }
 
+/* ---- per-bead LCG64 default streams ----------------------------------------------------------- */
+static uint64_t mulmod(uint64_t a, uint64_t b, uint64_t m) { return (uint64_t)(((__uint128_t)a * b) % m); }
+static uint64_t powmod(uint64_t a, uint64_t e, uint64_t m)
+{
+    uint64_t r = 1;
+    a %= m;
+    while (e)
+    {
+        if (e & 1) r = mulmod(r, a, m);
+        a = mulmod(a, a, m);
+        e >>= 1;
+    }
+    return r;
+}
+/* primality as isPrime1 decides it (src/primes.c:128-160): Miller-Rabin with the bases 2..17, exact below 3.4e14 */
+static int isPrime64(uint64_t n)
+{
+    static const uint64_t bases[7] = {2, 3, 5, 7, 11, 13, 17};
+    if (n < 2) return 0;
+    for (int i = 0; i < 7; i++)
+    {
+        if (n == bases[i]) return 1;
+        if (n % bases[i] == 0) return 0;
+    }
+    uint64_t s = n - 1;
+    int r = 0;
+    while ((s & 1) == 0) { s >>= 1; r++; }
+    for (int i = 0; i < 7; i++)
+    {
+        uint64_t x = powmod(bases[i], s, n);
+        if (x == 1 || x == n - 1) continue;
+        int comp = 1;
+        for (int k = 1; k < r && comp; k++)
+        {
+            x = mulmod(x, x, n);
+            if (x == n - 1) comp = 0;
+        }
+        if (comp) return 0;
+    }
+    return 1;
+}
+/* lcg64_default called for bead 0..n-1 in file order with seed = gid (src/collection.c:102-108, src/lcg64.c:96-109):
+ * state = INIT_SEED ^ gid, multID cycles 0,1,2, a new prime every third bead.  nextPrime (src/primes.c:33-66) on one
+ * task walks the odd numbers upwards from (2^31 + 1) - 30000 (prime_init(30000, 0, 1), src/ddcMD.c:70). */
+static void lcg64Defaults(ddcb200_deck *d)
+{
+    const uint64_t INIT_SEED = 0x2bc6ffff8cfe166dull;
+    uint64_t cand = ((2ull << 30) + 1ull) - 30000ull;
+    if ((cand & 1) == 0) cand++;
+    int first = 1;
+    uint64_t prime = 0;
+    unsigned mult = 0;
+    for (int64_t i = 0; i < d->n; i++)
+    {
+        if (mult == 0)
+        {
+            if (!first) cand += 2;
+            first = 0;
+            while (!isPrime64(cand)) cand += 2;
+            prime = cand;
+        }
+        d->rngState[i] = INIT_SEED ^ d->gid[i];
+        d->rngMult[i] = mult;
+        d->rngPrime[i] = (uint32_t)prime;
+        mult = (mult + 1) % 3;
+    }
+}
+
 void ddcb200_deckFree(ddcb200_deck *d)
 {
     if (!d) return;
@@ -389,6 +489,10 @@ void ddcb200_deckFree(ddcb200_deck *d)
     free(d->termKind); free(d->termIdx); free(d->termParm);
     free(d->restrBead); free(d->restrFrac0); free(d->restrKb); free(d->restrFc);
     free(d->molOffset); free(d->molBeads);
+    for (int i = 0; i < d->nGroups; i++) free(d->groupName[i]);
+    free(d->groupName); free(d->groupType); free(d->groupTeq); free(d->groupTau); free(d->groupVcm); free(d->groupOfBead);
+    free(d->rngState); free(d->rngMult); free(d->rngPrime);
+    free(d->consAtomOffset); free(d->consPairOffset); free(d->consAtomBead); free(d->consPairA); free(d->consPairB); free(d->consPairDist);
     free(d);
 }
 
@@ -440,28 +544,102 @@ int ddcb200_deckLoad(const char *objectFile, const char *restartFile, const char
     if (odb_getWithUnits(sim, "time", &d->time, 1, "0.0", "t", NULL) < 0) FAIL("bad time unit");
     if (odb_getWithUnits(sim, "dt", &d->dt, 1, "1.0", "t", NULL) < 0) FAIL("bad dt unit");
 
-    /* INTEGRATOR: only NGLF (src/integrator.c:59-64); GROUPs: only FREE (src/group.c:78-82) */
+    /* INTEGRATOR: NGLF or NGLFCONSTRAINT (src/integrator.c:59-83) */
     const ODB_OBJECT *integ = odb_find(db, intName, "INTEGRATOR");
     if (!integ) FAIL("INTEGRATOR %s not found", intName);
     odb_getString(integ, "type", &s, "");
-    if (strcmp(s, "NGLF") != 0) { char t[64]; snprintf(t, 64, "%s", s); free(s); FAIL("INTEGRATOR type %s is not supported (only NGLF)", t); }
+    if (strcmp(s, "NGLF") == 0) d->integratorType = 0;
+    else if (strcmp(s, "NGLFCONSTRAINT") == 0)
+    {
+        /* nglfconstraint_parms (src/nglfconstraint.c:86-95) */
+        d->integratorType = 1;
+        if (odb_getWithUnits(integ, "T", &d->ncT, 1, "310", "T", NULL) < 0 || odb_getWithUnits(integ, "P0", &d->ncP0, 1, "0.0", "pressure", NULL) < 0 ||
+            odb_getWithUnits(integ, "beta", &d->ncBeta, 1, "0.0", "1/pressure", NULL) < 0 ||
+            odb_getWithUnits(integ, "tauBarostat", &d->ncTauBarostat, 1, "0.0", "t", NULL) < 0)
+        { free(s); s = NULL; FAIL("bad unit in INTEGRATOR %s", intName); }
+        odb_getInts(integ, "isotropic", &d->ncIsotropic, 1, "0");
+    }
+    else { char t[64]; snprintf(t, 64, "%s", s); free(s); s = NULL; FAIL("INTEGRATOR type %s is not supported (NGLF, NGLFCONSTRAINT)", t); }
     free(s);
+    s = NULL;
 
     const ODB_OBJECT *sys = odb_find(db, sysName, "SYSTEM");
     if (!sys) FAIL("SYSTEM %s not found", sysName);
     {
+        /* GROUP objects: FREE (src/free.c) and LANGEVIN with a numeric tau = NORMAL Langevin, constant Teq (src/langevin.c:63-91,130-170) */
         char **gn;
         int ng = odb_getStrings(sys, "groups", &gn, NULL);
+        if (ng > 8) { odb_freeStrings(gn, ng); FAIL("more than 8 GROUP objects are not supported"); }
+        d->nGroups = ng > 0 ? ng : 0;
+        d->groupName = (char **)calloc(ng > 0 ? ng : 1, sizeof(char *));
+        d->groupType = (int *)calloc(ng > 0 ? ng : 1, sizeof(int));
+        d->groupTeq = (double *)calloc(ng > 0 ? ng : 1, sizeof(double));
+        d->groupTau = (double *)calloc(ng > 0 ? ng : 1, sizeof(double));
+        d->groupVcm = (double *)calloc(ng > 0 ? 3 * ng : 1, sizeof(double));
+        for (int g = 0; g < ng; g++) d->groupName[g] = strdup(gn[g]);
         for (int g = 0; g < ng; g++)
         {
             const ODB_OBJECT *go = odb_find(db, gn[g], "GROUP");
-            if (!go) { odb_freeStrings(gn, ng); FAIL("GROUP %s not found", gn[g]); }
+            if (!go) { odb_freeStrings(gn, ng); FAIL("GROUP %s not found", d->groupName[g]); }
             odb_getString(go, "type", &s, "");
-            int ok = strcmp(s, "FREE") == 0;
+            int ok = 1;
+            if (strcmp(s, "FREE") == 0) d->groupType[g] = 0;
+            else if (strcmp(s, "LANGEVIN") == 0)
+            {
+                d->groupType[g] = 1;
+                char *tv = NULL, *end = NULL, *dyn = NULL;
+                odb_getString(go, "tau", &tv, "NotDefined");
+                strtod(tv, &end);
+                const int numericTau = end != tv;
+                free(tv);
+                odb_getString(go, "Teq_dynamics", &dyn, "EXPLICIT_TIME");
+                const int explicitTime = strcmp(dyn, "EXPLICIT_TIME") == 0;
+                free(dyn);
+                if (!numericTau || !explicitTime) { free(s); s = NULL; odb_freeStrings(gn, ng); FAIL("LANGEVIN group %s: only the NORMAL thermostat (numeric tau, Teq_dynamics=EXPLICIT_TIME) is supported", d->groupName[g]); }
+                char *tq = NULL;
+                odb_getString(go, "Teq", &tq, NULL);
+                if (!tq) { free(s); s = NULL; odb_freeStrings(gn, ng); FAIL("LANGEVIN group %s needs Teq", d->groupName[g]); }
+                /* Teq is an eq_parse expression of time in the reference; a constant "<number><unit>" is what Martini decks use */
+                strtod(tq, &end);
+                int constant = end != tq;
+                for (const char *q = end; constant && *q; q++)
+                    if (!(isalnum((unsigned char)*q) || *q == '_' || *q == ' ')) constant = 0;
+                free(tq);
+                if (!constant || odb_getWithUnits(go, "Teq", &d->groupTeq[g], 1, "0.0", "T", NULL) < 0)
+                { free(s); s = NULL; odb_freeStrings(gn, ng); FAIL("LANGEVIN group %s: Teq must be a constant temperature", d->groupName[g]); }
+                if (odb_getWithUnits(go, "tau", &d->groupTau[g], 1, "1.0", "t", NULL) < 0 ||
+                    odb_getWithUnits(go, "vcm", &d->groupVcm[3 * g], 3, "0.0 0.0 0.0", "l/t", NULL) < 0)
+                { free(s); s = NULL; odb_freeStrings(gn, ng); FAIL("bad unit in GROUP %s", d->groupName[g]); }
+                if (!(d->groupTau[g] > 0.0)) { free(s); s = NULL; odb_freeStrings(gn, ng); FAIL("LANGEVIN group %s: tau must be positive", d->groupName[g]); }
+            }
+            else ok = 0;
             free(s);
-            if (!ok) { odb_freeStrings(gn, ng); FAIL("GROUP type other than FREE is not supported"); }
+            s = NULL;
+            if (!ok) { odb_freeStrings(gn, ng); FAIL("GROUP %s: type other than FREE or LANGEVIN is not supported", d->groupName[g]); }
         }
         odb_freeStrings(gn, ng);
+    }
+    {
+        /* RANDOM (src/random.c:47-72): only LCG64; randomizeSeed only matters for generators made after start-up, the per-bead
+         * default streams are seeded by the gid (src/collection.c:96-110) */
+        char *rname = NULL;
+        odb_getString(sys, "random", &rname, "NotSet");
+        const ODB_OBJECT *ro = odb_find(db, rname, "RANDOM");
+        if (ro)
+        {
+            char *rt = NULL;
+            odb_getString(ro, "type", &rt, "");
+            const int lcg = strcmp(rt, "LCG64") == 0;
+            free(rt);
+            if (!lcg) { free(rname); FAIL("RANDOM type other than LCG64 is not supported"); }
+            int64_t seed = 0;
+            odb_getI64(ro, "seed", &seed, "0");
+            d->randomSeed = (uint64_t)seed;
+            d->haveRandom = 1;
+        }
+        free(rname);
+        for (int g = 0; g < d->nGroups; g++)
+            if (d->groupType[g] == 1 && !d->haveRandom) FAIL("LANGEVIN group %s needs a RANDOM object in SYSTEM (missingRandomError)", d->groupName[g]);
     }
     odb_getInts(sys, "nConstraints", &d->params.nConstraints, 1, "0");
 
@@ -716,6 +894,14 @@ int ddcb200_deckLoad(const char *objectFile, const char *restartFile, const char
         d->species = (int *)calloc(size, sizeof(int));
         d->rx = (double *)calloc(size, sizeof(double)); d->ry = (double *)calloc(size, sizeof(double)); d->rz = (double *)calloc(size, sizeof(double));
         d->vx = (double *)calloc(size, sizeof(double)); d->vy = (double *)calloc(size, sizeof(double)); d->vz = (double *)calloc(size, sizeof(double));
+        int randomMissing = 0;
+        if (d->nGroups > 0) d->groupOfBead = (unsigned char *)calloc(size, 1);
+        if (d->haveRandom)
+        {
+            d->rngState = (uint64_t *)calloc(size, sizeof(uint64_t));
+            d->rngMult = (uint32_t *)calloc(size, sizeof(uint32_t));
+            d->rngPrime = (uint32_t *)calloc(size, sizeof(uint32_t));
+        }
         sorted = (NameIdx *)calloc(d->nspecies, sizeof(NameIdx));
         for (int i = 0; i < d->nspecies; i++) { sorted[i].name = d->speciesName[i]; sorted[i].index = i; }
         qsort(sorted, d->nspecies, sizeof(NameIdx), cmpName);
@@ -728,12 +914,13 @@ int ddcb200_deckLoad(const char *objectFile, const char *restartFile, const char
             FILE *t = fopen(pp, "rb");
             if (!t) { free(pp); break; }
             fclose(t);
-            int e = readAtoms(pp, size, d, sorted, d->nspecies, &filled);
+            int e = readAtoms(pp, size, d, sorted, d->nspecies, &filled, &randomMissing);
             free(pp);
             if (e) { free(files); rc = -1; goto done; }
         }
         free(files);
         if (filled != size) FAIL("COLLECTION size=%lld but %lld records were read", (long long)size, (long long)filled);
+        if (d->haveRandom && randomMissing) lcg64Defaults(d);
     }
 
     /* flatten bonded terms: walk residues in gid order (charmmResidues, src/bioCharmmCovalent.c:48-93) */
@@ -746,7 +933,7 @@ int ddcb200_deckLoad(const char *objectFile, const char *restartFile, const char
         const int ex = d->excludePotentialTerm;
         for (int pass = 0; pass < 2; pass++)
         {
-            int64_t nt = 0, nm = 0, nmb = 0, nmt = 0;
+            int64_t nt = 0, nm = 0, nmb = 0, nmt = 0, nc = 0, nca = 0, ncp = 0;
             for (int64_t a = 0; a < n;)
             {
                 int64_t b = a;
@@ -813,6 +1000,54 @@ int ddcb200_deckLoad(const char *objectFile, const char *restartFile, const char
                     }
                     nt++;
                 }
+                /* constraint clusters (genConstraint, src/bioMartini.c:445-565): one per CONSLISTPARMS, in the order of
+                 * the lowest atom that carries each list; an atom named by two lists belongs to the later one */
+                if (r->nCons > 0)
+                {
+                    int consIndex[r->nAtoms], done[r->nConsLists];
+                    for (int k = 0; k < r->nAtoms; k++) consIndex[k] = -1;
+                    for (int k = 0; k < r->nConsLists; k++) done[k] = 0;
+                    for (int q = 0; q < r->nCons; q++)
+                    {
+                        CHECKOFF(r->cons[q].atomI); CHECKOFF(r->cons[q].atomJ);
+                        consIndex[r->cons[q].atomI] = r->cons[q].list;
+                        consIndex[r->cons[q].atomJ] = r->cons[q].list;
+                    }
+                    for (int k = 0; k < r->nAtoms; k++)
+                    {
+                        const int cl = consIndex[k];
+                        if (cl < 0 || done[cl]) continue;
+                        done[cl] = 1;
+                        int local[r->nAtoms], na = 0;
+                        for (int a2 = 0; a2 < r->nAtoms; a2++)
+                        {
+                            local[a2] = -1;
+                            if (consIndex[a2] == cl)
+                            {
+                                if (pass) d->consAtomBead[nca + na] = BEAD(a2);
+                                local[a2] = na++;
+                            }
+                        }
+                        int np = 0;
+                        for (int q = 0; q < r->nCons; q++)
+                        {
+                            if (r->cons[q].list != cl) continue;
+                            const int la = local[r->cons[q].atomI], lb = local[r->cons[q].atomJ];
+                            if (la < 0 || lb < 0) FAIL("residue %s: constraint lists overlap (findIndexInConsGroup would abort)", r->resName);
+                            if (pass)
+                            {
+                                d->consPairA[ncp + np] = la;
+                                d->consPairB[ncp + np] = lb;
+                                d->consPairDist[ncp + np] = r->cons[q].r0;
+                            }
+                            np++;
+                        }
+                        if (pass) { d->consAtomOffset[nc] = nca; d->consPairOffset[nc] = ncp; }
+                        nc++;
+                        nca += na;
+                        ncp += np;
+                    }
+                }
                 /* molecule bookkeeping (moleculeScanState, src/molecule.c:118-211): one molecule per (gid>>32) */
                 {
                     const int mt = d->specMolType[sp0];
@@ -844,8 +1079,20 @@ int ddcb200_deckLoad(const char *objectFile, const char *restartFile, const char
                 d->nMolTotal = nmt;
                 d->molOffset = (int64_t *)calloc(nm + 1, sizeof(int64_t));
                 d->molBeads = (int *)calloc(nmb > 0 ? nmb : 1, sizeof(int));
+                d->nCons = nc;
+                d->consAtomOffset = (int64_t *)calloc(nc + 1, sizeof(int64_t));
+                d->consPairOffset = (int64_t *)calloc(nc + 1, sizeof(int64_t));
+                d->consAtomBead = (int *)calloc(nca > 0 ? nca : 1, sizeof(int));
+                d->consPairA = (int *)calloc(ncp > 0 ? ncp : 1, sizeof(int));
+                d->consPairB = (int *)calloc(ncp > 0 ? ncp : 1, sizeof(int));
+                d->consPairDist = (double *)calloc(ncp > 0 ? ncp : 1, sizeof(double));
             }
-            else d->molOffset[nm] = nmb;
+            else
+            {
+                d->molOffset[nm] = nmb;
+                d->consAtomOffset[nc] = nca;
+                d->consPairOffset[nc] = ncp;
+            }
         }
     }
 
@@ -938,6 +1185,18 @@ int ddcb200_simulateBindRank(const ddcb200_deck *d, int device, int rank, int nr
     TRY(ddcb200_martiniBondParms(c, d->nTerms, d->termKind, d->termIdx, d->termParm));
     TRY(ddcb200_setRestraints(c, d->nRestraints, d->restrBead, d->restrFrac0, d->restrKb, d->restrFc, d->restrOrigin));
     TRY(ddcb200_setMolecules(c, d->nMol, d->molOffset, d->molBeads, d->nMolTotal));
+    if (d->nGroups > 0)
+    {
+        double kBT[8];
+        for (int g = 0; g < d->nGroups && g < 8; g++) kBT[g] = d->kB * d->groupTeq[g];   /* langevin_Update: kBT = kB*Teq */
+        TRY(ddcb200_setGroups(c, d->nGroups, d->groupType, kBT, d->groupTau, d->groupVcm, d->n, d->groupOfBead));
+    }
+    if (d->haveRandom && d->rngState) TRY(ddcb200_setRandom(c, d->n, d->rngState, d->rngMult, d->rngPrime));
+    if (d->integratorType == 1)
+    {
+        TRY(ddcb200_setConstraints(c, d->nCons, d->consAtomOffset, d->consAtomBead, d->consPairOffset, d->consPairA, d->consPairB, d->consPairDist));
+        TRY(ddcb200_nglfconstraintParms(c, d->kB * d->ncT, d->ncP0, d->ncBeta, d->ncTauBarostat));
+    }
     int64_t lo = 0, hi = d->n;
     if (nranks > 1)
     {

@@ -54,11 +54,12 @@ k_pair(int nIon, int nPad, const double4 *__restrict__ pos, const uint32_t *__re
     const double kqi = pc.keR * qi;
     const double2 *ljRow = sLJ + ti * pc.ntypes;
     // Rows are ordered by build-time distance bin.  A pair listed at distance r_build can only be inside the
-    // cutoff now if r_build - 2*dmax < rmax, dmax = largest displacement of any bead since the build (measured
-    // by k_integrate): bins that start beyond rmax + 2*dmax are not even loaded.  Exact, not a heuristic.
+    // cutoff now if r_build - 2*dmax - listSlack < rmax, dmax = largest displacement of any bead since the build
+    // (measured by k_integrate / k_nglfc), listSlack = change of the box edges since the build (0 without a
+    // barostat): bins that start beyond that are not even loaded.  Exact, not a heuristic.
     int binLimit = 0;
     {
-        const double lim = (pc.rmax + 2.0 * sqrt(__longlong_as_double((long long)*dmax2))) * (1.0 + 1e-12);
+        const double lim = (pc.rmax + pc.listSlack + 2.0 * sqrt(__longlong_as_double((long long)*dmax2))) * (1.0 + 1e-12);
 #pragma unroll
         for (int e = 0; e < NBINS - 1; e++) binLimit += (pc.binEdge[e] < lim) ? 1 : 0;
     }

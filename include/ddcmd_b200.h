@@ -153,6 +153,42 @@ int ddcb200_nglf(ddcb200_ctx *ctx, int nsteps, double dt);
  * molecularPressure (src/molecularPressure.c:57-67). kB in internal units. */
 int ddcb200_energyInfo(ddcb200_ctx *ctx, double kB, ddcb200_etype *out);
 
+/* ---- NGLFCONSTRAINT integrator ----------------------------------------------
+ * Replaces nglfconstraint_parms + nglfconstraint (src/nglfconstraint.c:86-115, :510-574) and the GPU analogue
+ * nglfconstraintGPU (src/nglfconstraintGPU.cu:1255-1365).  One GPU in this version. */
+
+/* GROUP objects (src/group.c:78-82) and the group of every bead (the "group" column of the atoms file, input order;
+ * NULL = every bead in group 0).  type: 0 FREE (free_velocityUpdate, src/free.c:13-28), 1 LANGEVIN
+ * (langevin_velocityUpdate, src/langevin.c:92-128) with kBT = kB*Teq, tau and vcm[3] per group, internal units. */
+int ddcb200_setGroups(ddcb200_ctx *ctx, int ngroups, const int *type, const double *kBT, const double *tau, const double *vcm,
+                      int64_t nGlobal, const unsigned char *groupOfBead);
+
+/* Per-bead LCG64 streams, input order: LCG64_PARM {state, multID, prime} (src/lcg64.h:8-12), as read from the atoms file
+ * or made by lcg64_default (src/lcg64.c:96-109).  getRandom returns the current states (for restart files). */
+int ddcb200_setRandom(ddcb200_ctx *ctx, int64_t nGlobal, const uint64_t *state, const uint32_t *multID, const uint32_t *prime);
+int ddcb200_getRandom(ddcb200_ctx *ctx, int64_t nGlobal, uint64_t *state);
+
+/* Constraint clusters = the CONSTRAINT objects of genConstraint (src/bioMartini.c:445-565), one per residue instance
+ * and CONSLISTPARMS: atomOffset/pairOffset have nCons+1 entries; atomBead = bead indices (input order) in
+ * atomIDList order; pairA/pairB index into the cluster's own atom list (atomIindex/atomJindex); pairDist = r0.
+ * Clusters must be disjoint; at most 32 atoms and 48 pairs each. */
+int ddcb200_setConstraints(ddcb200_ctx *ctx, int64_t nCons, const int64_t *atomOffset, const int *atomBead, const int64_t *pairOffset,
+                           const int *pairA, const int *pairB, const double *pairDist);
+
+/* INTEGRATOR NGLFCONSTRAINT keys: kBT = kB*T, P0, beta (0 = no barostat), tauBarostat, internal units. */
+int ddcb200_nglfconstraintParms(ddcb200_ctx *ctx, double kBT, double P0, double beta, double tauBarostat);
+
+/* nglfconstraint called nsteps times: [barostat: molecularPressure -> changeVolume -> adjustPosn] -> group FRONT
+ * velocity update -> velocity constraints -> drift + wrap -> ddcenergy -> group BACK update -> velocity constraints ->
+ * kinetic_terms.  The last step is an energy step. */
+int ddcb200_nglfconstraint(ddcb200_ctx *ctx, int nsteps, double dt);
+
+/* Current box matrix (the barostat changes it; box_get_h, src/box.c:173-176). */
+int ddcb200_getBox(ddcb200_ctx *ctx, double h[9]);
+
+/* Constraint clusters that reached the 500-iteration cap so far (the reference prints a warning and goes on). */
+int64_t ddcb200_constraintFailures(ddcb200_ctx *ctx);
+
 /* Parity hooks: cell index of every local bead in the reference's GeomBox numbering
  * (src/geom.c:386-454), the grid {nx,ny,nz}, geom = {min[3], max[3], d[3]} in normalised
  * coordinates; and the half list as (beadI, beadJ, pruned) triples with gid_I < gid_J. */

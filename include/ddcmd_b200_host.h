@@ -4,7 +4,7 @@
  * It reads the same decks ddcMD reads (object.data + restart + martini.data + restraint.data +
  * atoms#NNNNNN, reference src/objectSetup.c:35-41, src/collection_read.c:86-170) and mirrors
  * the reference's init chain: simulate_init -> system_init -> {species, molecule, box,
- * collection, potential(MARTINI|RESTRAINT), neighbor} -> integrator(NGLF) -> ddc
+ * collection, potential(MARTINI|RESTRAINT), neighbor} -> integrator(NGLF|NGLFCONSTRAINT) -> ddc
  * (SURVEY.md section 3.1).  The result is a flat, POD description (ddcb200_deck) that
  * ddcb200_simulateBind() pushes through the C-ABI setters.
  */
@@ -65,6 +65,29 @@ typedef struct ddcb200_deck
     int64_t nMol, nMolTotal;
     int64_t *molOffset;
     int *molBeads;
+    /* INTEGRATOR (src/integrator.c:59-83): 0 = NGLF, 1 = NGLFCONSTRAINT with its keys T, P0, beta, tauBarostat,
+     * isotropic (src/nglfconstraint.c:86-95), internal units */
+    int integratorType;
+    double ncT, ncP0, ncBeta, ncTauBarostat;
+    int ncIsotropic;
+    /* GROUP objects of SYSTEM groups (src/group.c:78-82): 0 = FREE, 1 = LANGEVIN {Teq, tau, vcm} (src/langevin.c:63-91,
+     * 130-170); groupOfBead = index of the group named in each atoms record */
+    int nGroups;
+    char **groupName;
+    int *groupType;
+    double *groupTeq, *groupTau, *groupVcm;
+    unsigned char *groupOfBead;
+    /* RANDOM LCG64 (src/random.c:47-72): per-bead LCG64_PARM read from the atoms records or made by lcg64_default
+     * (src/lcg64.c:96-109; src/collection.c:96-110) */
+    int haveRandom;
+    uint64_t randomSeed;
+    uint64_t *rngState;
+    uint32_t *rngMult, *rngPrime;
+    /* constraint clusters (genConstraint, src/bioMartini.c:445-565), see ddcb200_setConstraints */
+    int64_t nCons;
+    int64_t *consAtomOffset, *consPairOffset;
+    int *consAtomBead, *consPairA, *consPairB;
+    double *consPairDist;
 } ddcb200_deck;
 
 /* object_compilefile(object.data) + object_compilefile(restart) + the init chain.

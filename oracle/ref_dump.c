@@ -42,6 +42,8 @@ void objectSetup(void *parms, MPI_Comm comm);
 #include "box.h"
 #include "ddcenergy.h"
 #include "preduce.h"
+#include "random.h"
+#include "lcg64.h"
 
 void mpiStartUp(int argc, char *argv[]);
 void commons_init(void);
@@ -103,6 +105,30 @@ static void dump_state(const char *prefix, SYSTEM *sys)
     snprintf(nm, sizeof nm, "%sspecies", prefix);
     rec(nm, 'i', sp, n);
     free(sp);
+}
+
+/* per-bead LCG64 state (LANGEVIN groups; src/lcg64.h:8-12), when the SYSTEM has a RANDOM object */
+static void dump_rng(const char *prefix, SYSTEM *sys)
+{
+    RANDOM *random = system_getRandom(sys);
+    if (random == NULL || random->itype != LCG64) return;
+    unsigned n = sys->nlocal;
+    uint64_t *st = malloc(8 * (n + 1));
+    int *mp = malloc(sizeof(int) * 2 * (n + 1));
+    for (unsigned i = 0; i < n; i++)
+    {
+        LCG64_PARM *p = (LCG64_PARM *)random_getParms(random, i);
+        st[i] = p->state;
+        mp[2 * i] = (int)p->multID;
+        mp[2 * i + 1] = (int)p->prime;
+    }
+    char nm[32];
+    snprintf(nm, sizeof nm, "%srng_state", prefix);
+    rec(nm, 'q', st, n);
+    snprintf(nm, sizeof nm, "%srng_mp", prefix);
+    rec(nm, 'i', mp, 2 * (uint64_t)n);
+    free(st);
+    free(mp);
 }
 
 static void dump_neighbor(SYSTEM *sys)
@@ -189,6 +215,7 @@ static void dumpMaster(void *parms, MPI_Comm comm)
         free(buf);
     }
     if (!light) dump_state("s0_", sys);
+    if (!light) dump_rng("s0_", sys);
     dump_energy("s0_", sys);
     if (!light) dump_neighbor(sys);
     rec_i("npairs0", (int)sys->neighbor->npairs);
@@ -197,6 +224,7 @@ static void dumpMaster(void *parms, MPI_Comm comm)
     {
         double *trace = malloc(sizeof(double) * 16 * (size_t)nsteps);
         double *wall = malloc(sizeof(double) * (size_t)nsteps);
+        double *boxtrace = malloc(sizeof(double) * 3 * (size_t)nsteps);   /* barostat: box edges after every step */
         const double t0 = MPI_Wtime();
         for (int s = 0; s < nsteps; s++)
         {
@@ -211,6 +239,10 @@ static void dumpMaster(void *parms, MPI_Comm comm)
             t[11] = e->tion.xx; t[12] = e->tion.yy; t[13] = e->tion.zz;
             t[14] = (double)sys->neighbor->npairs; t[15] = (double)sys->neighbor->lastUpdate;
             wall[s] = MPI_Wtime() - t0;
+            {
+                THREE_MATRIX hs = box_get_h(sys->box);
+                boxtrace[3 * s] = hs.xx; boxtrace[3 * s + 1] = hs.yy; boxtrace[3 * s + 2] = hs.zz;
+            }
             if (dump_every > 0 && (s + 1) % dump_every == 0 && s + 1 < nsteps)
             {
                 char pre[32];
@@ -220,9 +252,12 @@ static void dumpMaster(void *parms, MPI_Comm comm)
         }
         rec("trace", 'd', trace, 16 * (uint64_t)nsteps);
         rec("wall", 'd', wall, (uint64_t)nsteps);
+        rec("boxtrace", 'd', boxtrace, 3 * (uint64_t)nsteps);
+        free(boxtrace);
         free(trace);
         free(wall);
         if (!light) dump_state("sN_", sys);
+        if (!light) dump_rng("sN_", sys);
         dump_energy("sN_", sys);
     }
     fclose(out);

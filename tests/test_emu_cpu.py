@@ -65,6 +65,18 @@ def test_emu_displacement_triggered_rebuild(emu, golden_dir, tmp_path):
     tu.check_ur0(golden_dir, "popc_small", tmp_path, 40)
 
 
+@pytest.mark.parametrize("deck,variant", [("popc_small", "full"), ("ras_small", "full"), ("popc_small", "lang")])
+def test_emu_nglfconstraint(emu, golden_dir, tmp_path, deck, variant):
+    """NGLFCONSTRAINT: Langevin groups (bit-equal LCG64 streams), velocity constraints, barostat box trace (k_nglfc, k_constraint)."""
+    import test_zzzzz_nglfc as tn
+    tn.check_nglfc(golden_dir, deck, variant, tmp_path, 40 if deck == "popc_small" else 22)
+
+
+def test_emu_nglf_with_langevin_groups(emu, golden_dir, tmp_path):
+    import test_zzzzz_nglfc as tn
+    tn.test_nglf_with_langevin_groups_is_the_unconstrained_pass(golden_dir, tmp_path)
+
+
 def _torchrun(nproc, port, script, *args, env=None):
     import subprocess
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))

@@ -146,3 +146,51 @@ def test_product_does_not_reference_the_oracle():
                 # prose may mention the oracle; code may not name it in a string literal, import or include
                 bad = re.findall(r"""["'][^"'\n]*(?:oracle|ref_dump|_ref)[^"'\n]*["']|import\s+oracle|from\s+oracle|#include\s*[<"][^>"]*oracle""", txt)
                 assert not bad, (os.path.join(root, f), bad)
+
+
+def test_nglfconstraint_deck_parsing(golden_dir, tmp_path):
+    """INTEGRATOR NGLFCONSTRAINT keys, LANGEVIN groups, the default per-bead LCG64 streams (lcg64_default + nextPrime) and the
+    constraint clusters of genConstraint, against what the reference's own init produced (tests/golden/nglfc.npz)."""
+    import nglfc_decks
+    g = np.load(os.path.join(golden_dir, "nglfc.npz"))
+    d = nglfc_decks.make_variant(golden_dir, "waterbox", "full", tmp_path)
+    deck = dd.Deck(os.path.join(d, "object.data"))
+    s = deck.s
+    assert int(s.integratorType) == 1 and int(s.nGroups) == 2 and [s.groupType[0], s.groupType[1]] == [1, 1]
+    K, bar, ps = dd.units_convert(1.0, "K", None), dd.units_convert(1.0, "bar", None), dd.units_convert(1.0, "ps", None)
+    assert abs(s.ncT - 310 * K) < 1e-15 * 310 * K and abs(s.ncP0 - bar) < 1e-12 * bar
+    assert abs(s.ncBeta - 3.0e-4 / bar) < 1e-12 * 3.0e-4 / bar and abs(s.ncTauBarostat - ps) < 1e-12 * ps
+    assert abs(s.groupTeq[0] - 310 * K) < 1e-15 * 310 * K and abs(s.groupTau[1] - ps) < 1e-12 * ps
+    assert np.array_equal(deck.array("rngState"), g["waterbox_rng0_state"])
+    assert np.array_equal(deck.array("rngMult"), g["waterbox_rng0_mp"][:, 0].astype(np.uint32))
+    assert np.array_equal(deck.array("rngPrime"), g["waterbox_rng0_mp"][:, 1].astype(np.uint32))
+    assert int(s.nCons) == 0 and set(deck.array("groupOfBead").tolist()) == {0}      # every waterbox record names "group"
+    # ras_small: one CONSLISTPARMS on the protein-like residue -> one cluster
+    d2 = nglfc_decks.make_variant(golden_dir, "ras_small", "full", tmp_path)
+    deck2 = dd.Deck(os.path.join(d2, "object.data"))
+    assert int(deck2.s.nCons) == 1
+    ao, po = deck2.array("consAtomOffset"), deck2.array("consPairOffset")
+    atoms, pa, pb, dist = deck2.array("consAtomBead"), deck2.array("consPairA"), deck2.array("consPairB"), deck2.array("consPairDist")
+    assert ao[1] == 2 * po[1] and len(set(atoms.tolist())) == len(atoms)             # disjoint (i, i+4) pairs
+    assert np.all(np.diff(atoms) > 0) and np.all(dist > 0)
+    assert np.all(pa < ao[1]) and np.all(pb < ao[1]) and np.all(pa != pb)
+    # the cluster's distances are the r0 of the CONSPARMS objects (nm -> internal length)
+    txt = open(os.path.join(d2, "martini.data")).read()
+    r0 = [float(x) for x in re.findall(r"CONSPARMS\{[^}]*r0=([0-9.eE+-]+) nm", txt)]
+    assert np.allclose(dist, np.array(r0) * dd.units_convert(1.0, "nm", None), rtol=1e-14)
+
+
+def test_nglfconstraint_deck_errors(golden_dir, tmp_path):
+    import nglfc_decks
+    d = nglfc_decks.make_variant(golden_dir, "popc_small", "lang", tmp_path)
+    p = os.path.join(d, "object.data")
+    s = open(p).read()
+    open(p, "w").write(s.replace("group GROUP { type = LANGEVIN; Teq=310K;", "group GROUP { type = LANGEVIN; Teq=310K+t*0.1;"))
+    with pytest.raises(dd.DdcError, match="constant temperature"):
+        dd.Deck(p)
+    open(p, "w").write(s.replace("random = lcg64;", ""))
+    with pytest.raises(dd.DdcError, match="RANDOM"):
+        dd.Deck(p)
+    open(p, "w").write(s.replace("type = NGLFCONSTRAINT;", "type = NEXTGEN;"))
+    with pytest.raises(dd.DdcError, match="NEXTGEN"):
+        dd.Deck(p)
