@@ -66,7 +66,11 @@ class DeckStruct(C.Structure):
                 ("haveRandom", C.c_int), ("randomSeed", C.c_uint64), ("rngState", _P(C.c_uint64)), ("rngMult", _P(C.c_uint32)),
                 ("rngPrime", _P(C.c_uint32)),
                 ("nCons", C.c_int64), ("consAtomOffset", _P(C.c_int64)), ("consPairOffset", _P(C.c_int64)),
-                ("consAtomBead", _P(C.c_int)), ("consPairA", _P(C.c_int)), ("consPairB", _P(C.c_int)), ("consPairDist", _P(C.c_double))]
+                ("consAtomBead", _P(C.c_int)), ("consPairA", _P(C.c_int)), ("consPairB", _P(C.c_int)), ("consPairDist", _P(C.c_double)),
+                ("runDir", C.c_char_p), ("simulateName", C.c_char_p), ("boxName", C.c_char_p), ("collectionName", C.c_char_p),
+                ("atomsdir", C.c_char_p), ("nLoopDigits", C.c_int), ("gidFormatHex", C.c_int), ("runId", C.c_uint),
+                ("speciesType", _P(C.c_char_p)), ("printUnit", C.c_char_p * 6), ("printConvert", C.c_double * 6),
+                ("reducedCorner", C.c_double * 3)]
 
 
 class DdcError(RuntimeError):
@@ -155,6 +159,10 @@ def _declare(L):
         "ddcb200_simulateBindRank": (i32, [_P(DeckStruct), i32, i32, i32, i32, i32, i32, C.c_char_p, _P(vp)]),
         "ddcb200_printinfoLine": (i32, [_P(DeckStruct), _P(EType), C.c_char_p, C.c_size_t]),
         "ddcb200_unitsConvert": (dbl, [dbl, C.c_char_p, C.c_char_p]),
+        "ddcb200_printinfoHeader": (i32, [_P(DeckStruct), C.c_char_p, C.c_size_t]),
+        "ddcb200_writeRestart": (i32, [_P(DeckStruct), C.c_char_p, i64, dbl, pd, pd, pd, pd, pd, pd, pd, _P(C.c_uint64), i32, C.c_char_p, C.c_size_t]),
+        "ddcb200_readCMDS": (i32, [C.c_char_p]),
+        "ddcb200_simulateMaster": (i32, [C.c_char_p, C.c_char_p, C.c_char_p, i32]),
     }
     for name, (res, args) in sig.items():
         f = getattr(L, name)
@@ -170,7 +178,8 @@ EXPORTS = ["ddcb200_lastError", "ddcb200_deviceCount", "ddcb200_create", "ddcb20
            "ddcb200_nglf", "ddcb200_energyInfo", "ddcb200_setGroups", "ddcb200_setRandom", "ddcb200_getRandom", "ddcb200_setConstraints",
            "ddcb200_nglfconstraintParms", "ddcb200_nglfconstraint", "ddcb200_getBox", "ddcb200_constraintFailures", "ddcb200_getCells", "ddcb200_getPairs", "ddcb200_profile",
            "ddcb200_profileRead", "ddcb200_timerRecord", "ddcb200_timerElapsed", "ddcb200_kernelLaunches", "ddcb200_lastListBuild", "ddcb200_ncclUniqueId", "ddcb200_ddcInit", "ddcb200_ddcPlan", "ddcb200_deckLoad", "ddcb200_deckFree",
-           "ddcb200_lastHostError", "ddcb200_simulateBind", "ddcb200_simulateBindRank", "ddcb200_printinfoLine", "ddcb200_unitsConvert"]
+           "ddcb200_lastHostError", "ddcb200_simulateBind", "ddcb200_simulateBindRank", "ddcb200_printinfoLine", "ddcb200_unitsConvert",
+           "ddcb200_printinfoHeader", "ddcb200_writeRestart", "ddcb200_readCMDS", "ddcb200_simulateMaster"]
 
 
 def _arr(ptr, n, dtype):
@@ -240,6 +249,29 @@ class Deck:
             return _arr(s.molBeads, int(self.array("molOffset")[-1]), np.int32)
         ptr, cnt, dt = table[name]
         return _arr(ptr, cnt, dt)
+
+    def writeRestart(self, rx=None, ry=None, rz=None, vx=None, vy=None, vz=None, loop=None, time=None, h=None, rng=None, dirname=None,
+                     restart_link=False):
+        """writeRestart (src/io.c:58-113) of a state in this deck's bead order (default: the state the deck was read with).
+        Returns the snapshot directory."""
+        L = lib()
+        a = [np.ascontiguousarray(x if x is not None else self.array(k), np.float64)
+             for k, x in zip(("rx", "ry", "rz", "vx", "vy", "vz"), (rx, ry, rz, vx, vy, vz))]
+        hh = np.ascontiguousarray(h if h is not None else np.array(self.s.params.h[:]), np.float64)
+        r = np.ascontiguousarray(rng, np.uint64) if rng is not None else None
+        pd = _P(C.c_double)
+        out = C.create_string_buffer(1024)
+        rc = L.ddcb200_writeRestart(self._p, os.fsencode(dirname) if dirname else None, int(self.s.loop if loop is None else loop),
+                                    float(self.s.time if time is None else time), hh.ctypes.data_as(pd), *[x.ctypes.data_as(pd) for x in a],
+                                    r.ctypes.data_as(_P(C.c_uint64)) if r is not None else None, int(restart_link), out, 1024)
+        if rc != 0:
+            raise DdcError(L.ddcb200_lastHostError().decode())
+        return os.fsdecode(out.value)
+
+    def printinfoHeader(self):
+        buf = C.create_string_buffer(1024)
+        lib().ddcb200_printinfoHeader(self._p, buf, 1024)
+        return buf.value.decode()
 
     @property
     def species_names(self):
@@ -390,6 +422,16 @@ class Simulate:
         """sys->neighbor->lastUpdate: loop of the last list build."""
         return int(lib().ddcb200_lastListBuild(self.ctx))
 
+    def writeRestart(self, dirname=None, restart_link=True):
+        """checkpointSimulate (src/masters.c:51-56): CreateSnapshotdir + writeRestart of the current device state."""
+        if self.nranks != 1:
+            raise DdcError("writeRestart gathers one rank's beads only; gather getState() of all ranks and use Deck.writeRestart")
+        e = self.energyInfo()
+        st = self.getState()
+        rng = self.getRandom() if int(self.deck.s.haveRandom) else None
+        return self.deck.writeRestart(st["rx"], st["ry"], st["rz"], st["vx"], st["vy"], st["vz"], loop=int(e.loop), time=float(e.time),
+                                      h=self.getBox(), rng=rng, dirname=dirname, restart_link=restart_link)
+
     def printinfo(self, e=None):
         e = e or self.energyInfo()
         buf = C.create_string_buffer(512)
@@ -440,6 +482,20 @@ def ddc_plan(h, lattice, rlist, rx, ry, rz, rank, owner_bead=None):
     if rc != 0:
         raise DdcError(L.ddcb200_lastError().decode())
     return owner, mask
+
+
+def read_cmds(filename):
+    """readCMDS (src/readCmds.c:20-57)."""
+    return int(lib().ddcb200_readCMDS(os.fsencode(filename)))
+
+
+def simulateMaster(object_file, restart_file=None, simulate_name=None, device=0):
+    """simulateMaster (src/masters.c:383-559): the whole run of a deck - data lines, ddcMD_CMDS, restarts - in the deck's directory."""
+    L = lib()
+    rc = L.ddcb200_simulateMaster(os.fsencode(object_file), os.fsencode(restart_file) if restart_file else None,
+                                  simulate_name.encode() if simulate_name else None, int(device))
+    if rc != 0:
+        raise DdcError(L.ddcb200_lastHostError().decode())
 
 
 def simulate_init(object_file, restart_file=None, device=0, simulate_name=None, rank=0, nranks=1, lattice=None, nccl_id=None):

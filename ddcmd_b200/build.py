@@ -11,6 +11,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OBJ = os.path.join(HERE, "_build")
 LIB = os.path.join(HERE, "libddcmd_b200.so")
+EXE = os.path.join(HERE, "ddcMD_b200")
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
@@ -21,7 +22,7 @@ GCC_FLAGS = ["-std=gnu99", "-O2", "-ffp-contract=off", "-fPIC", "-Wall", "-Wno-u
 
 def _sources():
     cu = [os.path.join(CSRC, "api.cu")]
-    c = [os.path.join(CSRC, "host", f) for f in ("units.c", "objdb.c", "deck.c")]
+    c = [os.path.join(CSRC, "host", f) for f in ("units.c", "objdb.c", "deck.c", "snapshot.c")]
     deps = []
     for root, _, files in os.walk(CSRC):
         deps += [os.path.join(root, f) for f in files]
@@ -61,6 +62,11 @@ def build(force=False, verbose=False):
         subprocess.check_call(cmd)
         objs.append(o)
     cmd = [nvcc, "-shared", "-o", LIB] + objs + ["-lcudart", "-lnccl", "-lm"]
+    if verbose:
+        print(" ".join(cmd))
+    subprocess.check_call(cmd)
+    # the stand-alone driver (main of the reference, src/ddcMD.c:66-88, for Martini decks): ddcMD_b200 [-o object.data] [-r restart] [-s simulate]
+    cmd = ["gcc"] + GCC_FLAGS + [os.path.join(CSRC, "host", "main.c"), "-o", EXE, "-L", HERE, "-lddcmd_b200", "-Wl,-rpath,$ORIGIN", "-lm"]
     if verbose:
         print(" ".join(cmd))
     subprocess.check_call(cmd)

@@ -19,10 +19,12 @@
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#include <strings.h>
+#include <time.h>
 
 static char g_hostErr[1024];
 const char *ddcb200_lastHostError(void) { return g_hostErr; }
-static int herr(const char *fmt, ...)
+int herr(const char *fmt, ...)
 {
     va_list ap;
     va_start(ap, fmt);
@@ -263,6 +265,26 @@ static void freeMMFF(H_MMFF *m)
     free(m->resi); free(m->typeID); free(m->typeName);
 }
 
+/* CRC-32 (reflected 0x04c11db7, as checksum_crc32_table src/crc32.c:70-82) */
+uint32_t hcrc32(const unsigned char *data, size_t len)
+{
+    static uint32_t lut[256];
+    static int inited = 0;
+    if (!inited)
+    {
+        for (uint32_t n = 0; n < 256; n++)
+        {
+            uint32_t c = n;
+            for (int k = 0; k < 8; k++) c = (c & 1) ? 0xedb88320u ^ (c >> 1) : c >> 1;
+            lut[n] = c;
+        }
+        inited = 1;
+    }
+    uint32_t crc = 0xffffffffu;
+    while (len--) crc = (crc >> 8) ^ lut[(crc & 0xff) ^ *data++];
+    return crc ^ 0xffffffffu;
+}
+
 /* ---- atoms file (VARRECORDASCII, src/collection_read.c:86-170) ---------------------------------- */
 typedef struct { const char *name; int index; } NameIdx;
 static int cmpName(const void *a, const void *b) { return strcmp(((const NameIdx *)a)->name, ((const NameIdx *)b)->name); }
@@ -278,6 +300,7 @@ static int readAtoms(const char *path, int64_t size, ddcb200_deck *d, NameIdx *s
     size_t got = fread(text, 1, (size_t)sz, f);
     fclose(f);
     text[got] = 0;
+    int crcField = 0, gidBase = 10, lrec = 0;
     char *p = strchr(text, '}');
     if (!p) { free(text); return herr("atoms file %s has no FILEHEADER", path); }
     /* header checks: ASCII variable records with the standard field list */
@@ -296,9 +319,24 @@ static int readAtoms(const char *path, int64_t size, ddcb200_deck *d, NameIdx *s
             char **fn;
             int nf = odb_getStrings(hdb->obj[0], "field_names", &fn, "id class type group rx ry rz vx vy vz");
             const char *want[10] = {"id", "class", "type", "group", "rx", "ry", "rz", "vx", "vy", "vz"};
-            if (nf < 10) bad = 1;
-            for (int i = 0; i < 10 && i < nf; i++) bad |= strcmp(fn[i], want[i]) != 0;
+            /* restart files written by collection_writeBLOCK carry a CRC32 per record as the first field
+             * (src/collection_write.c:104-108; checkRecord skips it, src/check_line.c:70-109) */
+            crcField = nf > 0 && strcmp(fn[0], "checksum") == 0;
+            if (nf < 10 + crcField) bad = 1;
+            for (int i = 0; i < 10 && i + crcField < nf; i++) bad |= strcmp(fn[i + crcField], want[i]) != 0;
             odb_freeStrings(fn, nf);
+            {
+                char *ck = NULL;
+                odb_getString(hdb->obj[0], "checksum", &ck, "NONE");
+                if ((strcmp(ck, "CRC32") == 0) != crcField) bad = 1;
+                free(ck);
+                /* the id is hexadecimal when its field_format ends in 'x' (src/collection_read.c:113-127) */
+                char **ff;
+                int nff = odb_getStrings(hdb->obj[0], "field_format", &ff, NULL);
+                if (nff > 1 && ff[1][0] && ff[1][strlen(ff[1]) - 1] == 'x') gidBase = 16;
+                odb_freeStrings(ff, nff);
+                odb_getInts(hdb->obj[0], "lrec", &lrec, 1, "0");
+            }
             {
                 char *rnd = NULL;
                 odb_getString(hdb->obj[0], "random", &rnd, "NotSet");
@@ -318,7 +356,19 @@ static int readAtoms(const char *path, int64_t size, ddcb200_deck *d, NameIdx *s
         while (*p && isspace((unsigned char)*p)) p++;
         if (!*p) break;
         char *end;
-        uint64_t gid = strtoull(p, &end, 10);
+        if (crcField)
+        {
+            /* 8 hex digits + ' ' ; the CRC covers the rest of the fixed-length record, newline included */
+            unsigned long want = strtoul(p, &end, 16);
+            if (end != p + 8) { free(text); return herr("atoms file %s: bad checksum field in record %lld", path, (long long)i); }
+            if (lrec > 8 && (size_t)(p - text) + (size_t)lrec <= got && hcrc32((const unsigned char *)p + 8, (size_t)lrec - 8) != (uint32_t)want)
+            {
+                free(text);
+                return herr("atoms file %s: CRC32 mismatch in record %lld", path, (long long)i);
+            }
+            p = end;
+        }
+        uint64_t gid = strtoull(p, &end, gidBase);
         if (end == p) { free(text); return herr("atoms file %s: bad record %lld", path, (long long)i); }
         p = end;
         /* class, species ("type") and group names: manual tokens (sscanf would strlen the whole file per record) */
@@ -493,6 +543,11 @@ void ddcb200_deckFree(ddcb200_deck *d)
     free(d->groupName); free(d->groupType); free(d->groupTeq); free(d->groupTau); free(d->groupVcm); free(d->groupOfBead);
     free(d->rngState); free(d->rngMult); free(d->rngPrime);
     free(d->consAtomOffset); free(d->consPairOffset); free(d->consAtomBead); free(d->consPairA); free(d->consPairB); free(d->consPairDist);
+    free(d->runDir); free(d->simulateName); free(d->boxName); free(d->collectionName); free(d->atomsdir);
+    if (d->speciesType)
+        for (int i = 0; i < d->nspecies; i++) free(d->speciesType[i]);
+    free(d->speciesType);
+    for (int i = 0; i < 6; i++) free(d->printUnit[i]);
     free(d);
 }
 
@@ -535,6 +590,28 @@ int ddcb200_deckLoad(const char *objectFile, const char *restartFile, const char
     odb_getString(sim, "ddc", &ddcName, "ddc");
     odb_getString(sim, "printinfo", &piName, "printinfo");
     if (!sysName || !intName) FAIL("SIMULATE needs system and integrator keywords");
+    d->runDir = strdup(dir);
+    d->simulateName = strdup(simulateName ? simulateName : "simulate");
+    {
+        /* snapshotRootDir -> atomsdir (atomsdirParse, src/simulate.c:38-57: first word, trailing '/' dropped), gidFormat,
+         * nLoopDigits, run_id (src/simulate.c:159-183,209) */
+        char *root = NULL, *gf = NULL;
+        odb_getString(sim, "snapshotRootDir", &root, "./");
+        char *sp = root;
+        while (*sp && !isspace((unsigned char)*sp)) sp++;
+        *sp = 0;
+        size_t rl = strlen(root);
+        if (rl > 0 && root[rl - 1] == '/') root[rl - 1] = 0;
+        d->atomsdir = root;
+        odb_getString(sim, "gidFormat", &gf, "decimal");
+        d->gidFormatHex = strcasecmp(gf, "hex") == 0;
+        free(gf);
+        odb_getInts(sim, "nLoopDigits", &d->nLoopDigits, 1, "8");
+        if (d->nLoopDigits < 1 || d->nLoopDigits > 18) FAIL("SIMULATE nLoopDigits out of range");
+        int64_t rid = 0;
+        odb_getI64(sim, "run_id", &rid, "0");
+        d->runId = rid ? (unsigned)rid : (unsigned)time(NULL);
+    }
     odb_getI64(sim, "loop", &d->loop, "0");
     odb_getI64(sim, "maxloop", &d->maxloop, "0");
     odb_getInts(sim, "printrate", &d->printrate, 1, "5");
@@ -651,6 +728,9 @@ int ddcb200_deckLoad(const char *objectFile, const char *restartFile, const char
     if (!boxName || !nbrName || !colName) FAIL("SYSTEM needs box, neighbor and collection");
     const ODB_OBJECT *box = odb_find(db, boxName, "BOX");
     if (!box) FAIL("BOX %s not found", boxName);
+    d->boxName = strdup(boxName);
+    d->collectionName = strdup(colName);
+    odb_getDoubles(box, "reducedcorner", d->reducedCorner, 3, "-0.5 -0.5 -0.5");
     if (odb_getWithUnits(box, "h", d->params.h, 9, "1 0 0 0 1 0 0 0 1", "l", NULL) < 0) FAIL("bad box unit");
     odb_getInts(box, odb_has(box, "bndcdn") ? "bndcdn" : "pbc", &d->params.pbc, 1, "7");
     const ODB_OBJECT *nbr = odb_find(db, nbrName, "NEIGHBOR");
@@ -668,6 +748,18 @@ int ddcb200_deckLoad(const char *objectFile, const char *restartFile, const char
     if (d->params.updateRate < 0) FAIL("DDC updateRate must be >= 0");
     const ODB_OBJECT *pi = odb_find(db, piName, "PRINTINFO");
     if (pi) odb_getInts(pi, "printMolecularPressure", &d->printMolecularPressure, 1, "0");
+    {
+        /* PRINTINFO units (src/printinfo.c:35-36,60-77): value strings and factors from internal units */
+        static const char *key[6] = {"LENGTH", "TIME", "TEMPERATURE", "ENERGY", "PRESSURE", "VOLUME"};
+        static const char *dflt[6] = {"Ang", "fs", "K", "eV", "GPa", "Bohr^3"};
+        for (int k = 0; k < 6; k++)
+        {
+            if (pi) odb_getString(pi, key[k], &d->printUnit[k], dflt[k]);
+            else d->printUnit[k] = strdup(dflt[k]);
+            d->printConvert[k] = hu_convert(1.0, NULL, d->printUnit[k]);
+            if (!(d->printConvert[k] == d->printConvert[k]) || d->printConvert[k] == 0.0) FAIL("PRINTINFO %s = %s is not a unit", key[k], d->printUnit[k]);
+        }
+    }
 
     /* MOLECULECLASS -> MOLECULE -> SPECIES */
     if (strcmp(mcName, "NONE") == 0) FAIL("SYSTEM without moleculeClass is not supported (Martini decks define one)");
@@ -704,9 +796,12 @@ int ddcb200_deckLoad(const char *objectFile, const char *restartFile, const char
                 d->specMolType = (int *)realloc(d->specMolType, spCap * sizeof(int));
                 d->specResidue = (int *)realloc(d->specResidue, spCap * sizeof(int));
                 d->specAtom = (int *)realloc(d->specAtom, spCap * sizeof(int));
+                d->speciesType = (char **)realloc(d->speciesType, spCap * sizeof(char *));
             }
             const int idx = d->nspecies++;
             d->speciesName[idx] = strdup(sn[k]);
+            d->speciesType[idx] = NULL;
+            odb_getString(so, "type", &d->speciesType[idx], "ATOM");
             d->specMolType[idx] = m;
             if (odb_getWithUnits(so, "mass", &d->specMass[idx], 1, "1.0", "m", NULL) < 0) FAIL("bad mass unit in SPECIES %s", sn[k]);
             if (odb_getWithUnits(so, "charge", &d->specCharge[idx], 1, "0.0", "i*t", NULL) < 0) FAIL("bad charge unit in SPECIES %s", sn[k]);
@@ -1226,12 +1321,28 @@ int ddcb200_simulateBind(const ddcb200_deck *d, int device, ddcb200_ctx **out)
 
 int ddcb200_printinfoLine(const ddcb200_deck *d, const ddcb200_etype *e, char *buf, size_t len)
 {
-    /* printinfoA, src/printinfo.c:125-232 with PRINTINFO units ns / kJ/mol / K / bar / Ang^3 / Ang */
+    /* printinfoA, src/printinfo.c:125-232, in the PRINTINFO object's units.  The box edges are deck->params.h: a caller that
+     * runs the barostat refreshes them from ddcb200_getBox before printing (ddcb200_simulateMaster does) */
     const double n = e->number;
-    const double cE = hu_convert(1.0, NULL, "kJ/mol"), cT = hu_convert(1.0, NULL, "K"), cP = hu_convert(1.0, NULL, "bar");
-    const double cV = hu_convert(1.0, NULL, "Ang^3"), cL = hu_convert(1.0, NULL, "Ang"), ct = hu_convert(1.0, NULL, "ns");
+    const double cL = d->printConvert[0], ct = d->printConvert[1], cT = d->printConvert[2], cE = d->printConvert[3], cP = d->printConvert[4],
+                 cV = d->printConvert[5];
     const double pressure = d->printMolecularPressure ? e->pMolecular : e->pion;
-    return snprintf(buf, len, "%012lld %16.6f %18.12f %18.12f %18.12f %18.8f %18.12f %18.12f %15.8f %15.8f %15.8f",
-                    (long long)e->loop, ct * e->time, cE * ((e->eion + e->rk) / n), cE * (e->rk / n), cE * (e->eion / n),
-                    cT * e->temperature, cP * pressure, cV * e->volume / n, cL * d->params.h[0], cL * d->params.h[4], cL * d->params.h[8]);
+    char loopFmt[16];
+    snprintf(loopFmt, sizeof loopFmt, "%%%d.%dllu", d->nLoopDigits, d->nLoopDigits);   /* loopFormatInit, src/format.c:7-11 */
+    int k = snprintf(buf, len, loopFmt, (unsigned long long)e->loop);
+    if (k < 0 || (size_t)k >= len) return k;
+    return k + snprintf(buf + k, len - (size_t)k, " %16.6f %18.12f %18.12f %18.12f %18.8f %18.12f %18.12f %15.8f %15.8f %15.8f",
+                        ct * e->time, cE * ((e->eion + e->rk) / n), cE * (e->rk / n), cE * (e->eion / n),
+                        cT * e->temperature, cP * pressure, cV * e->volume / n, cL * d->params.h[0], cL * d->params.h[4], cL * d->params.h[8]);
+}
+
+int ddcb200_printinfoHeader(const ddcb200_deck *d, char *buf, size_t len)
+{
+    /* src/printinfo.c:153-168: "#loop" left-justified in the loop width, then name(unit) columns */
+    char col[10][96];
+    static const char *name[10] = {"time", "Etotal", "Ekin", "Epot", "Temp", "Press", "Volume", "lx", "ly", "lz"};
+    static const int unit[10] = {1, 3, 3, 3, 2, 4, 5, 0, 0, 0};
+    for (int k = 0; k < 10; k++) snprintf(col[k], sizeof col[k], "%s(%s)", name[k], d->printUnit[unit[k]]);
+    return snprintf(buf, len, "%-*s %16s %18s %18s %18s %18s %18s %18s %15s %15s %15s", d->nLoopDigits, "#loop", col[0], col[1], col[2], col[3],
+                    col[4], col[5], col[6], col[7], col[8], col[9]);
 }

@@ -10,6 +10,10 @@ double hu_kB(void);
 double hu_ke(void);
 double hu_convert(double value, const char *from, const char *to);
 
+/* deck.c */
+uint32_t hcrc32(const unsigned char *data, size_t len);
+int herr(const char *fmt, ...);
+
 /* objdb.c : "name CLASS { key=value; ... }" records (reference src/object.c) */
 typedef struct
 {

@@ -1,0 +1,347 @@
+/* snapshot.c - ddcMD-format output and the simulateMaster loop, host side (plain C).
+ *
+ * Mirrors, for a Martini deck on one rank:
+ *   writeRestart            src/io.c:58-113        <snapshotdir>/atoms#000000 + <snapshotdir>/restart (+ ./restart link)
+ *   CreateSnapshotdir       src/io.c:115-143       "<snapshotRootDir>/snapshot.<loop>"
+ *   collection_writeBLOCK   src/collection_write.c:57-186   FIXRECORDASCII records, CRC32 per record, LCG64 field
+ *   write_fileheader        src/io.c:352-407       the pio FILEHEADER object
+ *   box_write               src/box.c:91-108
+ *   langevin_write_dynamics src/langevin.c:25-30
+ *   readCMDS                src/readCmds.c:20-57
+ *   simulateMaster          src/masters.c:383-559  (findEndLoop :263-281, doCheckpoint :319-326)
+ *
+ * Records written here are byte-identical to the reference's for the same state (tests/test_snapshot_cpu.py compares
+ * with a snapshot written by the unmodified reference); header lines that name the writer (create_time, run_id,
+ * code_version, srcpath) differ by construction.
+ */
+#include "host.h"
+#include "../../../include/ddcmd_b200_host.h"
+#include <errno.h>
+#include <math.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <sys/stat.h>
+#include <time.h>
+#include <unistd.h>
+
+#define MAXLREC 1024   /* src/collection_write.c:27 */
+
+typedef struct { char *p; size_t n, cap; } SBuf;
+static void sbCat(SBuf *b, const char *fmt, ...) __attribute__((format(printf, 2, 3)));
+#include <stdarg.h>
+static void sbCat(SBuf *b, const char *fmt, ...)
+{
+    va_list ap;
+    for (;;)
+    {
+        va_start(ap, fmt);
+        int k = vsnprintf(b->p ? b->p + b->n : NULL, b->p ? b->cap - b->n : 0, fmt, ap);
+        va_end(ap);
+        if (b->p && (size_t)k < b->cap - b->n) { b->n += (size_t)k; return; }
+        b->cap = 2 * (b->cap + (size_t)k) + 64;
+        b->p = (char *)realloc(b->p, b->cap);
+    }
+}
+
+static char *pathJoin(const char *a, const char *b)
+{
+    if (b[0] == '/') return strdup(b);
+    size_t n = strlen(a) + strlen(b) + 2;
+    char *p = (char *)malloc(n);
+    snprintf(p, n, "%s/%s", a, b);
+    return p;
+}
+
+/* matinv of a diagonal box as src/three_algebra.c:37-64 evaluates it (cofactor / determinant): the factors Preduce uses */
+static void diagInverse(const double h[9], double hi[3])
+{
+    const double d00 = h[4] * h[8] - h[5] * h[7], d11 = h[8] * h[0] - h[6] * h[2], d22 = h[0] * h[4] - h[1] * h[3];
+    const double d01 = h[5] * h[6] - h[3] * h[8], d02 = h[3] * h[7] - h[6] * h[4];
+    const double det = h[0] * d00 + h[1] * d01 + h[2] * d02;
+    hi[0] = d00 / det;
+    hi[1] = d11 / det;
+    hi[2] = d22 / det;
+}
+
+int ddcb200_writeRestart(const ddcb200_deck *d, const char *dirname, int64_t loop, double time_, const double h[9],
+                         const double *rx, const double *ry, const double *rz, const double *vx, const double *vy,
+                         const double *vz, const uint64_t *rngState, int restartLink, char *snapshotdirOut, size_t len)
+{
+    if (!d || !h || !rx || !ry || !rz || !vx || !vy || !vz) return herr("writeRestart: null argument");
+    for (int k = 0; k < 9; k++)
+        if ((k % 4) != 0 && fabs(h[k]) > 1e-10) return herr("writeRestart: only orthorhombic boxes are supported");
+    if (d->params.pbc != 7) return herr("writeRestart: only pbc = 7 is supported");
+    if (!rngState) rngState = d->rngState;
+    const int haveRandom = d->haveRandom && rngState && d->rngMult && d->rngPrime;
+
+    /* CreateSnapshotdir: <atomsdir>/snapshot.<loopFormat> or <atomsdir>/<dirname>; relative to the deck's directory */
+    char rel[1024], loopFmt[16];
+    snprintf(loopFmt, sizeof loopFmt, "%%%d.%dllu", d->nLoopDigits, d->nLoopDigits);
+    int k = snprintf(rel, sizeof rel, "%s/", d->atomsdir);
+    if (dirname) snprintf(rel + k, sizeof rel - (size_t)k, "%s", dirname);
+    else
+    {
+        k += snprintf(rel + k, sizeof rel - (size_t)k, "snapshot.");
+        snprintf(rel + k, sizeof rel - (size_t)k, loopFmt, (unsigned long long)loop);
+    }
+    char *dir = pathJoin(d->runDir, rel);
+    if (mkdir(dir, 0777) != 0 && errno != EEXIST) { herr("writeRestart: cannot create %s: %s", dir, strerror(errno)); free(dir); return -1; }
+    if (snapshotdirOut) snprintf(snapshotdirOut, len, "%s", dir);
+
+    /* ---- record format and length (src/collection_write.c:65-99) ---- */
+    char fmt[160];
+    snprintf(fmt, sizeof fmt, "%s %s %s", "%08x ", d->gidFormatHex ? "%16.16lx" : "%12.12lu", " %s %s %s %21.13e %21.13e %21.13e %21.13e %21.13e %21.13e");
+    char line[MAXLREC + 64];
+    int lrec = snprintf(line, MAXLREC, fmt, 0u, 0ul, " ", " ", " ", 0.0, 0.0, 0.0, 0.0, 0.0, 0.0);
+    int maxType = 0, maxName = 0, maxGroup = 0;
+    for (int s = 0; s < d->nspecies; s++)
+    {
+        int a = (int)strlen(d->speciesType[s]), b = (int)strlen(d->speciesName[s]);
+        if (a > maxType) maxType = a;
+        if (b > maxName) maxName = b;
+    }
+    const int nGroups = d->nGroups > 0 ? d->nGroups : 1;
+    for (int g = 0; g < d->nGroups; g++)
+    {
+        int a = (int)strlen(d->groupName[g]);
+        if (a > maxGroup) maxGroup = a;
+    }
+    if (d->nGroups <= 0) maxGroup = 5;   /* "group" */
+    lrec += maxType - 1;
+    lrec += maxName - 1;
+    lrec += maxGroup - 1;
+    const int randomFieldSize = haveRandom ? 27 : 0;   /* strlen(lcg64_write(NULL)) = 16 + 1 + 1 + 1 + 8, src/lcg64.c:56-63 */
+    lrec += randomFieldSize + 1;
+    /* FREE and LANGEVIN groups have no per-particle write (GROUPMAXWRITELENGTH = 0) */
+    lrec++;
+    lrec = 8 * ((lrec + 7) / 8);
+    if (lrec > MAXLREC) { herr("writeRestart: record length %d exceeds MAXLREC=%d", lrec, MAXLREC); free(dir); return -1; }
+
+    const double cLen = hu_convert(1.0, NULL, "l"), cTime = hu_convert(1.0, NULL, "t"), cVel = cLen / cTime;
+
+    /* ---- FILEHEADER (write_fileheader, src/io.c:352-407) ---- */
+    SBuf hb = {0};
+    {
+        time_t now = time(NULL);
+        char stamp[64];
+        snprintf(stamp, sizeof stamp, "%s", ctime(&now));
+        stamp[strcspn(stamp, "\n")] = 0;
+        sbCat(&hb, "particle FILEHEADER {type=MULTILINE; datatype=FIXRECORDASCII; checksum=CRC32; create_time=%s; run_id=0x%08x;\n", stamp, d->runId);
+        sbCat(&hb, "code_version=ddcmd_b200 (B200-native Martini step); srcpath=ddcmd_b200;\n");
+        sbCat(&hb, "loop=%lld; time=%f fs;\n", (long long)loop, time_ * cTime);
+        sbCat(&hb, "nfiles=1; nrecord=%llu; lrec=%d; nfields=11; endian_key=%d;\n", (unsigned long long)d->n, lrec, 875770417);
+        sbCat(&hb, "field_names=checksum id class type group rx ry rz vx vy vz;\n");
+        sbCat(&hb, "field_types=u u s s s f f f f f f;\n");
+        sbCat(&hb, "field_units=1 1 1 1 1 Ang Ang Ang Ang/fs Ang/fs Ang/fs;\n");
+        sbCat(&hb, "field_format=%s;\n", fmt);
+        sbCat(&hb, "reducedcorner=%21.14f %21.14f %21.14f;\n", d->reducedCorner[0], d->reducedCorner[1], d->reducedCorner[2]);
+        sbCat(&hb, "h=%21.14f %21.14f %21.14f\n", h[0] * cLen, h[1] * cLen, h[2] * cLen);
+        sbCat(&hb, "  %21.14f %21.14f %21.14f\n", h[3] * cLen, h[4] * cLen, h[5] * cLen);
+        sbCat(&hb, "  %21.14f %21.14f %21.14f Ang;\n", h[6] * cLen, h[7] * cLen, h[8] * cLen);
+        /* misc_info: every PioSet appends its string and one blank (src/pio.c:209-216) */
+        sbCat(&hb, "random = %s ;\nrandomFieldSize = %d ;\ngroups = ", haveRandom ? "lcg64" : "NONE", randomFieldSize);
+        if (d->nGroups > 0) for (int g = 0; g < d->nGroups; g++) sbCat(&hb, "%s ", d->groupName[g]);
+        else sbCat(&hb, "group ");
+        sbCat(&hb, ";\nspecies = ");
+        for (int s = 0; s < d->nspecies; s++) sbCat(&hb, "%s ", d->speciesName[s]);
+        sbCat(&hb, ";\ntypes = ");
+        for (int s = 0; s < d->nspecies; s++)
+        {
+            int seen = 0;
+            for (int t = 0; t < s && !seen; t++) seen = strcmp(d->speciesType[t], d->speciesType[s]) == 0;
+            if (!seen) sbCat(&hb, "%s ", d->speciesType[s]);
+        }
+        sbCat(&hb, "; \n}\n \n\n");
+    }
+    (void)nGroups;
+
+    char *apath = pathJoin(dir, "atoms#000000");
+    FILE *f = fopen(apath, "wb");
+    if (!f) { herr("writeRestart: cannot open %s: %s", apath, strerror(errno)); free(apath); free(dir); free(hb.p); return -1; }
+    fwrite(hb.p, 1, hb.n, f);
+    free(hb.p);
+
+    /* ---- records (src/collection_write.c:150-184) ---- */
+    double hi[3];
+    diagInverse(h, hi);
+    int rc = 0;
+    for (int64_t i = 0; i < d->n && rc == 0; i++)
+    {
+        /* backInBox = Preduce, pbc 7 (src/preduce.c:282-340): r += h * (-rint(hinv r)) */
+        double x = rx[i], y = ry[i], z = rz[i];
+        x += h[0] * -rint(hi[0] * x);
+        y += h[4] * -rint(hi[1] * y);
+        z += h[8] * -rint(hi[2] * z);
+        const int s = d->species[i];
+        const char *gname = (d->nGroups > 0 && d->groupOfBead) ? d->groupName[d->groupOfBead[i]] : (d->nGroups > 0 ? d->groupName[0] : "group");
+        int length = snprintf(line, MAXLREC, fmt, 0u, (unsigned long)d->gid[i], d->speciesType[s], d->speciesName[s], gname,
+                              x * cLen, y * cLen, z * cLen, vx[i] * cVel, vy[i] * cVel, vz[i] * cVel);
+        if (haveRandom)
+            length += snprintf(line + length, (size_t)(MAXLREC - length), " %16.16llx %1u %8.8x", (unsigned long long)rngState[i], d->rngMult[i], d->rngPrime[i]);
+        if (length > lrec - 1) { rc = herr("writeRestart: record of gid %llu is longer than lrec=%d", (unsigned long long)d->gid[i], lrec); break; }
+        for (int l = length; l < lrec; l++) line[l] = ' ';
+        line[lrec - 1] = '\n';
+        char ck[16];
+        snprintf(ck, sizeof ck, "%08x", hcrc32((const unsigned char *)line + 8, (size_t)lrec - 8));
+        memcpy(line, ck, 8);
+        if (fwrite(line, 1, (size_t)lrec, f) != (size_t)lrec) rc = herr("writeRestart: short write to %s", apath);
+    }
+    if (fclose(f) != 0 && rc == 0) rc = herr("writeRestart: closing %s failed", apath);
+    free(apath);
+    if (rc) { free(dir); return rc; }
+
+    /* ---- restart (src/io.c:75-104) ---- */
+    char *rpath = pathJoin(dir, "restart");
+    f = fopen(rpath, "w");
+    if (!f) { herr("writeRestart: cannot open %s: %s", rpath, strerror(errno)); free(rpath); free(dir); return -1; }
+    fprintf(f, "%s SIMULATE { run_id=0x%08x; loop=%lld; time=%f fs;}\n", d->simulateName, d->runId, (long long)loop, time_ * cTime);
+    fprintf(f, "%s BOX {\n h  = ", d->boxName);
+    fprintf(f, "%21.14e %21.14e %21.14e\n      %21.14e %21.14e %21.14e\n      %21.14e %21.14e %21.14e;\n", h[0] * cLen, h[1] * cLen, h[2] * cLen,
+            h[3] * cLen, h[4] * cLen, h[5] * cLen, h[6] * cLen, h[7] * cLen, h[8] * cLen);
+    fprintf(f, "}\n");
+    /* NGLF / NGLFCONSTRAINT write nothing (writeNULL, src/integrator.c:48); LANGEVIN groups with an explicit Teq write it */
+    for (int g = 0; g < d->nGroups; g++)
+        if (d->groupType[g] == 1) fprintf(f, "%s GROUP { Teq=%f ;}\n", d->groupName[g], hu_convert(d->groupTeq[g], NULL, "T"));
+    fprintf(f, "%s COLLECTION { size=%llu; files=%s/atoms#;}\n", d->collectionName, (unsigned long long)d->n, rel);
+    fclose(f);
+    if (restartLink)
+    {
+        /* unlink("restart"); symlink(<snapshotdir>/restart, "restart") in the run directory */
+        char *lpath = pathJoin(d->runDir, "restart");
+        char target[1100];
+        snprintf(target, sizeof target, "%s/restart", rel);
+        unlink(lpath);
+        if (symlink(target, lpath) != 0) { herr("writeRestart: cannot link %s: %s", lpath, strerror(errno)); rc = -1; }
+        free(lpath);
+    }
+    free(rpath);
+    free(dir);
+    return rc;
+}
+
+int ddcb200_readCMDS(const char *filename)
+{
+    int flag = 0;
+    FILE *file = fopen(filename, "r");
+    if (!file) return 0;
+    char line[256];
+    line[0] = 0;
+    if (fgets(line, 255, file))
+    {
+        if (strchr(line, '{')) flag |= DDCB200_CMD_NEW_OBJECT;   /* object text: reported, not applied (object_rescan is out of scope) */
+        do
+        {
+            line[strcspn(line, "\n")] = 0;
+            printf("Received command \"%s\" from ddcMD_CMDS\n", line);
+            if (strcmp(line, "checkpoint") == 0) flag |= DDCB200_CMD_CHECKPOINT;
+            if (strcmp(line, "kill") == 0) flag |= DDCB200_CMD_STOP;
+            if (strcmp(line, "exit") == 0) flag |= DDCB200_CMD_STOP | DDCB200_CMD_CHECKPOINT;
+            if (strcmp(line, "profile") == 0) flag |= DDCB200_CMD_DUMP_PROFILE;
+            if (strcmp(line, "hpm") == 0) flag |= DDCB200_CMD_HPM_PRINT;
+            if (strcmp(line, "analysis") == 0) flag |= DDCB200_CMD_DO_ANALYSIS;
+        } while (fgets(line, 255, file));
+    }
+    fclose(file);
+    if (truncate(filename, 0) != 0) { /* the reference ignores this too */ }
+    return flag;
+}
+
+#define TEST0(A, B) ((B) != 0 && ((A) % (B)) == 0)   /* src/object.h:17 */
+
+static int64_t findEndLoop(const ddcb200_deck *d, int64_t loop, int64_t maxloop)
+{
+    /* the next loop at which something is printed or written (src/masters.c:263-281) */
+    for (int64_t l = loop + 1; l < maxloop; l++)
+        if (TEST0(l, d->printrate) || TEST0(l, d->snapshotrate) || TEST0(l, d->checkpointrate)) return l;
+    return maxloop;
+}
+
+typedef struct { double *r[6]; uint64_t *rng; } HostState;
+
+static int checkpoint(ddcb200_deck *d, ddcb200_ctx *c, HostState *hs, const ddcb200_etype *e)
+{
+    double h[9];
+    if (ddcb200_getState(c, hs->r[0], hs->r[1], hs->r[2], hs->r[3], hs->r[4], hs->r[5], NULL, NULL, NULL)) return herr("getState: %s", ddcb200_lastError());
+    if (ddcb200_getBox(c, h)) return herr("getBox: %s", ddcb200_lastError());
+    if (d->haveRandom && ddcb200_getRandom(c, d->n, hs->rng)) return herr("getRandom: %s", ddcb200_lastError());
+    char where[1024];
+    int rc = ddcb200_writeRestart(d, NULL, e->loop, e->time, h, hs->r[0], hs->r[1], hs->r[2], hs->r[3], hs->r[4], hs->r[5],
+                                  d->haveRandom ? hs->rng : NULL, 1, where, sizeof where);
+    if (rc == 0) printf("Wrote restart %s\n", where);
+    return rc;
+}
+
+int ddcb200_simulateMaster(const char *objectFile, const char *restartFile, const char *simulateName, int device)
+{
+    ddcb200_deck *d = NULL;
+    ddcb200_ctx *c = NULL;
+    HostState hs;
+    memset(&hs, 0, sizeof hs);
+    FILE *data = NULL;
+    int rc = ddcb200_deckLoad(objectFile, restartFile, simulateName, &d);
+    if (rc) return rc;
+    rc = ddcb200_simulateBind(d, device, &c);
+    if (rc) { ddcb200_deckFree(d); return rc; }
+#define CK(call, what) do { if ((call) != 0) { rc = herr(what ": %s", ddcb200_lastError()); goto done; } } while (0)
+    for (int k = 0; k < 6; k++) hs.r[k] = (double *)malloc(sizeof(double) * (size_t)(d->n + 1));
+    hs.rng = (uint64_t *)malloc(sizeof(uint64_t) * (size_t)(d->n + 1));
+    int64_t loop = d->loop, maxloop = d->maxloop;
+    if (d->deltaloop > -1 && loop + d->deltaloop < maxloop) maxloop = loop + d->deltaloop;   /* src/simulate.c:242 */
+    {
+        char *dpath = pathJoin(d->runDir, "data");
+        data = fopen(dpath, "a");
+        if (!data) { rc = herr("cannot open %s", dpath); free(dpath); goto done; }
+        free(dpath);
+    }
+    char *cmds = pathJoin(d->runDir, "ddcMD_CMDS");
+    char buf[1024];
+    ddcb200_etype e;
+    /* firstEnergyCall (src/masters.c:579-620) + the first printinfoAll with the header */
+    CK(ddcb200_ddcenergy(c, 1), "ddcenergy");
+    CK(ddcb200_energyInfo(c, d->kB, &e), "energyInfo");
+    ddcb200_printinfoHeader(d, buf, sizeof buf);
+    printf("%s\n", buf);
+    fprintf(data, "%s\n", buf);
+#define PRINTLINE() do { ddcb200_getBox(c, d->params.h); ddcb200_printinfoLine(d, &e, buf, sizeof buf); printf("%s\n", buf); \
+                         fprintf(data, "%s\n", buf); fflush(stdout); fflush(data); } while (0)
+    PRINTLINE();
+    while (loop < maxloop)
+    {
+        const int64_t endLoop = findEndLoop(d, loop, maxloop);
+        const int n = (int)(endLoop - loop);
+        if (d->integratorType == 1) CK(ddcb200_nglfconstraint(c, n, d->dt), "nglfconstraint");
+        else CK(ddcb200_nglf(c, n, d->dt), "nglf");
+        loop = endLoop;
+        CK(ddcb200_energyInfo(c, d->kB, &e), "energyInfo");
+        int flag = 0;
+        if (!isfinite(e.eion))
+        {
+            /* src/masters.c:467-472 */
+            flag = DDCB200_CMD_STOP;
+            printf("eion = %e is bad. Simulation is being killed at loop = %lld\n", e.eion, (long long)loop);
+            PRINTLINE();
+            rc = herr("eion is not finite at loop %lld", (long long)loop);
+            break;
+        }
+        if (TEST0(loop, d->printrate))
+        {
+            PRINTLINE();
+            flag = ddcb200_readCMDS(cmds);
+        }
+        if (TEST0(loop, d->checkpointrate) || (flag & DDCB200_CMD_CHECKPOINT))
+            if ((rc = checkpoint(d, c, &hs, &e)) != 0) break;
+        if (flag & DDCB200_CMD_STOP) break;
+    }
+    if (rc == 0 && !TEST0(loop, d->printrate)) PRINTLINE();
+    free(cmds);
+done:
+    if (data) fclose(data);
+    for (int k = 0; k < 6; k++) free(hs.r[k]);
+    free(hs.rng);
+    ddcb200_destroy(c);
+    ddcb200_deckFree(d);
+    return rc;
+#undef CK
+#undef PRINTLINE
+}

@@ -88,6 +88,17 @@ typedef struct ddcb200_deck
     int64_t *consAtomOffset, *consPairOffset;
     int *consAtomBead, *consPairA, *consPairB;
     double *consPairDist;
+    /* what the writers need (writeRestart src/io.c:58-113, printinfoA src/printinfo.c:125-232): object names, the
+     * directory the deck lives in (the reference's cwd), SIMULATE snapshotRootDir / gidFormat / nLoopDigits / run_id
+     * (src/simulate.c:159-183,209), the SPECIES type strings, and the PRINTINFO units (src/printinfo.c:35-36,60-77)
+     * in the order LENGTH TIME TEMPERATURE ENERGY PRESSURE VOLUME with their factors from internal units */
+    char *runDir, *simulateName, *boxName, *collectionName, *atomsdir;
+    int nLoopDigits, gidFormatHex;
+    unsigned runId;
+    char **speciesType;
+    char *printUnit[6];
+    double printConvert[6];
+    double reducedCorner[3];
 } ddcb200_deck;
 
 /* object_compilefile(object.data) + object_compilefile(restart) + the init chain.
@@ -110,6 +121,37 @@ int ddcb200_simulateBindRank(const ddcb200_deck *deck, int device, int rank, int
  * Etotal, Ekin, Epot (kJ/mol per bead), T (K), P (bar; molecular if printMolecularPressure),
  * volume per bead (Ang^3), lx ly lz (Ang).  Returns the number of characters written. */
 int ddcb200_printinfoLine(const ddcb200_deck *deck, const ddcb200_etype *e, char *buf, size_t len);
+
+/* The header line printinfoA writes once at the top of `data` (src/printinfo.c:153-185). */
+int ddcb200_printinfoHeader(const ddcb200_deck *deck, char *buf, size_t len);
+
+/* One ddcMD-format snapshot: writeRestart (src/io.c:58-113) = CreateSnapshotdir (src/io.c:115-143) +
+ * collection_writeBLOCK (src/collection_write.c:57-186: FIXRECORDASCII records with a CRC32 per record, pio FILEHEADER
+ * of write_fileheader src/io.c:352-407) into <snapshotdir>/atoms#000000 + the `restart` object file (SIMULATE loop/time,
+ * BOX h, LANGEVIN groups' Teq, COLLECTION size/files), and the ./restart link when restartLink != 0.
+ * dirname NULL = "snapshot.<loop>" under SIMULATE snapshotRootDir; paths are relative to the deck's directory.
+ * State arrays are in the deck's bead order, internal units; rngState NULL = the deck's LCG64 states.
+ * snapshotdirOut (may be NULL) receives the directory written.  Returns 0, or <0 with ddcb200_lastHostError(). */
+int ddcb200_writeRestart(const ddcb200_deck *deck, const char *dirname, int64_t loop, double time, const double h[9],
+                         const double *rx, const double *ry, const double *rz, const double *vx, const double *vy,
+                         const double *vz, const uint64_t *rngState, int restartLink, char *snapshotdirOut, size_t len);
+
+/* readCMDS (src/readCmds.c:20-57): commands left in <runDir>/ddcMD_CMDS ("checkpoint", "kill", "exit", "profile", "hpm",
+ * "analysis"), one per line; the file is truncated after reading.  Returns the OR of the DDCB200_CMD_* flags. */
+#define DDCB200_CMD_CHECKPOINT 1
+#define DDCB200_CMD_STOP 2
+#define DDCB200_CMD_DUMP_PROFILE 4
+#define DDCB200_CMD_HPM_PRINT 8
+#define DDCB200_CMD_DO_ANALYSIS 16
+#define DDCB200_CMD_NEW_OBJECT 32
+int ddcb200_readCMDS(const char *filename);
+
+/* simulateMaster (src/masters.c:383-559) for a Martini deck on one GPU: simulate_init, firstEnergyCall, then the MD loop
+ * with the reference's cadence - eval_integrator up to the next printrate / snapshotrate / checkpointrate loop
+ * (findEndLoop, src/masters.c:263-281), a `data` line (and stdout line) every printrate loops, ddcMD_CMDS polled on print
+ * loops, writeRestart every checkpointrate loops or on a "checkpoint"/"exit" command, a final data line when maxloop is
+ * not a print loop.  Files are written into the deck's directory.  Returns 0, or <0 with ddcb200_lastHostError(). */
+int ddcb200_simulateMaster(const char *objectFile, const char *restartFile, const char *simulateName, int device);
 
 /* unit conversion exposed for tests: units_convert(value, from, to), NULL = internal. */
 double ddcb200_unitsConvert(double value, const char *from, const char *to);

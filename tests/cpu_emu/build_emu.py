@@ -25,7 +25,7 @@ def build(force=False, verbose=False):
         return LIB
     os.makedirs(OBJ, exist_ok=True)
     objs = []
-    for f in ("units.c", "objdb.c", "deck.c"):
+    for f in ("units.c", "objdb.c", "deck.c", "snapshot.c"):
         o = os.path.join(OBJ, f + ".o")
         subprocess.check_call(["gcc", "-std=gnu99", "-O2", "-ffp-contract=off", "-fPIC", "-w", "-c", os.path.join(CSRC, "host", f), "-o", o])
         objs.append(o)

@@ -1,0 +1,99 @@
+"""Snapshot / restart / data-file goldens from the UNMODIFIED reference (oracle/_ref/ddcMD_ref).
+
+  loop0:  `ddcMD_ref readWrite` (readWriteMaster, src/masters.c:100-124) on a golden deck: the reference reads the deck and
+          writes snapshot.000000000000/{atoms#000000,restart} without stepping -> header text, sha256 of the record block,
+          the first records and the restart text.  The writer must reproduce the record block byte for byte.
+  run:    `ddcMD_ref` (simulateMaster) for 10 steps with printrate=5 and checkpointrate=10 -> the `data` file, the restart
+          text and the parsed records of snapshot.000000000010 (popc_small only) for the simulateMaster test.
+
+Run in the build container after make_golden.py:  python tests/golden/make_snapshot_golden.py
+Writes tests/golden/snapshot.json and tests/golden/snapshot_run.npz.
+"""
+import hashlib
+import json
+import os
+import re
+import shutil
+import subprocess
+import sys
+import tempfile
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+import nglfc_decks  # noqa: E402
+
+REF = os.path.join(ROOT, "oracle", "_ref", "ddcMD_ref")
+CASES = [("waterbox", None), ("popc_small", None), ("popc_small", "full"), ("ras_small", "full")]
+
+
+def stage(deck, variant, tmp):
+    if variant:
+        return nglfc_decks.make_variant(HERE, deck, variant, tmp)
+    dst = os.path.join(tmp, deck)
+    shutil.copytree(os.path.join(HERE, deck), dst, symlinks=True)
+    return dst
+
+
+def split_atoms(path):
+    raw = open(path, "rb").read()
+    k = raw.index(b"}")
+    return raw[:k].decode(), raw[k:]
+
+
+def run_deck_edit(d):
+    p = os.path.join(d, "object.data")
+    s = open(p).read()
+    s = re.sub(r"deltaloop=\d+;", "deltaloop=10;", s)
+    s = re.sub(r"printrate=\d+;", "printrate=5;", s)
+    s = re.sub(r"checkpointrate=\d+;", "checkpointrate=10;", s)
+    open(p, "w").write(s)
+
+
+def parse_records(body, lrec):
+    recs = body[body.index(b"\n\n") + 2:] if not body.startswith(b"}") else body[body.index(b"\n\n", 1) + 2:]
+    n = len(recs) // lrec
+    out = np.zeros((n, 6))
+    gid = np.zeros(n, np.uint64)
+    for i in range(n):
+        f = recs[i * lrec:(i + 1) * lrec].split()
+        gid[i] = int(f[1], 16)
+        out[i] = [float(x) for x in f[5:11]]
+    return gid, out
+
+
+if __name__ == "__main__":
+    gold = {}
+    runz = {}
+    for deck, variant in CASES:
+        key = deck + ("_" + variant if variant else "")
+        tmp = tempfile.mkdtemp(prefix="snap_")
+        d = stage(deck, variant, tmp)
+        subprocess.check_call([REF, "readWrite"], cwd=d, stdout=open(os.path.join(d, "_rw.log"), "w"), stderr=subprocess.STDOUT)
+        snap = [x for x in os.listdir(d) if x.startswith("snapshot.0")][0]
+        header, body = split_atoms(os.path.join(d, snap, "atoms#000000"))
+        lrec = int(re.search(r"lrec=(\d+)", header).group(1))
+        first = body.index(b"\n\n") + 2
+        gold[key] = {"loop0": {"snapshot": snap, "header": header, "lrec": lrec, "body_bytes": len(body), "body_sha256": hashlib.sha256(body).hexdigest(),
+                               "first_records": body[first:first + 2 * lrec].decode(), "restart": open(os.path.join(d, snap, "restart")).read()}}
+        shutil.rmtree(tmp)
+
+        tmp = tempfile.mkdtemp(prefix="snap_")
+        d = stage(deck, variant, tmp)
+        run_deck_edit(d)
+        subprocess.check_call([REF], cwd=d, stdout=open(os.path.join(d, "_run.log"), "w"), stderr=subprocess.STDOUT)
+        snap = "snapshot.000000000010"
+        header, body = split_atoms(os.path.join(d, snap, "atoms#000000"))
+        lrec = int(re.search(r"lrec=(\d+)", header).group(1))
+        gold[key]["run"] = {"data": open(os.path.join(d, "data")).read(), "restart": open(os.path.join(d, snap, "restart")).read(), "lrec": lrec,
+                            "restart_link": os.readlink(os.path.join(d, "restart"))}
+        if deck == "popc_small":
+            gid, rv = parse_records(body, lrec)
+            runz[key + "_gid"] = gid
+            runz[key + "_rv"] = rv
+        shutil.rmtree(tmp)
+        print(key, "lrec", lrec, gold[key]["loop0"]["body_bytes"], "bytes")
+    json.dump(gold, open(os.path.join(HERE, "snapshot.json"), "w"), indent=1)
+    np.savez_compressed(os.path.join(HERE, "snapshot_run.npz"), **runz)

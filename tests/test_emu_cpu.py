@@ -77,6 +77,13 @@ def test_emu_nglf_with_langevin_groups(emu, golden_dir, tmp_path):
     tn.test_nglf_with_langevin_groups_is_the_unconstrained_pass(golden_dir, tmp_path)
 
 
+@pytest.mark.parametrize("deck,variant", [("popc_small", None), ("popc_small", "full")])
+def test_emu_simulateMaster(emu, golden_dir, tmp_path, deck, variant):
+    """ddcb200_simulateMaster: data file, checkpoint cadence, ddcMD_CMDS and restart continuation against the reference's run."""
+    import test_zzzzzz_master as tm
+    tm.check_master(golden_dir, deck, variant, tmp_path)
+
+
 def _torchrun(nproc, port, script, *args, env=None):
     import subprocess
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))

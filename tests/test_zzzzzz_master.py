@@ -1,0 +1,109 @@
+"""simulateMaster through the C-ABI: the whole run of a deck - firstEnergyCall, the MD loop with
+the reference's print / checkpoint cadence, the `data` file, ddcMD_CMDS control and ddcMD-format restarts - against what the
+UNMODIFIED reference wrote for the same deck (tests/golden/snapshot.json, snapshot_run.npz; made by
+tests/golden/make_snapshot_golden.py).  Collected after the step parity tests."""
+import json
+import os
+import re
+import shutil
+
+import numpy as np
+import pytest
+
+import ddcmd_b200 as dd
+import nglfc_decks
+
+pytestmark = pytest.mark.gpu
+
+
+def stage_run(golden_dir, deck, variant, tmp_path, deltaloop=10):
+    if variant:
+        d = nglfc_decks.make_variant(golden_dir, deck, variant, tmp_path)
+    else:
+        d = os.path.join(str(tmp_path), deck)
+        shutil.copytree(os.path.join(golden_dir, deck), d, symlinks=True)
+    p = os.path.join(d, "object.data")
+    s = open(p).read()
+    s = re.sub(r"deltaloop=\d+;", "deltaloop=%d;" % deltaloop, s)
+    s = re.sub(r"printrate=\d+;", "printrate=5;", s)
+    s = re.sub(r"checkpointrate=\d+;", "checkpointrate=10;", s)
+    open(p, "w").write(s)
+    return d
+
+
+def read_snapshot(snap):
+    raw = open(os.path.join(snap, "atoms#000000"), "rb").read()
+    header = raw[:raw.index(b"}")].decode()
+    lrec = int(re.search(r"lrec=(\d+)", header).group(1))
+    recs = raw[raw.index(b"\n\n", raw.index(b"}")) + 2:]
+    n = len(recs) // lrec
+    gid = np.array([int(recs[i * lrec:(i + 1) * lrec].split()[1], 16) for i in range(n)], np.uint64)
+    rv = np.array([[float(x) for x in recs[i * lrec:(i + 1) * lrec].split()[5:11]] for i in range(n)])
+    return header, gid, rv
+
+
+def check_master(golden_dir, deck, variant, tmp_path):
+    key = deck + ("_" + variant if variant else "")
+    g = json.load(open(os.path.join(golden_dir, "snapshot.json")))[key]["run"]
+    d = stage_run(golden_dir, deck, variant, tmp_path)
+    dd.simulateMaster(os.path.join(d, "object.data"))
+    # ---- the data file: same header, same loops, numbers to the step-parity tolerances
+    ours, ref = open(os.path.join(d, "data")).read().splitlines(), g["data"].splitlines()
+    assert ours[0] == ref[0]
+    assert len(ours) == len(ref) == 4
+    cons = variant is not None and deck == "ras_small"
+    for a, b in zip(ours[1:], ref[1:]):
+        fa, fb = a.split(), b.split()
+        assert fa[0] == fb[0] and len(fa) == len(fb) == 11
+        va, vb = np.array(fa[1:], float), np.array(fb[1:], float)
+        etol = 1e-7 if cons else 1e-9
+        scale = max(abs(vb[1]), abs(vb[2]))
+        assert abs(va[0] - vb[0]) < 1e-9                       # time
+        assert np.all(np.abs(va[1:4] - vb[1:4]) <= etol * scale + 2e-12)     # Etotal, Ekin, Epot (12 decimals printed)
+        assert abs(va[4] - vb[4]) <= etol * abs(vb[4]) + 2e-8   # temperature
+        assert abs(va[5] - vb[5]) <= 1e-6 * max(abs(vb[5]), 100.0)    # pressure: a difference of large virial terms
+        assert np.all(np.abs(va[6:] - vb[6:]) <= 1e-9 * np.abs(vb[6:]) + 2e-8)   # volume per bead, box edges
+    # ---- the checkpoint at loop 10
+    snap = os.path.join(d, "snapshot.000000000010")
+    assert os.readlink(os.path.join(d, "restart")) == g["restart_link"]
+    strip = lambda t: re.sub(r"run_id=0x[0-9a-f]{8}", "run_id=X", t)          # noqa: E731
+    tr, to = strip(g["restart"]).split(), strip(open(os.path.join(snap, "restart")).read()).split()
+    assert len(tr) == len(to)
+    for x, y in zip(to, tr):
+        try:
+            fx, fy = float(x.rstrip(";")), float(y.rstrip(";"))
+        except ValueError:
+            assert x == y
+        else:
+            assert abs(fx - fy) <= 1e-11 * abs(fy)
+    header, gid, rv = read_snapshot(snap)
+    assert "loop=10;" in header and "lrec=%d;" % g["lrec"] in header
+    if deck == "popc_small":
+        z = np.load(os.path.join(golden_dir, "snapshot_run.npz"))
+        assert np.array_equal(gid, z[key + "_gid"])
+        ref_rv = z[key + "_rv"]
+        h = np.array([float(x) for x in ref[-1].split()[8:11]])
+        dr = rv[:, :3] - ref_rv[:, :3]
+        dr -= h * np.rint(dr / h)
+        assert np.abs(dr).max() < 1e-8
+        assert np.abs(rv[:, 3:] - ref_rv[:, 3:]).max() <= 1e-8 * np.abs(ref_rv[:, 3:]).max()
+    # ---- the restart written here starts the next run (loop 10 -> 15) and a ddcMD_CMDS "exit" stops and checkpoints it
+    p = os.path.join(d, "object.data")
+    s = open(p).read()
+    open(p, "w").write(re.sub(r"deltaloop=\d+;", "deltaloop=1000;", s))
+    open(os.path.join(d, "ddcMD_CMDS"), "w").write("exit\n")
+    dd.simulateMaster(p)
+    lines = open(os.path.join(d, "data")).read().splitlines()
+    assert [ln.split()[0] for ln in lines[-2:]] == ["000000000010", "000000000015"]
+    assert os.path.getsize(os.path.join(d, "ddcMD_CMDS")) == 0
+    assert os.readlink(os.path.join(d, "restart")) == "./snapshot.000000000015/restart"
+    d2 = dd.Deck(p)
+    assert int(d2.s.loop) == 15
+    # the restarted trajectory continues the first one: loop-10 line re-printed from the restart file agrees to print precision of the file
+    a, b = np.array(lines[-2].split()[1:], float), np.array(ours[-1].split()[1:], float)
+    assert np.all(np.abs(a[1:4] - b[1:4]) <= 1e-9 * max(abs(b[1]), abs(b[2])))
+
+
+@pytest.mark.parametrize("deck,variant", [("popc_small", None), ("popc_small", "full"), ("ras_small", "full"), ("waterbox", None)])
+def test_simulateMaster_matches_reference_run(golden_dir, tmp_path, deck, variant):
+    check_master(golden_dir, deck, variant, tmp_path)
