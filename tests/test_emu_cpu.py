@@ -84,6 +84,16 @@ def test_emu_simulateMaster(emu, golden_dir, tmp_path, deck, variant):
     tm.check_master(golden_dir, deck, variant, tmp_path)
 
 
+def test_emu_fullsize_checks_on_a_small_generated_deck(emu, tmp_path, monkeypatch):
+    """The live-oracle comparison and the size-independent property checks of tests/test_zzz_fullsize.py, on the synthetic
+    generator's ~4k-bead configuration so the emulation finishes in seconds."""
+    import test_zzz_fullsize as tf
+    monkeypatch.setattr(tf, "CACHE", str(tmp_path))
+    if os.path.exists(tf.REF_DUMP):
+        assert tf.check_against_live_oracle("popc_small") > 3000
+    assert tf.check_properties("popc_small") > 3000
+
+
 def _torchrun(nproc, port, script, *args, env=None):
     import subprocess
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
