@@ -149,6 +149,7 @@ def _declare(L):
         "ddcb200_timerElapsed": (i32, [vp, i32, i32, pd]),
         "ddcb200_kernelLaunches": (i64, [vp]),
         "ddcb200_lastListBuild": (i64, [vp]),
+        "ddcb200_listBuildInfo": (i32, [vp, pi, pd]),
         "ddcb200_ncclUniqueId": (i32, [C.c_char_p]),
         "ddcb200_ddcInit": (i32, [vp, i32, i32, i32, i32, i32, C.c_char_p]),
         "ddcb200_ddcPlan": (i32, [pd, i32, i32, i32, dbl, i64, pd, pd, pd, pi, i32, pi, _P(C.c_uint32)]),
@@ -179,7 +180,7 @@ EXPORTS = ["ddcb200_lastError", "ddcb200_deviceCount", "ddcb200_create", "ddcb20
            "ddcb200_nglfconstraintParms", "ddcb200_nglfconstraint", "ddcb200_getBox", "ddcb200_constraintFailures", "ddcb200_getCells", "ddcb200_getPairs", "ddcb200_profile",
            "ddcb200_profileRead", "ddcb200_timerRecord", "ddcb200_timerElapsed", "ddcb200_kernelLaunches", "ddcb200_lastListBuild", "ddcb200_ncclUniqueId", "ddcb200_ddcInit", "ddcb200_ddcPlan", "ddcb200_deckLoad", "ddcb200_deckFree",
            "ddcb200_lastHostError", "ddcb200_simulateBind", "ddcb200_simulateBindRank", "ddcb200_printinfoLine", "ddcb200_unitsConvert",
-           "ddcb200_printinfoHeader", "ddcb200_writeRestart", "ddcb200_readCMDS", "ddcb200_simulateMaster"]
+           "ddcb200_printinfoHeader", "ddcb200_writeRestart", "ddcb200_readCMDS", "ddcb200_simulateMaster", "ddcb200_listBuildInfo"]
 
 
 def _arr(ptr, n, dtype):
@@ -431,6 +432,13 @@ class Simulate:
         rng = self.getRandom() if int(self.deck.s.haveRandom) else None
         return self.deck.writeRestart(st["rx"], st["ry"], st["rz"], st["vx"], st["vy"], st["vz"], loop=int(e.loop), time=float(e.time),
                                       h=self.getBox(), rng=rng, dirname=dirname, restart_link=restart_link)
+
+    def listBuildInfo(self):
+        """(variant in use: 0 undecided / 1 two-pass / 2 one-pass cell build, [ms of the timed two-pass build, ms of the timed cell build])"""
+        v = C.c_int()
+        ms = (C.c_double * 2)()
+        self._ck(lib().ddcb200_listBuildInfo(self.ctx, C.byref(v), ms))
+        return int(v.value), [ms[0], ms[1]]
 
     def printinfo(self, e=None):
         e = e or self.energyInfo()

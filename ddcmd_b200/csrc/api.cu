@@ -208,6 +208,16 @@ extern "C" int ddcb200_create(const ddcb200_params *p, ddcb200_ctx **out)
         return rc;
     }
     CK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    if (const char *lb = getenv("DDCB200_LISTBUILD"))
+    {
+        if (strcmp(lb, "twopass") == 0) c->listBuildMode = 1;
+        else if (strcmp(lb, "cell") == 0) c->listBuildMode = 2;
+        else if (strcmp(lb, "auto") != 0)
+        {
+            delete c;
+            return fail(DDCB200_ERR_ARG, "DDCB200_LISTBUILD must be auto, twopass or cell");
+        }
+    }
     CK(cudaMalloc((void **)&c->grid, sizeof(GridDev)));
     CK(cudaMemset(c->grid, 0, sizeof(GridDev)));
     CK(cudaMallocHost((void **)&c->gridHost, sizeof(GridDev)));
@@ -788,21 +798,65 @@ extern "C" int ddcb200_constructList(ddcb200_ctx *c)
     const double margin = std::max(1e-3, 64.0 * 1.1920929e-7 * 1.5 * Lmax / rl);
     const float rl2f = (float)(c->box.rlist2 * (1.0 + margin));
     if (c->nbrCap == 0) c->nbrCap = 176;
+    // which build: fixed by DDCB200_LISTBUILD, else the first four rebuilds alternate between the two-pass and the one-pass
+    // cell build under CUDA events and the faster one is kept (the rows are bit-identical: the choice never changes a result)
+    int variant = c->listBuildMode;
+    if (variant == 0) variant = c->listBuildsTimed < 4 ? 1 + (c->listBuildsTimed & 1) : (c->listBuildMs[1] < c->listBuildMs[0] ? 2 : 1);
+    const bool timeIt = c->listBuildMode == 0 && c->listBuildsTimed < 4;
+    if (timeIt && !c->evList[0])
+    {
+        CK(cudaEventCreate(&c->evList[0]));
+        CK(cudaEventCreate(&c->evList[1]));
+    }
     for (int attempt = 0; attempt < 4; attempt++)
     {
-        CK(c->nbrRaw.ensure((size_t)c->nbrCap * nPad));
         CK(c->nbr.ensure((size_t)c->nbrCap * nPad));
-        LAUNCH(k_nbr_filter, nPad / 128, 128, 0, st)(nIon, nPad, c->pos32.p, c->cellOfSlot[nxt].p, c->cellStart.p, c->box, rl2f, c->grid,
-                                                c->nbrCap, c->nbrRaw.p, c->nbrRawCount.p);
-        CKL("k_nbr_filter");
-        LAUNCH(k_nbr_exact, nPad / 128, 128, 0, st)(nIon, nPad, c->nbrCap, c->pos4[nxt].p, c->box, c->grid, c->nbrRaw.p, c->nbrRawCount.p,
-                                               c->nbr.p, c->nbrCount.p, c->nbrCum.p, c->gidOfBead.p, c->molTypeOfBead.p,
-                                               c->molTypeSingle.p, c->bpairOffset.p, c->bpairKey.p, c->haveExcl ? 1 : 0);
-        CKL("k_nbr_exact");
+        // one-pass build: one warp per cell, staging rows of `cap` entries per lane in shared memory: as many warps per CTA as
+        // ~110 KB hold (two CTAs per SM), a persistent grid striding over the cells
+        const size_t perWarp = (size_t)c->nbrCap * 32 * sizeof(uint32_t);
+        const int wpb = (int)std::min<size_t>(8, std::max<size_t>(1, (size_t)(110 * 1024) / perWarp));
+        const size_t smem = perWarp * wpb;
+        if (variant == 1) CK(c->nbrRaw.ensure((size_t)c->nbrCap * nPad));
+        else
+        {
+            if (smem > (size_t)220 * 1024) return fail(DDCB200_ERR_CAPACITY, "neighbor rows too long for the one-pass list build (set DDCB200_LISTBUILD=twopass)");
+            CK(cudaFuncSetAttribute(k_nbr_cell, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        }
+        if (timeIt) CK(cudaEventRecord(c->evList[0], st));
+        if (variant == 1)
+        {
+            LAUNCH(k_nbr_filter, nPad / 128, 128, 0, st)(nIon, nPad, c->pos32.p, c->cellOfSlot[nxt].p, c->cellStart.p, c->box, rl2f, c->grid,
+                                                    c->nbrCap, c->nbrRaw.p, c->nbrRawCount.p);
+            CKL("k_nbr_filter");
+            LAUNCH(k_nbr_exact, nPad / 128, 128, 0, st)(nIon, nPad, c->nbrCap, c->pos4[nxt].p, c->box, c->grid, c->nbrRaw.p, c->nbrRawCount.p,
+                                                   c->nbr.p, c->nbrCount.p, c->nbrCum.p, c->gidOfBead.p, c->molTypeOfBead.p,
+                                                   c->molTypeSingle.p, c->bpairOffset.p, c->bpairKey.p, c->haveExcl ? 1 : 0);
+            CKL("k_nbr_exact");
+        }
+        else
+        {
+            const int perSM = (int)std::max<size_t>(1, (size_t)(224 * 1024) / (smem + 1024));
+            LAUNCH(k_nbr_cell, c->numSM * perSM, 32 * wpb, smem, st)(nIon, nPad, c->nbrCap, c->pos4[nxt].p, c->cellStart.p, c->box, c->grid,
+                                                                 c->nbr.p, c->nbrCount.p, c->nbrCum.p, c->gidOfBead.p, c->molTypeOfBead.p,
+                                                                 c->molTypeSingle.p, c->bpairOffset.p, c->bpairKey.p, c->haveExcl ? 1 : 0);
+            CKL("k_nbr_cell");
+        }
+        if (timeIt) CK(cudaEventRecord(c->evList[1], st));
         CK(cudaMemcpyAsync(c->gridHost, c->grid, sizeof(GridDev), cudaMemcpyDeviceToHost, st));
         CK(cudaStreamSynchronize(st));
         if (c->gridHost->error & 2) return fail(DDCB200_ERR_CAPACITY, "cell grid larger than the bead count bound");
-        if (!(c->gridHost->error & 1)) break;
+        if (!(c->gridHost->error & 1))
+        {
+            if (timeIt)
+            {
+                float ms = 0.f;
+                CK(cudaEventElapsedTime(&ms, c->evList[0], c->evList[1]));
+                float &best = c->listBuildMs[c->listBuildsTimed & 1];      // two samples each (the very first build runs on a cold GPU)
+                best = c->listBuildsTimed < 2 ? ms : std::min(best, ms);
+                c->listBuildsTimed++;
+            }
+            break;
+        }
         // a candidate row overflowed: grow and redo both passes
         if (attempt == 3) return fail(DDCB200_ERR_CAPACITY, "neighbor list capacity could not be satisfied");
         c->nbrCap = (int)(c->gridHost->maxRaw * 1.25) + 8;
@@ -1545,6 +1599,20 @@ extern "C" int ddcb200_timerElapsed(ddcb200_ctx *c, int from, int to, double *ms
 extern "C" int64_t ddcb200_kernelLaunches(ddcb200_ctx *c) { return c ? c->kernelLaunches : 0; }
 
 extern "C" int64_t ddcb200_lastListBuild(ddcb200_ctx *c) { return c ? c->lastBuildLoop : -1; }
+
+extern "C" int ddcb200_listBuildInfo(ddcb200_ctx *c, int *variant, double ms[2])
+{
+    if (!c) return fail(DDCB200_ERR_ARG, "null ctx");
+    int v = c->listBuildMode;
+    if (v == 0) v = c->listBuildsTimed < 4 ? 0 : (c->listBuildMs[1] < c->listBuildMs[0] ? 2 : 1);
+    if (variant) *variant = v;
+    if (ms)
+    {
+        ms[0] = c->listBuildMs[0];
+        ms[1] = c->listBuildMs[1];
+    }
+    return DDCB200_OK;
+}
 
 extern "C" int ddcb200_profile(ddcb200_ctx *c, int enable)
 {

@@ -462,3 +462,191 @@ k_nbr_exact(int nIon, int nPad, int cap, const double4 *__restrict__ pos, BoxCon
         atomicAdd(&gp->totalEntries, t);
     }
 }
+
+// ---- 8b/9b. one-pass list build: one warp per cell ------------------------------------------
+// All beads of a cell share the cell's stencil, so with one lane per bead of the cell every lane tests the SAME
+// candidate j at the same time: the j position is one broadcast load (one L1 tag per candidate instead of one per
+// lane), the exact fp64 membership test of pairlist1 runs directly on every stencil candidate - no fp32 candidate
+// pass, no candidate buffer in HBM - and the accepted entries are staged per lane in shared memory (bank = lane, so
+// the staging stores never conflict) until the per-bin counts are known and the row can be written in bin order.
+// Candidate order (stencil cells dz, dy, dx ascending, then slot order), the membership test, the bin of every entry
+// (compared on the bit patterns: exact for positive doubles) and the pruning flag are those of k_nbr_filter +
+// k_nbr_exact, so both builds write bit-identical rows (tests/test_gpu_parity.py::test_list_builds_agree_bit_for_bit).
+// Cells with more than 32 beads take several passes over their stencil.
+#define CELL_PF 4      // candidate positions in flight per warp
+
+// bin of r2 among the 7 ascending edges, on the bit patterns: high words first (edges are >= 1 A^2 apart, their high
+// words differ), the low words only decide when a high word ties
+__device__ __forceinline__ int binOfBits(unsigned long long rb, const unsigned long long *edgeBits)
+{
+    const uint32_t hi = (uint32_t)(rb >> 32);
+    int bin = 0;
+    bool tie = false;
+#pragma unroll
+    for (int e = 0; e < NBINS - 1; e++)
+    {
+        const uint32_t eh = (uint32_t)(edgeBits[e] >> 32);
+        bin += (hi >= eh) ? 1 : 0;
+        tie = tie || (hi == eh);
+    }
+    if (tie)
+    {
+        bin = 0;
+#pragma unroll
+        for (int e = 0; e < NBINS - 1; e++) bin += (rb >= edgeBits[e]) ? 1 : 0;
+    }
+    return bin;
+}
+
+__global__ void __launch_bounds__(256)
+k_nbr_cell(int nIon, int nPad, int cap, const double4 *__restrict__ pos, const int *__restrict__ cellStart, BoxConst b, GridDev *gp,
+           uint32_t *__restrict__ out, int *__restrict__ count, uint16_t *__restrict__ cum, const uint64_t *__restrict__ gid,
+           const int *__restrict__ molTypeOfBead, const int *__restrict__ molTypeSingle, const int *__restrict__ bpairOffset,
+           const uint32_t *__restrict__ bpairKey, int haveExcl)
+{
+    EXTERN_SHARED(uint32_t, stageAll);                    // [warps per block][cap][32]
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, wpb = blockDim.x >> 5;
+    uint32_t *stage = stageAll + (size_t)wib * cap * 32 + lane;
+    if (gp->error & 2) return;
+    const int nx = gp->n[0], ny = gp->n[1], nz = gp->n[2];
+    const int ncell = nx * ny * nz;
+    const int lx = nx >= 3 ? -1 : 0, hx = nx >= 2 ? 1 : 0;
+    const int ly = ny >= 3 ? -1 : 0, hy = ny >= 2 ? 1 : 0;
+    const int lz = nz >= 3 ? -1 : 0, hz = nz >= 2 ? 1 : 0;
+    unsigned long long edgeBits[NBINS - 1];
+#pragma unroll
+    for (int e = 0; e < NBINS - 1; e++) edgeBits[e] = (unsigned long long)__double_as_longlong(b.binEdge2[e]);
+    int statMax = 0;
+    unsigned long long statTotal = 0ull;
+    for (int c = blockIdx.x * wpb + wib; c < ncell; c += gridDim.x * wpb)
+    {
+        const int lo = cellStart[c], hi = cellStart[c + 1];
+        const int cx = c % nx, cy = (c / nx) % ny, cz = c / (nx * ny);
+        for (int base = lo; base < hi; base += 32)
+        {
+            const int i = base + lane;
+            const bool have = i < hi;
+            const double4 pi = ldPos256(pos + (have ? i : lo));
+            const uint64_t wi = (uint64_t)__double_as_longlong(pi.w);
+            const bool act = have && !(wi >> 63);            // ghost slots own no row
+            const uint32_t molI = (uint32_t)wi & 0xffff0000u;
+            int cnt = 0;
+            if (__any_sync(0xffffffffu, act))
+            {
+                for (int dz = lz; dz <= hz; dz++)
+                {
+                    int az = cz + dz;
+                    if (az < 0) az += nz;
+                    else if (az >= nz) az -= nz;
+                    for (int dy = ly; dy <= hy; dy++)
+                    {
+                        int ay = cy + dy;
+                        if (ay < 0) ay += ny;
+                        else if (ay >= ny) ay -= ny;
+                        for (int dx = lx; dx <= hx; dx++)
+                        {
+                            int ax = cx + dx;
+                            if (ax < 0) ax += nx;
+                            else if (ax >= nx) ax -= nx;
+                            const int cc = ax + nx * (ay + ny * az);
+                            const int jlo = cellStart[cc], jhi = cellStart[cc + 1];
+                            for (int j0 = jlo; j0 < jhi; j0 += CELL_PF)
+                            {
+                                double4 pjv[CELL_PF];
+#pragma unroll
+                                for (int u = 0; u < CELL_PF; u++) pjv[u] = ldPos256(pos + min(j0 + u, jhi - 1));
+#pragma unroll
+                                for (int u = 0; u < CELL_PF; u++)
+                                {
+                                    const int j = j0 + u;
+                                    const double4 pj = pjv[u];
+                                    // pairlist1, src/pairlist.c:280-288
+                                    double x = __dadd_rn(pi.x, -pj.x), y = __dadd_rn(pi.y, -pj.y), z = __dadd_rn(pi.z, -pj.z);
+                                    double r2 = exactR2(x, y, z);
+                                    if (r2 > b.R2cut)
+                                    {
+                                        wrapOnce(x, y, z, b);
+                                        r2 = exactR2(x, y, z);
+                                    }
+                                    if (act && j < jhi && r2 < b.rlist2 && j != i)
+                                    {
+                                        const int bin = binOfBits((unsigned long long)__double_as_longlong(r2), edgeBits);
+                                        uint32_t ent = (uint32_t)j | ((uint32_t)bin << 27);
+                                        if (haveExcl && ((uint32_t)__double_as_longlong(pj.w) & 0xffff0000u) == molI)
+                                        {
+                                            // same low 16 bits of the molecule id: the gid tables decide (reOrgPairs)
+                                            const uint64_t wj = (uint64_t)__double_as_longlong(pj.w);
+                                            if (isPruned((int)((wi >> 32) & 0x7fffffffull), (int)((wj >> 32) & 0x7fffffffull), gid, molTypeOfBead,
+                                                         molTypeSingle, bpairOffset, bpairKey))
+                                                ent |= EXCL_BIT;
+                                        }
+                                        if (cnt < cap) stage[(size_t)cnt * 32] = ent;
+                                        cnt++;
+                                    }
+                                }
+                            }
+                        }
+                    }
+                }
+            }
+            if (have)
+            {
+                // per-bin counts from the staged entries (eight 16-bit counters in two words, as k_nbr_exact), exclusive prefix,
+                // cumulative counts at every bin boundary, then the row in bin order
+                const int stored = min(cnt, cap);
+                uint64_t A = 0ull, B = 0ull;
+                for (int k = 0; k < stored; k++)
+                {
+                    const int bin = (stage[(size_t)k * 32] >> 27) & 7;
+                    const uint64_t one = 1ull << (16 * (bin & 3));
+                    if (bin < 4) A += one;
+                    else B += one;
+                }
+                const uint64_t totA = (A * 0x0001000100010001ull) >> 48;
+                uint64_t offA = A * 0x0001000100010000ull;
+                uint64_t offB = B * 0x0001000100010000ull + totA * 0x0001000100010001ull;
+#pragma unroll
+                for (int bnd = 0; bnd < NBINS; bnd++)
+                {
+                    const uint64_t off = bnd < 4 ? offA : offB, cn = bnd < 4 ? A : B;
+                    const int sh = 16 * (bnd & 3);
+                    cum[(size_t)bnd * nPad + i] = (uint16_t)(((off >> sh) & 0xffffull) + ((cn >> sh) & 0xffffull));
+                }
+                if (cnt <= cap)
+                    for (int k = 0; k < stored; k++)
+                    {
+                        const uint32_t e = stage[(size_t)k * 32];
+                        const int bin = (e >> 27) & 7;
+                        const int sh = 16 * (bin & 3);
+                        int dst;
+                        if (bin < 4)
+                        {
+                            dst = (int)((offA >> sh) & 0xffffull);
+                            offA += 1ull << sh;
+                        }
+                        else
+                        {
+                            dst = (int)((offB >> sh) & 0xffffull);
+                            offB += 1ull << sh;
+                        }
+                        out[(size_t)dst * nPad + i] = (e & 0x07ffffffu) | (e & EXCL_BIT);
+                    }
+                count[i] = cnt;
+            }
+            statMax = max(statMax, cnt);
+            statTotal += (unsigned long long)cnt;
+        }
+    }
+    for (int o = 16; o > 0; o >>= 1)
+    {
+        statMax = max(statMax, __shfl_xor_sync(0xffffffffu, statMax, o));
+        statTotal += __shfl_xor_sync(0xffffffffu, statTotal, o);
+    }
+    if (lane == 0 && statMax > 0)
+    {
+        atomicMax(&gp->maxCount, statMax);
+        atomicMax(&gp->maxRaw, statMax);            // drives the capacity regrow, like the candidate count of the two-pass build
+        atomicAdd(&gp->totalEntries, statTotal);
+        if (statMax > cap) atomicOr(&gp->error, 1);
+    }
+}

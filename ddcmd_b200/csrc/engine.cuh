@@ -181,6 +181,13 @@ struct ddcb200_ctx
     int nbrCap = 0;               // entries per bead allocated
     bool listValid = false;
     int64_t lastBuildLoop = -1;
+    // list-build variant: 0 = auto (the first four rebuilds alternate between the two builds under CUDA events, then the
+    // faster is kept; both write bit-identical rows), 1 = two-pass (k_nbr_filter + k_nbr_exact), 2 = one-pass (k_nbr_cell).
+    // DDCB200_LISTBUILD=auto|twopass|cell
+    int listBuildMode = 0;
+    int listBuildsTimed = 0;
+    float listBuildMs[2] = {0.f, 0.f};
+    cudaEvent_t evList[2] = {nullptr, nullptr};
     // displacement-triggered rebuild (updateRate == 0, nbrcheck.cuh)
     DevBuf<double> chk, chkPartial;   // chk: 3 sums now, 3 sums at the build, bits of max d^2
     double *chkHost = nullptr;        // pinned

@@ -213,6 +213,12 @@ int64_t ddcb200_kernelLaunches(ddcb200_ctx *ctx);
  * check4updateNeighbor / evalUpdateFlag (src/ddcUpdateAll.c:48-71). */
 int64_t ddcb200_lastListBuild(ddcb200_ctx *ctx);
 
+/* Which list build runs: 1 = two passes (fp32 candidate filter, then the exact pairlist1 test over the candidates),
+ * 2 = one pass (one warp per cell, exact test on every stencil candidate), 0 = not decided yet.  Both write the same
+ * rows bit for bit.  Unless DDCB200_LISTBUILD=twopass|cell fixes it, the first four rebuilds alternate between the
+ * variants under CUDA events and the faster is kept; ms[0], ms[1] are the best device time of each. */
+int ddcb200_listBuildInfo(ddcb200_ctx *ctx, int *variant, double ms[2]);
+
 /* ---- multi-GPU: ddc-style spatial decomposition over the GPUs of one box, one process per GPU ----
  * Replaces ddc_init + ddcAssignment + ddcSendRecvTables + ddcUpdate (src/ddc.c:61-117,
  * src/ddcAssignment.c:64-107, src/ddcSendRecv.c:41-277, src/ddcUpdate.c:40-88) and the reduction of

@@ -51,6 +51,11 @@ def test_emu_step0_forces_energy_virial(emu, golden_dir, name):
 
 
 @pytest.mark.parametrize("name", SMALL)
+def test_emu_list_builds_agree(emu, golden_dir, name, monkeypatch):
+    tg.test_list_builds_agree_bit_for_bit(golden_dir, name, monkeypatch)
+
+
+@pytest.mark.parametrize("name", SMALL)
 def test_emu_trajectory_40_steps(emu, golden_dir, name):
     tg.test_trajectory_40_steps(golden_dir, name)
 

@@ -122,6 +122,44 @@ def test_deterministic_forces(golden_dir):
     assert e1 == sim2.energyInfo().eion
 
 
+def _rows_and_forces(golden_dir, name, mode, monkeypatch):
+    monkeypatch.setenv("DDCB200_LISTBUILD", mode)
+    sim, ref = _load(golden_dir, name)
+    sim.ddcenergy(1)
+    e = sim.energyInfo()
+    st = sim.getState()
+    pairs = sim.getPairs()          # decoded in row order: equal arrays = equal rows, entry for entry
+    cells = sim.getCells()[0]
+    sim.nglf(61)                    # across three rebuilds: the auto mode has timed both builds twice by then
+    e2 = sim.energyInfo()
+    st2 = sim.getState()
+    info = sim.listBuildInfo()
+    sim.close()
+    return pairs, cells, st, e, st2, e2, info
+
+
+@pytest.mark.parametrize("name", DECKS)
+def test_list_builds_agree_bit_for_bit(golden_dir, name, monkeypatch):
+    """The one-pass cell build (k_nbr_cell) and the two-pass build (k_nbr_filter + k_nbr_exact) write the same rows in the same
+    order, so forces, energies and the trajectory across a rebuild are bitwise equal whichever one the timing picks."""
+    a = _rows_and_forces(golden_dir, name, "twopass", monkeypatch)
+    b = _rows_and_forces(golden_dir, name, "cell", monkeypatch)
+    assert a[6][0] == 1 and b[6][0] == 2
+    for x, y in zip(a[0], b[0]):
+        assert np.array_equal(x, y)
+    assert np.array_equal(a[1], b[1])
+    for k in ("fx", "fy", "fz"):
+        assert np.array_equal(a[2][k], b[2][k])
+    assert a[3].eion == b[3].eion and a[3].nPairsListed == b[3].nPairsListed
+    for k in ("rx", "ry", "rz", "vx", "vy", "vz", "fx"):
+        assert np.array_equal(a[4][k], b[4][k])
+    assert a[5].eion == b[5].eion and a[5].rk == b[5].rk and a[5].nPairsListed == b[5].nPairsListed
+    # auto: the first four builds alternate, then the faster of the two
+    c = _rows_and_forces(golden_dir, name, "auto", monkeypatch)
+    assert c[6][0] in (1, 2) and c[6][1][0] > 0.0 and c[6][1][1] > 0.0
+    assert np.array_equal(c[4]["rx"], a[4]["rx"]) and c[5].eion == a[5].eion
+
+
 def test_printinfo_line_matches_reference_data_file(golden_dir):
     """Step-0 'data' line of examples/waterbox pinned by SURVEY.md (the reference's own output)."""
     sim, _ = _load(golden_dir, "waterbox")
