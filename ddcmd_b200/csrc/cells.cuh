@@ -475,30 +475,33 @@ k_nbr_exact(int nIon, int nPad, int cap, const double4 *__restrict__ pos, BoxCon
 // Cells with more than 32 beads take several passes over their stencil.
 #define CELL_PF 4      // candidate positions in flight per warp
 
-// bin of r2 among the 7 ascending edges, on the bit patterns: high words first (edges are >= 1 A^2 apart, their high
-// words differ), the low words only decide when a high word ties
-__device__ __forceinline__ int binOfBits(unsigned long long rb, const unsigned long long *edgeBits)
+// bin of r2 among the 7 ascending edges = number of edges <= r2, on the bit patterns (exact for positive doubles): a
+// three-level tree on the high words; only when a compared high word ties do the full 64-bit patterns decide
+__device__ __forceinline__ int binOfBits(double r2, const int *eh, const double *edge2)
 {
-    const uint32_t hi = (uint32_t)(rb >> 32);
-    int bin = 0;
-    bool tie = false;
-#pragma unroll
-    for (int e = 0; e < NBINS - 1; e++)
+#if NBINS != 8
+#error "binOfBits is written for 7 edges"
+#endif
+    const int hi = __double2hiint(r2);           // r2 > 0: the high words order like the values
+    const bool g3 = hi >= eh[3];
+    const int m1 = g3 ? eh[5] : eh[1];
+    const bool g1 = hi >= m1;
+    const int lo0 = g1 ? eh[2] : eh[0];
+    const int hi0 = g1 ? eh[6] : eh[4];
+    const int m2 = g3 ? hi0 : lo0;
+    const bool g0 = hi >= m2;
+    int bin = (g3 ? 4 : 0) + (g1 ? 2 : 0) + (g0 ? 1 : 0);
+    if (hi == eh[3] || hi == m1 || hi == m2)
     {
-        const uint32_t eh = (uint32_t)(edgeBits[e] >> 32);
-        bin += (hi >= eh) ? 1 : 0;
-        tie = tie || (hi == eh);
-    }
-    if (tie)
-    {
+        const unsigned long long rb = (unsigned long long)__double_as_longlong(r2);
         bin = 0;
 #pragma unroll
-        for (int e = 0; e < NBINS - 1; e++) bin += (rb >= edgeBits[e]) ? 1 : 0;
+        for (int e = 0; e < NBINS - 1; e++) bin += (rb >= (unsigned long long)__double_as_longlong(edge2[e])) ? 1 : 0;
     }
     return bin;
 }
 
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 1)
 k_nbr_cell(int nIon, int nPad, int cap, const double4 *__restrict__ pos, const int *__restrict__ cellStart, BoxConst b, GridDev *gp,
            uint32_t *__restrict__ out, int *__restrict__ count, uint16_t *__restrict__ cum, const uint64_t *__restrict__ gid,
            const int *__restrict__ molTypeOfBead, const int *__restrict__ molTypeSingle, const int *__restrict__ bpairOffset,
@@ -513,9 +516,9 @@ k_nbr_cell(int nIon, int nPad, int cap, const double4 *__restrict__ pos, const i
     const int lx = nx >= 3 ? -1 : 0, hx = nx >= 2 ? 1 : 0;
     const int ly = ny >= 3 ? -1 : 0, hy = ny >= 2 ? 1 : 0;
     const int lz = nz >= 3 ? -1 : 0, hz = nz >= 2 ? 1 : 0;
-    unsigned long long edgeBits[NBINS - 1];
+    int eh[NBINS - 1];
 #pragma unroll
-    for (int e = 0; e < NBINS - 1; e++) edgeBits[e] = (unsigned long long)__double_as_longlong(b.binEdge2[e]);
+    for (int e = 0; e < NBINS - 1; e++) eh[e] = __double2hiint(b.binEdge2[e]);
     int statMax = 0;
     unsigned long long statTotal = 0ull;
     for (int c = blockIdx.x * wpb + wib; c < ncell; c += gridDim.x * wpb)
@@ -531,6 +534,7 @@ k_nbr_cell(int nIon, int nPad, int cap, const double4 *__restrict__ pos, const i
             const bool act = have && !(wi >> 63);            // ghost slots own no row
             const uint32_t molI = (uint32_t)wi & 0xffff0000u;
             int cnt = 0;
+            uint32_t *sp = stage;
             if (__any_sync(0xffffffffu, act))
             {
                 for (int dz = lz; dz <= hz; dz++)
@@ -568,9 +572,9 @@ k_nbr_cell(int nIon, int nPad, int cap, const double4 *__restrict__ pos, const i
                                         wrapOnce(x, y, z, b);
                                         r2 = exactR2(x, y, z);
                                     }
-                                    if (act && j < jhi && r2 < b.rlist2 && j != i)
+                                    if (r2 < b.rlist2 && act && j < jhi && j != i)
                                     {
-                                        const int bin = binOfBits((unsigned long long)__double_as_longlong(r2), edgeBits);
+                                        const int bin = binOfBits(r2, eh, b.binEdge2);
                                         uint32_t ent = (uint32_t)j | ((uint32_t)bin << 27);
                                         if (haveExcl && ((uint32_t)__double_as_longlong(pj.w) & 0xffff0000u) == molI)
                                         {
@@ -580,7 +584,8 @@ k_nbr_cell(int nIon, int nPad, int cap, const double4 *__restrict__ pos, const i
                                                          molTypeSingle, bpairOffset, bpairKey))
                                                 ent |= EXCL_BIT;
                                         }
-                                        if (cnt < cap) stage[(size_t)cnt * 32] = ent;
+                                        if (cnt < cap) *sp = ent;
+                                        sp += 32;
                                         cnt++;
                                     }
                                 }
