@@ -802,7 +802,7 @@ extern "C" int ddcb200_constructList(ddcb200_ctx *c)
     // cell build under CUDA events and the faster one is kept (the rows are bit-identical: the choice never changes a result)
     int variant = c->listBuildMode;
     if (variant == 0) variant = c->listBuildsTimed < 4 ? 1 + (c->listBuildsTimed & 1) : (c->listBuildMs[1] < c->listBuildMs[0] ? 2 : 1);
-    const bool timeIt = c->listBuildMode == 0 && c->listBuildsTimed < 4;
+    bool timeIt = c->listBuildMode == 0 && c->listBuildsTimed < 4;
     if (timeIt && !c->evList[0])
     {
         CK(cudaEventCreate(&c->evList[0]));
@@ -839,7 +839,24 @@ extern "C" int ddcb200_constructList(ddcb200_ctx *c)
             LAUNCH(k_nbr_cell, c->numSM * perSM, 32 * wpb, smem, st)(nIon, nPad, c->nbrCap, c->pos4[nxt].p, c->cellStart.p, c->box, c->grid,
                                                                  c->nbr.p, c->nbrCount.p, c->nbrCum.p, c->gidOfBead.p, c->molTypeOfBead.p,
                                                                  c->molTypeSingle.p, c->bpairOffset.p, c->bpairKey.p, c->haveExcl ? 1 : 0);
-            CKL("k_nbr_cell");
+            if (c->listBuildMode == 0)
+            {
+                // auto mode: a launch the device refuses (shared-memory carve-out, limits) just means "use the other build";
+                // this is a choice between two device kernels that write the same rows, reported on stderr - never a CPU path
+                const cudaError_t le = cudaGetLastError();
+                if (le != cudaSuccess)
+                {
+                    fprintf(stderr, "ddcmd_b200: one-pass list build not launchable here (%s); keeping the two-pass build\n", cudaGetErrorString(le));
+                    c->listBuildMode = 1;
+                    variant = 1;
+                    timeIt = false;
+                    attempt--;
+                    continue;
+                }
+                c->kernelLaunches += 1;
+            }
+            else
+                CKL("k_nbr_cell");
         }
         if (timeIt) CK(cudaEventRecord(c->evList[1], st));
         CK(cudaMemcpyAsync(c->gridHost, c->grid, sizeof(GridDev), cudaMemcpyDeviceToHost, st));
