@@ -425,13 +425,30 @@ class Simulate:
 
     def writeRestart(self, dirname=None, restart_link=True):
         """checkpointSimulate (src/masters.c:51-56): CreateSnapshotdir + writeRestart of the current device state."""
-        if self.nranks != 1:
-            raise DdcError("writeRestart gathers one rank's beads only; gather getState() of all ranks and use Deck.writeRestart")
         e = self.energyInfo()
         st = self.getState()
-        rng = self.getRandom() if int(self.deck.s.haveRandom) else None
-        return self.deck.writeRestart(st["rx"], st["ry"], st["rz"], st["vx"], st["vy"], st["vz"], loop=int(e.loop), time=float(e.time),
-                                      h=self.getBox(), rng=rng, dirname=dirname, restart_link=restart_link)
+        if self.nranks == 1:
+            rng = self.getRandom() if int(self.deck.s.haveRandom) else None
+            return self.deck.writeRestart(st["rx"], st["ry"], st["rz"], st["vx"], st["vy"], st["vz"], loop=int(e.loop), time=float(e.time),
+                                          h=self.getBox(), rng=rng, dirname=dirname, restart_link=restart_link)
+        # several ranks (collective call): the reference funnels every task's records to the writer tasks of pio
+        # (src/pio.c); here the ranks' beads are gathered over the caller's torch.distributed group and rank 0 writes the
+        # single atoms#000000 in the deck's bead order.  Returns the snapshot directory on rank 0, None elsewhere.
+        import torch.distributed as dist
+        keys = ("rx", "ry", "rz", "vx", "vy", "vz")
+        parts = [None] * dist.get_world_size()
+        dist.all_gather_object(parts, (self.getLocalBeads(), {k: st[k] for k in keys}))
+        if dist.get_rank() != 0:
+            return None
+        n = self.deck.n
+        full = {k: np.full(n, np.nan) for k in keys}
+        for beads, d in parts:
+            for k in keys:
+                full[k][beads] = d[k]
+        if any(np.isnan(full[k]).any() for k in keys):
+            raise DdcError("writeRestart: some beads are local on no rank")
+        return self.deck.writeRestart(*[full[k] for k in keys], loop=int(e.loop), time=float(e.time), h=self.getBox(), dirname=dirname,
+                                      restart_link=restart_link)
 
     def listBuildInfo(self):
         """(variant in use: 0 undecided / 1 two-pass / 2 one-pass cell build, [ms of the timed two-pass build, ms of the timed cell build])"""

@@ -78,7 +78,7 @@ int ddcb200_writeRestart(const ddcb200_deck *d, const char *dirname, int64_t loo
     /* CreateSnapshotdir: <atomsdir>/snapshot.<loopFormat> or <atomsdir>/<dirname>; relative to the deck's directory */
     char rel[1024], loopFmt[16];
     snprintf(loopFmt, sizeof loopFmt, "%%%d.%dllu", d->nLoopDigits, d->nLoopDigits);
-    int k = snprintf(rel, sizeof rel, "%s/", d->atomsdir);
+    int k = (dirname && dirname[0] == '/') ? 0 : snprintf(rel, sizeof rel, "%s/", d->atomsdir);   /* an absolute dirname is taken as it is */
     if (dirname) snprintf(rel + k, sizeof rel - (size_t)k, "%s", dirname);
     else
     {
@@ -279,6 +279,7 @@ int ddcb200_simulateMaster(const char *objectFile, const char *restartFile, cons
     HostState hs;
     memset(&hs, 0, sizeof hs);
     FILE *data = NULL;
+    char *cmds = NULL;
     int rc = ddcb200_deckLoad(objectFile, restartFile, simulateName, &d);
     if (rc) return rc;
     rc = ddcb200_simulateBind(d, device, &c);
@@ -294,7 +295,7 @@ int ddcb200_simulateMaster(const char *objectFile, const char *restartFile, cons
         if (!data) { rc = herr("cannot open %s", dpath); free(dpath); goto done; }
         free(dpath);
     }
-    char *cmds = pathJoin(d->runDir, "ddcMD_CMDS");
+    cmds = pathJoin(d->runDir, "ddcMD_CMDS");
     char buf[1024];
     ddcb200_etype e;
     /* firstEnergyCall (src/masters.c:579-620) + the first printinfoAll with the header */
@@ -334,8 +335,8 @@ int ddcb200_simulateMaster(const char *objectFile, const char *restartFile, cons
         if (flag & DDCB200_CMD_STOP) break;
     }
     if (rc == 0 && !TEST0(loop, d->printrate)) PRINTLINE();
-    free(cmds);
 done:
+    free(cmds);
     if (data) fclose(data);
     for (int k = 0; k < 6; k++) free(hs.r[k]);
     free(hs.rng);

@@ -101,6 +101,21 @@ def main():
         assert abs((e.eion + e.rk) - etot) <= 1e-9 * max(abs(etot), abs(tr[39, 2])), (e.eion + e.rk, etot)
         dz = np.abs(st["rz"] - ref["sN_rz"])
         assert np.quantile(dz, 0.99) < 1e-9 and dz.max() < 1e-6, (np.quantile(dz, 0.99), dz.max())
+    # ---- a ddcMD-format restart written from the decomposed state: every bead once, in the deck's order ----
+    import tempfile
+    tmp = tempfile.mkdtemp(prefix="mgpu_snap_") if rank == 0 else None
+    snap = sim.writeRestart(dirname=os.path.join(tmp, "snapshot.mgpu") if rank == 0 else None, restart_link=False)
+    if rank == 0:
+        import shutil
+        raw = open(os.path.join(snap, "atoms#000000"), "rb").read()
+        recs = raw[raw.index(b"\n\n", raw.index(b"}")) + 2:].split(b"\n")[:n]
+        got = np.array([[float(x) for x in r.split()[5:8]] for r in recs])
+        h = np.array([sim.getBox()[k] for k in (0, 4, 8)])
+        d = got - np.stack([st["rx"], st["ry"], st["rz"]], 1) * dd.units_convert(1.0, None, "Angstrom")
+        d -= h * dd.units_convert(1.0, None, "Angstrom") * np.rint(d / (h * dd.units_convert(1.0, None, "Angstrom")))
+        assert np.abs(d).max() < 1e-10, np.abs(d).max()
+        assert b"loop=40;" in raw[:2000]
+        shutil.rmtree(tmp)
         print("MGPU_OK %s world=%d locals=%s" % (name, world, nloc), flush=True)
     sim.close()
     dist.barrier()
