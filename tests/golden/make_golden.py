@@ -76,4 +76,6 @@ if __name__ == "__main__":
     waterbox()
     synthetic("popc_small", lambda: synth.make_membrane(lx=57.0, ly=57.0, lz=112.0, seed=1))
     synthetic("ras_small", lambda: synth.make_membrane(lx=68.0, ly=57.0, lz=160.0, seed=2, protein_beads=120), ras_restraints)
+    # two cells per axis in x and y (33.9 A box edge against the 15 A list radius): the deduplicated stencil of both list builds
+    synthetic("tiny2", lambda: synth.make_membrane(lx=34.0, ly=34.0, lz=100.0, seed=5))
     print("golden fixtures written under", HERE)

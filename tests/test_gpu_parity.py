@@ -13,7 +13,7 @@ import ddcmd_b200 as dd
 
 pytestmark = pytest.mark.gpu
 
-DECKS = ["waterbox", "popc_small", "ras_small"]
+DECKS = ["waterbox", "popc_small", "ras_small", "tiny2"]   # tiny2: two cells per axis in x and y
 F_TOL = 1e-6      # per-bead force, relative to max(|f_ref|, rms force)
 E_TOL = 1e-9      # energies, relative
 
@@ -172,7 +172,7 @@ def test_printinfo_line_matches_reference_data_file(golden_dir):
     assert abs(float(line[7]) - 133.942256177663) < 1e-9         # volume per bead
 
 
-@pytest.mark.parametrize("name", ["popc_small", "ras_small", "waterbox"])
+@pytest.mark.parametrize("name", ["popc_small", "ras_small", "waterbox", "tiny2"])
 def test_two_gpus_match_reference(name):
     """ddc decomposition over 2 GPUs (NCCL halo, re-domain every 20 steps) against the single-rank reference."""
     import subprocess
