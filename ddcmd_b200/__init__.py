@@ -70,7 +70,7 @@ class DeckStruct(C.Structure):
                 ("runDir", C.c_char_p), ("simulateName", C.c_char_p), ("boxName", C.c_char_p), ("collectionName", C.c_char_p),
                 ("atomsdir", C.c_char_p), ("nLoopDigits", C.c_int), ("gidFormatHex", C.c_int), ("runId", C.c_uint),
                 ("speciesType", _P(C.c_char_p)), ("printUnit", C.c_char_p * 6), ("printConvert", C.c_double * 6),
-                ("reducedCorner", C.c_double * 3)]
+                ("reducedCorner", C.c_double * 3), ("checkpointBinary", C.c_int), ("checkpointBrief", C.c_int)]
 
 
 class DdcError(RuntimeError):

@@ -289,6 +289,115 @@ uint32_t hcrc32(const unsigned char *data, size_t len)
 typedef struct { const char *name; int index; } NameIdx;
 static int cmpName(const void *a, const void *b) { return strcmp(((const NameIdx *)a)->name, ((const NameIdx *)b)->name); }
 
+/* FIXRECORDBINARY records (collection_readBINARY, src/collection_read.c:201-345; written by collection_writeBLOCK_binary,
+ * src/collection_write.c:188-336): checksum u4 | id bN (big-endian) | pinfo bM | rx ry rz f8 | vx vy vz f8 or f4 | LCG64 16 B.
+ * pinfo = group + species * nGroups over the header's `groups` / `species` lists (pinfoDecode, src/pinfo.c:129-146). */
+static uint64_t beField(const unsigned char *b, int n)
+{
+    uint64_t r = 0;
+    for (int i = 0; i < n; i++) r = r * 256 + b[i];
+    return r;
+}
+static int readAtomsBinary(const char *path, const unsigned char *data, size_t ndata, const ODB_OBJECT *h, int64_t size, ddcb200_deck *d,
+                           NameIdx *sortedSpecies, int nspecies, int64_t *filled, int *randomMissing)
+{
+    int lrec = 0, key = 0, rfs = 0;
+    odb_getInts(h, "lrec", &lrec, 1, "0");
+    odb_getInts(h, "endian_key", &key, 1, "0");
+    odb_getInts(h, "randomFieldSize", &rfs, 1, "0");
+    if (key != 875770417) return herr("atoms file %s: byte-swapped binary records are not supported (endian_key %d)", path, key);
+    char **ft, **fn, **gn, **sn, **tn, *ck = NULL, *rnd = NULL;
+    const int nt = odb_getStrings(h, "field_types", &ft, NULL), nf = odb_getStrings(h, "field_names", &fn, NULL);
+    const int ng = odb_getStrings(h, "groups", &gn, NULL), ns = odb_getStrings(h, "species", &sn, NULL), nty = odb_getStrings(h, "types", &tn, NULL);
+    odb_getString(h, "checksum", &ck, "NONE");
+    odb_getString(h, "random", &rnd, "NotSet");
+    int rc = 0;
+    int off[16], len[16], role[16], fixed = 0;   /* role: 0 checksum 1 id 2 pinfo 3..8 rx..vz, -1 ignored */
+    static const char *names[9] = {"checksum", "id", "pinfo", "rx", "ry", "rz", "vx", "vy", "vz"};
+    int *spOf = NULL, *grOf = NULL;
+    if (nt != nf || nf < 1 || nf > 16 || lrec <= 0 || ng < 1 || ns < 1 || nty != 1) { rc = herr("atoms file %s: malformed binary header", path); goto out; }
+    for (int k = 0; k < nf; k++)
+    {
+        len[k] = atoi(ft[k] + 1);
+        off[k] = fixed;
+        fixed += len[k];
+        role[k] = -1;
+        for (int r = 0; r < 9; r++)
+            if (strcmp(fn[k], names[r]) == 0) role[k] = r;
+        if (len[k] <= 0 || len[k] > 8 || (role[k] >= 3 && ft[k][0] != 'f') || (role[k] >= 3 && len[k] != 8 && len[k] != 4))
+        { rc = herr("atoms file %s: unsupported binary field %s %s", path, fn[k], ft[k]); goto out; }
+    }
+    const int haveRnd = strcmp(rnd, "NotSet") != 0 && strcmp(rnd, "NONE") != 0 && rfs == 16;
+    if (!haveRnd) *randomMissing = 1;
+    if (fixed + (haveRnd ? 16 : 0) > lrec) { rc = herr("atoms file %s: fields exceed lrec", path); goto out; }
+    spOf = (int *)malloc(sizeof(int) * (size_t)ns);
+    grOf = (int *)malloc(sizeof(int) * (size_t)ng);
+    for (int k = 0; k < ns; k++)
+    {
+        NameIdx q = {sn[k], 0};
+        NameIdx *hit = (NameIdx *)bsearch(&q, sortedSpecies, nspecies, sizeof(NameIdx), cmpName);
+        spOf[k] = hit ? hit->index : -1;
+    }
+    for (int k = 0; k < ng; k++)
+    {
+        grOf[k] = -1;
+        for (int g = 0; g < d->nGroups; g++)
+            if (strcmp(d->groupName[g], gn[k]) == 0) grOf[k] = g;
+    }
+    const double lc = hu_convert(1.0, "l", NULL), tc = hu_convert(1.0, "t", NULL), vc = lc / tc;
+    const int useCrc = strcmp(ck, "CRC32") == 0;
+    int64_t i = *filled;
+    const int64_t nrec = (int64_t)(ndata / (size_t)lrec);
+    for (int64_t r = 0; r < nrec && i < size; r++, i++)
+    {
+        const unsigned char *b = data + (size_t)r * (size_t)lrec;
+        double v[6] = {0, 0, 0, 0, 0, 0};
+        for (int k = 0; k < nf; k++)
+        {
+            const unsigned char *q = b + off[k];
+            if (role[k] == 0)
+            {
+                uint32_t want;
+                memcpy(&want, q, 4);
+                if (useCrc && len[k] == 4 && hcrc32(b + 4, (size_t)lrec - 4) != want) { rc = herr("atoms file %s: CRC32 mismatch in record %lld", path, (long long)i); goto out; }
+            }
+            else if (role[k] == 1) d->gid[i] = beField(q, len[k]);
+            else if (role[k] == 2)
+            {
+                const uint64_t pin = beField(q, len[k]);
+                const int ig = (int)(pin % (uint64_t)ng), is = (int)((pin / (uint64_t)ng) % (uint64_t)ns);
+                if (pin >= (uint64_t)ng * (uint64_t)ns || spOf[is] < 0) { rc = herr("atoms file %s: record %lld names an unknown species", path, (long long)i); goto out; }
+                d->species[i] = spOf[is];
+                if (d->groupOfBead)
+                {
+                    if (grOf[ig] < 0) { rc = herr("atoms file %s: record %lld names GROUP %s, which SYSTEM groups does not list", path, (long long)i, gn[ig]); goto out; }
+                    d->groupOfBead[i] = (unsigned char)grOf[ig];
+                }
+            }
+            else if (role[k] >= 3)
+            {
+                if (len[k] == 8) memcpy(&v[role[k] - 3], q, 8);
+                else { float f4; memcpy(&f4, q, 4); v[role[k] - 3] = f4; }
+            }
+        }
+        d->rx[i] = lc * v[0]; d->ry[i] = lc * v[1]; d->rz[i] = lc * v[2];
+        d->vx[i] = vc * v[3]; d->vy[i] = vc * v[4]; d->vz[i] = vc * v[5];
+        if (haveRnd && d->rngState)
+        {
+            /* lcg64_bread (src/lcg64.c:65-74): state u8, multID u4, prime u4, native byte order */
+            uint64_t st; uint32_t m, pr;
+            memcpy(&st, b + fixed, 8); memcpy(&m, b + fixed + 8, 4); memcpy(&pr, b + fixed + 12, 4);
+            if (pr == 0 || m > 2) *randomMissing = 1;
+            else { d->rngState[i] = st; d->rngMult[i] = m; d->rngPrime[i] = pr; }
+        }
+    }
+    *filled = i;
+out:
+    free(spOf); free(grOf); free(ck); free(rnd);
+    odb_freeStrings(ft, nt); odb_freeStrings(fn, nf); odb_freeStrings(gn, ng); odb_freeStrings(sn, ns); odb_freeStrings(tn, nty);
+    return rc;
+}
+
 static int readAtoms(const char *path, int64_t size, ddcb200_deck *d, NameIdx *sortedSpecies, int nspecies, int64_t *filled, int *randomMissing)
 {
     FILE *f = fopen(path, "rb");
@@ -314,6 +423,20 @@ static int readAtoms(const char *path, int64_t size, ddcb200_deck *d, NameIdx *s
         {
             char *dt = NULL;
             odb_getString(hdb->obj[0], "datatype", &dt, "VARRECORDASCII");
+            if (strcmp(dt, "FIXRECORDBINARY") == 0)
+            {
+                /* the records start after the first blank line that follows the header (readPheader, src/pio.c:751-781) */
+                free(dt);
+                const char *q = p + 1;
+                const char *end = text + got;
+                while (q + 1 < end && !(q[0] == '\n' && q[1] == '\n')) q++;
+                int rcb = q + 2 <= end ? readAtomsBinary(path, (const unsigned char *)q + 2, (size_t)(end - (q + 2)), hdb->obj[0], size, d, sortedSpecies,
+                                                         nspecies, filled, randomMissing)
+                                       : herr("atoms file %s: no records after the header", path);
+                odb_free(hdb);
+                free(text);
+                return rcb;
+            }
             int bad = strcmp(dt, "VARRECORDASCII") != 0 && strcmp(dt, "FIXRECORDASCII") != 0;
             free(dt);
             char **fn;
@@ -606,6 +729,14 @@ int ddcb200_deckLoad(const char *objectFile, const char *restartFile, const char
         odb_getString(sim, "gidFormat", &gf, "decimal");
         d->gidFormatHex = strcasecmp(gf, "hex") == 0;
         free(gf);
+        char *cm = NULL;
+        odb_getString(sim, "checkpointmode", &cm, "ASCII");
+        d->checkpointBinary = strcasecmp(cm, "BINARY") == 0;
+        free(cm);
+        cm = NULL;
+        odb_getString(sim, "checkpointprecision", &cm, "FULL");
+        d->checkpointBrief = strcasecmp(cm, "BRIEF") == 0;
+        free(cm);
         odb_getInts(sim, "nLoopDigits", &d->nLoopDigits, 1, "8");
         if (d->nLoopDigits < 1 || d->nLoopDigits > 18) FAIL("SIMULATE nLoopDigits out of range");
         int64_t rid = 0;

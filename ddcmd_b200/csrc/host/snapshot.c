@@ -53,6 +53,18 @@ static char *pathJoin(const char *a, const char *b)
     return p;
 }
 
+/* bFieldSize / bFieldPack (src/ioUtils.c:183-204): big-endian integer fields of the binary records */
+static int bFieldSize(uint64_t i)
+{
+    int r = 0;
+    do { i /= 256; r++; } while (i > 0);
+    return r;
+}
+static void bFieldPack(unsigned char *buf, int size, uint64_t in)
+{
+    for (int k = 0; k < size; k++) { buf[(size - 1) - k] = (unsigned char)(in % 256); in /= 256; }
+}
+
 /* matinv of a diagonal box as src/three_algebra.c:37-64 evaluates it (cofactor / determinant): the factors Preduce uses */
 static void diagInverse(const double h[9], double hi[3])
 {
@@ -111,11 +123,32 @@ int ddcb200_writeRestart(const ddcb200_deck *d, const char *dirname, int64_t loo
     lrec += maxType - 1;
     lrec += maxName - 1;
     lrec += maxGroup - 1;
-    const int randomFieldSize = haveRandom ? 27 : 0;   /* strlen(lcg64_write(NULL)) = 16 + 1 + 1 + 1 + 8, src/lcg64.c:56-63 */
+    int randomFieldSize = haveRandom ? 27 : 0;   /* strlen(lcg64_write(NULL)) = 16 + 1 + 1 + 1 + 8, src/lcg64.c:56-63 */
     lrec += randomFieldSize + 1;
     /* FREE and LANGEVIN groups have no per-particle write (GROUPMAXWRITELENGTH = 0) */
     lrec++;
     lrec = 8 * ((lrec + 7) / 8);
+    /* binary records (collection_writeBLOCK_binary, src/collection_write.c:188-260): u4 crc | id | pinfo | 3 f8 | 3 f8 or f4 | LCG64 */
+    const int binary = d->checkpointBinary != 0;
+    int gidFieldSize = 1, pinfoFieldSize = 1, nTypes = 0;
+    const int vsize = d->checkpointBrief ? 4 : 8;
+    if (binary)
+    {
+        uint64_t gmax = 0;
+        for (int64_t i = 0; i < d->n; i++)
+            if (d->gid[i] > gmax) gmax = d->gid[i];
+        for (int s = 0; s < d->nspecies; s++)
+        {
+            int seen = 0;
+            for (int t = 0; t < s && !seen; t++) seen = strcmp(d->speciesType[t], d->speciesType[s]) == 0;
+            nTypes += !seen;
+        }
+        if (nTypes != 1) { herr("writeRestart: binary restarts need a single SPECIES type (found %d)", nTypes); free(dir); return -1; }
+        gidFieldSize = bFieldSize(gmax);                                                     /* bFieldSize(mpiMaxVal(label)) */
+        pinfoFieldSize = bFieldSize((uint64_t)nGroups * (uint64_t)d->nspecies * (uint64_t)nTypes);   /* pinfoMaxIndex */
+        randomFieldSize = haveRandom ? 16 : 0;                                               /* lcg64_bwrite, src/lcg64.c:75-84 */
+        lrec = 4 + gidFieldSize + pinfoFieldSize + 24 + 3 * vsize + randomFieldSize;
+    }
     if (lrec > MAXLREC) { herr("writeRestart: record length %d exceeds MAXLREC=%d", lrec, MAXLREC); free(dir); return -1; }
 
     const double cLen = hu_convert(1.0, NULL, "l"), cTime = hu_convert(1.0, NULL, "t"), cVel = cLen / cTime;
@@ -127,14 +160,24 @@ int ddcb200_writeRestart(const ddcb200_deck *d, const char *dirname, int64_t loo
         char stamp[64];
         snprintf(stamp, sizeof stamp, "%s", ctime(&now));
         stamp[strcspn(stamp, "\n")] = 0;
-        sbCat(&hb, "particle FILEHEADER {type=MULTILINE; datatype=FIXRECORDASCII; checksum=CRC32; create_time=%s; run_id=0x%08x;\n", stamp, d->runId);
+        sbCat(&hb, "particle FILEHEADER {type=MULTILINE; datatype=%s; checksum=CRC32; create_time=%s; run_id=0x%08x;\n",
+              binary ? "FIXRECORDBINARY" : "FIXRECORDASCII", stamp, d->runId);
         sbCat(&hb, "code_version=ddcmd_b200 (B200-native Martini step); srcpath=ddcmd_b200;\n");
         sbCat(&hb, "loop=%lld; time=%f fs;\n", (long long)loop, time_ * cTime);
-        sbCat(&hb, "nfiles=1; nrecord=%llu; lrec=%d; nfields=11; endian_key=%d;\n", (unsigned long long)d->n, lrec, 875770417);
-        sbCat(&hb, "field_names=checksum id class type group rx ry rz vx vy vz;\n");
-        sbCat(&hb, "field_types=u u s s s f f f f f f;\n");
-        sbCat(&hb, "field_units=1 1 1 1 1 Ang Ang Ang Ang/fs Ang/fs Ang/fs;\n");
-        sbCat(&hb, "field_format=%s;\n", fmt);
+        sbCat(&hb, "nfiles=1; nrecord=%llu; lrec=%d; nfields=%d; endian_key=%d;\n", (unsigned long long)d->n, lrec, binary ? 9 : 11, 875770417);
+        if (binary)
+        {
+            /* src/collection_write.c:207-225,255-256: " %.1s%1d" per field */
+            sbCat(&hb, "field_names=checksum id pinfo rx  ry  rz  vx  vy  vz;\n");
+            sbCat(&hb, "field_types= u4 b%d b%d f8 f8 f8 f%d f%d f%d;\n", gidFieldSize, pinfoFieldSize, vsize, vsize, vsize);
+        }
+        else
+        {
+            sbCat(&hb, "field_names=checksum id class type group rx ry rz vx vy vz;\n");
+            sbCat(&hb, "field_types=u u s s s f f f f f f;\n");
+            sbCat(&hb, "field_units=1 1 1 1 1 Ang Ang Ang Ang/fs Ang/fs Ang/fs;\n");
+            sbCat(&hb, "field_format=%s;\n", fmt);
+        }
         sbCat(&hb, "reducedcorner=%21.14f %21.14f %21.14f;\n", d->reducedCorner[0], d->reducedCorner[1], d->reducedCorner[2]);
         sbCat(&hb, "h=%21.14f %21.14f %21.14f\n", h[0] * cLen, h[1] * cLen, h[2] * cLen);
         sbCat(&hb, "  %21.14f %21.14f %21.14f\n", h[3] * cLen, h[4] * cLen, h[5] * cLen);
@@ -154,7 +197,6 @@ int ddcb200_writeRestart(const ddcb200_deck *d, const char *dirname, int64_t loo
         }
         sbCat(&hb, "; \n}\n \n\n");
     }
-    (void)nGroups;
 
     char *apath = pathJoin(dir, "atoms#000000");
     FILE *f = fopen(apath, "wb");
@@ -174,6 +216,34 @@ int ddcb200_writeRestart(const ddcb200_deck *d, const char *dirname, int64_t loo
         y += h[4] * -rint(hi[1] * y);
         z += h[8] * -rint(hi[2] * z);
         const int s = d->species[i];
+        if (binary)
+        {
+            unsigned char *b = (unsigned char *)line;
+            memset(b, 0, (size_t)lrec);
+            const int ig = (d->nGroups > 0 && d->groupOfBead) ? d->groupOfBead[i] : 0;
+            int o = 4;
+            bFieldPack(b + o, gidFieldSize, d->gid[i]);
+            o += gidFieldSize;
+            bFieldPack(b + o, pinfoFieldSize, (uint64_t)ig + (uint64_t)s * (uint64_t)nGroups);    /* pinfoEncode with one type */
+            o += pinfoFieldSize;
+            double f8[6] = {x * cLen, y * cLen, z * cLen, vx[i] * cVel, vy[i] * cVel, vz[i] * cVel};
+            memcpy(b + o, f8, 24);
+            o += 24;
+            if (vsize == 8) memcpy(b + o, f8 + 3, 24);
+            else
+                for (int k = 0; k < 3; k++) { float f4 = (float)f8[3 + k]; memcpy(b + o + 4 * k, &f4, 4); }
+            o += 3 * vsize;
+            if (haveRandom)
+            {
+                memcpy(b + o, &rngState[i], 8);
+                memcpy(b + o + 8, &d->rngMult[i], 4);
+                memcpy(b + o + 12, &d->rngPrime[i], 4);
+            }
+            const uint32_t crc = hcrc32(b + 4, (size_t)lrec - 4);
+            memcpy(b, &crc, 4);
+            if (fwrite(b, 1, (size_t)lrec, f) != (size_t)lrec) rc = herr("writeRestart: short write to %s", apath);
+            continue;
+        }
         const char *gname = (d->nGroups > 0 && d->groupOfBead) ? d->groupName[d->groupOfBead[i]] : (d->nGroups > 0 ? d->groupName[0] : "group");
         int length = snprintf(line, MAXLREC, fmt, 0u, (unsigned long)d->gid[i], d->speciesType[s], d->speciesName[s], gname,
                               x * cLen, y * cLen, z * cLen, vx[i] * cVel, vy[i] * cVel, vz[i] * cVel);

@@ -99,6 +99,9 @@ typedef struct ddcb200_deck
     char *printUnit[6];
     double printConvert[6];
     double reducedCorner[3];
+    /* SIMULATE checkpointmode = ASCII | BINARY, checkpointprecision = FULL | BRIEF (src/simulate.c:166-196): writeRestart
+     * writes FIXRECORDBINARY records (collection_writeBLOCK_binary, src/collection_write.c:188-336) when checkpointBinary */
+    int checkpointBinary, checkpointBrief;
 } ddcb200_deck;
 
 /* object_compilefile(object.data) + object_compilefile(restart) + the init chain.
@@ -127,7 +130,8 @@ int ddcb200_printinfoHeader(const ddcb200_deck *deck, char *buf, size_t len);
 
 /* One ddcMD-format snapshot: writeRestart (src/io.c:58-113) = CreateSnapshotdir (src/io.c:115-143) +
  * collection_writeBLOCK (src/collection_write.c:57-186: FIXRECORDASCII records with a CRC32 per record, pio FILEHEADER
- * of write_fileheader src/io.c:352-407) into <snapshotdir>/atoms#000000 + the `restart` object file (SIMULATE loop/time,
+ * of write_fileheader src/io.c:352-407; or collection_writeBLOCK_binary, :188-336, when the deck says
+ * checkpointmode=BINARY) into <snapshotdir>/atoms#000000 + the `restart` object file (SIMULATE loop/time,
  * BOX h, LANGEVIN groups' Teq, COLLECTION size/files), and the ./restart link when restartLink != 0.
  * dirname NULL = "snapshot.<loop>" under SIMULATE snapshotRootDir; paths are relative to the deck's directory.
  * State arrays are in the deck's bead order, internal units; rngState NULL = the deck's LCG64 states.

@@ -80,6 +80,21 @@ if __name__ == "__main__":
                                "first_records": body[first:first + 2 * lrec].decode(), "restart": open(os.path.join(d, snap, "restart")).read()}}
         shutil.rmtree(tmp)
 
+        # the same with SIMULATE checkpointmode=BINARY (collection_writeBLOCK_binary), full and brief precision
+        for mode in ("BINARY", "BRIEF"):
+            tmp = tempfile.mkdtemp(prefix="snap_")
+            d = stage(deck, variant, tmp)
+            p = os.path.join(d, "object.data")
+            text = open(p).read()
+            extra = "checkpointmode=BINARY;" + (" checkpointprecision=BRIEF;" if mode == "BRIEF" else "")
+            open(p, "w").write(re.sub(r"checkpointrate=\d+;", "checkpointrate=10; " + extra, text, count=1))
+            subprocess.check_call([REF, "readWrite"], cwd=d, stdout=open(os.path.join(d, "_rw.log"), "w"), stderr=subprocess.STDOUT)
+            snap = [x for x in os.listdir(d) if x.startswith("snapshot.0")][0]
+            raw = open(os.path.join(d, snap, "atoms#000000"), "rb").read()
+            k = raw.index(b"}")
+            gold[key]["loop0_" + mode.lower()] = {"header": raw[:k].decode(), "body_bytes": len(raw) - k, "body_sha256": hashlib.sha256(raw[k:]).hexdigest()}
+            shutil.rmtree(tmp)
+
         tmp = tempfile.mkdtemp(prefix="snap_")
         d = stage(deck, variant, tmp)
         run_deck_edit(d)

@@ -64,6 +64,55 @@ def test_writeRestart_matches_reference_bytes(golden_dir, gold, tmp_path, deck, 
     assert strip_ids(open(os.path.join(snap, "restart")).read()) == strip_ids(g["restart"])
 
 
+@pytest.mark.parametrize("deck,variant", CASES)
+@pytest.mark.parametrize("mode", ["binary", "brief"])
+def test_binary_restart_matches_reference_bytes(golden_dir, gold, tmp_path, deck, variant, mode):
+    """SIMULATE checkpointmode=BINARY (and checkpointprecision=BRIEF): FIXRECORDBINARY records of collection_writeBLOCK_binary."""
+    g = gold[deck + ("_" + variant if variant else "")]["loop0_" + mode]
+    d = stage(golden_dir, deck, variant, tmp_path)
+    p = os.path.join(d, "object.data")
+    extra = "checkpointmode=BINARY;" + (" checkpointprecision=BRIEF;" if mode == "brief" else "")
+    text = open(p).read()
+    open(p, "w").write(re.sub(r"checkpointrate=\d+;", "checkpointrate=10; " + extra, text, count=1))
+    dk = dd.Deck(p)
+    assert int(dk.s.checkpointBinary) == 1 and int(dk.s.checkpointBrief) == (mode == "brief")
+    snap = dk.writeRestart(restart_link=True)
+    raw = open(os.path.join(snap, "atoms#000000"), "rb").read()
+    k = raw.index(b"}")
+    assert len(raw) - k == g["body_bytes"] and hashlib.sha256(raw[k:]).hexdigest() == g["body_sha256"]
+    strip = lambda t: [re.sub(r"create_time=[^;]*;", "", x) for x in strip_ids(t).splitlines() if not x.startswith("code_version")]   # noqa: E731
+    assert strip(raw[:k].decode()) == strip(g["header"])
+    # and back through the reader: ids, species, groups and LCG64 states exactly; positions and velocities to the format's precision
+    d2 = dd.Deck(p)
+    assert np.array_equal(d2.array("gid"), dk.array("gid")) and np.array_equal(d2.array("species"), dk.array("species"))
+    assert np.array_equal(d2.array("groupOfBead"), dk.array("groupOfBead"))
+    if int(dk.s.haveRandom):
+        assert np.array_equal(d2.array("rngState"), dk.array("rngState")) and np.array_equal(d2.array("rngPrime"), dk.array("rngPrime"))
+    h = np.array(dk.s.params.h[:])[[0, 4, 8]]
+    for kx, a in zip(("rx", "ry", "rz"), h):
+        dx = d2.array(kx) - dk.array(kx)
+        dx -= a * np.rint(dx / a)
+        assert np.abs(dx).max() <= 1e-15 * a
+    vtol = 1e-7 if mode == "brief" else 1e-15
+    for kv in ("vx", "vy", "vz"):
+        assert np.abs(d2.array(kv) - dk.array(kv)).max() <= vtol * max(np.abs(dk.array(kv)).max(), 1e-30)
+
+
+def test_corrupt_binary_record_is_rejected(golden_dir, tmp_path):
+    d = stage(golden_dir, "popc_small", None, tmp_path)
+    p = os.path.join(d, "object.data")
+    text = open(p).read()
+    open(p, "w").write(re.sub(r"checkpointrate=\d+;", "checkpointrate=10; checkpointmode=BINARY;", text, count=1))
+    snap = dd.Deck(p).writeRestart(restart_link=True)
+    f = os.path.join(snap, "atoms#000000")
+    raw = bytearray(open(f, "rb").read())
+    k = raw.index(b"\n\n", raw.index(b"}")) + 2 + 7 * 75 + 30
+    raw[k] ^= 0x10
+    open(f, "wb").write(raw)
+    with pytest.raises(dd.DdcError, match="CRC32 mismatch in record 7"):
+        dd.Deck(p)
+
+
 def test_restart_round_trip_through_the_reader(golden_dir, tmp_path):
     """write -> read back through ddcb200_deckLoad (CRC32 records, hexadecimal ids, LCG64 fields)."""
     d = stage(golden_dir, "popc_small", "full", tmp_path)
@@ -104,11 +153,15 @@ def test_corrupt_record_is_rejected(golden_dir, tmp_path):
 
 
 @pytest.mark.skipif(not os.path.exists(REF), reason="oracle/_ref/ddcMD_ref not built")
-@pytest.mark.parametrize("deck,variant", [("popc_small", "full"), ("waterbox", None)])
-def test_reference_reads_our_snapshot(golden_dir, tmp_path, deck, variant):
+@pytest.mark.parametrize("deck,variant,binary", [("popc_small", "full", False), ("waterbox", None, False), ("popc_small", "full", True)])
+def test_reference_reads_our_snapshot(golden_dir, tmp_path, deck, variant, binary):
     """Drop-in check in the other direction: the unmodified reference starts from a restart written here (perturbed state,
     loop 40) and its own readWrite pass re-writes exactly the records it was given."""
     d = stage(golden_dir, deck, variant, tmp_path)
+    if binary:
+        p = os.path.join(d, "object.data")
+        text = open(p).read()
+        open(p, "w").write(re.sub(r"checkpointrate=\d+;", "checkpointrate=10; checkpointmode=BINARY;", text, count=1))
     dk = dd.Deck(os.path.join(d, "object.data"))
     rng = np.random.default_rng(7)
     st = {k: dk.array(k) * (1.0 + 1e-4 * rng.standard_normal(dk.n)) for k in ("rx", "ry", "rz", "vx", "vy", "vz")}
@@ -124,8 +177,26 @@ def test_reference_reads_our_snapshot(golden_dir, tmp_path, deck, variant):
     r = subprocess.run([REF, "readWrite"], cwd=d, capture_output=True, text=True, timeout=300)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
     _, theirs = split_atoms(os.path.join(snap, "atoms#000000"))
-    assert theirs == ours
     assert "loop=40;" in open(os.path.join(snap, "restart")).read()
+    if not binary:
+        assert theirs == ours
+        return
+    # binary fields carry all 53 bits, so the reference's internal-units round trip (x * l_in * l_out) may move a last bit:
+    # same record count and layout, ids / species / LCG64 states identical, coordinates to 4 ulp
+    assert len(theirs) == len(ours)
+    os.unlink(os.path.join(d, "restart"))
+    os.symlink("./snapshot.000000000040/restart", os.path.join(d, "restart"))
+    back = dd.Deck(os.path.join(d, "object.data"))
+    assert int(back.s.loop) == 40
+    assert np.array_equal(back.array("gid"), dk.array("gid")) and np.array_equal(back.array("species"), dk.array("species"))
+    assert np.array_equal(back.array("rngState"), dk.array("rngState"))
+    h = np.array(dk.s.params.h[:])[[0, 4, 8]]
+    for k, a in zip(("rx", "ry", "rz"), h):
+        dx = back.array(k) - st[k]
+        dx -= a * np.rint(dx / a)
+        assert np.abs(dx).max() <= 1e-15 * a
+    for k in ("vx", "vy", "vz"):
+        assert np.abs(back.array(k) - st[k]).max() <= 1e-15 * np.abs(st[k]).max()
 
 
 def test_readCMDS(tmp_path):
