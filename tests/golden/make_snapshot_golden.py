@@ -26,7 +26,7 @@ sys.path.insert(0, os.path.join(ROOT, "tests"))
 import nglfc_decks  # noqa: E402
 
 REF = os.path.join(ROOT, "oracle", "_ref", "ddcMD_ref")
-CASES = [("waterbox", None), ("popc_small", None), ("popc_small", "full"), ("ras_small", "full")]
+CASES = [("waterbox", None), ("waterbox", "full"), ("popc_small", None), ("popc_small", "full"), ("ras_small", "full")]
 
 
 def stage(deck, variant, tmp):

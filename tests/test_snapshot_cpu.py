@@ -19,7 +19,7 @@ import nglfc_decks
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 REF = os.path.join(ROOT, "oracle", "_ref", "ddcMD_ref")
-CASES = [("waterbox", None), ("popc_small", None), ("popc_small", "full"), ("ras_small", "full")]
+CASES = [("waterbox", None), ("waterbox", "full"), ("popc_small", None), ("popc_small", "full"), ("ras_small", "full")]
 WRITER_LINES = ("create_time", "code_version")     # header lines that name the writer
 
 

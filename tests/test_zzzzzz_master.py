@@ -104,6 +104,7 @@ def check_master(golden_dir, deck, variant, tmp_path):
     assert np.all(np.abs(a[1:4] - b[1:4]) <= 1e-9 * max(abs(b[1]), abs(b[2])))
 
 
-@pytest.mark.parametrize("deck,variant", [("popc_small", None), ("popc_small", "full"), ("ras_small", "full"), ("waterbox", None)])
+# ("waterbox", "full") is the configuration the reference ships in examples/waterbox (NGLFCONSTRAINT + LANGEVIN groups + barostat)
+@pytest.mark.parametrize("deck,variant", [("popc_small", None), ("popc_small", "full"), ("ras_small", "full"), ("waterbox", None), ("waterbox", "full")])
 def test_simulateMaster_matches_reference_run(golden_dir, tmp_path, deck, variant):
     check_master(golden_dir, deck, variant, tmp_path)
