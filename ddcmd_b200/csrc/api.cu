@@ -163,7 +163,7 @@ static int setupBox(ddcb200_ctx *c)
     }
     // ordering bins (not part of parity): edges relative to cutoff and skin
     {
-        const double f[NBINS - 1] = {-0.25, -0.125, 0.0, 0.125, 0.25, 0.375, 0.625};
+        const double *f = c->binFrac;
         for (int k = 0; k < NBINS - 1; k++)
         {
             const double r = p.rmax + f[k] * p.deltaR;
@@ -201,6 +201,30 @@ extern "C" int ddcb200_create(const ddcb200_params *p, ddcb200_ctx **out)
     c->prm = *p;
     c->device = p->device;
     c->numSM = prop.multiProcessorCount;
+    if (const char *be = getenv("DDCB200_BIN_EDGES"))
+    {
+        // tuning knob: the NBINS-1 ascending edges of the row-ordering bins as fractions of deltaR around the cutoff
+        // (equal values merge bins).  Any choice gives the same pair set; only the order of the entries in a row changes.
+        double v[NBINS - 1];
+        int n = 0;
+        const char *q = be;
+        while (n < NBINS - 1)
+        {
+            char *end;
+            v[n] = strtod(q, &end);
+            if (end == q) break;
+            n++;
+            q = (*end == ',') ? end + 1 : end;
+        }
+        bool ok = n == NBINS - 1;
+        for (int k = 0; ok && k < NBINS - 1; k++) ok = v[k] > -1.0 && v[k] <= 1.0 && (k == 0 || v[k] >= v[k - 1]);
+        if (!ok)
+        {
+            delete c;
+            return fail(DDCB200_ERR_ARG, "DDCB200_BIN_EDGES needs 7 ascending fractions of deltaR in (-1, 1]");
+        }
+        for (int k = 0; k < NBINS - 1; k++) c->binFrac[k] = v[k];
+    }
     int rc = setupBox(c);
     if (rc != DDCB200_OK)
     {

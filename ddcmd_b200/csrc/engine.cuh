@@ -184,6 +184,7 @@ struct ddcb200_ctx
     // list-build variant: 0 = auto (the first four rebuilds alternate between the two builds under CUDA events, then the
     // faster is kept; both write bit-identical rows), 1 = two-pass (k_nbr_filter + k_nbr_exact), 2 = one-pass (k_nbr_cell).
     // DDCB200_LISTBUILD=auto|twopass|cell
+    double binFrac[NBINS - 1] = {-0.25, -0.125, 0.0, 0.125, 0.25, 0.375, 0.625};   // ordering-bin edges, fractions of deltaR (DDCB200_BIN_EDGES)
     int listBuildMode = 0;
     int listBuildsTimed = 0;
     float listBuildMs[2] = {0.f, 0.f};

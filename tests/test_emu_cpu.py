@@ -55,6 +55,10 @@ def test_emu_list_builds_agree(emu, golden_dir, name, monkeypatch):
     tg.test_list_builds_agree_bit_for_bit(golden_dir, name, monkeypatch)
 
 
+def test_emu_bin_edges_knob(emu, golden_dir, monkeypatch):
+    tg.test_bin_edges_knob_keeps_the_pair_set(golden_dir, monkeypatch)
+
+
 @pytest.mark.parametrize("name", SMALL)
 def test_emu_trajectory_40_steps(emu, golden_dir, name):
     tg.test_trajectory_40_steps(golden_dir, name)

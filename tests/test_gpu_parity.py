@@ -184,3 +184,30 @@ def test_two_gpus_match_reference(name):
            "--master-port", "29533", os.path.join(root, "tests", "mgpu_worker.py"), name]
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
     assert r.returncode == 0 and "MGPU_OK" in r.stdout, r.stdout[-3000:] + r.stderr[-6000:]
+
+
+def test_bin_edges_knob_keeps_the_pair_set(golden_dir, monkeypatch):
+    """DDCB200_BIN_EDGES only reorders the entries of a row (here: two bins instead of eight): same pairs, forces to rounding."""
+    sim, ref = _load(golden_dir, "popc_small")
+    sim.ddcenergy(1)
+    a = sim.getState()
+    pa = sim.getPairs()
+    sim.close()
+    monkeypatch.setenv("DDCB200_BIN_EDGES", "-0.25,-0.25,-0.25,0.25,0.25,0.25,0.25")
+    sim, _ = _load(golden_dir, "popc_small")
+    sim.ddcenergy(1)
+    b = sim.getState()
+    pb = sim.getPairs()
+    assert _force_err(b, ref, "s0_") < F_TOL
+    assert np.array_equal(np.sort(_pairkey(pa[0], pa[1])), np.sort(_pairkey(pb[0], pb[1])))
+    assert not np.array_equal(pa[1], pb[1])              # the rows really are in a different order
+    assert np.abs(a["fx"] - b["fx"]).max() <= 1e-10 * np.abs(a["fx"]).max()
+    sim.nglf(25)                                         # displacement-bounded walk across a rebuild with the merged bins
+    tr = ref["trace"].reshape(-1, 16)
+    e = sim.energyInfo()
+    etot = tr[24, 1] + tr[24, 2]
+    assert abs((e.eion + e.rk) - etot) <= 1e-9 * max(abs(etot), abs(tr[24, 2]))
+    sim.close()
+    monkeypatch.setenv("DDCB200_BIN_EDGES", "0.5,0.1")
+    with pytest.raises(dd.DdcError):
+        _load(golden_dir, "popc_small")
