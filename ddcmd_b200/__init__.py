@@ -373,9 +373,14 @@ class Simulate:
         self._ck(lib().ddcb200_getLocalBeads(self.ctx, bead.ctypes.data_as(_P(C.c_int))))
         return bead
 
-    def getState(self):
+    def getState(self, out=None):
+        """rx ry rz vx vy vz fx fy fz of the local beads; `out` = a caller-owned C-contiguous float64 array of shape (9, numLocal),
+        e.g. a view of pinned memory, to copy into instead of a fresh (pageable) array."""
         n = int(lib().ddcb200_numLocal(self.ctx))
-        out = np.empty((9, n), np.float64)
+        if out is None:
+            out = np.empty((9, n), np.float64)
+        elif out.shape != (9, n) or out.dtype != np.float64 or not out.flags["C_CONTIGUOUS"]:
+            raise DdcError("getState: out must be a C-contiguous float64 array of shape (9, %d)" % n)
         pd = _P(C.c_double)
         self._ck(lib().ddcb200_getState(self.ctx, *[out[k].ctypes.data_as(pd) for k in range(9)]))
         return dict(zip(("rx", "ry", "rz", "vx", "vy", "vz", "fx", "fy", "fz"), out))
