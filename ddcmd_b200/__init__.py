@@ -70,7 +70,8 @@ class DeckStruct(C.Structure):
                 ("runDir", C.c_char_p), ("simulateName", C.c_char_p), ("boxName", C.c_char_p), ("collectionName", C.c_char_p),
                 ("atomsdir", C.c_char_p), ("nLoopDigits", C.c_int), ("gidFormatHex", C.c_int), ("runId", C.c_uint),
                 ("speciesType", _P(C.c_char_p)), ("printUnit", C.c_char_p * 6), ("printConvert", C.c_double * 6),
-                ("reducedCorner", C.c_double * 3), ("checkpointBinary", C.c_int), ("checkpointBrief", C.c_int)]
+                ("reducedCorner", C.c_double * 3), ("checkpointBinary", C.c_int), ("checkpointBrief", C.c_int),
+                ("nSubsets", C.c_int), ("subsets", C.c_void_p)]
 
 
 class DdcError(RuntimeError):
@@ -163,6 +164,7 @@ def _declare(L):
         "ddcb200_printinfoHeader": (i32, [_P(DeckStruct), C.c_char_p, C.c_size_t]),
         "ddcb200_writeRestart": (i32, [_P(DeckStruct), C.c_char_p, i64, dbl, pd, pd, pd, pd, pd, pd, pd, _P(C.c_uint64), i32, C.c_char_p, C.c_size_t]),
         "ddcb200_readCMDS": (i32, [C.c_char_p]),
+        "ddcb200_subsetWrite": (i64, [_P(DeckStruct), i32, C.c_char_p, i64, dbl, pd, pd, pd, pd, pd, pd, pd]),
         "ddcb200_simulateMaster": (i32, [C.c_char_p, C.c_char_p, C.c_char_p, i32]),
     }
     for name, (res, args) in sig.items():
@@ -180,7 +182,7 @@ EXPORTS = ["ddcb200_lastError", "ddcb200_deviceCount", "ddcb200_create", "ddcb20
            "ddcb200_nglfconstraintParms", "ddcb200_nglfconstraint", "ddcb200_getBox", "ddcb200_constraintFailures", "ddcb200_getCells", "ddcb200_getPairs", "ddcb200_profile",
            "ddcb200_profileRead", "ddcb200_timerRecord", "ddcb200_timerElapsed", "ddcb200_kernelLaunches", "ddcb200_lastListBuild", "ddcb200_ncclUniqueId", "ddcb200_ddcInit", "ddcb200_ddcPlan", "ddcb200_deckLoad", "ddcb200_deckFree",
            "ddcb200_lastHostError", "ddcb200_simulateBind", "ddcb200_simulateBindRank", "ddcb200_printinfoLine", "ddcb200_unitsConvert",
-           "ddcb200_printinfoHeader", "ddcb200_writeRestart", "ddcb200_readCMDS", "ddcb200_simulateMaster", "ddcb200_listBuildInfo"]
+           "ddcb200_printinfoHeader", "ddcb200_writeRestart", "ddcb200_readCMDS", "ddcb200_simulateMaster", "ddcb200_listBuildInfo", "ddcb200_subsetWrite"]
 
 
 def _arr(ptr, n, dtype):

@@ -14,6 +14,7 @@
 #include "host.h"
 #include "../../../include/ddcmd_b200_host.h"
 #include <ctype.h>
+#include <float.h>
 #include <math.h>
 #include <stdarg.h>
 #include <stdio.h>
@@ -666,6 +667,12 @@ void ddcb200_deckFree(ddcb200_deck *d)
     free(d->groupName); free(d->groupType); free(d->groupTeq); free(d->groupTau); free(d->groupVcm); free(d->groupOfBead);
     free(d->rngState); free(d->rngMult); free(d->rngPrime);
     free(d->consAtomOffset); free(d->consPairOffset); free(d->consAtomBead); free(d->consPairA); free(d->consPairB); free(d->consPairDist);
+    for (int a = 0; a < d->nSubsets; a++)
+    {
+        ddcb200_subset *q = &d->subsets[a];
+        free(q->name); free(q->filename); free(q->lengthUnit); free(q->parmsInfo); free(q->idList); free(q->includeSpecies);
+    }
+    free(d->subsets);
     free(d->runDir); free(d->simulateName); free(d->boxName); free(d->collectionName); free(d->atomsdir);
     if (d->speciesType)
         for (int i = 0; i < d->nspecies; i++) free(d->speciesType[i]);
@@ -1363,6 +1370,106 @@ int ddcb200_deckLoad(const char *objectFile, const char *restartFile, const char
 
     d->kB = hu_kB();
     d->ke = hu_ke();
+    /* ANALYSIS objects named by SIMULATE analysis (src/simulate.c:264-271, src/analysis.c:142-176): subsetWrite only */
+    {
+        char **an;
+        const int na = odb_getStrings(sim, "analysis", &an, NULL);
+        if (na > 0) d->subsets = (ddcb200_subset *)calloc((size_t)na, sizeof(ddcb200_subset));
+        for (int a = 0; a < na; a++)
+        {
+            const ODB_OBJECT *ao = odb_find(db, an[a], "ANALYSIS");
+            if (!ao) { herr("ANALYSIS %s not found", an[a]); odb_freeStrings(an, na); rc = -1; goto done; }
+            char *type = NULL, *fmt = NULL;
+            odb_getString(ao, "type", &type, "NONE");
+            odb_getString(ao, "format", &fmt, "pio");
+            const int isSubset = strcasecmp(type, "subsetWrite") == 0 || strcasecmp(type, "subset_write") == 0;
+            if (!isSubset || strcmp(fmt, "binaryCharmm") != 0)
+            {
+                herr("ANALYSIS %s: only type = subsetWrite with format = binaryCharmm is supported (type %s, format %s)", an[a], type, fmt);
+                free(type); free(fmt); odb_freeStrings(an, na);
+                rc = -1;
+                goto done;
+            }
+            free(type); free(fmt);
+            ddcb200_subset *q = &d->subsets[d->nSubsets++];
+            q->name = strdup(an[a]);
+            odb_getInts(ao, "eval_rate", &q->evalRate, 1, "0");
+            odb_getInts(ao, "outputrate", &q->outputRate, 1, "0");
+            odb_getInts(ao, "modulus", &q->modulus, 1, "1");
+            odb_getInts(ao, "odd", &q->odd, 1, "0");
+            odb_getString(ao, "filename", &q->filename, "subset");
+            odb_getString(ao, "lengthUnit", &q->lengthUnit, "Ang");
+            char **t;
+            int nt = odb_getStrings(ao, "idmin", &t, "0");
+            q->idMin = nt > 0 ? strtoull(t[0], NULL, 0) : 0;
+            odb_freeStrings(t, nt);
+            nt = odb_getStrings(ao, "idmax", &t, "18446744073709551614");      /* gid_max */
+            q->idMax = nt > 0 ? strtoull(t[0], NULL, 0) : 18446744073709551614ull;
+            odb_freeStrings(t, nt);
+            nt = odb_getStrings(ao, "idList", &t, NULL);
+            q->nIdList = nt > 0 ? nt : 0;
+            if (nt > 0)
+            {
+                q->idList = (uint64_t *)malloc(sizeof(uint64_t) * (size_t)nt);
+                for (int k = 0; k < nt; k++) q->idList[k] = strtoull(t[k], NULL, 0);
+                for (int k = 1; k < nt; k++)               /* insertion sort: the lists are short */
+                {
+                    uint64_t v = q->idList[k];
+                    int m = k - 1;
+                    while (m >= 0 && q->idList[m] > v) { q->idList[m + 1] = q->idList[m]; m--; }
+                    q->idList[m + 1] = v;
+                }
+            }
+            odb_freeStrings(t, nt);
+            q->includeSpecies = (int *)malloc(sizeof(int) * (size_t)(d->nspecies + 1));
+            nt = odb_getStrings(ao, "species", &t, NULL);
+            for (int k = 0; k < d->nspecies; k++) q->includeSpecies[k] = nt > 0 ? 0 : 1;
+            for (int k = 0; k < nt; k++)
+            {
+                int hit = -1;
+                for (int sidx = 0; sidx < d->nspecies; sidx++)
+                    if (strcmp(d->speciesName[sidx], t[k]) == 0) hit = sidx;
+                if (hit < 0) { herr("ANALYSIS %s: unknown species %s", an[a], t[k]); odb_freeStrings(t, nt); odb_freeStrings(an, na); rc = -1; goto done; }
+                q->includeSpecies[hit] = 1;
+            }
+            odb_freeStrings(t, nt);
+            /* bounds: defaults are -/+ the longest box edge, printed with %e as the reference does (src/subsetWrite.c:119-139) */
+            double maxSize = fmax(fabs(d->params.h[0]), fmax(fabs(d->params.h[4]), fabs(d->params.h[8])));
+            maxSize = hu_convert(maxSize, NULL, "l");
+            char lo[32], hi[32], vlo[32], vhi[32];
+            snprintf(lo, sizeof lo, "%e", -maxSize);
+            snprintf(hi, sizeof hi, "%e", maxSize);
+            snprintf(vlo, sizeof vlo, "%e", -DBL_MAX);
+            snprintf(vhi, sizeof vhi, "%e", DBL_MAX);
+            static const char *ax[3] = {"x", "y", "z"};
+            int bad = 0;
+            for (int k = 0; k < 3; k++)
+            {
+                char key[16];
+                snprintf(key, sizeof key, "%smin", ax[k]);
+                bad |= odb_getWithUnits(ao, key, &q->lo[k], 1, lo, "l", NULL) < 0;
+                snprintf(key, sizeof key, "%smax", ax[k]);
+                bad |= odb_getWithUnits(ao, key, &q->hi[k], 1, hi, "l", NULL) < 0;
+                snprintf(key, sizeof key, "v%smin", ax[k]);
+                bad |= odb_getWithUnits(ao, key, &q->vlo[k], 1, vlo, "l/t", NULL) < 0;
+                snprintf(key, sizeof key, "v%smax", ax[k]);
+                bad |= odb_getWithUnits(ao, key, &q->vhi[k], 1, vhi, "l/t", NULL) < 0;
+            }
+            if (bad) { herr("ANALYSIS %s: bad unit in a bound", an[a]); odb_freeStrings(an, na); rc = -1; goto done; }
+            if (hu_convert(1.0, NULL, q->lengthUnit) != hu_convert(1.0, NULL, q->lengthUnit)) { herr("ANALYSIS %s: lengthUnit %s is not a unit", an[a], q->lengthUnit); odb_freeStrings(an, na); rc = -1; goto done; }
+            const double lcv = hu_convert(1.0, NULL, "Angstrom"), vcv = hu_convert(1.0, NULL, "Angstrom/fs");
+            char info[1024];
+            snprintf(info, sizeof info, "idmin = %llu; idmax = %llu; modulus = %d; odd = %d;\n"
+                     "xmin = %f Ang; xmax = %f Ang;\nymin = %f Ang; ymax = %f Ang;\nzmin = %f Ang; zmax = %f Ang;\n"
+                     "vxmin = %f Ang/fs; vxmax = %f Ang/fs;\nvymin = %f Ang/fs; vymax = %f Ang/fs;\nvzmin = %f Ang/fs; vzmax = %f Ang/fs;\n",
+                     (unsigned long long)q->idMin, (unsigned long long)q->idMax, q->modulus, q->odd,
+                     q->lo[0] * lcv, q->hi[0] * lcv, q->lo[1] * lcv, q->hi[1] * lcv, q->lo[2] * lcv, q->hi[2] * lcv,
+                     q->vlo[0] * vcv, q->vhi[0] * vcv, q->vlo[1] * vcv, q->vhi[1] * vcv, q->vlo[2] * vcv, q->vhi[2] * vcv);
+            q->parmsInfo = strdup(info);
+            if (q->modulus < 1) { herr("ANALYSIS %s: modulus must be >= 1", an[a]); odb_freeStrings(an, na); rc = -1; goto done; }
+        }
+        odb_freeStrings(an, na);
+    }
     d->lengthPerAngstrom = hu_convert(1.0, "Angstrom", NULL);
     d->energyPerKJmol = hu_convert(1.0, "kJ/mol", NULL);
     d->massPerAmu = hu_convert(1.0, "amu", NULL);

@@ -290,6 +290,109 @@ int ddcb200_writeRestart(const ddcb200_deck *d, const char *dirname, int64_t loo
     return rc;
 }
 
+int64_t ddcb200_subsetWrite(const ddcb200_deck *d, int which, const char *dirname, int64_t loop, double time_, const double h[9],
+                            const double *rx, const double *ry, const double *rz, const double *vx, const double *vy, const double *vz)
+{
+    if (!d || !h || !rx || !ry || !rz || !vx || !vy || !vz) return herr("subsetWrite: null argument");
+    if (which < 0 || which >= d->nSubsets) return herr("subsetWrite: no such ANALYSIS (%d of %d)", which, d->nSubsets);
+    const ddcb200_subset *q = &d->subsets[which];
+    /* CreateSnapshotdir(simulate, NULL) + "<snapshotdir>/<filename>" (src/subsetWrite.c:441-444) */
+    char rel[1024], loopFmt[16];
+    snprintf(loopFmt, sizeof loopFmt, "%%%d.%dllu", d->nLoopDigits, d->nLoopDigits);
+    int k = (dirname && dirname[0] == '/') ? 0 : snprintf(rel, sizeof rel, "%s/", d->atomsdir);
+    if (dirname) snprintf(rel + k, sizeof rel - (size_t)k, "%s", dirname);
+    else
+    {
+        k += snprintf(rel + k, sizeof rel - (size_t)k, "snapshot.");
+        snprintf(rel + k, sizeof rel - (size_t)k, loopFmt, (unsigned long long)loop);
+    }
+    char *dir = pathJoin(d->runDir, rel);
+    if (mkdir(dir, 0777) != 0 && errno != EEXIST) { herr("subsetWrite: cannot create %s: %s", dir, strerror(errno)); free(dir); return -1; }
+    char fname[300];
+    snprintf(fname, sizeof fname, "%s#000000", q->filename);
+    char *path = pathJoin(dir, fname);
+    free(dir);
+
+    /* rejectParticle (src/subsetWrite.c:532-564) on the positions as they are in the state (the integrator keeps them in the box) */
+    const int nGroups = d->nGroups > 0 ? d->nGroups : 1;
+    unsigned char *keep = (unsigned char *)malloc((size_t)d->n + 1);
+    int64_t nrec = 0;
+    for (int64_t i = 0; i < d->n; i++)
+    {
+        const uint64_t gid = d->gid[i];
+        int rej = gid < q->idMin || gid > q->idMax || (gid % (uint64_t)q->modulus) != 0 || (q->odd && gid % 2 == 0) ||
+                  rx[i] > q->hi[0] || ry[i] > q->hi[1] || rz[i] > q->hi[2] || rx[i] < q->lo[0] || ry[i] < q->lo[1] || rz[i] < q->lo[2] ||
+                  vx[i] > q->vhi[0] || vy[i] > q->vhi[1] || vz[i] > q->vhi[2] || vx[i] < q->vlo[0] || vy[i] < q->vlo[1] || vz[i] < q->vlo[2] ||
+                  q->includeSpecies[d->species[i]] == 0;
+        if (!rej && q->idList)
+        {
+            int64_t lo = 0, hi = q->nIdList;
+            while (lo < hi)
+            {
+                const int64_t mid = (lo + hi) / 2;
+                if (q->idList[mid] < gid) lo = mid + 1;
+                else hi = mid;
+            }
+            rej = !(lo < q->nIdList && q->idList[lo] == gid);
+        }
+        keep[i] = (unsigned char)!rej;
+        nrec += !rej;
+    }
+    const double cLen = hu_convert(1.0, NULL, "l"), cTime = hu_convert(1.0, NULL, "t");
+    SBuf hb = {0};
+    time_t now = time(NULL);
+    char stamp[64];
+    snprintf(stamp, sizeof stamp, "%s", ctime(&now));
+    stamp[strcspn(stamp, "\n")] = 0;
+    sbCat(&hb, "subset FILEHEADER {type=MULTILINE; datatype=FIXRECORDBINARY; checksum=NONE; create_time=%s; run_id=0x%08x;\n", stamp, d->runId);
+    sbCat(&hb, "code_version=ddcmd_b200 (B200-native Martini step); srcpath=ddcmd_b200;\n");
+    sbCat(&hb, "loop=%lld; time=%f fs;\n", (long long)loop, time_ * cTime);
+    sbCat(&hb, "nfiles=1; nrecord=%llu; lrec=24; nfields=5; endian_key=%d;\n", (unsigned long long)nrec, 875770417);
+    sbCat(&hb, "field_names=id pinfo rx ry  rz;\nfield_types= u8 u4 f4 f4 f4;\nfield_units=1 1 %s %s %s;\n", q->lengthUnit, q->lengthUnit, q->lengthUnit);
+    sbCat(&hb, "reducedcorner=%21.14f %21.14f %21.14f;\n", d->reducedCorner[0], d->reducedCorner[1], d->reducedCorner[2]);
+    sbCat(&hb, "h=%21.14f %21.14f %21.14f\n", h[0] * cLen, h[1] * cLen, h[2] * cLen);
+    sbCat(&hb, "  %21.14f %21.14f %21.14f\n", h[3] * cLen, h[4] * cLen, h[5] * cLen);
+    sbCat(&hb, "  %21.14f %21.14f %21.14f Ang;\n", h[6] * cLen, h[7] * cLen, h[8] * cLen);
+    sbCat(&hb, "random = NONE;\n nrandomFieldSize = 0;\n types = ");
+    for (int s = 0; s < d->nspecies; s++)
+    {
+        int seen = 0;
+        for (int t = 0; t < s && !seen; t++) seen = strcmp(d->speciesType[t], d->speciesType[s]) == 0;
+        if (!seen) sbCat(&hb, "%s ", d->speciesType[s]);
+    }
+    sbCat(&hb, ";\n groups = ");
+    if (d->nGroups > 0) for (int g = 0; g < d->nGroups; g++) sbCat(&hb, "%s ", d->groupName[g]);
+    else sbCat(&hb, "group ");
+    sbCat(&hb, ";\n species = ");
+    for (int s = 0; s < d->nspecies; s++) sbCat(&hb, "%s ", d->speciesName[s]);
+    sbCat(&hb, ";\n %s \n}\n \n\n", q->parmsInfo);
+    FILE *f = fopen(path, "wb");
+    if (!f) { herr("subsetWrite: cannot open %s: %s", path, strerror(errno)); free(path); free(keep); free(hb.p); return -1; }
+    fwrite(hb.p, 1, hb.n, f);
+    free(hb.p);
+    /* box corner = h * reducedcorner (src/box.c:46); positions relative to it, in lengthUnit, as floats */
+    const double corner[3] = {h[0] * d->reducedCorner[0], h[4] * d->reducedCorner[1], h[8] * d->reducedCorner[2]};
+    const double cL = hu_convert(1.0, NULL, q->lengthUnit);
+    int64_t rc = nrec;
+    for (int64_t i = 0; i < d->n; i++)
+    {
+        if (!keep[i]) continue;
+        unsigned char line[24];
+        const uint64_t gid = d->gid[i];
+        const int ig = (d->nGroups > 0 && d->groupOfBead) ? d->groupOfBead[i] : 0;
+        const uint32_t index = (uint32_t)ig + (uint32_t)d->species[i] * (uint32_t)nGroups;     /* pinfoEncode, one type */
+        const float f4[3] = {(float)((rx[i] - corner[0]) * cL), (float)((ry[i] - corner[1]) * cL), (float)((rz[i] - corner[2]) * cL)};
+        memcpy(line, &gid, 8);
+        memcpy(line + 8, &index, 4);
+        memcpy(line + 12, f4, 12);
+        if (fwrite(line, 1, 24, f) != 24) { rc = herr("subsetWrite: short write to %s", path); break; }
+    }
+    fclose(f);
+    free(path);
+    free(keep);
+    return rc;
+}
+
 int ddcb200_readCMDS(const char *filename)
 {
     int flag = 0;
@@ -323,7 +426,11 @@ static int64_t findEndLoop(const ddcb200_deck *d, int64_t loop, int64_t maxloop)
 {
     /* the next loop at which something is printed or written (src/masters.c:263-281) */
     for (int64_t l = loop + 1; l < maxloop; l++)
+    {
         if (TEST0(l, d->printrate) || TEST0(l, d->snapshotrate) || TEST0(l, d->checkpointrate)) return l;
+        for (int a = 0; a < d->nSubsets; a++)
+            if (TEST0(l, d->subsets[a].evalRate) || TEST0(l, d->subsets[a].outputRate)) return l;
+    }
     return maxloop;
 }
 
@@ -402,6 +509,18 @@ int ddcb200_simulateMaster(const char *objectFile, const char *restartFile, cons
         }
         if (TEST0(loop, d->checkpointrate) || (flag & DDCB200_CMD_CHECKPOINT))
             if ((rc = checkpoint(d, c, &hs, &e)) != 0) break;
+        /* doAnalysis (src/masters.c:295-302) */
+        int fetched = 0;
+        for (int a = 0; a < d->nSubsets && rc == 0; a++)
+        {
+            if (!(TEST0(loop, d->subsets[a].outputRate) || (flag & DDCB200_CMD_DO_ANALYSIS))) continue;
+            double hh[9];
+            if (!fetched && ddcb200_getState(c, hs.r[0], hs.r[1], hs.r[2], hs.r[3], hs.r[4], hs.r[5], NULL, NULL, NULL)) { rc = herr("getState: %s", ddcb200_lastError()); break; }
+            fetched = 1;
+            if (ddcb200_getBox(c, hh)) { rc = herr("getBox: %s", ddcb200_lastError()); break; }
+            if (ddcb200_subsetWrite(d, a, NULL, e.loop, e.time, hh, hs.r[0], hs.r[1], hs.r[2], hs.r[3], hs.r[4], hs.r[5]) < 0) rc = -1;
+        }
+        if (rc) break;
         if (flag & DDCB200_CMD_STOP) break;
     }
     if (rc == 0 && !TEST0(loop, d->printrate)) PRINTLINE();

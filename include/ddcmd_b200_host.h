@@ -16,6 +16,19 @@
 extern "C" {
 #endif
 
+/* ANALYSIS type = subsetWrite (src/subsetWrite.c:62-168): which beads go into the periodic subset files */
+typedef struct ddcb200_subset
+{
+    char *name, *filename, *lengthUnit, *parmsInfo;
+    int evalRate, outputRate;            /* ANALYSIS eval_rate / outputrate (src/analysis.c:152-153) */
+    int modulus, odd;
+    uint64_t idMin, idMax;
+    int64_t nIdList;
+    uint64_t *idList;                    /* sorted */
+    double lo[3], hi[3], vlo[3], vhi[3]; /* internal units */
+    int *includeSpecies;                 /* per SPECIES index */
+} ddcb200_subset;
+
 typedef struct ddcb200_deck
 {
     /* SIMULATE (src/simulate.c:151-169) */
@@ -102,6 +115,10 @@ typedef struct ddcb200_deck
     /* SIMULATE checkpointmode = ASCII | BINARY, checkpointprecision = FULL | BRIEF (src/simulate.c:166-196): writeRestart
      * writes FIXRECORDBINARY records (collection_writeBLOCK_binary, src/collection_write.c:188-336) when checkpointBinary */
     int checkpointBinary, checkpointBrief;
+    /* SIMULATE analysis = ... : the ANALYSIS objects of type subsetWrite with format = binaryCharmm (the positions feed of the
+     * MuMMI workflow); any other ANALYSIS type or format is an error at load time */
+    int nSubsets;
+    ddcb200_subset *subsets;
 } ddcb200_deck;
 
 /* object_compilefile(object.data) + object_compilefile(restart) + the init chain.
@@ -140,6 +157,13 @@ int ddcb200_writeRestart(const ddcb200_deck *deck, const char *dirname, int64_t 
                          const double *rx, const double *ry, const double *rz, const double *vx, const double *vy,
                          const double *vz, const uint64_t *rngState, int restartLink, char *snapshotdirOut, size_t len);
 
+/* subsetWriteBinaryCharmm (src/subsetWrite.c:409-522): <snapshotdir>/<filename>#000000 with one 24-byte record
+ * {id u8, pinfo u4, rx ry rz f4 relative to the box corner, in lengthUnit} per bead that passes the subset's filters
+ * (rejectParticle, :532-564).  snapshotdir as in ddcb200_writeRestart (dirname NULL = snapshot.<loop>).  Returns the number
+ * of records written, or <0. */
+int64_t ddcb200_subsetWrite(const ddcb200_deck *deck, int which, const char *dirname, int64_t loop, double time, const double h[9],
+                            const double *rx, const double *ry, const double *rz, const double *vx, const double *vy, const double *vz);
+
 /* readCMDS (src/readCmds.c:20-57): commands left in <runDir>/ddcMD_CMDS ("checkpoint", "kill", "exit", "profile", "hpm",
  * "analysis"), one per line; the file is truncated after reading.  Returns the OR of the DDCB200_CMD_* flags. */
 #define DDCB200_CMD_CHECKPOINT 1
@@ -153,7 +177,8 @@ int ddcb200_readCMDS(const char *filename);
 /* simulateMaster (src/masters.c:383-559) for a Martini deck on one GPU: simulate_init, firstEnergyCall, then the MD loop
  * with the reference's cadence - eval_integrator up to the next printrate / snapshotrate / checkpointrate loop
  * (findEndLoop, src/masters.c:263-281), a `data` line (and stdout line) every printrate loops, ddcMD_CMDS polled on print
- * loops, writeRestart every checkpointrate loops or on a "checkpoint"/"exit" command, a final data line when maxloop is
+ * loops, writeRestart every checkpointrate loops or on a "checkpoint"/"exit" command, the subsetWrite analyses every
+ * outputrate loops (doAnalysis, src/masters.c:295-302), a final data line when maxloop is
  * not a print loop.  Files are written into the deck's directory.  Returns 0, or <0 with ddcb200_lastHostError(). */
 int ddcb200_simulateMaster(const char *objectFile, const char *restartFile, const char *simulateName, int device);
 

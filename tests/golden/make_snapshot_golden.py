@@ -52,6 +52,17 @@ def run_deck_edit(d):
     open(p, "w").write(s)
 
 
+SUBSET_DTYPE = np.dtype([("gid", "<u8"), ("pin", "<u4"), ("r", "<f4", 3)])
+
+
+def subset_deck(text):
+    """popc_small with a subsetWrite analysis: the phosphate and sodium beads above z = -30 A, every 5 loops"""
+    text = text.replace("printinfo=printinfo;", "printinfo=printinfo; analysis=subset;", 1)
+    text = re.sub(r"printrate=\d+;", "printrate=5;", text)
+    return text + ("\nsubset ANALYSIS { type = subsetWrite; outputrate=5; format=binaryCharmm; filename=pos; "
+                   "species = POPCxPO4 POPExPO4 NAxNA; zmin=-30 Ang; }\n")
+
+
 def parse_records(body, lrec):
     recs = body[body.index(b"\n\n") + 2:] if not body.startswith(b"}") else body[body.index(b"\n\n", 1) + 2:]
     n = len(recs) // lrec
@@ -110,5 +121,21 @@ if __name__ == "__main__":
             runz[key + "_rv"] = rv
         shutil.rmtree(tmp)
         print(key, "lrec", lrec, gold[key]["loop0"]["body_bytes"], "bytes")
+    # ANALYSIS type = subsetWrite, format = binaryCharmm (src/subsetWrite.c): 10 steps of popc_small, output every 5 loops
+    tmp = tempfile.mkdtemp(prefix="snap_")
+    d = stage("popc_small", None, tmp)
+    p = os.path.join(d, "object.data")
+    text = open(p).read()
+    open(p, "w").write(subset_deck(text))
+    subprocess.check_call([REF], cwd=d, stdout=open(os.path.join(d, "_run.log"), "w"), stderr=subprocess.STDOUT)
+    gold["popc_small_subset"] = {}
+    for loop in (5, 10):
+        raw = open(os.path.join(d, "snapshot.%012d" % loop, "pos#000000"), "rb").read()
+        k = raw.index(b"}")
+        rec = np.frombuffer(raw[raw.index(b"\n\n", k) + 2:], dtype=SUBSET_DTYPE)
+        gold["popc_small_subset"]["header_%d" % loop] = raw[:k].decode()
+        for f in ("gid", "pin", "r"):
+            runz["subset_%d_%s" % (loop, f)] = rec[f].copy()
+    shutil.rmtree(tmp)
     json.dump(gold, open(os.path.join(HERE, "snapshot.json"), "w"), indent=1)
     np.savez_compressed(os.path.join(HERE, "snapshot_run.npz"), **runz)

@@ -108,3 +108,40 @@ def check_master(golden_dir, deck, variant, tmp_path):
 @pytest.mark.parametrize("deck,variant", [("popc_small", None), ("popc_small", "full"), ("ras_small", "full"), ("waterbox", None), ("waterbox", "full")])
 def test_simulateMaster_matches_reference_run(golden_dir, tmp_path, deck, variant):
     check_master(golden_dir, deck, variant, tmp_path)
+
+
+def check_subset(golden_dir, tmp_path):
+    """ANALYSIS type = subsetWrite, format = binaryCharmm: the files the reference wrote at loops 5 and 10, record for record."""
+    sys_path = os.path.join(golden_dir)
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("make_snapshot_golden", os.path.join(sys_path, "make_snapshot_golden.py"))
+    mg = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mg)
+    g = json.load(open(os.path.join(golden_dir, "snapshot.json")))["popc_small_subset"]
+    z = np.load(os.path.join(golden_dir, "snapshot_run.npz"))
+    d = os.path.join(str(tmp_path), "popc_small")
+    shutil.copytree(os.path.join(golden_dir, "popc_small"), d, symlinks=True)
+    p = os.path.join(d, "object.data")
+    text = open(p).read()
+    open(p, "w").write(mg.subset_deck(text))
+    deck = dd.Deck(p)
+    assert int(deck.s.nSubsets) == 1
+    dd.simulateMaster(p)
+    for loop in (5, 10):
+        raw = open(os.path.join(d, "snapshot.%012d" % loop, "pos#000000"), "rb").read()
+        k = raw.index(b"}")
+        rec = np.frombuffer(raw[raw.index(b"\n\n", k) + 2:], dtype=mg.SUBSET_DTYPE)
+        assert np.array_equal(rec["gid"], z["subset_%d_gid" % loop]) and np.array_equal(rec["pin"], z["subset_%d_pin" % loop])
+        # float32 of positions that agree to ~1e-12: equal, or one float ulp apart where the double sits on a rounding boundary
+        assert np.abs(rec["r"] - z["subset_%d_r" % loop]).max() <= 1e-5
+        assert (rec["r"] != z["subset_%d_r" % loop]).mean() < 0.01
+        strip = lambda t: [re.sub(r"create_time=[^;]*;|run_id=0x[0-9a-f]{8};", "", x) for x in t.splitlines() if not x.startswith("code_version")]   # noqa: E731
+        assert strip(raw[:k].decode()) == strip(g["header_%d" % loop])
+    # unsupported analyses are refused at load time, loudly
+    open(p, "w").write(mg.subset_deck(text).replace("format=binaryCharmm;", "format=ovito;"))
+    with pytest.raises(dd.DdcError, match="only type = subsetWrite with format = binaryCharmm"):
+        dd.Deck(p)
+
+
+def test_subsetWrite_matches_reference(golden_dir, tmp_path):
+    check_subset(golden_dir, tmp_path)
