@@ -232,6 +232,17 @@ extern "C" int ddcb200_create(const ddcb200_params *p, ddcb200_ctx **out)
         return rc;
     }
     CK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    if (const char *wk = getenv("DDCB200_WALK"))
+    {
+        // list-walk bound: "bead" (default) = rmax + dmax + this bead's own displacement, "global" = rmax + 2 dmax.
+        // Both are exact and give bitwise equal forces; "global" walks more entries (A/B knob)
+        if (strcmp(wk, "global") == 0) c->walkPerBead = false;
+        else if (strcmp(wk, "bead") != 0)
+        {
+            delete c;
+            return fail(DDCB200_ERR_ARG, "DDCB200_WALK must be bead or global");
+        }
+    }
     if (const char *lb = getenv("DDCB200_LISTBUILD"))
     {
         if (strcmp(lb, "twopass") == 0) c->listBuildMode = 1;
@@ -278,6 +289,7 @@ extern "C" void ddcb200_destroy(ddcb200_ctx *c)
     c->colMap.release(); c->stage.release(); c->stageI.release();
     c->orderKey.release(); c->pos32.release(); c->nbrRawCount.release(); c->nbrCum.release();
     for (int a = 0; a < 3; a++) c->posBuild[a].release();
+    c->dispOfSlot.release();
     if (c->dmax2) cudaFree(c->dmax2);
     c->groupOfBead.release(); c->rngState.release(); c->rngMP.release(); c->consAtomOff.release(); c->consAtomBead.release();
     c->consPairOff.release(); c->consPairA.release(); c->consPairB.release(); c->consPairDist.release();
@@ -815,6 +827,8 @@ extern "C" int ddcb200_constructList(ddcb200_ctx *c)
     CKL("cell sort");
     c->cur = nxt;
     CK(cudaMemsetAsync(c->dmax2, 0, sizeof(unsigned long long), st));
+    CK(c->dispOfSlot.ensure((size_t)nPad));
+    CK(cudaMemsetAsync(c->dispOfSlot.p, 0, (size_t)nPad * sizeof(float), st));
 
     // fp32 candidate filter: margin covers the rounding of box-sized coordinates (and the image shift) to fp32
     const double Lmax = std::max(c->box.hxx, std::max(c->box.hyy, c->box.hzz));
@@ -1064,10 +1078,10 @@ extern "C" int ddcb200_ddcenergy(ddcb200_ctx *c, int withEnergy)
         ProfScope ps(c, PROF_PAIR);
         const size_t smem = (size_t)c->ntypes * c->ntypes * (sizeof(double2) + sizeof(double)) + 256 * sizeof(double);
         if (withEnergy)
-            LAUNCH(k_pair<true>, tiles, TILE, smem, st)(nLocal, nPad, c->pos4[cur].p, c->nbr.p, c->nbrCum.p, c->dmax2, c->ljTab.p, c->shiftTab.p,
+            LAUNCH(k_pair<true>, tiles, TILE, smem, st)(nLocal, nPad, c->pos4[cur].p, c->nbr.p, c->nbrCum.p, c->dmax2, c->walkPerBead ? c->dispOfSlot.p : nullptr, c->ljTab.p, c->shiftTab.p,
                                                     c->qTab.p, c->pc, c->frc[0].p, c->frc[1].p, c->frc[2].p, c->pairPartial.p);
         else
-            LAUNCH(k_pair<false>, tiles, TILE, smem, st)(nLocal, nPad, c->pos4[cur].p, c->nbr.p, c->nbrCum.p, c->dmax2, c->ljTab.p, c->shiftTab.p,
+            LAUNCH(k_pair<false>, tiles, TILE, smem, st)(nLocal, nPad, c->pos4[cur].p, c->nbr.p, c->nbrCum.p, c->dmax2, c->walkPerBead ? c->dispOfSlot.p : nullptr, c->ljTab.p, c->shiftTab.p,
                                                      c->qTab.p, c->pc, c->frc[0].p, c->frc[1].p, c->frc[2].p, c->pairPartial.p);
         CKL("k_pair");
     }
@@ -1114,7 +1128,7 @@ static int launchIntegrate(ddcb200_ctx *c, double halfDt2, double halfDt1, doubl
     if (MODE & INT_KICK1_DRIFT) c->haloDirty = true;
     LAUNCH(k_integrate<MODE>, tiles, TILE, 0, c->stream)((int)c->nIon, c->pos4[cur].p, c->vel[cur][0].p, c->vel[cur][1].p, c->vel[cur][2].p,
                                                      c->frc[0].p, c->frc[1].p, c->frc[2].p, c->massOfBead.p, halfDt2, halfDt1, dt, c->pc,
-                                                     c->kinPartial.p, c->posBuild[0].p, c->posBuild[1].p, c->posBuild[2].p, c->dmax2);
+                                                     c->kinPartial.p, c->posBuild[0].p, c->posBuild[1].p, c->posBuild[2].p, c->dmax2, c->dispOfSlot.p);
     CKL("k_integrate");
     return DDCB200_OK;
 }
@@ -1410,7 +1424,7 @@ static int launchNglfc(ddcb200_ctx *c, double halfDt, double dt, const double sc
     LAUNCH(k_nglfc<MODE>, tiles, TILE, 0, c->stream)((int)c->nIon, c->pos4[cur].p, c->vel[cur][0].p, c->vel[cur][1].p, c->vel[cur][2].p,
                                                  c->frc[0].p, c->frc[1].p, c->frc[2].p, c->massOfBead.p, c->groupOfBead.p, c->rngState.p,
                                                  c->rngMP.p, groupTabOf(c), halfDt, dt, scale[0], scale[1], scale[2], c->pc, c->kinPartial.p,
-                                                 c->posBuild[0].p, c->posBuild[1].p, c->posBuild[2].p, c->dmax2);
+                                                 c->posBuild[0].p, c->posBuild[1].p, c->posBuild[2].p, c->dmax2, c->dispOfSlot.p);
     CKL("k_nglfc");
     return DDCB200_OK;
 }

@@ -170,6 +170,8 @@ struct ddcb200_ctx
     DevBuf<float4> pos32;         // fp32 copy of the build-time positions (candidate filter)
     DevBuf<double> posBuild[3];   // build-time positions, slot order (displacement bound)
     unsigned long long *dmax2 = nullptr;   // device: bits of max squared displacement since the build
+    bool walkPerBead = true;      // DDCB200_WALK
+    DevBuf<float> dispOfSlot;     // each local bead's own displacement since the build, rounded up (0 right after a build)
     DevBuf<double> mmPartial;
     GridDev *grid = nullptr;      // device
     GridDev *gridHost = nullptr;  // pinned

@@ -19,7 +19,8 @@ __global__ void __launch_bounds__(TILE)
 k_integrate(int nIon, double4 *__restrict__ pos, double *__restrict__ vx, double *__restrict__ vy, double *__restrict__ vz,
             const double *__restrict__ fx, const double *__restrict__ fy, const double *__restrict__ fz,
             const double *__restrict__ massOfBead, double halfDt2, double halfDt1, double dt, PairConst pc, double *__restrict__ partial,
-            const double *__restrict__ bx, const double *__restrict__ by, const double *__restrict__ bz, unsigned long long *__restrict__ dmax2)
+            const double *__restrict__ bx, const double *__restrict__ by, const double *__restrict__ bz, unsigned long long *__restrict__ dmax2,
+            float *__restrict__ dispOfSlot)
 {
     const int i = blockIdx.x * TILE + threadIdx.x;
     double ke[7] = {0, 0, 0, 0, 0, 0, 0};
@@ -76,6 +77,7 @@ k_integrate(int nIon, double4 *__restrict__ pos, double *__restrict__ vx, double
             if (dz > pc.hhz) dz -= pc.hzz;
             if (dz < -pc.hhz) dz += pc.hzz;
             disp2 = dx * dx + dy * dy + dz * dz;
+            dispOfSlot[i] = __double2float_ru(sqrt(disp2));     // this bead's own displacement, rounded up: k_pair's per-bead walk bound
         }
         if (MODE & (INT_KICK2 | INT_KICK1_DRIFT))
         {

@@ -29,7 +29,7 @@ __device__ __forceinline__ double4 ldPos(const double4 *p)
 template <bool ENERGY>
 __global__ void __launch_bounds__(TILE)
 k_pair(int nIon, int nPad, const double4 *__restrict__ pos, const uint32_t *__restrict__ nbr, const uint16_t *__restrict__ cum,
-       const unsigned long long *__restrict__ dmax2,
+       const unsigned long long *__restrict__ dmax2, const float *__restrict__ dispOfSlot,
        const double2 *__restrict__ ljTab, const double *__restrict__ shiftTab, const double *__restrict__ qTab, PairConst pc,
        double *__restrict__ fx, double *__restrict__ fy, double *__restrict__ fz, double *__restrict__ accPartial)
 {
@@ -53,13 +53,17 @@ k_pair(int nIon, int nPad, const double4 *__restrict__ pos, const uint32_t *__re
     const double qi = sQ[(wi >> 8) & 0xff];
     const double kqi = pc.keR * qi;
     const double2 *ljRow = sLJ + ti * pc.ntypes;
-    // Rows are ordered by build-time distance bin.  A pair listed at distance r_build can only be inside the
-    // cutoff now if r_build - 2*dmax - listSlack < rmax, dmax = largest displacement of any bead since the build
-    // (measured by k_integrate / k_nglfc), listSlack = change of the box edges since the build (0 without a
-    // barostat): bins that start beyond that are not even loaded.  Exact, not a heuristic.
+    // Rows are ordered by build-time distance bin.  A pair (i, j) listed at distance r_build can only be inside the
+    // cutoff now if r_build - d_i - d_j - listSlack < rmax; d_i = this bead's own displacement since the build (rounded
+    // up, written by k_integrate / k_nglfc), d_j <= dmax = the largest displacement of any resident bead, listSlack =
+    // change of the box edges since the build (0 without a barostat): bins that start beyond that are not even loaded.
+    // Exact, not a heuristic - the skipped entries would have added exact zeros, so the forces are bit-for-bit the same.
     int binLimit = 0;
     {
-        const double lim = (pc.rmax + pc.listSlack + 2.0 * sqrt(__longlong_as_double((long long)*dmax2))) * (1.0 + 1e-12);
+        const double dmax = sqrt(__longlong_as_double((long long)*dmax2));
+        // dispOfSlot == nullptr (DDCB200_WALK=global): every bead takes the global bound, d_i := dmax
+        const double di = (live && dispOfSlot) ? fmin((double)dispOfSlot[ii], dmax) : dmax;
+        const double lim = (pc.rmax + pc.listSlack + dmax + di) * (1.0 + 1e-12);
 #pragma unroll
         for (int e = 0; e < NBINS - 1; e++) binLimit += (pc.binEdge[e] < lim) ? 1 : 0;
     }

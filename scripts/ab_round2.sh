@@ -16,6 +16,7 @@ run() {  # name, env...
 run auto            DDCB200_LISTBUILD=auto
 run twopass         DDCB200_LISTBUILD=twopass
 run cell            DDCB200_LISTBUILD=cell
+run cell_walkglobal DDCB200_LISTBUILD=cell DDCB200_WALK=global
 run cell_bins4      DDCB200_LISTBUILD=cell DDCB200_BIN_EDGES=-0.25,-0.25,0.0,0.0,0.25,0.25,0.625
 run cell_bins2      DDCB200_LISTBUILD=cell DDCB200_BIN_EDGES=-0.25,-0.25,-0.25,0.25,0.25,0.25,0.25
 run cell_bins1      DDCB200_LISTBUILD=cell DDCB200_BIN_EDGES=1.0,1.0,1.0,1.0,1.0,1.0,1.0

@@ -383,6 +383,7 @@ static inline double __fma_rn(double a, double b, double c) { return fma(a, b, c
 static inline double __dsqrt_rn(double a) { return sqrt(a); }
 static inline double __ull2double_rn(unsigned long long v) { return (double)v; }
 static inline long long __double_as_longlong(double v) { long long r; memcpy(&r, &v, 8); return r; }
+static inline float __double2float_ru(double v) { float f = (float)v; return ((double)f < v) ? nextafterf(f, INFINITY) : f; }
 static inline int __double2hiint(double v) { long long r; memcpy(&r, &v, 8); return (int)(r >> 32); }
 static inline double __longlong_as_double(long long v) { double r; memcpy(&r, &v, 8); return r; }
 static inline int __float_as_int(float v) { int r; memcpy(&r, &v, 4); return r; }

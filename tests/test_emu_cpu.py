@@ -55,6 +55,11 @@ def test_emu_list_builds_agree(emu, golden_dir, name, monkeypatch):
     tg.test_list_builds_agree_bit_for_bit(golden_dir, name, monkeypatch)
 
 
+@pytest.mark.parametrize("name", ["popc_small", "ras_small"])
+def test_emu_per_bead_walk_bound(emu, golden_dir, name, monkeypatch):
+    tg.test_per_bead_walk_bound_is_bitwise_neutral(golden_dir, name, monkeypatch)
+
+
 def test_emu_bin_edges_knob(emu, golden_dir, monkeypatch):
     tg.test_bin_edges_knob_keeps_the_pair_set(golden_dir, monkeypatch)
 

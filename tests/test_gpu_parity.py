@@ -211,3 +211,22 @@ def test_bin_edges_knob_keeps_the_pair_set(golden_dir, monkeypatch):
     monkeypatch.setenv("DDCB200_BIN_EDGES", "0.5,0.1")
     with pytest.raises(dd.DdcError):
         _load(golden_dir, "popc_small")
+
+
+@pytest.mark.parametrize("name", ["popc_small", "ras_small"])
+def test_per_bead_walk_bound_is_bitwise_neutral(golden_dir, name, monkeypatch):
+    """k_pair stops each row at rmax + dmax + the bead's own displacement instead of rmax + 2 dmax: the entries it no longer visits
+    would have added exact zeros, so 45 steps (two rebuilds, growing displacements) are bitwise the same with either bound."""
+    out = {}
+    for mode in ("global", "bead"):
+        monkeypatch.setenv("DDCB200_WALK", mode)
+        sim, _ = _load(golden_dir, name)
+        sim.nglf(45)
+        e = sim.energyInfo()
+        st = sim.getState()
+        out[mode] = (st, e.eion, e.rk, np.array(e.virial[:]))
+        sim.close()
+    a, b = out["global"], out["bead"]
+    for k in ("rx", "ry", "rz", "vx", "vy", "vz", "fx", "fy", "fz"):
+        assert np.array_equal(a[0][k], b[0][k]), k
+    assert a[1] == b[1] and a[2] == b[2] and np.array_equal(a[3], b[3])
