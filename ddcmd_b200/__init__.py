@@ -164,6 +164,7 @@ def _declare(L):
         "ddcb200_printinfoHeader": (i32, [_P(DeckStruct), C.c_char_p, C.c_size_t]),
         "ddcb200_writeRestart": (i32, [_P(DeckStruct), C.c_char_p, i64, dbl, pd, pd, pd, pd, pd, pd, pd, _P(C.c_uint64), i32, C.c_char_p, C.c_size_t]),
         "ddcb200_readCMDS": (i32, [C.c_char_p]),
+        "ddcb200_writeBXYZ": (i32, [_P(DeckStruct), C.c_char_p, i64, dbl, pd, pd, pd, pd, pd, pd, pd]),
         "ddcb200_subsetWrite": (i64, [_P(DeckStruct), i32, C.c_char_p, i64, dbl, pd, pd, pd, pd, pd, pd, pd]),
         "ddcb200_simulateMaster": (i32, [C.c_char_p, C.c_char_p, C.c_char_p, i32]),
     }
@@ -182,7 +183,7 @@ EXPORTS = ["ddcb200_lastError", "ddcb200_deviceCount", "ddcb200_create", "ddcb20
            "ddcb200_nglfconstraintParms", "ddcb200_nglfconstraint", "ddcb200_getBox", "ddcb200_constraintFailures", "ddcb200_getCells", "ddcb200_getPairs", "ddcb200_profile",
            "ddcb200_profileRead", "ddcb200_timerRecord", "ddcb200_timerElapsed", "ddcb200_kernelLaunches", "ddcb200_lastListBuild", "ddcb200_ncclUniqueId", "ddcb200_ddcInit", "ddcb200_ddcPlan", "ddcb200_deckLoad", "ddcb200_deckFree",
            "ddcb200_lastHostError", "ddcb200_simulateBind", "ddcb200_simulateBindRank", "ddcb200_printinfoLine", "ddcb200_unitsConvert",
-           "ddcb200_printinfoHeader", "ddcb200_writeRestart", "ddcb200_readCMDS", "ddcb200_simulateMaster", "ddcb200_listBuildInfo", "ddcb200_subsetWrite"]
+           "ddcb200_printinfoHeader", "ddcb200_writeRestart", "ddcb200_readCMDS", "ddcb200_simulateMaster", "ddcb200_listBuildInfo", "ddcb200_subsetWrite", "ddcb200_writeBXYZ"]
 
 
 def _arr(ptr, n, dtype):
@@ -270,6 +271,17 @@ class Deck:
         if rc != 0:
             raise DdcError(L.ddcb200_lastHostError().decode())
         return os.fsdecode(out.value)
+
+    def writeBXYZ(self, dirname=None):
+        """writeBXYZ (src/io.c:144-155) of the state the deck was read with; returns nothing (the file is <snapshotdir>/bxyz#000000)."""
+        L = lib()
+        a = [np.ascontiguousarray(self.array(k), np.float64) for k in ("rx", "ry", "rz", "vx", "vy", "vz")]
+        hh = np.ascontiguousarray(np.array(self.s.params.h[:]), np.float64)
+        pd = _P(C.c_double)
+        rc = L.ddcb200_writeBXYZ(self._p, os.fsencode(dirname) if dirname else None, int(self.s.loop), float(self.s.time), hh.ctypes.data_as(pd),
+                                 *[x.ctypes.data_as(pd) for x in a])
+        if rc != 0:
+            raise DdcError(L.ddcb200_lastHostError().decode())
 
     def printinfoHeader(self):
         buf = C.create_string_buffer(1024)

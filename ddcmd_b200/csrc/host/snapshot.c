@@ -290,6 +290,92 @@ int ddcb200_writeRestart(const ddcb200_deck *d, const char *dirname, int64_t loo
     return rc;
 }
 
+int ddcb200_writeBXYZ(const ddcb200_deck *d, const char *dirname, int64_t loop, double time_, const double h[9],
+                      const double *rx, const double *ry, const double *rz, const double *vx, const double *vy, const double *vz)
+{
+    /* writeBXYZ (src/io.c:144-155) + collection_writeBXYZ mode 1 (src/collection_write.c:338-465): crc u4 | id | pinfo | r f4 x3 |
+     * v f4 x3 | energy f4 | virial f4.  The Martini path keeps no per-particle energy or virial (they stay at zeroAll's 0). */
+    if (!d || !h || !rx || !ry || !rz || !vx || !vy || !vz) return herr("writeBXYZ: null argument");
+    char rel[1024], loopFmt[16];
+    snprintf(loopFmt, sizeof loopFmt, "%%%d.%dllu", d->nLoopDigits, d->nLoopDigits);
+    int k = (dirname && dirname[0] == '/') ? 0 : snprintf(rel, sizeof rel, "%s/", d->atomsdir);
+    if (dirname) snprintf(rel + k, sizeof rel - (size_t)k, "%s", dirname);
+    else
+    {
+        k += snprintf(rel + k, sizeof rel - (size_t)k, "snapshot.");
+        snprintf(rel + k, sizeof rel - (size_t)k, loopFmt, (unsigned long long)loop);
+    }
+    char *dir = pathJoin(d->runDir, rel);
+    if (mkdir(dir, 0777) != 0 && errno != EEXIST) { herr("writeBXYZ: cannot create %s: %s", dir, strerror(errno)); free(dir); return -1; }
+    char *path = pathJoin(dir, "bxyz#000000");
+    free(dir);
+    const int nGroups = d->nGroups > 0 ? d->nGroups : 1;
+    uint64_t gmax = 0;
+    for (int64_t i = 0; i < d->n; i++)
+        if (d->gid[i] > gmax) gmax = d->gid[i];
+    const int gs = bFieldSize(gmax), ps = bFieldSize((uint64_t)nGroups * (uint64_t)d->nspecies);
+    const int lrec = 9 * 4 + gs + ps;
+    const double cLen = hu_convert(1.0, NULL, "l"), cTime = hu_convert(1.0, NULL, "t"), cVel = cLen / cTime;
+    SBuf hb = {0};
+    time_t now = time(NULL);
+    char stamp[64];
+    snprintf(stamp, sizeof stamp, "%s", ctime(&now));
+    stamp[strcspn(stamp, "\n")] = 0;
+    sbCat(&hb, "bxyz FILEHEADER {type=MULTILINE; datatype=FIXRECORDBINARY; checksum=CRC32; create_time=%s; run_id=0x%08x;\n", stamp, d->runId);
+    sbCat(&hb, "code_version=ddcmd_b200 (B200-native Martini step); srcpath=ddcmd_b200;\n");
+    sbCat(&hb, "loop=%lld; time=%f fs;\n", (long long)loop, time_ * cTime);
+    sbCat(&hb, "nfiles=1; nrecord=%llu; lrec=%d; nfields=11; endian_key=%d;\n", (unsigned long long)d->n, lrec, 875770417);
+    sbCat(&hb, "field_names=checksum id pinfo rx ry rz vx vy vz energy virial ;\n");
+    sbCat(&hb, "field_types=u4 b%d b%d f4 f4 f4 f4 f4 f4 f4 f4 ;\n", gs, ps);
+    sbCat(&hb, "reducedcorner=%21.14f %21.14f %21.14f;\n", d->reducedCorner[0], d->reducedCorner[1], d->reducedCorner[2]);
+    sbCat(&hb, "h=%21.14f %21.14f %21.14f\n", h[0] * cLen, h[1] * cLen, h[2] * cLen);
+    sbCat(&hb, "  %21.14f %21.14f %21.14f\n", h[3] * cLen, h[4] * cLen, h[5] * cLen);
+    sbCat(&hb, "  %21.14f %21.14f %21.14f Ang;\n", h[6] * cLen, h[7] * cLen, h[8] * cLen);
+    sbCat(&hb, "groups = ");
+    if (d->nGroups > 0) for (int g = 0; g < d->nGroups; g++) sbCat(&hb, "%s ", d->groupName[g]);
+    else sbCat(&hb, "group ");
+    sbCat(&hb, ";\nspecies = ");
+    for (int s = 0; s < d->nspecies; s++) sbCat(&hb, "%s ", d->speciesName[s]);
+    sbCat(&hb, ";\ntypes = ");
+    for (int s = 0; s < d->nspecies; s++)
+    {
+        int seen = 0;
+        for (int t = 0; t < s && !seen; t++) seen = strcmp(d->speciesType[t], d->speciesType[s]) == 0;
+        if (!seen) sbCat(&hb, "%s ", d->speciesType[s]);
+    }
+    sbCat(&hb, "; \n}\n \n\n");
+    FILE *f = fopen(path, "wb");
+    if (!f) { herr("writeBXYZ: cannot open %s: %s", path, strerror(errno)); free(path); free(hb.p); return -1; }
+    fwrite(hb.p, 1, hb.n, f);
+    free(hb.p);
+    double hi[3];
+    diagInverse(h, hi);
+    int rc = 0;
+    for (int64_t i = 0; i < d->n; i++)
+    {
+        unsigned char b[64];
+        memset(b, 0, sizeof b);
+        double x = rx[i], y = ry[i], z = rz[i];
+        x += h[0] * -rint(hi[0] * x);
+        y += h[4] * -rint(hi[1] * y);
+        z += h[8] * -rint(hi[2] * z);
+        const int ig = (d->nGroups > 0 && d->groupOfBead) ? d->groupOfBead[i] : 0;
+        int o = 4;
+        bFieldPack(b + o, gs, d->gid[i]);
+        o += gs;
+        bFieldPack(b + o, ps, (uint64_t)ig + (uint64_t)d->species[i] * (uint64_t)nGroups);
+        o += ps;
+        const float f4[6] = {(float)(x * cLen), (float)(y * cLen), (float)(z * cLen), (float)(vx[i] * cVel), (float)(vy[i] * cVel), (float)(vz[i] * cVel)};
+        memcpy(b + o, f4, 24);
+        const uint32_t crc = hcrc32(b + 4, (size_t)lrec - 4);
+        memcpy(b, &crc, 4);
+        if (fwrite(b, 1, (size_t)lrec, f) != (size_t)lrec) { rc = herr("writeBXYZ: short write to %s", path); break; }
+    }
+    fclose(f);
+    free(path);
+    return rc;
+}
+
 int64_t ddcb200_subsetWrite(const ddcb200_deck *d, int which, const char *dirname, int64_t loop, double time_, const double h[9],
                             const double *rx, const double *ry, const double *rz, const double *vx, const double *vy, const double *vz)
 {
@@ -465,6 +551,7 @@ int ddcb200_simulateMaster(const char *objectFile, const char *restartFile, cons
     for (int k = 0; k < 6; k++) hs.r[k] = (double *)malloc(sizeof(double) * (size_t)(d->n + 1));
     hs.rng = (uint64_t *)malloc(sizeof(uint64_t) * (size_t)(d->n + 1));
     int64_t loop = d->loop, maxloop = d->maxloop;
+    const int64_t startLoop = loop;
     if (d->deltaloop > -1 && loop + d->deltaloop < maxloop) maxloop = loop + d->deltaloop;   /* src/simulate.c:242 */
     {
         char *dpath = pathJoin(d->runDir, "data");
@@ -509,8 +596,17 @@ int ddcb200_simulateMaster(const char *objectFile, const char *restartFile, cons
         }
         if (TEST0(loop, d->checkpointrate) || (flag & DDCB200_CMD_CHECKPOINT))
             if ((rc = checkpoint(d, c, &hs, &e)) != 0) break;
-        /* doAnalysis (src/masters.c:295-302) */
         int fetched = 0;
+        /* doSnapshot (src/masters.c:340-352): bxyz every snapshotrate loops once the run has advanced */
+        if (loop > startLoop && TEST0(loop, d->snapshotrate))
+        {
+            double hh[9];
+            if (ddcb200_getState(c, hs.r[0], hs.r[1], hs.r[2], hs.r[3], hs.r[4], hs.r[5], NULL, NULL, NULL)) { rc = herr("getState: %s", ddcb200_lastError()); break; }
+            fetched = 1;
+            if (ddcb200_getBox(c, hh)) { rc = herr("getBox: %s", ddcb200_lastError()); break; }
+            if ((rc = ddcb200_writeBXYZ(d, NULL, e.loop, e.time, hh, hs.r[0], hs.r[1], hs.r[2], hs.r[3], hs.r[4], hs.r[5])) != 0) break;
+        }
+        /* doAnalysis (src/masters.c:295-302) */
         for (int a = 0; a < d->nSubsets && rc == 0; a++)
         {
             if (!(TEST0(loop, d->subsets[a].outputRate) || (flag & DDCB200_CMD_DO_ANALYSIS))) continue;

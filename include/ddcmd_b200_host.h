@@ -157,6 +157,11 @@ int ddcb200_writeRestart(const ddcb200_deck *deck, const char *dirname, int64_t 
                          const double *rx, const double *ry, const double *rz, const double *vx, const double *vy,
                          const double *vz, const uint64_t *rngState, int restartLink, char *snapshotdirOut, size_t len);
 
+/* writeBXYZ (src/io.c:144-155, collection_writeBXYZ mode 1 src/collection_write.c:338-465): <snapshotdir>/bxyz#000000, single-precision
+ * positions and velocities with CRC32 per record; ddcb200_simulateMaster writes it every SIMULATE snapshotrate loops. */
+int ddcb200_writeBXYZ(const ddcb200_deck *deck, const char *dirname, int64_t loop, double time, const double h[9],
+                      const double *rx, const double *ry, const double *rz, const double *vx, const double *vy, const double *vz);
+
 /* subsetWriteBinaryCharmm (src/subsetWrite.c:409-522): <snapshotdir>/<filename>#000000 with one 24-byte record
  * {id u8, pinfo u4, rx ry rz f4 relative to the box corner, in lengthUnit} per bead that passes the subset's filters
  * (rejectParticle, :532-564).  snapshotdir as in ddcb200_writeRestart (dirname NULL = snapshot.<loop>).  Returns the number

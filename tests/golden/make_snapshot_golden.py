@@ -87,7 +87,10 @@ if __name__ == "__main__":
         header, body = split_atoms(os.path.join(d, snap, "atoms#000000"))
         lrec = int(re.search(r"lrec=(\d+)", header).group(1))
         first = body.index(b"\n\n") + 2
-        gold[key] = {"loop0": {"snapshot": snap, "header": header, "lrec": lrec, "body_bytes": len(body), "body_sha256": hashlib.sha256(body).hexdigest(),
+        braw = open(os.path.join(d, snap, "bxyz#000000"), "rb").read()     # readWriteMaster also writes bxyz at loop 0
+        bk = braw.index(b"}")
+        bxyz = {"header": braw[:bk].decode(), "body_bytes": len(braw) - bk, "body_sha256": hashlib.sha256(braw[bk:]).hexdigest()}
+        gold[key] = {"bxyz0": bxyz, "loop0": {"snapshot": snap, "header": header, "lrec": lrec, "body_bytes": len(body), "body_sha256": hashlib.sha256(body).hexdigest(),
                                "first_records": body[first:first + 2 * lrec].decode(), "restart": open(os.path.join(d, snap, "restart")).read()}}
         shutil.rmtree(tmp)
 

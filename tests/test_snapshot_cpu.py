@@ -113,6 +113,20 @@ def test_corrupt_binary_record_is_rejected(golden_dir, tmp_path):
         dd.Deck(p)
 
 
+@pytest.mark.parametrize("deck,variant", CASES)
+def test_writeBXYZ_matches_reference_bytes(golden_dir, gold, tmp_path, deck, variant):
+    """bxyz#000000 (collection_writeBXYZ): single-precision snapshot records with CRC32, as readWriteMaster writes them at loop 0."""
+    g = gold[deck + ("_" + variant if variant else "")]["bxyz0"]
+    d = stage(golden_dir, deck, variant, tmp_path)
+    dk = dd.Deck(os.path.join(d, "object.data"))
+    dk.writeBXYZ()
+    raw = open(os.path.join(d, "snapshot.%0*d" % (int(dk.s.nLoopDigits), 0), "bxyz#000000"), "rb").read()
+    k = raw.index(b"}")
+    assert len(raw) - k == g["body_bytes"] and hashlib.sha256(raw[k:]).hexdigest() == g["body_sha256"]
+    strip = lambda t: [re.sub(r"create_time=[^;]*;", "", x) for x in strip_ids(t).splitlines() if not x.startswith("code_version")]   # noqa: E731
+    assert strip(raw[:k].decode()) == strip(g["header"])
+
+
 def test_restart_round_trip_through_the_reader(golden_dir, tmp_path):
     """write -> read back through ddcb200_deckLoad (CRC32 records, hexadecimal ids, LCG64 fields)."""
     d = stage(golden_dir, "popc_small", "full", tmp_path)
