@@ -89,7 +89,9 @@ k_pair(int nIon, int nPad, const double4 *__restrict__ pos, const uint32_t *__re
         for (int u = 0; u < PF; u++)
         {
             eCur[u] = eNext[u];
-            pCur[u] = ldPos(pos + (eCur[u] & 0x07ffffffu));
+            // lanes past the end of their own row issue no load at all (a dummy gather would still cost an L1 tag lookup)
+            pCur[u] = pi;
+            if (k0 + u < n) pCur[u] = ldPos(pos + (eCur[u] & 0x07ffffffu));
         }
 #pragma unroll
         for (int u = 0; u < PF; u++) eNext[u] = (k0 + PF + u < n) ? row[(size_t)(k0 + PF + u) * nPad] : (uint32_t)ii;
