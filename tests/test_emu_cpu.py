@@ -15,6 +15,7 @@ import pytest
 
 import ddcmd_b200 as dd
 import test_gpu_parity as tg
+import test_zzzzzzz_variants as tv
 
 sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "cpu_emu"))
 import build_emu  # noqa: E402
@@ -52,16 +53,16 @@ def test_emu_step0_forces_energy_virial(emu, golden_dir, name):
 
 @pytest.mark.parametrize("name", SMALL)
 def test_emu_list_builds_agree(emu, golden_dir, name, monkeypatch):
-    tg.test_list_builds_agree_bit_for_bit(golden_dir, name, monkeypatch)
+    tv.test_list_builds_agree_bit_for_bit(golden_dir, name, monkeypatch)
 
 
 @pytest.mark.parametrize("name", ["popc_small", "ras_small"])
 def test_emu_per_bead_walk_bound(emu, golden_dir, name, monkeypatch):
-    tg.test_per_bead_walk_bound_is_bitwise_neutral(golden_dir, name, monkeypatch)
+    tv.test_per_bead_walk_bound_is_bitwise_neutral(golden_dir, name, monkeypatch)
 
 
 def test_emu_bin_edges_knob(emu, golden_dir, monkeypatch):
-    tg.test_bin_edges_knob_keeps_the_pair_set(golden_dir, monkeypatch)
+    tv.test_bin_edges_knob_keeps_the_pair_set(golden_dir, monkeypatch)
 
 
 @pytest.mark.parametrize("name", SMALL)
