@@ -835,7 +835,12 @@ extern "C" int ddcb200_constructList(ddcb200_ctx *c)
     const double rl = sqrt(c->box.rlist2);
     const double margin = std::max(1e-3, 64.0 * 1.1920929e-7 * 1.5 * Lmax / rl);
     const float rl2f = (float)(c->box.rlist2 * (1.0 + margin));
-    if (c->nbrCap == 0) c->nbrCap = 176;
+    if (c->nbrCap == 0)
+    {
+        // entries per row allocated at first; a build that overflows it regrows from the measured maximum and repeats
+        const char *cp = getenv("DDCB200_NBRCAP");
+        c->nbrCap = cp ? std::max(8, atoi(cp)) : 176;
+    }
     // which build: fixed by DDCB200_LISTBUILD, else the first four rebuilds alternate between the two-pass and the one-pass
     // cell build under CUDA events and the faster one is kept (the rows are bit-identical: the choice never changes a result)
     int variant = c->listBuildMode;

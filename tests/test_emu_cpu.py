@@ -61,6 +61,11 @@ def test_emu_per_bead_walk_bound(emu, golden_dir, name, monkeypatch):
     tv.test_per_bead_walk_bound_is_bitwise_neutral(golden_dir, name, monkeypatch)
 
 
+@pytest.mark.parametrize("mode", ["twopass", "cell"])
+def test_emu_row_capacity_regrow(emu, golden_dir, monkeypatch, mode):
+    tv.test_row_capacity_regrow(golden_dir, monkeypatch, mode)
+
+
 def test_emu_bin_edges_knob(emu, golden_dir, monkeypatch):
     tv.test_bin_edges_knob_keeps_the_pair_set(golden_dir, monkeypatch)
 

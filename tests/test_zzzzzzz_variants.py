@@ -95,3 +95,28 @@ def test_per_bead_walk_bound_is_bitwise_neutral(golden_dir, name, monkeypatch):
     for k in ("rx", "ry", "rz", "vx", "vy", "vz", "fx", "fy", "fz"):
         assert np.array_equal(a[0][k], b[0][k]), k
     assert a[1] == b[1] and a[2] == b[2] and np.array_equal(a[3], b[3])
+
+
+@pytest.mark.parametrize("mode", ["twopass", "cell"])
+def test_row_capacity_regrow(golden_dir, monkeypatch, mode):
+    """A first build whose rows overflow the allocated capacity (forced small here) regrows from the measured maximum and repeats:
+    same pairs, same forces as with the default capacity, in both builds."""
+    monkeypatch.setenv("DDCB200_LISTBUILD", mode)
+    sim, ref = _load(golden_dir, "popc_small")
+    sim.ddcenergy(1)
+    a = sim.getState()
+    pa = sim.getPairs()
+    sim.close()
+    monkeypatch.setenv("DDCB200_NBRCAP", "40")
+    sim, _ = _load(golden_dir, "popc_small")
+    sim.ddcenergy(1)
+    b = sim.getState()
+    pb = sim.getPairs()
+    assert len(pb[0]) == int(ref["npairs"][0])
+    for x, y in zip(pa, pb):
+        assert np.array_equal(x, y)
+    for k in ("fx", "fy", "fz"):
+        assert np.array_equal(a[k], b[k])
+    sim.nglf(21)
+    assert sim.energyInfo().nPairsListed == int(ref["trace"].reshape(-1, 16)[20, 14])
+    sim.close()
