@@ -71,7 +71,7 @@ class DeckStruct(C.Structure):
                 ("atomsdir", C.c_char_p), ("nLoopDigits", C.c_int), ("gidFormatHex", C.c_int), ("runId", C.c_uint),
                 ("speciesType", _P(C.c_char_p)), ("printUnit", C.c_char_p * 6), ("printConvert", C.c_double * 6),
                 ("reducedCorner", C.c_double * 3), ("checkpointBinary", C.c_int), ("checkpointBrief", C.c_int),
-                ("nSubsets", C.c_int), ("subsets", C.c_void_p)]
+                ("nSubsets", C.c_int), ("subsets", C.c_void_p), ("nPairCorr", C.c_int), ("pairCorr", C.c_void_p)]
 
 
 class DdcError(RuntimeError):
@@ -151,6 +151,8 @@ def _declare(L):
         "ddcb200_kernelLaunches": (i64, [vp]),
         "ddcb200_lastListBuild": (i64, [vp]),
         "ddcb200_listBuildInfo": (i32, [vp, pi, pd]),
+        "ddcb200_pairCorrelation": (i32, [vp, i32, dbl, dbl, i32, dbl, _P(C.c_uint64), _P(C.c_uint64)]),
+        "ddcb200_pairCorrelationWrite": (i32, [_P(DeckStruct), i32, C.c_char_p, i64, dbl, pd, i32]),
         "ddcb200_ncclUniqueId": (i32, [C.c_char_p]),
         "ddcb200_ddcInit": (i32, [vp, i32, i32, i32, i32, i32, C.c_char_p]),
         "ddcb200_ddcPlan": (i32, [pd, i32, i32, i32, dbl, i64, pd, pd, pd, pi, i32, pi, _P(C.c_uint32)]),
@@ -183,7 +185,8 @@ EXPORTS = ["ddcb200_lastError", "ddcb200_deviceCount", "ddcb200_create", "ddcb20
            "ddcb200_nglfconstraintParms", "ddcb200_nglfconstraint", "ddcb200_getBox", "ddcb200_constraintFailures", "ddcb200_getCells", "ddcb200_getPairs", "ddcb200_profile",
            "ddcb200_profileRead", "ddcb200_timerRecord", "ddcb200_timerElapsed", "ddcb200_kernelLaunches", "ddcb200_lastListBuild", "ddcb200_ncclUniqueId", "ddcb200_ddcInit", "ddcb200_ddcPlan", "ddcb200_deckLoad", "ddcb200_deckFree",
            "ddcb200_lastHostError", "ddcb200_simulateBind", "ddcb200_simulateBindRank", "ddcb200_printinfoLine", "ddcb200_unitsConvert",
-           "ddcb200_printinfoHeader", "ddcb200_writeRestart", "ddcb200_readCMDS", "ddcb200_simulateMaster", "ddcb200_listBuildInfo", "ddcb200_subsetWrite", "ddcb200_writeBXYZ"]
+           "ddcb200_printinfoHeader", "ddcb200_writeRestart", "ddcb200_readCMDS", "ddcb200_simulateMaster", "ddcb200_listBuildInfo", "ddcb200_subsetWrite", "ddcb200_writeBXYZ", "ddcb200_pairCorrelation",
+           "ddcb200_pairCorrelationWrite"]
 
 
 def _arr(ptr, n, dtype):
@@ -468,6 +471,16 @@ class Simulate:
             raise DdcError("writeRestart: some beads are local on no rank")
         return self.deck.writeRestart(*[full[k] for k in keys], loop=int(e.loop), time=float(e.time), h=self.getBox(), dirname=dirname,
                                       restart_link=restart_link)
+
+    def pairCorrelation(self, nbins, rmin, delta, rmax, log_scale=False):
+        """paircorrelation_eval's counts (src/paircorrelation.c:158-420): (counts[np, nbins] uint64, atoms per species uint64), internal units."""
+        ns = int(self.deck.s.nspecies)
+        npair = ns * (ns + 1) // 2
+        counts = np.zeros(npair * int(nbins), np.uint64)
+        natoms = np.zeros(ns, np.uint64)
+        self._ck(lib().ddcb200_pairCorrelation(self.ctx, int(nbins), float(rmin), float(delta), int(bool(log_scale)), float(rmax),
+                                               counts.ctypes.data_as(_P(C.c_uint64)), natoms.ctypes.data_as(_P(C.c_uint64))))
+        return counts.reshape(npair, int(nbins)), natoms
 
     def listBuildInfo(self):
         """(variant in use: 0 undecided / 1 two-pass / 2 one-pass cell build, [ms of the timed two-pass build, ms of the timed cell build])"""

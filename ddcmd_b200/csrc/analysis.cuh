@@ -1,0 +1,77 @@
+// analysis.cuh - pair correlation counts on the device.
+//
+// Replaces the pair loops of paircorrelation_eval_{geom,grid,nbrList} (src/paircorrelation.c:174-420): every pair with
+// gid_i < gid_j and r < rmax is counted in (species pair, distance bin), 2 for a same-species pair and 1 otherwise.  The
+// three methods of the reference find the same pairs; here they come from a walk over the cell structure of the last
+// build, widened by the displacement since then.  Counts are integers, so the atomics make the result independent of the
+// order of the threads.
+#pragma once
+#include "engine.cuh"
+#include "cells.cuh"
+
+__host__ __device__ inline int comboIndexOf(int i, int j, int ns)
+{
+    // comboIndex, src/paircorrelation.c:516-521
+    const int mx = i > j ? i : j, mn = i > j ? j : i;
+    return (mx - mn) + ns * mn - (mn * (mn - 1)) / 2;
+}
+
+__global__ void __launch_bounds__(TILE)
+k_paircorr(int nIon, const double4 *__restrict__ pos, const int *__restrict__ cellOfSlot, const int *__restrict__ cellStart,
+           const GridDev *__restrict__ gp, int reach, const uint64_t *__restrict__ gid, const int *__restrict__ speciesOfBead, BoxConst b,
+           double rmax2, double rmin, double delta, int logScale, double log10rmin, int nBins, int ns,
+           unsigned long long *__restrict__ hist, unsigned long long *__restrict__ nAtoms)
+{
+    // One thread per local bead walks the cells within `reach` cells of the cell the bead was sorted into at the last build.
+    // Slots keep their build-time cell between builds, and the host chose reach so that reach x (smallest cell edge) covers
+    // rmax + twice the largest displacement since the build: every pair with r < rmax now is among the candidates.
+    const int i = blockIdx.x * TILE + threadIdx.x;
+    if (i >= nIon) return;
+    const double4 pi = pos[i];
+    const uint64_t wi = (uint64_t)__double_as_longlong(pi.w);
+    if (wi >> 63) return;                                  // ghosts are counted by their owner
+    const int bi = (int)((wi >> 32) & 0x7fffffffull);
+    const int si = speciesOfBead[bi];
+    const uint64_t gi = gid[bi];
+    atomicAdd(&nAtoms[si], 1ull);
+    const int nx = gp->n[0], ny = gp->n[1], nz = gp->n[2];
+    const int c = cellOfSlot[i];
+    const int cx = c % nx, cy = (c / nx) % ny, cz = c / (nx * ny);
+    // along an axis with fewer than 2 reach + 1 cells every cell is visited exactly once
+    const int wx = min(2 * reach + 1, nx), wy = min(2 * reach + 1, ny), wz = min(2 * reach + 1, nz);
+    const int x0 = wx == nx ? 0 : cx - reach, y0 = wy == ny ? 0 : cy - reach, z0 = wz == nz ? 0 : cz - reach;
+    for (int dz = 0; dz < wz; dz++)
+    {
+        const int az = ((z0 + dz) % nz + nz) % nz;
+        for (int dy = 0; dy < wy; dy++)
+        {
+            const int ay = ((y0 + dy) % ny + ny) % ny;
+            for (int dx = 0; dx < wx; dx++)
+            {
+                const int ax = ((x0 + dx) % nx + nx) % nx;
+                const int cc = ax + nx * (ay + ny * az);
+                for (int j = cellStart[cc]; j < cellStart[cc + 1]; j++)
+                {
+                    const double4 pj = pos[j];
+                    const int bj = (int)((((uint64_t)__double_as_longlong(pj.w)) >> 32) & 0x7fffffffull);
+                    if (!(gi < gid[bj])) continue;
+                    double x = __dadd_rn(pi.x, -pj.x), y = __dadd_rn(pi.y, -pj.y), z = __dadd_rn(pi.z, -pj.z);
+                    double r2 = exactR2(x, y, z);
+                    if (r2 > b.R2cut)
+                    {
+                        wrapOnce(x, y, z, b);
+                        r2 = exactR2(x, y, z);
+                    }
+                    if (!(r2 < rmax2)) continue;
+                    const double r = sqrt(r2);
+                    // linearBins / logBins, src/paircorrelation.c:60-68
+                    const double q = logScale ? __ddiv_rn(__dadd_rn(log10(r), -log10rmin), delta) : __ddiv_rn(__dadd_rn(r, -rmin), delta);
+                    const int bin = (int)q;
+                    if (q < 0.0 || bin >= nBins) continue;
+                    const int sj = speciesOfBead[bj];
+                    atomicAdd(&hist[(size_t)bin + (size_t)nBins * comboIndexOf(si, sj, ns)], si == sj ? 2ull : 1ull);
+                }
+            }
+        }
+    }
+}

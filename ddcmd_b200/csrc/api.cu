@@ -9,6 +9,7 @@
 #include "nbrcheck.cuh"
 #include "nglfcons.cuh"
 #include "ddc.cuh"
+#include "analysis.cuh"
 #include <nccl.h>
 #include <math.h>
 #include <stdlib.h>
@@ -1659,6 +1660,64 @@ extern "C" int ddcb200_timerElapsed(ddcb200_ctx *c, int from, int to, double *ms
 extern "C" int64_t ddcb200_kernelLaunches(ddcb200_ctx *c) { return c ? c->kernelLaunches : 0; }
 
 extern "C" int64_t ddcb200_lastListBuild(ddcb200_ctx *c) { return c ? c->lastBuildLoop : -1; }
+
+extern "C" int ddcb200_pairCorrelation(ddcb200_ctx *c, int nBins, double rmin, double delta, int logScale, double rmax,
+                                       unsigned long long *counts, unsigned long long *nAtoms)
+{
+    if (!c || !counts || !nAtoms || nBins < 1 || !(delta > 0.0) || !(rmax > 0.0) || (logScale && !(rmin > 0.0)))
+        return fail(DDCB200_ERR_ARG, "pairCorrelation: bad arguments");
+    if (c->nLocal == 0) return fail(DDCB200_ERR_STATE, "no state");
+    CK(cudaSetDevice(c->device));
+    int rc;
+    if (!c->listValid)
+    {
+        rc = ddcb200_constructList(c);
+        if (rc) return rc;
+    }
+    if (c->nranks > 1 && c->haloDirty)
+    {
+        rc = haloExchange(c);
+        if (rc) return rc;
+    }
+    cudaStream_t st = c->stream;
+    // candidates: the cells within `reach` cells of a bead's build-time cell.  A pair with r < rmax now was within
+    // rmax + 2 dmax + box slack at the build, and a cell is at least d_min wide: reach = ceil of that over d_min
+    unsigned long long dbits = 0;
+    CK(cudaMemcpyAsync(&dbits, c->dmax2, sizeof dbits, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(c->gridHost, c->grid, sizeof(GridDev), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    double d2;
+    memcpy(&d2, &dbits, sizeof d2);
+    const double need = (rmax + 2.0 * sqrt(d2) + c->pc.listSlack) * (1.0 + 1e-9);
+    // cell edges in length units: d (fraction of the box span) x span
+    const double edge[3] = {c->gridHost->d[0] * c->box.spanx, c->gridHost->d[1] * c->box.spany, c->gridHost->d[2] * c->box.spanz};
+    const double dmin = std::min(edge[0], std::min(edge[1], edge[2]));
+    if (!(dmin > 0.0)) return fail(DDCB200_ERR_STATE, "pairCorrelation: no cell grid");
+    if (c->nranks > 1 && need > sqrt(c->box.rlist2))
+        return fail(DDCB200_ERR_STATE, "pairCorrelation on several ranks: rmax plus twice the largest displacement exceeds the ghost shell (list radius)");
+    const int reach = std::max(1, (int)ceil(need / dmin));
+    if (rmax > 0.5 * std::min(c->box.hxx, std::min(c->box.hyy, c->box.hzz)))
+        return fail(DDCB200_ERR_ARG, "pairCorrelation: rmax exceeds half the shortest box edge");
+    const int ns = c->nspecies;
+    const size_t nh = (size_t)nBins * (size_t)(ns * (ns + 1) / 2);
+    DevBuf<unsigned long long> hist;
+    DevBuf<int> spec;
+    CK(hist.ensure(nh + (size_t)ns));
+    CK(spec.ensure((size_t)c->nGlobal + 1));
+    CK(cudaMemsetAsync(hist.p, 0, (nh + (size_t)ns) * sizeof(unsigned long long), st));
+    CK(cudaMemcpyAsync(spec.p, c->hSpecies.data(), (size_t)c->nGlobal * sizeof(int), cudaMemcpyHostToDevice, st));
+    const int cur = c->cur;
+    LAUNCH(k_paircorr, (int)(c->nPad / TILE), TILE, 0, st)((int)c->nIon, c->pos4[cur].p, c->cellOfSlot[cur].p, c->cellStart.p, c->grid, reach,
+                                                       c->gidOfBead.p, spec.p, c->box, rmax * rmax, rmin, delta, logScale,
+                                                       logScale ? log10(rmin) : 0.0, nBins, ns, hist.p, hist.p + nh);
+    CKL("k_paircorr");
+    CK(cudaMemcpyAsync(counts, hist.p, nh * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(nAtoms, hist.p + nh, (size_t)ns * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    hist.release();
+    spec.release();
+    return DDCB200_OK;
+}
 
 extern "C" int ddcb200_listBuildInfo(ddcb200_ctx *c, int *variant, double ms[2])
 {

@@ -673,6 +673,8 @@ void ddcb200_deckFree(ddcb200_deck *d)
         free(q->name); free(q->filename); free(q->lengthUnit); free(q->parmsInfo); free(q->idList); free(q->includeSpecies);
     }
     free(d->subsets);
+    for (int a = 0; a < d->nPairCorr; a++) { free(d->pairCorr[a].name); free(d->pairCorr[a].filename); free(d->pairCorr[a].miscInfo); }
+    free(d->pairCorr);
     free(d->runDir); free(d->simulateName); free(d->boxName); free(d->collectionName); free(d->atomsdir);
     if (d->speciesType)
         for (int i = 0; i < d->nspecies; i++) free(d->speciesType[i]);
@@ -1383,9 +1385,41 @@ int ddcb200_deckLoad(const char *objectFile, const char *restartFile, const char
             odb_getString(ao, "type", &type, "NONE");
             odb_getString(ao, "format", &fmt, "pio");
             const int isSubset = strcasecmp(type, "subsetWrite") == 0 || strcasecmp(type, "subset_write") == 0;
+            if (strncasecmp(type, "PAIRCORRELATION", 15) == 0)
+            {
+                /* paircorrelation_parms, src/paircorrelation.c:71-145 (the three pair-finding methods give the same counts) */
+                free(type); free(fmt);
+                if (!d->pairCorr) d->pairCorr = (ddcb200_paircorr *)calloc((size_t)na, sizeof(ddcb200_paircorr));
+                ddcb200_paircorr *g = &d->pairCorr[d->nPairCorr++];
+                g->name = strdup(an[a]);
+                odb_getInts(ao, "eval_rate", &g->evalRate, 1, "0");
+                odb_getInts(ao, "outputrate", &g->outputRate, 1, "0");
+                odb_getString(ao, "filename", &g->filename, "paircorrelation.dat");
+                odb_getInts(ao, "length", &g->nBins, 1, "1");
+                char *rs = NULL;
+                odb_getString(ao, "rscale", &rs, "normal");
+                g->logScale = strcasecmp(rs, "log") == 0;
+                const int okScale = g->logScale || strcasecmp(rs, "normal") == 0;
+                free(rs);
+                if (odb_getWithUnits(ao, "delta_r", &g->deltaR, 1, "1", "l", NULL) < 0 || odb_getWithUnits(ao, "rmin", &g->rmin, 1, "0", "l", NULL) < 0 ||
+                    !okScale || g->nBins < 1 || !(g->deltaR > 0.0) || (g->logScale && !(g->rmin > 0.0)))
+                {
+                    herr("ANALYSIS %s: bad PAIRCORRELATION parameters", an[a]);
+                    odb_freeStrings(an, na);
+                    rc = -1;
+                    goto done;
+                }
+                g->rmax = g->rmin + g->nBins * g->deltaR;
+                if (g->logScale) g->logDelta = (log10(g->rmax) - log10(g->rmin)) / (g->nBins * 1.0);
+                char info[256];
+                snprintf(info, sizeof info, "rmin = %f Ang; delta_r = %f Ang; length = %d; eval_rate = %d; outputrate = %d;",
+                         hu_convert(g->rmin, NULL, "Angstrom"), hu_convert(g->deltaR, NULL, "Angstrom"), g->nBins, g->evalRate, g->outputRate);
+                g->miscInfo = strdup(info);
+                continue;
+            }
             if (!isSubset || strcmp(fmt, "binaryCharmm") != 0)
             {
-                herr("ANALYSIS %s: only type = subsetWrite with format = binaryCharmm is supported (type %s, format %s)", an[a], type, fmt);
+                herr("ANALYSIS %s: only type = PAIRCORRELATION, or subsetWrite with format = binaryCharmm, is supported (type %s, format %s)", an[a], type, fmt);
                 free(type); free(fmt); odb_freeStrings(an, na);
                 rc = -1;
                 goto done;

@@ -479,6 +479,74 @@ int64_t ddcb200_subsetWrite(const ddcb200_deck *d, int which, const char *dirnam
     return rc;
 }
 
+static int comboIndexHost(int i, int j, int ns)
+{
+    const int mx = i > j ? i : j, mn = i > j ? j : i;      /* comboIndex, src/paircorrelation.c:516-521 */
+    return (mx - mn) + ns * mn - (mn * (mn - 1)) / 2;
+}
+
+int ddcb200_pairCorrelationWrite(const ddcb200_deck *d, int which, const char *dirname, int64_t loop, double volume, const double *gacc, int nsample)
+{
+    if (!d || !gacc) return herr("pairCorrelationWrite: null argument");
+    if (which < 0 || which >= d->nPairCorr) return herr("pairCorrelationWrite: no such ANALYSIS (%d of %d)", which, d->nPairCorr);
+    if (nsample <= 0) return 0;                              /* nothing sampled: the reference writes nothing */
+    const ddcb200_paircorr *q = &d->pairCorr[which];
+    char rel[1024], loopFmt[16];
+    snprintf(loopFmt, sizeof loopFmt, "%%%d.%dllu", d->nLoopDigits, d->nLoopDigits);
+    int k = (dirname && dirname[0] == '/') ? 0 : snprintf(rel, sizeof rel, "%s/", d->atomsdir);
+    if (dirname) snprintf(rel + k, sizeof rel - (size_t)k, "%s", dirname);
+    else
+    {
+        k += snprintf(rel + k, sizeof rel - (size_t)k, "snapshot.");
+        snprintf(rel + k, sizeof rel - (size_t)k, loopFmt, (unsigned long long)loop);
+    }
+    char *dir = pathJoin(d->runDir, rel);
+    if (mkdir(dir, 0777) != 0 && errno != EEXIST) { herr("pairCorrelationWrite: cannot create %s: %s", dir, strerror(errno)); free(dir); return -1; }
+    char *path = pathJoin(dir, q->filename);
+    free(dir);
+    FILE *f = fopen(path, "w");
+    if (!f) { herr("pairCorrelationWrite: cannot open %s: %s", path, strerror(errno)); free(path); return -1; }
+    const int ns = d->nspecies, np = ns * (ns + 1) / 2, nb = q->nBins;
+    /* bin edges as paircorrelation_parms makes them (src/paircorrelation.c:100-131), scaling of :470-479 */
+    const double s = volume / nsample;
+    fprintf(f, "# %s\n# nsample = %d;\n# r(Ang) ", q->miscInfo, nsample);
+    for (int l = 0; l < np; l++)
+    {
+        int ti = -1, tj = -1;
+        for (int a = 0; a < ns && ti < 0; a++)
+            for (int b = a; b < ns; b++)
+                if (comboIndexHost(a, b, ns) == l) { ti = a; tj = b; break; }
+        fprintf(f, "%s-%s ", d->speciesName[ti], d->speciesName[tj]);
+    }
+    fprintf(f, "\n");
+    for (int kb = 0; kb < nb; kb++)
+    {
+        double r0, r1;
+        if (q->logScale)
+        {
+            r0 = pow(10, log10(q->rmin) + kb * q->logDelta);
+            r1 = kb == nb - 1 ? q->rmax : pow(10, log10(q->rmin) + (kb + 1) * q->logDelta);
+        }
+        else
+        {
+            r0 = q->rmin + kb * q->deltaR;
+            r1 = q->rmin + (kb + 1) * q->deltaR;
+        }
+        const double dv = 4.0 * M_PI / 3.0 * (r1 * r1 * r1 - r0 * r0 * r0);
+        fprintf(f, "%f ", hu_convert(0.5 * (r0 + r1), NULL, "Angstrom"));
+        for (int l = 0; l < np; l++)
+        {
+            double g = gacc[kb + nb * l];
+            g *= s / dv;
+            fprintf(f, "%e ", g);
+        }
+        fprintf(f, "\n");
+    }
+    fclose(f);
+    free(path);
+    return 0;
+}
+
 int ddcb200_readCMDS(const char *filename)
 {
     int flag = 0;
@@ -516,6 +584,8 @@ static int64_t findEndLoop(const ddcb200_deck *d, int64_t loop, int64_t maxloop)
         if (TEST0(l, d->printrate) || TEST0(l, d->snapshotrate) || TEST0(l, d->checkpointrate)) return l;
         for (int a = 0; a < d->nSubsets; a++)
             if (TEST0(l, d->subsets[a].evalRate) || TEST0(l, d->subsets[a].outputRate)) return l;
+        for (int a = 0; a < d->nPairCorr; a++)
+            if (TEST0(l, d->pairCorr[a].evalRate) || TEST0(l, d->pairCorr[a].outputRate)) return l;
     }
     return maxloop;
 }
@@ -543,6 +613,8 @@ int ddcb200_simulateMaster(const char *objectFile, const char *restartFile, cons
     memset(&hs, 0, sizeof hs);
     FILE *data = NULL;
     char *cmds = NULL;
+    double *pcG[16] = {0};
+    int pcSamples[16] = {0};
     int rc = ddcb200_deckLoad(objectFile, restartFile, simulateName, &d);
     if (rc) return rc;
     rc = ddcb200_simulateBind(d, device, &c);
@@ -552,6 +624,9 @@ int ddcb200_simulateMaster(const char *objectFile, const char *restartFile, cons
     hs.rng = (uint64_t *)malloc(sizeof(uint64_t) * (size_t)(d->n + 1));
     int64_t loop = d->loop, maxloop = d->maxloop;
     const int64_t startLoop = loop;
+    for (int a = 0; a < d->nPairCorr && a < 16; a++)
+        pcG[a] = (double *)calloc((size_t)d->pairCorr[a].nBins * (size_t)(d->nspecies * (d->nspecies + 1) / 2) + 1, sizeof(double));
+    if (d->nPairCorr > 16) { rc = herr("more than 16 PAIRCORRELATION analyses"); goto done; }
     if (d->deltaloop > -1 && loop + d->deltaloop < maxloop) maxloop = loop + d->deltaloop;   /* src/simulate.c:242 */
     {
         char *dpath = pathJoin(d->runDir, "data");
@@ -617,11 +692,52 @@ int ddcb200_simulateMaster(const char *objectFile, const char *restartFile, cons
             if (ddcb200_subsetWrite(d, a, NULL, e.loop, e.time, hh, hs.r[0], hs.r[1], hs.r[2], hs.r[3], hs.r[4], hs.r[5]) < 0) rc = -1;
         }
         if (rc) break;
+        for (int a = 0; a < d->nPairCorr && rc == 0; a++)
+        {
+            const ddcb200_paircorr *q = &d->pairCorr[a];
+            const int ns = d->nspecies, np = ns * (ns + 1) / 2;
+            const size_t nh = (size_t)q->nBins * (size_t)np;
+            if (TEST0(loop, q->evalRate) || (flag & DDCB200_CMD_DO_ANALYSIS))
+            {
+                /* paircorrelation_eval: g += counts / (N_i N_j) (src/paircorrelation.c:222-235) */
+                unsigned long long *cnt = (unsigned long long *)malloc(sizeof(unsigned long long) * (nh + (size_t)ns));
+                if (ddcb200_pairCorrelation(c, q->nBins, q->rmin, q->logScale ? q->logDelta : q->deltaR, q->logScale, q->rmax, cnt, cnt + nh))
+                {
+                    rc = herr("ANALYSIS %s: %s", q->name, ddcb200_lastError());
+                    free(cnt);
+                    break;
+                }
+                for (int si = 0; si < ns; si++)
+                    for (int sj = si; sj < ns; sj++)
+                    {
+                        const int l = comboIndexHost(si, sj, ns);
+                        const double recip = 1.0 / ((double)cnt[nh + (size_t)si] * (double)cnt[nh + (size_t)sj]);
+                        for (int kb = 0; kb < q->nBins; kb++)
+                        {
+                            double v = (double)cnt[(size_t)kb + (size_t)q->nBins * (size_t)l];
+                            v *= recip;
+                            pcG[a][(size_t)kb + (size_t)q->nBins * (size_t)l] += v;
+                        }
+                    }
+                pcSamples[a]++;
+                free(cnt);
+            }
+            if (TEST0(loop, q->outputRate) || (flag & DDCB200_CMD_DO_ANALYSIS))
+            {
+                double hh[9];
+                if (ddcb200_getBox(c, hh)) { rc = herr("getBox: %s", ddcb200_lastError()); break; }
+                rc = ddcb200_pairCorrelationWrite(d, a, NULL, e.loop, hh[0] * hh[4] * hh[8], pcG[a], pcSamples[a]);
+                memset(pcG[a], 0, sizeof(double) * nh);       /* paircorrelation_clear */
+                pcSamples[a] = 0;
+            }
+        }
+        if (rc) break;
         if (flag & DDCB200_CMD_STOP) break;
     }
     if (rc == 0 && !TEST0(loop, d->printrate)) PRINTLINE();
 done:
     free(cmds);
+    for (int a = 0; a < 16; a++) free(pcG[a]);
     if (data) fclose(data);
     for (int k = 0; k < 6; k++) free(hs.r[k]);
     free(hs.rng);

@@ -213,6 +213,14 @@ int64_t ddcb200_kernelLaunches(ddcb200_ctx *ctx);
  * check4updateNeighbor / evalUpdateFlag (src/ddcUpdateAll.c:48-71). */
 int64_t ddcb200_lastListBuild(ddcb200_ctx *ctx);
 
+/* Replaces the pair loops of paircorrelation_eval (src/paircorrelation.c:158-420, methods geom / grid / neighborList alike):
+ * counts[bin + nBins * comboIndex(si, sj)] over the local beads' pairs with gid_i < gid_j and r < rmax, 2 per same-species pair
+ * and 1 otherwise; bin = (int)((r - rmin) / delta), or (int)((log10 r - log10 rmin) / delta) with logScale; nAtoms[species] =
+ * local beads per species.  np = ns (ns + 1) / 2 species pairs in the reference's comboIndex order.  rmax may be any length up
+ * to half the shortest box edge: the walk over the cells of the last build is widened by the displacement since then. */
+int ddcb200_pairCorrelation(ddcb200_ctx *ctx, int nBins, double rmin, double delta, int logScale, double rmax,
+                            unsigned long long *counts, unsigned long long *nAtoms);
+
 /* Which list build runs: 1 = two passes (fp32 candidate filter, then the exact pairlist1 test over the candidates),
  * 2 = one pass (one warp per cell, exact test on every stencil candidate), 0 = not decided yet.  Both write the same
  * rows bit for bit.  Unless DDCB200_LISTBUILD=twopass|cell fixes it, the first four rebuilds alternate between the

@@ -29,6 +29,14 @@ typedef struct ddcb200_subset
     int *includeSpecies;                 /* per SPECIES index */
 } ddcb200_subset;
 
+/* ANALYSIS type = PAIRCORRELATION (src/paircorrelation.c:71-145): g(r) per species pair, linear or logarithmic bins */
+typedef struct ddcb200_paircorr
+{
+    char *name, *filename, *miscInfo;
+    int evalRate, outputRate, nBins, logScale;
+    double rmin, deltaR, logDelta, rmax;     /* internal units */
+} ddcb200_paircorr;
+
 typedef struct ddcb200_deck
 {
     /* SIMULATE (src/simulate.c:151-169) */
@@ -116,9 +124,11 @@ typedef struct ddcb200_deck
      * writes FIXRECORDBINARY records (collection_writeBLOCK_binary, src/collection_write.c:188-336) when checkpointBinary */
     int checkpointBinary, checkpointBrief;
     /* SIMULATE analysis = ... : the ANALYSIS objects of type subsetWrite with format = binaryCharmm (the positions feed of the
-     * MuMMI workflow); any other ANALYSIS type or format is an error at load time */
+     * MuMMI workflow) and of type PAIRCORRELATION; any other ANALYSIS type or format is an error at load time */
     int nSubsets;
     ddcb200_subset *subsets;
+    int nPairCorr;
+    ddcb200_paircorr *pairCorr;
 } ddcb200_deck;
 
 /* object_compilefile(object.data) + object_compilefile(restart) + the init chain.
@@ -168,6 +178,10 @@ int ddcb200_writeBXYZ(const ddcb200_deck *deck, const char *dirname, int64_t loo
  * of records written, or <0. */
 int64_t ddcb200_subsetWrite(const ddcb200_deck *deck, int which, const char *dirname, int64_t loop, double time, const double h[9],
                             const double *rx, const double *ry, const double *rz, const double *vx, const double *vy, const double *vz);
+
+/* paircorrelation_output (src/paircorrelation.c:448-513): <snapshotdir>/<filename> with one row per bin (bin centre in Ang, then
+ * g for every species pair) from the accumulated g[nBins * np] (sum over the samples of counts / (N_i N_j)) and the sample count. */
+int ddcb200_pairCorrelationWrite(const ddcb200_deck *deck, int which, const char *dirname, int64_t loop, double volume, const double *g, int nsample);
 
 /* readCMDS (src/readCmds.c:20-57): commands left in <runDir>/ddcMD_CMDS ("checkpoint", "kill", "exit", "profile", "hpm",
  * "analysis"), one per line; the file is truncated after reading.  Returns the OR of the DDCB200_CMD_* flags. */

@@ -63,6 +63,13 @@ def subset_deck(text):
                    "species = POPCxPO4 POPExPO4 NAxNA; zmin=-30 Ang; }\n")
 
 
+def paircorr_deck(text):
+    """popc_small with a pair-correlation analysis: 22 bins of 0.5 A, sampled every 5 loops, written every 10"""
+    text = text.replace("printinfo=printinfo;", "printinfo=printinfo; analysis=gr;", 1)
+    text = re.sub(r"printrate=\d+;", "printrate=5;", text)
+    return text + "\ngr ANALYSIS { type = PAIRCORRELATION; eval_rate=5; outputrate=10; length=22; delta_r=0.5 Ang; rmin=0 Ang; filename=gr.dat; }\n"
+
+
 def parse_records(body, lrec):
     recs = body[body.index(b"\n\n") + 2:] if not body.startswith(b"}") else body[body.index(b"\n\n", 1) + 2:]
     n = len(recs) // lrec
@@ -139,6 +146,17 @@ if __name__ == "__main__":
         gold["popc_small_subset"]["header_%d" % loop] = raw[:k].decode()
         for f in ("gid", "pin", "r"):
             runz["subset_%d_%s" % (loop, f)] = rec[f].copy()
+    shutil.rmtree(tmp)
+    # ANALYSIS type = PAIRCORRELATION (src/paircorrelation.c): 10 steps of popc_small, sampled every 5 loops, written at loop 10
+    tmp = tempfile.mkdtemp(prefix="snap_")
+    d = stage("popc_small", None, tmp)
+    p = os.path.join(d, "object.data")
+    text = open(p).read()
+    open(p, "w").write(paircorr_deck(text))
+    subprocess.check_call([REF], cwd=d, stdout=open(os.path.join(d, "_run.log"), "w"), stderr=subprocess.STDOUT)
+    lines = open(os.path.join(d, "snapshot.%012d" % 10, "gr.dat")).read().splitlines()
+    gold["popc_small_gr"] = {"header": lines[:3]}
+    runz["gr_table"] = np.array([[float(x) for x in ln.split()] for ln in lines[3:]])
     shutil.rmtree(tmp)
     json.dump(gold, open(os.path.join(HERE, "snapshot.json"), "w"), indent=1)
     np.savez_compressed(os.path.join(HERE, "snapshot_run.npz"), **runz)

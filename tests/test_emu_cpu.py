@@ -109,6 +109,11 @@ def test_emu_subsetWrite(emu, golden_dir, tmp_path):
     tm.check_subset(golden_dir, tmp_path)
 
 
+def test_emu_paircorrelation(emu, golden_dir, tmp_path):
+    import test_zzzzzz_master as tm
+    tm.check_paircorr(golden_dir, tmp_path)
+
+
 def test_emu_fullsize_checks_on_a_small_generated_deck(emu, tmp_path, monkeypatch):
     """The live-oracle comparison and the size-independent property checks of tests/test_zzz_fullsize.py, on the synthetic
     generator's ~4k-bead configuration so the emulation finishes in seconds."""
