@@ -51,12 +51,12 @@ def test_emu_step0_forces_energy_virial(emu, golden_dir, name):
     tg.test_step0_forces_energy_virial(golden_dir, name)
 
 
-@pytest.mark.parametrize("name", SMALL)
+@pytest.mark.parametrize("name", ["popc_small", "tiny2"])
 def test_emu_list_builds_agree(emu, golden_dir, name, monkeypatch):
     tv.test_list_builds_agree_bit_for_bit(golden_dir, name, monkeypatch)
 
 
-@pytest.mark.parametrize("name", ["popc_small", "ras_small"])
+@pytest.mark.parametrize("name", ["popc_small"])
 def test_emu_per_bead_walk_bound(emu, golden_dir, name, monkeypatch):
     tv.test_per_bead_walk_bound_is_bitwise_neutral(golden_dir, name, monkeypatch)
 
