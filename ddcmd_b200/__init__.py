@@ -127,6 +127,7 @@ def _declare(L):
         "ddcb200_setRestraints": (i32, [vp, i64, pi, pd, pd, pd, i32]),
         "ddcb200_setMolecules": (i32, [vp, i64, _P(C.c_int64), pi, i64]),
         "ddcb200_sendState": (i32, [vp, i64, pi, pd, pd, pd, pd, pd, pd, i64, dbl]),
+        "ddcb200_updateState": (i32, [vp, i64, pi, pd, pd, pd, pd, pd, pd, i64, dbl]),
         "ddcb200_numLocal": (i64, [vp]),
         "ddcb200_getLocalBeads": (i32, [vp, pi]),
         "ddcb200_getState": (i32, [vp] + [pd] * 9),
@@ -180,7 +181,7 @@ def _declare(L):
 EXPORTS = ["ddcb200_lastError", "ddcb200_deviceCount", "ddcb200_create", "ddcb200_destroy", "ddcb200_sync",
            "ddcb200_martiniNonBondParms", "ddcb200_setSpecies", "ddcb200_setBeads", "ddcb200_setExclusions",
            "ddcb200_martiniBondParms", "ddcb200_setRestraints", "ddcb200_setMolecules", "ddcb200_sendState",
-           "ddcb200_numLocal", "ddcb200_getLocalBeads", "ddcb200_getState", "ddcb200_constructList", "ddcb200_ddcenergy",
+           "ddcb200_updateState", "ddcb200_numLocal", "ddcb200_getLocalBeads", "ddcb200_getState", "ddcb200_constructList", "ddcb200_ddcenergy",
            "ddcb200_nglf", "ddcb200_energyInfo", "ddcb200_setGroups", "ddcb200_setRandom", "ddcb200_getRandom", "ddcb200_setConstraints",
            "ddcb200_nglfconstraintParms", "ddcb200_nglfconstraint", "ddcb200_getBox", "ddcb200_constraintFailures", "ddcb200_getCells", "ddcb200_getPairs", "ddcb200_profile",
            "ddcb200_profileRead", "ddcb200_timerRecord", "ddcb200_timerElapsed", "ddcb200_kernelLaunches", "ddcb200_lastListBuild", "ddcb200_ncclUniqueId", "ddcb200_ddcInit", "ddcb200_ddcPlan", "ddcb200_deckLoad", "ddcb200_deckFree",

@@ -594,6 +594,43 @@ extern "C" int ddcb200_sendState(ddcb200_ctx *c, int64_t nLocal, const int *bead
     return DDCB200_OK;
 }
 
+// New positions / velocities for the beads that are already resident, e.g. from a host-side integrator between two force
+// evaluations (the reference's per-step sendPosnToGPU, src/gpuMemUtils.h): unlike sendState the cell order and the neighbor list
+// are kept, so the list is rebuilt on the DDC schedule exactly as when the whole step runs on the device.
+extern "C" int ddcb200_updateState(ddcb200_ctx *c, int64_t nLocal, const int *bead, const double *rx, const double *ry, const double *rz,
+                                   const double *vx, const double *vy, const double *vz, int64_t loop, double time)
+{
+    if (!c || nLocal <= 0 || !rx || !ry || !rz || !vx || !vy || !vz) return fail(DDCB200_ERR_ARG, "bad state");
+    if (!c->listValid || c->nranks > 1 || nLocal != c->nLocal) return ddcb200_sendState(c, nLocal, bead, rx, ry, rz, vx, vy, vz, loop, time);
+    CK(cudaSetDevice(c->device));
+    CK(c->stage.ensure((size_t)nLocal * 9));
+    CK(c->stageI.ensure((size_t)nLocal));
+    const double *src[6] = {rx, ry, rz, vx, vy, vz};
+    for (int a = 0; a < 6; a++)
+        CK(cudaMemcpyAsync(c->stage.p + (size_t)a * nLocal, src[a], nLocal * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    if (bead)
+    {
+        c->hLocalBeads.assign(bead, bead + nLocal);
+        CK(cudaMemcpyAsync(c->stageI.p, c->hLocalBeads.data(), nLocal * sizeof(int), cudaMemcpyHostToDevice, c->stream));
+    }
+    else
+        for (int64_t i = 0; i < nLocal; i++) c->hLocalBeads[(size_t)i] = (int)i;
+    const int cur = c->cur;
+    const double *s = c->stage.p;
+    LAUNCH(k_update_state, (int)((nLocal + 255) / 256), 256, 0, c->stream)((int)nLocal, bead ? c->stageI.p : nullptr, c->slotOfBead.p, s, s + nLocal,
+                                                                       s + 2 * nLocal, s + 3 * nLocal, s + 4 * nLocal, s + 5 * nLocal, c->pos4[cur].p,
+                                                                       c->vel[cur][0].p, c->vel[cur][1].p, c->vel[cur][2].p, c->pc, c->posBuild[0].p,
+                                                                       c->posBuild[1].p, c->posBuild[2].p, c->dmax2, c->dispOfSlot.p);
+    CKL("k_update_state");
+    c->loop = loop;
+    c->time = time;
+    c->forcesValid = false;
+    c->energyValid = false;
+    c->kineticValid = false;
+    c->pendingKick2 = false;
+    return DDCB200_OK;
+}
+
 // After a re-domain the set of local beads has changed: list them (slot order is not meaningful to callers).
 static int refreshLocals(ddcb200_ctx *c)
 {

@@ -221,6 +221,38 @@ __global__ void k_upload_state(int n, const int *__restrict__ bead, const double
     slotOfBead[b] = i;
 }
 
+// new positions and velocities for beads that are already resident (slots, cells and the neighbor list are kept): the
+// displacement bookkeeping of the list walk is refreshed from the build-time positions, as the integrator kernels do
+__global__ void k_update_state(int n, const int *__restrict__ bead, const int *__restrict__ slotOfBead, const double *__restrict__ rx,
+                               const double *__restrict__ ry, const double *__restrict__ rz, const double *__restrict__ vxi,
+                               const double *__restrict__ vyi, const double *__restrict__ vzi, double4 *__restrict__ pos,
+                               double *__restrict__ vx, double *__restrict__ vy, double *__restrict__ vz, PairConst pc,
+                               const double *__restrict__ bx, const double *__restrict__ by, const double *__restrict__ bz,
+                               unsigned long long *__restrict__ dmax2, float *__restrict__ dispOfSlot)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int s = slotOfBead[bead ? bead[i] : i];
+    double4 p = pos[s];
+    p.x = rx[i];
+    p.y = ry[i];
+    p.z = rz[i];
+    pos[s] = p;
+    vx[s] = vxi[i];
+    vy[s] = vyi[i];
+    vz[s] = vzi[i];
+    double dx = p.x - bx[s], dy = p.y - by[s], dz = p.z - bz[s];
+    if (dx > pc.hhx) dx -= pc.hxx;
+    if (dx < -pc.hhx) dx += pc.hxx;
+    if (dy > pc.hhy) dy -= pc.hyy;
+    if (dy < -pc.hhy) dy += pc.hyy;
+    if (dz > pc.hhz) dz -= pc.hzz;
+    if (dz < -pc.hhz) dz += pc.hzz;
+    const double disp2 = dx * dx + dy * dy + dz * dz;
+    dispOfSlot[s] = __double2float_ru(sqrt(disp2));
+    atomicMax(dmax2, (unsigned long long)__double_as_longlong(disp2));
+}
+
 __global__ void k_download_state(int n, const int *__restrict__ bead, const int *__restrict__ slotOfBead, const double4 *__restrict__ pos,
                                  const double *__restrict__ vx, const double *__restrict__ vy, const double *__restrict__ vz,
                                  const double *__restrict__ fx, const double *__restrict__ fy, const double *__restrict__ fz,

@@ -128,6 +128,12 @@ int ddcb200_sendState(ddcb200_ctx *ctx, int64_t nLocal, const int *bead, const d
 /* Replaces sendPosnToHost / sendForceVelocityToHost.  Any pointer may be NULL.  Output is
  * ordered like the bead[] array returned by ddcb200_getLocalBeads (for one context that
  * never migrates beads: the order given to sendState). */
+/* The per-step upload of a host-side integrator (the reference's sendPosnToGPU / sendForceVelocityToGPU between force
+ * evaluations): new positions and velocities of the beads that are already resident, same set as the last sendState.  The
+ * cell order and the neighbor list are kept and rebuilt on the DDC schedule, exactly as when the step runs on the device;
+ * sendState, in contrast, starts a new run (the next force evaluation rebuilds).  Falls back to sendState when no list exists. */
+int ddcb200_updateState(ddcb200_ctx *ctx, int64_t nLocal, const int *bead, const double *rx, const double *ry, const double *rz,
+                        const double *vx, const double *vy, const double *vz, int64_t loop, double time);
 int64_t ddcb200_numLocal(ddcb200_ctx *ctx);
 int ddcb200_getLocalBeads(ddcb200_ctx *ctx, int *bead);
 int ddcb200_getState(ddcb200_ctx *ctx, double *rx, double *ry, double *rz, double *vx, double *vy, double *vz,
