@@ -47,7 +47,7 @@ static int fail(int code, const std::string &msg)
     } while (0)
 
 // number of kernels launched before each CKL() checkpoint (for the bench's gpu_launches count)
-static int launchesOf(const char *what) { return strcmp(what, "cell sort") == 0 ? 7 : 1; }   // minmax, grid, count, scan, scatter, rank, gather
+static int launchesOf(const char *what) { return strcmp(what, "cell sort") == 0 ? 7 : (strcmp(what, "list self-check") == 0 ? 3 : 1); }   // minmax, grid, count, scan, scatter, rank, gather
 
 extern "C" const char *ddcb200_lastError(void) { return g_err.c_str(); }
 
@@ -945,6 +945,52 @@ extern "C" int ddcb200_constructList(ddcb200_ctx *c)
         if (c->gridHost->error & 2) return fail(DDCB200_ERR_CAPACITY, "cell grid larger than the bead count bound");
         if (!(c->gridHost->error & 1))
         {
+            if (variant == 2 && c->listBuildMode == 0 && !c->cellBuildChecked)
+            {
+                // one-time self-check, auto mode only: the same state through the two-pass build into scratch buffers, rows compared
+                // on the device.  A difference (none is known; the two builds are bit-identical in every test) makes the context
+                // keep the two-pass build, says so on stderr, and rebuilds this list with it.
+                c->cellBuildChecked = true;
+                DevBuf<uint32_t> rows2;
+                DevBuf<int> count2;
+                DevBuf<uint16_t> cum2;
+                DevBuf<int> bad;
+                CK(rows2.ensure((size_t)c->nbrCap * nPad));
+                CK(count2.ensure((size_t)nPad));
+                CK(cum2.ensure((size_t)NBINS * nPad));
+                CK(bad.ensure(1));
+                CK(c->nbrRaw.ensure((size_t)c->nbrCap * nPad));
+                CK(cudaMemsetAsync(bad.p, 0, sizeof(int), st));
+                LAUNCH(k_nbr_filter, nPad / 128, 128, 0, st)(nIon, nPad, c->pos32.p, c->cellOfSlot[nxt].p, c->cellStart.p, c->box, rl2f, c->grid,
+                                                        c->nbrCap, c->nbrRaw.p, c->nbrRawCount.p);
+                LAUNCH(k_nbr_exact, nPad / 128, 128, 0, st)(nIon, nPad, c->nbrCap, c->pos4[nxt].p, c->box, c->grid, c->nbrRaw.p, c->nbrRawCount.p,
+                                                       rows2.p, count2.p, cum2.p, c->gidOfBead.p, c->molTypeOfBead.p, c->molTypeSingle.p,
+                                                       c->bpairOffset.p, c->bpairKey.p, c->haveExcl ? 1 : 0);
+                LAUNCH(k_rows_compare, (nIon + 255) / 256, 256, 0, st)(nIon, nPad, c->nbr.p, c->nbrCount.p, c->nbrCum.p, rows2.p, count2.p, cum2.p, bad.p);
+                CKL("list self-check");
+                int nbad = 0;
+                GridDev after;
+                CK(cudaMemcpyAsync(&nbad, bad.p, sizeof(int), cudaMemcpyDeviceToHost, st));
+                CK(cudaMemcpyAsync(&after, c->grid, sizeof(GridDev), cudaMemcpyDeviceToHost, st));
+                CK(cudaStreamSynchronize(st));
+                rows2.release(); count2.release(); cum2.release(); bad.release();
+                const char *inject = getenv("DDCB200_SELFCHECK_FAULT");      // test hook: pretend the check failed
+                if (nbad != 0 || (after.error & 1) || (inject && inject[0] == '1'))
+                {
+                    fprintf(stderr, "ddcmd_b200: the one-pass list build differs from the two-pass build on %d rows; keeping the two-pass build\n", nbad);
+                    c->listBuildMode = 1;
+                    variant = 1;
+                    timeIt = false;
+                    CK(cudaMemsetAsync(&c->grid->error, 0, sizeof(int), st));
+                    CK(cudaMemsetAsync(&c->grid->maxCount, 0, sizeof(int), st));
+                    CK(cudaMemsetAsync(&c->grid->maxRaw, 0, sizeof(int), st));
+                    CK(cudaMemsetAsync(&c->grid->totalEntries, 0, sizeof(unsigned long long), st));
+                    attempt--;
+                    continue;
+                }
+                // the scratch build added its rows to the device-side statistics: put the one-pass build's back
+                CK(cudaMemcpyAsync(c->grid, c->gridHost, sizeof(GridDev), cudaMemcpyHostToDevice, st));
+            }
             if (timeIt)
             {
                 float ms = 0.f;

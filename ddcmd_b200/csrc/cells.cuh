@@ -655,3 +655,17 @@ k_nbr_cell(int nIon, int nPad, int cap, const double4 *__restrict__ pos, const i
         if (statMax > cap) atomicOr(&gp->error, 1);
     }
 }
+
+// ---- one-time self-check of the one-pass build against the two-pass build (auto mode) ------------------------------------
+// mismatch[0] counts slots whose row length, bin boundaries or entries differ
+__global__ void k_rows_compare(int nIon, int nPad, const uint32_t *__restrict__ a, const int *__restrict__ ca, const uint16_t *__restrict__ cuma,
+                               const uint32_t *__restrict__ b, const int *__restrict__ cb, const uint16_t *__restrict__ cumb, int *__restrict__ mismatch)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nIon) return;
+    bool bad = ca[i] != cb[i];
+    for (int e = 0; e < NBINS && !bad; e++) bad = cuma[(size_t)e * nPad + i] != cumb[(size_t)e * nPad + i];
+    const int n = bad ? 0 : ca[i];
+    for (int k = 0; k < n && !bad; k++) bad = a[(size_t)k * nPad + i] != b[(size_t)k * nPad + i];
+    if (bad) atomicAdd(mismatch, 1);
+}

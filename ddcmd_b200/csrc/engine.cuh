@@ -188,6 +188,7 @@ struct ddcb200_ctx
     // DDCB200_LISTBUILD=auto|twopass|cell
     double binFrac[NBINS - 1] = {-0.25, -0.125, 0.0, 0.125, 0.25, 0.375, 0.625};   // ordering-bin edges, fractions of deltaR (DDCB200_BIN_EDGES)
     int listBuildMode = 0;
+    bool cellBuildChecked = false;   // auto mode: the first one-pass build is compared, row for row, with a two-pass build of the same state
     int listBuildsTimed = 0;
     float listBuildMs[2] = {0.f, 0.f};
     cudaEvent_t evList[2] = {nullptr, nullptr};

@@ -66,6 +66,10 @@ def test_emu_row_capacity_regrow(emu, golden_dir, monkeypatch, mode):
     tv.test_row_capacity_regrow(golden_dir, monkeypatch, mode)
 
 
+def test_emu_auto_mode_self_check(emu, golden_dir, monkeypatch, capfd):
+    tv.test_auto_mode_self_check_falls_back(golden_dir, monkeypatch, capfd)
+
+
 def test_emu_bin_edges_knob(emu, golden_dir, monkeypatch):
     tv.test_bin_edges_knob_keeps_the_pair_set(golden_dir, monkeypatch)
 

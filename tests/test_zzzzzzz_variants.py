@@ -120,3 +120,36 @@ def test_row_capacity_regrow(golden_dir, monkeypatch, mode):
     sim.nglf(21)
     assert sim.energyInfo().nPairsListed == int(ref["trace"].reshape(-1, 16)[20, 14])
     sim.close()
+
+
+def test_auto_mode_self_check_falls_back(golden_dir, monkeypatch, capfd):
+    """auto mode compares its first one-pass build with a two-pass build of the same state; a (here: injected) difference makes
+    the context keep the two-pass build, with the same results."""
+    monkeypatch.setenv("DDCB200_LISTBUILD", "twopass")
+    sim, ref = _load(golden_dir, "popc_small")
+    sim.nglf(45)
+    a = sim.getState()
+    ea = sim.energyInfo()
+    sim.close()
+    monkeypatch.setenv("DDCB200_LISTBUILD", "auto")
+    monkeypatch.setenv("DDCB200_SELFCHECK_FAULT", "1")
+    sim, _ = _load(golden_dir, "popc_small")
+    sim.nglf(45)
+    b = sim.getState()
+    eb = sim.energyInfo()
+    assert sim.listBuildInfo()[0] == 1
+    sim.close()
+    assert "keeping the two-pass build" in capfd.readouterr().err
+    for k in ("rx", "vx", "fx", "fz"):
+        assert np.array_equal(a[k], b[k])
+    assert ea.eion == eb.eion and ea.nPairsListed == eb.nPairsListed
+    # without the injected fault the check passes silently and both builds get timed
+    monkeypatch.delenv("DDCB200_SELFCHECK_FAULT")
+    sim, _ = _load(golden_dir, "popc_small")
+    sim.nglf(65)
+    info = sim.listBuildInfo()
+    c = sim.getState()
+    sim.close()
+    assert info[0] in (1, 2) and info[1][0] > 0 and info[1][1] > 0
+    assert "keeping the two-pass build" not in capfd.readouterr().err
+    assert np.array_equal(c["rx"][:10], c["rx"][:10])
