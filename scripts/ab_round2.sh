@@ -11,7 +11,7 @@ OUT=gpurun_out/ab_round2.jsonl
 run() {  # name, env...
     local name="$1"; shift
     echo "== $name" >&2
-    env "$@" python bench.py --steps 120 --warmup 61 --no-cpu-baseline 2> "gpurun_out/ab_$name.log" | sed "s/^{/{\"variant\": \"$name\", /" >> "$OUT"
+    env "$@" python bench.py --steps 120 --warmup 20 --no-cpu-baseline 2> "gpurun_out/ab_$name.log" | sed "s/^{/{\"variant\": \"$name\", /" >> "$OUT"
 }
 run auto            DDCB200_LISTBUILD=auto
 run twopass         DDCB200_LISTBUILD=twopass
