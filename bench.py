@@ -313,8 +313,8 @@ def main():
     for k, name in enumerate(("rx", "ry", "rz", "vx", "vy", "vz")):
         host[k] = st[name]
     KE = K
-    pinned_out = torch.empty((9, nl), dtype=torch.float64).pin_memory()
-    host_out = pinned_out.numpy()
+    pinned_out = torch.empty(9 * n, dtype=torch.float64).pin_memory()      # room for every bead: on several ranks the locals migrate
+    host_flat = pinned_out.numpy()
     sim.sync()
     barrier()
     t0 = time.perf_counter()
@@ -323,7 +323,8 @@ def main():
     for _ in range(KE):
         sim.nglf(1)
         ee = sim.energyInfo()
-    st2 = sim.getState(out=host_out)
+    nl2 = sim.numLocal()
+    st2 = sim.getState(out=host_flat[:9 * nl2].reshape(9, nl2))
     barrier()
     t1 = time.perf_counter()
     e2e_sps = KE / max_over_ranks(t1 - t0)
