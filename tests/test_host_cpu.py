@@ -194,3 +194,22 @@ def test_nglfconstraint_deck_errors(golden_dir, tmp_path):
     open(p, "w").write(s.replace("type = NGLFCONSTRAINT;", "type = NEXTGEN;"))
     with pytest.raises(dd.DdcError, match="NEXTGEN"):
         dd.Deck(p)
+
+
+def test_standalone_driver_fails_loudly_without_a_device(golden_dir, tmp_path):
+    """ddcmd_b200/ddcMD_b200 (the reference's `ddcMD -o object.data` for Martini decks): no device, no run, a clear message."""
+    import shutil
+    import subprocess
+    import ddcmd_b200.build as b
+    exe = b.EXE
+    if not os.path.exists(exe):
+        b.build(force=True)
+    if dd.lib().ddcb200_deviceCount() > 0:
+        pytest.skip("a CUDA device is present")
+    d = os.path.join(str(tmp_path), "popc_small")
+    shutil.copytree(os.path.join(golden_dir, "popc_small"), d, symlinks=True)
+    r = subprocess.run([exe, "-o", "object.data"], cwd=d, capture_output=True, text=True, timeout=120)
+    assert r.returncode == 1 and "no CUDA device" in r.stderr
+    assert not os.path.exists(os.path.join(d, "data"))
+    r = subprocess.run([exe, "analysis"], cwd=d, capture_output=True, text=True, timeout=120)
+    assert r.returncode == 2 and "not supported" in r.stderr
