@@ -231,26 +231,35 @@ __global__ void k_update_state(int n, const int *__restrict__ bead, const int *_
                                unsigned long long *__restrict__ dmax2, float *__restrict__ dispOfSlot)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    const int s = slotOfBead[bead ? bead[i] : i];
-    double4 p = pos[s];
-    p.x = rx[i];
-    p.y = ry[i];
-    p.z = rz[i];
-    pos[s] = p;
-    vx[s] = vxi[i];
-    vy[s] = vyi[i];
-    vz[s] = vzi[i];
-    double dx = p.x - bx[s], dy = p.y - by[s], dz = p.z - bz[s];
-    if (dx > pc.hhx) dx -= pc.hxx;
-    if (dx < -pc.hhx) dx += pc.hxx;
-    if (dy > pc.hhy) dy -= pc.hyy;
-    if (dy < -pc.hhy) dy += pc.hyy;
-    if (dz > pc.hhz) dz -= pc.hzz;
-    if (dz < -pc.hhz) dz += pc.hzz;
-    const double disp2 = dx * dx + dy * dy + dz * dz;
-    dispOfSlot[s] = __double2float_ru(sqrt(disp2));
-    atomicMax(dmax2, (unsigned long long)__double_as_longlong(disp2));
+    double disp2 = 0.0;
+    if (i < n)
+    {
+        const int s = slotOfBead[bead ? bead[i] : i];
+        double4 p = pos[s];
+        p.x = rx[i];
+        p.y = ry[i];
+        p.z = rz[i];
+        pos[s] = p;
+        vx[s] = vxi[i];
+        vy[s] = vyi[i];
+        vz[s] = vzi[i];
+        double dx = p.x - bx[s], dy = p.y - by[s], dz = p.z - bz[s];
+        if (dx > pc.hhx) dx -= pc.hxx;
+        if (dx < -pc.hhx) dx += pc.hxx;
+        if (dy > pc.hhy) dy -= pc.hyy;
+        if (dy < -pc.hhy) dy += pc.hyy;
+        if (dz > pc.hhz) dz -= pc.hzz;
+        if (dz < -pc.hhz) dz += pc.hzz;
+        disp2 = dx * dx + dy * dy + dz * dz;
+        dispOfSlot[s] = __double2float_ru(sqrt(disp2));
+    }
+    // one atomicMax per warp, and only when it can raise the running maximum (as k_integrate)
+    for (int o = 16; o > 0; o >>= 1) disp2 = fmax(disp2, __shfl_xor_sync(0xffffffffu, disp2, o));
+    if ((threadIdx.x & 31) == 0)
+    {
+        const unsigned long long bits = (unsigned long long)__double_as_longlong(disp2);
+        if (bits > *(volatile unsigned long long *)dmax2) atomicMax(dmax2, bits);
+    }
 }
 
 __global__ void k_download_state(int n, const int *__restrict__ bead, const int *__restrict__ slotOfBead, const double4 *__restrict__ pos,
