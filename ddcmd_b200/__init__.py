@@ -142,6 +142,7 @@ def _declare(L):
         "ddcb200_nglfconstraintParms": (i32, [vp, dbl, dbl, dbl, dbl]),
         "ddcb200_nglfconstraint": (i32, [vp, i32, dbl]),
         "ddcb200_getBox": (i32, [vp, pd]),
+        "ddcb200_setBox": (i32, [vp, pd]),
         "ddcb200_constraintFailures": (i64, [vp]),
         "ddcb200_getCells": (i32, [vp, pi, pi, pd]),
         "ddcb200_getPairs": (i64, [vp, i64, pi, pi, pi]),
@@ -183,7 +184,7 @@ EXPORTS = ["ddcb200_lastError", "ddcb200_deviceCount", "ddcb200_create", "ddcb20
            "ddcb200_martiniBondParms", "ddcb200_setRestraints", "ddcb200_setMolecules", "ddcb200_sendState",
            "ddcb200_updateState", "ddcb200_numLocal", "ddcb200_getLocalBeads", "ddcb200_getState", "ddcb200_constructList", "ddcb200_ddcenergy",
            "ddcb200_nglf", "ddcb200_energyInfo", "ddcb200_setGroups", "ddcb200_setRandom", "ddcb200_getRandom", "ddcb200_setConstraints",
-           "ddcb200_nglfconstraintParms", "ddcb200_nglfconstraint", "ddcb200_getBox", "ddcb200_constraintFailures", "ddcb200_getCells", "ddcb200_getPairs", "ddcb200_profile",
+           "ddcb200_nglfconstraintParms", "ddcb200_nglfconstraint", "ddcb200_getBox", "ddcb200_setBox", "ddcb200_constraintFailures", "ddcb200_getCells", "ddcb200_getPairs", "ddcb200_profile",
            "ddcb200_profileRead", "ddcb200_timerRecord", "ddcb200_timerElapsed", "ddcb200_kernelLaunches", "ddcb200_lastListBuild", "ddcb200_ncclUniqueId", "ddcb200_ddcInit", "ddcb200_ddcPlan", "ddcb200_deckLoad", "ddcb200_deckFree",
            "ddcb200_lastHostError", "ddcb200_simulateBind", "ddcb200_simulateBindRank", "ddcb200_printinfoLine", "ddcb200_unitsConvert",
            "ddcb200_printinfoHeader", "ddcb200_writeRestart", "ddcb200_readCMDS", "ddcb200_simulateMaster", "ddcb200_listBuildInfo", "ddcb200_subsetWrite", "ddcb200_writeBXYZ", "ddcb200_pairCorrelation",

@@ -1479,6 +1479,26 @@ extern "C" int ddcb200_nglfconstraintParms(ddcb200_ctx *c, double kBT, double P0
     return DDCB200_OK;
 }
 
+// box_put(NULL, HO, &h) (src/box.c:130-150) from the host side, e.g. a barostat that runs in the caller: positions sent afterwards are
+// in the new box; the neighbor list survives, its walk bound grows by the change of the box edges since the build (listSlack)
+extern "C" int ddcb200_setBox(ddcb200_ctx *c, const double h[9])
+{
+    if (!c || !h) return fail(DDCB200_ERR_ARG, "null argument");
+    double old[9];
+    memcpy(old, c->prm.h, sizeof old);
+    memcpy(c->prm.h, h, 9 * sizeof(double));
+    const int rc = setupBox(c);
+    if (rc != DDCB200_OK)
+    {
+        memcpy(c->prm.h, old, sizeof old);
+        setupBox(c);
+        return rc;
+    }
+    c->forcesValid = false;
+    c->energyValid = false;
+    return DDCB200_OK;
+}
+
 extern "C" int ddcb200_getBox(ddcb200_ctx *c, double h[9])
 {
     if (!c || !h) return fail(DDCB200_ERR_ARG, "null argument");

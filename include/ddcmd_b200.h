@@ -191,6 +191,9 @@ int ddcb200_nglfconstraint(ddcb200_ctx *ctx, int nsteps, double dt);
 
 /* Current box matrix (the barostat changes it; box_get_h, src/box.c:173-176). */
 int ddcb200_getBox(ddcb200_ctx *ctx, double h[9]);
+/* box_put(NULL, HO, &h) from the caller's side (a barostat that runs in the host code): orthorhombic h, positions sent afterwards
+ * are in the new box, the neighbor list is kept (its walk bound grows by the change of the box edges since the build). */
+int ddcb200_setBox(ddcb200_ctx *ctx, const double h[9]);
 
 /* Constraint clusters that reached the 500-iteration cap so far (the reference prints a warning and goes on). */
 int64_t ddcb200_constraintFailures(ddcb200_ctx *ctx);

@@ -26,6 +26,7 @@
 #include "error.h"
 #include "ddc.h"
 #include "codata.h"
+#include "box.h"
 #include "../include/ddcmd_b200_host.h"
 
 static ddcb200_ctx *b200;
@@ -75,6 +76,16 @@ static void sendState(SYSTEM *sys)
 {
     STATE *s = sys->collection->state;
     mapLocals(sys);                          /* ddcMD may reorder its locals inside ddcenergy */
+    {
+        /* a host-side barostat (nglfconstraint's changeVolume) may have changed the box since the last call */
+        static THREE_MATRIX last;
+        THREE_MATRIX h = box_get_h(sys->box);
+        if (memcmp(&h, &last, sizeof h) != 0)
+        {
+            ck(ddcb200_setBox(b200, (const double *)&h), "setBox", ddcb200_lastError());
+            last = h;
+        }
+    }
     /* the first call starts the run (sendState); later calls are the per-step upload that keeps the neighbor list */
     static int started;
     if (!started)

@@ -17,9 +17,15 @@ SHIM = os.path.join(ROOT, "oracle", "_ref", "ddcMD_shim")
 SHIM_EMU = os.path.join(ROOT, "oracle", "_ref", "ddcMD_shim_emu")
 
 
-def run_deck(golden_dir, deck, tmp_path, exe, args, tag):
-    d = os.path.join(str(tmp_path), "%s_%s" % (deck, tag))
-    shutil.copytree(os.path.join(golden_dir, deck), d, symlinks=True)
+def run_deck(golden_dir, deck, tmp_path, exe, args, tag, variant=None):
+    if variant:
+        import nglfc_decks
+        sub = os.path.join(str(tmp_path), tag)
+        os.makedirs(sub)
+        d = nglfc_decks.make_variant(golden_dir, deck, variant, sub)
+    else:
+        d = os.path.join(str(tmp_path), "%s_%s" % (deck, tag))
+        shutil.copytree(os.path.join(golden_dir, deck), d, symlinks=True)
     p = os.path.join(d, "object.data")
     s = open(p).read()
     s = re.sub(r"deltaloop=\d+;", "deltaloop=25;", s)
@@ -30,11 +36,12 @@ def run_deck(golden_dir, deck, tmp_path, exe, args, tag):
     return open(os.path.join(d, "data")).read().splitlines()
 
 
-def check_shim(golden_dir, deck, tmp_path, exe):
-    ref = run_deck(golden_dir, deck, tmp_path, REF, [], "ref")
+def check_shim(golden_dir, deck, tmp_path, exe, variant=None):
+    ref = run_deck(golden_dir, deck, tmp_path, REF, [], "ref", variant)
     assert len(ref) == 7                                            # header + loops 0, 5, ..., 25 (across the rebuild at 20)
-    for mode in ("1", "2"):
-        got = run_deck(golden_dir, deck, tmp_path, exe, [mode], "mode" + mode)
+    # with the NGLFCONSTRAINT variants (Langevin groups, constraints, barostat) ddcMD's own integrator stays: mode 1 only
+    for mode in (("1",) if variant else ("1", "2")):
+        got = run_deck(golden_dir, deck, tmp_path, exe, [mode], "mode" + mode, variant)
         assert got[0] == ref[0] and len(got) == len(ref)
         for a, b in zip(got[1:], ref[1:]):
             fa, fb = a.split(), b.split()
@@ -44,7 +51,7 @@ def check_shim(golden_dir, deck, tmp_path, exe):
             assert np.all(np.abs(va[1:4] - vb[1:4]) <= 1e-9 * scale + 2e-12), (mode, a, b)     # Etotal, Ekin, Epot
             assert abs(va[4] - vb[4]) <= 1e-9 * abs(vb[4]) + 2e-8                              # temperature
             assert abs(va[5] - vb[5]) <= 1e-6 * max(abs(vb[5]), 100.0)                         # molecular pressure
-            assert np.array_equal(va[6:], vb[6:])                                              # volume, box
+            assert np.all(np.abs(va[6:] - vb[6:]) <= 1e-9 * np.abs(vb[6:]) + 2e-8)            # volume, box (barostat in the variants)
 
 
 @pytest.mark.skipif(not (os.path.exists(REF) and os.path.exists(SHIM_EMU)), reason="oracle/_ref binaries not built")
@@ -52,6 +59,20 @@ def check_shim(golden_dir, deck, tmp_path, exe):
 def test_ddcmd_with_the_emulated_library_plugged_in(golden_dir, tmp_path, deck):
     """The seam in the build container: the shim binary linked against the CPU emulation of the kernels (test infrastructure)."""
     check_shim(golden_dir, deck, tmp_path, SHIM_EMU)
+
+
+@pytest.mark.skipif(not (os.path.exists(REF) and os.path.exists(SHIM_EMU)), reason="oracle/_ref binaries not built")
+def test_shipped_configuration_with_the_emulated_library_as_potential(golden_dir, tmp_path):
+    """examples/waterbox as shipped - NGLFCONSTRAINT, LANGEVIN groups and the barostat all run by ddcMD on the host - with the
+    library as its MARTINI potential: the barostat's box reaches the library through ddcb200_setBox."""
+    check_shim(golden_dir, "waterbox", tmp_path, SHIM_EMU, "full")
+
+
+@pytest.mark.gpu
+@pytest.mark.skipif(not (os.path.exists(REF) and os.path.exists(SHIM)), reason="oracle/_ref binaries not built")
+@pytest.mark.parametrize("deck,variant", [("waterbox", "full"), ("ras_small", "full")])
+def test_ddcmd_integrators_with_the_library_as_potential(golden_dir, tmp_path, deck, variant):
+    check_shim(golden_dir, deck, tmp_path, SHIM, variant)
 
 
 @pytest.mark.gpu
