@@ -330,6 +330,29 @@ def main():
     e2e_sps = KE / max_over_ranks(t1 - t0)
     e2e = {"value": e2e_sps, "unit": "steps/s", "h2d_bytes_per_step": 6 * 8 * n / KE, "d2h_bytes_per_step": 9 * 8 * n / KE + 24 * 8 * world,
            "steps": KE, "note": "sendState(H2D, pinned) + per step [nglf(1) + energyInfo D2H] (printrate=1) + getState(D2H); bytes summed over ranks"}
+    # ---- the same through the plug-in seam of a host-side integrator (eval_potential, integration/ddcmd_shim.c mode 1): every step
+    # uploads positions and velocities from pinned host memory, evaluates forces + energies, reads the forces and energyInfo back
+    if world == 1:
+        KS = min(K, 60)
+        fpin = torch.empty(3 * nl, dtype=torch.float64).pin_memory()
+        fout = fpin.numpy().reshape(3, nl)
+        for k, name in enumerate(("rx", "ry", "rz", "vx", "vy", "vz")):
+            host[k] = st2[name]
+        l0 = int(ee.loop)
+        sim.updateState(host[0], host[1], host[2], host[3], host[4], host[5], loop=l0, time=float(ee.time))
+        sim.ddcenergy(1)
+        sim.sync()
+        t0 = time.perf_counter()
+        for s_ in range(KS):
+            sim.updateState(host[0], host[1], host[2], host[3], host[4], host[5], loop=l0 + s_ + 1, time=float(ee.time))
+            sim.ddcenergy(1)
+            ep = sim.energyInfo()
+            sim.getForces(out=fout)
+        t1 = time.perf_counter()
+        e2e["plugin_seam"] = {"value": KS / (t1 - t0), "unit": "force evaluations/s", "steps": KS, "h2d_bytes_per_step": 6 * 8 * nl,
+                              "d2h_bytes_per_step": 3 * 8 * nl + 24 * 8,
+                              "note": "per step: updateState(H2D r, v, pinned) + ddcenergy + energyInfo(D2H) + forces(D2H, pinned) = the eval_potential seam "
+                                      "with ddcMD's own integrator on the host; the list is rebuilt every 20 loops as in a device-resident run"}
     sim.close()
     if rank != 0:
         return

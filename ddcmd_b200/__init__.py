@@ -383,6 +383,29 @@ class Simulate:
         self._ck(lib().ddcb200_sendState(self.ctx, a[0].size, b.ctypes.data_as(_P(C.c_int)) if b is not None else None,
                                          *[x.ctypes.data_as(pd) for x in a], int(loop), float(time)))
 
+    def updateState(self, rx, ry, rz, vx, vy, vz, loop=0, time=0.0, bead=None):
+        """per-step upload of a host-side integrator (keeps cells and the neighbor list, unlike sendState)"""
+        a = [np.ascontiguousarray(x, np.float64) for x in (rx, ry, rz, vx, vy, vz)]
+        pd = _P(C.c_double)
+        b = np.ascontiguousarray(bead, np.int32) if bead is not None else None
+        self._ck(lib().ddcb200_updateState(self.ctx, a[0].size, b.ctypes.data_as(_P(C.c_int)) if b is not None else None,
+                                           *[x.ctypes.data_as(pd) for x in a], int(loop), float(time)))
+
+    def setBox(self, h):
+        hh = np.ascontiguousarray(h, np.float64)
+        self._ck(lib().ddcb200_setBox(self.ctx, hh.ctypes.data_as(_P(C.c_double))))
+
+    def getForces(self, out=None):
+        """fx fy fz of the local beads as a (3, numLocal) array (`out`: caller-owned, e.g. pinned)"""
+        n = int(lib().ddcb200_numLocal(self.ctx))
+        if out is None:
+            out = np.empty((3, n), np.float64)
+        elif out.shape != (3, n) or out.dtype != np.float64 or not out.flags["C_CONTIGUOUS"]:
+            raise DdcError("getForces: out must be a C-contiguous float64 array of shape (3, %d)" % n)
+        pd = _P(C.c_double)
+        self._ck(lib().ddcb200_getState(self.ctx, None, None, None, None, None, None, *[out[k].ctypes.data_as(pd) for k in range(3)]))
+        return out
+
     def numLocal(self):
         return int(lib().ddcb200_numLocal(self.ctx))
 
