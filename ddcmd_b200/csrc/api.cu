@@ -951,10 +951,18 @@ extern "C" int ddcb200_constructList(ddcb200_ctx *c)
                 // on the device.  A difference (none is known; the two builds are bit-identical in every test) makes the context
                 // keep the two-pass build, says so on stderr, and rebuilds this list with it.
                 c->cellBuildChecked = true;
-                DevBuf<uint32_t> rows2;
-                DevBuf<int> count2;
-                DevBuf<uint16_t> cum2;
-                DevBuf<int> bad;
+                struct Scratch
+                {
+                    DevBuf<uint32_t> rows2;
+                    DevBuf<int> count2;
+                    DevBuf<uint16_t> cum2;
+                    DevBuf<int> bad;
+                    ~Scratch() { rows2.release(); count2.release(); cum2.release(); bad.release(); }
+                } scratch;
+                DevBuf<uint32_t> &rows2 = scratch.rows2;
+                DevBuf<int> &count2 = scratch.count2;
+                DevBuf<uint16_t> &cum2 = scratch.cum2;
+                DevBuf<int> &bad = scratch.bad;
                 CK(rows2.ensure((size_t)c->nbrCap * nPad));
                 CK(count2.ensure((size_t)nPad));
                 CK(cum2.ensure((size_t)NBINS * nPad));
@@ -973,7 +981,6 @@ extern "C" int ddcb200_constructList(ddcb200_ctx *c)
                 CK(cudaMemcpyAsync(&nbad, bad.p, sizeof(int), cudaMemcpyDeviceToHost, st));
                 CK(cudaMemcpyAsync(&after, c->grid, sizeof(GridDev), cudaMemcpyDeviceToHost, st));
                 CK(cudaStreamSynchronize(st));
-                rows2.release(); count2.release(); cum2.release(); bad.release();
                 const char *inject = getenv("DDCB200_SELFCHECK_FAULT");      // test hook: pretend the check failed
                 if (nbad != 0 || (after.error & 1) || (inject && inject[0] == '1'))
                 {
@@ -1803,8 +1810,14 @@ extern "C" int ddcb200_pairCorrelation(ddcb200_ctx *c, int nBins, double rmin, d
         return fail(DDCB200_ERR_ARG, "pairCorrelation: rmax exceeds half the shortest box edge");
     const int ns = c->nspecies;
     const size_t nh = (size_t)nBins * (size_t)(ns * (ns + 1) / 2);
-    DevBuf<unsigned long long> hist;
-    DevBuf<int> spec;
+    struct Scratch
+    {
+        DevBuf<unsigned long long> hist;
+        DevBuf<int> spec;
+        ~Scratch() { hist.release(); spec.release(); }      // also on the early returns of CK
+    } scratch;
+    DevBuf<unsigned long long> &hist = scratch.hist;
+    DevBuf<int> &spec = scratch.spec;
     CK(hist.ensure(nh + (size_t)ns));
     CK(spec.ensure((size_t)c->nGlobal + 1));
     CK(cudaMemsetAsync(hist.p, 0, (nh + (size_t)ns) * sizeof(unsigned long long), st));
@@ -1817,8 +1830,6 @@ extern "C" int ddcb200_pairCorrelation(ddcb200_ctx *c, int nBins, double rmin, d
     CK(cudaMemcpyAsync(counts, hist.p, nh * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
     CK(cudaMemcpyAsync(nAtoms, hist.p + nh, (size_t)ns * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
-    hist.release();
-    spec.release();
     return DDCB200_OK;
 }
 
