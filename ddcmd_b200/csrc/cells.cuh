@@ -554,11 +554,21 @@ k_nbr_cell(int nIon, int nPad, int cap, const double4 *__restrict__ pos, const i
                             else if (ax >= nx) ax -= nx;
                             const int cc = ax + nx * (ay + ny * az);
                             const int jlo = cellStart[cc], jhi = cellStart[cc + 1];
+                            if (jlo >= jhi) continue;
+                            // double-buffered: the next CELL_PF candidate positions are in flight while this batch is tested
+                            double4 nxt[CELL_PF];
+#pragma unroll
+                            for (int u = 0; u < CELL_PF; u++) nxt[u] = ldPos256(pos + min(jlo + u, jhi - 1));
                             for (int j0 = jlo; j0 < jhi; j0 += CELL_PF)
                             {
                                 double4 pjv[CELL_PF];
 #pragma unroll
-                                for (int u = 0; u < CELL_PF; u++) pjv[u] = ldPos256(pos + min(j0 + u, jhi - 1));
+                                for (int u = 0; u < CELL_PF; u++) pjv[u] = nxt[u];
+                                if (j0 + CELL_PF < jhi)
+                                {
+#pragma unroll
+                                    for (int u = 0; u < CELL_PF; u++) nxt[u] = ldPos256(pos + min(j0 + CELL_PF + u, jhi - 1));
+                                }
 #pragma unroll
                                 for (int u = 0; u < CELL_PF; u++)
                                 {
