@@ -894,7 +894,7 @@ extern "C" int ddcb200_constructList(ddcb200_ctx *c)
         CK(c->nbr.ensure((size_t)c->nbrCap * nPad));
         // one-pass build: one warp per cell, staging rows of `cap` entries per lane in shared memory: as many warps per CTA as
         // ~110 KB hold (two CTAs per SM), a persistent grid striding over the cells
-        const size_t perWarp = (size_t)c->nbrCap * 32 * sizeof(uint32_t);
+        const size_t perWarp = ((size_t)c->nbrCap * 32 + 4 * CELL_TAB) * sizeof(uint16_t);
         const int wpb = (int)std::min<size_t>(8, std::max<size_t>(1, (size_t)(110 * 1024) / perWarp));
         const size_t smem = perWarp * wpb;
         if (variant == 1) CK(c->nbrRaw.ensure((size_t)c->nbrCap * nPad));
@@ -943,6 +943,20 @@ extern "C" int ddcb200_constructList(ddcb200_ctx *c)
         CK(cudaMemcpyAsync(c->gridHost, c->grid, sizeof(GridDev), cudaMemcpyDeviceToHost, st));
         CK(cudaStreamSynchronize(st));
         if (c->gridHost->error & 2) return fail(DDCB200_ERR_CAPACITY, "cell grid larger than the bead count bound");
+        if (c->gridHost->error & 4)
+        {
+            // a cell neighbourhood holds more beads than the one-pass build's 12-bit candidate ordinals can number
+            if (c->listBuildMode == 2) return fail(DDCB200_ERR_CAPACITY, "one-pass list build: more than 4096 beads in a 27-cell neighbourhood (use DDCB200_LISTBUILD=twopass)");
+            c->listBuildMode = 1;
+            variant = 1;
+            timeIt = false;
+            CK(cudaMemsetAsync(&c->grid->error, 0, sizeof(int), st));
+            CK(cudaMemsetAsync(&c->grid->maxCount, 0, sizeof(int), st));
+            CK(cudaMemsetAsync(&c->grid->maxRaw, 0, sizeof(int), st));
+            CK(cudaMemsetAsync(&c->grid->totalEntries, 0, sizeof(unsigned long long), st));
+            attempt--;
+            continue;
+        }
         if (!(c->gridHost->error & 1))
         {
             if (variant == 2 && c->listBuildMode == 0 && !c->cellBuildChecked)

@@ -473,7 +473,8 @@ k_nbr_exact(int nIon, int nPad, int cap, const double4 *__restrict__ pos, BoxCon
 // (compared on the bit patterns: exact for positive doubles) and the pruning flag are those of k_nbr_filter +
 // k_nbr_exact, so both builds write bit-identical rows (tests/test_gpu_parity.py::test_list_builds_agree_bit_for_bit).
 // Cells with more than 32 beads take several passes over their stencil.
-#define CELL_PF 4      // candidate positions in flight per warp
+#define CELL_PF 4      // candidate positions per batch (two batches in flight per warp)
+#define CELL_TAB 32    // entries of the per-warp stencil tables (<= 27 cells + the end marker)
 
 // bin of r2 among the 7 ascending edges = number of edges <= r2, on the bit patterns (exact for positive doubles): a
 // three-level tree on the high words; only when a compared high word ties do the full 64-bit patterns decide
@@ -501,15 +502,20 @@ __device__ __forceinline__ int binOfBits(double r2, const int *eh, const double 
     return bin;
 }
 
-__global__ void __launch_bounds__(256, 1)
+__global__ void __launch_bounds__(256, 2)   // two 8-warp CTAs per SM: at most 128 registers
 k_nbr_cell(int nIon, int nPad, int cap, const double4 *__restrict__ pos, const int *__restrict__ cellStart, BoxConst b, GridDev *gp,
            uint32_t *__restrict__ out, int *__restrict__ count, uint16_t *__restrict__ cum, const uint64_t *__restrict__ gid,
            const int *__restrict__ molTypeOfBead, const int *__restrict__ molTypeSingle, const int *__restrict__ bpairOffset,
            const uint32_t *__restrict__ bpairKey, int haveExcl)
 {
-    EXTERN_SHARED(uint32_t, stageAll);                    // [warps per block][cap][32]
+    // per warp: 16-bit staged entries [cap][32] (candidate ordinal of this chunk's stencil walk : 12, bin : 3, pruned : 1), then the
+    // stencil tables that turn an ordinal back into a slot: first ordinal and first slot of each of the <= 27 stencil cells
+    EXTERN_SHARED(uint16_t, stageAll);
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, wpb = blockDim.x >> 5;
-    uint32_t *stage = stageAll + (size_t)wib * cap * 32 + lane;
+    const size_t warpU16 = (size_t)cap * 32 + 4 * CELL_TAB;        // uint16 units: the staged rows + two tables of CELL_TAB ints
+    uint16_t *stage = stageAll + (size_t)wib * warpU16 + lane;
+    int *pref = (int *)(stageAll + (size_t)wib * warpU16 + (size_t)cap * 32);
+    int *base0 = pref + CELL_TAB;
     if (gp->error & 2) return;
     const int nx = gp->n[0], ny = gp->n[1], nz = gp->n[2];
     const int ncell = nx * ny * nz;
@@ -534,7 +540,8 @@ k_nbr_cell(int nIon, int nPad, int cap, const double4 *__restrict__ pos, const i
             const bool act = have && !(wi >> 63);            // ghost slots own no row
             const uint32_t molI = (uint32_t)wi & 0xffff0000u;
             int cnt = 0;
-            uint32_t *sp = stage;
+            uint16_t *sp = stage;
+            int ord0 = 0, ncellsWalked = 0;          // warp-uniform: candidates walked so far, stencil cells walked so far
             if (__any_sync(0xffffffffu, act))
             {
                 for (int dz = lz; dz <= hz; dz++)
@@ -554,7 +561,15 @@ k_nbr_cell(int nIon, int nPad, int cap, const double4 *__restrict__ pos, const i
                             else if (ax >= nx) ax -= nx;
                             const int cc = ax + nx * (ay + ny * az);
                             const int jlo = cellStart[cc], jhi = cellStart[cc + 1];
+                            if (lane == 0)
+                            {
+                                pref[ncellsWalked] = ord0;
+                                base0[ncellsWalked] = jlo;
+                            }
+                            ncellsWalked++;
                             if (jlo >= jhi) continue;
+                            const int ordBase = ord0 - jlo;
+                            ord0 += jhi - jlo;
                             // double-buffered: the next CELL_PF candidate positions are in flight while this batch is tested
                             double4 nxt[CELL_PF];
 #pragma unroll
@@ -585,16 +600,16 @@ k_nbr_cell(int nIon, int nPad, int cap, const double4 *__restrict__ pos, const i
                                     if (r2 < b.rlist2 && act && j < jhi && j != i)
                                     {
                                         const int bin = binOfBits(r2, eh, b.binEdge2);
-                                        uint32_t ent = (uint32_t)j | ((uint32_t)bin << 27);
+                                        uint32_t ent = (uint32_t)(ordBase + j) | ((uint32_t)bin << 12);
                                         if (haveExcl && ((uint32_t)__double_as_longlong(pj.w) & 0xffff0000u) == molI)
                                         {
                                             // same low 16 bits of the molecule id: the gid tables decide (reOrgPairs)
                                             const uint64_t wj = (uint64_t)__double_as_longlong(pj.w);
                                             if (isPruned((int)((wi >> 32) & 0x7fffffffull), (int)((wj >> 32) & 0x7fffffffull), gid, molTypeOfBead,
                                                          molTypeSingle, bpairOffset, bpairKey))
-                                                ent |= EXCL_BIT;
+                                                ent |= 0x8000u;
                                         }
-                                        if (cnt < cap) *sp = ent;
+                                        if (cnt < cap) *sp = (uint16_t)ent;
                                         sp += 32;
                                         cnt++;
                                     }
@@ -604,6 +619,9 @@ k_nbr_cell(int nIon, int nPad, int cap, const double4 *__restrict__ pos, const i
                     }
                 }
             }
+            if (lane == 0) pref[ncellsWalked] = ord0;
+            if (ord0 > 4096) cnt = max(cnt, cap + 1) | 0x40000000;      // ordinals no longer fit 12 bits: reported as an overflow the host cannot grow away
+            __syncwarp();
             if (have)
             {
                 // per-bin counts from the staged entries (eight 16-bit counters in two words, as k_nbr_exact), exclusive prefix,
@@ -612,7 +630,7 @@ k_nbr_cell(int nIon, int nPad, int cap, const double4 *__restrict__ pos, const i
                 uint64_t A = 0ull, B = 0ull;
                 for (int k = 0; k < stored; k++)
                 {
-                    const int bin = (stage[(size_t)k * 32] >> 27) & 7;
+                    const int bin = (stage[(size_t)k * 32] >> 12) & 7;
                     const uint64_t one = 1ull << (16 * (bin & 3));
                     if (bin < 4) A += one;
                     else B += one;
@@ -627,11 +645,15 @@ k_nbr_cell(int nIon, int nPad, int cap, const double4 *__restrict__ pos, const i
                     const int sh = 16 * (bnd & 3);
                     cum[(size_t)bnd * nPad + i] = (uint16_t)(((off >> sh) & 0xffffull) + ((cn >> sh) & 0xffffull));
                 }
+                int sc = 0;                              // staged ordinals ascend: the stencil cell of an entry is found by a running pointer
                 if (cnt <= cap)
                     for (int k = 0; k < stored; k++)
                     {
                         const uint32_t e = stage[(size_t)k * 32];
-                        const int bin = (e >> 27) & 7;
+                        const int ord = (int)(e & 0x0fffu);
+                        while (ord >= pref[sc + 1]) sc++;
+                        const uint32_t j = (uint32_t)(base0[sc] + (ord - pref[sc]));
+                        const int bin = (e >> 12) & 7;
                         const int sh = 16 * (bin & 3);
                         int dst;
                         if (bin < 4)
@@ -644,12 +666,13 @@ k_nbr_cell(int nIon, int nPad, int cap, const double4 *__restrict__ pos, const i
                             dst = (int)((offB >> sh) & 0xffffull);
                             offB += 1ull << sh;
                         }
-                        out[(size_t)dst * nPad + i] = (e & 0x07ffffffu) | (e & EXCL_BIT);
+                        out[(size_t)dst * nPad + i] = j | ((e & 0x8000u) ? EXCL_BIT : 0u);
                     }
-                count[i] = cnt;
+                count[i] = cnt & 0x3fffffff;
             }
+            __syncwarp();                                // the tables are rewritten by the next chunk
             statMax = max(statMax, cnt);
-            statTotal += (unsigned long long)cnt;
+            statTotal += (unsigned long long)(cnt & 0x3fffffff);
         }
     }
     for (int o = 16; o > 0; o >>= 1)
@@ -659,6 +682,8 @@ k_nbr_cell(int nIon, int nPad, int cap, const double4 *__restrict__ pos, const i
     }
     if (lane == 0 && statMax > 0)
     {
+        if (statMax & 0x40000000) atomicOr(&gp->error, 4);      // a cell neighbourhood with more than 4096 beads: not for this build
+        statMax &= 0x3fffffff;
         atomicMax(&gp->maxCount, statMax);
         atomicMax(&gp->maxRaw, statMax);            // drives the capacity regrow, like the candidate count of the two-pass build
         atomicAdd(&gp->totalEntries, statTotal);
