@@ -242,6 +242,8 @@ def main():
     log("[bench] rank %d deck parsed: %d beads, %d bonded terms in %.1fs" % (rank, n, deck.s.nTerms, time.time() - t))
     lattice = dd.default_lattice(world, [deck.s.params.h[0], deck.s.params.h[4], deck.s.params.h[8]]) if world > 1 else (1, 1, 1)
     sim = dd.Simulate(deck, device=local, rank=rank, nranks=world, lattice=lattice, nccl_id=nccl_id)
+    if os.environ.get("DDCB200_BENCH_RETRY"):
+        config["fallback"] = "first attempt failed; this run uses DDCB200_LISTBUILD=twopass DDCB200_WALK=global"
     config["parallelism"] = "ddc bricks %dx%dx%d, one process per GPU, ghost halo per step over NCCL" % lattice if world > 1 else "single GPU"
 
     # ---- device-resident throughput ------------------------------------------------------
@@ -377,4 +379,17 @@ def main():
 
 
 if __name__ == "__main__":
-    main()
+    try:
+        main()
+    except Exception as ex:
+        # Single-GPU safety net: the list-build and walk variants added without a GPU at hand are result-neutral but had never run
+        # on a B200 when this was written.  If the run dies, repeat it ONCE in a fresh process (a CUDA error is sticky) with the
+        # variants that produced the committed profiles, and say so on stderr; the JSON line then carries config.fallback.
+        if int(os.environ.get("WORLD_SIZE", "1")) == 1 and "--impl" not in " ".join(sys.argv) and not os.environ.get("DDCB200_BENCH_RETRY"):
+            import traceback
+            traceback.print_exc()
+            log("[bench] run failed (%s); repeating once with DDCB200_LISTBUILD=twopass DDCB200_WALK=global" % ex)
+            env = dict(os.environ, DDCB200_BENCH_RETRY="1", DDCB200_LISTBUILD="twopass", DDCB200_WALK="global")
+            sys.stdout.flush()
+            os.execve(sys.executable, [sys.executable] + sys.argv, env)
+        raise
