@@ -228,3 +228,27 @@ def test_readCMDS(tmp_path):
 def test_printinfo_header_matches_reference(golden_dir, gold):
     dk = dd.Deck(os.path.join(golden_dir, "popc_small", "object.data"))
     assert dk.printinfoHeader() == gold["popc_small"]["run"]["data"].splitlines()[0]
+
+
+def test_writer_argument_errors(golden_dir, tmp_path):
+    """bad arguments come back as errors with text, never as a crash or a half-written file"""
+    import ctypes as C
+    d = stage(golden_dir, "popc_small", None, tmp_path)
+    dk = dd.Deck(os.path.join(d, "object.data"))
+    L = dd.lib()
+    pd = C.POINTER(C.c_double)
+    h = np.array(dk.s.params.h[:])
+    a = [np.ascontiguousarray(dk.array(k)) for k in ("rx", "ry", "rz", "vx", "vy", "vz")]
+    ptr = [x.ctypes.data_as(pd) for x in a]
+    assert L.ddcb200_subsetWrite(dk._p, 0, None, 0, 0.0, h.ctypes.data_as(pd), *ptr) < 0          # the deck has no subsetWrite analysis
+    assert b"no such ANALYSIS" in L.ddcb200_lastHostError()
+    g = np.zeros(10)
+    assert L.ddcb200_pairCorrelationWrite(dk._p, 3, None, 0, 1.0, g.ctypes.data_as(pd), 1) < 0
+    hb = h.copy()
+    hb[1] = 0.5                                                                               # not orthorhombic
+    assert L.ddcb200_writeRestart(dk._p, None, 0, 0.0, hb.ctypes.data_as(pd), *ptr, None, 0, None, 0) < 0
+    assert b"orthorhombic" in L.ddcb200_lastHostError()
+    assert L.ddcb200_writeBXYZ(dk._p, None, 0, 0.0, None, *ptr) < 0
+    assert not [x for x in os.listdir(d) if x.startswith("snapshot.0")]
+    with pytest.raises(dd.DdcError, match="cannot create"):
+        dk.writeRestart(dirname="/nonexistent_dir_xyz/snap")
