@@ -153,6 +153,7 @@ def _declare(L):
         "ddcb200_kernelLaunches": (i64, [vp]),
         "ddcb200_lastListBuild": (i64, [vp]),
         "ddcb200_listBuildInfo": (i32, [vp, pi, pd]),
+        "ddcb200_kineticByClass": (i32, [vp, i32, i32, pd]),
         "ddcb200_pairCorrelation": (i32, [vp, i32, dbl, dbl, i32, dbl, _P(C.c_uint64), _P(C.c_uint64)]),
         "ddcb200_pairCorrelationWrite": (i32, [_P(DeckStruct), i32, C.c_char_p, i64, dbl, pd, i32]),
         "ddcb200_ncclUniqueId": (i32, [C.c_char_p]),
@@ -188,7 +189,7 @@ EXPORTS = ["ddcb200_lastError", "ddcb200_deviceCount", "ddcb200_create", "ddcb20
            "ddcb200_profileRead", "ddcb200_timerRecord", "ddcb200_timerElapsed", "ddcb200_kernelLaunches", "ddcb200_lastListBuild", "ddcb200_ncclUniqueId", "ddcb200_ddcInit", "ddcb200_ddcPlan", "ddcb200_deckLoad", "ddcb200_deckFree",
            "ddcb200_lastHostError", "ddcb200_simulateBind", "ddcb200_simulateBindRank", "ddcb200_printinfoLine", "ddcb200_unitsConvert",
            "ddcb200_printinfoHeader", "ddcb200_writeRestart", "ddcb200_readCMDS", "ddcb200_simulateMaster", "ddcb200_listBuildInfo", "ddcb200_subsetWrite", "ddcb200_writeBXYZ", "ddcb200_pairCorrelation",
-           "ddcb200_pairCorrelationWrite"]
+           "ddcb200_pairCorrelationWrite", "ddcb200_kineticByClass"]
 
 
 def _arr(ptr, n, dtype):
@@ -496,6 +497,14 @@ class Simulate:
             raise DdcError("writeRestart: some beads are local on no rank")
         return self.deck.writeRestart(*[full[k] for k in keys], loop=int(e.loop), time=float(e.time), h=self.getBox(), dirname=dirname,
                                       restart_link=restart_link)
+
+    def kineticByClass(self, by_species=False):
+        """per-GROUP or per-SPECIES kinetic terms of kinetic_terms (src/energy.c:116-143): array [class, 12] =
+        rk, mass, number, sum m v_a v_b (xx yy zz xy xz yz), sum K v (x y z)"""
+        n = int(self.deck.s.nspecies) if by_species else max(1, int(self.deck.s.nGroups))
+        out = np.zeros((n, 12), np.float64)
+        self._ck(lib().ddcb200_kineticByClass(self.ctx, int(bool(by_species)), n, out.ctypes.data_as(_P(C.c_double))))
+        return out
 
     def pairCorrelation(self, nbins, rmin, delta, rmax, log_scale=False):
         """paircorrelation_eval's counts (src/paircorrelation.c:158-420): (counts[np, nbins] uint64, atoms per species uint64), internal units."""

@@ -75,3 +75,45 @@ k_paircorr(int nIon, const double4 *__restrict__ pos, const int *__restrict__ ce
         }
     }
 }
+
+// ---- per-group / per-species kinetic terms and the thermal flux ---------------------------------------------------------
+// kinetic_terms (src/energy.c:48-163) also files rk, mass, number and the kinetic stress under the bead's GROUP and SPECIES and
+// sums the thermal flux J = sum (K + U) v - S v / 2 (U and S, the per-particle energy and stress, are not kept by the Martini
+// path: they stay zero, so J = sum K v).  One CTA per class (group or species) strides over the slots in a fixed thread -> slot
+// assignment and reduces in a fixed tree: deterministic.  out[class][13] = rk, mass, number, m v_a v_b (xx yy zz xy xz yz), K v (xyz), pad.
+__global__ void __launch_bounds__(256)
+k_kinetic_classes(int nIon, const double4 *__restrict__ pos, const double *__restrict__ vx, const double *__restrict__ vy, const double *__restrict__ vz,
+                  const double *__restrict__ massOfBead, const int *__restrict__ classOfBead, double *__restrict__ out)
+{
+    const int cls = blockIdx.x;
+    double a[12];
+#pragma unroll
+    for (int k = 0; k < 12; k++) a[k] = 0.0;
+    for (int i = threadIdx.x; i < nIon; i += blockDim.x)
+    {
+        const uint64_t w = (uint64_t)__double_as_longlong(pos[i].w);
+        if (w >> 63) continue;
+        const int bead = (int)((w >> 32) & 0x7fffffffull);
+        if (classOfBead[bead] != cls) continue;
+        const double m = massOfBead[bead], x = vx[i], y = vy[i], z = vz[i];
+        const double K = 0.5 * m * (x * x + y * y + z * z);
+        a[0] += K; a[1] += m; a[2] += 1.0;
+        a[3] += m * x * x; a[4] += m * y * y; a[5] += m * z * z; a[6] += m * x * y; a[7] += m * x * z; a[8] += m * y * z;
+        a[9] += K * x; a[10] += K * y; a[11] += K * z;
+    }
+    __shared__ double red[12][8];
+#pragma unroll
+    for (int k = 0; k < 12; k++)
+    {
+        double t = a[k];
+        for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+        if ((threadIdx.x & 31) == 0) red[k][threadIdx.x >> 5] = t;
+    }
+    __syncthreads();
+    if (threadIdx.x < 12)
+    {
+        double t = 0.0;
+        for (int w = 0; w < 8; w++) t += red[threadIdx.x][w];
+        out[(size_t)cls * 12 + threadIdx.x] = t;
+    }
+}

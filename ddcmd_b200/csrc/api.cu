@@ -1785,6 +1785,41 @@ extern "C" int64_t ddcb200_kernelLaunches(ddcb200_ctx *c) { return c ? c->kernel
 
 extern "C" int64_t ddcb200_lastListBuild(ddcb200_ctx *c) { return c ? c->lastBuildLoop : -1; }
 
+extern "C" int ddcb200_kineticByClass(ddcb200_ctx *c, int bySpecies, int nClasses, double *out12)
+{
+    if (!c || !out12 || nClasses < 1) return fail(DDCB200_ERR_ARG, "kineticByClass: bad arguments");
+    if (c->nLocal == 0) return fail(DDCB200_ERR_STATE, "no state");
+    if (bySpecies ? nClasses != c->nspecies : nClasses != std::max(1, c->nGroups)) return fail(DDCB200_ERR_ARG, "kineticByClass: class count does not match the deck");
+    CK(cudaSetDevice(c->device));
+    cudaStream_t st = c->stream;
+    if (c->pendingKick2) return fail(DDCB200_ERR_STATE, "kineticByClass: velocities are mid-step");
+    struct Scratch
+    {
+        DevBuf<int> cls;
+        DevBuf<double> out;
+        ~Scratch() { cls.release(); out.release(); }
+    } sc;
+    std::vector<int> h((size_t)c->nGlobal);
+    if (bySpecies) h = c->hSpecies;
+    else if (c->groupOfBead.p)
+    {
+        std::vector<unsigned char> g((size_t)c->nGlobal);
+        CK(cudaMemcpy(g.data(), c->groupOfBead.p, (size_t)c->nGlobal, cudaMemcpyDeviceToHost));
+        for (size_t i = 0; i < g.size(); i++) h[i] = g[i];
+    }
+    else std::fill(h.begin(), h.end(), 0);
+    CK(sc.cls.ensure((size_t)c->nGlobal + 1));
+    CK(sc.out.ensure((size_t)nClasses * 12));
+    CK(cudaMemcpyAsync(sc.cls.p, h.data(), (size_t)c->nGlobal * sizeof(int), cudaMemcpyHostToDevice, st));
+    const int cur = c->cur;
+    LAUNCH(k_kinetic_classes, nClasses, 256, 0, st)((int)c->nIon, c->pos4[cur].p, c->vel[cur][0].p, c->vel[cur][1].p, c->vel[cur][2].p, c->massOfBead.p,
+                                                sc.cls.p, sc.out.p);
+    CKL("k_kinetic_classes");
+    CK(cudaMemcpyAsync(out12, sc.out.p, (size_t)nClasses * 12 * sizeof(double), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    return DDCB200_OK;
+}
+
 extern "C" int ddcb200_pairCorrelation(ddcb200_ctx *c, int nBins, double rmin, double delta, int logScale, double rmax,
                                        unsigned long long *counts, unsigned long long *nAtoms)
 {

@@ -222,6 +222,12 @@ int64_t ddcb200_kernelLaunches(ddcb200_ctx *ctx);
  * check4updateNeighbor / evalUpdateFlag (src/ddcUpdateAll.c:48-71). */
 int64_t ddcb200_lastListBuild(ddcb200_ctx *ctx);
 
+/* The per-GROUP (bySpecies = 0) or per-SPECIES (1) copies kinetic_terms files (src/energy.c:116-143) and each class's share of the
+ * thermal flux (src/energy.c:104-106; the Martini path keeps no per-particle energy or stress, so J = sum K v), from the local beads'
+ * current velocities.  out12[class * 12 + k]: k = 0 rk, 1 mass, 2 number, 3-8 sum m v_a v_b (xx yy zz xy xz yz), 9-11 sum K v.
+ * nClasses = the deck's group count (at least 1) or species count.  Sums are taken in a fixed order: reproducible. */
+int ddcb200_kineticByClass(ddcb200_ctx *ctx, int bySpecies, int nClasses, double *out12);
+
 /* Replaces the pair loops of paircorrelation_eval (src/paircorrelation.c:158-420, methods geom / grid / neighborList alike):
  * counts[bin + nBins * comboIndex(si, sj)] over the local beads' pairs with gid_i < gid_j and r < rmax, 2 per same-species pair
  * and 1 otherwise; bin = (int)((r - rmin) / delta), or (int)((log10 r - log10 rmin) / delta) with logScale; nAtoms[species] =

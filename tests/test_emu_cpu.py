@@ -113,6 +113,11 @@ def test_emu_subsetWrite(emu, golden_dir, tmp_path):
     tm.check_subset(golden_dir, tmp_path)
 
 
+def test_emu_kinetic_classes(emu, golden_dir, tmp_path):
+    import test_zzzzzz_master as tm
+    tm.check_kinetic_classes(golden_dir, tmp_path)
+
+
 def test_emu_paircorrelation(emu, golden_dir, tmp_path):
     import test_zzzzzz_master as tm
     tm.check_paircorr(golden_dir, tmp_path)

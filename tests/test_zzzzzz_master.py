@@ -210,3 +210,40 @@ def check_paircorr(golden_dir, tmp_path):
 
 def test_paircorrelation_matches_reference(golden_dir, tmp_path):
     check_paircorr(golden_dir, tmp_path)
+
+
+def check_kinetic_classes(golden_dir, tmp_path):
+    """per-GROUP / per-SPECIES kinetic terms and thermal flux (kinetic_terms, src/energy.c:116-143) against numpy on the same state"""
+    d = nglfc_decks.make_variant(golden_dir, "popc_small", "lang", tmp_path)      # two GROUP objects (every bead names the first), 28 species
+    sim = dd.simulate_init(os.path.join(d, "object.data"))
+    sim.ddcenergy(1)
+    sim.eval_integrator(7)
+    e = sim.energyInfo()
+    st = sim.getState()
+    dk = sim.deck
+    sp = dk.array("species").astype(np.int64)
+    m = dk.array("specMass")[sp]
+    grp = dk.array("groupOfBead").astype(np.int64)
+    v = np.stack([st["vx"], st["vy"], st["vz"]], 1)
+    K = 0.5 * m * (v ** 2).sum(1)
+    for by_species, cls, n in ((False, grp, int(dk.s.nGroups)), (True, sp, int(dk.s.nspecies))):
+        got = sim.kineticByClass(by_species)
+        assert got.shape == (n, 12)
+        want = np.zeros((n, 12))
+        np.add.at(want[:, 0], cls, K)
+        np.add.at(want[:, 1], cls, m)
+        np.add.at(want[:, 2], cls, 1.0)
+        for k, (a, b) in enumerate(((0, 0), (1, 1), (2, 2), (0, 1), (0, 2), (1, 2))):
+            np.add.at(want[:, 3 + k], cls, m * v[:, a] * v[:, b])
+        for a in range(3):
+            np.add.at(want[:, 9 + a], cls, K * v[:, a])
+        scale = np.abs(want).max(0) + 1e-300
+        assert np.all(np.abs(got - want) <= 1e-12 * scale)
+        assert np.array_equal(got[:, 2], want[:, 2])
+        assert abs(got[:, 0].sum() - e.rk) <= 1e-12 * e.rk                        # the classes partition the system
+        assert np.allclose(got[:, 3:9].sum(0), np.array(e.tion[:]), rtol=1e-12, atol=1e-12 * abs(e.tion[0]))
+    sim.close()
+
+
+def test_kinetic_terms_by_group_and_species(golden_dir, tmp_path):
+    check_kinetic_classes(golden_dir, tmp_path)
