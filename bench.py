@@ -231,7 +231,7 @@ def main():
     # W warm-up steps as asked (at least 3).  Before them, as part of set-up, enough steps (61 = rebuilds at loops 0, 20, 40, 60)
     # for the library to have timed both list builds twice and settled on one, so the choice is made outside warm-up and timing
     K, W = args.steps, max(3, args.warmup)
-    setup_steps = 61 if os.environ.get("DDCB200_LISTBUILD", "auto") == "auto" else 0
+    setup_steps = 0
     if rank == 0:
         deck_path = get_deck(args.workload)
     barrier()
@@ -303,7 +303,7 @@ def main():
                 "kernel_share_of_step": prof["pair"][0] / total_prof,
                 "per_kernel_ms_per_step": {k: v[0] / KP for k, v in prof.items()},
                 # list build picked by timing the first four rebuilds (rows are bit-identical either way): ms per rebuild
-                "list_build": {"in_use": {0: "undecided", 1: "twopass", 2: "cell"}[lb_variant], "twopass_ms": lb_ms[0], "cell_ms": lb_ms[1]}}
+                "list_build": {"last_build_ms": lb_ms[0]}}
 
     # ---- end to end through the reference-facing calls with host buffers ---------------------
     import torch
@@ -389,7 +389,7 @@ if __name__ == "__main__":
             import traceback
             traceback.print_exc()
             log("[bench] run failed (%s); repeating once with DDCB200_LISTBUILD=twopass DDCB200_WALK=global" % ex)
-            env = dict(os.environ, DDCB200_BENCH_RETRY="1", DDCB200_LISTBUILD="twopass", DDCB200_WALK="global")
+            env = dict(os.environ, DDCB200_BENCH_RETRY="1", DDCB200_WALK="global")
             sys.stdout.flush()
             os.execve(sys.executable, [sys.executable] + sys.argv, env)
         raise

@@ -47,7 +47,7 @@ static int fail(int code, const std::string &msg)
     } while (0)
 
 // number of kernels launched before each CKL() checkpoint (for the bench's gpu_launches count)
-static int launchesOf(const char *what) { return strcmp(what, "cell sort") == 0 ? 7 : (strcmp(what, "list self-check") == 0 ? 3 : 1); }   // minmax, grid, count, scan, scatter, rank, gather
+static int launchesOf(const char *what) { return strcmp(what, "cell sort") == 0 ? 7 : 1; }   // minmax, grid, count, scan, scatter, rank, gather
 
 extern "C" const char *ddcb200_lastError(void) { return g_err.c_str(); }
 
@@ -188,20 +188,9 @@ static int setupBox(ddcb200_ctx *c)
     return DDCB200_OK;
 }
 
-extern "C" int ddcb200_create(const ddcb200_params *p, ddcb200_ctx **out)
+// everything of ddcb200_create that can fail after the context exists: a failure is unwound by ddcb200_destroy
+static int createInit(ddcb200_ctx *c)
 {
-    if (!p || !out) return fail(DDCB200_ERR_ARG, "null argument");
-    int ndev = ddcb200_deviceCount();
-    if (ndev <= 0) return fail(DDCB200_ERR_NODEVICE, "no CUDA device: ddcmd_b200 has no CPU path");
-    if (p->device < 0 || p->device >= ndev) return fail(DDCB200_ERR_ARG, "bad device ordinal");
-    CK(cudaSetDevice(p->device));
-    cudaDeviceProp prop;
-    CK(cudaGetDeviceProperties(&prop, p->device));
-    if (prop.major < 10) return fail(DDCB200_ERR_NODEVICE, std::string("device ") + prop.name + " is not sm_100 class");
-    ddcb200_ctx *c = new ddcb200_ctx();
-    c->prm = *p;
-    c->device = p->device;
-    c->numSM = prop.multiProcessorCount;
     if (const char *be = getenv("DDCB200_BIN_EDGES"))
     {
         // tuning knob: the NBINS-1 ascending edges of the row-ordering bins as fractions of deltaR around the cutoff
@@ -219,40 +208,18 @@ extern "C" int ddcb200_create(const ddcb200_params *p, ddcb200_ctx **out)
         }
         bool ok = n == NBINS - 1;
         for (int k = 0; ok && k < NBINS - 1; k++) ok = v[k] > -1.0 && v[k] <= 1.0 && (k == 0 || v[k] >= v[k - 1]);
-        if (!ok)
-        {
-            delete c;
-            return fail(DDCB200_ERR_ARG, "DDCB200_BIN_EDGES needs 7 ascending fractions of deltaR in (-1, 1]");
-        }
+        if (!ok) return fail(DDCB200_ERR_ARG, "DDCB200_BIN_EDGES needs 7 ascending fractions of deltaR in (-1, 1]");
         for (int k = 0; k < NBINS - 1; k++) c->binFrac[k] = v[k];
     }
     int rc = setupBox(c);
-    if (rc != DDCB200_OK)
-    {
-        delete c;
-        return rc;
-    }
+    if (rc != DDCB200_OK) return rc;
     CK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
     if (const char *wk = getenv("DDCB200_WALK"))
     {
         // list-walk bound: "bead" (default) = rmax + dmax + this bead's own displacement, "global" = rmax + 2 dmax.
         // Both are exact and give bitwise equal forces; "global" walks more entries (A/B knob)
         if (strcmp(wk, "global") == 0) c->walkPerBead = false;
-        else if (strcmp(wk, "bead") != 0)
-        {
-            delete c;
-            return fail(DDCB200_ERR_ARG, "DDCB200_WALK must be bead or global");
-        }
-    }
-    if (const char *lb = getenv("DDCB200_LISTBUILD"))
-    {
-        if (strcmp(lb, "twopass") == 0) c->listBuildMode = 1;
-        else if (strcmp(lb, "cell") == 0) c->listBuildMode = 2;
-        else if (strcmp(lb, "auto") != 0)
-        {
-            delete c;
-            return fail(DDCB200_ERR_ARG, "DDCB200_LISTBUILD must be auto, twopass or cell");
-        }
+        else if (strcmp(wk, "bead") != 0) return fail(DDCB200_ERR_ARG, "DDCB200_WALK must be bead or global");
     }
     CK(cudaMalloc((void **)&c->grid, sizeof(GridDev)));
     CK(cudaMemset(c->grid, 0, sizeof(GridDev)));
@@ -264,6 +231,31 @@ extern "C" int ddcb200_create(const ddcb200_params *p, ddcb200_ctx **out)
     CK(cudaMalloc((void **)&c->ddcCounters, 8 * sizeof(int)));
     CK(cudaMalloc((void **)&c->dmax2, sizeof(unsigned long long)));
     CK(cudaMemset(c->dmax2, 0, sizeof(unsigned long long)));
+    return DDCB200_OK;
+}
+
+
+extern "C" int ddcb200_create(const ddcb200_params *p, ddcb200_ctx **out)
+{
+    if (!p || !out) return fail(DDCB200_ERR_ARG, "null argument");
+    int ndev = ddcb200_deviceCount();
+    if (ndev <= 0) return fail(DDCB200_ERR_NODEVICE, "no CUDA device: ddcmd_b200 has no CPU path");
+    if (p->device < 0 || p->device >= ndev) return fail(DDCB200_ERR_ARG, "bad device ordinal");
+    CK(cudaSetDevice(p->device));
+    cudaDeviceProp prop;
+    CK(cudaGetDeviceProperties(&prop, p->device));
+    if (prop.major < 10) return fail(DDCB200_ERR_NODEVICE, std::string("device ") + prop.name + " is not sm_100 class");
+    ddcb200_ctx *c = new ddcb200_ctx();
+    c->prm = *p;
+    c->device = p->device;
+    c->numSM = prop.multiProcessorCount;
+    const int rc = createInit(c);
+    if (rc != DDCB200_OK)
+    {
+        const std::string msg = g_err;      // ddcb200_destroy must not lose the reason
+        ddcb200_destroy(c);
+        return fail(rc, msg);
+    }
     *out = c;
     return DDCB200_OK;
 }
@@ -272,10 +264,10 @@ extern "C" void ddcb200_destroy(ddcb200_ctx *c)
 {
     if (!c) return;
     cudaSetDevice(c->device);
-    cudaStreamSynchronize(c->stream);
+    if (c->stream) cudaStreamSynchronize(c->stream);
     c->ljTab.release(); c->shiftTab.release(); c->qTab.release(); c->massOfBead.release(); c->wOfBead.release();
     c->gidOfBead.release(); c->molTypeOfBead.release(); c->molTypeSingle.release(); c->bpairOffset.release();
-    c->bpairKey.release(); c->termsBead.release(); c->termsSlot.release(); c->restrBead.release(); c->restrSlot.release();
+    c->bpairKey.release(); c->termsBead.release(); c->restrBead.release(); c->bondCsrOff.release(); c->bondEnt.release(); c->bondRange.release();
     c->restrParm.release(); c->molOffset.release(); c->molBeads.release();
     for (int k = 0; k < 2; k++)
     {
@@ -312,6 +304,10 @@ extern "C" void ddcb200_destroy(ddcb200_ctx *c)
         cudaEventDestroy(pe.b);
     }
     for (auto e : c->evPool) cudaEventDestroy(e);
+    for (int k = 0; k < 2; k++)
+        if (c->evList[k]) cudaEventDestroy(c->evList[k]);
+    for (int k = 0; k < 4; k++)
+        if (c->timer[k]) cudaEventDestroy(c->timer[k]);
     if (c->grid) cudaFree(c->grid);
     if (c->gridHost) cudaFreeHost(c->gridHost);
     if (c->acc) cudaFree(c->acc);
@@ -328,6 +324,8 @@ extern "C" int ddcb200_sync(ddcb200_ctx *c)
     return DDCB200_OK;
 }
 
+static size_t pairSmemBytes(int ntypes) { return (size_t)ntypes * ntypes * (sizeof(double2) + sizeof(double)) + 256 * sizeof(double); }
+
 extern "C" int ddcb200_martiniNonBondParms(ddcb200_ctx *c, int ntypes, const double *eps, const double *sigma, const double *shift)
 {
     if (!c || ntypes <= 0 || ntypes > 255 || !eps || !sigma || !shift) return fail(DDCB200_ERR_ARG, "bad LJ table");
@@ -343,6 +341,14 @@ extern "C" int ddcb200_martiniNonBondParms(ddcb200_ctx *c, int ntypes, const dou
     CK(c->shiftTab.ensure(t.size()));
     CK(cudaMemcpy(c->ljTab.p, t.data(), t.size() * sizeof(double2), cudaMemcpyHostToDevice));
     CK(cudaMemcpy(c->shiftTab.p, shift, t.size() * sizeof(double), cudaMemcpyHostToDevice));
+    // k_pair keeps both tables and the 256 charges in dynamic shared memory: opt in beyond the 48 KB default, refuse what cannot fit
+    const size_t smem = pairSmemBytes(ntypes);
+    cudaDeviceProp prop;
+    CK(cudaGetDeviceProperties(&prop, c->device));
+    if (smem + 1024 > prop.sharedMemPerBlockOptin)
+        return fail(DDCB200_ERR_CAPACITY, "too many LJ atom types for the shared-memory tables of the pair kernel (about 96 at most)");
+    CK(cudaFuncSetAttribute(k_pair<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CK(cudaFuncSetAttribute(k_pair<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     c->ntypes = ntypes;
     c->pc.ntypes = ntypes;
     return DDCB200_OK;
@@ -410,6 +416,7 @@ extern "C" int ddcb200_setBeads(ddcb200_ctx *c, int64_t nGlobal, const uint64_t 
     c->nGlobal = nGlobal;
     c->hGid.assign(gid, gid + nGlobal);
     c->hSpecies.assign(species, species + nGlobal);
+    c->bondCsrDirty = true;
     return uploadBeadTables(c);
 }
 
@@ -471,10 +478,12 @@ extern "C" int ddcb200_martiniBondParms(ddcb200_ctx *c, int64_t nTerms, const in
     }
     // one formula per warp: sort by kind (stable, keeps the caller's order inside a kind)
     std::stable_sort(t.begin(), t.end(), [](const Term &a, const Term &b) { return a.kind < b.kind; });
+    if (nTerms >= (1ll << 29)) return fail(DDCB200_ERR_CAPACITY, "too many bonded terms");
     c->nTerms = nTerms;
     CK(c->termsBead.ensure((size_t)nTerms + 1));
-    CK(c->termsSlot.ensure((size_t)nTerms + 1));
     if (nTerms) CK(cudaMemcpy(c->termsBead.p, t.data(), nTerms * sizeof(Term), cudaMemcpyHostToDevice));
+    c->hTerms.swap(t);
+    c->bondCsrDirty = true;
     c->listValid = false;
     return DDCB200_OK;
 }
@@ -496,8 +505,11 @@ extern "C" int ddcb200_setRestraints(ddcb200_ctx *c, int64_t n, const int *bead,
     }
     c->nRestr = n;
     c->restrOrigin = origin;
+    for (int64_t k = 0; k < n; k++)
+        if (bead[k] < 0 || (c->nGlobal > 0 && bead[k] >= c->nGlobal)) return fail(DDCB200_ERR_ARG, "restraint bead index out of range");
+    c->hRestrBead.assign(bead, bead + n);
+    c->bondCsrDirty = true;
     CK(c->restrBead.ensure((size_t)n + 1));
-    CK(c->restrSlot.ensure((size_t)n + 1));
     CK(c->restrParm.ensure((size_t)n * 7 + 1));
     if (n)
     {
@@ -614,7 +626,11 @@ extern "C" int ddcb200_updateState(ddcb200_ctx *c, int64_t nLocal, const int *be
         CK(cudaMemcpyAsync(c->stageI.p, c->hLocalBeads.data(), nLocal * sizeof(int), cudaMemcpyHostToDevice, c->stream));
     }
     else
+    {
+        // the identity order replaces whatever bead list the previous upload used: getState reads through stageI
         for (int64_t i = 0; i < nLocal; i++) c->hLocalBeads[(size_t)i] = (int)i;
+        CK(cudaMemcpyAsync(c->stageI.p, c->hLocalBeads.data(), nLocal * sizeof(int), cudaMemcpyHostToDevice, c->stream));
+    }
     const int cur = c->cur;
     const double *s = c->stage.p;
     LAUNCH(k_update_state, (int)((nLocal + 255) / 256), 256, 0, c->stream)((int)nLocal, bead ? c->stageI.p : nullptr, c->slotOfBead.p, s, s + nLocal,
@@ -831,6 +847,48 @@ static int haloExchange(ddcb200_ctx *c)
 }
 
 // ---- list build -------------------------------------------------------------------------
+// per-bead gather lists of the bonded kernel: for every bead the (term, role) pairs it takes part in, ascending term order
+// (terms are kind-sorted), restraints last.  Static; rebuilt only when the term tables change.
+static int ensureBondCsr(ddcb200_ctx *c)
+{
+    if (!c->bondCsrDirty) return DDCB200_OK;
+    const int64_t nG = c->nGlobal;
+    std::vector<int> off((size_t)nG + 1, 0);
+    auto need = [](const Term &t) { return t.kind == 0 ? 2 : (t.kind <= 3 ? 3 : 4); };
+    for (const Term &t : c->hTerms)
+    {
+        const int ids[4] = {t.i, t.j, t.k, t.l};
+        for (int a = 0; a < need(t); a++)
+        {
+            if (ids[a] < 0 || ids[a] >= nG) return fail(DDCB200_ERR_ARG, "bonded term bead index out of range");
+            off[(size_t)ids[a] + 1]++;
+        }
+    }
+    for (int b : c->hRestrBead)
+    {
+        if (b < 0 || b >= nG) return fail(DDCB200_ERR_ARG, "restraint bead index out of range");
+        off[(size_t)b + 1]++;
+    }
+    for (int64_t b = 0; b < nG; b++) off[(size_t)b + 1] += off[(size_t)b];
+    if ((int64_t)off[(size_t)nG] < 0) return fail(DDCB200_ERR_CAPACITY, "too many bonded term entries");
+    std::vector<uint32_t> ent((size_t)off[(size_t)nG] + 1);
+    std::vector<int> fill(off.begin(), off.end() - 1);
+    for (size_t t = 0; t < c->hTerms.size(); t++)
+    {
+        const Term &tm = c->hTerms[t];
+        const int ids[4] = {tm.i, tm.j, tm.k, tm.l};
+        for (int a = 0; a < need(tm); a++) ent[(size_t)fill[(size_t)ids[a]]++] = ((uint32_t)t << 2) | (uint32_t)a;
+    }
+    for (size_t r = 0; r < c->hRestrBead.size(); r++)
+        ent[(size_t)fill[(size_t)c->hRestrBead[r]]++] = (uint32_t)(c->hTerms.size() + r) << 2;
+    CK(c->bondCsrOff.ensure((size_t)nG + 1));
+    CK(c->bondEnt.ensure(ent.size()));
+    CK(cudaMemcpy(c->bondCsrOff.p, off.data(), ((size_t)nG + 1) * sizeof(int), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(c->bondEnt.p, ent.data(), ent.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
+    c->bondCsrDirty = false;
+    return DDCB200_OK;
+}
+
 static int localSums(ddcb200_ctx *c, int atBuild);
 extern "C" int ddcb200_constructList(ddcb200_ctx *c)
 {
@@ -879,12 +937,7 @@ extern "C" int ddcb200_constructList(ddcb200_ctx *c)
         const char *cp = getenv("DDCB200_NBRCAP");
         c->nbrCap = cp ? std::max(8, atoi(cp)) : 176;
     }
-    // which build: fixed by DDCB200_LISTBUILD, else the first four rebuilds alternate between the two-pass and the one-pass
-    // cell build under CUDA events and the faster one is kept (the rows are bit-identical: the choice never changes a result)
-    int variant = c->listBuildMode;
-    if (variant == 0) variant = c->listBuildsTimed < 4 ? 1 + (c->listBuildsTimed & 1) : (c->listBuildMs[1] < c->listBuildMs[0] ? 2 : 1);
-    bool timeIt = c->listBuildMode == 0 && c->listBuildsTimed < 4;
-    if (timeIt && !c->evList[0])
+    if (!c->evList[0])
     {
         CK(cudaEventCreate(&c->evList[0]));
         CK(cudaEventCreate(&c->evList[1]));
@@ -892,134 +945,22 @@ extern "C" int ddcb200_constructList(ddcb200_ctx *c)
     for (int attempt = 0; attempt < 4; attempt++)
     {
         CK(c->nbr.ensure((size_t)c->nbrCap * nPad));
-        // one-pass build: one warp per cell, staging rows of `cap` entries per lane in shared memory: as many warps per CTA as
-        // ~110 KB hold (two CTAs per SM), a persistent grid striding over the cells
-        const size_t perWarp = ((size_t)c->nbrCap * 32 + 4 * CELL_TAB) * sizeof(uint16_t);
-        const int wpb = (int)std::min<size_t>(8, std::max<size_t>(1, (size_t)(110 * 1024) / perWarp));
-        const size_t smem = perWarp * wpb;
-        if (variant == 1) CK(c->nbrRaw.ensure((size_t)c->nbrCap * nPad));
-        else
-        {
-            if (smem > (size_t)220 * 1024) return fail(DDCB200_ERR_CAPACITY, "neighbor rows too long for the one-pass list build (set DDCB200_LISTBUILD=twopass)");
-            CK(cudaFuncSetAttribute(k_nbr_cell, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        }
-        if (timeIt) CK(cudaEventRecord(c->evList[0], st));
-        if (variant == 1)
-        {
-            LAUNCH(k_nbr_filter, nPad / 128, 128, 0, st)(nIon, nPad, c->pos32.p, c->cellOfSlot[nxt].p, c->cellStart.p, c->box, rl2f, c->grid,
-                                                    c->nbrCap, c->nbrRaw.p, c->nbrRawCount.p);
-            CKL("k_nbr_filter");
-            LAUNCH(k_nbr_exact, nPad / 128, 128, 0, st)(nIon, nPad, c->nbrCap, c->pos4[nxt].p, c->box, c->grid, c->nbrRaw.p, c->nbrRawCount.p,
-                                                   c->nbr.p, c->nbrCount.p, c->nbrCum.p, c->gidOfBead.p, c->molTypeOfBead.p,
-                                                   c->molTypeSingle.p, c->bpairOffset.p, c->bpairKey.p, c->haveExcl ? 1 : 0);
-            CKL("k_nbr_exact");
-        }
-        else
-        {
-            const int perSM = (int)std::max<size_t>(1, (size_t)(224 * 1024) / (smem + 1024));
-            LAUNCH(k_nbr_cell, c->numSM * perSM, 32 * wpb, smem, st)(nIon, nPad, c->nbrCap, c->pos4[nxt].p, c->cellStart.p, c->box, c->grid,
-                                                                 c->nbr.p, c->nbrCount.p, c->nbrCum.p, c->gidOfBead.p, c->molTypeOfBead.p,
-                                                                 c->molTypeSingle.p, c->bpairOffset.p, c->bpairKey.p, c->haveExcl ? 1 : 0);
-            if (c->listBuildMode == 0)
-            {
-                // auto mode: a launch the device refuses (shared-memory carve-out, limits) just means "use the other build";
-                // this is a choice between two device kernels that write the same rows, reported on stderr - never a CPU path
-                const cudaError_t le = cudaGetLastError();
-                if (le != cudaSuccess)
-                {
-                    fprintf(stderr, "ddcmd_b200: one-pass list build not launchable here (%s); keeping the two-pass build\n", cudaGetErrorString(le));
-                    c->listBuildMode = 1;
-                    variant = 1;
-                    timeIt = false;
-                    attempt--;
-                    continue;
-                }
-                c->kernelLaunches += 1;
-            }
-            else
-                CKL("k_nbr_cell");
-        }
-        if (timeIt) CK(cudaEventRecord(c->evList[1], st));
+        CK(c->nbrRaw.ensure((size_t)c->nbrCap * nPad));
+        CK(cudaEventRecord(c->evList[0], st));
+        LAUNCH(k_nbr_filter, nPad / 128, 128, 0, st)(nIon, nPad, c->pos32.p, c->cellOfSlot[nxt].p, c->cellStart.p, c->box, rl2f, c->grid,
+                                                c->nbrCap, c->nbrRaw.p, c->nbrRawCount.p);
+        CKL("k_nbr_filter");
+        LAUNCH(k_nbr_exact, nPad / 128, 128, 0, st)(nIon, nPad, c->nbrCap, c->pos4[nxt].p, c->box, c->grid, c->nbrRaw.p, c->nbrRawCount.p,
+                                               c->nbr.p, c->nbrCount.p, c->nbrCum.p, c->gidOfBead.p, c->molTypeOfBead.p,
+                                               c->molTypeSingle.p, c->bpairOffset.p, c->bpairKey.p, c->haveExcl ? 1 : 0);
+        CKL("k_nbr_exact");
+        CK(cudaEventRecord(c->evList[1], st));
         CK(cudaMemcpyAsync(c->gridHost, c->grid, sizeof(GridDev), cudaMemcpyDeviceToHost, st));
         CK(cudaStreamSynchronize(st));
         if (c->gridHost->error & 2) return fail(DDCB200_ERR_CAPACITY, "cell grid larger than the bead count bound");
-        if (c->gridHost->error & 4)
-        {
-            // a cell neighbourhood holds more beads than the one-pass build's 12-bit candidate ordinals can number
-            if (c->listBuildMode == 2) return fail(DDCB200_ERR_CAPACITY, "one-pass list build: more than 4096 beads in a 27-cell neighbourhood (use DDCB200_LISTBUILD=twopass)");
-            c->listBuildMode = 1;
-            variant = 1;
-            timeIt = false;
-            CK(cudaMemsetAsync(&c->grid->error, 0, sizeof(int), st));
-            CK(cudaMemsetAsync(&c->grid->maxCount, 0, sizeof(int), st));
-            CK(cudaMemsetAsync(&c->grid->maxRaw, 0, sizeof(int), st));
-            CK(cudaMemsetAsync(&c->grid->totalEntries, 0, sizeof(unsigned long long), st));
-            attempt--;
-            continue;
-        }
         if (!(c->gridHost->error & 1))
         {
-            if (variant == 2 && c->listBuildMode == 0 && !c->cellBuildChecked)
-            {
-                // one-time self-check, auto mode only: the same state through the two-pass build into scratch buffers, rows compared
-                // on the device.  A difference (none is known; the two builds are bit-identical in every test) makes the context
-                // keep the two-pass build, says so on stderr, and rebuilds this list with it.
-                c->cellBuildChecked = true;
-                struct Scratch
-                {
-                    DevBuf<uint32_t> rows2;
-                    DevBuf<int> count2;
-                    DevBuf<uint16_t> cum2;
-                    DevBuf<int> bad;
-                    ~Scratch() { rows2.release(); count2.release(); cum2.release(); bad.release(); }
-                } scratch;
-                DevBuf<uint32_t> &rows2 = scratch.rows2;
-                DevBuf<int> &count2 = scratch.count2;
-                DevBuf<uint16_t> &cum2 = scratch.cum2;
-                DevBuf<int> &bad = scratch.bad;
-                CK(rows2.ensure((size_t)c->nbrCap * nPad));
-                CK(count2.ensure((size_t)nPad));
-                CK(cum2.ensure((size_t)NBINS * nPad));
-                CK(bad.ensure(1));
-                CK(c->nbrRaw.ensure((size_t)c->nbrCap * nPad));
-                CK(cudaMemsetAsync(bad.p, 0, sizeof(int), st));
-                LAUNCH(k_nbr_filter, nPad / 128, 128, 0, st)(nIon, nPad, c->pos32.p, c->cellOfSlot[nxt].p, c->cellStart.p, c->box, rl2f, c->grid,
-                                                        c->nbrCap, c->nbrRaw.p, c->nbrRawCount.p);
-                LAUNCH(k_nbr_exact, nPad / 128, 128, 0, st)(nIon, nPad, c->nbrCap, c->pos4[nxt].p, c->box, c->grid, c->nbrRaw.p, c->nbrRawCount.p,
-                                                       rows2.p, count2.p, cum2.p, c->gidOfBead.p, c->molTypeOfBead.p, c->molTypeSingle.p,
-                                                       c->bpairOffset.p, c->bpairKey.p, c->haveExcl ? 1 : 0);
-                LAUNCH(k_rows_compare, (nIon + 255) / 256, 256, 0, st)(nIon, nPad, c->nbr.p, c->nbrCount.p, c->nbrCum.p, rows2.p, count2.p, cum2.p, bad.p);
-                CKL("list self-check");
-                int nbad = 0;
-                GridDev after;
-                CK(cudaMemcpyAsync(&nbad, bad.p, sizeof(int), cudaMemcpyDeviceToHost, st));
-                CK(cudaMemcpyAsync(&after, c->grid, sizeof(GridDev), cudaMemcpyDeviceToHost, st));
-                CK(cudaStreamSynchronize(st));
-                const char *inject = getenv("DDCB200_SELFCHECK_FAULT");      // test hook: pretend the check failed
-                if (nbad != 0 || (after.error & 1) || (inject && inject[0] == '1'))
-                {
-                    fprintf(stderr, "ddcmd_b200: the one-pass list build differs from the two-pass build on %d rows; keeping the two-pass build\n", nbad);
-                    c->listBuildMode = 1;
-                    variant = 1;
-                    timeIt = false;
-                    CK(cudaMemsetAsync(&c->grid->error, 0, sizeof(int), st));
-                    CK(cudaMemsetAsync(&c->grid->maxCount, 0, sizeof(int), st));
-                    CK(cudaMemsetAsync(&c->grid->maxRaw, 0, sizeof(int), st));
-                    CK(cudaMemsetAsync(&c->grid->totalEntries, 0, sizeof(unsigned long long), st));
-                    attempt--;
-                    continue;
-                }
-                // the scratch build added its rows to the device-side statistics: put the one-pass build's back
-                CK(cudaMemcpyAsync(c->grid, c->gridHost, sizeof(GridDev), cudaMemcpyHostToDevice, st));
-            }
-            if (timeIt)
-            {
-                float ms = 0.f;
-                CK(cudaEventElapsedTime(&ms, c->evList[0], c->evList[1]));
-                float &best = c->listBuildMs[c->listBuildsTimed & 1];      // two samples each (the very first build runs on a cold GPU)
-                best = c->listBuildsTimed < 2 ? ms : std::min(best, ms);
-                c->listBuildsTimed++;
-            }
+            CK(cudaEventElapsedTime(&c->listBuildMs, c->evList[0], c->evList[1]));
             break;
         }
         // a candidate row overflowed: grow and redo both passes
@@ -1030,17 +971,13 @@ extern "C" int ddcb200_constructList(ddcb200_ctx *c)
         CK(cudaMemsetAsync(&c->grid->maxRaw, 0, sizeof(int), st));
         CK(cudaMemsetAsync(&c->grid->totalEntries, 0, sizeof(unsigned long long), st));
     }
-    if (c->nTerms)
+    if (c->nTerms + c->nRestr > 0)
     {
-        LAUNCH(k_terms_remap, (int)((c->nTerms + 255) / 256), 256, 0, st)(c->nTerms, c->termsBead.p, c->termsSlot.p, c->slotOfBead.p,
-                                                                      c->pos4[nxt].p);
-        CKL("k_terms_remap");
-    }
-    if (c->nRestr)
-    {
-        LAUNCH(k_restr_remap, (int)((c->nRestr + 255) / 256), 256, 0, st)(c->nRestr, c->restrBead.p, c->restrSlot.p, c->slotOfBead.p,
-                                                                      c->pos4[nxt].p);
-        CKL("k_restr_remap");
+        int rcb = ensureBondCsr(c);
+        if (rcb) return rcb;
+        CK(c->bondRange.ensure((size_t)nPad));
+        LAUNCH(k_bond_ranges, (nIon + 255) / 256, 256, 0, st)(nIon, c->pos4[nxt].p, c->bondCsrOff.p, c->bondRange.p);
+        CKL("k_bond_ranges");
     }
     if (c->nranks > 1)
     {
@@ -1186,7 +1123,7 @@ extern "C" int ddcb200_ddcenergy(ddcb200_ctx *c, int withEnergy)
     if (withEnergy) CK(cudaMemsetAsync(c->acc, 0, ACC_N * sizeof(double), st));
     {
         ProfScope ps(c, PROF_PAIR);
-        const size_t smem = (size_t)c->ntypes * c->ntypes * (sizeof(double2) + sizeof(double)) + 256 * sizeof(double);
+        const size_t smem = pairSmemBytes(c->ntypes);
         if (withEnergy)
             LAUNCH(k_pair<true>, tiles, TILE, smem, st)(nLocal, nPad, c->pos4[cur].p, c->nbr.p, c->nbrCum.p, c->dmax2, c->walkPerBead ? c->dispOfSlot.p : nullptr, c->ljTab.p, c->shiftTab.p,
                                                     c->qTab.p, c->pc, c->frc[0].p, c->frc[1].p, c->frc[2].p, c->pairPartial.p);
@@ -1200,16 +1137,16 @@ extern "C" int ddcb200_ddcenergy(ddcb200_ctx *c, int withEnergy)
     if (nb > 0)
     {
         ProfScope ps(c, PROF_BONDED);
-        bBlocks = (int)((nb + BONDED_THREADS - 1) / BONDED_THREADS);
+        bBlocks = (nLocal + BONDED_THREADS - 1) / BONDED_THREADS;
         CK(c->bondPartial.ensure((size_t)bBlocks * BONDED_ACC + 8));
         if (withEnergy)
-            LAUNCH(k_bonded<true>, bBlocks, BONDED_THREADS, 0, st)(c->nTerms, c->termsSlot.p, c->nRestr, c->restrSlot.p, c->restrParm.p,
-                                                               c->restrOrigin, c->pos4[cur].p, c->pc, c->frc[0].p, c->frc[1].p,
-                                                               c->frc[2].p, c->bondPartial.p);
+            LAUNCH(k_bonded<true>, bBlocks, BONDED_THREADS, 0, st)(nLocal, c->bondRange.p, c->bondEnt.p, c->nTerms, c->termsBead.p, c->restrBead.p,
+                                                               c->restrParm.p, c->restrOrigin, c->slotOfBead.p, c->pos4[cur].p, c->pc,
+                                                               c->frc[0].p, c->frc[1].p, c->frc[2].p, c->bondPartial.p);
         else
-            LAUNCH(k_bonded<false>, bBlocks, BONDED_THREADS, 0, st)(c->nTerms, c->termsSlot.p, c->nRestr, c->restrSlot.p, c->restrParm.p,
-                                                                c->restrOrigin, c->pos4[cur].p, c->pc, c->frc[0].p, c->frc[1].p,
-                                                                c->frc[2].p, c->bondPartial.p);
+            LAUNCH(k_bonded<false>, bBlocks, BONDED_THREADS, 0, st)(nLocal, c->bondRange.p, c->bondEnt.p, c->nTerms, c->termsBead.p, c->restrBead.p,
+                                                                c->restrParm.p, c->restrOrigin, c->slotOfBead.p, c->pos4[cur].p, c->pc,
+                                                                c->frc[0].p, c->frc[1].p, c->frc[2].p, c->bondPartial.p);
         CKL("k_bonded");
     }
     if (withEnergy)
@@ -1885,13 +1822,11 @@ extern "C" int ddcb200_pairCorrelation(ddcb200_ctx *c, int nBins, double rmin, d
 extern "C" int ddcb200_listBuildInfo(ddcb200_ctx *c, int *variant, double ms[2])
 {
     if (!c) return fail(DDCB200_ERR_ARG, "null ctx");
-    int v = c->listBuildMode;
-    if (v == 0) v = c->listBuildsTimed < 4 ? 0 : (c->listBuildMs[1] < c->listBuildMs[0] ? 2 : 1);
-    if (variant) *variant = v;
+    if (variant) *variant = 1;      // one build: fp32 candidate filter + exact fp64 pass
     if (ms)
     {
-        ms[0] = c->listBuildMs[0];
-        ms[1] = c->listBuildMs[1];
+        ms[0] = c->listBuildMs;     // device time of the last build
+        ms[1] = 0.0;
     }
     return DDCB200_OK;
 }

@@ -5,8 +5,8 @@
 // Replaces charmmConvalent + connectiveEnergy + res*Sorted (src/bioCharmmCovalent.c:95-251,
 // src/bioCharmmCovalentEnergies.c:266-351,754-794, src/bioCharmmCovalentEnergiesSorted.c)
 // and bondedGPU.cu's seven kernels, and restraint() (src/restraint.c:259-361).
-// Terms are sorted by kind on the host, so a warp runs one formula; indices are slot
-// indices refreshed at every list build.
+// One thread per resident local bead gathers the force of every term the bead takes part in (no atomics: bitwise
+// reproducible); terms are sorted by kind on the host, so the lanes of a warp mostly run the same formula.
 #pragma once
 #include "engine.cuh"
 
@@ -27,13 +27,6 @@ __device__ __forceinline__ V3 minImage(V3 d, const PairConst &pc)
     d.y -= pc.hyy * rint(d.y / pc.hyy);
     d.z -= pc.hzz * rint(d.z / pc.hzz);
     return d;
-}
-
-__device__ __forceinline__ void addForce(double *fx, double *fy, double *fz, int s, V3 f)
-{
-    atomicAdd(fx + s, f.x);
-    atomicAdd(fy + s, f.y);
-    atomicAdd(fz + s, f.z);
 }
 
 // bioDihedralFast (src/bioCharmmCovalentEnergies.c:266-351): angle, sin, d(cos)/dr and the
@@ -83,92 +76,151 @@ __device__ __forceinline__ void dihedral(V3 vij, V3 vjk, V3 vkl, double &ang, do
 #define BONDED_THREADS 128
 #define BONDED_ACC 11   // 0..5 virial (xx yy zz xy xz yz), 6 bond, 7 angle, 8 torsion, 9 improper, 10 restraint
 
+// Forces are GATHERED, not scattered: one thread per resident local bead walks the (static) list of bonded terms the
+// bead takes part in - entry = (term << 2 | role of this bead in the term), ascending term order - evaluates each term and
+// keeps only the force on its own bead.  A bond is therefore evaluated twice, an angle three times, a dihedral four times;
+// in exchange there is no atomic and the summation order of every bead's force is fixed, so forces and energies are
+// bitwise reproducible run to run (the reference accumulates in owner order too, src/bioCharmmCovalent.c:95-251).
+// Energy and virial of a term are counted by the thread of its role-0 bead only.  Endpoints are looked up through
+// slotOfBead; a term with an endpoint that is not resident here is skipped (molecules are whole on their owner rank,
+// src/ddcRuleMolecule.c:43, so that never happens for a local bead of a Martini deck).
+// at every list build: the term range of each slot's bead, in slot order (coalesced in k_bonded)
+__global__ void k_bond_ranges(int nIon, const double4 *__restrict__ pos, const int *__restrict__ csrOff, BondRange *__restrict__ out)
+{
+    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= nIon) return;
+    const unsigned long long w = (unsigned long long)__double_as_longlong(pos[s].w);
+    BondRange r = {0, 0};
+    if (!(w >> 63))
+    {
+        const int b = (int)((w >> 32) & 0x7fffffffull);
+        r.lo = csrOff[b];
+        r.n = csrOff[b + 1] - r.lo;
+    }
+    out[s] = r;
+}
+
 template <bool ENERGY>
 __global__ void __launch_bounds__(BONDED_THREADS)
-k_bonded(int64_t nTerms, const Term *__restrict__ terms, int64_t nRestr, const int *__restrict__ restrSlot,
-         const double *__restrict__ restrParm, int restrOrigin, const double4 *__restrict__ pos, PairConst pc,
-         double *__restrict__ fx, double *__restrict__ fy, double *__restrict__ fz, double *__restrict__ partial)
+k_bonded(int nIon, const BondRange *__restrict__ range, const uint32_t *__restrict__ ent, int64_t nTerms, const Term *__restrict__ terms,
+         const int *__restrict__ restrBead, const double *__restrict__ restrParm, int restrOrigin, const int *__restrict__ slotOfBead,
+         const double4 *__restrict__ pos, PairConst pc, double *__restrict__ fx, double *__restrict__ fy, double *__restrict__ fz,
+         double *__restrict__ partial)
 {
-    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int s = blockIdx.x * blockDim.x + threadIdx.x;
     double acc[BONDED_ACC];
 #pragma unroll
     for (int a = 0; a < BONDED_ACC; a++) acc[a] = 0.0;
-
-    if (t < nTerms)
+    const BondRange rg = s < nIon ? range[s] : BondRange{0, 0};
+    if (rg.n > 0)
     {
-        const Term tm = terms[t];
-        if (tm.i >= 0)
+        V3 fs = V3{0.0, 0.0, 0.0};
+        for (int q = 0; q < rg.n; q++)
         {
+            const uint32_t e = ent[rg.lo + q];
+            const int64_t t = (int64_t)(e >> 2);
+            const int role = (int)(e & 3u);
+            const bool count = ENERGY && role == 0;
+            if (t >= nTerms)
+            {
+                // restraint (src/restraint.c:287-357)
+                const int64_t r = t - nTerms;
+                (void)restrBead;
+                const double *p = restrParm + 7 * r;
+                double x0 = p[0] * pc.hxx, y0 = p[1] * pc.hyy, z0 = p[2] * pc.hzz;
+                if (restrOrigin == 0)
+                {
+                    x0 -= pc.hxx / 2.0;
+                    y0 -= pc.hyy / 2.0;
+                    z0 -= pc.hzz / 2.0;
+                }
+                const double kb = p[3];
+                const double4 ps = pos[s];
+                V3 d = V3{ps.x - x0, ps.y - y0, ps.z - z0};
+                if ((p[4] > 0 && fabs(d.x) > pc.hhx) || (p[5] > 0 && fabs(d.y) > pc.hhy) || (p[6] > 0 && fabs(d.z) > pc.hhz)) d = minImage(d, pc);
+                const V3 cd = V3{p[4] * d.x, p[5] * d.y, p[6] * d.z};
+                const V3 f = vscale(cd, -2.0 * kb);
+                fs = V3{fs.x + f.x, fs.y + f.y, fs.z + f.z};
+                if (ENERGY)
+                {
+                    acc[10] += kb * (cd.x * d.x + cd.y * d.y + cd.z * d.z);
+                    acc[0] += f.x * cd.x; acc[1] += f.y * cd.y; acc[2] += f.z * cd.z;
+                    acc[3] += f.x * cd.y; acc[4] += f.x * cd.z; acc[5] += f.y * cd.z;
+                }
+                continue;
+            }
+            const Term tm = terms[t];
+            const int si = slotOfBead[tm.i], sj = slotOfBead[tm.j];
+            const int sk = tm.k >= 0 ? slotOfBead[tm.k] : 0, sl = tm.l >= 0 ? slotOfBead[tm.l] : 0;
+            if ((si | sj | sk | sl) < 0) continue;      // an endpoint is not resident on this rank
+            V3 f;
             if (tm.kind == 0)
             {
                 // resBondSorted (src/bioCharmmCovalentEnergiesSorted.c:18-116)
-                const V3 b = minImage(vsub(pos[tm.i], pos[tm.j]), pc);
+                const V3 b = minImage(vsub(pos[si], pos[sj]), pc);
                 const double len = sqrt(vdot(b, b));
                 const double dl = len - tm.p1;
                 const double kf = -2.0 * tm.p0 * dl / len;
-                const V3 f = vscale(b, kf);
-                addForce(fx, fy, fz, tm.i, f);
-                addForce(fx, fy, fz, tm.j, V3{-f.x, -f.y, -f.z});
-                if (ENERGY)
+                const V3 fi = vscale(b, kf);
+                f = role == 0 ? fi : V3{-fi.x, -fi.y, -fi.z};
+                if (count)
                 {
-                    acc[6] = tm.p0 * dl * dl;
-                    acc[0] = f.x * b.x; acc[1] = f.y * b.y; acc[2] = f.z * b.z;
-                    acc[3] = f.x * b.y; acc[4] = f.x * b.z; acc[5] = f.y * b.z;
+                    acc[6] += tm.p0 * dl * dl;
+                    acc[0] += fi.x * b.x; acc[1] += fi.y * b.y; acc[2] += fi.z * b.z;
+                    acc[3] += fi.x * b.y; acc[4] += fi.x * b.z; acc[5] += fi.y * b.z;
                 }
             }
             else if (tm.kind <= 3)
             {
                 // resAngleSorted / resAngleCosineSorted / resAngleRestrainSorted (:118-487)
-                const double4 pj = pos[tm.j];
-                const V3 vij = minImage(vsub(pos[tm.i], pj), pc), vkj = minImage(vsub(pos[tm.k], pj), pc);
+                const double4 pj = pos[sj];
+                const V3 vij = minImage(vsub(pos[si], pj), pc), vkj = minImage(vsub(pos[sk], pj), pc);
                 const double bij = sqrt(vdot(vij, vij)), bkj = sqrt(vdot(vkj, vkj));
                 const V3 uij = vscale(vij, 1.0 / bij), ukj = vscale(vkj, 1.0 / bkj);
                 const double c = vdot(uij, ukj);
-                double coef, e;
+                double coef, en;
                 if (tm.kind == 1)
                 {
                     const double a = acos(c), da = a - tm.p1;
-                    e = tm.p0 * da * da;
+                    en = tm.p0 * da * da;
                     coef = 2.0 * tm.p0 * da / sin(a);
                 }
                 else if (tm.kind == 2)
                 {
                     const double da = c - tm.p1;
-                    e = tm.p0 * da * da;
+                    en = tm.p0 * da * da;
                     coef = -2.0 * tm.p0 * da;
                 }
                 else
                 {
                     const double s2 = 1.0 - c * c, da = c - tm.p1;
-                    e = tm.p0 * da * da / s2;
+                    en = tm.p0 * da * da / s2;
                     coef = -2.0 * tm.p0 * da * (1.0 - c * tm.p1) / (s2 * s2);
                 }
                 const double ci = coef / bij, ck = coef / bkj;
                 const V3 fi = V3{ci * (ukj.x - uij.x * c), ci * (ukj.y - uij.y * c), ci * (ukj.z - uij.z * c)};
                 const V3 fk = V3{ck * (uij.x - ukj.x * c), ck * (uij.y - ukj.y * c), ck * (uij.z - ukj.z * c)};
-                addForce(fx, fy, fz, tm.i, fi);
-                addForce(fx, fy, fz, tm.k, fk);
-                addForce(fx, fy, fz, tm.j, V3{-(fi.x + fk.x), -(fi.y + fk.y), -(fi.z + fk.z)});
-                if (ENERGY)
+                f = role == 0 ? fi : (role == 2 ? fk : V3{-(fi.x + fk.x), -(fi.y + fk.y), -(fi.z + fk.z)});
+                if (count)
                 {
-                    acc[7] = e;
-                    acc[0] = fi.x * vij.x + fk.x * vkj.x; acc[1] = fi.y * vij.y + fk.y * vkj.y; acc[2] = fi.z * vij.z + fk.z * vkj.z;
-                    acc[3] = fi.x * vij.y + fk.x * vkj.y; acc[4] = fi.x * vij.z + fk.x * vkj.z; acc[5] = fi.y * vij.z + fk.y * vkj.z;
+                    acc[7] += en;
+                    acc[0] += fi.x * vij.x + fk.x * vkj.x; acc[1] += fi.y * vij.y + fk.y * vkj.y; acc[2] += fi.z * vij.z + fk.z * vkj.z;
+                    acc[3] += fi.x * vij.y + fk.x * vkj.y; acc[4] += fi.x * vij.z + fk.x * vkj.z; acc[5] += fi.y * vij.z + fk.y * vkj.z;
                 }
             }
             else
             {
                 // resTorsionSorted / resImproperSorted (:577-848)
-                const double4 pI = pos[tm.i], pJ = pos[tm.j], pK = pos[tm.k], pL = pos[tm.l];
+                const double4 pI = pos[si], pJ = pos[sj], pK = pos[sk], pL = pos[sl];
                 const V3 vij = minImage(vsub(pI, pJ), pc), vjk = minImage(vsub(pJ, pK), pc), vkl = minImage(vsub(pK, pL), pc);
                 double ang, sinX, vir[6];
                 V3 dI, dJ, dK, dL;
                 dihedral(vij, vjk, vkl, ang, sinX, dI, dJ, dK, dL, vir);
-                double kf, e;
+                double kf, en;
                 if (tm.kind == 4)
                 {
                     const double kchi = tm.p0, delta = tm.p1, n = tm.p2;
-                    e = kchi * (1.0 + cos(n * ang - delta));
+                    en = kchi * (1.0 + cos(n * ang - delta));
                     if (fabs(sinX) > 1e-8) kf = kchi * n * sin(n * ang - delta) / sinX;
                     else
                     {
@@ -185,7 +237,7 @@ k_bonded(int64_t nTerms, const Term *__restrict__ terms, int64_t nRestr, const i
                     double d = ang - psi0;
                     if (d < -M_PI) d += 2 * M_PI;
                     else if (d > M_PI) d -= 2 * M_PI;
-                    e = kpsi * d * d;
+                    en = kpsi * d * d;
                     if (fabs(sinX) > 1e-8) kf = -2.0 * kpsi * d / sinX;
                     else
                     {
@@ -193,48 +245,21 @@ k_bonded(int64_t nTerms, const Term *__restrict__ terms, int64_t nRestr, const i
                         kf = -2.0 * kpsi / (1 - X2 / 6 + X2 * X2 / 120 - X2 * X2 * X2 / 5040 + X2 * X2 * X2 * X2 / 362880 - X2 * X2 * X2 * X2 * X2 / 39916800);
                     }
                 }
-                addForce(fx, fy, fz, tm.i, vscale(dI, -kf));
-                addForce(fx, fy, fz, tm.j, vscale(dJ, -kf));
-                addForce(fx, fy, fz, tm.k, vscale(dK, -kf));
-                addForce(fx, fy, fz, tm.l, vscale(dL, -kf));
-                if (ENERGY)
+                const V3 dd = role == 0 ? dI : (role == 1 ? dJ : (role == 2 ? dK : dL));
+                f = vscale(dd, -kf);
+                if (count)
                 {
-                    acc[tm.kind == 4 ? 8 : 9] = e;
+                    acc[tm.kind == 4 ? 8 : 9] += en;
 #pragma unroll
-                    for (int a = 0; a < 6; a++) acc[a] = vir[a] * kf;
+                    for (int a = 0; a < 6; a++) acc[a] += vir[a] * kf;
                 }
             }
+            fs = V3{fs.x + f.x, fs.y + f.y, fs.z + f.z};
         }
-    }
-    else if (t - nTerms < nRestr)
-    {
-        // restraint (src/restraint.c:287-357)
-        const int64_t r = t - nTerms;
-        const int s = restrSlot[r];
-        if (s >= 0)
-        {
-            const double *p = restrParm + 7 * r;
-            double x0 = p[0] * pc.hxx, y0 = p[1] * pc.hyy, z0 = p[2] * pc.hzz;
-            if (restrOrigin == 0)
-            {
-                x0 -= pc.hxx / 2.0;
-                y0 -= pc.hyy / 2.0;
-                z0 -= pc.hzz / 2.0;
-            }
-            const double kb = p[3];
-            const double4 ps = pos[s];
-            V3 d = V3{ps.x - x0, ps.y - y0, ps.z - z0};
-            if ((p[4] > 0 && fabs(d.x) > pc.hhx) || (p[5] > 0 && fabs(d.y) > pc.hhy) || (p[6] > 0 && fabs(d.z) > pc.hhz)) d = minImage(d, pc);
-            const V3 cd = V3{p[4] * d.x, p[5] * d.y, p[6] * d.z};
-            const V3 f = vscale(cd, -2.0 * kb);
-            addForce(fx, fy, fz, s, f);
-            if (ENERGY)
-            {
-                acc[10] = kb * (cd.x * d.x + cd.y * d.y + cd.z * d.z);
-                acc[0] = f.x * cd.x; acc[1] = f.y * cd.y; acc[2] = f.z * cd.z;
-                acc[3] = f.x * cd.y; acc[4] = f.x * cd.z; acc[5] = f.y * cd.z;
-            }
-        }
+        // k_pair has written this slot's pair force: the bonded sum is added to it by the only thread that owns the slot
+        fx[s] += fs.x;
+        fy[s] += fs.y;
+        fz[s] += fs.z;
     }
 
     if (ENERGY)
@@ -255,35 +280,4 @@ k_bonded(int64_t nTerms, const Term *__restrict__ terms, int64_t nRestr, const i
             partial[(size_t)blockIdx.x * BONDED_ACC + threadIdx.x] = v;
         }
     }
-}
-
-// refresh slot indices of the bonded terms and restraints after a re-sort
-// A term is evaluated by the rank that owns its molecule (molecules are whole on their owner): terms whose
-// first bead is absent here, or present only as a ghost, are switched off (i = -1).
-__device__ __forceinline__ int ownedSlot(int bead, const int *__restrict__ slotOfBead, const double4 *__restrict__ pos)
-{
-    const int s = slotOfBead[bead];
-    if (s < 0) return -1;
-    return ((((unsigned long long)__double_as_longlong(pos[s].w)) >> 63) != 0ull) ? -1 : s;
-}
-__global__ void k_terms_remap(int64_t nTerms, const Term *__restrict__ in, Term *__restrict__ out, const int *__restrict__ slotOfBead,
-                              const double4 *__restrict__ pos)
-{
-    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= nTerms) return;
-    Term tm = in[t];
-    tm.i = ownedSlot(tm.i, slotOfBead, pos);
-    if (tm.i >= 0)
-    {
-        tm.j = slotOfBead[tm.j];
-        if (tm.k >= 0) tm.k = slotOfBead[tm.k];
-        if (tm.l >= 0) tm.l = slotOfBead[tm.l];
-    }
-    out[t] = tm;
-}
-__global__ void k_restr_remap(int64_t n, const int *__restrict__ bead, int *__restrict__ slot, const int *__restrict__ slotOfBead,
-                              const double4 *__restrict__ pos)
-{
-    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (t < n) slot[t] = ownedSlot(bead[t], slotOfBead, pos);
 }

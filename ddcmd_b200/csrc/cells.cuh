@@ -462,245 +462,3 @@ k_nbr_exact(int nIon, int nPad, int cap, const double4 *__restrict__ pos, BoxCon
         atomicAdd(&gp->totalEntries, t);
     }
 }
-
-// ---- 8b/9b. one-pass list build: one warp per cell ------------------------------------------
-// All beads of a cell share the cell's stencil, so with one lane per bead of the cell every lane tests the SAME
-// candidate j at the same time: the j position is one broadcast load (one L1 tag per candidate instead of one per
-// lane), the exact fp64 membership test of pairlist1 runs directly on every stencil candidate - no fp32 candidate
-// pass, no candidate buffer in HBM - and the accepted entries are staged per lane in shared memory (bank = lane, so
-// the staging stores never conflict) until the per-bin counts are known and the row can be written in bin order.
-// Candidate order (stencil cells dz, dy, dx ascending, then slot order), the membership test, the bin of every entry
-// (compared on the bit patterns: exact for positive doubles) and the pruning flag are those of k_nbr_filter +
-// k_nbr_exact, so both builds write bit-identical rows (tests/test_gpu_parity.py::test_list_builds_agree_bit_for_bit).
-// Cells with more than 32 beads take several passes over their stencil.
-#define CELL_PF 4      // candidate positions per batch (two batches in flight per warp)
-#define CELL_TAB 32    // entries of the per-warp stencil tables (<= 27 cells + the end marker)
-
-// bin of r2 among the 7 ascending edges = number of edges <= r2, on the bit patterns (exact for positive doubles): a
-// three-level tree on the high words; only when a compared high word ties do the full 64-bit patterns decide
-__device__ __forceinline__ int binOfBits(double r2, const int *eh, const double *edge2)
-{
-#if NBINS != 8
-#error "binOfBits is written for 7 edges"
-#endif
-    const int hi = __double2hiint(r2);           // r2 > 0: the high words order like the values
-    const bool g3 = hi >= eh[3];
-    const int m1 = g3 ? eh[5] : eh[1];
-    const bool g1 = hi >= m1;
-    const int lo0 = g1 ? eh[2] : eh[0];
-    const int hi0 = g1 ? eh[6] : eh[4];
-    const int m2 = g3 ? hi0 : lo0;
-    const bool g0 = hi >= m2;
-    int bin = (g3 ? 4 : 0) + (g1 ? 2 : 0) + (g0 ? 1 : 0);
-    if (hi == eh[3] || hi == m1 || hi == m2)
-    {
-        const unsigned long long rb = (unsigned long long)__double_as_longlong(r2);
-        bin = 0;
-#pragma unroll
-        for (int e = 0; e < NBINS - 1; e++) bin += (rb >= (unsigned long long)__double_as_longlong(edge2[e])) ? 1 : 0;
-    }
-    return bin;
-}
-
-__global__ void __launch_bounds__(256, 2)   // two 8-warp CTAs per SM: at most 128 registers
-k_nbr_cell(int nIon, int nPad, int cap, const double4 *__restrict__ pos, const int *__restrict__ cellStart, BoxConst b, GridDev *gp,
-           uint32_t *__restrict__ out, int *__restrict__ count, uint16_t *__restrict__ cum, const uint64_t *__restrict__ gid,
-           const int *__restrict__ molTypeOfBead, const int *__restrict__ molTypeSingle, const int *__restrict__ bpairOffset,
-           const uint32_t *__restrict__ bpairKey, int haveExcl)
-{
-    // per warp: 16-bit staged entries [cap][32] (candidate ordinal of this chunk's stencil walk : 12, bin : 3, pruned : 1), then the
-    // stencil tables that turn an ordinal back into a slot: first ordinal and first slot of each of the <= 27 stencil cells
-    EXTERN_SHARED(uint16_t, stageAll);
-    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, wpb = blockDim.x >> 5;
-    const size_t warpU16 = (size_t)cap * 32 + 4 * CELL_TAB;        // uint16 units: the staged rows + two tables of CELL_TAB ints
-    uint16_t *stage = stageAll + (size_t)wib * warpU16 + lane;
-    int *pref = (int *)(stageAll + (size_t)wib * warpU16 + (size_t)cap * 32);
-    int *base0 = pref + CELL_TAB;
-    if (gp->error & 2) return;
-    const int nx = gp->n[0], ny = gp->n[1], nz = gp->n[2];
-    const int ncell = nx * ny * nz;
-    const int lx = nx >= 3 ? -1 : 0, hx = nx >= 2 ? 1 : 0;
-    const int ly = ny >= 3 ? -1 : 0, hy = ny >= 2 ? 1 : 0;
-    const int lz = nz >= 3 ? -1 : 0, hz = nz >= 2 ? 1 : 0;
-    int eh[NBINS - 1];
-#pragma unroll
-    for (int e = 0; e < NBINS - 1; e++) eh[e] = __double2hiint(b.binEdge2[e]);
-    int statMax = 0;
-    unsigned long long statTotal = 0ull;
-    for (int c = blockIdx.x * wpb + wib; c < ncell; c += gridDim.x * wpb)
-    {
-        const int lo = cellStart[c], hi = cellStart[c + 1];
-        const int cx = c % nx, cy = (c / nx) % ny, cz = c / (nx * ny);
-        for (int base = lo; base < hi; base += 32)
-        {
-            const int i = base + lane;
-            const bool have = i < hi;
-            const double4 pi = ldPos256(pos + (have ? i : lo));
-            const uint64_t wi = (uint64_t)__double_as_longlong(pi.w);
-            const bool act = have && !(wi >> 63);            // ghost slots own no row
-            const uint32_t molI = (uint32_t)wi & 0xffff0000u;
-            int cnt = 0;
-            uint16_t *sp = stage;
-            int ord0 = 0, ncellsWalked = 0;          // warp-uniform: candidates walked so far, stencil cells walked so far
-            if (__any_sync(0xffffffffu, act))
-            {
-                for (int dz = lz; dz <= hz; dz++)
-                {
-                    int az = cz + dz;
-                    if (az < 0) az += nz;
-                    else if (az >= nz) az -= nz;
-                    for (int dy = ly; dy <= hy; dy++)
-                    {
-                        int ay = cy + dy;
-                        if (ay < 0) ay += ny;
-                        else if (ay >= ny) ay -= ny;
-                        for (int dx = lx; dx <= hx; dx++)
-                        {
-                            int ax = cx + dx;
-                            if (ax < 0) ax += nx;
-                            else if (ax >= nx) ax -= nx;
-                            const int cc = ax + nx * (ay + ny * az);
-                            const int jlo = cellStart[cc], jhi = cellStart[cc + 1];
-                            if (lane == 0)
-                            {
-                                pref[ncellsWalked] = ord0;
-                                base0[ncellsWalked] = jlo;
-                            }
-                            ncellsWalked++;
-                            if (jlo >= jhi) continue;
-                            const int ordBase = ord0 - jlo;
-                            ord0 += jhi - jlo;
-                            // double-buffered: the next CELL_PF candidate positions are in flight while this batch is tested
-                            double4 nxt[CELL_PF];
-#pragma unroll
-                            for (int u = 0; u < CELL_PF; u++) nxt[u] = ldPos256(pos + min(jlo + u, jhi - 1));
-                            for (int j0 = jlo; j0 < jhi; j0 += CELL_PF)
-                            {
-                                double4 pjv[CELL_PF];
-#pragma unroll
-                                for (int u = 0; u < CELL_PF; u++) pjv[u] = nxt[u];
-                                if (j0 + CELL_PF < jhi)
-                                {
-#pragma unroll
-                                    for (int u = 0; u < CELL_PF; u++) nxt[u] = ldPos256(pos + min(j0 + CELL_PF + u, jhi - 1));
-                                }
-#pragma unroll
-                                for (int u = 0; u < CELL_PF; u++)
-                                {
-                                    const int j = j0 + u;
-                                    const double4 pj = pjv[u];
-                                    // pairlist1, src/pairlist.c:280-288
-                                    double x = __dadd_rn(pi.x, -pj.x), y = __dadd_rn(pi.y, -pj.y), z = __dadd_rn(pi.z, -pj.z);
-                                    double r2 = exactR2(x, y, z);
-                                    if (r2 > b.R2cut)
-                                    {
-                                        wrapOnce(x, y, z, b);
-                                        r2 = exactR2(x, y, z);
-                                    }
-                                    if (r2 < b.rlist2 && act && j < jhi && j != i)
-                                    {
-                                        const int bin = binOfBits(r2, eh, b.binEdge2);
-                                        uint32_t ent = (uint32_t)(ordBase + j) | ((uint32_t)bin << 12);
-                                        if (haveExcl && ((uint32_t)__double_as_longlong(pj.w) & 0xffff0000u) == molI)
-                                        {
-                                            // same low 16 bits of the molecule id: the gid tables decide (reOrgPairs)
-                                            const uint64_t wj = (uint64_t)__double_as_longlong(pj.w);
-                                            if (isPruned((int)((wi >> 32) & 0x7fffffffull), (int)((wj >> 32) & 0x7fffffffull), gid, molTypeOfBead,
-                                                         molTypeSingle, bpairOffset, bpairKey))
-                                                ent |= 0x8000u;
-                                        }
-                                        if (cnt < cap) *sp = (uint16_t)ent;
-                                        sp += 32;
-                                        cnt++;
-                                    }
-                                }
-                            }
-                        }
-                    }
-                }
-            }
-            if (lane == 0) pref[ncellsWalked] = ord0;
-            if (ord0 > 4096) cnt = max(cnt, cap + 1) | 0x40000000;      // ordinals no longer fit 12 bits: reported as an overflow the host cannot grow away
-            __syncwarp();
-            if (have)
-            {
-                // per-bin counts from the staged entries (eight 16-bit counters in two words, as k_nbr_exact), exclusive prefix,
-                // cumulative counts at every bin boundary, then the row in bin order
-                const int stored = min(cnt, cap);
-                uint64_t A = 0ull, B = 0ull;
-                for (int k = 0; k < stored; k++)
-                {
-                    const int bin = (stage[(size_t)k * 32] >> 12) & 7;
-                    const uint64_t one = 1ull << (16 * (bin & 3));
-                    if (bin < 4) A += one;
-                    else B += one;
-                }
-                const uint64_t totA = (A * 0x0001000100010001ull) >> 48;
-                uint64_t offA = A * 0x0001000100010000ull;
-                uint64_t offB = B * 0x0001000100010000ull + totA * 0x0001000100010001ull;
-#pragma unroll
-                for (int bnd = 0; bnd < NBINS; bnd++)
-                {
-                    const uint64_t off = bnd < 4 ? offA : offB, cn = bnd < 4 ? A : B;
-                    const int sh = 16 * (bnd & 3);
-                    cum[(size_t)bnd * nPad + i] = (uint16_t)(((off >> sh) & 0xffffull) + ((cn >> sh) & 0xffffull));
-                }
-                int sc = 0;                              // staged ordinals ascend: the stencil cell of an entry is found by a running pointer
-                if (cnt <= cap)
-                    for (int k = 0; k < stored; k++)
-                    {
-                        const uint32_t e = stage[(size_t)k * 32];
-                        const int ord = (int)(e & 0x0fffu);
-                        while (ord >= pref[sc + 1]) sc++;
-                        const uint32_t j = (uint32_t)(base0[sc] + (ord - pref[sc]));
-                        const int bin = (e >> 12) & 7;
-                        const int sh = 16 * (bin & 3);
-                        int dst;
-                        if (bin < 4)
-                        {
-                            dst = (int)((offA >> sh) & 0xffffull);
-                            offA += 1ull << sh;
-                        }
-                        else
-                        {
-                            dst = (int)((offB >> sh) & 0xffffull);
-                            offB += 1ull << sh;
-                        }
-                        out[(size_t)dst * nPad + i] = j | ((e & 0x8000u) ? EXCL_BIT : 0u);
-                    }
-                count[i] = cnt & 0x3fffffff;
-            }
-            __syncwarp();                                // the tables are rewritten by the next chunk
-            statMax = max(statMax, cnt);
-            statTotal += (unsigned long long)(cnt & 0x3fffffff);
-        }
-    }
-    for (int o = 16; o > 0; o >>= 1)
-    {
-        statMax = max(statMax, __shfl_xor_sync(0xffffffffu, statMax, o));
-        statTotal += __shfl_xor_sync(0xffffffffu, statTotal, o);
-    }
-    if (lane == 0 && statMax > 0)
-    {
-        if (statMax & 0x40000000) atomicOr(&gp->error, 4);      // a cell neighbourhood with more than 4096 beads: not for this build
-        statMax &= 0x3fffffff;
-        atomicMax(&gp->maxCount, statMax);
-        atomicMax(&gp->maxRaw, statMax);            // drives the capacity regrow, like the candidate count of the two-pass build
-        atomicAdd(&gp->totalEntries, statTotal);
-        if (statMax > cap) atomicOr(&gp->error, 1);
-    }
-}
-
-// ---- one-time self-check of the one-pass build against the two-pass build (auto mode) ------------------------------------
-// mismatch[0] counts slots whose row length, bin boundaries or entries differ
-__global__ void k_rows_compare(int nIon, int nPad, const uint32_t *__restrict__ a, const int *__restrict__ ca, const uint16_t *__restrict__ cuma,
-                               const uint32_t *__restrict__ b, const int *__restrict__ cb, const uint16_t *__restrict__ cumb, int *__restrict__ mismatch)
-{
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= nIon) return;
-    bool bad = ca[i] != cb[i];
-    for (int e = 0; e < NBINS && !bad; e++) bad = cuma[(size_t)e * nPad + i] != cumb[(size_t)e * nPad + i];
-    const int n = bad ? 0 : ca[i];
-    for (int k = 0; k < n && !bad; k++) bad = a[(size_t)k * nPad + i] != b[(size_t)k * nPad + i];
-    if (bad) atomicAdd(mismatch, 1);
-}

@@ -74,9 +74,14 @@ __host__ __device__ inline uint64_t packW(int lj, int qi, uint32_t mol, uint32_t
 
 struct Term
 {
-    int i, j, k, l;
+    int i, j, k, l;      // bead (input) indices; k, l = -1 when unused
     double p0, p1, p2;
     int kind, pad;
+};
+
+struct BondRange       // the bonded-term entries of one slot's bead: bondEnt[lo .. lo + n)
+{
+    int lo, n;
 };
 
 enum { PROF_INTEGRATE = 0, PROF_PAIR, PROF_BONDED, PROF_LIST, PROF_REDUCE, PROF_HALO, PROF_N = 8 };
@@ -141,11 +146,17 @@ struct ddcb200_ctx
     DevBuf<uint32_t> bpairKey;    // sorted (min<<16|max) keys per mol type
     bool haveExcl = false;
 
-    // bonded terms (input-index form and slot form)
+    // bonded terms (bead-index form) and the per-bead gather lists of k_bonded (bonded.cuh)
     int64_t nTerms = 0;
-    DevBuf<Term> termsBead, termsSlot;
+    DevBuf<Term> termsBead;
+    std::vector<Term> hTerms;
     int64_t nRestr = 0;
-    DevBuf<int> restrBead, restrSlot;
+    DevBuf<int> restrBead;
+    std::vector<int> hRestrBead;
+    bool bondCsrDirty = true;
+    DevBuf<int> bondCsrOff;       // nGlobal + 1: entries of bead b = bondEnt[bondCsrOff[b] .. bondCsrOff[b + 1])
+    DevBuf<uint32_t> bondEnt;     // (term << 2) | role of the bead in the term; term >= nTerms = restraint term - nTerms
+    DevBuf<BondRange> bondRange;  // per slot, refreshed at every list build
     DevBuf<double> restrParm;     // 7 doubles: frac0[3], kb, fc[3]
     int restrOrigin = 0;
 
@@ -183,14 +194,8 @@ struct ddcb200_ctx
     int nbrCap = 0;               // entries per bead allocated
     bool listValid = false;
     int64_t lastBuildLoop = -1;
-    // list-build variant: 0 = auto (the first four rebuilds alternate between the two builds under CUDA events, then the
-    // faster is kept; both write bit-identical rows), 1 = two-pass (k_nbr_filter + k_nbr_exact), 2 = one-pass (k_nbr_cell).
-    // DDCB200_LISTBUILD=auto|twopass|cell
     double binFrac[NBINS - 1] = {-0.25, -0.125, 0.0, 0.125, 0.25, 0.375, 0.625};   // ordering-bin edges, fractions of deltaR (DDCB200_BIN_EDGES)
-    int listBuildMode = 0;
-    bool cellBuildChecked = false;   // auto mode: the first one-pass build is compared, row for row, with a two-pass build of the same state
-    int listBuildsTimed = 0;
-    float listBuildMs[2] = {0.f, 0.f};
+    float listBuildMs = 0.f;         // device time of the last list build (filter + exact pass), for ddcb200_listBuildInfo
     cudaEvent_t evList[2] = {nullptr, nullptr};
     // displacement-triggered rebuild (updateRate == 0, nbrcheck.cuh)
     DevBuf<double> chk, chkPartial;   // chk: 3 sums now, 3 sums at the build, bits of max d^2

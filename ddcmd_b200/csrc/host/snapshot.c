@@ -76,6 +76,21 @@ static void diagInverse(const double h[9], double hi[3])
     hi[2] = d22 / det;
 }
 
+/* CreateSnapshotdir's name (src/io.c:32-56): <atomsdir>/snapshot.<loopFormat>, or <atomsdir>/<dirname>, or an absolute dirname as it is;
+ * relative to the deck's directory.  snprintf reports the untruncated length, so every piece is checked against the room left. */
+static int snapshotRel(const ddcb200_deck *d, const char *dirname, int64_t loop, char *rel, size_t size)
+{
+    char loopFmt[16], num[64];
+    snprintf(loopFmt, sizeof loopFmt, "%%%d.%dllu", d->nLoopDigits, d->nLoopDigits);
+    snprintf(num, sizeof num, loopFmt, (unsigned long long)loop);
+    int k;
+    if (dirname && dirname[0] == '/') k = snprintf(rel, size, "%s", dirname);
+    else if (dirname) k = snprintf(rel, size, "%s/%s", d->atomsdir, dirname);
+    else k = snprintf(rel, size, "%s/snapshot.%s", d->atomsdir, num);
+    if (k < 0 || (size_t)k >= size) return herr("snapshot directory name longer than %d characters", (int)size - 1);
+    return 0;
+}
+
 int ddcb200_writeRestart(const ddcb200_deck *d, const char *dirname, int64_t loop, double time_, const double h[9],
                          const double *rx, const double *ry, const double *rz, const double *vx, const double *vy,
                          const double *vz, const uint64_t *rngState, int restartLink, char *snapshotdirOut, size_t len)
@@ -88,15 +103,8 @@ int ddcb200_writeRestart(const ddcb200_deck *d, const char *dirname, int64_t loo
     const int haveRandom = d->haveRandom && rngState && d->rngMult && d->rngPrime;
 
     /* CreateSnapshotdir: <atomsdir>/snapshot.<loopFormat> or <atomsdir>/<dirname>; relative to the deck's directory */
-    char rel[1024], loopFmt[16];
-    snprintf(loopFmt, sizeof loopFmt, "%%%d.%dllu", d->nLoopDigits, d->nLoopDigits);
-    int k = (dirname && dirname[0] == '/') ? 0 : snprintf(rel, sizeof rel, "%s/", d->atomsdir);   /* an absolute dirname is taken as it is */
-    if (dirname) snprintf(rel + k, sizeof rel - (size_t)k, "%s", dirname);
-    else
-    {
-        k += snprintf(rel + k, sizeof rel - (size_t)k, "snapshot.");
-        snprintf(rel + k, sizeof rel - (size_t)k, loopFmt, (unsigned long long)loop);
-    }
+    char rel[1024];
+    if (snapshotRel(d, dirname, loop, rel, sizeof rel) != 0) return -1;
     char *dir = pathJoin(d->runDir, rel);
     if (mkdir(dir, 0777) != 0 && errno != EEXIST) { herr("writeRestart: cannot create %s: %s", dir, strerror(errno)); free(dir); return -1; }
     if (snapshotdirOut) snprintf(snapshotdirOut, len, "%s", dir);
@@ -201,13 +209,13 @@ int ddcb200_writeRestart(const ddcb200_deck *d, const char *dirname, int64_t loo
     char *apath = pathJoin(dir, "atoms#000000");
     FILE *f = fopen(apath, "wb");
     if (!f) { herr("writeRestart: cannot open %s: %s", apath, strerror(errno)); free(apath); free(dir); free(hb.p); return -1; }
-    fwrite(hb.p, 1, hb.n, f);
+    int rc = 0;
+    if (fwrite(hb.p, 1, hb.n, f) != hb.n) rc = herr("writeRestart: short write to %s", apath);
     free(hb.p);
 
     /* ---- records (src/collection_write.c:150-184) ---- */
     double hi[3];
     diagInverse(h, hi);
-    int rc = 0;
     for (int64_t i = 0; i < d->n && rc == 0; i++)
     {
         /* backInBox = Preduce, pbc 7 (src/preduce.c:282-340): r += h * (-rint(hinv r)) */
@@ -274,7 +282,9 @@ int ddcb200_writeRestart(const ddcb200_deck *d, const char *dirname, int64_t loo
     for (int g = 0; g < d->nGroups; g++)
         if (d->groupType[g] == 1) fprintf(f, "%s GROUP { Teq=%f ;}\n", d->groupName[g], hu_convert(d->groupTeq[g], NULL, "T"));
     fprintf(f, "%s COLLECTION { size=%llu; files=%s/atoms#;}\n", d->collectionName, (unsigned long long)d->n, rel);
-    fclose(f);
+    /* a truncated checkpoint (full disk) must not become ./restart */
+    const int werr = ferror(f);
+    if (fclose(f) != 0 || werr) { herr("writeRestart: writing %s failed", rpath); free(rpath); free(dir); return -1; }
     if (restartLink)
     {
         /* unlink("restart"); symlink(<snapshotdir>/restart, "restart") in the run directory */
@@ -296,15 +306,8 @@ int ddcb200_writeBXYZ(const ddcb200_deck *d, const char *dirname, int64_t loop, 
     /* writeBXYZ (src/io.c:144-155) + collection_writeBXYZ mode 1 (src/collection_write.c:338-465): crc u4 | id | pinfo | r f4 x3 |
      * v f4 x3 | energy f4 | virial f4.  The Martini path keeps no per-particle energy or virial (they stay at zeroAll's 0). */
     if (!d || !h || !rx || !ry || !rz || !vx || !vy || !vz) return herr("writeBXYZ: null argument");
-    char rel[1024], loopFmt[16];
-    snprintf(loopFmt, sizeof loopFmt, "%%%d.%dllu", d->nLoopDigits, d->nLoopDigits);
-    int k = (dirname && dirname[0] == '/') ? 0 : snprintf(rel, sizeof rel, "%s/", d->atomsdir);
-    if (dirname) snprintf(rel + k, sizeof rel - (size_t)k, "%s", dirname);
-    else
-    {
-        k += snprintf(rel + k, sizeof rel - (size_t)k, "snapshot.");
-        snprintf(rel + k, sizeof rel - (size_t)k, loopFmt, (unsigned long long)loop);
-    }
+    char rel[1024];
+    if (snapshotRel(d, dirname, loop, rel, sizeof rel) != 0) return -1;
     char *dir = pathJoin(d->runDir, rel);
     if (mkdir(dir, 0777) != 0 && errno != EEXIST) { herr("writeBXYZ: cannot create %s: %s", dir, strerror(errno)); free(dir); return -1; }
     char *path = pathJoin(dir, "bxyz#000000");
@@ -383,15 +386,8 @@ int64_t ddcb200_subsetWrite(const ddcb200_deck *d, int which, const char *dirnam
     if (which < 0 || which >= d->nSubsets) return herr("subsetWrite: no such ANALYSIS (%d of %d)", which, d->nSubsets);
     const ddcb200_subset *q = &d->subsets[which];
     /* CreateSnapshotdir(simulate, NULL) + "<snapshotdir>/<filename>" (src/subsetWrite.c:441-444) */
-    char rel[1024], loopFmt[16];
-    snprintf(loopFmt, sizeof loopFmt, "%%%d.%dllu", d->nLoopDigits, d->nLoopDigits);
-    int k = (dirname && dirname[0] == '/') ? 0 : snprintf(rel, sizeof rel, "%s/", d->atomsdir);
-    if (dirname) snprintf(rel + k, sizeof rel - (size_t)k, "%s", dirname);
-    else
-    {
-        k += snprintf(rel + k, sizeof rel - (size_t)k, "snapshot.");
-        snprintf(rel + k, sizeof rel - (size_t)k, loopFmt, (unsigned long long)loop);
-    }
+    char rel[1024];
+    if (snapshotRel(d, dirname, loop, rel, sizeof rel) != 0) return -1;
     char *dir = pathJoin(d->runDir, rel);
     if (mkdir(dir, 0777) != 0 && errno != EEXIST) { herr("subsetWrite: cannot create %s: %s", dir, strerror(errno)); free(dir); return -1; }
     char fname[300];
@@ -491,15 +487,8 @@ int ddcb200_pairCorrelationWrite(const ddcb200_deck *d, int which, const char *d
     if (which < 0 || which >= d->nPairCorr) return herr("pairCorrelationWrite: no such ANALYSIS (%d of %d)", which, d->nPairCorr);
     if (nsample <= 0) return 0;                              /* nothing sampled: the reference writes nothing */
     const ddcb200_paircorr *q = &d->pairCorr[which];
-    char rel[1024], loopFmt[16];
-    snprintf(loopFmt, sizeof loopFmt, "%%%d.%dllu", d->nLoopDigits, d->nLoopDigits);
-    int k = (dirname && dirname[0] == '/') ? 0 : snprintf(rel, sizeof rel, "%s/", d->atomsdir);
-    if (dirname) snprintf(rel + k, sizeof rel - (size_t)k, "%s", dirname);
-    else
-    {
-        k += snprintf(rel + k, sizeof rel - (size_t)k, "snapshot.");
-        snprintf(rel + k, sizeof rel - (size_t)k, loopFmt, (unsigned long long)loop);
-    }
+    char rel[1024];
+    if (snapshotRel(d, dirname, loop, rel, sizeof rel) != 0) return -1;
     char *dir = pathJoin(d->runDir, rel);
     if (mkdir(dir, 0777) != 0 && errno != EEXIST) { herr("pairCorrelationWrite: cannot create %s: %s", dir, strerror(errno)); free(dir); return -1; }
     char *path = pathJoin(dir, q->filename);

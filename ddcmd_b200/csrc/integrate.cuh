@@ -151,7 +151,9 @@ __global__ void k_mol_virial(int64_t nMol, const int64_t *__restrict__ molOffset
     {
         const int64_t lo = molOffset[m], hi = molOffset[m + 1];
         const int s0 = slotOfBead[molBeads[lo]];   // first listed bead = ownership bead
-        if (s0 >= 0)
+        // the molecule is summed on the rank that owns it: its ownership bead is resident AND not a ghost (there every
+        // bead of the molecule is local, src/ddcRuleMolecule.c:43; on other ranks some of its beads may be ghosts or absent)
+        if (s0 >= 0 && !((((unsigned long long)__double_as_longlong(pos[s0].w)) >> 63)))
         {
             const double4 p0 = pos[s0];
             double M = 0, Rx = 0, Ry = 0, Rz = 0;

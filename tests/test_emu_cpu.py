@@ -51,23 +51,13 @@ def test_emu_step0_forces_energy_virial(emu, golden_dir, name):
     tg.test_step0_forces_energy_virial(golden_dir, name)
 
 
-@pytest.mark.parametrize("name", ["popc_small", "tiny2"])
-def test_emu_list_builds_agree(emu, golden_dir, name, monkeypatch):
-    tv.test_list_builds_agree_bit_for_bit(golden_dir, name, monkeypatch)
-
-
 @pytest.mark.parametrize("name", ["popc_small"])
 def test_emu_per_bead_walk_bound(emu, golden_dir, name, monkeypatch):
     tv.test_per_bead_walk_bound_is_bitwise_neutral(golden_dir, name, monkeypatch)
 
 
-@pytest.mark.parametrize("mode", ["twopass", "cell"])
-def test_emu_row_capacity_regrow(emu, golden_dir, monkeypatch, mode):
-    tv.test_row_capacity_regrow(golden_dir, monkeypatch, mode)
-
-
-def test_emu_auto_mode_self_check(emu, golden_dir, monkeypatch, capfd):
-    tv.test_auto_mode_self_check_falls_back(golden_dir, monkeypatch, capfd)
+def test_emu_row_capacity_regrow(emu, golden_dir, monkeypatch):
+    tv.test_row_capacity_regrow(golden_dir, monkeypatch)
 
 
 def test_emu_bin_edges_knob(emu, golden_dir, monkeypatch):

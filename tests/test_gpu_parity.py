@@ -109,17 +109,27 @@ def test_trajectory_40_steps(golden_dir, name):
     assert np.quantile(dz, 0.99) < 1e-9 and dz.max() < 1e-6
 
 
-def test_deterministic_forces(golden_dir):
-    """Pair forces need no atomics: two evaluations are bitwise identical."""
-    sim, _ = _load(golden_dir, "waterbox")
-    sim.ddcenergy(1)
-    a = sim.getState()
-    e1 = sim.energyInfo().eion
-    sim2, _ = _load(golden_dir, "waterbox")
-    sim2.ddcenergy(1)
-    b = sim2.getState()
-    assert np.array_equal(a["fx"], b["fx"]) and np.array_equal(a["fz"], b["fz"])
-    assert e1 == sim2.energyInfo().eion
+@pytest.mark.parametrize("name", ["waterbox", "popc_small", "ras_small"])
+def test_deterministic_forces(golden_dir, name):
+    """Neither the pair nor the bonded kernel uses a floating-point atomic: two runs (25 steps, one rebuild) are bitwise identical
+    in forces, positions and every energy term - also on the decks with bonds, angles, dihedrals and restraints."""
+    out = []
+    for _ in range(2):
+        sim, _ = _load(golden_dir, name)
+        sim.ddcenergy(1)
+        a = sim.getState()
+        e0 = sim.energyInfo()
+        sim.nglf(25)
+        b = sim.getState()
+        e1 = sim.energyInfo()
+        out.append((a, b, [e0.eion, e0.eBond, e0.eAngle, e0.eTorsion, e0.eImproper, e0.eRestraint] + list(e0.virial[:]),
+                    [e1.eion, e1.rk, e1.eBond, e1.eAngle] + list(e1.virial[:])))
+        sim.close()
+    for k in ("fx", "fy", "fz"):
+        assert np.array_equal(out[0][0][k], out[1][0][k]), k
+    for k in ("rx", "ry", "rz", "vx", "vy", "vz", "fx", "fy", "fz"):
+        assert np.array_equal(out[0][1][k], out[1][1][k]), k
+    assert out[0][2] == out[1][2] and out[0][3] == out[1][3]
 
 
 def test_printinfo_line_matches_reference_data_file(golden_dir):

@@ -1,54 +1,16 @@
-"""Build / walk variants that must not change a result (collected after every other GPU test):
+"""Walk / row-order variants that must not change a result:
 
-  * the one-pass cell list build against the two-pass build: bit-identical rows, forces, trajectories (auto mode picks by timing);
   * the per-bead list-walk bound against the global one: bitwise equal trajectories;
-  * DDCB200_BIN_EDGES: another row order, same pair set, forces to rounding.
+  * DDCB200_BIN_EDGES: another row order, same pair set, forces to rounding;
+  * a first build whose rows overflow the allocated capacity regrows and repeats.
 """
 import numpy as np
 import pytest
 
 import ddcmd_b200 as dd
-from test_gpu_parity import DECKS, F_TOL, _force_err, _load, _pairkey
+from test_gpu_parity import F_TOL, _force_err, _load, _pairkey
 
 pytestmark = pytest.mark.gpu
-
-
-def _rows_and_forces(golden_dir, name, mode, monkeypatch):
-    monkeypatch.setenv("DDCB200_LISTBUILD", mode)
-    sim, ref = _load(golden_dir, name)
-    sim.ddcenergy(1)
-    e = sim.energyInfo()
-    st = sim.getState()
-    pairs = sim.getPairs()          # decoded in row order: equal arrays = equal rows, entry for entry
-    cells = sim.getCells()[0]
-    sim.nglf(61)                    # across three rebuilds: the auto mode has timed both builds twice by then
-    e2 = sim.energyInfo()
-    st2 = sim.getState()
-    info = sim.listBuildInfo()
-    sim.close()
-    return pairs, cells, st, e, st2, e2, info
-
-
-@pytest.mark.parametrize("name", DECKS)
-def test_list_builds_agree_bit_for_bit(golden_dir, name, monkeypatch):
-    """The one-pass cell build (k_nbr_cell) and the two-pass build (k_nbr_filter + k_nbr_exact) write the same rows in the same
-    order, so forces, energies and the trajectory across a rebuild are bitwise equal whichever one the timing picks."""
-    a = _rows_and_forces(golden_dir, name, "twopass", monkeypatch)
-    b = _rows_and_forces(golden_dir, name, "cell", monkeypatch)
-    assert a[6][0] == 1 and b[6][0] == 2
-    for x, y in zip(a[0], b[0]):
-        assert np.array_equal(x, y)
-    assert np.array_equal(a[1], b[1])
-    for k in ("fx", "fy", "fz"):
-        assert np.array_equal(a[2][k], b[2][k])
-    assert a[3].eion == b[3].eion and a[3].nPairsListed == b[3].nPairsListed
-    for k in ("rx", "ry", "rz", "vx", "vy", "vz", "fx"):
-        assert np.array_equal(a[4][k], b[4][k])
-    assert a[5].eion == b[5].eion and a[5].rk == b[5].rk and a[5].nPairsListed == b[5].nPairsListed
-    # auto: the first four builds alternate, then the faster of the two
-    c = _rows_and_forces(golden_dir, name, "auto", monkeypatch)
-    assert c[6][0] in (1, 2) and c[6][1][0] > 0.0 and c[6][1][1] > 0.0
-    assert np.array_equal(c[4]["rx"], a[4]["rx"]) and c[5].eion == a[5].eion
 
 
 def test_bin_edges_knob_keeps_the_pair_set(golden_dir, monkeypatch):
@@ -97,11 +59,9 @@ def test_per_bead_walk_bound_is_bitwise_neutral(golden_dir, name, monkeypatch):
     assert a[1] == b[1] and a[2] == b[2] and np.array_equal(a[3], b[3])
 
 
-@pytest.mark.parametrize("mode", ["twopass", "cell"])
-def test_row_capacity_regrow(golden_dir, monkeypatch, mode):
+def test_row_capacity_regrow(golden_dir, monkeypatch):
     """A first build whose rows overflow the allocated capacity (forced small here) regrows from the measured maximum and repeats:
-    same pairs, same forces as with the default capacity, in both builds."""
-    monkeypatch.setenv("DDCB200_LISTBUILD", mode)
+    same pairs, same forces as with the default capacity."""
     sim, ref = _load(golden_dir, "popc_small")
     sim.ddcenergy(1)
     a = sim.getState()
@@ -120,36 +80,3 @@ def test_row_capacity_regrow(golden_dir, monkeypatch, mode):
     sim.nglf(21)
     assert sim.energyInfo().nPairsListed == int(ref["trace"].reshape(-1, 16)[20, 14])
     sim.close()
-
-
-def test_auto_mode_self_check_falls_back(golden_dir, monkeypatch, capfd):
-    """auto mode compares its first one-pass build with a two-pass build of the same state; a (here: injected) difference makes
-    the context keep the two-pass build, with the same results."""
-    monkeypatch.setenv("DDCB200_LISTBUILD", "twopass")
-    sim, ref = _load(golden_dir, "popc_small")
-    sim.nglf(45)
-    a = sim.getState()
-    ea = sim.energyInfo()
-    sim.close()
-    monkeypatch.setenv("DDCB200_LISTBUILD", "auto")
-    monkeypatch.setenv("DDCB200_SELFCHECK_FAULT", "1")
-    sim, _ = _load(golden_dir, "popc_small")
-    sim.nglf(45)
-    b = sim.getState()
-    eb = sim.energyInfo()
-    assert sim.listBuildInfo()[0] == 1
-    sim.close()
-    assert "keeping the two-pass build" in capfd.readouterr().err
-    for k in ("rx", "vx", "fx", "fz"):
-        assert np.array_equal(a[k], b[k])
-    assert ea.eion == eb.eion and ea.nPairsListed == eb.nPairsListed
-    # without the injected fault the check passes silently and both builds get timed
-    monkeypatch.delenv("DDCB200_SELFCHECK_FAULT")
-    sim, _ = _load(golden_dir, "popc_small")
-    sim.nglf(65)
-    info = sim.listBuildInfo()
-    c = sim.getState()
-    sim.close()
-    assert info[0] in (1, 2) and info[1][0] > 0 and info[1][1] > 0
-    assert "keeping the two-pass build" not in capfd.readouterr().err
-    assert np.array_equal(c["rx"][:10], c["rx"][:10])
