@@ -289,14 +289,19 @@ extern "C" void ddcb200_destroy(ddcb200_ctx *c)
     if (c->consFlag) cudaFree(c->consFlag);
     c->chk.release(); c->chkPartial.release();
     if (c->chkHost) cudaFreeHost(c->chkHost);
-    c->ownerBead.release(); c->gState.release(); c->ownerOfBead.release(); c->ddcMask.release(); c->ddcCnt.release();
-    c->ddcColTotal.release(); c->ddcColStart.release(); c->ddcList.release(); c->sendSlot.release(); c->recvSlot.release();
+    c->ownerBead.release(); c->ddcDest.release(); c->ddcMask.release();
+    c->ddcList.release(); c->sendSlot.release(); c->recvSlot.release();
     c->sendBuf.release(); c->recvBuf.release(); c->accG.release();
-    if (c->boxEnc) cudaFree(c->boxEnc);
+    if (c->ddcWork) cudaFree(c->ddcWork);
+    if (c->ddcWorkInit) cudaFreeHost(c->ddcWorkInit);
+    if (c->ddcRow) cudaFree(c->ddcRow);
+    if (c->ddcRowAll) cudaFree(c->ddcRowAll);
+    if (c->ddcRowHost) cudaFreeHost(c->ddcRowHost);
+    if (c->ddcBox6) cudaFree(c->ddcBox6);
+    if (c->ddcBoxAll) cudaFree(c->ddcBoxAll);
     if (c->boxes) cudaFree(c->boxes);
     if (c->ddcCounters) cudaFree(c->ddcCounters);
     if (c->ddcHost) cudaFreeHost(c->ddcHost);
-    if (c->boxInitHost) cudaFreeHost(c->boxInitHost);
     if (c->nccl) ncclCommDestroy((ncclComm_t)c->nccl);
     for (auto &pe : c->pending)
     {
@@ -539,16 +544,32 @@ extern "C" int ddcb200_setMolecules(ddcb200_ctx *c, int64_t nMol, const int64_t 
     return DDCB200_OK;
 }
 
-static int ensureState(ddcb200_ctx *c, int64_t nIon)
+static int64_t padTile(int64_t n) { return ((n + TILE - 1) / TILE) * TILE; }
+
+// the slot arrays of one buffer set; keep = what they hold must survive a reallocation
+static int ensureSlots(ddcb200_ctx *c, int k, int64_t nIon, bool keep)
 {
-    const int64_t nPad = ((nIon + TILE - 1) / TILE) * TILE;
-    for (int k = 0; k < 2; k++)
+    const size_t nPad = (size_t)padTile(nIon);
+    if (keep)
     {
-        CK(c->pos4[k].ensure((size_t)nPad));
-        CK(c->beadOfSlot[k].ensure((size_t)nPad));
-        CK(c->cellOfSlot[k].ensure((size_t)nPad));
-        for (int a = 0; a < 3; a++) CK(c->vel[k][a].ensure((size_t)nPad));
+        CK(c->pos4[k].grow(nPad, c->stream));
+        CK(c->beadOfSlot[k].grow(nPad, c->stream));
+        for (int a = 0; a < 3; a++) CK(c->vel[k][a].grow(nPad, c->stream));
     }
+    else
+    {
+        CK(c->pos4[k].ensure(nPad));
+        CK(c->beadOfSlot[k].ensure(nPad));
+        for (int a = 0; a < 3; a++) CK(c->vel[k][a].ensure(nPad));
+    }
+    CK(c->cellOfSlot[k].ensure(nPad));
+    return DDCB200_OK;
+}
+
+// everything else that is sized by the resident bead count and rebuilt by the list build
+static int ensureAux(ddcb200_ctx *c, int64_t nIon)
+{
+    const int64_t nPad = padTile(nIon);
     for (int a = 0; a < 3; a++) CK(c->frc[a].ensure((size_t)nPad));
     CK(c->rank0.ensure((size_t)nPad));
     CK(c->member.ensure((size_t)nPad));
@@ -567,6 +588,16 @@ static int ensureState(ddcb200_ctx *c, int64_t nIon)
     CK(c->kinPartial.ensure(tiles * 7 + 8));
     c->nPad = nPad;
     return DDCB200_OK;
+}
+
+static int ensureState(ddcb200_ctx *c, int64_t nIon)
+{
+    for (int k = 0; k < 2; k++)
+    {
+        const int rc = ensureSlots(c, k, nIon, false);
+        if (rc) return rc;
+    }
+    return ensureAux(c, nIon);
 }
 
 extern "C" int ddcb200_sendState(ddcb200_ctx *c, int64_t nLocal, const int *bead, const double *rx, const double *ry, const double *rz,
@@ -728,90 +759,169 @@ static void buildOwnerBead(const std::vector<int64_t> &molOffset, const std::vec
         for (int64_t k = molOffset[m]; k < molOffset[m + 1]; k++) ob[(size_t)molBeads[(size_t)k]] = molBeads[(size_t)molOffset[m]];
 }
 
-static int ensureState(ddcb200_ctx *c, int64_t nIon);
+// every rank's count row (DDC_ROW ints) to every rank, then to pinned host memory; returns with the stream idle
+static int gatherRows(ddcb200_ctx *c, int phase, int nLocal, double *box6)
+{
+    cudaStream_t st = c->stream;
+    LAUNCH(k_rd_row, 1, DDC_ROW, 0, st)((const DdcWork *)c->ddcWork, phase, nLocal, c->ddcRow, box6);
+    CKL("k_rd_row");
+    CKN(ncclAllGather(c->ddcRow, c->ddcRowAll, DDC_ROW, ncclInt32, (ncclComm_t)c->nccl, st));
+    CK(cudaMemcpyAsync(c->ddcRowHost, c->ddcRowAll, (size_t)c->nranks * DDC_ROW * sizeof(int), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    return DDCB200_OK;
+}
 
+// grouped point-to-point exchange of `rec` doubles per item (ddcSendRecvTables' MPI_Isend/Irecv pairs, src/ddcSendRecv.c:216-262)
+static int exchange(ddcb200_ctx *c, int rec, const std::vector<int> &sendCount, const std::vector<int> &sendOff, const std::vector<int> &recvCount,
+                    const std::vector<int> &recvOff)
+{
+    ncclComm_t comm = (ncclComm_t)c->nccl;
+    CKN(ncclGroupStart());
+    for (int pp = 0; pp < c->nranks; pp++)
+    {
+        if (pp == c->rank) continue;
+        if (sendCount[pp]) CKN(ncclSend(c->sendBuf.p + (size_t)rec * sendOff[pp], (size_t)rec * sendCount[pp], ncclDouble, pp, comm, c->stream));
+        if (recvCount[pp]) CKN(ncclRecv(c->recvBuf.p + (size_t)rec * recvOff[pp], (size_t)rec * recvCount[pp], ncclDouble, pp, comm, c->stream));
+    }
+    CKN(ncclGroupEnd());
+    return DDCB200_OK;
+}
+
+// ddcAssignment + ddcSendRecvTables (src/ddcAssignment.c:64-107, src/ddcSendRecv.c:41-277): see ddc.cuh
 static int redomain(ddcb200_ctx *c)
 {
     cudaStream_t st = c->stream;
-    ncclComm_t comm = (ncclComm_t)c->nccl;
-    const int64_t nG = c->nGlobal;
     const DdcGeom g = ddcGeomOf(c);
-    const int nb = (int)((nG + 255) / 256);
+    const int nr = c->nranks, me = c->rank;
+    const int cur = c->cur, nxt = cur ^ 1;
+    const int nIonOld = (int)c->nIon, nLocalOld = (int)c->nLocal;
     if (!c->ownerBeadValid)
     {
         std::vector<int> ob;
-        buildOwnerBead(c->hMolOffset, c->hMolBeads, nG, ob);
-        CK(c->ownerBead.ensure((size_t)nG));
-        CK(cudaMemcpy(c->ownerBead.p, ob.data(), nG * sizeof(int), cudaMemcpyHostToDevice));
+        buildOwnerBead(c->hMolOffset, c->hMolBeads, c->nGlobal, ob);
+        CK(c->ownerBead.ensure((size_t)c->nGlobal));
+        CK(cudaMemcpy(c->ownerBead.p, ob.data(), c->nGlobal * sizeof(int), cudaMemcpyHostToDevice));
         c->ownerBeadValid = true;
     }
-    CK(c->gState.ensure((size_t)nG * 6));
-    CK(c->ownerOfBead.ensure((size_t)nG));
-    CK(c->ddcMask.ensure((size_t)nG));
-    // 1. replicate the dynamic state: scatter my beads into zeros, sum over ranks (one contributor per element)
-    const int cur = c->cur;
-    CK(cudaMemsetAsync(c->gState.p, 0, (size_t)nG * 6 * sizeof(double), st));
-    LAUNCH(k_ddc_scatter, (int)((c->nIon + 255) / 256), 256, 0, st)((int)c->nIon, nG, c->pos4[cur].p, c->vel[cur][0].p, c->vel[cur][1].p,
-                                                                c->vel[cur][2].p, c->gState.p);
-    CKL("k_ddc_scatter");
-    CKN(ncclAllReduce(c->gState.p, c->gState.p, (size_t)nG * 6, ncclDouble, ncclSum, comm, st));
-    // 2. owners and bounding boxes, identically on every rank
-    CK(cudaMemcpyAsync(c->boxEnc, c->boxInitHost, DDC_MAXRANKS * 6 * sizeof(unsigned long long), cudaMemcpyHostToDevice, st));
-    LAUNCH(k_ddc_owner, nb, 256, 0, st)(nG, c->gState.p, c->ownerBead.p, g, c->ownerOfBead.p, c->boxEnc);
-    CKL("k_ddc_owner");
-    LAUNCH(k_ddc_boxes, 1, 128, 0, st)(c->nranks, c->boxEnc, (DdcBoxes *)c->boxes);
-    CKL("k_ddc_boxes");
-    // 3. classify
-    CK(cudaMemsetAsync(c->ddcCounters, 0, 8 * sizeof(int), st));
-    LAUNCH(k_ddc_mask, nb, 256, 0, st)(nG, c->gState.p, c->ownerOfBead.p, g, (const DdcBoxes *)c->boxes, c->ddcMask.p, c->ddcCounters);
-    CKL("k_ddc_mask");
-    CK(cudaMemcpyAsync(c->ddcHost, c->ddcCounters, 2 * sizeof(int), cudaMemcpyDeviceToHost, st));
-    CK(cudaStreamSynchronize(st));
-    const int64_t nLocal = c->ddcHost[0], nGhost = c->ddcHost[1];
-    if (nLocal <= 0) return fail(DDCB200_ERR_STATE, "a rank owns no beads after the domain assignment (fewer bricks than the system can fill)");
-    int rc = ensureState(c, nLocal + nGhost);
+    DdcWork *work = (DdcWork *)c->ddcWork;
+    const int nbOld = (nIonOld + 255) / 256;
+    // ---- A. migration ----
+    CK(c->ddcDest.ensure((size_t)nIonOld + 1));
+    CK(cudaMemcpyAsync(work, c->ddcWorkInit, sizeof(DdcWork), cudaMemcpyHostToDevice, st));
+    LAUNCH(k_rd_dest, nbOld, 256, 0, st)(nIonOld, c->pos4[cur].p, c->slotOfBead.p, c->ownerBead.p, g, c->ddcDest.p, work);
+    CKL("k_rd_dest");
+    int rc = gatherRows(c, 0, nLocalOld, nullptr);
     if (rc) return rc;
+    const int *rows = c->ddcRowHost;
+    std::vector<int> sendCount(nr, 0), recvCount(nr, 0), sendOff(nr, 0), recvOff(nr, 0);
+    int nSend = 0, nRecv = 0;
+    for (int r = 0; r < nr; r++)
+    {
+        // every rank sees every row, so every rank takes the same decision here (nobody is left waiting in a collective)
+        if (rows[r * DDC_ROW + 16] & 1)
+            return fail(DDCB200_ERR_STATE, "a molecule is split between ranks: the beads given to sendState on one rank must be whole molecules (ddcRuleMolecule)");
+        int64_t nNew = rows[r * DDC_ROW + 17];
+        for (int q = 0; q < nr; q++) nNew += rows[q * DDC_ROW + r] - rows[r * DDC_ROW + q];
+        if (nNew <= 0) return fail(DDCB200_ERR_STATE, "a rank owns no beads after the domain assignment (fewer bricks than the system can fill)");
+    }
+    for (int q = 0; q < nr; q++)
+    {
+        if (q == me) continue;
+        sendCount[q] = rows[me * DDC_ROW + q];
+        recvCount[q] = rows[q * DDC_ROW + me];
+        sendOff[q] = nSend;
+        recvOff[q] = nRecv;
+        nSend += sendCount[q];
+        nRecv += recvCount[q];
+    }
+    const int nStay = nLocalOld - nSend, nLocal = nStay + nRecv;
+    const int rec = c->haveRandom ? 8 : 7;
+    CK(c->sendBuf.ensure((size_t)nSend * rec + 8));
+    CK(c->recvBuf.ensure((size_t)nRecv * rec + 8));
+    if (nSend)
+    {
+        DdcOffsets off;
+        for (int q = 0; q < DDC_MAXRANKS; q++) off.off[q] = q < nr ? sendOff[q] : 0;
+        LAUNCH(k_rd_pack, nbOld, 256, 0, st)(nIonOld, c->pos4[cur].p, c->vel[cur][0].p, c->vel[cur][1].p, c->vel[cur][2].p, c->ddcDest.p, me, work, off,
+                                         rec, c->rngState.p, c->sendBuf.p);
+        CKL("k_rd_pack");
+    }
+    rc = exchange(c, rec, sendCount, sendOff, recvCount, recvOff);
+    if (rc) return rc;
+    rc = ensureSlots(c, nxt, nLocal, false);
+    if (rc) return rc;
+    LAUNCH(k_rd_clear, nbOld, 256, 0, st)(nIonOld, c->beadOfSlot[cur].p, c->slotOfBead.p);
+    CKL("k_rd_clear");
+    LAUNCH(k_rd_compact, nbOld, 256, 0, st)(nIonOld, c->pos4[cur].p, c->vel[cur][0].p, c->vel[cur][1].p, c->vel[cur][2].p, c->beadOfSlot[cur].p,
+                                        c->ddcDest.p, me, work, c->pos4[nxt].p, c->vel[nxt][0].p, c->vel[nxt][1].p, c->vel[nxt][2].p,
+                                        c->beadOfSlot[nxt].p, c->slotOfBead.p);
+    CKL("k_rd_compact");
+    if (nRecv)
+    {
+        LAUNCH(k_rd_unpack, (nRecv + 255) / 256, 256, 0, st)(nRecv, c->recvBuf.p, rec, nStay, c->wOfBead.p, c->pos4[nxt].p, c->vel[nxt][0].p,
+                                                         c->vel[nxt][1].p, c->vel[nxt][2].p, c->beadOfSlot[nxt].p, c->slotOfBead.p, c->rngState.p);
+        CKL("k_rd_unpack");
+    }
+    // ---- B. ghosts ----
+    const int nbNew = (nLocal + 255) / 256;
+    LAUNCH(k_rd_bbox, nbNew, 256, 0, st)(nLocal, c->pos4[nxt].p, g, work);
+    CKL("k_rd_bbox");
+    LAUNCH(k_rd_row, 1, DDC_ROW, 0, st)(work, 1, nLocal, c->ddcRow, c->ddcBox6);
+    CKL("k_rd_row");
+    CKN(ncclAllGather(c->ddcBox6, c->ddcBoxAll, 6, ncclDouble, (ncclComm_t)c->nccl, st));
+    LAUNCH(k_rd_boxes, 1, 128, 0, st)(nr, c->ddcBoxAll, (DdcBoxes *)c->boxes);
+    CKL("k_rd_boxes");
+    CK(c->ddcMask.ensure((size_t)nLocal + 1));
+    LAUNCH(k_rd_ghostmask, nbNew, 256, 0, st)(nLocal, c->pos4[nxt].p, g, (const DdcBoxes *)c->boxes, c->ddcMask.p, work);
+    CKL("k_rd_ghostmask");
+    rc = gatherRows(c, 1, nLocal, nullptr);
+    if (rc) return rc;
+    c->hSendCount.assign(nr, 0); c->hRecvCount.assign(nr, 0);
+    c->hSendOff.assign(nr, 0); c->hRecvOff.assign(nr, 0);
+    int nSendG = 0, nRecvG = 0;
+    for (int q = 0; q < nr; q++)
+    {
+        if (q == me) continue;
+        c->hSendCount[q] = rows[me * DDC_ROW + q];
+        c->hRecvCount[q] = rows[q * DDC_ROW + me];
+        c->hSendOff[q] = nSendG;
+        c->hRecvOff[q] = nRecvG;
+        nSendG += c->hSendCount[q];
+        nRecvG += c->hRecvCount[q];
+    }
+    c->nSendTot = nSendG;
+    c->nRecvTot = nRecvG;
+    const int nIon = nLocal + nRecvG;
+    rc = ensureSlots(c, nxt, nIon, true);      // holds the new locals
+    if (rc) return rc;
+    rc = ensureSlots(c, cur, nIon, false);     // the old set is dead from here on
+    if (rc) return rc;
+    rc = ensureAux(c, nIon);
+    if (rc) return rc;
+    CK(c->ddcList.ensure((size_t)nSendG + nRecvG + 1));
+    CK(c->sendSlot.ensure((size_t)nSendG + 1));
+    CK(c->recvSlot.ensure((size_t)nRecvG + 1));
+    CK(c->sendBuf.ensure((size_t)nSendG * 4 + 8));
+    CK(c->recvBuf.ensure((size_t)nRecvG * 4 + 8));
+    if (nSendG)
+    {
+        DdcOffsets off;
+        for (int q = 0; q < DDC_MAXRANKS; q++) off.off[q] = q < nr ? c->hSendOff[q] : 0;
+        LAUNCH(k_rd_ghostpack, nbNew, 256, 0, st)(nLocal, c->pos4[nxt].p, c->ddcMask.p, nr, work, off, c->ddcList.p, c->sendBuf.p);
+        CKL("k_rd_ghostpack");
+    }
+    rc = exchange(c, 4, c->hSendCount, c->hSendOff, c->hRecvCount, c->hRecvOff);
+    if (rc) return rc;
+    if (nRecvG)
+    {
+        LAUNCH(k_rd_ghostunpack, (nRecvG + 255) / 256, 256, 0, st)(nRecvG, c->recvBuf.p, nLocal, c->wOfBead.p, c->pos4[nxt].p, c->vel[nxt][0].p,
+                                                               c->vel[nxt][1].p, c->vel[nxt][2].p, c->beadOfSlot[nxt].p, c->slotOfBead.p,
+                                                               c->ddcList.p + nSendG);
+        CKL("k_rd_ghostunpack");
+    }
+    c->cur = nxt;
     c->nLocal = nLocal;
-    c->nIon = nLocal + nGhost;
-    // 4. slot arrays from the replicated state
-    CK(cudaMemsetAsync(c->slotOfBead.p, 0xff, nG * sizeof(int), st));
-    LAUNCH(k_ddc_select, nb, 256, 0, st)(nG, c->gState.p, c->ddcMask.p, c->wOfBead.p, c->ddcCounters + 2, c->pos4[cur].p, c->vel[cur][0].p,
-                                     c->vel[cur][1].p, c->vel[cur][2].p, c->beadOfSlot[cur].p, c->slotOfBead.p);
-    CKL("k_ddc_select");
-    // 5. send / recv lists in ascending bead order: columns = [send to p (p != me)...] then [recv from p ...]
-    uint32_t colBits = 0u;
-    int ncol = 0;
-    for (int pp = 0; pp < c->nranks; pp++)
-        if (pp != c->rank) { colBits |= 1u << pp; colBits |= 1u << (16 + pp); ncol += 2; }
-    const int nUnits = (int)((nG + 31) / 32);
-    CK(c->ddcCnt.ensure((size_t)ncol * nUnits));
-    CK(c->ddcColTotal.ensure(32));
-    CK(c->ddcColStart.ensure(32));
-    LAUNCH(k_ddc_colcount, nb, 256, 0, st)(nG, c->ddcMask.p, colBits, nUnits, c->ddcCnt.p);
-    CKL("k_ddc_colcount");
-    LAUNCH(k_ddc_colscan, ncol, 1024, 0, st)(nUnits, c->ddcCnt.p, c->ddcColTotal.p);
-    CKL("k_ddc_colscan");
-    CK(cudaMemcpyAsync(c->ddcHost + 8, c->ddcColTotal.p, ncol * sizeof(int), cudaMemcpyDeviceToHost, st));
-    CK(cudaStreamSynchronize(st));
-    c->hSendCount.assign(c->nranks, 0); c->hRecvCount.assign(c->nranks, 0);
-    c->hSendOff.assign(c->nranks, 0); c->hRecvOff.assign(c->nranks, 0);
-    int *colStart = c->ddcHost + 40;
-    int run = 0, col = 0;
-    for (int pp = 0; pp < c->nranks; pp++)
-        if (pp != c->rank) { c->hSendCount[pp] = c->ddcHost[8 + col]; c->hSendOff[pp] = run; colStart[col] = run; run += c->hSendCount[pp]; col++; }
-    c->nSendTot = run;
-    for (int pp = 0; pp < c->nranks; pp++)
-        if (pp != c->rank) { c->hRecvCount[pp] = c->ddcHost[8 + col]; c->hRecvOff[pp] = run - c->nSendTot; colStart[col] = run; run += c->hRecvCount[pp]; col++; }
-    c->nRecvTot = run - c->nSendTot;
-    if (c->nRecvTot != nGhost) return fail(DDCB200_ERR_STATE, "ghost count and receive lists disagree");
-    CK(cudaMemcpyAsync(c->ddcColStart.p, colStart, ncol * sizeof(int), cudaMemcpyHostToDevice, st));
-    CK(c->ddcList.ensure((size_t)run + 1));
-    CK(c->sendSlot.ensure((size_t)c->nSendTot + 1));
-    CK(c->recvSlot.ensure((size_t)c->nRecvTot + 1));
-    CK(c->sendBuf.ensure((size_t)c->nSendTot * 3 + 1));
-    CK(c->recvBuf.ensure((size_t)c->nRecvTot * 3 + 1));
-    LAUNCH(k_ddc_colscatter, nb, 256, 0, st)(nG, c->ddcMask.p, colBits, nUnits, c->ddcCnt.p, c->ddcColStart.p, c->ddcList.p);
-    CKL("k_ddc_colscatter");
+    c->nIon = nIon;
     c->localsDirty = true;
     return DDCB200_OK;
 }
@@ -1892,16 +2002,22 @@ extern "C" int ddcb200_ddcInit(ddcb200_ctx *c, int rank, int nranks, int lx, int
     ncclComm_t comm;
     CKN(ncclCommInitRank(&comm, nranks, u, rank));
     c->nccl = (void *)comm;
-    CK(cudaMalloc((void **)&c->boxEnc, DDC_MAXRANKS * 6 * sizeof(unsigned long long)));
     CK(cudaMalloc((void **)&c->boxes, sizeof(DdcBoxes)));
-    CK(cudaMallocHost((void **)&c->boxInitHost, DDC_MAXRANKS * 6 * sizeof(unsigned long long)));
-    for (int k = 0; k < DDC_MAXRANKS * 6; k++) c->boxInitHost[k] = ((k % 6) < 3) ? ~0ull : 0ull;
+    CK(cudaMalloc((void **)&c->ddcWork, sizeof(DdcWork)));
+    CK(cudaMallocHost((void **)&c->ddcWorkInit, sizeof(DdcWork)));
+    memset(c->ddcWorkInit, 0, sizeof(DdcWork));
+    for (int k = 0; k < 3; k++) ((DdcWork *)c->ddcWorkInit)->boxEnc[k] = ~0ull;     // running minima start at the top
+    CK(cudaMalloc((void **)&c->ddcRow, DDC_ROW * sizeof(int)));
+    CK(cudaMalloc((void **)&c->ddcRowAll, DDC_MAXRANKS * DDC_ROW * sizeof(int)));
+    CK(cudaMallocHost((void **)&c->ddcRowHost, DDC_MAXRANKS * DDC_ROW * sizeof(int)));
+    CK(cudaMalloc((void **)&c->ddcBox6, 6 * sizeof(double)));
+    CK(cudaMalloc((void **)&c->ddcBoxAll, DDC_MAXRANKS * 6 * sizeof(double)));
     c->listValid = false;
     return DDCB200_OK;
 }
 
 // CPU restatement of the domain classification, running the same __host__ __device__ predicates as the kernels
-// (k_ddc_owner, k_ddc_mask).  Used by the world_size-2 tests; not part of the step.
+// (k_rd_dest, k_rd_bbox, k_rd_ghostmask) on a replicated copy of the positions.  Used by the CPU tests; not part of the step.
 extern "C" int ddcb200_ddcPlan(const double h[9], int lx, int ly, int lz, double rlist, int64_t nGlobal, const double *rx, const double *ry,
                                const double *rz, const int *ownerBead, int rank, int *owner, uint32_t *mask)
 {
@@ -1941,7 +2057,7 @@ extern "C" int ddcb200_ddcPlan(const double h[9], int lx, int ly, int lz, double
             for (int pp = 0; pp < g.nranks; pp++)
                 if (pp != rank && ddcNear(rx[b], ry[b], rz[b], pp, g, bx)) m |= 1u << pp;
         }
-        else if (ddcNear(rx[b], ry[b], rz[b], rank, g, bx)) m = 1u << (16 + owner[b]);
+        else if (ddcNear(rx[b], ry[b], rz[b], rank, g, bx)) m = 0x40000000u | (1u << owner[b]);
         mask[b] = m;
     }
     return DDCB200_OK;

@@ -8,15 +8,13 @@
 // (src/energyInfo.c:9-63).
 //
 // B200-first choices (DESIGN.md "Multi-GPU"):
-//   * Every rank holds the static bead tables.  At a re-domain step (every DDC updateRate steps,
-//     together with the list rebuild) the dynamic state is replicated once with one in-place
-//     all-reduce over NVSwitch (each element has exactly one non-zero contributor, so the sum is
-//     exact); ownership, ghost sets and BOTH ends of every send/recv list are then derived
-//     independently - and identically - on every rank from the same replicated data.  There
-//     is no handshake, no count exchange and no particle-migration message.
-//   * Pair rows are full (both directions), so a cross-boundary pair is evaluated by both owners
-//     and ddcUpdateForce's force back-communication has no message at all; per step the only
-//     exchange is ghost positions (24 B per ghost).
+//   * Every rank holds the STATIC bead tables (species, gid, molecule and bonded-term tables); the dynamic state lives only
+//     on the owner (locals) and on the ranks whose bricks it borders (ghost positions).  A re-domain step (every DDC
+//     updateRate steps, together with the list rebuild) moves emigrants and rebuilds the ghost lists with two grouped
+//     ncclSend/ncclRecv exchanges whose sizes come from two small all-gathers; all kernels run over this rank's beads only.
+//   * Pair rows are full (both directions), so a cross-boundary pair is evaluated by both owners and ddcUpdateForce's
+//     force back-communication has no message at all; per step the only exchange is ghost positions (24 B per ghost), on
+//     its own stream, hidden behind the pair work of the rows that touch no ghost.
 //
 // The geometric predicates are __host__ __device__ so the CPU-side planner used by the
 // world_size-2 tests (ddcb200_ddcPlan) runs the very same code as the kernels.
@@ -114,195 +112,247 @@ __device__ __forceinline__ double decOrd(unsigned long long e)
 
 __device__ __forceinline__ bool isGhostW(double w) { return (((unsigned long long)__double_as_longlong(w)) & DDC_GHOST_BIT) != 0ull; }
 
-// 1. every local bead writes its state at its bead index of the (zeroed) replicated arrays
-__global__ void k_ddc_scatter(int nIon, int64_t nGlobal, const double4 *__restrict__ pos, const double *__restrict__ vx,
-                              const double *__restrict__ vy, const double *__restrict__ vz, double *__restrict__ gs)
+// ---- re-domain (every DDC updateRate steps, together with the list rebuild) ---------------------------------------------
+// Two exchanges between the ranks, as ddcAssignment + ddcSendRecvTables (src/ddcAssignment.c:64-107, src/ddcSendRecv.c:41-277):
+//   A. migration: every local bead goes to the brick of its molecule's ownership bead; emigrants travel as records
+//      {bead, r, v[, random state]} straight to their new owner;
+//   B. ghosts: every rank tells the others the bounding box of its new locals, and each owner sends every local bead that is
+//      within the list radius of a peer's box to that peer.  The order of those records IS the order of the per-step halo
+//      messages until the next re-domain, on both sides.
+// Every kernel runs over this rank's beads only; nothing is sized by the global bead count.
+struct DdcWork                    // device scratch of one re-domain (zeroed before each)
+{
+    int sendMig[DDC_MAXRANKS];    // emigrants per destination
+    int sendGhost[DDC_MAXRANKS];  // ghost copies per peer
+    int fillMig[DDC_MAXRANKS], fillGhost[DDC_MAXRANKS];
+    int nStay;
+    int error;                    // bit 0: a molecule is not whole on this rank (its ownership bead is not local)
+    unsigned long long boxEnc[6]; // bounding box of the new locals about the brick centre, order-encoded min[3] max[3]
+};
+struct DdcOffsets
+{
+    int off[DDC_MAXRANKS];
+};
+#define DDC_ROW 32                // ints per rank in the gathered count rows: [0,16) counts, [16] error flags, [17] locals
+
+__device__ __forceinline__ void warpCountByRank(int r, bool on, int nranks, int *counts)
+{
+    const int lane = threadIdx.x & 31;
+    for (int p = 0; p < nranks; p++)
+    {
+        const unsigned m = __ballot_sync(0xffffffffu, on && r == p);
+        if (m && lane == (__ffs(m) - 1)) atomicAdd(&counts[p], __popc(m));
+    }
+}
+
+// A1. destination of every local bead = brick of its molecule's ownership bead (ddcRuleMolecule, src/ddcRuleMolecule.c:43)
+__global__ void __launch_bounds__(256)
+k_rd_dest(int nIon, const double4 *__restrict__ pos, const int *__restrict__ slotOfBead, const int *__restrict__ ownerBead, DdcGeom g,
+          int *__restrict__ dest, DdcWork *__restrict__ work)
+{
+    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    int r = -1;
+    if (s < nIon)
+    {
+        const double4 p = pos[s];
+        const unsigned long long w = (unsigned long long)__double_as_longlong(p.w);
+        if (!(w & DDC_GHOST_BIT))
+        {
+            const int ob = ownerBead[(int)((w >> 32) & 0x7fffffffull)];
+            const int so = slotOfBead[ob];
+            if (so < 0 || isGhostW(pos[so].w))
+            {
+                atomicOr(&work->error, 1);
+                r = g.me;
+            }
+            else
+            {
+                const double4 po = pos[so];
+                r = ddcBrickOf(po.x, po.y, po.z, g);
+            }
+        }
+        dest[s] = r;
+    }
+    warpCountByRank(r, r >= 0 && r != g.me, g.nranks, work->sendMig);
+}
+
+// A4. emigrant records: {bead, x, y, z, vx, vy, vz[, random state]}; the order inside a message is arbitrary (the cell sort
+// that follows orders the slots by (cell, sub-cell, bead) whatever the order here)
+__global__ void k_rd_pack(int nIon, const double4 *__restrict__ pos, const double *__restrict__ vx, const double *__restrict__ vy,
+                          const double *__restrict__ vz, const int *__restrict__ dest, int me, DdcWork *__restrict__ work, DdcOffsets off,
+                          int rec, const uint64_t *__restrict__ rngState, double *__restrict__ buf)
 {
     const int s = blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= nIon) return;
+    const int d = dest[s];
+    if (d < 0 || d == me) return;
+    const int k = off.off[d] + atomicAdd(&work->fillMig[d], 1);
     const double4 p = pos[s];
     const unsigned long long w = (unsigned long long)__double_as_longlong(p.w);
-    if (w & DDC_GHOST_BIT) return;
-    const size_t b = (size_t)((w >> 32) & 0x7fffffffull);
-    gs[b] = p.x;
-    gs[(size_t)nGlobal + b] = p.y;
-    gs[2 * (size_t)nGlobal + b] = p.z;
-    gs[3 * (size_t)nGlobal + b] = vx[s];
-    gs[4 * (size_t)nGlobal + b] = vy[s];
-    gs[5 * (size_t)nGlobal + b] = vz[s];
+    const int bead = (int)((w >> 32) & 0x7fffffffull);
+    double *o = buf + (size_t)k * rec;
+    o[0] = (double)bead;
+    o[1] = p.x; o[2] = p.y; o[3] = p.z;
+    o[4] = vx[s]; o[5] = vy[s]; o[6] = vz[s];
+    if (rec > 7) o[7] = __longlong_as_double((long long)rngState[bead]);
 }
 
-// 2. owner of every bead = brick of its molecule's ownership bead; bounding box of every rank's beads
-//    (encoded min/max; boxEnc[r*6 + a] = min, boxEnc[r*6 + 3 + a] = max)
-__global__ void __launch_bounds__(256)
-k_ddc_owner(int64_t nGlobal, const double *__restrict__ gs, const int *__restrict__ ownerBead, DdcGeom g, int *__restrict__ owner,
-            unsigned long long *__restrict__ boxEnc)
+__global__ void k_rd_clear(int nIon, const int *__restrict__ beadOfSlot, int *__restrict__ slotOfBead)
 {
-    __shared__ unsigned long long sEnc[DDC_MAXRANKS * 6];
-    for (int k = threadIdx.x; k < g.nranks * 6; k += blockDim.x) sEnc[k] = ((k % 6) < 3) ? ~0ull : 0ull;
+    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s < nIon) slotOfBead[beadOfSlot[s]] = -1;
+}
+
+// A6. the beads that stay, compacted into the other buffer set
+__global__ void __launch_bounds__(256)
+k_rd_compact(int nIon, const double4 *__restrict__ pos, const double *__restrict__ vx, const double *__restrict__ vy,
+             const double *__restrict__ vz, const int *__restrict__ bead, const int *__restrict__ dest, int me, DdcWork *__restrict__ work,
+             double4 *__restrict__ posN, double *__restrict__ vxN, double *__restrict__ vyN, double *__restrict__ vzN,
+             int *__restrict__ beadN, int *__restrict__ slotOfBead)
+{
+    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    const bool stay = s < nIon && dest[s] == me;
+    const unsigned m = __ballot_sync(0xffffffffu, stay);
+    const int lane = threadIdx.x & 31;
+    int base = 0;
+    if (m && lane == (__ffs(m) - 1)) base = atomicAdd(&work->nStay, __popc(m));
+    base = __shfl_sync(0xffffffffu, base, m ? __ffs(m) - 1 : 0);
+    if (!stay) return;
+    const int k = base + __popc(m & ((1u << lane) - 1u));
+    posN[k] = pos[s];
+    vxN[k] = vx[s]; vyN[k] = vy[s]; vzN[k] = vz[s];
+    const int b = bead[s];
+    beadN[k] = b;
+    slotOfBead[b] = k;
+}
+
+__global__ void k_rd_unpack(int n, const double *__restrict__ buf, int rec, int base, const uint64_t *__restrict__ wOfBead,
+                            double4 *__restrict__ pos, double *__restrict__ vx, double *__restrict__ vy, double *__restrict__ vz,
+                            int *__restrict__ beadOfSlot, int *__restrict__ slotOfBead, uint64_t *__restrict__ rngState)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const double *o = buf + (size_t)i * rec;
+    const int b = (int)o[0];
+    const int k = base + i;
+    pos[k] = make_double4(o[1], o[2], o[3], __longlong_as_double((long long)wOfBead[b]));
+    vx[k] = o[4]; vy[k] = o[5]; vz[k] = o[6];
+    beadOfSlot[k] = b;
+    slotOfBead[b] = k;
+    if (rec > 7) rngState[b] = (uint64_t)__double_as_longlong(o[7]);
+}
+
+// B1. bounding box of my new locals about my brick centre (nearest image), for the peers' ghost test
+__global__ void __launch_bounds__(256)
+k_rd_bbox(int n, const double4 *__restrict__ pos, DdcGeom g, DdcWork *__restrict__ work)
+{
+    __shared__ unsigned long long sEnc[6];
+    if (threadIdx.x < 6) sEnc[threadIdx.x] = threadIdx.x < 3 ? ~0ull : 0ull;
     __syncthreads();
-    const int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (b < nGlobal)
+    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s < n)
     {
-        const int ob = ownerBead[b];
-        const int r = ddcBrickOf(gs[ob], gs[(size_t)nGlobal + ob], gs[2 * (size_t)nGlobal + ob], g);
-        owner[b] = r;
         double c[3];
-        ddcBrickCentre(r, g, c);
+        ddcBrickCentre(g.me, g, c);
+        const double4 p = pos[s];
+        const double q[3] = {p.x, p.y, p.z};
         for (int a = 0; a < 3; a++)
         {
-            const double d = ddcMinImg(gs[(size_t)a * nGlobal + b] - c[a], g.L[a], g.hL[a]);
-            const unsigned long long e = encOrd(d);
-            atomicMin(&sEnc[r * 6 + a], e);
-            atomicMax(&sEnc[r * 6 + 3 + a], e);
+            const unsigned long long e = encOrd(ddcMinImg(q[a] - c[a], g.L[a], g.hL[a]));
+            atomicMin(&sEnc[a], e);
+            atomicMax(&sEnc[3 + a], e);
         }
     }
     __syncthreads();
-    for (int k = threadIdx.x; k < g.nranks * 6; k += blockDim.x)
+    if (threadIdx.x < 3) atomicMin(&work->boxEnc[threadIdx.x], sEnc[threadIdx.x]);
+    else if (threadIdx.x < 6) atomicMax(&work->boxEnc[threadIdx.x], sEnc[threadIdx.x]);
+}
+
+// counts (and the box) of this rank as one row for the all-gather
+__global__ void k_rd_row(const DdcWork *__restrict__ work, int phase, int nLocal, int *__restrict__ row, double *__restrict__ box6)
+{
+    const int k = threadIdx.x;
+    if (k < DDC_MAXRANKS) row[k] = phase == 0 ? work->sendMig[k] : work->sendGhost[k];
+    if (k == 16) row[16] = work->error;
+    if (k == 17) row[17] = nLocal;
+    if (k > 17 && k < DDC_ROW) row[k] = 0;
+    if (box6 && k < 6)
     {
-        if ((k % 6) < 3) { if (sEnc[k] != ~0ull) atomicMin(&boxEnc[k], sEnc[k]); }
-        else { if (sEnc[k] != 0ull) atomicMax(&boxEnc[k], sEnc[k]); }
+        const unsigned long long e = work->boxEnc[k];
+        box6[k] = k < 3 ? ((e == ~0ull) ? 1e300 : decOrd(e)) : ((e == 0ull) ? -1e300 : decOrd(e));   // empty rank: nothing is near it
     }
 }
 
-__global__ void k_ddc_boxes(int nranks, const unsigned long long *__restrict__ boxEnc, DdcBoxes *__restrict__ bx)
+__global__ void k_rd_boxes(int nranks, const double *__restrict__ all6, DdcBoxes *__restrict__ bx)
 {
     const int k = threadIdx.x;
     if (k >= nranks * 6) return;
     const int r = k / 6, a = k % 6;
-    const unsigned long long e = boxEnc[k];
-    if (a < 3) bx->lo[r][a] = (e == ~0ull) ? 1e300 : decOrd(e);      // empty rank: nothing is near it
-    else bx->hi[r][a - 3] = (e == 0ull) ? -1e300 : decOrd(e);
+    if (a < 3) bx->lo[r][a] = all6[k];
+    else bx->hi[r][a - 3] = all6[k];
 }
 
-// 3. classify every bead for this rank: bit p (p != me) = mine and needed by rank p as a ghost;
-//    bit 16+p = owned by p and needed here as a ghost; bit 31 = mine.  Counts locals / ghosts.
+// B2. which peers need which of my locals as ghosts (domain_possibleRemote, src/domain.c:101-124, against the peers' boxes)
 __global__ void __launch_bounds__(256)
-k_ddc_mask(int64_t nGlobal, const double *__restrict__ gs, const int *__restrict__ owner, DdcGeom g, const DdcBoxes *__restrict__ bxp,
-           uint32_t *__restrict__ mask, int *__restrict__ counters)
+k_rd_ghostmask(int nLocal, const double4 *__restrict__ pos, DdcGeom g, const DdcBoxes *__restrict__ bxp, uint32_t *__restrict__ mask,
+               DdcWork *__restrict__ work)
 {
     __shared__ DdcBoxes bx;
     for (int k = threadIdx.x; k < (int)(sizeof(DdcBoxes) / sizeof(double)); k += blockDim.x) ((double *)&bx)[k] = ((const double *)bxp)[k];
     __syncthreads();
-    const int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int s = blockIdx.x * blockDim.x + threadIdx.x;
     uint32_t m = 0u;
-    if (b < nGlobal)
+    if (s < nLocal)
     {
-        const int o = owner[b];
-        const double x = gs[b], y = gs[(size_t)nGlobal + b], z = gs[2 * (size_t)nGlobal + b];
-        if (o == g.me)
-        {
-            m = 0x80000000u;
-            for (int p = 0; p < g.nranks; p++)
-                if (p != g.me && ddcNear(x, y, z, p, g, bx)) m |= 1u << p;
-        }
-        else if (ddcNear(x, y, z, g.me, g, bx)) m = 1u << (16 + o);
-        mask[b] = m;
+        const double4 p = pos[s];
+        for (int q = 0; q < g.nranks; q++)
+            if (q != g.me && ddcNear(p.x, p.y, p.z, q, g, bx)) m |= 1u << q;
+        mask[s] = m;
     }
-    const unsigned nl = __popc(__ballot_sync(0xffffffffu, (m & 0x80000000u) != 0u));
-    const unsigned ng = __popc(__ballot_sync(0xffffffffu, (m & 0xffff0000u) != 0u && !(m & 0x80000000u)));
-    if ((threadIdx.x & 31) == 0)
-    {
-        if (nl) atomicAdd(&counters[0], (int)nl);
-        if (ng) atomicAdd(&counters[1], (int)ng);
-    }
-}
-
-// 4. rebuild the slot arrays from the replicated state: locals and ghosts in arbitrary order (the
-//    cell sort that follows orders slots by (cell, sub-cell, bead) whatever the order here)
-__global__ void k_ddc_select(int64_t nGlobal, const double *__restrict__ gs, const uint32_t *__restrict__ mask,
-                             const uint64_t *__restrict__ wOfBead, int *__restrict__ counter, double4 *__restrict__ pos,
-                             double *__restrict__ vx, double *__restrict__ vy, double *__restrict__ vz, int *__restrict__ beadOfSlot,
-                             int *__restrict__ slotOfBead)
-{
-    const int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (b >= nGlobal) return;
-    const uint32_t m = mask[b];
-    if (m == 0u) return;
-    const bool local = (m & 0x80000000u) != 0u;
-    const int s = atomicAdd(counter, 1);
-    unsigned long long w = wOfBead[b];
-    if (!local) w |= DDC_GHOST_BIT;
-    pos[s] = make_double4(gs[b], gs[(size_t)nGlobal + b], gs[2 * (size_t)nGlobal + b], __longlong_as_double((long long)w));
-    vx[s] = local ? gs[3 * (size_t)nGlobal + b] : 0.0;
-    vy[s] = local ? gs[4 * (size_t)nGlobal + b] : 0.0;
-    vz[s] = local ? gs[5 * (size_t)nGlobal + b] : 0.0;
-    beadOfSlot[s] = (int)b;
-    slotOfBead[b] = s;
-}
-
-// 5. ordered multi-column compaction of the mask bits into bead lists (ascending bead index), so
-//    sender and receiver build the same list in the same order without talking to each other.
-//    unit = one warp = 32 consecutive beads; cnt[col][unit].
-__global__ void __launch_bounds__(256)
-k_ddc_colcount(int64_t nGlobal, const uint32_t *__restrict__ mask, uint32_t colBits, int nUnits, int *__restrict__ cnt)
-{
-    const int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    const uint32_t m = (b < nGlobal) ? mask[b] : 0u;
-    const int unit = (int)(b >> 5);
-    if (unit >= nUnits) return;
     const int lane = threadIdx.x & 31;
-    uint32_t bits = colBits;
-    int col = 0;
-    while (bits)
+    for (int q = 0; q < g.nranks; q++)
     {
-        const int bit = __ffs(bits) - 1;
-        bits &= bits - 1;
-        const unsigned v = __ballot_sync(0xffffffffu, (m >> bit) & 1u);
-        if (lane == 0) cnt[(size_t)col * nUnits + unit] = __popc(v);
-        col++;
+        const unsigned v = __ballot_sync(0xffffffffu, (m >> q) & 1u);
+        if (v && lane == (__ffs(v) - 1)) atomicAdd(&work->sendGhost[q], __popc(v));
     }
 }
 
-// one CTA per column: exclusive scan over the units (in place), total to colTotal[col]
-__global__ void __launch_bounds__(1024)
-k_ddc_colscan(int nUnits, int *__restrict__ cnt, int *__restrict__ colTotal)
+// B4. ghost records {bead, x, y, z} and the send list (bead ids) in the same order
+__global__ void k_rd_ghostpack(int nLocal, const double4 *__restrict__ pos, const uint32_t *__restrict__ mask, int nranks,
+                               DdcWork *__restrict__ work, DdcOffsets off, int *__restrict__ sendBead, double *__restrict__ buf)
 {
-    __shared__ int sums[1024];
-    int *c = cnt + (size_t)blockIdx.x * nUnits;
-    const int per = (nUnits + blockDim.x - 1) / blockDim.x;
-    const int lo = min(nUnits, (int)threadIdx.x * per), hi = min(nUnits, lo + per);
-    int s = 0;
-    for (int i = lo; i < hi; i++) s += c[i];
-    sums[threadIdx.x] = s;
-    __syncthreads();
-    for (int o = 1; o < blockDim.x; o <<= 1)
+    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= nLocal) return;
+    uint32_t m = mask[s];
+    if (!m) return;
+    const double4 p = pos[s];
+    const int bead = (int)((((unsigned long long)__double_as_longlong(p.w)) >> 32) & 0x7fffffffull);
+    while (m)
     {
-        int v = (threadIdx.x >= o) ? sums[threadIdx.x - o] : 0;
-        __syncthreads();
-        sums[threadIdx.x] += v;
-        __syncthreads();
+        const int q = __ffs(m) - 1;
+        m &= m - 1;
+        const int k = off.off[q] + atomicAdd(&work->fillGhost[q], 1);
+        sendBead[k] = bead;
+        double *o = buf + 4 * (size_t)k;
+        o[0] = (double)bead;
+        o[1] = p.x; o[2] = p.y; o[3] = p.z;
     }
-    int run = sums[threadIdx.x] - s;
-    for (int i = lo; i < hi; i++)
-    {
-        const int v = c[i];
-        c[i] = run;
-        run += v;
-    }
-    if (threadIdx.x == blockDim.x - 1) colTotal[blockIdx.x] = sums[threadIdx.x];
 }
 
-__global__ void __launch_bounds__(256)
-k_ddc_colscatter(int64_t nGlobal, const uint32_t *__restrict__ mask, uint32_t colBits, int nUnits, const int *__restrict__ off,
-                 const int *__restrict__ colStart, int *__restrict__ list)
+__global__ void k_rd_ghostunpack(int n, const double *__restrict__ buf, int base, const uint64_t *__restrict__ wOfBead,
+                                 double4 *__restrict__ pos, double *__restrict__ vx, double *__restrict__ vy, double *__restrict__ vz,
+                                 int *__restrict__ beadOfSlot, int *__restrict__ slotOfBead, int *__restrict__ recvBead)
 {
-    const int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    const uint32_t m = (b < nGlobal) ? mask[b] : 0u;
-    const int unit = (int)(b >> 5);
-    if (unit >= nUnits) return;
-    const unsigned lt = (1u << (threadIdx.x & 31)) - 1u;
-    uint32_t bits = colBits;
-    int col = 0;
-    while (bits)
-    {
-        const int bit = __ffs(bits) - 1;
-        bits &= bits - 1;
-        const bool on = (m >> bit) & 1u;
-        const unsigned v = __ballot_sync(0xffffffffu, on);
-        if (on) list[colStart[col] + off[(size_t)col * nUnits + unit] + __popc(v & lt)] = (int)b;
-        col++;
-    }
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const double *o = buf + 4 * (size_t)i;
+    const int b = (int)o[0];
+    const int k = base + i;
+    pos[k] = make_double4(o[1], o[2], o[3], __longlong_as_double((long long)(wOfBead[b] | DDC_GHOST_BIT)));
+    vx[k] = 0.0; vy[k] = 0.0; vz[k] = 0.0;      // velocities only exist for local beads
+    beadOfSlot[k] = b;
+    slotOfBead[b] = k;
+    recvBead[i] = b;
 }
 
 __global__ void k_ddc_toslots(int n, const int *__restrict__ beads, const int *__restrict__ slotOfBead, int *__restrict__ slots)

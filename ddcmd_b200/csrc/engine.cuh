@@ -105,6 +105,31 @@ struct DevBuf
         if (e == cudaSuccess) cap = want;
         return e;
     }
+    // like ensure(), but what the buffer holds survives the reallocation
+    cudaError_t grow(size_t n, cudaStream_t st)
+    {
+        if (n <= cap) return cudaSuccess;
+        const size_t want = n + n / 8 + 256;
+        T *q = nullptr;
+        cudaError_t e = cudaMalloc((void **)&q, want * sizeof(T));
+        if (e != cudaSuccess) return e;
+        if (p)
+        {
+            e = cudaMemcpyAsync(q, p, cap * sizeof(T), cudaMemcpyDeviceToDevice, st);
+            if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+            cudaFree(p);
+            if (e != cudaSuccess)
+            {
+                cudaFree(q);
+                p = nullptr;
+                cap = 0;
+                return e;
+            }
+        }
+        p = q;
+        cap = want;
+        return cudaSuccess;
+    }
     void release()
     {
         if (p) cudaFree(p);
@@ -237,16 +262,18 @@ struct ddcb200_ctx
     std::vector<int> hMolBeads;
     DevBuf<int> ownerBead;            // static: bead index of the ownership bead of each bead's molecule
     bool ownerBeadValid = false;
-    DevBuf<double> gState;            // replicated x y z vx vy vz by bead index (re-domain steps only)
-    DevBuf<int> ownerOfBead;
-    DevBuf<uint32_t> ddcMask;
-    DevBuf<int> ddcCnt, ddcColTotal, ddcColStart, ddcList, sendSlot, recvSlot;
+    DevBuf<int> ddcDest;              // re-domain: destination rank of every slot (-1: ghost)
+    DevBuf<uint32_t> ddcMask;         // re-domain: bit p = this local bead is a ghost of rank p
+    DevBuf<int> ddcList, sendSlot, recvSlot;   // ddcList = bead ids [send lists by peer | recv lists by peer]
     DevBuf<double> sendBuf, recvBuf;
-    unsigned long long *boxEnc = nullptr;   // device, DDC_MAXRANKS*6
+    void *ddcWork = nullptr;                // device DdcWork
+    void *ddcWorkInit = nullptr;            // pinned DdcWork: the cleared pattern
+    int *ddcRow = nullptr, *ddcRowAll = nullptr;   // device: this rank's count row, and every rank's (all-gather)
+    int *ddcRowHost = nullptr;              // pinned copy of ddcRowAll
+    double *ddcBox6 = nullptr, *ddcBoxAll = nullptr;   // device: my bounding box, every rank's
     void *boxes = nullptr;                  // device DdcBoxes
     int *ddcCounters = nullptr;             // device, 8 ints
     int *ddcHost = nullptr;                 // pinned, 64 ints
-    unsigned long long *boxInitHost = nullptr;   // pinned init pattern for boxEnc
     std::vector<int> hSendCount, hRecvCount, hSendOff, hRecvOff;
     int nSendTot = 0, nRecvTot = 0;
     bool haloDirty = false, localsDirty = false;

@@ -1564,22 +1564,37 @@ int ddcb200_simulateBindRank(const ddcb200_deck *d, int device, int rank, int nr
         TRY(ddcb200_setConstraints(c, d->nCons, d->consAtomOffset, d->consAtomBead, d->consPairOffset, d->consPairA, d->consPairB, d->consPairDist));
         TRY(ddcb200_nglfconstraintParms(c, d->kB * d->ncT, d->ncP0, d->ncBeta, d->ncTauBarostat));
     }
-    int64_t lo = 0, hi = d->n;
     if (nranks > 1)
     {
         if (!ncclId) { herr("multi-rank bind needs the NCCL unique id"); ddcb200_destroy(c); return -1; }
         TRY(ddcb200_ddcInit(c, rank, nranks, lx, ly, lz, ncclId));
-        lo = d->n * rank / nranks;
-        hi = d->n * (rank + 1) / nranks;
+        /* the start-up partition only has to keep molecules whole (ddcRuleMolecule): every bead goes with its molecule's
+         * ownership bead, and those are dealt out in equal index ranges; the first re-domain moves everything to its brick */
+        int *ob = (int *)malloc(sizeof(int) * (size_t)(d->n + 1));
+        for (int64_t i = 0; i < d->n; i++) ob[i] = (int)i;
+        for (int64_t m = 0; m < d->nMol; m++)
+            for (int64_t k = d->molOffset[m]; k < d->molOffset[m + 1]; k++) ob[d->molBeads[k]] = d->molBeads[d->molOffset[m]];
+        int64_t cnt = 0;
+        for (int64_t i = 0; i < d->n; i++) cnt += ((int64_t)ob[i] * nranks / d->n == rank);
+        int *bead = (int *)malloc(sizeof(int) * (size_t)(cnt + 1));
+        double *st = (double *)malloc(sizeof(double) * 6 * (size_t)(cnt + 1));
+        int64_t k = 0;
+        for (int64_t i = 0; i < d->n; i++)
+            if ((int64_t)ob[i] * nranks / d->n == rank)
+            {
+                bead[k] = (int)i;
+                st[k] = d->rx[i]; st[cnt + k] = d->ry[i]; st[2 * cnt + k] = d->rz[i];
+                st[3 * cnt + k] = d->vx[i]; st[4 * cnt + k] = d->vy[i]; st[5 * cnt + k] = d->vz[i];
+                k++;
+            }
+        free(ob);
+        rc = cnt > 0 ? ddcb200_sendState(c, cnt, bead, st, st + cnt, st + 2 * cnt, st + 3 * cnt, st + 4 * cnt, st + 5 * cnt, d->loop, d->time) : -1;
+        free(bead);
+        free(st);
+        if (cnt <= 0) { herr("rank %d of %d gets no beads at start-up", rank, nranks); ddcb200_destroy(c); return -1; }
     }
-    int *bead = NULL;
-    if (nranks > 1)
-    {
-        bead = (int *)malloc(sizeof(int) * (size_t)(hi - lo + 1));
-        for (int64_t i = lo; i < hi; i++) bead[i - lo] = (int)i;
-    }
-    rc = ddcb200_sendState(c, hi - lo, bead, d->rx + lo, d->ry + lo, d->rz + lo, d->vx + lo, d->vy + lo, d->vz + lo, d->loop, d->time);
-    free(bead);
+    else
+        rc = ddcb200_sendState(c, d->n, NULL, d->rx, d->ry, d->rz, d->vx, d->vy, d->vz, d->loop, d->time);
     if (rc) { herr("ddcb200_sendState: %s", ddcb200_lastError()); ddcb200_destroy(c); return rc; }
 #undef TRY
     *out = c;

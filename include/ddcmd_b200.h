@@ -255,8 +255,8 @@ int ddcb200_ncclUniqueId(unsigned char id[128]);
 int ddcb200_ddcInit(ddcb200_ctx *ctx, int rank, int nranks, int lx, int ly, int lz, const unsigned char id[128]);
 
 /* Host restatement of the domain classification (same predicates as the kernels), for tests and tools:
- * owner[b] = rank owning bead b; mask[b] for `rank`: bit 31 = mine, bit p = mine and a ghost on rank p,
- * bit 16+p = owned by p and a ghost here.  ownerBead[b] = ownership bead of b's molecule (NULL = b). */
+ * owner[b] = rank owning bead b; mask[b] for `rank`: bit 31 = mine, and then bit p (p < 16) = a ghost on rank p;
+ * bit 30 = owned elsewhere and a ghost here, and then bit p = its owner.  ownerBead[b] = ownership bead of b's molecule (NULL = b). */
 int ddcb200_ddcPlan(const double h[9], int lx, int ly, int lz, double rlist, int64_t nGlobal, const double *rx, const double *ry,
                     const double *rz, const int *ownerBead, int rank, int *owner, uint32_t *mask);
 

@@ -1,7 +1,7 @@
 // nccl.h (CPU EMULATION SHIM) - TEST INFRASTRUCTURE ONLY.
 // The handful of NCCL calls the product makes, emulated between PROCESSES of one host through a POSIX shared-memory
 // segment: all-reduce (sum of doubles, summed in rank order) and grouped send/recv.  Every call is collective over
-// the communicator and synchronous, which is how the product uses them (one group per halo exchange, every rank in it).
+// the communicator and synchronous, which is how the product uses them (one group per exchange, every rank in it).
 #pragma once
 #include <fcntl.h>
 #include <sched.h>
@@ -26,7 +26,8 @@ typedef struct emuNcclComm
 typedef struct { char internal[128]; } ncclUniqueId;
 typedef int ncclResult_t;
 enum { ncclSuccess = 0, ncclSystemError = 2, ncclInvalidUsage = 5 };
-enum ncclDataType_t { ncclDouble = 8 };
+enum ncclDataType_t { ncclInt8 = 0, ncclInt32 = 2, ncclDouble = 8 };
+static inline size_t ncclTypeSize(ncclDataType_t t) { return t == ncclDouble ? 8 : (t == ncclInt32 ? 4 : 1); }
 enum ncclRedOp_t { ncclSum = 0, ncclMax = 2 };
 
 namespace emu
@@ -107,19 +108,30 @@ static inline ncclResult_t ncclAllReduce(const void *src, void *dst, size_t coun
     emu::ncclBarrier(c);
     return ncclSuccess;
 }
-static inline ncclResult_t ncclGroupStart() { emu::ncclGroupDepth()++; return ncclSuccess; }
-static inline ncclResult_t ncclSend(const void *src, size_t count, ncclDataType_t, int peer, ncclComm_t c, cudaStream_t)
+// every rank's `count` elements, in rank order, to every rank
+static inline ncclResult_t ncclAllGather(const void *src, void *dst, size_t count, ncclDataType_t t, ncclComm_t c, cudaStream_t)
 {
-    if (!emu::ncclGroupDepth()) return ncclInvalidUsage;
-    emu::ncclGroupComm() = c;
-    emu::ncclQueue().push_back({1, src, nullptr, count * 8, peer});
+    const size_t bytes = count * ncclTypeSize(t);
+    if (bytes > c->slot) return ncclInvalidUsage;
+    memcpy(emu::ncclSlot(c, c->rank), src, bytes);
+    emu::ncclBarrier(c);
+    for (int r = 0; r < c->nranks; r++) memcpy((char *)dst + (size_t)r * bytes, emu::ncclSlot(c, r), bytes);
+    emu::ncclBarrier(c);
     return ncclSuccess;
 }
-static inline ncclResult_t ncclRecv(void *dst, size_t count, ncclDataType_t, int peer, ncclComm_t c, cudaStream_t)
+static inline ncclResult_t ncclGroupStart() { emu::ncclGroupDepth()++; return ncclSuccess; }
+static inline ncclResult_t ncclSend(const void *src, size_t count, ncclDataType_t t, int peer, ncclComm_t c, cudaStream_t)
 {
     if (!emu::ncclGroupDepth()) return ncclInvalidUsage;
     emu::ncclGroupComm() = c;
-    emu::ncclQueue().push_back({0, nullptr, dst, count * 8, peer});
+    emu::ncclQueue().push_back({1, src, nullptr, count * ncclTypeSize(t), peer});
+    return ncclSuccess;
+}
+static inline ncclResult_t ncclRecv(void *dst, size_t count, ncclDataType_t t, int peer, ncclComm_t c, cudaStream_t)
+{
+    if (!emu::ncclGroupDepth()) return ncclInvalidUsage;
+    emu::ncclGroupComm() = c;
+    emu::ncclQueue().push_back({0, nullptr, dst, count * ncclTypeSize(t), peer});
     return ncclSuccess;
 }
 // The product issues exactly one group per halo exchange and every rank takes part (possibly with no messages), so

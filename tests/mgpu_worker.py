@@ -18,7 +18,7 @@ if os.environ.get("DDCB200_TEST_EMU") == "1":
     import ctypes
     sys.path.insert(0, os.path.join(ROOT, "tests", "cpu_emu"))
     import build_emu
-    dd._lib = dd._declare(ctypes.CDLL(build_emu.build()))
+    dd._lib = dd._declare(ctypes.CDLL(os.environ.get("DDCB200_EMU_LIB") or build_emu.build()))     # DDCB200_EMU_LIB: e.g. an ASan build
 
 
 def gather_by_bead(sim, n, keys):
@@ -79,7 +79,17 @@ def main():
         p0 = ref["pairs0"].reshape(-1, 2); p1 = ref["pairs1"].reshape(-1, 2)
         assert np.array_equal(np.sort(pairkey(abi[apr == 0], abj[apr == 0])), np.sort(pairkey(p0[:, 0], p0[:, 1])))
         assert np.array_equal(np.sort(pairkey(abi[apr == 1], abj[apr == 1])), np.sort(pairkey(p1[:, 0], p1[:, 1])))
-        print("step0 ok: locals per rank %s, force err %.2e, eion %.12g" % (nloc, ferr, e.eion), flush=True)
+        # molecular virial / pressure: every molecule is summed once, on its owner (ghost copies elsewhere contribute nothing);
+        # checked against a single-rank context of the same deck on this rank's device
+        one = dd.simulate_init(os.path.join(g, "object.data"), device=local)
+        one.ddcenergy(1)
+        e1 = one.energyInfo()
+        one.close()
+        mv, mv1 = np.array(e.molVirial[:]), np.array(e1.molVirial[:])
+        assert np.allclose(mv, mv1, rtol=1e-9, atol=1e-9 * np.abs(mv1).max()), (mv, mv1)
+        assert abs(e.pMolecular - e1.pMolecular) <= 1e-9 * max(abs(e1.pMolecular), abs(e1.pion)), (e.pMolecular, e1.pMolecular)
+        assert e.nMolecules == e1.nMolecules
+        print("step0 ok: locals per rank %s, force err %.2e, eion %.12g, pMolecular %.12g" % (nloc, ferr, e.eion, e.pMolecular), flush=True)
 
     # ---- 40 steps: halo every step, re-domain + migration at steps 20 and 40 ----
     tr = ref["trace"].reshape(-1, 16)

@@ -142,6 +142,14 @@ def test_emu_two_ranks_match_reference(emu_handle, name):
     assert r.returncode == 0 and "MGPU_OK" in r.stdout, r.stdout[-2000:] + r.stderr[-4000:]
 
 
+@pytest.mark.parametrize("nproc,name,lattice", [(4, "ras_small", (4, 1, 1)), (8, "popc_small", (4, 2, 1))])
+def test_emu_four_and_eight_ranks_match_reference(emu_handle, nproc, name, lattice):
+    """The same worker on 4 and 8 emulated ranks: emigrants to non-adjacent bricks, rank pairs that exchange nothing (4x2x1 is
+    the lattice of the 8-GPU scaling run), molecules with bonded terms and restraints crossing brick faces."""
+    r = _torchrun(nproc, 29564 + nproc, "mgpu_worker.py", name, *[str(x) for x in lattice], env={"DDCB200_TEST_EMU": "1"})
+    assert r.returncode == 0 and "MGPU_OK" in r.stdout, r.stdout[-2000:] + r.stderr[-4000:]
+
+
 def test_emu_bench_contract_two_ranks(emu_handle):
     """bench.py's multi-rank arm end to end (rank plumbing, max-over-ranks timing, one JSON line from rank 0)."""
     import json

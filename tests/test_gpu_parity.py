@@ -144,15 +144,30 @@ def test_printinfo_line_matches_reference_data_file(golden_dir):
     assert abs(float(line[7]) - 133.942256177663) < 1e-9         # volume per bead
 
 
-@pytest.mark.parametrize("name", ["popc_small", "ras_small", "waterbox", "tiny2"])
-def test_two_gpus_match_reference(name):
-    """ddc decomposition over 2 GPUs (NCCL halo, re-domain every 20 steps) against the single-rank reference."""
+def _mgpu(nproc, port, name, lattice=()):
     import subprocess
     import sys
-    if dd.lib().ddcb200_deviceCount() < 2:
-        pytest.skip("needs 2 GPUs")
+    if dd.lib().ddcb200_deviceCount() < nproc:
+        pytest.skip("needs %d GPUs" % nproc)
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
-           "--master-port", "29533", os.path.join(root, "tests", "mgpu_worker.py"), name]
-    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=%d" % nproc, "--master-addr", "127.0.0.1",
+           "--master-port", str(port), os.path.join(root, "tests", "mgpu_worker.py"), name] + [str(x) for x in lattice]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=900)
     assert r.returncode == 0 and "MGPU_OK" in r.stdout, r.stdout[-3000:] + r.stderr[-6000:]
+
+
+@pytest.mark.parametrize("name", ["popc_small", "ras_small", "waterbox", "tiny2"])
+def test_two_gpus_match_reference(name):
+    """ddc decomposition over 2 GPUs (migration + ghost exchange every 20 steps, NCCL halo per step) against the single-rank reference."""
+    _mgpu(2, 29533, name)
+
+
+@pytest.mark.parametrize("name,lattice", [("popc_small", (2, 2, 1)), ("ras_small", (4, 1, 1))])
+def test_four_gpus_match_reference(name, lattice):
+    _mgpu(4, 29534, name, lattice)
+
+
+@pytest.mark.parametrize("name,lattice", [("popc_small", (4, 2, 1)), ("ras_small", (2, 2, 2))])
+def test_eight_gpus_match_reference(name, lattice):
+    """4x2x1: the lattice of the 1M-bead scaling run (some rank pairs exchange nothing); 2x2x2: bricks in every direction."""
+    _mgpu(8, 29535, name, lattice)
