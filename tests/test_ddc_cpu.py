@@ -56,7 +56,7 @@ def test_plan_invariants(golden_dir, lattice):
         for p in range(nranks):
             if p == r:
                 continue
-            send = np.nonzero((plans[r][1] >> p) & 1)[0]
+            send = np.nonzero(((plans[r][1] >> 31) & 1) & ((plans[r][1] >> p) & 1))[0]
             recv = np.nonzero(((plans[p][1] >> 30) & 1) & ((plans[p][1] >> r) & 1))[0]
             assert np.array_equal(send, recv)
     # completeness: every pair within the list range has, on the owner of either bead, the partner present
@@ -97,7 +97,7 @@ lattice = dd.default_lattice(world, [h[0], h[4], h[8]])
 owner, mask = dd.ddc_plan(h, lattice, rlist, rx, ry, rz, rank, ob)
 # halo exchange over gloo using only locally derived lists: positions of my beads that the peer holds as ghosts
 peer = 1 - rank
-send = np.nonzero((mask >> peer) & 1)[0]
+send = np.nonzero(((mask >> 31) & 1) & ((mask >> peer) & 1))[0]
 recv = np.nonzero(((mask >> 30) & 1) & ((mask >> peer) & 1))[0]
 # counts are NOT exchanged: the receive buffer is sized from the local plan alone
 out = torch.from_numpy(np.stack([rx[send], ry[send], rz[send]], 1).copy())
