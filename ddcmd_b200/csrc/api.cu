@@ -68,7 +68,8 @@ struct ProfScope
     ddcb200_ctx *c;
     int slot;
     cudaEvent_t a = nullptr, b = nullptr;
-    ProfScope(ddcb200_ctx *ctx, int s) : c(ctx), slot(s)
+    cudaStream_t st;
+    ProfScope(ddcb200_ctx *ctx, int s, cudaStream_t stream = nullptr) : c(ctx), slot(s), st(stream ? stream : ctx->stream)
     {
         c->profLaunch[slot]++;
         if (!c->prof) return;
@@ -85,12 +86,12 @@ struct ProfScope
         };
         a = get();
         b = get();
-        cudaEventRecord(a, c->stream);
+        cudaEventRecord(a, st);
     }
     ~ProfScope()
     {
         if (!a) return;
-        cudaEventRecord(b, c->stream);
+        cudaEventRecord(b, st);
         c->pending.push_back({a, b, slot});
     }
 };
@@ -229,8 +230,15 @@ static int createInit(ddcb200_ctx *c)
     CK(cudaMallocHost((void **)&c->accHost, (ACC_N + 8) * sizeof(double)));
     CK(cudaMallocHost((void **)&c->ddcHost, 64 * sizeof(int)));
     CK(cudaMalloc((void **)&c->ddcCounters, 8 * sizeof(int)));
-    CK(cudaMalloc((void **)&c->dmax2, sizeof(unsigned long long)));
-    CK(cudaMemset(c->dmax2, 0, sizeof(unsigned long long)));
+    CK(cudaMalloc((void **)&c->dmax2, 2 * sizeof(unsigned long long)));
+    CK(cudaMemset(c->dmax2, 0, 2 * sizeof(unsigned long long)));
+    if (const char *hm = getenv("DDCB200_HALO"))
+    {
+        // several ranks: "overlap" (default) = the ghost halo runs on its own stream beside the pair rows that read no ghost,
+        // "inline" = on the compute stream before the pair kernel.  Same results (A/B knob)
+        if (strcmp(hm, "inline") == 0) c->haloOverlap = false;
+        else if (strcmp(hm, "overlap") != 0) return fail(DDCB200_ERR_ARG, "DDCB200_HALO must be overlap or inline");
+    }
     return DDCB200_OK;
 }
 
@@ -292,6 +300,10 @@ extern "C" void ddcb200_destroy(ddcb200_ctx *c)
     c->ownerBead.release(); c->ddcDest.release(); c->ddcMask.release();
     c->ddcList.release(); c->sendSlot.release(); c->recvSlot.release();
     c->sendBuf.release(); c->recvBuf.release(); c->accG.release();
+    if (c->streamH) { cudaStreamSynchronize(c->streamH); cudaStreamDestroy(c->streamH); }
+    if (c->evPos) cudaEventDestroy(c->evPos);
+    if (c->evHalo) cudaEventDestroy(c->evHalo);
+    c->tileGhost.release(); c->tileOrder.release();
     if (c->ddcWork) cudaFree(c->ddcWork);
     if (c->ddcWorkInit) cudaFreeHost(c->ddcWorkInit);
     if (c->ddcRow) cudaFree(c->ddcRow);
@@ -927,10 +939,9 @@ static int redomain(ddcb200_ctx *c)
 }
 
 // ddcUpdate (src/ddcUpdate.c:40-88): owners send the new positions of the beads their neighbours hold as ghosts
-static int haloExchange(ddcb200_ctx *c)
+static int haloExchange(ddcb200_ctx *c, cudaStream_t st)
 {
-    ProfScope ps(c, PROF_HALO);
-    cudaStream_t st = c->stream;
+    ProfScope ps(c, PROF_HALO, st);
     ncclComm_t comm = (ncclComm_t)c->nccl;
     const int cur = c->cur;
     if (c->nSendTot)
@@ -1032,7 +1043,7 @@ extern "C" int ddcb200_constructList(ddcb200_ctx *c)
                                  c->pos32.p, c->posBuild[0].p, c->posBuild[1].p, c->posBuild[2].p);
     CKL("cell sort");
     c->cur = nxt;
-    CK(cudaMemsetAsync(c->dmax2, 0, sizeof(unsigned long long), st));
+    CK(cudaMemsetAsync(c->dmax2, 0, 2 * sizeof(unsigned long long), st));
     CK(c->dispOfSlot.ensure((size_t)nPad));
     CK(cudaMemsetAsync(c->dispOfSlot.p, 0, (size_t)nPad * sizeof(float), st));
 
@@ -1052,6 +1063,11 @@ extern "C" int ddcb200_constructList(ddcb200_ctx *c)
         CK(cudaEventCreate(&c->evList[0]));
         CK(cudaEventCreate(&c->evList[1]));
     }
+    if (c->nranks > 1)
+    {
+        CK(c->tileGhost.ensure((size_t)(nPad / TILE) + 1));
+        CK(c->tileOrder.ensure((size_t)(nPad / TILE) + 1));
+    }
     for (int attempt = 0; attempt < 4; attempt++)
     {
         CK(c->nbr.ensure((size_t)c->nbrCap * nPad));
@@ -1062,9 +1078,15 @@ extern "C" int ddcb200_constructList(ddcb200_ctx *c)
         CKL("k_nbr_filter");
         LAUNCH(k_nbr_exact, nPad / 128, 128, 0, st)(nIon, nPad, c->nbrCap, c->pos4[nxt].p, c->box, c->grid, c->nbrRaw.p, c->nbrRawCount.p,
                                                c->nbr.p, c->nbrCount.p, c->nbrCum.p, c->gidOfBead.p, c->molTypeOfBead.p,
-                                               c->molTypeSingle.p, c->bpairOffset.p, c->bpairKey.p, c->haveExcl ? 1 : 0);
+                                               c->molTypeSingle.p, c->bpairOffset.p, c->bpairKey.p, c->haveExcl ? 1 : 0,
+                                               c->nranks > 1 ? c->tileGhost.p : nullptr);
         CKL("k_nbr_exact");
         CK(cudaEventRecord(c->evList[1], st));
+        if (c->nranks > 1)
+        {
+            LAUNCH(k_tile_order, 1, 1024, 0, st)(nPad / TILE, c->tileGhost.p, c->tileOrder.p, c->grid);
+            CKL("k_tile_order");
+        }
         CK(cudaMemcpyAsync(c->gridHost, c->grid, sizeof(GridDev), cudaMemcpyDeviceToHost, st));
         CK(cudaStreamSynchronize(st));
         if (c->gridHost->error & 2) return fail(DDCB200_ERR_CAPACITY, "cell grid larger than the bead count bound");
@@ -1114,6 +1136,7 @@ extern "C" int ddcb200_constructList(ddcb200_ctx *c)
     c->lastBuildLoop = c->loop;
     c->totalEntries = (int64_t)c->gridHost->totalEntries;
     c->nPairsListed = (int64_t)(c->gridHost->totalEntries / 2);
+    c->nTilesInterior = c->nranks > 1 ? c->gridHost->nInterior : nPad / TILE;
     return DDCB200_OK;
 }
 
@@ -1211,10 +1234,25 @@ extern "C" int ddcb200_ddcenergy(ddcb200_ctx *c, int withEnergy)
     if (rc) return rc;
     // evalUpdateFlag, src/ddcUpdateAll.c:64-71
     bool due = c->prm.updateRate > 0 && (c->loop % c->prm.updateRate) == 0 && c->lastBuildLoop != c->loop;
+    // ddcUpdate (src/ddcUpdate.c:40-88).  With a fixed rebuild rate the halo goes to its own stream: the pair rows that read no
+    // ghost position run meanwhile, the others wait for it.  (updateRate = 0: neighborCheck needs the ghosts first)
+    bool overlapped = false;
     if (c->listValid && !due && c->nranks > 1 && c->haloDirty)
     {
-        rc = haloExchange(c);
-        if (rc) return rc;
+        if (c->haloOverlap && c->prm.updateRate > 0)
+        {
+            CK(cudaEventRecord(c->evPos, c->stream));
+            CK(cudaStreamWaitEvent(c->streamH, c->evPos, 0));
+            rc = haloExchange(c, c->streamH);
+            if (rc) return rc;
+            CK(cudaEventRecord(c->evHalo, c->streamH));
+            overlapped = true;
+        }
+        else
+        {
+            rc = haloExchange(c, c->stream);
+            if (rc) return rc;
+        }
     }
     if (c->listValid && c->prm.updateRate == 0 && c->lastBuildLoop != c->loop)
     {
@@ -1232,15 +1270,32 @@ extern "C" int ddcb200_ddcenergy(ddcb200_ctx *c, int withEnergy)
     const int tiles = nPad / TILE;
     if (withEnergy) CK(cudaMemsetAsync(c->acc, 0, ACC_N * sizeof(double), st));
     {
-        ProfScope ps(c, PROF_PAIR);
         const size_t smem = pairSmemBytes(c->ntypes);
-        if (withEnergy)
-            LAUNCH(k_pair<true>, tiles, TILE, smem, st)(nLocal, nPad, c->pos4[cur].p, c->nbr.p, c->nbrCum.p, c->dmax2, c->walkPerBead ? c->dispOfSlot.p : nullptr, c->ljTab.p, c->shiftTab.p,
-                                                    c->qTab.p, c->pc, c->frc[0].p, c->frc[1].p, c->frc[2].p, c->pairPartial.p);
+        const float *disp = c->walkPerBead ? c->dispOfSlot.p : nullptr;
+        auto launchPair = [&](int nTiles, const int *order, int base, int withGhosts) -> int {
+            if (nTiles <= 0) return DDCB200_OK;
+            ProfScope ps(c, PROF_PAIR);
+            if (withEnergy)
+                LAUNCH(k_pair<true>, nTiles, TILE, smem, st)(nLocal, nPad, order, base, c->pos4[cur].p, c->nbr.p, c->nbrCum.p, c->dmax2, withGhosts, disp,
+                                                         c->ljTab.p, c->shiftTab.p, c->qTab.p, c->pc, c->frc[0].p, c->frc[1].p, c->frc[2].p,
+                                                         c->pairPartial.p);
+            else
+                LAUNCH(k_pair<false>, nTiles, TILE, smem, st)(nLocal, nPad, order, base, c->pos4[cur].p, c->nbr.p, c->nbrCum.p, c->dmax2, withGhosts, disp,
+                                                          c->ljTab.p, c->shiftTab.p, c->qTab.p, c->pc, c->frc[0].p, c->frc[1].p, c->frc[2].p,
+                                                          c->pairPartial.p);
+            CKL("k_pair");
+            return DDCB200_OK;
+        };
+        if (c->nranks > 1)
+        {
+            rc = launchPair(c->nTilesInterior, c->tileOrder.p, 0, 0);
+            if (rc) return rc;
+            if (overlapped) CK(cudaStreamWaitEvent(st, c->evHalo, 0));
+            rc = launchPair(tiles - c->nTilesInterior, c->tileOrder.p, c->nTilesInterior, 1);
+        }
         else
-            LAUNCH(k_pair<false>, tiles, TILE, smem, st)(nLocal, nPad, c->pos4[cur].p, c->nbr.p, c->nbrCum.p, c->dmax2, c->walkPerBead ? c->dispOfSlot.p : nullptr, c->ljTab.p, c->shiftTab.p,
-                                                     c->qTab.p, c->pc, c->frc[0].p, c->frc[1].p, c->frc[2].p, c->pairPartial.p);
-        CKL("k_pair");
+            rc = launchPair(tiles, nullptr, 0, 0);
+        if (rc) return rc;
     }
     const int64_t nb = c->nTerms + c->nRestr;
     int bBlocks = 0;
@@ -1882,16 +1937,17 @@ extern "C" int ddcb200_pairCorrelation(ddcb200_ctx *c, int nBins, double rmin, d
     }
     if (c->nranks > 1 && c->haloDirty)
     {
-        rc = haloExchange(c);
+        rc = haloExchange(c, c->stream);
         if (rc) return rc;
     }
     cudaStream_t st = c->stream;
     // candidates: the cells within `reach` cells of a bead's build-time cell.  A pair with r < rmax now was within
     // rmax + 2 dmax + box slack at the build, and a cell is at least d_min wide: reach = ceil of that over d_min
-    unsigned long long dbits = 0;
-    CK(cudaMemcpyAsync(&dbits, c->dmax2, sizeof dbits, cudaMemcpyDeviceToHost, st));
+    unsigned long long dbits2[2] = {0, 0};
+    CK(cudaMemcpyAsync(dbits2, c->dmax2, sizeof dbits2, cudaMemcpyDeviceToHost, st));
     CK(cudaMemcpyAsync(c->gridHost, c->grid, sizeof(GridDev), cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
+    const unsigned long long dbits = std::max(dbits2[0], dbits2[1]);     // locals and ghosts
     double d2;
     memcpy(&d2, &dbits, sizeof d2);
     const double need = (rmax + 2.0 * sqrt(d2) + c->pc.listSlack) * (1.0 + 1e-9);
@@ -2002,6 +2058,9 @@ extern "C" int ddcb200_ddcInit(ddcb200_ctx *c, int rank, int nranks, int lx, int
     ncclComm_t comm;
     CKN(ncclCommInitRank(&comm, nranks, u, rank));
     c->nccl = (void *)comm;
+    CK(cudaStreamCreateWithFlags(&c->streamH, cudaStreamNonBlocking));
+    CK(cudaEventCreateWithFlags(&c->evPos, cudaEventDisableTiming));
+    CK(cudaEventCreateWithFlags(&c->evHalo, cudaEventDisableTiming));
     CK(cudaMalloc((void **)&c->boxes, sizeof(DdcBoxes)));
     CK(cudaMalloc((void **)&c->ddcWork, sizeof(DdcWork)));
     CK(cudaMallocHost((void **)&c->ddcWorkInit, sizeof(DdcWork)));

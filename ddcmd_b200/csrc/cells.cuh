@@ -371,10 +371,11 @@ __global__ void __launch_bounds__(128)
 k_nbr_exact(int nIon, int nPad, int cap, const double4 *__restrict__ pos, BoxConst b, GridDev *gp, uint32_t *__restrict__ raw,
             const int *__restrict__ rawCount, uint32_t *__restrict__ out, int *__restrict__ count, uint16_t *__restrict__ cum,
             const uint64_t *__restrict__ gid, const int *__restrict__ molTypeOfBead, const int *__restrict__ molTypeSingle,
-            const int *__restrict__ bpairOffset, const uint32_t *__restrict__ bpairKey, int haveExcl)
+            const int *__restrict__ bpairOffset, const uint32_t *__restrict__ bpairKey, int haveExcl, int *__restrict__ tileGhost)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     int total = 0;
+    bool ghostEntry = false;      // some entry of this row is a ghost slot (several ranks): the row waits for the halo
     if (i < nIon)
     {
         // ghost slots have no candidates (rawCount 0): their row stays empty
@@ -403,10 +404,11 @@ k_nbr_exact(int nIon, int nPad, int cap, const double4 *__restrict__ pos, BoxCon
 #pragma unroll
                 for (int e = 0; e < NBINS - 1; e++) bin += (r2 >= b.binEdge2[e]) ? 1 : 0;
                 ent = j | ((uint32_t)bin << 27);
+                const uint64_t wj = (uint64_t)__double_as_longlong(pj.w);
+                ghostEntry |= (wj >> 63) != 0ull;
                 if (haveExcl)
                 {
                     // same molecule? bits 16..31 of w carry the low 16 bits of gid>>32: cheap reject before the gid gathers
-                    const uint64_t wj = (uint64_t)__double_as_longlong(pj.w);
                     if (((wi ^ wj) & 0xffff0000ull) == 0ull &&
                         isPruned((int)((wi >> 32) & 0x7fffffffull), (int)((wj >> 32) & 0x7fffffffull), gid, molTypeOfBead, molTypeSingle, bpairOffset, bpairKey))
                         ent |= EXCL_BIT;
@@ -461,4 +463,46 @@ k_nbr_exact(int nIon, int nPad, int cap, const double4 *__restrict__ pos, BoxCon
         atomicMax(&gp->maxCount, m);
         atomicAdd(&gp->totalEntries, t);
     }
+    if (tileGhost)
+    {
+        // one tile of k_pair = this block (TILE threads): does any of its rows read a ghost position?
+        __shared__ int anyGhost;
+        if (threadIdx.x == 0) anyGhost = 0;
+        __syncthreads();
+        if (ghostEntry) atomicOr(&anyGhost, 1);
+        __syncthreads();
+        if (threadIdx.x == 0) tileGhost[blockIdx.x] = anyGhost;
+    }
+}
+
+// Order of the k_pair tiles on several ranks: the tiles whose rows touch no ghost first (they run while the halo is in
+// flight), then the others; ascending inside each group.  One block; nInterior goes to the grid record.
+__global__ void __launch_bounds__(1024)
+k_tile_order(int nTiles, const int *__restrict__ tileGhost, int *__restrict__ order, GridDev *gp)
+{
+    __shared__ int sums[1024];
+    __shared__ int totalInterior;
+    const int per = (nTiles + blockDim.x - 1) / blockDim.x;
+    const int lo = min(nTiles, (int)threadIdx.x * per), hi = min(nTiles, lo + per);
+    int s = 0;
+    for (int t = lo; t < hi; t++) s += tileGhost[t] ? 0 : 1;
+    sums[threadIdx.x] = s;
+    __syncthreads();
+    for (int o = 1; o < (int)blockDim.x; o <<= 1)
+    {
+        int v = ((int)threadIdx.x >= o) ? sums[threadIdx.x - o] : 0;
+        __syncthreads();
+        sums[threadIdx.x] += v;
+        __syncthreads();
+    }
+    if (threadIdx.x == blockDim.x - 1) totalInterior = sums[threadIdx.x];
+    __syncthreads();
+    int ni = sums[threadIdx.x] - s;            // interior tiles before my chunk
+    int nb = lo - ni;                          // boundary tiles before my chunk
+    for (int t = lo; t < hi; t++)
+    {
+        if (tileGhost[t]) order[totalInterior + nb++] = t;
+        else order[ni++] = t;
+    }
+    if (threadIdx.x == 0) gp->nInterior = totalInterior;
 }

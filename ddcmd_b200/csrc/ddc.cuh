@@ -393,7 +393,7 @@ __global__ void k_halo_unpack(int n, const int *__restrict__ slot, const double 
     if ((threadIdx.x & 31) == 0)
     {
         const unsigned long long bits = (unsigned long long)__double_as_longlong(disp2);
-        if (bits > *(volatile unsigned long long *)dmax2) atomicMax(dmax2, bits);
+        if (bits > *(volatile unsigned long long *)(dmax2 + 1)) atomicMax(dmax2 + 1, bits);      // [1]: ghosts (engine.cuh)
     }
 }
 

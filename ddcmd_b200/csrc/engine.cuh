@@ -52,6 +52,7 @@ struct GridDev
     int error;       // sticky error flags (bit0: neighbor capacity overflow, bit1: cell overflow)
     int maxCount;    // max full-list length over beads
     int maxRaw;      // max candidate count over beads (fp32 filter pass)
+    int nInterior;   // several ranks: k_pair tiles whose rows touch no ghost slot
     unsigned long long totalEntries;
 };
 
@@ -205,7 +206,7 @@ struct ddcb200_ctx
     DevBuf<uint64_t> orderKey;    // (sub-cell Morton key, bead) : slot order inside a cell
     DevBuf<float4> pos32;         // fp32 copy of the build-time positions (candidate filter)
     DevBuf<double> posBuild[3];   // build-time positions, slot order (displacement bound)
-    unsigned long long *dmax2 = nullptr;   // device: bits of max squared displacement since the build
+    unsigned long long *dmax2 = nullptr;   // device: [0] bits of the max squared displacement of a LOCAL bead since the build, [1] of a ghost
     bool walkPerBead = true;      // DDCB200_WALK
     DevBuf<float> dispOfSlot;     // each local bead's own displacement since the build, rounded up (0 right after a build)
     DevBuf<double> mmPartial;
@@ -277,6 +278,11 @@ struct ddcb200_ctx
     std::vector<int> hSendCount, hRecvCount, hSendOff, hRecvOff;
     int nSendTot = 0, nRecvTot = 0;
     bool haloDirty = false, localsDirty = false;
+    cudaStream_t streamH = nullptr;         // the halo runs here, beside the pair work of the rows that read no ghost
+    cudaEvent_t evPos = nullptr, evHalo = nullptr;
+    DevBuf<int> tileGhost, tileOrder;
+    int nTilesInterior = 0;
+    bool haloOverlap = true;                // DDCB200_HALO=overlap|inline
     DevBuf<double> accG;              // all-reduced accumulators
 
     // NGLFCONSTRAINT (nglfcons.cuh): groups, per-bead LCG64 streams, constraint clusters, barostat

@@ -28,8 +28,8 @@ __device__ __forceinline__ double4 ldPos(const double4 *p)
 
 template <bool ENERGY>
 __global__ void __launch_bounds__(TILE)
-k_pair(int nIon, int nPad, const double4 *__restrict__ pos, const uint32_t *__restrict__ nbr, const uint16_t *__restrict__ cum,
-       const unsigned long long *__restrict__ dmax2, const float *__restrict__ dispOfSlot,
+k_pair(int nIon, int nPad, const int *__restrict__ tileOrder, int tileBase, const double4 *__restrict__ pos, const uint32_t *__restrict__ nbr,
+       const uint16_t *__restrict__ cum, const unsigned long long *__restrict__ dmax2, int withGhosts, const float *__restrict__ dispOfSlot,
        const double2 *__restrict__ ljTab, const double *__restrict__ shiftTab, const double *__restrict__ qTab, PairConst pc,
        double *__restrict__ fx, double *__restrict__ fy, double *__restrict__ fz, double *__restrict__ accPartial)
 {
@@ -44,7 +44,9 @@ k_pair(int nIon, int nPad, const double4 *__restrict__ pos, const uint32_t *__re
     for (int k = threadIdx.x; k < 256; k += blockDim.x) sQ[k] = qTab[k];
     __syncthreads();
 
-    const int i = blockIdx.x * TILE + threadIdx.x;
+    // several ranks: the launch covers a range of the tile order (rows without / with ghost entries)
+    const int tile = tileOrder ? tileOrder[tileBase + blockIdx.x] : (int)blockIdx.x;
+    const int i = tile * TILE + threadIdx.x;
     const int ii = i < nIon ? i : 0;
     const double4 pi = ldPos(pos + ii);
     const uint64_t wi = (uint64_t)__double_as_longlong(pi.w);
@@ -60,7 +62,11 @@ k_pair(int nIon, int nPad, const double4 *__restrict__ pos, const uint32_t *__re
     // Exact, not a heuristic - the skipped entries would have added exact zeros, so the forces are bit-for-bit the same.
     int binLimit = 0;
     {
-        const double dmax = sqrt(__longlong_as_double((long long)*dmax2));
+        // dmax2[0]: local beads (complete when this kernel starts), dmax2[1]: ghosts (complete once the halo has arrived, which
+        // the launch over the rows with ghost entries waits for; rows without ghost entries only have local partners)
+        unsigned long long db = dmax2[0];
+        if (withGhosts) db = max(db, dmax2[1]);
+        const double dmax = sqrt(__longlong_as_double((long long)db));
         // dispOfSlot == nullptr (DDCB200_WALK=global): every bead takes the global bound, d_i := dmax
         const double di = (live && dispOfSlot) ? fmin((double)dispOfSlot[ii], dmax) : dmax;
         const double lim = (pc.rmax + pc.listSlack + dmax + di) * (1.0 + 1e-12);
@@ -190,7 +196,7 @@ k_pair(int nIon, int nPad, const double4 *__restrict__ pos, const uint32_t *__re
         {
             double t = 0.0;
             for (int w = 0; w < TILE / 32; w++) t += red[threadIdx.x][w];
-            accPartial[(size_t)blockIdx.x * 8 + threadIdx.x] = t;
+            accPartial[(size_t)tile * 8 + threadIdx.x] = t;
         }
     }
 }

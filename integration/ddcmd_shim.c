@@ -27,6 +27,8 @@
 #include "ddc.h"
 #include "codata.h"
 #include "box.h"
+#include "bioCharmmParms.h"
+void charmmResidues(SYSTEM *sys, CHARMMPOT_PARMS *parms);
 #include "../include/ddcmd_b200_host.h"
 
 static ddcb200_ctx *b200;
@@ -111,7 +113,10 @@ static void martiniB200(void *sys_, void *parms, void *e_)
     SYSTEM *sys = (SYSTEM *)sys_;
     STATE *s = sys->collection->state;
     ddcb200_etype o;
-    (void)parms;
+    /* bookkeeping of martini() that other parts of ddcMD read: nglfconstraint takes the residue table and the gid order of the
+     * local beads from the potential's parms (paddingCons / velocityConstraintOld, src/nglfconstraint.c:316-391,439-457), and it is
+     * charmmConvalent that refreshes them on every call (charmmResidues, src/bioCharmmCovalent.c:48-93).  Host-side, O(n log n). */
+    charmmResidues(sys, (CHARMMPOT_PARMS *)parms);
     sendState(sys);
     ck(ddcb200_ddcenergy(b200, 1), "martiniB200", ddcb200_lastError());
     ck(ddcb200_energyInfo(b200, kB, &o), "martiniB200", ddcb200_lastError());

@@ -110,6 +110,9 @@ static inline cudaError_t cudaStreamCreateWithFlags(cudaStream_t *s, unsigned) {
 static inline cudaError_t cudaStreamDestroy(cudaStream_t s) { free(s); return cudaSuccess; }
 static inline cudaError_t cudaStreamSynchronize(cudaStream_t) { return cudaSuccess; }
 static inline cudaError_t cudaDeviceSynchronize() { return cudaSuccess; }
+enum { cudaEventDisableTiming = 2 };
+static inline cudaError_t cudaEventCreateWithFlags(cudaEvent_t *e, unsigned) { *e = (cudaEvent_t)malloc(sizeof(emuEvent)); (*e)->t = 0; return cudaSuccess; }
+static inline cudaError_t cudaStreamWaitEvent(cudaStream_t, cudaEvent_t, unsigned) { return cudaSuccess; }   // streams run in program order here
 static inline cudaError_t cudaEventCreate(cudaEvent_t *e) { *e = (cudaEvent_t)malloc(sizeof(emuEvent)); (*e)->t = 0; return cudaSuccess; }
 static inline cudaError_t cudaEventDestroy(cudaEvent_t e) { free(e); return cudaSuccess; }
 static inline cudaError_t cudaEventRecord(cudaEvent_t e, cudaStream_t = nullptr) { e->t = emu::now(); return cudaSuccess; }

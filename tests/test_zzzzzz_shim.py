@@ -62,10 +62,12 @@ def test_ddcmd_with_the_emulated_library_plugged_in(golden_dir, tmp_path, deck):
 
 
 @pytest.mark.skipif(not (os.path.exists(REF) and os.path.exists(SHIM_EMU)), reason="oracle/_ref binaries not built")
-def test_shipped_configuration_with_the_emulated_library_as_potential(golden_dir, tmp_path):
+@pytest.mark.parametrize("deck", ["waterbox", "ras_small"])
+def test_shipped_configuration_with_the_emulated_library_as_potential(golden_dir, tmp_path, deck):
     """examples/waterbox as shipped - NGLFCONSTRAINT, LANGEVIN groups and the barostat all run by ddcMD on the host - with the
-    library as its MARTINI potential: the barostat's box reaches the library through ddcb200_setBox."""
-    check_shim(golden_dir, "waterbox", tmp_path, SHIM_EMU, "full")
+    library as its MARTINI potential: the barostat's box reaches the library through ddcb200_setBox.  ras_small adds velocity
+    constraints, which ddcMD applies through the residue table that martini() refreshes on every call: the binding keeps it."""
+    check_shim(golden_dir, deck, tmp_path, SHIM_EMU, "full")
 
 
 @pytest.mark.gpu
