@@ -272,8 +272,15 @@ def main():
         log("[bench] %d steps in %.2f ms -> %.1f steps/s; T=%.1f K" % (K, ms, sps, e.temperature / dd.units_convert(1.0, "K", None)))
 
     if args.kernels_only:
+        sim.profile(True)
+        sim.profileRead(reset=True)
+        sim.nglf(40)
+        prof = sim.profileRead(reset=True)
         if rank == 0:
-            print(json.dumps({"steps_per_s": sps, "ms_per_step": ms / K, "gpu_launches": int(launches), "clocks": clk}))
+            print(json.dumps({"steps_per_s": sps, "ms_per_step": ms / K, "gpu_launches": int(launches), "clocks": clk,
+                              "variant": os.environ.get("DDCB200_PAIR", "default"),
+                              "per_kernel_ms_per_step": {k: v[0] / 40 for k, v in prof.items()},
+                              "list_build_ms": sim.listBuildInfo()[1][0]}))
         sim.close()
         return
 

@@ -189,6 +189,20 @@ static int setupBox(ddcb200_ctx *c)
     return DDCB200_OK;
 }
 
+// The k_pair2 instantiations (gathers in flight per thread, CTAs per SM the register allocation is capped for): A/B-ed on the
+// B200 through DDCB200_PAIR=<pf>,<minb> | old
+typedef void (*PairKernel)(int, int, const int *, int, const double4 *, const uint32_t *, const uint16_t *, const unsigned long long *, int,
+                           const float *, const double2 *, const double *, const double *, PairConst, double *, double *, double *, double *);
+struct PairVariant
+{
+    int pf, minb;
+    PairKernel force, energy;
+};
+#define PV(P, M) {P, M, k_pair2<false, P, M>, k_pair2<true, P, M>}
+static const PairVariant g_pairVariants[] = {PV(1, 1), PV(1, 12), PV(2, 1), PV(2, 8), PV(2, 10), PV(3, 8), PV(4, 1), PV(4, 8)};
+#undef PV
+static const int g_nPairVariants = (int)(sizeof(g_pairVariants) / sizeof(g_pairVariants[0]));
+
 // everything of ddcb200_create that can fail after the context exists: a failure is unwound by ddcb200_destroy
 static int createInit(ddcb200_ctx *c)
 {
@@ -232,6 +246,19 @@ static int createInit(ddcb200_ctx *c)
     CK(cudaMalloc((void **)&c->ddcCounters, 8 * sizeof(int)));
     CK(cudaMalloc((void **)&c->dmax2, 2 * sizeof(unsigned long long)));
     CK(cudaMemset(c->dmax2, 0, 2 * sizeof(unsigned long long)));
+    if (const char *pv = getenv("DDCB200_PAIR"))
+    {
+        int pf = 0, mb = 0;
+        if (strcmp(pv, "old") == 0) c->pairVariant = -1;
+        else if (sscanf(pv, "%d,%d", &pf, &mb) == 2)
+        {
+            c->pairVariant = -2;
+            for (int v = 0; v < g_nPairVariants; v++)
+                if (g_pairVariants[v].pf == pf && g_pairVariants[v].minb == mb) c->pairVariant = v;
+        }
+        else c->pairVariant = -2;
+        if (c->pairVariant == -2) return fail(DDCB200_ERR_ARG, "DDCB200_PAIR must be old or one of the built <pf>,<minb> pairs");
+    }
     if (const char *hm = getenv("DDCB200_HALO"))
     {
         // several ranks: "overlap" (default) = the ghost halo runs on its own stream beside the pair rows that read no ghost,
@@ -275,7 +302,7 @@ extern "C" void ddcb200_destroy(ddcb200_ctx *c)
     if (c->stream) cudaStreamSynchronize(c->stream);
     c->ljTab.release(); c->shiftTab.release(); c->qTab.release(); c->massOfBead.release(); c->wOfBead.release();
     c->gidOfBead.release(); c->molTypeOfBead.release(); c->molTypeSingle.release(); c->bpairOffset.release();
-    c->bpairKey.release(); c->termsBead.release(); c->restrBead.release(); c->bondCsrOff.release(); c->bondEnt.release(); c->bondRange.release();
+    c->bpairKey.release(); c->termsBead.release(); c->restrBead.release(); c->bondCsrOff.release(); c->bondEnt.release(); c->bondRange.release(); c->bondRec.release(); c->bondCount.release(); c->bondStart.release();
     c->restrParm.release(); c->molOffset.release(); c->molBeads.release();
     for (int k = 0; k < 2; k++)
     {
@@ -366,6 +393,11 @@ extern "C" int ddcb200_martiniNonBondParms(ddcb200_ctx *c, int ntypes, const dou
         return fail(DDCB200_ERR_CAPACITY, "too many LJ atom types for the shared-memory tables of the pair kernel (about 96 at most)");
     CK(cudaFuncSetAttribute(k_pair<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     CK(cudaFuncSetAttribute(k_pair<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    for (int v = 0; v < g_nPairVariants; v++)
+    {
+        CK(cudaFuncSetAttribute(g_pairVariants[v].force, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        CK(cudaFuncSetAttribute(g_pairVariants[v].energy, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    }
     c->ntypes = ntypes;
     c->pc.ntypes = ntypes;
     return DDCB200_OK;
@@ -1063,6 +1095,19 @@ extern "C" int ddcb200_constructList(ddcb200_ctx *c)
         CK(cudaEventCreate(&c->evList[0]));
         CK(cudaEventCreate(&c->evList[1]));
     }
+    // bonded records of the resident local beads: counted and scanned here so that the total comes back with the grid record
+    const bool haveBonded = c->nTerms + c->nRestr > 0;
+    if (haveBonded)
+    {
+        int rcb = ensureBondCsr(c);
+        if (rcb) return rcb;
+        CK(c->bondCount.ensure((size_t)nPad));
+        CK(c->bondStart.ensure((size_t)nPad));
+        LAUNCH(k_bond_count, (nIon + 255) / 256, 256, 0, st)(nIon, c->pos4[nxt].p, c->bondCsrOff.p, c->bondCount.p);
+        CKL("k_bond_count");
+        LAUNCH(k_scan_int, 1, 1024, 0, st)(nIon, c->bondCount.p, c->bondStart.p, &c->grid->bondTotal);
+        CKL("k_scan_int");
+    }
     if (c->nranks > 1)
     {
         CK(c->tileGhost.ensure((size_t)(nPad / TILE) + 1));
@@ -1103,13 +1148,14 @@ extern "C" int ddcb200_constructList(ddcb200_ctx *c)
         CK(cudaMemsetAsync(&c->grid->maxRaw, 0, sizeof(int), st));
         CK(cudaMemsetAsync(&c->grid->totalEntries, 0, sizeof(unsigned long long), st));
     }
-    if (c->nTerms + c->nRestr > 0)
+    if (haveBonded)
     {
-        int rcb = ensureBondCsr(c);
-        if (rcb) return rcb;
         CK(c->bondRange.ensure((size_t)nPad));
-        LAUNCH(k_bond_ranges, (nIon + 255) / 256, 256, 0, st)(nIon, c->pos4[nxt].p, c->bondCsrOff.p, c->bondRange.p);
-        CKL("k_bond_ranges");
+        CK(c->bondRec.ensure((size_t)c->gridHost->bondTotal + 1));
+        LAUNCH(k_bond_resolve, (nIon + 255) / 256, 256, 0, st)(nIon, c->pos4[nxt].p, c->bondCsrOff.p, c->bondEnt.p, c->nTerms, c->termsBead.p,
+                                                           c->restrParm.p, c->slotOfBead.p, c->bondStart.p, c->bondCount.p, c->bondRange.p,
+                                                           c->bondRec.p);
+        CKL("k_bond_resolve");
     }
     if (c->nranks > 1)
     {
@@ -1275,7 +1321,14 @@ extern "C" int ddcb200_ddcenergy(ddcb200_ctx *c, int withEnergy)
         auto launchPair = [&](int nTiles, const int *order, int base, int withGhosts) -> int {
             if (nTiles <= 0) return DDCB200_OK;
             ProfScope ps(c, PROF_PAIR);
-            if (withEnergy)
+            if (c->pairVariant >= 0)
+            {
+                const PairVariant &pv = g_pairVariants[c->pairVariant];
+                LAUNCH(withEnergy ? pv.energy : pv.force, nTiles, TILE, smem, st)(nLocal, nPad, order, base, c->pos4[cur].p, c->nbr.p, c->nbrCum.p,
+                                                                                 c->dmax2, withGhosts, disp, c->ljTab.p, c->shiftTab.p, c->qTab.p,
+                                                                                 c->pc, c->frc[0].p, c->frc[1].p, c->frc[2].p, c->pairPartial.p);
+            }
+            else if (withEnergy)
                 LAUNCH(k_pair<true>, nTiles, TILE, smem, st)(nLocal, nPad, order, base, c->pos4[cur].p, c->nbr.p, c->nbrCum.p, c->dmax2, withGhosts, disp,
                                                          c->ljTab.p, c->shiftTab.p, c->qTab.p, c->pc, c->frc[0].p, c->frc[1].p, c->frc[2].p,
                                                          c->pairPartial.p);
@@ -1305,13 +1358,11 @@ extern "C" int ddcb200_ddcenergy(ddcb200_ctx *c, int withEnergy)
         bBlocks = (nLocal + BONDED_THREADS - 1) / BONDED_THREADS;
         CK(c->bondPartial.ensure((size_t)bBlocks * BONDED_ACC + 8));
         if (withEnergy)
-            LAUNCH(k_bonded<true>, bBlocks, BONDED_THREADS, 0, st)(nLocal, c->bondRange.p, c->bondEnt.p, c->nTerms, c->termsBead.p, c->restrBead.p,
-                                                               c->restrParm.p, c->restrOrigin, c->slotOfBead.p, c->pos4[cur].p, c->pc,
-                                                               c->frc[0].p, c->frc[1].p, c->frc[2].p, c->bondPartial.p);
+            LAUNCH(k_bonded<true>, bBlocks, BONDED_THREADS, 0, st)(nLocal, c->bondRange.p, c->bondRec.p, c->restrParm.p, c->restrOrigin,
+                                                               c->pos4[cur].p, c->pc, c->frc[0].p, c->frc[1].p, c->frc[2].p, c->bondPartial.p);
         else
-            LAUNCH(k_bonded<false>, bBlocks, BONDED_THREADS, 0, st)(nLocal, c->bondRange.p, c->bondEnt.p, c->nTerms, c->termsBead.p, c->restrBead.p,
-                                                                c->restrParm.p, c->restrOrigin, c->slotOfBead.p, c->pos4[cur].p, c->pc,
-                                                                c->frc[0].p, c->frc[1].p, c->frc[2].p, c->bondPartial.p);
+            LAUNCH(k_bonded<false>, bBlocks, BONDED_THREADS, 0, st)(nLocal, c->bondRange.p, c->bondRec.p, c->restrParm.p, c->restrOrigin,
+                                                                c->pos4[cur].p, c->pc, c->frc[0].p, c->frc[1].p, c->frc[2].p, c->bondPartial.p);
         CKL("k_bonded");
     }
     if (withEnergy)

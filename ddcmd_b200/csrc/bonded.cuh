@@ -81,29 +81,96 @@ __device__ __forceinline__ void dihedral(V3 vij, V3 vjk, V3 vkl, double &ang, do
 // keeps only the force on its own bead.  A bond is therefore evaluated twice, an angle three times, a dihedral four times;
 // in exchange there is no atomic and the summation order of every bead's force is fixed, so forces and energies are
 // bitwise reproducible run to run (the reference accumulates in owner order too, src/bioCharmmCovalent.c:95-251).
-// Energy and virial of a term are counted by the thread of its role-0 bead only.  Endpoints are looked up through
-// slotOfBead; a term with an endpoint that is not resident here is skipped (molecules are whole on their owner rank,
-// src/ddcRuleMolecule.c:43, so that never happens for a local bead of a Martini deck).
-// at every list build: the term range of each slot's bead, in slot order (coalesced in k_bonded)
-__global__ void k_bond_ranges(int nIon, const double4 *__restrict__ pos, const int *__restrict__ csrOff, BondRange *__restrict__ out)
+// Energy and virial of a term are counted by the thread of its role-0 bead only.  At every list build the entries of the
+// resident local beads are resolved into records in slot order (endpoint slots + parameters), so a step reads one record
+// and the partners' positions per entry.  A term with an endpoint that is not resident here is skipped (molecules are
+// whole on their owner rank, src/ddcRuleMolecule.c:43, so that never happens for a local bead of a Martini deck).
+// ---- at every list build: the records of the resident local beads, in slot order -------------------------------------
+__global__ void k_bond_count(int nIon, const double4 *__restrict__ pos, const int *__restrict__ csrOff, int *__restrict__ cnt)
 {
     const int s = blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= nIon) return;
     const unsigned long long w = (unsigned long long)__double_as_longlong(pos[s].w);
-    BondRange r = {0, 0};
+    int n = 0;
     if (!(w >> 63))
     {
         const int b = (int)((w >> 32) & 0x7fffffffull);
-        r.lo = csrOff[b];
-        r.n = csrOff[b + 1] - r.lo;
+        n = csrOff[b + 1] - csrOff[b];
     }
-    out[s] = r;
+    cnt[s] = n;
+}
+
+// exclusive scan of n ints in one block (n is a few million at most and this runs once per list build)
+__global__ void __launch_bounds__(1024)
+k_scan_int(int n, const int *__restrict__ in, int *__restrict__ out, int *__restrict__ total)
+{
+    __shared__ int sums[1024];
+    const int per = (n + blockDim.x - 1) / blockDim.x;
+    const int lo = min(n, (int)threadIdx.x * per), hi = min(n, lo + per);
+    int s = 0;
+    for (int i = lo; i < hi; i++) s += in[i];
+    sums[threadIdx.x] = s;
+    __syncthreads();
+    for (int o = 1; o < (int)blockDim.x; o <<= 1)
+    {
+        int v = ((int)threadIdx.x >= o) ? sums[threadIdx.x - o] : 0;
+        __syncthreads();
+        sums[threadIdx.x] += v;
+        __syncthreads();
+    }
+    int run = sums[threadIdx.x] - s;
+    for (int i = lo; i < hi; i++)
+    {
+        out[i] = run;
+        run += in[i];
+    }
+    if (threadIdx.x == blockDim.x - 1) *total = sums[threadIdx.x];
+}
+
+__global__ void k_bond_resolve(int nIon, const double4 *__restrict__ pos, const int *__restrict__ csrOff, const uint32_t *__restrict__ ent,
+                               int64_t nTerms, const Term *__restrict__ terms, const double *__restrict__ restrParm,
+                               const int *__restrict__ slotOfBead, const int *__restrict__ start, const int *__restrict__ cnt,
+                               BondRange *__restrict__ range, BondRec *__restrict__ recs)
+{
+    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= nIon) return;
+    const int n = cnt[s], lo = start[s];
+    range[s] = BondRange{lo, n};
+    if (n == 0) return;
+    const unsigned long long w = (unsigned long long)__double_as_longlong(pos[s].w);
+    const int elo = csrOff[(int)((w >> 32) & 0x7fffffffull)];
+    for (int q = 0; q < n; q++)
+    {
+        const uint32_t e = ent[elo + q];
+        const int64_t t = (int64_t)(e >> 2);
+        BondRec r;
+        r.role = (int)(e & 3u);
+        if (t >= nTerms)
+        {
+            // restraint (src/restraint.c:287-357): frac0[3] in p0..p2 is not enough room for its 7 parameters, so the record
+            // keeps the restraint's index in s[1] and the kernel reads the table
+            r.kind = 6;
+            r.s[0] = s; r.s[1] = (int)(t - nTerms); r.s[2] = 0; r.s[3] = 0;
+            r.p0 = r.p1 = r.p2 = 0.0;
+        }
+        else
+        {
+            const Term tm = terms[t];
+            r.s[0] = slotOfBead[tm.i];
+            r.s[1] = slotOfBead[tm.j];
+            r.s[2] = tm.k >= 0 ? slotOfBead[tm.k] : 0;
+            r.s[3] = tm.l >= 0 ? slotOfBead[tm.l] : 0;
+            r.p0 = tm.p0; r.p1 = tm.p1; r.p2 = tm.p2;
+            r.kind = ((r.s[0] | r.s[1] | r.s[2] | r.s[3]) < 0) ? -1 : tm.kind;      // an endpoint is not resident on this rank
+        }
+        recs[lo + q] = r;
+    }
+    (void)restrParm;
 }
 
 template <bool ENERGY>
 __global__ void __launch_bounds__(BONDED_THREADS)
-k_bonded(int nIon, const BondRange *__restrict__ range, const uint32_t *__restrict__ ent, int64_t nTerms, const Term *__restrict__ terms,
-         const int *__restrict__ restrBead, const double *__restrict__ restrParm, int restrOrigin, const int *__restrict__ slotOfBead,
+k_bonded(int nIon, const BondRange *__restrict__ range, const BondRec *__restrict__ recs, const double *__restrict__ restrParm, int restrOrigin,
          const double4 *__restrict__ pos, PairConst pc, double *__restrict__ fx, double *__restrict__ fy, double *__restrict__ fz,
          double *__restrict__ partial)
 {
@@ -117,16 +184,14 @@ k_bonded(int nIon, const BondRange *__restrict__ range, const uint32_t *__restri
         V3 fs = V3{0.0, 0.0, 0.0};
         for (int q = 0; q < rg.n; q++)
         {
-            const uint32_t e = ent[rg.lo + q];
-            const int64_t t = (int64_t)(e >> 2);
-            const int role = (int)(e & 3u);
+            const BondRec tm = recs[rg.lo + q];
+            const int role = tm.role;
             const bool count = ENERGY && role == 0;
-            if (t >= nTerms)
+            if (tm.kind < 0) continue;
+            if (tm.kind == 6)
             {
                 // restraint (src/restraint.c:287-357)
-                const int64_t r = t - nTerms;
-                (void)restrBead;
-                const double *p = restrParm + 7 * r;
+                const double *p = restrParm + 7 * (size_t)tm.s[1];
                 double x0 = p[0] * pc.hxx, y0 = p[1] * pc.hyy, z0 = p[2] * pc.hzz;
                 if (restrOrigin == 0)
                 {
@@ -149,10 +214,7 @@ k_bonded(int nIon, const BondRange *__restrict__ range, const uint32_t *__restri
                 }
                 continue;
             }
-            const Term tm = terms[t];
-            const int si = slotOfBead[tm.i], sj = slotOfBead[tm.j];
-            const int sk = tm.k >= 0 ? slotOfBead[tm.k] : 0, sl = tm.l >= 0 ? slotOfBead[tm.l] : 0;
-            if ((si | sj | sk | sl) < 0) continue;      // an endpoint is not resident on this rank
+            const int si = tm.s[0], sj = tm.s[1], sk = tm.s[2], sl = tm.s[3];
             V3 f;
             if (tm.kind == 0)
             {

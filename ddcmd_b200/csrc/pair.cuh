@@ -200,3 +200,178 @@ k_pair(int nIon, int nPad, const int *__restrict__ tileOrder, int tileBase, cons
         }
     }
 }
+
+
+// ---- k_pair2: the same walk with fewer instructions per entry -------------------------------------------------------------
+// ncu on k_pair (profiles/r02a_k_pair_ncu_full.txt): 68 warp instructions per walked entry of which 18 are FP64, issue slots 50 %
+// busy with 4.7 warps per scheduler (83 registers), stalls split between the L1 scoreboard and fixed-latency FP64 chains.  So the
+// walk is bound by instruction issue and latency, not by a pipe.  Here:
+//   * the in-cutoff work sits behind a real branch (lanes outside the cutoff skip it) instead of warp votes + 64-bit selects;
+//   * the Coulomb part is only entered for charged i beads (most Martini beads carry no charge);
+//   * the reciprocal square root is the hardware approximation + two Newton steps (no special-case handling: r2 is a finite
+//     positive distance), the LJ table holds 6 c6 and 12 c12 so the force needs no extra factor;
+//   * PF (gathers in flight per thread) and the register cap (MINB CTAs per SM) are template parameters, A/B-ed on the B200.
+__device__ __forceinline__ double rsqrtFast(double x)
+{
+#ifdef DDCB200_EMU
+    return 1.0 / sqrt(x);
+#else
+    double y;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));      // MUFU.RSQ64H: about 2^-22 relative
+    const double h = 0.5 * x;
+    y = y * fma(-h * y, y, 1.5);
+    y = y * fma(-h * y, y, 1.5);
+    return y;
+#endif
+}
+
+template <bool ENERGY, int NPF, int MINB>
+__global__ void __launch_bounds__(TILE, MINB)
+k_pair2(int nIon, int nPad, const int *__restrict__ tileOrder, int tileBase, const double4 *__restrict__ pos, const uint32_t *__restrict__ nbr,
+        const uint16_t *__restrict__ cum, const unsigned long long *__restrict__ dmax2, int withGhosts, const float *__restrict__ dispOfSlot,
+        const double2 *__restrict__ ljTab, const double *__restrict__ shiftTab, const double *__restrict__ qTab, PairConst pc,
+        double *__restrict__ fx, double *__restrict__ fy, double *__restrict__ fz, double *__restrict__ accPartial)
+{
+    EXTERN_SHARED(double2, sLJ);               // ntypes*ntypes {6 c6, 12 c12}
+    double *sQ = (double *)(sLJ + pc.ntypes * pc.ntypes);   // 256 charges
+    double *sShift = sQ + 256;                              // ntypes*ntypes, ENERGY only
+    for (int k = threadIdx.x; k < pc.ntypes * pc.ntypes; k += blockDim.x)
+    {
+        const double2 c = ljTab[k];
+        sLJ[k] = make_double2(6.0 * c.x, 12.0 * c.y);
+        if (ENERGY) sShift[k] = shiftTab[k];
+    }
+    for (int k = threadIdx.x; k < 256; k += blockDim.x) sQ[k] = qTab[k];
+    __syncthreads();
+
+    const int tile = tileOrder ? tileOrder[tileBase + blockIdx.x] : (int)blockIdx.x;
+    const int i = tile * TILE + threadIdx.x;
+    const int ii = i < nIon ? i : 0;
+    const double4 pi = ldPos(pos + ii);
+    const uint64_t wi = (uint64_t)__double_as_longlong(pi.w);
+    const bool live = i < nIon && !(wi >> 63);
+    const int ti = (int)(wi & 0xff);
+    const double qi = sQ[(wi >> 8) & 0xff];
+    const double kqi = pc.keR * qi;
+    const bool charged = kqi != 0.0;
+    const double2 *ljRow = sLJ + ti * pc.ntypes;
+    int binLimit = 0;
+    {
+        unsigned long long db = dmax2[0];
+        if (withGhosts) db = max(db, dmax2[1]);
+        const double dmax = sqrt(__longlong_as_double((long long)db));
+        const double di = (live && dispOfSlot) ? fmin((double)dispOfSlot[ii], dmax) : dmax;
+        const double lim = (pc.rmax + pc.listSlack + dmax + di) * (1.0 + 1e-12);
+#pragma unroll
+        for (int e = 0; e < NBINS - 1; e++) binLimit += (pc.binEdge[e] < lim) ? 1 : 0;
+    }
+    const int n = live ? (int)cum[(size_t)binLimit * nPad + ii] : 0;
+    int nmax = n;
+    for (int o = 16; o > 0; o >>= 1) nmax = max(nmax, __shfl_xor_sync(0xffffffffu, nmax, o));
+
+    double fxi = 0.0, fyi = 0.0, fzi = 0.0;
+    double eLJ = 0.0, eEle = 0.0, vxx = 0.0, vyy = 0.0, vzz = 0.0, vxy = 0.0, vxz = 0.0, vyz = 0.0;
+    const double twoKrf = 2.0 * pc.krf;
+
+    const uint32_t *row = nbr + ii;
+    uint32_t eNext[NPF];
+#pragma unroll
+    for (int u = 0; u < NPF; u++) eNext[u] = (u < n) ? row[(size_t)u * nPad] : 0u;
+    for (int k0 = 0; k0 < nmax; k0 += NPF)
+    {
+        uint32_t eCur[NPF];
+        double4 pCur[NPF];      // only read where the lane still has an entry (k0 + u < n)
+#pragma unroll
+        for (int u = 0; u < NPF; u++)
+        {
+            eCur[u] = eNext[u];
+            // lanes past the end of their own row issue no load at all (a dummy gather would still cost an L1 tag lookup)
+            if (k0 + u < n) pCur[u] = ldPos(pos + (eCur[u] & 0x07ffffffu));
+        }
+#pragma unroll
+        for (int u = 0; u < NPF; u++) eNext[u] = (k0 + NPF + u < n) ? row[(size_t)(k0 + NPF + u) * nPad] : 0u;
+#pragma unroll
+        for (int u = 0; u < NPF; u++)
+        {
+            const bool have = k0 + u < n;
+            const double4 pj = pCur[u];
+            double x = pi.x - pj.x, y = pi.y - pj.y, z = pi.z - pj.z;
+            double r2 = x * x + y * y + z * z;
+            if (have && r2 > pc.R2cut)
+            {
+                // nearestImage_fast: one lattice reduction per component (src/preduce.c:147-160)
+                if (x > pc.hhx) x -= pc.hxx;
+                if (x < -pc.hhx) x += pc.hxx;
+                if (y > pc.hhy) y -= pc.hyy;
+                if (y < -pc.hhy) y += pc.hyy;
+                if (z > pc.hhz) z -= pc.hzz;
+                if (z < -pc.hhz) z += pc.hzz;
+                r2 = x * x + y * y + z * z;
+            }
+            if (have && r2 < pc.rc2)
+            {
+                const uint64_t wj = (uint64_t)__double_as_longlong(pj.w);
+                const bool excl = (eCur[u] & EXCL_BIT) != 0u;
+                const double ir1 = rsqrtFast(r2);
+                const double ir2 = ir1 * ir1;
+                double dvdr = 0.0;
+                if (!excl)
+                {
+                    // Lennard-Jones: 4 eps (s12 - s6) + shift ; dvdr = 24 eps (s6 - 2 s12)/r^2 (src/bioMartini.c:1073-1080)
+                    const double2 cc = ljRow[wj & 0xff];
+                    const double ir6 = ir2 * ir2 * ir2;
+                    const double a6 = cc.x * ir6, a12 = cc.y * ir6 * ir6;
+                    dvdr = (a6 - a12) * ir2;
+                    if (ENERGY) eLJ += (a12 * (1.0 / 12.0) - a6 * (1.0 / 6.0)) + sShift[ti * pc.ntypes + (int)(wj & 0xff)];
+                }
+                if (charged)
+                {
+                    const double kqij = kqi * sQ[(wj >> 8) & 0xff];
+                    // reaction field (src/bioMartini.c:1082-1085); pruned pairs keep only krf r^2 - crf (:1172-1174)
+                    const double ir = excl ? 0.0 : ir1;
+                    dvdr += kqij * (twoKrf - ir2 * ir);
+                    if (ENERGY) eEle += kqij * (ir + pc.krf * r2 - pc.crf);
+                }
+                const double fxij = -dvdr * x, fyij = -dvdr * y, fzij = -dvdr * z;
+                fxi += fxij;
+                fyi += fyij;
+                fzi += fzij;
+                if (ENERGY)
+                {
+                    vxx += fxij * x;
+                    vyy += fyij * y;
+                    vzz += fzij * z;
+                    vxy += fxij * y;
+                    vxz += fxij * z;
+                    vyz += fyij * z;
+                }
+            }
+        }
+    }
+    if (live)
+    {
+        fx[i] = fxi;
+        fy[i] = fyi;
+        fz[i] = fzi;
+    }
+    if (ENERGY)
+    {
+        double v[8] = {0.5 * eLJ, 0.5 * eEle + (live ? -0.5 * qi * qi * pc.keR * pc.crf : 0.0),
+                       0.5 * vxx, 0.5 * vyy, 0.5 * vzz, 0.5 * vxy, 0.5 * vxz, 0.5 * vyz};
+        __shared__ double red[8][TILE / 32];
+#pragma unroll
+        for (int a = 0; a < 8; a++)
+        {
+            double t = v[a];
+            for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+            if ((threadIdx.x & 31) == 0) red[a][threadIdx.x >> 5] = t;
+        }
+        __syncthreads();
+        if (threadIdx.x < 8)
+        {
+            double t = 0.0;
+            for (int w = 0; w < TILE / 32; w++) t += red[threadIdx.x][w];
+            accPartial[(size_t)tile * 8 + threadIdx.x] = t;
+        }
+    }
+}
