@@ -1324,7 +1324,8 @@ extern "C" int ddcb200_ddcenergy(ddcb200_ctx *c, int withEnergy)
             if (c->pairVariant >= 0)
             {
                 const PairVariant &pv = g_pairVariants[c->pairVariant];
-                LAUNCH(withEnergy ? pv.energy : pv.force, nTiles, TILE, smem, st)(nLocal, nPad, order, base, c->pos4[cur].p, c->nbr.p, c->nbrCum.p,
+                const PairKernel kern = withEnergy ? pv.energy : pv.force;
+                LAUNCH(kern, nTiles, TILE, smem, st)(nLocal, nPad, order, base, c->pos4[cur].p, c->nbr.p, c->nbrCum.p,
                                                                                  c->dmax2, withGhosts, disp, c->ljTab.p, c->shiftTab.p, c->qTab.p,
                                                                                  c->pc, c->frc[0].p, c->frc[1].p, c->frc[2].p, c->pairPartial.p);
             }
