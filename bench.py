@@ -5,14 +5,15 @@
 
 A "step" is one nglf velocity-Verlet MD step (dt = 20 fs) of the synthetic Martini membrane
 named in config.workload: list rebuild every 20 steps, non-bonded + bonded forces,
-integrate.  `value` = steps/s with the state resident in HBM, timed with CUDA events on the
+integrate.  Before the warm-up the deck is brought to 310 K (untimed set-up).  `value` = steps/s with the state resident in HBM, timed with CUDA events on the
 stream the kernels are launched on; `e2e` = the same through the reference-facing call
 sequence with HOST buffers (sendState H2D from pinned memory, then nglf(1) + energyInfo D2H
 every step = the shipped deck's printrate=1, then getState D2H).  The `roofline` object is
 for the dominant kernel (k_pair); `cpu_baseline` times the UNMODIFIED reference CPU path
 (oracle/_ref) on a bounded sample of the same membrane.
 
---impl reference times only the reference CPU path (no GPU work).
+--impl reference times only the reference CPU path (no GPU work): the same full deck, one single-rank
+instance per host core.
 """
 import argparse
 import json
@@ -125,27 +126,49 @@ def host_cores():
     return max(1, min(n, int(os.environ.get("DDCB200_CPU_RANKS", "64"))))
 
 
-def run_reference(workload_n, steps, warmup, procs=None):
-    """Reference CPU path (oracle/_ref/ref_dump = the unmodified ddcMD objects) on the bounded sample.
+def mem_available_gb():
+    try:
+        for line in open("/proc/meminfo"):
+            if line.startswith("MemAvailable:"):
+                return int(line.split()[1]) / 1048576.0
+    except Exception:
+        pass
+    return 64.0
+
+
+def run_reference(deck_name, deck_kwargs, steps, warmup, procs=None, gb_per_proc=0.0, scale_to=None):
+    """Reference CPU path (oracle/_ref/ref_dump = the unmodified ddcMD objects) on a deck of this repo's generator.
 
     ddcMD's CPU parallelism is MPI ranks over spatial domains; the image has no MPI runtime (the oracle links a single-rank
-    shim), so "all the host cores" is emulated by running one single-rank instance per core CONCURRENTLY, each on its own
-    copy of the sample patch, and adding up their bead-steps per second.  That is what a perfectly load-balanced MPI run
-    with free halo exchange would reach on these cores - an upper bound for the reference, i.e. a conservative baseline."""
+    shim), so "all the host cores" means one single-rank instance per core running CONCURRENTLY, each on the whole deck, and
+    the aggregate is instances x steps / time: the throughput of that many independent replicas, which an MPI run of ONE
+    system on the same cores cannot exceed (it adds halo exchange and imbalance) - an upper bound for the reference, i.e. a
+    conservative baseline.  The slowest single instance is reported as well (`single_instance`)."""
     import shutil
     ref = os.path.join(ROOT, "oracle", "_ref", "ref_dump")
     if not os.path.exists(ref):
         raise RuntimeError("oracle/_ref/ref_dump is missing (run oracle/build_ref.sh in the build container)")
     from refdump import read_records
-    path = get_deck("cpu_sample", CPU_SAMPLE)
+    path = get_deck(deck_name, deck_kwargs)
     procs = procs or host_cores()
+    if gb_per_proc > 0.0:
+        procs = max(1, min(procs, int(mem_available_gb() * 0.8 / gb_per_proc)))
     n_steps = max(2, steps + warmup)
     dirs = []
     for p in range(procs):
         d = path if p == 0 else "%s.rank%d" % (path, p)
         if p > 0 and not os.path.exists(os.path.join(d, "object.data")):
+            # a private run directory per instance (ddcMD writes into its cwd); the atoms file is shared read-only
             shutil.rmtree(d, ignore_errors=True)
-            shutil.copytree(path, d, symlinks=True, ignore=shutil.ignore_patterns("_bench.*", "snapshot.0*", "data", "*.rank*"))
+            os.makedirs(d)
+            for f in os.listdir(path):
+                if f.startswith(("_bench", "snapshot.0", "data", "ddcMD", "hpm", "profile")) or ".rank" in f:
+                    continue
+                src = os.path.join(path, f)
+                if os.path.isdir(src) and not os.path.islink(src):
+                    os.symlink(src, os.path.join(d, f))
+                else:
+                    shutil.copy2(src, os.path.join(d, f), follow_symlinks=False)
         dirs.append(d)
     t = time.time()
     running = [subprocess.Popen(["bash", "-c", "ulimit -s unlimited; exec '%s' '%s' %d 0 light" % (ref, os.path.join(d, "_bench.bin"), n_steps)],
@@ -154,17 +177,50 @@ def run_reference(workload_n, steps, warmup, procs=None):
     wall_total = time.time() - t
     if any(codes):
         raise RuntimeError("reference run failed (exit codes %s, see %s/_bench.log)" % (codes, path))
-    bead_steps_per_s = 0.0
+    steps_per_s, slowest = 0.0, None
     for d in dirs:
         r = read_records(os.path.join(d, "_bench.bin"))
         wall = r["wall"]
-        n_sample = int(r["nion"][0])
+        n_deck = int(r["nion"][0])
         w = min(warmup, len(wall) - 1)
         t_timed = wall[-1] - (wall[w - 1] if w > 0 else 0.0)
         k = len(wall) - w
-        bead_steps_per_s += k * n_sample / t_timed
-    return {"n_sample": n_sample, "steps_timed": k, "wall_total_s": wall_total, "procs": procs,
-            "value": bead_steps_per_s / workload_n, "us_per_bead_step": 1e6 * procs / bead_steps_per_s}
+        steps_per_s += k / t_timed
+        slowest = k / t_timed if slowest is None else min(slowest, k / t_timed)
+    scale = (n_deck / float(scale_to)) if scale_to else 1.0          # a smaller patch of the same recipe: cost is linear in beads
+    return {"n_deck": n_deck, "steps_timed": k, "wall_total_s": wall_total, "procs": procs, "value": steps_per_s * scale,
+            "single_instance": slowest * scale, "us_per_bead_step": 1e6 * procs / (steps_per_s * n_deck)}
+
+
+def static_config(workload, world):
+    """The same dictionary in both arms: what is run, not how it went."""
+    from ddcmd_b200 import synth
+    desc = synth.CONFIGS[workload][1]
+    return {"workload": "%s: %s; NGLF dt=20fs, cutoff 11 A + 4 A skin, list rebuild every 20 steps; equilibrated to 310 K before timing"
+                        % (workload, desc),
+            "l2": "inputs larger than L2: the neighbor list alone is 4 B x ~100 entries per bead (403 MB at 1M beads vs 126 MB of L2), "
+                  "re-read every step",
+            "ranks": world}
+
+
+def equilibrate(sim, dd, rounds=8, steps=100, target_K=310.0):
+    """The generated membranes start from a lattice and heat up while they relax; the timed region should see the deck at
+    its working temperature (the displacement bound of the list walk depends on it).  Untimed set-up: blocks of `steps`
+    NGLF steps, after each of which the velocities are rescaled to target_K through the public getState / sendState calls."""
+    kelvin = dd.units_convert(1.0, "K", None)
+    temps = []
+    for _ in range(rounds):
+        sim.nglf(steps)
+        e = sim.energyInfo()
+        T = e.temperature / kelvin
+        temps.append(T)
+        st = sim.getState()
+        f = (target_K / T) ** 0.5
+        beads = sim.getLocalBeads() if sim.nranks > 1 else None
+        sim.sendState(st["rx"], st["ry"], st["rz"], st["vx"] * f, st["vy"] * f, st["vz"] * f, loop=int(e.loop), time=float(e.time), bead=beads)
+    sim.nglf(steps)
+    temps.append(sim.energyInfo().temperature / kelvin)
+    return temps
 
 
 def main():
@@ -175,29 +231,35 @@ def main():
     ap.add_argument("--impl", default="ours")
     ap.add_argument("--workload", default="membrane_1m")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-equilibration", action="store_true")
+    ap.add_argument("--equil-rounds", type=int, default=8)
+    ap.add_argument("--equil-steps", type=int, default=100)
+    ap.add_argument("--weak", default="auto", help="also run this workload for the weak-scaling record (auto: membrane_10m on 8 ranks, none elsewhere)")
     ap.add_argument("--kernels-only", action="store_true", help="profiler runs: warm-up + timed steps, then exit (no e2e, no CPU baseline)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
-    from ddcmd_b200 import synth
-    desc = synth.CONFIGS[args.workload][1]
-    config = {"workload": "%s: %s; NGLF dt=20fs, cutoff 11 A + 4 A skin, rebuild every 20 steps" % (args.workload, desc),
-              "l2": "inputs larger than L2: the neighbor list alone is 4 B x ~100 entries per bead (403 MB at 1M beads vs 126 MB of L2), "
-                    "re-read every step"}
+    config = static_config(args.workload, max(world, args.gpus))
 
     if args.impl == "reference":
         if rank != 0:
             return
-        n_full = synth.make(args.workload).n        # bead count of the workload (the generator takes seconds; nothing is written)
-        r = run_reference(n_full, max(2, min(args.steps, 40)), min(args.warmup, 5))
+        # the real deck of the workload, one instance per host core as far as the memory goes (about 3 GB per million beads)
+        from ddcmd_b200 import synth
+        n_full = synth.make(args.workload).n
+        K, W = max(2, min(args.steps, 40)), max(1, min(args.warmup, 5))
+        r = run_reference(args.workload, None, K, W, gb_per_proc=3.0 * n_full / 1e6)
         line = {"impl": "reference", "metric": "Martini MD steps/s (20 fs)", "value": r["value"], "unit": "steps/s", "n_gpus": args.gpus,
-                "steps": r["steps_timed"], "warmup": min(args.warmup, 5), "ms_per_step": 1e3 / r["value"], "higher_is_better": True,
+                "steps": r["steps_timed"], "warmup": W, "ms_per_step": 1e3 / r["value"], "higher_is_better": True,
                 "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config,
                 "cpu_baseline": {"value": r["value"], "unit": "steps/s", "cores": r["procs"], "kind": "reference",
-                                 "sample": "%d concurrent single-rank instances (one per host core; no MPI runtime in the image) of oracle/_ref = the unmodified ddcMD CPU "
-                                           "path, each %d steps of a %d-bead patch of the same membrane recipe; their bead-steps/s are summed and scaled by bead "
-                                           "count to the %d-bead workload (cost is linear in beads: %.2f core-us/bead-step) - the throughput of an ideally balanced "
-                                           "MPI run with free halo exchange" % (r["procs"], r["steps_timed"], r["n_sample"], n_full, r["us_per_bead_step"])},
+                                 "sample": "%d concurrent single-rank instances (one per host core; the image has no MPI runtime) of oracle/_ref = the unmodified "
+                                           "ddcMD CPU path, each running %d timed steps of the full %d-bead deck of config.workload; value = instances x steps / "
+                                           "time (independent replicas: an upper bound for an MPI run of one system on these cores; the deck runs as generated - the CPU "
+                                           "path walks its whole list at a fixed rebuild rate, so its cost does not depend on the temperature); one instance alone: "
+                                           "%.4f steps/s (%.2f core-us/bead-step)" % (r["procs"], r["steps_timed"], r["n_deck"], r["single_instance"],
+                                                                                        r["us_per_bead_step"])},
+                "single_instance_steps_per_s": r["single_instance"],
                 "e2e": {"value": r["value"], "unit": "steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
                 "ns_per_day": r["value"] * DT_FS * 86400 * 1e-6}
         print(json.dumps(line))
@@ -208,14 +270,11 @@ def main():
     nccl_id = None
     local = int(os.environ.get("LOCAL_RANK", rank))
     if world > 1:
-        # host-side plumbing only (barriers, the NCCL id, max over ranks): gloo.  The data path - ghost halo,
-        # re-domain, energyInfo all-reduce - is NCCL inside libddcmd_b200.so.
+        # host-side plumbing only (barriers, the NCCL id, max over ranks): gloo.  The data path - migration, ghost lists, ghost
+        # halo, energyInfo all-reduce - is NCCL inside libddcmd_b200.so.
         import torch
         import torch.distributed as dist
         dist.init_process_group("gloo")
-        ident = [dd.nccl_unique_id() if rank == 0 else None]
-        dist.broadcast_object_list(ident, src=0)
-        nccl_id = ident[0]
 
     def barrier():
         if dist is not None:
@@ -228,48 +287,73 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t[0])
 
-    # W warm-up steps as asked (at least 3).  Before them, as part of set-up, enough steps (61 = rebuilds at loops 0, 20, 40, 60)
-    # for the library to have timed both list builds twice and settled on one, so the choice is made outside warm-up and timing
-    K, W = args.steps, max(3, args.warmup)
-    setup_steps = 0
-    if rank == 0:
-        deck_path = get_deck(args.workload)
-    barrier()
-    deck_path = get_deck(args.workload)
-    t = time.time()
-    deck = dd.Deck(os.path.join(deck_path, "object.data"))
-    n = deck.n
-    log("[bench] rank %d deck parsed: %d beads, %d bonded terms in %.1fs" % (rank, n, deck.s.nTerms, time.time() - t))
-    lattice = dd.default_lattice(world, [deck.s.params.h[0], deck.s.params.h[4], deck.s.params.h[8]]) if world > 1 else (1, 1, 1)
-    sim = dd.Simulate(deck, device=local, rank=rank, nranks=world, lattice=lattice, nccl_id=nccl_id)
-    if os.environ.get("DDCB200_BENCH_RETRY"):
-        config["fallback"] = "first attempt failed; this run uses DDCB200_LISTBUILD=twopass DDCB200_WALK=global"
-    config["parallelism"] = "ddc bricks %dx%dx%d, one process per GPU, ghost halo per step over NCCL" % lattice if world > 1 else "single GPU"
+    def measure(workload, K, W, full):
+        """device-resident throughput of one workload; full = also the per-kernel profile"""
+        ident = None
+        if world > 1:
+            ident = [dd.nccl_unique_id() if rank == 0 else None]
+            dist.broadcast_object_list(ident, src=0)
+            ident = ident[0]
+        if rank == 0:
+            get_deck(workload)
+        barrier()
+        deck_path = get_deck(workload)
+        t = time.time()
+        deck = dd.Deck(os.path.join(deck_path, "object.data"))
+        log("[bench] rank %d %s parsed: %d beads, %d bonded terms in %.1fs" % (rank, workload, deck.n, deck.s.nTerms, time.time() - t))
+        lattice = dd.default_lattice(world, [deck.s.params.h[0], deck.s.params.h[4], deck.s.params.h[8]]) if world > 1 else (1, 1, 1)
+        sim = dd.Simulate(deck, device=local, rank=rank, nranks=world, lattice=lattice, nccl_id=ident)
+        out = {"beads": deck.n, "bonded_terms": int(deck.s.nTerms), "lattice": list(lattice)}
+        if not args.no_equilibration:
+            temps = equilibrate(sim, dd, args.equil_rounds, args.equil_steps)
+            out["equilibration_T_K"] = [round(x, 1) for x in temps]
+        sim.nglf(W)
+        sim.sync()
+        l0 = sim.kernelLaunches()
+        clocks = ClockSampler(local)
+        clocks.start()
+        time.sleep(0.3)
+        barrier()
+        sim.sync()
+        sim.timerRecord(0)
+        sim.nglf(K)
+        sim.timerRecord(1)
+        sim.sync()
+        barrier()
+        ms = max_over_ranks(sim.timerElapsed(0, 1))      # device time on the launching stream, max over ranks
+        out["launches"] = sim.kernelLaunches() - l0
+        out["clocks"] = clocks.finish()
+        out["ms"] = ms
+        out["steps_per_s"] = K / (ms * 1e-3)
+        e = sim.energyInfo()
+        out["T_K"] = e.temperature / dd.units_convert(1.0, "K", None)
+        out["pairs_listed"] = int(e.nPairsListed)
+        if rank == 0:
+            log("[bench] %s: %d steps in %.2f ms -> %.1f steps/s; T=%.1f K" % (workload, K, ms, out["steps_per_s"], out["T_K"]))
+        # a longer window (20 rebuilds) for the record when the asked one is short
+        if full and K < 400:
+            barrier()
+            sim.sync()
+            sim.timerRecord(2)
+            sim.nglf(400)
+            sim.timerRecord(3)
+            sim.sync()
+            barrier()
+            ms_long = max_over_ranks(sim.timerElapsed(2, 3))
+            out["long_run"] = {"steps": 400, "steps_per_s": 400 / (ms_long * 1e-3), "ms_per_step": ms_long / 400}
+        return sim, deck, out, e
 
-    # ---- device-resident throughput ------------------------------------------------------
-    if setup_steps:
-        sim.nglf(setup_steps)
-        config["setup"] = "%d untimed set-up steps before the warm-up (the library times its two list builds on the first four rebuilds)" % setup_steps
-    sim.nglf(W)
-    sim.sync()
-    l0 = sim.kernelLaunches()
-    clocks = ClockSampler(local)
-    clocks.start()
-    time.sleep(0.3)
-    barrier()
-    sim.sync()
-    sim.timerRecord(0)
-    sim.nglf(K)
-    sim.timerRecord(1)
-    sim.sync()
-    barrier()
-    ms = max_over_ranks(sim.timerElapsed(0, 1))      # device time on the launching stream, max over ranks
-    launches = sim.kernelLaunches() - l0
-    clk = clocks.finish()
-    e = sim.energyInfo()
-    sps = K / (ms * 1e-3)
-    if rank == 0:
-        log("[bench] %d steps in %.2f ms -> %.1f steps/s; T=%.1f K" % (K, ms, sps, e.temperature / dd.units_convert(1.0, "K", None)))
+    K, W = args.steps, max(3, args.warmup)
+    sim, deck, res, e = measure(args.workload, K, W, True)
+    n = deck.n
+    lattice = tuple(res["lattice"])
+    ms, sps, launches, clk = res["ms"], res["steps_per_s"], res["launches"], res["clocks"]
+    run_info = {"beads": n, "bonded_terms": res["bonded_terms"], "pairs_listed": res["pairs_listed"], "temperature_K": round(res["T_K"], 1),
+                "equilibration_T_K": res.get("equilibration_T_K"), "long_run": res.get("long_run"),
+                "parallelism": "ddc bricks %dx%dx%d, one process per GPU; migration + ghost lists every 20 steps and the per-step ghost halo "
+                               "over NCCL (halo on its own stream beside the rows that read no ghost)" % lattice if world > 1 else "single GPU"}
+    if os.environ.get("DDCB200_BENCH_RETRY"):
+        run_info["fallback"] = "first attempt failed; this run uses DDCB200_PAIR=old DDCB200_WALK=global"
 
     if args.kernels_only:
         sim.profile(True)
@@ -278,7 +362,7 @@ def main():
         prof = sim.profileRead(reset=True)
         if rank == 0:
             print(json.dumps({"steps_per_s": sps, "ms_per_step": ms / K, "gpu_launches": int(launches), "clocks": clk,
-                              "variant": os.environ.get("DDCB200_PAIR", "default"),
+                              "variant": os.environ.get("DDCB200_PAIR", "default"), "T_K": res["T_K"], "long_run": res.get("long_run"),
                               "per_kernel_ms_per_step": {k: v[0] / 40 for k, v in prof.items()},
                               "list_build_ms": sim.listBuildInfo()[1][0]}))
         sim.close()
@@ -291,25 +375,26 @@ def main():
     sim.nglf(KP)
     prof = sim.profileRead(reset=True)
     sim.profile(False)
-    pair_ms = prof["pair"][0] / max(1, prof["pair"][1])
+    pair_ms = prof["pair"][0] / KP                      # per step (on several ranks the rows run as two launches)
     total_prof = sum(v[0] for v in prof.values())
     lb_variant, lb_ms = sim.listBuildInfo()
-    # ALGORITHMIC bytes of one k_pair launch on this rank (DESIGN.md "k_pair"): one 32-byte position record per resident
-    # bead + one 24-byte force per local bead + 4 bytes per stored list entry (full list = 2 x the half-list pairs;
-    # at N > 1 the entries are taken as evenly split over the ranks)
+    # ALGORITHMIC bytes of the pair kernel per step on this rank, SURVEY 8(d): N (24 r + 4 type + 8 q) read + N 24 f written +
+    # 4 bytes per pair of the HALF list (P = the reference's pair count) = 60 N + 4 P.  What the kernel really streams is more:
+    # it stores the full list (every pair from both ends, so that forces need no atomics and no force back-communication):
+    # stored_bytes = 56 N + 8 P.  Both are reported; frac uses the SURVEY figure.  (N > 1: beads and pairs taken as evenly split)
     n_loc = int(sim.numLocal())
-    entries = 2 * int(e.nPairsListed) // world
-    alg_bytes = n_loc * (32 + 24) + 4 * entries
+    pairs = int(e.nPairsListed) // world
+    alg_bytes = 60 * n_loc + 4 * pairs
+    stored_bytes = 56 * n_loc + 8 * pairs
     peak, peak_kind = measured_peaks()
     achieved = alg_bytes / (pair_ms * 1e-3) / 1e9
-    # dram bytes of the committed ncu capture: only meaningful for the workload and GPU count it was taken on
-    traffic = ncu_traffic("k_pair") if (args.workload == "membrane_1m" and world == 1) else None
-    roofline = {"bound": "hbm", "kernel": "k_pair", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+    traffic = ncu_traffic("k_pair2") if (args.workload == "membrane_1m" and world == 1) else None
+    roofline = {"bound": "hbm", "kernel": "k_pair2", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": traffic["bytes_per_launch"] if traffic else None, "traffic_source": traffic["source"] if traffic else None,
-                "peak_kind": peak_kind, "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms": pair_ms,
+                "peak_kind": peak_kind, "algorithmic_bytes_per_launch": alg_bytes, "stored_bytes_per_launch": stored_bytes,
+                "achieved_stored": stored_bytes / (pair_ms * 1e-3) / 1e9, "kernel_ms": pair_ms,
                 "kernel_share_of_step": prof["pair"][0] / total_prof,
                 "per_kernel_ms_per_step": {k: v[0] / KP for k, v in prof.items()},
-                # list build picked by timing the first four rebuilds (rows are bit-identical either way): ms per rebuild
                 "list_build": {"last_build_ms": lb_ms[0]}}
 
     # ---- end to end through the reference-facing calls with host buffers ---------------------
@@ -324,10 +409,11 @@ def main():
     KE = K
     pinned_out = torch.empty(9 * n, dtype=torch.float64).pin_memory()      # room for every bead: on several ranks the locals migrate
     host_flat = pinned_out.numpy()
+    ee = sim.energyInfo()
     sim.sync()
     barrier()
     t0 = time.perf_counter()
-    sim.sendState(host[0], host[1], host[2], host[3], host[4], host[5], loop=int(e.loop), time=float(e.time),
+    sim.sendState(host[0], host[1], host[2], host[3], host[4], host[5], loop=int(ee.loop), time=float(ee.time),
                   bead=beads if world > 1 else None)
     for _ in range(KE):
         sim.nglf(1)
@@ -338,7 +424,8 @@ def main():
     t1 = time.perf_counter()
     e2e_sps = KE / max_over_ranks(t1 - t0)
     e2e = {"value": e2e_sps, "unit": "steps/s", "h2d_bytes_per_step": 6 * 8 * n / KE, "d2h_bytes_per_step": 9 * 8 * n / KE + 24 * 8 * world,
-           "steps": KE, "note": "sendState(H2D, pinned) + per step [nglf(1) + energyInfo D2H] (printrate=1) + getState(D2H); bytes summed over ranks"}
+           "steps": KE, "note": "sendState(H2D, pinned) + per step [nglf(1) + energyInfo D2H] (printrate=1) + getState(D2H); bytes summed over ranks; "
+                                "MD keeps the state on the device between prints, so the state copies are per run; plugin_seam has them per step"}
     # ---- the same through the plug-in seam of a host-side integrator (eval_potential, integration/ddcmd_shim.c mode 1): every step
     # uploads positions and velocities from pinned host memory, evaluates forces + energies, reads the forces and energyInfo back
     if world == 1:
@@ -363,25 +450,42 @@ def main():
                               "note": "per step: updateState(H2D r, v, pinned) + ddcenergy + energyInfo(D2H) + forces(D2H, pinned) = the eval_potential seam "
                                       "with ddcMD's own integrator on the host; the list is rebuilt every 20 loops as in a device-resident run"}
     sim.close()
+    del sim
+
+    # ---- weak-scaling record: BASELINE.json's 10M-bead membrane on 8 GPUs (1.25M beads per GPU, the single-GPU size) --------
+    weak = None
+    weak_name = ("membrane_10m" if world == 8 and args.workload == "membrane_1m" else None) if args.weak == "auto" else (None if args.weak == "none" else args.weak)
+    if weak_name:
+        try:
+            simw, deckw, resw, ew = measure(weak_name, max(K, 40), W, False)
+            simw.close()
+            weak = {"workload": weak_name, "beads": deckw.n, "n_gpus": world, "steps": max(K, 40), "steps_per_s": resw["steps_per_s"],
+                    "ms_per_step": resw["ms"] / max(K, 40), "bead_steps_per_s": resw["steps_per_s"] * deckw.n,
+                    "single_gpu_bead_steps_per_s": sps * n if world == 1 else None, "T_K": round(resw["T_K"], 1), "lattice": resw["lattice"],
+                    "note": "weak-scaling efficiency = bead_steps_per_s / (n_gpus x bead-steps/s of the 1-GPU run of this bench on ~1M beads)"}
+        except Exception as ex:      # the record is extra: the headline line must not depend on it
+            weak = {"workload": weak_name, "failed": str(ex)[:300]}
     if rank != 0:
         return
 
     cpu = None
     if not args.no_cpu_baseline and world == 1:
         try:
-            r = run_reference(n, 30, 5)
+            r = run_reference("cpu_sample", CPU_SAMPLE, 30, 5, scale_to=n)
             cpu = {"value": r["value"], "unit": "steps/s", "cores": r["procs"], "kind": "reference",
                    "sample": "%d concurrent single-rank instances (one per host core) of oracle/_ref (unmodified ddcMD CPU path), each %d steps of a %d-bead patch "
-                             "of the same membrane recipe; summed bead-steps/s scaled by bead count to %d beads (%.2f core-us/bead-step)" % (
-                                 r["procs"], r["steps_timed"], r["n_sample"], n, r["us_per_bead_step"])}
+                             "of the same membrane recipe; summed steps/s scaled by bead count to %d beads (%.2f core-us/bead-step); bench.py --impl reference runs "
+                             "the full deck" % (r["procs"], r["steps_timed"], r["n_deck"], n, r["us_per_bead_step"])}
         except Exception as ex:  # the baseline is reported, never required for the GPU number
             cpu = {"value": None, "unit": "steps/s", "cores": host_cores(), "kind": "reference", "sample": "failed: %s" % ex}
 
     line = {"metric": "Martini MD steps/s (20 fs)", "value": sps, "unit": "steps/s", "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": ms / K, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
-            "data": "synthetic", "config": dict(config, beads=n, bonded_terms=int(deck.s.nTerms), pairs_listed=int(e.nPairsListed)),
+            "data": "synthetic", "config": config, "run_info": run_info,
             "ns_per_day": sps * DT_FS * 86400 * 1e-6, "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e,
             "gpu_launches": int(launches), "clocks": clk}
+    if weak:
+        line["weak_scaling"] = weak
     print(json.dumps(line))
 
 
@@ -389,14 +493,13 @@ if __name__ == "__main__":
     try:
         main()
     except Exception as ex:
-        # Single-GPU safety net: the list-build and walk variants added without a GPU at hand are result-neutral but had never run
-        # on a B200 when this was written.  If the run dies, repeat it ONCE in a fresh process (a CUDA error is sticky) with the
-        # variants that produced the committed profiles, and say so on stderr; the JSON line then carries config.fallback.
+        # Single-GPU safety net: if the run dies, repeat it ONCE in a fresh process (a CUDA error is sticky) with the round-1 pair
+        # kernel and walk bound, and say so on stderr; the JSON line then carries run_info.fallback.
         if int(os.environ.get("WORLD_SIZE", "1")) == 1 and "--impl" not in " ".join(sys.argv) and not os.environ.get("DDCB200_BENCH_RETRY"):
             import traceback
             traceback.print_exc()
-            log("[bench] run failed (%s); repeating once with DDCB200_LISTBUILD=twopass DDCB200_WALK=global" % ex)
-            env = dict(os.environ, DDCB200_BENCH_RETRY="1", DDCB200_WALK="global")
+            log("[bench] run failed (%s); repeating once with DDCB200_PAIR=old DDCB200_WALK=global" % ex)
+            env = dict(os.environ, DDCB200_BENCH_RETRY="1", DDCB200_PAIR="old", DDCB200_WALK="global")
             sys.stdout.flush()
             os.execve(sys.executable, [sys.executable] + sys.argv, env)
         raise

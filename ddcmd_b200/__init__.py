@@ -146,6 +146,7 @@ def _declare(L):
         "ddcb200_constraintFailures": (i64, [vp]),
         "ddcb200_getCells": (i32, [vp, pi, pi, pd]),
         "ddcb200_getPairs": (i64, [vp, i64, pi, pi, pi]),
+        "ddcb200_pairSetHash": (i32, [vp, _P(C.c_uint64)]),
         "ddcb200_profile": (i32, [vp, i32]),
         "ddcb200_profileRead": (i32, [vp, pd, _P(C.c_int64), i32]),
         "ddcb200_timerRecord": (i32, [vp, i32]),
@@ -189,7 +190,7 @@ EXPORTS = ["ddcb200_lastError", "ddcb200_deviceCount", "ddcb200_create", "ddcb20
            "ddcb200_profileRead", "ddcb200_timerRecord", "ddcb200_timerElapsed", "ddcb200_kernelLaunches", "ddcb200_lastListBuild", "ddcb200_ncclUniqueId", "ddcb200_ddcInit", "ddcb200_ddcPlan", "ddcb200_deckLoad", "ddcb200_deckFree",
            "ddcb200_lastHostError", "ddcb200_simulateBind", "ddcb200_simulateBindRank", "ddcb200_printinfoLine", "ddcb200_unitsConvert",
            "ddcb200_printinfoHeader", "ddcb200_writeRestart", "ddcb200_readCMDS", "ddcb200_simulateMaster", "ddcb200_listBuildInfo", "ddcb200_subsetWrite", "ddcb200_writeBXYZ", "ddcb200_pairCorrelation",
-           "ddcb200_pairCorrelationWrite", "ddcb200_kineticByClass"]
+           "ddcb200_pairCorrelationWrite", "ddcb200_kineticByClass", "ddcb200_pairSetHash"]
 
 
 def _arr(ptr, n, dtype):
@@ -445,6 +446,13 @@ class Simulate:
         pi = _P(C.c_int)
         L.ddcb200_getPairs(self.ctx, n, bi.ctypes.data_as(pi), bj.ctypes.data_as(pi), pr.ctypes.data_as(pi))
         return bi, bj, pr
+
+    def pairSetHash(self):
+        """(count, sum, xor) of the interacting list and of the pruned list: order-independent 64-bit hashes of the (gid, gid) pairs
+        this rank owns, comparable with oracle/ref_dump's "pairhash" record."""
+        h = np.zeros(6, np.uint64)
+        self._ck(lib().ddcb200_pairSetHash(self.ctx, h.ctypes.data_as(_P(C.c_uint64))))
+        return h
 
     def profile(self, enable=True):
         self._ck(lib().ddcb200_profile(self.ctx, int(enable)))

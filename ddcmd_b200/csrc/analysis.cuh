@@ -117,3 +117,56 @@ k_kinetic_classes(int nIon, const double4 *__restrict__ pos, const double *__res
         out[(size_t)cls * 12 + threadIdx.x] = t;
     }
 }
+
+
+// ---- parity hook: order-independent hash of the pair set ------------------------------------------------------------------
+// sum and xor (mod 2^64) of a 64-bit mix of (smaller gid, larger gid) over the pairs this rank owns (smaller gid local, as
+// pairlist1 reports them, src/pairlist.c:244,279), separately for the interacting and the pruned list: what the million-bead
+// parity test compares with the same numbers from the reference (oracle/ref_dump.c "hash").  out: count, sum, xor per list.
+__device__ __forceinline__ unsigned long long mix64(unsigned long long x)
+{
+    x ^= x >> 30; x *= 0xbf58476d1ce4e5b9ull;
+    x ^= x >> 27; x *= 0x94d049bb133111ebull;
+    x ^= x >> 31;
+    return x;
+}
+
+__global__ void k_pair_hash(int nIon, int nPad, const uint32_t *__restrict__ nbr, const int *__restrict__ count, const int *__restrict__ beadOfSlot,
+                            const uint64_t *__restrict__ gid, unsigned long long *__restrict__ out)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    unsigned long long h[6] = {0, 0, 0, 0, 0, 0};
+    if (i < nIon)
+    {
+        const int n = count[i];
+        const uint64_t gi = gid[beadOfSlot[i]];
+        for (int k = 0; k < n; k++)
+        {
+            const uint32_t e = nbr[(size_t)k * nPad + i];
+            const uint64_t gj = gid[beadOfSlot[e & 0x07ffffffu]];
+            if (gi < gj)
+            {
+                const unsigned long long v = mix64(mix64(gi) + 0x9e3779b97f4a7c15ull * gj);
+                const int l = (e & EXCL_BIT) ? 3 : 0;
+                h[l]++;
+                h[l + 1] += v;
+                h[l + 2] ^= v;
+            }
+        }
+    }
+#pragma unroll
+    for (int a = 0; a < 6; a++)
+    {
+        unsigned long long v = h[a];
+        for (int o = 16; o > 0; o >>= 1)
+        {
+            const unsigned long long w = __shfl_xor_sync(0xffffffffu, v, o);
+            v = (a % 3 == 2) ? (v ^ w) : (v + w);
+        }
+        if ((threadIdx.x & 31) == 0)
+        {
+            if (a % 3 == 2) atomicXor(&out[a], v);
+            else atomicAdd(&out[a], v);
+        }
+    }
+}

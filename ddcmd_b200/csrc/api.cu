@@ -199,7 +199,7 @@ struct PairVariant
     PairKernel force, energy;
 };
 #define PV(P, M) {P, M, k_pair2<false, P, M>, k_pair2<true, P, M>}
-static const PairVariant g_pairVariants[] = {PV(1, 1), PV(1, 12), PV(2, 1), PV(2, 8), PV(2, 10), PV(3, 8), PV(4, 1), PV(4, 8)};
+static const PairVariant g_pairVariants[] = {PV(1, 1), PV(2, 1), PV(2, 8), PV(3, 8), PV(4, 1)};      // measured: profiles/r02d_pair_variants.txt
 #undef PV
 static const int g_nPairVariants = (int)(sizeof(g_pairVariants) / sizeof(g_pairVariants[0]));
 
@@ -302,7 +302,7 @@ extern "C" void ddcb200_destroy(ddcb200_ctx *c)
     if (c->stream) cudaStreamSynchronize(c->stream);
     c->ljTab.release(); c->shiftTab.release(); c->qTab.release(); c->massOfBead.release(); c->wOfBead.release();
     c->gidOfBead.release(); c->molTypeOfBead.release(); c->molTypeSingle.release(); c->bpairOffset.release();
-    c->bpairKey.release(); c->termsBead.release(); c->restrBead.release(); c->bondCsrOff.release(); c->bondEnt.release(); c->bondRange.release(); c->bondRec.release(); c->bondCount.release(); c->bondStart.release();
+    c->bpairKey.release(); c->termsBead.release(); c->restrBead.release(); c->bondCsrOff.release(); c->bondEnt.release(); c->bondRec.release(); c->bondCount.release(); c->bondStart.release();
     c->restrParm.release(); c->molOffset.release(); c->molBeads.release();
     for (int k = 0; k < 2; k++)
     {
@@ -1024,6 +1024,9 @@ static int ensureBondCsr(ddcb200_ctx *c)
     }
     for (int64_t b = 0; b < nG; b++) off[(size_t)b + 1] += off[(size_t)b];
     if ((int64_t)off[(size_t)nG] < 0) return fail(DDCB200_ERR_CAPACITY, "too many bonded term entries");
+    for (int64_t b = 0; b < nG; b++)
+        if (off[(size_t)b + 1] - off[(size_t)b] > BONDED_SPILL)
+            return fail(DDCB200_ERR_CAPACITY, "a bead takes part in more than 256 bonded terms");
     std::vector<uint32_t> ent((size_t)off[(size_t)nG] + 1);
     std::vector<int> fill(off.begin(), off.end() - 1);
     for (size_t t = 0; t < c->hTerms.size(); t++)
@@ -1150,11 +1153,10 @@ extern "C" int ddcb200_constructList(ddcb200_ctx *c)
     }
     if (haveBonded)
     {
-        CK(c->bondRange.ensure((size_t)nPad));
-        CK(c->bondRec.ensure((size_t)c->gridHost->bondTotal + 1));
+        c->nBondRec = c->gridHost->bondTotal;
+        CK(c->bondRec.ensure((size_t)c->nBondRec + 1));
         LAUNCH(k_bond_resolve, (nIon + 255) / 256, 256, 0, st)(nIon, c->pos4[nxt].p, c->bondCsrOff.p, c->bondEnt.p, c->nTerms, c->termsBead.p,
-                                                           c->restrParm.p, c->slotOfBead.p, c->bondStart.p, c->bondCount.p, c->bondRange.p,
-                                                           c->bondRec.p);
+                                                           c->restrParm.p, c->slotOfBead.p, c->bondStart.p, c->bondCount.p, c->bondRec.p);
         CKL("k_bond_resolve");
     }
     if (c->nranks > 1)
@@ -1351,19 +1353,18 @@ extern "C" int ddcb200_ddcenergy(ddcb200_ctx *c, int withEnergy)
             rc = launchPair(tiles, nullptr, 0, 0);
         if (rc) return rc;
     }
-    const int64_t nb = c->nTerms + c->nRestr;
     int bBlocks = 0;
-    if (nb > 0)
+    if (c->nTerms + c->nRestr > 0 && c->nBondRec > 0)
     {
         ProfScope ps(c, PROF_BONDED);
-        bBlocks = (nLocal + BONDED_THREADS - 1) / BONDED_THREADS;
+        bBlocks = (c->nBondRec + BONDED_THREADS - 1) / BONDED_THREADS;
         CK(c->bondPartial.ensure((size_t)bBlocks * BONDED_ACC + 8));
         if (withEnergy)
-            LAUNCH(k_bonded<true>, bBlocks, BONDED_THREADS, 0, st)(nLocal, c->bondRange.p, c->bondRec.p, c->restrParm.p, c->restrOrigin,
-                                                               c->pos4[cur].p, c->pc, c->frc[0].p, c->frc[1].p, c->frc[2].p, c->bondPartial.p);
+            LAUNCH(k_bonded<true>, bBlocks, BONDED_THREADS, 0, st)(c->nBondRec, c->bondRec.p, c->restrParm.p, c->restrOrigin, c->pos4[cur].p, c->pc,
+                                                               c->frc[0].p, c->frc[1].p, c->frc[2].p, c->bondPartial.p);
         else
-            LAUNCH(k_bonded<false>, bBlocks, BONDED_THREADS, 0, st)(nLocal, c->bondRange.p, c->bondRec.p, c->restrParm.p, c->restrOrigin,
-                                                                c->pos4[cur].p, c->pc, c->frc[0].p, c->frc[1].p, c->frc[2].p, c->bondPartial.p);
+            LAUNCH(k_bonded<false>, bBlocks, BONDED_THREADS, 0, st)(c->nBondRec, c->bondRec.p, c->restrParm.p, c->restrOrigin, c->pos4[cur].p, c->pc,
+                                                                c->frc[0].p, c->frc[1].p, c->frc[2].p, c->bondPartial.p);
         CKL("k_bonded");
     }
     if (withEnergy)
@@ -1913,6 +1914,26 @@ extern "C" int64_t ddcb200_getPairs(ddcb200_ctx *c, int64_t capacity, int *beadI
             emit(i, (int)(e & 0x07ffffffu), (e & EXCL_BIT) != 0u);
         }
     return np;
+}
+
+extern "C" int ddcb200_pairSetHash(ddcb200_ctx *c, uint64_t out[6])
+{
+    if (!c || !out) return fail(DDCB200_ERR_ARG, "null argument");
+    if (!c->listValid) return fail(DDCB200_ERR_STATE, "no list built");
+    CK(cudaSetDevice(c->device));
+    struct Scratch
+    {
+        DevBuf<unsigned long long> h;
+        ~Scratch() { h.release(); }
+    } sc;
+    CK(sc.h.ensure(8));
+    CK(cudaMemsetAsync(sc.h.p, 0, 8 * sizeof(unsigned long long), c->stream));
+    LAUNCH(k_pair_hash, (int)((c->nIon + 255) / 256), 256, 0, c->stream)((int)c->nIon, (int)c->nPad, c->nbr.p, c->nbrCount.p, c->beadOfSlot[c->cur].p,
+                                                                     c->gidOfBead.p, sc.h.p);
+    CKL("k_pair_hash");
+    CK(cudaMemcpyAsync(out, sc.h.p, 6 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    return DDCB200_OK;
 }
 
 extern "C" int ddcb200_timerRecord(ddcb200_ctx *c, int which)

@@ -76,9 +76,9 @@ __device__ __forceinline__ void dihedral(V3 vij, V3 vjk, V3 vkl, double &ang, do
 #define BONDED_THREADS 128
 #define BONDED_ACC 11   // 0..5 virial (xx yy zz xy xz yz), 6 bond, 7 angle, 8 torsion, 9 improper, 10 restraint
 
-// Forces are GATHERED, not scattered: one thread per resident local bead walks the (static) list of bonded terms the
-// bead takes part in - entry = (term << 2 | role of this bead in the term), ascending term order - evaluates each term and
-// keeps only the force on its own bead.  A bond is therefore evaluated twice, an angle three times, a dihedral four times;
+// Forces are GATHERED, not scattered: every resident local bead has the (static) list of bonded terms it takes part in -
+// entry = (term << 2 | role of this bead in the term), ascending term order; each entry is evaluated for the force on that
+// one bead only, and a bead's entries are added up in their fixed order.  A bond is therefore evaluated twice, an angle three times, a dihedral four times;
 // in exchange there is no atomic and the summation order of every bead's force is fixed, so forces and energies are
 // bitwise reproducible run to run (the reference accumulates in owner order too, src/bioCharmmCovalent.c:95-251).
 // Energy and virial of a term are counted by the thread of its role-0 bead only.  At every list build the entries of the
@@ -130,12 +130,11 @@ k_scan_int(int n, const int *__restrict__ in, int *__restrict__ out, int *__rest
 __global__ void k_bond_resolve(int nIon, const double4 *__restrict__ pos, const int *__restrict__ csrOff, const uint32_t *__restrict__ ent,
                                int64_t nTerms, const Term *__restrict__ terms, const double *__restrict__ restrParm,
                                const int *__restrict__ slotOfBead, const int *__restrict__ start, const int *__restrict__ cnt,
-                               BondRange *__restrict__ range, BondRec *__restrict__ recs)
+                               BondRec *__restrict__ recs)
 {
     const int s = blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= nIon) return;
     const int n = cnt[s], lo = start[s];
-    range[s] = BondRange{lo, n};
     if (n == 0) return;
     const unsigned long long w = (unsigned long long)__double_as_longlong(pos[s].w);
     const int elo = csrOff[(int)((w >> 32) & 0x7fffffffull)];
@@ -144,7 +143,9 @@ __global__ void k_bond_resolve(int nIon, const double4 *__restrict__ pos, const 
         const uint32_t e = ent[elo + q];
         const int64_t t = (int64_t)(e >> 2);
         BondRec r;
-        r.role = (int)(e & 3u);
+        r.role = (short)(e & 3u);
+        r.q = (unsigned short)q;
+        r.n = (unsigned short)n;
         if (t >= nTerms)
         {
             // restraint (src/restraint.c:287-357): frac0[3] in p0..p2 is not enough room for its 7 parameters, so the record
@@ -161,33 +162,21 @@ __global__ void k_bond_resolve(int nIon, const double4 *__restrict__ pos, const 
             r.s[2] = tm.k >= 0 ? slotOfBead[tm.k] : 0;
             r.s[3] = tm.l >= 0 ? slotOfBead[tm.l] : 0;
             r.p0 = tm.p0; r.p1 = tm.p1; r.p2 = tm.p2;
-            r.kind = ((r.s[0] | r.s[1] | r.s[2] | r.s[3]) < 0) ? -1 : tm.kind;      // an endpoint is not resident on this rank
+            r.kind = (short)(((r.s[0] | r.s[1] | r.s[2] | r.s[3]) < 0) ? -1 : tm.kind);      // an endpoint is not resident on this rank
         }
         recs[lo + q] = r;
     }
     (void)restrParm;
 }
 
+// force of one record on its own bead (and, for the role-0 record of a term, the term's energy and virial into acc)
 template <bool ENERGY>
-__global__ void __launch_bounds__(BONDED_THREADS)
-k_bonded(int nIon, const BondRange *__restrict__ range, const BondRec *__restrict__ recs, const double *__restrict__ restrParm, int restrOrigin,
-         const double4 *__restrict__ pos, PairConst pc, double *__restrict__ fx, double *__restrict__ fy, double *__restrict__ fz,
-         double *__restrict__ partial)
+__device__ __forceinline__ V3 bondedEval(const BondRec &tm, const double *__restrict__ restrParm, int restrOrigin, const double4 *__restrict__ pos,
+                                         const PairConst &pc, double *acc)
 {
-    const int s = blockIdx.x * blockDim.x + threadIdx.x;
-    double acc[BONDED_ACC];
-#pragma unroll
-    for (int a = 0; a < BONDED_ACC; a++) acc[a] = 0.0;
-    const BondRange rg = s < nIon ? range[s] : BondRange{0, 0};
-    if (rg.n > 0)
-    {
-        V3 fs = V3{0.0, 0.0, 0.0};
-        for (int q = 0; q < rg.n; q++)
-        {
-            const BondRec tm = recs[rg.lo + q];
             const int role = tm.role;
             const bool count = ENERGY && role == 0;
-            if (tm.kind < 0) continue;
+            if (tm.kind < 0) return V3{0.0, 0.0, 0.0};
             if (tm.kind == 6)
             {
                 // restraint (src/restraint.c:287-357)
@@ -200,19 +189,18 @@ k_bonded(int nIon, const BondRange *__restrict__ range, const BondRec *__restric
                     z0 -= pc.hzz / 2.0;
                 }
                 const double kb = p[3];
-                const double4 ps = pos[s];
+                const double4 ps = pos[tm.s[0]];
                 V3 d = V3{ps.x - x0, ps.y - y0, ps.z - z0};
                 if ((p[4] > 0 && fabs(d.x) > pc.hhx) || (p[5] > 0 && fabs(d.y) > pc.hhy) || (p[6] > 0 && fabs(d.z) > pc.hhz)) d = minImage(d, pc);
                 const V3 cd = V3{p[4] * d.x, p[5] * d.y, p[6] * d.z};
                 const V3 f = vscale(cd, -2.0 * kb);
-                fs = V3{fs.x + f.x, fs.y + f.y, fs.z + f.z};
                 if (ENERGY)
                 {
                     acc[10] += kb * (cd.x * d.x + cd.y * d.y + cd.z * d.z);
                     acc[0] += f.x * cd.x; acc[1] += f.y * cd.y; acc[2] += f.z * cd.z;
                     acc[3] += f.x * cd.y; acc[4] += f.x * cd.z; acc[5] += f.y * cd.z;
                 }
-                continue;
+                return f;
             }
             const int si = tm.s[0], sj = tm.s[1], sk = tm.s[2], sl = tm.s[3];
             V3 f;
@@ -316,12 +304,73 @@ k_bonded(int nIon, const BondRange *__restrict__ range, const BondRec *__restric
                     for (int a = 0; a < 6; a++) acc[a] += vir[a] * kf;
                 }
             }
-            fs = V3{fs.x + f.x, fs.y + f.y, fs.z + f.z};
+            return f;
+}
+
+// One thread per RECORD (records of a bead are consecutive, beads in slot order): every thread evaluates its record, the forces
+// are staged in shared memory, and the thread of a bead's first record adds the bead's records up in their fixed order and
+// adds the sum to the slot's pair force - no atomic, one writer per slot.  A bead belongs to the CTA that holds its first
+// record; a CTA therefore also evaluates the up to BONDED_SPILL records of its last beads that lie beyond its 128.
+#define BONDED_SPILL 256
+template <bool ENERGY>
+__global__ void __launch_bounds__(BONDED_THREADS)
+k_bonded(int nRec, const BondRec *__restrict__ recs, const double *__restrict__ restrParm, int restrOrigin, const double4 *__restrict__ pos,
+         PairConst pc, double *__restrict__ fx, double *__restrict__ fy, double *__restrict__ fz, double *__restrict__ partial)
+{
+    __shared__ double sF[3][BONDED_THREADS + BONDED_SPILL];
+    __shared__ int sEnd;
+    const int base = blockIdx.x * BONDED_THREADS;
+    if (threadIdx.x == 0) sEnd = 0;
+    __syncthreads();
+    double acc[BONDED_ACC];
+#pragma unroll
+    for (int a = 0; a < BONDED_ACC; a++) acc[a] = 0.0;
+    int myHeadN = 0, myHeadSlot = -1;
+    {
+        // first pass: this CTA's own 128 records; the heads among them tell how far the CTA's last bead reaches
+        const int idx = threadIdx.x, k = base + idx;
+        V3 f = V3{0.0, 0.0, 0.0};
+        if (k < nRec)
+        {
+            const BondRec tm = recs[k];
+            if (k - (int)tm.q >= base)                    // the bead's first record is mine too
+            {
+                f = bondedEval<ENERGY>(tm, restrParm, restrOrigin, pos, pc, acc);
+                if (tm.q == 0)
+                {
+                    myHeadN = (int)tm.n;
+                    myHeadSlot = tm.s[tm.role];
+                    atomicMax(&sEnd, k + (int)tm.n);
+                }
+            }
+        }
+        sF[0][idx] = f.x; sF[1][idx] = f.y; sF[2][idx] = f.z;
+    }
+    __syncthreads();
+    const int end = min(min(sEnd, nRec), base + BONDED_THREADS + BONDED_SPILL);     // uniform over the CTA
+    for (int idx = BONDED_THREADS + threadIdx.x; base + idx < end; idx += BONDED_THREADS)
+    {
+        // records beyond the CTA's 128 that still belong to one of its beads (first record inside the 128)
+        const int k = base + idx;
+        const BondRec tm = recs[k];
+        V3 f = V3{0.0, 0.0, 0.0};
+        if (k - (int)tm.q < base + BONDED_THREADS) f = bondedEval<ENERGY>(tm, restrParm, restrOrigin, pos, pc, acc);
+        sF[0][idx] = f.x; sF[1][idx] = f.y; sF[2][idx] = f.z;
+    }
+    __syncthreads();
+    if (myHeadSlot >= 0)
+    {
+        V3 fs = V3{0.0, 0.0, 0.0};
+        for (int j = 0; j < myHeadN; j++)
+        {
+            fs.x += sF[0][threadIdx.x + j];
+            fs.y += sF[1][threadIdx.x + j];
+            fs.z += sF[2][threadIdx.x + j];
         }
         // k_pair has written this slot's pair force: the bonded sum is added to it by the only thread that owns the slot
-        fx[s] += fs.x;
-        fy[s] += fs.y;
-        fz[s] += fs.z;
+        fx[myHeadSlot] += fs.x;
+        fy[myHeadSlot] += fs.y;
+        fz[myHeadSlot] += fs.z;
     }
 
     if (ENERGY)

@@ -81,17 +81,13 @@ struct Term
     int kind, pad;
 };
 
-struct BondRange       // the bonded-term records of one slot: bondRec[lo .. lo + n)
-{
-    int lo, n;
-};
-
 struct alignas(16) BondRec   // one (term, endpoint) of a resident local bead, endpoints resolved to slots at the list build
 {
     int s[4];            // slots of the term's beads (unused: 0)
     double p0, p1, p2;
-    int kind;            // term kind 0..5, 6 = restraint, -1 = an endpoint is not resident: skip
-    int role;            // which of s[] is this slot
+    short kind;          // term kind 0..5, 6 = restraint, -1 = an endpoint is not resident: skip
+    short role;          // which of s[] is this slot
+    unsigned short q, n; // this is record q of the n records of its bead (consecutive)
 };
 
 enum { PROF_INTEGRATE = 0, PROF_PAIR, PROF_BONDED, PROF_LIST, PROF_REDUCE, PROF_HALO, PROF_N = 8 };
@@ -191,9 +187,9 @@ struct ddcb200_ctx
     bool bondCsrDirty = true;
     DevBuf<int> bondCsrOff;       // nGlobal + 1: entries of bead b = bondEnt[bondCsrOff[b] .. bondCsrOff[b + 1])
     DevBuf<uint32_t> bondEnt;     // (term << 2) | role of the bead in the term; term >= nTerms = restraint term - nTerms
-    DevBuf<BondRange> bondRange;  // per slot, refreshed at every list build
     DevBuf<BondRec> bondRec;      // slot order, refreshed at every list build
     DevBuf<int> bondCount, bondStart;
+    int nBondRec = 0;             // records of the resident local beads (set at the list build)
     DevBuf<double> restrParm;     // 7 doubles: frac0[3], kb, fc[3]
     int restrOrigin = 0;
 
@@ -219,7 +215,7 @@ struct ddcb200_ctx
     DevBuf<double> posBuild[3];   // build-time positions, slot order (displacement bound)
     unsigned long long *dmax2 = nullptr;   // device: [0] bits of the max squared displacement of a LOCAL bead since the build, [1] of a ghost
     bool walkPerBead = true;      // DDCB200_WALK
-    int pairVariant = 3;          // DDCB200_PAIR: index into the k_pair2 instantiations of api.cu (-1: the round-1 kernel)
+    int pairVariant = 2;          // DDCB200_PAIR: index into the k_pair2 instantiations of api.cu (-1: the round-1 kernel)
     DevBuf<float> dispOfSlot;     // each local bead's own displacement since the build, rounded up (0 right after a build)
     DevBuf<double> mmPartial;
     GridDev *grid = nullptr;      // device

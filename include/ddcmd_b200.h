@@ -254,6 +254,11 @@ int ddcb200_listBuildInfo(ddcb200_ctx *ctx, int *variant, double ms[2]);
 int ddcb200_ncclUniqueId(unsigned char id[128]);
 int ddcb200_ddcInit(ddcb200_ctx *ctx, int rank, int nranks, int lx, int ly, int lz, const unsigned char id[128]);
 
+/* Parity hook for decks too large to copy the pair list out: order-independent hash of the pairs this rank owns (smaller gid
+ * local, src/pairlist.c:244,279).  out = {count, sum, xor} of the interacting list, then of the pruned list, of
+ * mix64(mix64(gid_lo) + 0x9e3779b97f4a7c15 * gid_hi) (mod 2^64); oracle/ref_dump.c computes the same from ifirst[0] / ifirst[1]. */
+int ddcb200_pairSetHash(ddcb200_ctx *ctx, uint64_t out[6]);
+
 /* Host restatement of the domain classification (same predicates as the kernels), for tests and tools:
  * owner[b] = rank owning bead b; mask[b] for `rank`: bit 31 = mine, and then bit p (p < 16) = a ghost on rank p;
  * bit 30 = owned elsewhere and a ghost here, and then bit p = its owner.  ownerBead[b] = ownership bead of b's molecule (NULL = b). */

@@ -11,8 +11,9 @@
  * firstEnergyCall, then calls eval_integrator nsteps times.
  *
  * Usage (cwd = deck directory with object.data + restart):
- *     ref_dump <out.bin> [nsteps] [full_dump_every] [light]
- * "light" (any 4th argument) skips the per-bead and pair-list records: timing runs.
+ *     ref_dump <out.bin> [nsteps] [full_dump_every] [light|hash]
+ * "light" (4th argument) skips the per-bead and pair-list records: timing runs.  "hash" keeps the per-bead records and the
+ * cell ids but replaces the two pair lists by order-independent hashes of their (gid, gid) pairs: million-bead decks.
  *
  * Output: sequence of records  name[32] | dtype char ('d','q','i') | pad[7] |
  * count u64 | payload.  Read by tests/refdump.py.
@@ -58,6 +59,22 @@ static FILE *out;
 static int nsteps = 0;
 static int dump_every = 0;
 static int light = 0;
+static int hashPairs = 0;
+
+/* order-independent hash of a pair set: sum and xor (mod 2^64) of a 64-bit mix of (smaller gid, larger gid).  The CUDA side
+ * computes the same numbers on the device (ddcb200_pairSetHash) */
+static uint64_t mix64(uint64_t x)
+{
+    x ^= x >> 30; x *= 0xbf58476d1ce4e5b9ull;
+    x ^= x >> 27; x *= 0x94d049bb133111ebull;
+    x ^= x >> 31;
+    return x;
+}
+static uint64_t pairHash(uint64_t a, uint64_t b)
+{
+    const uint64_t lo = a < b ? a : b, hi = a < b ? b : a;
+    return mix64(mix64(lo) + 0x9e3779b97f4a7c15ull * hi);
+}
 
 static void rec(const char *name, char dtype, const void *data, uint64_t count)
 {
@@ -147,6 +164,22 @@ static void dump_neighbor(SYSTEM *sys)
                      getParticleSet()->center->x, getParticleSet()->center->y, getParticleSet()->center->z};
     rec("geom_parms", 'd', gp, 14);
     /* pair lists: ifirst[0] = interacting, ifirst[1] = pruned (reOrgPairs). */
+    if (hashPairs)
+    {
+        STATE *st = sys->collection->state;
+        uint64_t h[6] = {0, 0, 0, 0, 0, 0};      /* per list: count, sum, xor */
+        for (int l = 0; l < 2; l++)
+            for (unsigned i = 0; i < nlocal; i++)
+                for (PAIRS *p = nbr->particles[i].ifirst[l]; p; p = p->ilink)
+                {
+                    const uint64_t v = pairHash(st->label[i], st->label[p->j]);
+                    h[3 * l]++;
+                    h[3 * l + 1] += v;
+                    h[3 * l + 2] ^= v;
+                }
+        rec("pairhash", 'q', h, 6);
+    }
+    else
     for (int l = 0; l < 2; l++)
     {
         uint64_t cnt = 0;
@@ -274,7 +307,11 @@ int main(int argc, char *argv[])
     if (!out) { perror(argv[1]); return 2; }
     if (argc > 2) nsteps = atoi(argv[2]);
     if (argc > 3) dump_every = atoi(argv[3]);
-    if (argc > 4) light = 1;
+    if (argc > 4)
+    {
+        if (strcmp(argv[4], "hash") == 0) hashPairs = 1;
+        else light = 1;
+    }
     char *fake_argv[2] = {argv[0], NULL};
     int fake_argc = 1;
     mpiStartUp(fake_argc, fake_argv);

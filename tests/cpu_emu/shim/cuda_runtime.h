@@ -417,6 +417,8 @@ static inline T atomicOr(T *p, T v) { T o = *p; *p = o | v; return o; }
 template <class T>
 static inline T atomicAnd(T *p, T v) { T o = *p; *p = o & v; return o; }
 template <class T>
+static inline T atomicXor(T *p, T v) { T o = *p; *p = o ^ v; return o; }
+template <class T>
 static inline T atomicExch(T *p, T v) { T o = *p; *p = v; return o; }
 template <class T>
 static inline T atomicCAS(T *p, T c, T v) { T o = *p; if (o == c) *p = v; return o; }

@@ -120,6 +120,7 @@ def test_emu_fullsize_checks_on_a_small_generated_deck(emu, tmp_path, monkeypatc
     monkeypatch.setattr(tf, "CACHE", str(tmp_path))
     if os.path.exists(tf.REF_DUMP):
         assert tf.check_against_live_oracle("popc_small") > 3000
+        assert tf.check_against_live_oracle("popc_small", hashed=True) > 3000     # the million-bead form of the pair-list check
     assert tf.check_properties("popc_small") > 3000
 
 
@@ -153,13 +154,14 @@ def test_emu_four_and_eight_ranks_match_reference(emu_handle, nproc, name, latti
 def test_emu_bench_contract_two_ranks(emu_handle):
     """bench.py's multi-rank arm end to end (rank plumbing, max-over-ranks timing, one JSON line from rank 0)."""
     import json
-    r = _torchrun(2, 29562, "emu_bench_check.py", "--gpus", "2", "--workload", "popc_small", "--steps", "3", "--warmup", "3")
+    r = _torchrun(2, 29562, "emu_bench_check.py", "--gpus", "2", "--workload", "popc_small", "--steps", "3", "--warmup", "3",
+                  "--equil-rounds", "1", "--equil-steps", "2")
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-4000:]
     lines = [ln for ln in r.stdout.splitlines() if ln.startswith("{")]
     assert len(lines) == 1
     j = json.loads(lines[0])
     for key in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "vs_baseline", "dtype",
-                "data", "config", "roofline", "cpu_baseline", "e2e", "gpu_launches", "clocks"):
+                "data", "config", "run_info", "roofline", "cpu_baseline", "e2e", "gpu_launches", "clocks"):
         assert key in j, key
     assert j["n_gpus"] == 2 and j["steps"] == 3 and j["gpu_launches"] > 0
     assert set(("bound", "achieved", "peak", "unit", "frac", "traffic")) <= set(j["roofline"])

@@ -4,9 +4,10 @@
                          oracle/build_ref.sh) is run live on the same generated deck - it finishes in seconds at this size -
                          and the CUDA path must meet the same bars as on the small golden decks: cells and pair count
                          bit-exact, forces 1e-6, energies 1e-9, and the same energies after two integration steps.
-  membrane_1m            the bench workload, too big for a per-step oracle run inside a test: properties that hold at any
-                         size - Newton's third law over the full (both-direction) lists (sum of pair forces = 0), list entries =
-                         2 x listed pairs, bitwise run-to-run reproducibility, and energy conservation over a rebuild.
+  membrane_1m            the bench workload: the same comparison with the live reference (the two pair lists through an
+                         order-independent hash of their (gid, gid) pairs instead of 400 MB of indices), plus properties that hold
+                         at any size - Newton's third law over the full (both-direction) lists (sum of pair forces = 0), bitwise
+                         run-to-run reproducibility, and energy conservation over a rebuild.
 
 The decks come from ddcmd_b200.synth (fixed seeds) and are cached under DDCB200_DECK_CACHE like bench.py's.
 Collected after the golden-deck parity tests."""
@@ -35,18 +36,26 @@ def get_deck(name):
     return path
 
 
-def run_oracle(path, nsteps):
+def run_oracle(path, nsteps, mode=""):
     out = os.path.join(path, "_fullsize.bin")
-    subprocess.check_call(["bash", "-c", "ulimit -s unlimited; exec '%s' '%s' %d 0" % (REF_DUMP, out, nsteps)], cwd=path,
+    subprocess.check_call(["bash", "-c", "ulimit -s unlimited; exec '%s' '%s' %d 0 %s" % (REF_DUMP, out, nsteps, mode)], cwd=path,
                           stdout=open(os.path.join(path, "_fullsize.log"), "w"), stderr=subprocess.STDOUT)
     r = read_records(out)
     os.remove(out)
     return r
 
 
-def check_against_live_oracle(name, nsteps=2):
+def pair_key(a, b):
+    a = a.astype(np.int64)
+    b = b.astype(np.int64)
+    return (np.minimum(a, b) << 32) | np.maximum(a, b)
+
+
+def check_against_live_oracle(name, nsteps=2, hashed=False):
+    """hashed: the reference dumps order-independent hashes of its two pair lists instead of the lists (million-bead decks);
+    otherwise the full pair SETS are compared."""
     path = get_deck(name)
-    ref = run_oracle(path, nsteps)
+    ref = run_oracle(path, nsteps, "hash" if hashed else "")
     sim = dd.simulate_init(os.path.join(path, "object.data"))
     n = sim.deck.n
     assert n == int(ref["nion"][0])
@@ -58,6 +67,22 @@ def check_against_live_oracle(name, nsteps=2):
     assert np.array_equal(cell, ref["cell"])
     e = sim.energyInfo()
     assert e.nPairsListed == int(ref["npairs"][0])
+    if hashed:
+        # count, sum and xor (mod 2^64) of a 64-bit mix of every (gid, gid) pair, interacting list then pruned list
+        assert np.array_equal(sim.pairSetHash(), ref["pairhash"].view(np.uint64)), (sim.pairSetHash(), ref["pairhash"])
+    else:
+        bi, bj, pr = sim.getPairs()
+        p0, p1 = ref["pairs0"].reshape(-1, 2), ref["pairs1"].reshape(-1, 2)
+        assert np.array_equal(np.sort(pair_key(bi[pr == 0], bj[pr == 0])), np.sort(pair_key(p0[:, 0], p0[:, 1])))
+        assert np.array_equal(np.sort(pair_key(bi[pr == 1], bj[pr == 1])), np.sort(pair_key(p1[:, 0], p1[:, 1])))
+        # and the device-side hash agrees with the same hash of the reference's lists
+        lab = ref["s0_label"].view(np.uint64)
+        want = np.zeros(6, np.uint64)
+        for l, pp in enumerate((p0, p1)):
+            if len(pp):
+                v = pair_hash(lab[pp[:, 0]], lab[pp[:, 1]])
+                want[3 * l:3 * l + 3] = (len(pp), v.sum(dtype=np.uint64), np.bitwise_xor.reduce(v))
+        assert np.array_equal(sim.pairSetHash(), want)
     # forces 1e-6, energies 1e-9
     st = sim.getState()
     f = np.stack([st["fx"], st["fy"], st["fz"]], 1)
@@ -83,6 +108,21 @@ def check_against_live_oracle(name, nsteps=2):
     assert np.abs(st2["rx"] - ref["sN_rx"]).max() < 1e-10 and np.abs(st2["vz"] - ref["sN_vz"]).max() < 1e-13
     sim.close()
     return n
+
+
+def mix64(x):
+    x = x.astype(np.uint64)
+    with np.errstate(over="ignore"):
+        x ^= x >> np.uint64(30); x *= np.uint64(0xbf58476d1ce4e5b9)
+        x ^= x >> np.uint64(27); x *= np.uint64(0x94d049bb133111eb)
+        x ^= x >> np.uint64(31)
+    return x
+
+
+def pair_hash(ga, gb):
+    lo, hi = np.minimum(ga, gb), np.maximum(ga, gb)
+    with np.errstate(over="ignore"):
+        return mix64(mix64(lo) + np.uint64(0x9e3779b97f4a7c15) * hi)
 
 
 def check_properties(name, nsteps=25):
@@ -136,4 +176,13 @@ def test_single_gpu_configs_against_live_reference(name):
 
 def test_bench_workload_properties():
     n = check_properties("membrane_1m")
+    assert n > 1000000
+
+
+@pytest.mark.skipif(not os.path.exists(REF_DUMP), reason="oracle/_ref/ref_dump not built")
+def test_bench_workload_against_live_reference():
+    """BASELINE.json's 1M-bead membrane, the deck bench.py times, against the unmodified reference run live on the same files
+    (about half a minute of one host core): cells bit-exact, both pair lists as sets (through the order-independent hash),
+    forces 1e-6, energies and virial 1e-9, and the energies after two integration steps."""
+    n = check_against_live_oracle("membrane_1m", hashed=True)
     assert n > 1000000
