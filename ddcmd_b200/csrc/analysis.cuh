@@ -132,7 +132,7 @@ __device__ __forceinline__ unsigned long long mix64(unsigned long long x)
 }
 
 __global__ void k_pair_hash(int nIon, int nPad, const uint32_t *__restrict__ nbr, const int *__restrict__ count, const int *__restrict__ beadOfSlot,
-                            const uint64_t *__restrict__ gid, unsigned long long *__restrict__ out)
+                            const uint64_t *__restrict__ gid, const TileWin *__restrict__ tileWin, unsigned long long *__restrict__ out)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     unsigned long long h[6] = {0, 0, 0, 0, 0, 0};
@@ -143,7 +143,9 @@ __global__ void k_pair_hash(int nIon, int nPad, const uint32_t *__restrict__ nbr
         for (int k = 0; k < n; k++)
         {
             const uint32_t e = nbr[(size_t)k * nPad + i];
-            const uint64_t gj = gid[beadOfSlot[e & 0x07ffffffu]];
+            int j = (int)(e & 0x07ffffffu);
+            if (tileWin) j = winSlot(tileWin[i / TILE], j);      // rows of windowed tiles hold window offsets
+            const uint64_t gj = gid[beadOfSlot[j]];
             if (gi < gj)
             {
                 const unsigned long long v = mix64(mix64(gi) + 0x9e3779b97f4a7c15ull * gj);

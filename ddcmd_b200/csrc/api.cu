@@ -177,6 +177,7 @@ static int setupBox(ddcb200_ctx *c)
     pc.rc2 = b.rc2; pc.R2cut = b.R2cut;
     pc.hxx = b.hxx; pc.hyy = b.hyy; pc.hzz = b.hzz;
     pc.hhx = b.hhx; pc.hhy = b.hhy; pc.hhz = b.hhz;
+    pc.ihx = 1.0 / b.hxx; pc.ihy = 1.0 / b.hyy; pc.ihz = 1.0 / b.hzz;
     pc.keR = p.keR; pc.krf = p.krf; pc.crf = p.crf;
     pc.rmax = p.rmax;
     pc.ntypes = c->ntypes;
@@ -198,7 +199,7 @@ struct PairVariant
     int pf, minb;
     PairKernel force, energy;
 };
-#define PV(P, M) {P, M, k_pair2<false, P, M>, k_pair2<true, P, M>}
+#define PV(P, M) {P, M, k_pair2<false, P, M>, k_pair2<true, P, 1>}      // the energy instantiation needs more registers: never capped
 static const PairVariant g_pairVariants[] = {PV(1, 1), PV(2, 1), PV(2, 8), PV(3, 8), PV(4, 1)};      // measured: profiles/r02d_pair_variants.txt
 #undef PV
 static const int g_nPairVariants = (int)(sizeof(g_pairVariants) / sizeof(g_pairVariants[0]));
@@ -250,6 +251,7 @@ static int createInit(ddcb200_ctx *c)
     {
         int pf = 0, mb = 0;
         if (strcmp(pv, "old") == 0) c->pairVariant = -1;
+        else if (strcmp(pv, "win") == 0) c->pairWindows = true;
         else if (sscanf(pv, "%d,%d", &pf, &mb) == 2)
         {
             c->pairVariant = -2;
@@ -259,6 +261,7 @@ static int createInit(ddcb200_ctx *c)
         else c->pairVariant = -2;
         if (c->pairVariant == -2) return fail(DDCB200_ERR_ARG, "DDCB200_PAIR must be old or one of the built <pf>,<minb> pairs");
     }
+    if (const char *bm = getenv("DDCB200_BONDED")) c->bondedCapped = strcmp(bm, "capped") == 0;      // A/B: 64-register build of k_bonded
     if (const char *hm = getenv("DDCB200_HALO"))
     {
         // several ranks: "overlap" (default) = the ghost halo runs on its own stream beside the pair rows that read no ghost,
@@ -302,7 +305,7 @@ extern "C" void ddcb200_destroy(ddcb200_ctx *c)
     if (c->stream) cudaStreamSynchronize(c->stream);
     c->ljTab.release(); c->shiftTab.release(); c->qTab.release(); c->massOfBead.release(); c->wOfBead.release();
     c->gidOfBead.release(); c->molTypeOfBead.release(); c->molTypeSingle.release(); c->bpairOffset.release();
-    c->bpairKey.release(); c->termsBead.release(); c->restrBead.release(); c->bondCsrOff.release(); c->bondEnt.release(); c->bondRec.release(); c->bondCount.release(); c->bondStart.release();
+    c->bpairKey.release(); c->termsBead.release(); c->restrBead.release(); c->bondCsrOff.release(); c->bondEnt.release(); c->bondRec.release(); c->bondCount.release(); c->bondStart.release(); c->scanBlocks.release();
     c->restrParm.release(); c->molOffset.release(); c->molBeads.release();
     for (int k = 0; k < 2; k++)
     {
@@ -330,7 +333,7 @@ extern "C" void ddcb200_destroy(ddcb200_ctx *c)
     if (c->streamH) { cudaStreamSynchronize(c->streamH); cudaStreamDestroy(c->streamH); }
     if (c->evPos) cudaEventDestroy(c->evPos);
     if (c->evHalo) cudaEventDestroy(c->evHalo);
-    c->tileGhost.release(); c->tileOrder.release();
+    c->tileGhost.release(); c->tileOrder.release(); c->tileWin.release();
     if (c->ddcWork) cudaFree(c->ddcWork);
     if (c->ddcWorkInit) cudaFreeHost(c->ddcWorkInit);
     if (c->ddcRow) cudaFree(c->ddcRow);
@@ -368,6 +371,13 @@ extern "C" int ddcb200_sync(ddcb200_ctx *c)
     return DDCB200_OK;
 }
 
+// k_pair3: the tables, then the window ({x, y} and {z, w}, 32 bytes per bead)
+static size_t pair3TableBytes(int ntypes)
+{
+    const size_t nt2 = (size_t)ntypes * ntypes;
+    return nt2 * sizeof(double2) + 256 * sizeof(double) + (nt2 + (nt2 & 1)) * sizeof(double);
+}
+
 static size_t pairSmemBytes(int ntypes) { return (size_t)ntypes * ntypes * (sizeof(double2) + sizeof(double)) + 256 * sizeof(double); }
 
 extern "C" int ddcb200_martiniNonBondParms(ddcb200_ctx *c, int ntypes, const double *eps, const double *sigma, const double *shift)
@@ -397,6 +407,19 @@ extern "C" int ddcb200_martiniNonBondParms(ddcb200_ctx *c, int ntypes, const dou
     {
         CK(cudaFuncSetAttribute(g_pairVariants[v].force, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         CK(cudaFuncSetAttribute(g_pairVariants[v].energy, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    }
+    {
+        // windowed kernel: two CTAs per SM at the largest window it accepts; smaller windows leave room for more
+        const size_t perCta = prop.sharedMemPerBlockOptin / 2 - 2048;      // static shared memory + the per-CTA reservation
+        const size_t tab = pair3TableBytes(ntypes);
+        c->winMax = perCta > tab + 32 * 256 ? (int)((perCta - tab) / 32) : 0;
+        if (c->winMax > 0)
+        {
+            CK(cudaFuncSetAttribute(k_pair3<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(tab + 32 * (size_t)c->winMax)));
+            CK(cudaFuncSetAttribute(k_pair3<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(tab + 32 * (size_t)c->winMax)));
+        }
+        else
+            c->pairWindows = false;
     }
     c->ntypes = ntypes;
     c->pc.ntypes = ntypes;
@@ -1108,13 +1131,25 @@ extern "C" int ddcb200_constructList(ddcb200_ctx *c)
         CK(c->bondStart.ensure((size_t)nPad));
         LAUNCH(k_bond_count, (nIon + 255) / 256, 256, 0, st)(nIon, c->pos4[nxt].p, c->bondCsrOff.p, c->bondCount.p);
         CKL("k_bond_count");
-        LAUNCH(k_scan_int, 1, 1024, 0, st)(nIon, c->bondCount.p, c->bondStart.p, &c->grid->bondTotal);
-        CKL("k_scan_int");
+        const int nsb = (nIon + SCAN_BLOCK - 1) / SCAN_BLOCK;
+        CK(c->scanBlocks.ensure((size_t)nsb + 1));
+        LAUNCH(k_scan_local, nsb, SCAN_BLOCK, 0, st)(nIon, c->bondCount.p, c->bondStart.p, c->scanBlocks.p);
+        CKL("k_scan_local");
+        LAUNCH(k_scan_blocks, 1, 1024, 0, st)(nsb, c->scanBlocks.p, &c->grid->bondTotal);
+        CKL("k_scan_blocks");
+        LAUNCH(k_scan_add, nsb, SCAN_BLOCK, 0, st)(nIon, c->bondStart.p, c->scanBlocks.p);
+        CKL("k_scan_add");
     }
     if (c->nranks > 1)
     {
         CK(c->tileGhost.ensure((size_t)(nPad / TILE) + 1));
         CK(c->tileOrder.ensure((size_t)(nPad / TILE) + 1));
+    }
+    if (c->pairWindows)
+    {
+        CK(c->tileWin.ensure((size_t)(nPad / TILE) + 1));
+        LAUNCH(k_tile_window, (nPad / TILE + 3) / 4, 128, 0, st)(nIon, nPad / TILE, c->cellOfSlot[nxt].p, c->cellStart.p, c->grid, c->winMax, c->tileWin.p);
+        CKL("k_tile_window");
     }
     for (int attempt = 0; attempt < 4; attempt++)
     {
@@ -1127,7 +1162,7 @@ extern "C" int ddcb200_constructList(ddcb200_ctx *c)
         LAUNCH(k_nbr_exact, nPad / 128, 128, 0, st)(nIon, nPad, c->nbrCap, c->pos4[nxt].p, c->box, c->grid, c->nbrRaw.p, c->nbrRawCount.p,
                                                c->nbr.p, c->nbrCount.p, c->nbrCum.p, c->gidOfBead.p, c->molTypeOfBead.p,
                                                c->molTypeSingle.p, c->bpairOffset.p, c->bpairKey.p, c->haveExcl ? 1 : 0,
-                                               c->nranks > 1 ? c->tileGhost.p : nullptr);
+                                               c->nranks > 1 ? c->tileGhost.p : nullptr, c->pairWindows ? c->tileWin.p : nullptr);
         CKL("k_nbr_exact");
         CK(cudaEventRecord(c->evList[1], st));
         if (c->nranks > 1)
@@ -1185,6 +1220,7 @@ extern "C" int ddcb200_constructList(ddcb200_ctx *c)
     c->totalEntries = (int64_t)c->gridHost->totalEntries;
     c->nPairsListed = (int64_t)(c->gridHost->totalEntries / 2);
     c->nTilesInterior = c->nranks > 1 ? c->gridHost->nInterior : nPad / TILE;
+    c->winMaxTotal = c->gridHost->winMaxTotal;
     return DDCB200_OK;
 }
 
@@ -1323,7 +1359,20 @@ extern "C" int ddcb200_ddcenergy(ddcb200_ctx *c, int withEnergy)
         auto launchPair = [&](int nTiles, const int *order, int base, int withGhosts) -> int {
             if (nTiles <= 0) return DDCB200_OK;
             ProfScope ps(c, PROF_PAIR);
-            if (c->pairVariant >= 0)
+            if (c->pairWindows)
+            {
+                const int wcap = (c->winMaxTotal + 7) & ~7;
+                const size_t smem3 = pair3TableBytes(c->ntypes) + 32 * (size_t)wcap;
+                if (withEnergy)
+                    LAUNCH(k_pair3<true>, nTiles, PAIR3_THREADS, smem3, st)(nLocal, nPad, order, base, c->pos4[cur].p, c->nbr.p, c->nbrCum.p, c->dmax2, withGhosts,
+                                                                        disp, c->tileWin.p, wcap, c->ljTab.p, c->shiftTab.p, c->qTab.p, c->pc, c->frc[0].p,
+                                                                        c->frc[1].p, c->frc[2].p, c->pairPartial.p);
+                else
+                    LAUNCH(k_pair3<false>, nTiles, PAIR3_THREADS, smem3, st)(nLocal, nPad, order, base, c->pos4[cur].p, c->nbr.p, c->nbrCum.p, c->dmax2, withGhosts,
+                                                                         disp, c->tileWin.p, wcap, c->ljTab.p, c->shiftTab.p, c->qTab.p, c->pc, c->frc[0].p,
+                                                                         c->frc[1].p, c->frc[2].p, c->pairPartial.p);
+            }
+            else if (c->pairVariant >= 0)
             {
                 const PairVariant &pv = g_pairVariants[c->pairVariant];
                 const PairKernel kern = withEnergy ? pv.energy : pv.force;
@@ -1360,11 +1409,14 @@ extern "C" int ddcb200_ddcenergy(ddcb200_ctx *c, int withEnergy)
         bBlocks = (c->nBondRec + BONDED_THREADS - 1) / BONDED_THREADS;
         CK(c->bondPartial.ensure((size_t)bBlocks * BONDED_ACC + 8));
         if (withEnergy)
-            LAUNCH(k_bonded<true>, bBlocks, BONDED_THREADS, 0, st)(c->nBondRec, c->bondRec.p, c->restrParm.p, c->restrOrigin, c->pos4[cur].p, c->pc,
-                                                               c->frc[0].p, c->frc[1].p, c->frc[2].p, c->bondPartial.p);
+            LAUNCH((k_bonded<true, 1>), bBlocks, BONDED_THREADS, 0, st)(c->nBondRec, c->bondRec.p, c->restrParm.p, c->restrOrigin, c->pos4[cur].p, c->pc,
+                                                                    c->frc[0].p, c->frc[1].p, c->frc[2].p, c->bondPartial.p);
+        else if (c->bondedCapped)
+            LAUNCH((k_bonded<false, 8>), bBlocks, BONDED_THREADS, 0, st)(c->nBondRec, c->bondRec.p, c->restrParm.p, c->restrOrigin, c->pos4[cur].p, c->pc,
+                                                                     c->frc[0].p, c->frc[1].p, c->frc[2].p, c->bondPartial.p);
         else
-            LAUNCH(k_bonded<false>, bBlocks, BONDED_THREADS, 0, st)(c->nBondRec, c->bondRec.p, c->restrParm.p, c->restrOrigin, c->pos4[cur].p, c->pc,
-                                                                c->frc[0].p, c->frc[1].p, c->frc[2].p, c->bondPartial.p);
+            LAUNCH((k_bonded<false, 1>), bBlocks, BONDED_THREADS, 0, st)(c->nBondRec, c->bondRec.p, c->restrParm.p, c->restrOrigin, c->pos4[cur].p, c->pc,
+                                                                     c->frc[0].p, c->frc[1].p, c->frc[2].p, c->bondPartial.p);
         CKL("k_bonded");
     }
     if (withEnergy)
@@ -1907,11 +1959,20 @@ extern "C" int64_t ddcb200_getPairs(ddcb200_ctx *c, int64_t capacity, int *beadI
     std::vector<uint32_t> rows((size_t)maxc * nPad);
     if (maxc && cudaMemcpy(rows.data(), c->nbr.p, rows.size() * sizeof(uint32_t), cudaMemcpyDeviceToHost) != cudaSuccess)
         return fail(DDCB200_ERR_CUDA, "getPairs copy");
+    std::vector<TileWin> win;
+    if (c->pairWindows)
+    {
+        // rows of windowed tiles hold window offsets: turn them back into slots
+        win.resize((size_t)(nPad / TILE));
+        if (cudaMemcpy(win.data(), c->tileWin.p, win.size() * sizeof(TileWin), cudaMemcpyDeviceToHost) != cudaSuccess)
+            return fail(DDCB200_ERR_CUDA, "getPairs copy");
+    }
     for (int i = 0; i < n; i++)
         for (int k = 0; k < cnt[i]; k++)
         {
             const uint32_t e = rows[(size_t)k * nPad + i];
-            emit(i, (int)(e & 0x07ffffffu), (e & EXCL_BIT) != 0u);
+            const int idx = (int)(e & 0x07ffffffu);
+            emit(i, win.empty() ? idx : winSlot(win[(size_t)(i / TILE)], idx), (e & EXCL_BIT) != 0u);
         }
     return np;
 }
@@ -1929,7 +1990,7 @@ extern "C" int ddcb200_pairSetHash(ddcb200_ctx *c, uint64_t out[6])
     CK(sc.h.ensure(8));
     CK(cudaMemsetAsync(sc.h.p, 0, 8 * sizeof(unsigned long long), c->stream));
     LAUNCH(k_pair_hash, (int)((c->nIon + 255) / 256), 256, 0, c->stream)((int)c->nIon, (int)c->nPad, c->nbr.p, c->nbrCount.p, c->beadOfSlot[c->cur].p,
-                                                                     c->gidOfBead.p, sc.h.p);
+                                                                     c->gidOfBead.p, c->pairWindows ? c->tileWin.p : nullptr, sc.h.p);
     CKL("k_pair_hash");
     CK(cudaMemcpyAsync(out, sc.h.p, 6 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, c->stream));
     CK(cudaStreamSynchronize(c->stream));

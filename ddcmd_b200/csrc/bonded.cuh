@@ -22,10 +22,11 @@ __device__ __forceinline__ V3 vaxpy(double s, V3 a, V3 b) { return V3{s * a.x + 
 
 __device__ __forceinline__ V3 minImage(V3 d, const PairConst &pc)
 {
-    // nearestImage == Preduce for an orthorhombic box (src/preduce.c:449-470): d -= h*rint(d/h)
-    d.x -= pc.hxx * rint(d.x / pc.hxx);
-    d.y -= pc.hyy * rint(d.y / pc.hyy);
-    d.z -= pc.hzz * rint(d.z / pc.hzz);
+    // nearestImage == Preduce for an orthorhombic box (src/preduce.c:449-470): d -= h*rint(d/h).  The quotient only picks the
+    // lattice vector (an integer), so it is taken with the reciprocal edge: three multiplications instead of three divisions
+    d.x -= pc.hxx * rint(d.x * pc.ihx);
+    d.y -= pc.hyy * rint(d.y * pc.ihy);
+    d.z -= pc.hzz * rint(d.z * pc.ihz);
     return d;
 }
 
@@ -100,15 +101,47 @@ __global__ void k_bond_count(int nIon, const double4 *__restrict__ pos, const in
     cnt[s] = n;
 }
 
-// exclusive scan of n ints in one block (n is a few million at most and this runs once per list build)
+// exclusive scan of n ints (n = resident beads): per-block scans, a scan of the block totals by one block, then the offsets
+#define SCAN_BLOCK 1024
+__global__ void __launch_bounds__(SCAN_BLOCK)
+k_scan_local(int n, const int *__restrict__ in, int *__restrict__ out, int *__restrict__ blockSum)
+{
+    __shared__ int sums[SCAN_BLOCK / 32];
+    const int i = blockIdx.x * SCAN_BLOCK + threadIdx.x;
+    const int v = i < n ? in[i] : 0;
+    int s = v;
+    for (int o = 1; o < 32; o <<= 1)
+    {
+        const int t = __shfl_up_sync(0xffffffffu, s, o);
+        if ((int)(threadIdx.x & 31) >= o) s += t;
+    }
+    if ((threadIdx.x & 31) == 31) sums[threadIdx.x >> 5] = s;
+    __syncthreads();
+    if (threadIdx.x < 32)
+    {
+        int w = sums[threadIdx.x];
+        for (int o = 1; o < 32; o <<= 1)
+        {
+            const int t = __shfl_up_sync(0xffffffffu, w, o);
+            if ((int)threadIdx.x >= o) w += t;
+        }
+        sums[threadIdx.x] = w;
+    }
+    __syncthreads();
+    const int before = (threadIdx.x >> 5) ? sums[(threadIdx.x >> 5) - 1] : 0;
+    if (i < n) out[i] = before + s - v;
+    if (threadIdx.x == SCAN_BLOCK - 1) blockSum[blockIdx.x] = before + s;
+}
+
+// one block: exclusive scan of the block totals in place (a few thousand at most), grand total to *total
 __global__ void __launch_bounds__(1024)
-k_scan_int(int n, const int *__restrict__ in, int *__restrict__ out, int *__restrict__ total)
+k_scan_blocks(int nb, int *__restrict__ blockSum, int *__restrict__ total)
 {
     __shared__ int sums[1024];
-    const int per = (n + blockDim.x - 1) / blockDim.x;
-    const int lo = min(n, (int)threadIdx.x * per), hi = min(n, lo + per);
+    const int per = (nb + blockDim.x - 1) / blockDim.x;
+    const int lo = min(nb, (int)threadIdx.x * per), hi = min(nb, lo + per);
     int s = 0;
-    for (int i = lo; i < hi; i++) s += in[i];
+    for (int i = lo; i < hi; i++) s += blockSum[i];
     sums[threadIdx.x] = s;
     __syncthreads();
     for (int o = 1; o < (int)blockDim.x; o <<= 1)
@@ -121,10 +154,18 @@ k_scan_int(int n, const int *__restrict__ in, int *__restrict__ out, int *__rest
     int run = sums[threadIdx.x] - s;
     for (int i = lo; i < hi; i++)
     {
-        out[i] = run;
-        run += in[i];
+        const int v = blockSum[i];
+        blockSum[i] = run;
+        run += v;
     }
     if (threadIdx.x == blockDim.x - 1) *total = sums[threadIdx.x];
+}
+
+__global__ void __launch_bounds__(SCAN_BLOCK)
+k_scan_add(int n, int *__restrict__ out, const int *__restrict__ blockSum)
+{
+    const int i = blockIdx.x * SCAN_BLOCK + threadIdx.x;
+    if (i < n) out[i] += blockSum[blockIdx.x];
 }
 
 __global__ void k_bond_resolve(int nIon, const double4 *__restrict__ pos, const int *__restrict__ csrOff, const uint32_t *__restrict__ ent,
@@ -226,7 +267,8 @@ __device__ __forceinline__ V3 bondedEval(const BondRec &tm, const double *__rest
                 const double4 pj = pos[sj];
                 const V3 vij = minImage(vsub(pos[si], pj), pc), vkj = minImage(vsub(pos[sk], pj), pc);
                 const double bij = sqrt(vdot(vij, vij)), bkj = sqrt(vdot(vkj, vkj));
-                const V3 uij = vscale(vij, 1.0 / bij), ukj = vscale(vkj, 1.0 / bkj);
+                const double ibij = 1.0 / bij, ibkj = 1.0 / bkj;
+                const V3 uij = vscale(vij, ibij), ukj = vscale(vkj, ibkj);
                 const double c = vdot(uij, ukj);
                 double coef, en;
                 if (tm.kind == 1)
@@ -247,7 +289,7 @@ __device__ __forceinline__ V3 bondedEval(const BondRec &tm, const double *__rest
                     en = tm.p0 * da * da / s2;
                     coef = -2.0 * tm.p0 * da * (1.0 - c * tm.p1) / (s2 * s2);
                 }
-                const double ci = coef / bij, ck = coef / bkj;
+                const double ci = coef * ibij, ck = coef * ibkj;
                 const V3 fi = V3{ci * (ukj.x - uij.x * c), ci * (ukj.y - uij.y * c), ci * (ukj.z - uij.z * c)};
                 const V3 fk = V3{ck * (uij.x - ukj.x * c), ck * (uij.y - ukj.y * c), ck * (uij.z - ukj.z * c)};
                 f = role == 0 ? fi : (role == 2 ? fk : V3{-(fi.x + fk.x), -(fi.y + fk.y), -(fi.z + fk.z)});
@@ -312,8 +354,8 @@ __device__ __forceinline__ V3 bondedEval(const BondRec &tm, const double *__rest
 // adds the sum to the slot's pair force - no atomic, one writer per slot.  A bead belongs to the CTA that holds its first
 // record; a CTA therefore also evaluates the up to BONDED_SPILL records of its last beads that lie beyond its 128.
 #define BONDED_SPILL 256
-template <bool ENERGY>
-__global__ void __launch_bounds__(BONDED_THREADS)
+template <bool ENERGY, int MINB>
+__global__ void __launch_bounds__(BONDED_THREADS, MINB)
 k_bonded(int nRec, const BondRec *__restrict__ recs, const double *__restrict__ restrParm, int restrOrigin, const double4 *__restrict__ pos,
          PairConst pc, double *__restrict__ fx, double *__restrict__ fy, double *__restrict__ fz, double *__restrict__ partial)
 {

@@ -131,6 +131,8 @@ __global__ void k_grid_setup(const double *__restrict__ partial, int nblocks, in
     g->maxCount = 0;
     g->maxRaw = 0;
     g->totalEntries = 0ull;
+    g->winMaxTotal = 0;
+    g->winGlobal = 0;
 }
 
 __device__ __forceinline__ int spread2(int v) { return (v & 1) | ((v & 2) << 2); }   // bits 0,1 -> bits 0,3
@@ -327,6 +329,120 @@ k_nbr_filter(int nIon, int nPad, const float4 *__restrict__ pos32, const int *__
     }
 }
 
+// ---- 8c. tile windows (windowed pair kernel only) -----------------------------------------------------------------------------
+// One warp per tile: the distinct cells of the tile's slots, their stencil cells (the cells k_nbr_filter walks), sorted and
+// merged into runs of consecutive slots.  A window that needs more than WIN_MAXRUNS runs or more than wmax beads is left
+// empty: that tile keeps slot entries and gathers from global memory.
+#define WIN_IDS 1024
+__global__ void __launch_bounds__(128)
+k_tile_window(int nIon, int nTiles, const int *__restrict__ cellOfSlot, const int *__restrict__ cellStart, GridDev *gp, int wmax,
+              TileWin *__restrict__ out)
+{
+    __shared__ int sIds[4][WIN_IDS];
+    __shared__ int sDc[4][32];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const int t = blockIdx.x * 4 + wib;
+    if (t >= nTiles) return;
+    int *ids = sIds[wib], *dc = sDc[wib];
+    const int nx = gp->n[0], ny = gp->n[1], nz = gp->n[2];
+    const int lx = nx >= 3 ? -1 : 0, hx = nx >= 2 ? 1 : 0;
+    const int ly = ny >= 3 ? -1 : 0, hy = ny >= 2 ? 1 : 0;
+    const int lz = nz >= 3 ? -1 : 0, hz = nz >= 2 ? 1 : 0;
+    const unsigned lt = (1u << lane) - 1u;
+    // distinct cells of the tile (slots are sorted by cell)
+    int nCells = 0, last = -2;
+    for (int m = 0; m < TILE / 32; m++)
+    {
+        const int s = t * TILE + m * 32 + lane;
+        const int c = s < nIon ? cellOfSlot[s] : -1;
+        int prev = __shfl_up_sync(0xffffffffu, c, 1);
+        if (lane == 0) prev = last;
+        const bool isNew = c >= 0 && c != prev;
+        const unsigned mk = __ballot_sync(0xffffffffu, isNew);
+        const int p = nCells + __popc(mk & lt);
+        if (isNew && p < 32) dc[p] = c;
+        nCells += __popc(mk);
+        last = __shfl_sync(0xffffffffu, c, 31);
+    }
+    __syncwarp();
+    bool fits = nCells <= 32;
+    int nIds = 0;
+    if (fits)
+    {
+        for (int d = 0; d < nCells; d++)
+        {
+            const int c = dc[d];
+            const int cx = c % nx, cy = (c / nx) % ny, cz = c / (nx * ny);
+            const int dx = lane % 3 - 1, dy = (lane / 3) % 3 - 1, dz = lane / 9 - 1;
+            const bool ok = lane < 27 && dx >= lx && dx <= hx && dy >= ly && dy <= hy && dz >= lz && dz <= hz;
+            int ax = cx + dx, ay = cy + dy, az = cz + dz;
+            if (ax < 0) ax += nx; else if (ax >= nx) ax -= nx;
+            if (ay < 0) ay += ny; else if (ay >= ny) ay -= ny;
+            if (az < 0) az += nz; else if (az >= nz) az -= nz;
+            const unsigned mk = __ballot_sync(0xffffffffu, ok);
+            if (ok) ids[nIds + __popc(mk & lt)] = ax + nx * (ay + ny * az);
+            nIds += __popc(mk);
+        }
+        int np2 = 32;
+        while (np2 < nIds) np2 <<= 1;
+        for (int q = nIds + lane; q < np2; q += 32) ids[q] = 0x7fffffff;
+        __syncwarp();
+        // bitonic sort, ascending
+        for (int k = 2; k <= np2; k <<= 1)
+            for (int j = k >> 1; j > 0; j >>= 1)
+            {
+                for (int q = lane; q < np2; q += 32)
+                {
+                    const int r = q ^ j;
+                    if (r > q)
+                    {
+                        const int a = ids[q], b = ids[r];
+                        const bool up = (q & k) == 0;
+                        if ((a > b) == up) { ids[q] = b; ids[r] = a; }
+                    }
+                }
+                __syncwarp();
+            }
+    }
+    if (lane == 0)
+    {
+        TileWin w;
+        w.nRuns = 0;
+        w.total = 0;
+        w.pad = 0;
+        int prevC = -1;
+        for (int q = 0; q < nIds && fits; q++)
+        {
+            const int c = ids[q];
+            if (c == prevC) continue;
+            prevC = c;
+            const int lo = cellStart[c], n = cellStart[c + 1] - lo;
+            if (n == 0) continue;
+            if (w.nRuns > 0 && w.lo[w.nRuns - 1] + (w.total - w.off[w.nRuns - 1]) == lo) w.total += n;     // continues the last run
+            else if (w.nRuns == WIN_MAXRUNS) fits = false;
+            else
+            {
+                w.lo[w.nRuns] = lo;
+                w.off[w.nRuns] = w.total;
+                w.nRuns++;
+                w.total += n;
+            }
+            if (w.total > wmax) fits = false;
+        }
+        if (!fits)
+        {
+            w.nRuns = 0;
+            w.total = 0;
+            atomicAdd(&gp->winGlobal, 1);
+        }
+        for (int r = w.nRuns; r < WIN_MAXRUNS; r++) { w.lo[r] = 0x7fffffff; w.off[r] = w.total; }
+        w.off[WIN_MAXRUNS] = w.total;
+        if (w.nRuns > 0) w.off[w.nRuns] = w.total;
+        out[t] = w;
+        atomicMax(&gp->winMaxTotal, w.total);
+    }
+}
+
 // ---- 9. exact pass: pairlist1's test bit for bit, reOrgPairs' pruning, distance-bin order ----
 __device__ __forceinline__ bool isPruned(int bi, int bj, const uint64_t *__restrict__ gid,
                                          const int *__restrict__ molTypeOfBead, const int *__restrict__ molTypeSingle,
@@ -371,8 +487,16 @@ __global__ void __launch_bounds__(128)
 k_nbr_exact(int nIon, int nPad, int cap, const double4 *__restrict__ pos, BoxConst b, GridDev *gp, uint32_t *__restrict__ raw,
             const int *__restrict__ rawCount, uint32_t *__restrict__ out, int *__restrict__ count, uint16_t *__restrict__ cum,
             const uint64_t *__restrict__ gid, const int *__restrict__ molTypeOfBead, const int *__restrict__ molTypeSingle,
-            const int *__restrict__ bpairOffset, const uint32_t *__restrict__ bpairKey, int haveExcl, int *__restrict__ tileGhost)
+            const int *__restrict__ bpairOffset, const uint32_t *__restrict__ bpairKey, int haveExcl, int *__restrict__ tileGhost,
+            const TileWin *__restrict__ tileWin)
 {
+    // windowed pair kernel: this block is one tile; its rows hold offsets into the tile's window instead of slots
+    __shared__ TileWin sWin;
+    if (tileWin)
+    {
+        for (int k = threadIdx.x; k < (int)(sizeof(TileWin) / sizeof(int)); k += blockDim.x) ((int *)&sWin)[k] = ((const int *)(tileWin + blockIdx.x))[k];
+        __syncthreads();
+    }
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     int total = 0;
     bool ghostEntry = false;      // some entry of this row is a ghost slot (several ranks): the row waits for the halo
@@ -449,7 +573,20 @@ k_nbr_exact(int nIon, int nPad, int cap, const double4 *__restrict__ pos, BoxCon
                 dst = (int)((offB >> sh) & 0xffffull);
                 offB += 1ull << sh;
             }
-            out[(size_t)dst * nPad + i] = (e & 0x07ffffffu) | (e & EXCL_BIT);
+            uint32_t idx = e & 0x07ffffffu;
+            if (tileWin && sWin.nRuns > 0)
+            {
+                // the run that holds slot idx (runs ascend): binary search over at most WIN_MAXRUNS first slots
+                int lo = 0, hi = sWin.nRuns - 1;
+                while (lo < hi)
+                {
+                    const int mid = (lo + hi + 1) >> 1;
+                    if (sWin.lo[mid] <= (int)idx) lo = mid;
+                    else hi = mid - 1;
+                }
+                idx = (uint32_t)(sWin.off[lo] + ((int)idx - sWin.lo[lo]));
+            }
+            out[(size_t)dst * nPad + i] = idx | (e & EXCL_BIT);
         }
         count[i] = total;
     }

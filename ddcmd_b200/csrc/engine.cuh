@@ -54,12 +54,15 @@ struct GridDev
     int maxRaw;      // max candidate count over beads (fp32 filter pass)
     int nInterior;   // several ranks: k_pair tiles whose rows touch no ghost slot
     int bondTotal;   // bonded (term, endpoint) records of the resident local beads
+    int winMaxTotal; // largest tile window (beads)
+    int winGlobal;   // tiles whose window did not fit
     unsigned long long totalEntries;
 };
 
 struct PairConst
 {
     double rc2, R2cut, hxx, hyy, hzz, hhx, hhy, hhz;
+    double ihx, ihy, ihz;        // reciprocal box edges
     double keR, krf, crf;
     double rmax;
     double binEdge[NBINS - 1];   // r edges of the build-time distance bins
@@ -72,6 +75,27 @@ struct PairConst
 __host__ __device__ inline uint64_t packW(int lj, int qi, uint32_t mol, uint32_t bead)
 {
     return (uint64_t)(lj & 0xff) | ((uint64_t)(qi & 0xff) << 8) | ((uint64_t)(mol & 0xffff) << 16) | ((uint64_t)bead << 32);
+}
+
+// Window of one k_pair tile (TILE consecutive slots): the slot runs that hold every partner of the tile's rows (the union of the
+// stencil cells of the tile's cells), staged in shared memory by the windowed pair kernel.  Entries of a windowed tile's rows are
+// offsets into the window; nRuns = 0: the window did not fit (or windows are off) and the entries are slots.
+#define WIN_MAXRUNS 30
+struct TileWin
+{
+    int nRuns, total;
+    int lo[WIN_MAXRUNS];        // first slot of each run, ascending
+    int off[WIN_MAXRUNS + 1];   // window offset of each run's first bead; off[nRuns] = total
+    int pad;
+};
+
+// entry of a row -> slot
+__host__ __device__ inline int winSlot(const TileWin &w, int idx)
+{
+    if (w.nRuns == 0) return idx;
+    int r = 0;
+    while (r + 1 < w.nRuns && w.off[r + 1] <= idx) r++;
+    return w.lo[r] + (idx - w.off[r]);
 }
 
 struct Term
@@ -188,7 +212,7 @@ struct ddcb200_ctx
     DevBuf<int> bondCsrOff;       // nGlobal + 1: entries of bead b = bondEnt[bondCsrOff[b] .. bondCsrOff[b + 1])
     DevBuf<uint32_t> bondEnt;     // (term << 2) | role of the bead in the term; term >= nTerms = restraint term - nTerms
     DevBuf<BondRec> bondRec;      // slot order, refreshed at every list build
-    DevBuf<int> bondCount, bondStart;
+    DevBuf<int> bondCount, bondStart, scanBlocks;
     int nBondRec = 0;             // records of the resident local beads (set at the list build)
     DevBuf<double> restrParm;     // 7 doubles: frac0[3], kb, fc[3]
     int restrOrigin = 0;
@@ -215,7 +239,12 @@ struct ddcb200_ctx
     DevBuf<double> posBuild[3];   // build-time positions, slot order (displacement bound)
     unsigned long long *dmax2 = nullptr;   // device: [0] bits of the max squared displacement of a LOCAL bead since the build, [1] of a ghost
     bool walkPerBead = true;      // DDCB200_WALK
-    int pairVariant = 2;          // DDCB200_PAIR: index into the k_pair2 instantiations of api.cu (-1: the round-1 kernel)
+    int pairVariant = 2;          // DDCB200_PAIR
+    bool bondedCapped = false;    // DDCB200_BONDED=capped
+    bool pairWindows = false;     // DDCB200_PAIR=win: rows hold window offsets, k_pair3 gathers from shared memory
+    int winMax = 0;               // beads a window may hold (from the shared memory of the device)
+    DevBuf<TileWin> tileWin;
+    int winMaxTotal = 0;          // largest window of the current list: index into the k_pair2 instantiations of api.cu (-1: the round-1 kernel)
     DevBuf<float> dispOfSlot;     // each local bead's own displacement since the build, rounded up (0 right after a build)
     DevBuf<double> mmPartial;
     GridDev *grid = nullptr;      // device

@@ -375,3 +375,208 @@ k_pair2(int nIon, int nPad, const int *__restrict__ tileOrder, int tileBase, con
         }
     }
 }
+
+
+// ---- k_pair3: the tile's partners staged in shared memory --------------------------------------------------------------------
+// ncu on k_pair2 mid-cycle (profiles/r02d_k_pair2_ncu_full.txt): l1tex data-pipe wavefronts 83 % of peak - every gathered partner
+// is one 32-byte sector of its own, one wavefront each, whatever the hit rate.  Here the partners of a tile's rows come from
+// shared memory instead: the tile's WINDOW (the slot runs of the stencil cells of the tile's cells, k_tile_window) is copied in
+// with coalesced loads, split into {x, y} and {z, w} arrays so that a warp-wide gather of 16-byte halves spreads over all 32
+// banks, and the rows hold window offsets.  Two threads per bead walk the even and the odd entries of the row (twice the
+// warps for the same window) and are added with one shuffle, in a fixed order.  Tiles whose window did not fit keep slot
+// entries and gather from global memory as k_pair2 does.
+struct PairAcc
+{
+    double fx, fy, fz, eLJ, eEle, vxx, vyy, vzz, vxy, vxz, vyz;
+};
+
+template <bool ENERGY, bool WIN>
+__device__ __forceinline__ void pairWalk3(PairAcc &A, const double4 pi, int ti, double kqi, int n, int nmax, int h, const uint32_t *__restrict__ row,
+                                          int nPad, const double4 *__restrict__ pos, const double2 *__restrict__ sA, const double2 *__restrict__ sB,
+                                          const double2 *__restrict__ ljRow, const double *__restrict__ sQ, const double *__restrict__ sShiftRow,
+                                          const PairConst &pc)
+{
+    const bool charged = kqi != 0.0;
+    const double twoKrf = 2.0 * pc.krf;
+    // this thread's entries: k = h, h + 2, ...; two of them in flight
+    for (int k0 = h; k0 < nmax; k0 += 4)
+    {
+        uint32_t e[2];
+        double4 pj[2];
+#pragma unroll
+        for (int u = 0; u < 2; u++)
+        {
+            const int k = k0 + 2 * u;
+            e[u] = 0u;
+            if (k < n)
+            {
+                e[u] = row[(size_t)k * nPad];
+                const uint32_t idx = e[u] & 0x07ffffffu;
+                if (WIN)
+                {
+                    const double2 a = sA[idx], b = sB[idx];
+                    pj[u] = make_double4(a.x, a.y, b.x, b.y);
+                }
+                else pj[u] = ldPos(pos + idx);
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < 2; u++)
+        {
+            const bool have = k0 + 2 * u < n;
+            double x = pi.x - pj[u].x, y = pi.y - pj[u].y, z = pi.z - pj[u].z;
+            double r2 = x * x + y * y + z * z;
+            if (have && r2 > pc.R2cut)
+            {
+                // nearestImage_fast: one lattice reduction per component (src/preduce.c:147-160)
+                if (x > pc.hhx) x -= pc.hxx;
+                if (x < -pc.hhx) x += pc.hxx;
+                if (y > pc.hhy) y -= pc.hyy;
+                if (y < -pc.hhy) y += pc.hyy;
+                if (z > pc.hhz) z -= pc.hzz;
+                if (z < -pc.hhz) z += pc.hzz;
+                r2 = x * x + y * y + z * z;
+            }
+            if (have && r2 < pc.rc2)
+            {
+                const uint64_t wj = (uint64_t)__double_as_longlong(pj[u].w);
+                const bool excl = (e[u] & EXCL_BIT) != 0u;
+                const double ir1 = rsqrtFast(r2);
+                const double ir2 = ir1 * ir1;
+                double dvdr = 0.0;
+                if (!excl)
+                {
+                    const double2 cc = ljRow[wj & 0xff];
+                    const double ir6 = ir2 * ir2 * ir2;
+                    const double a6 = cc.x * ir6, a12 = cc.y * ir6 * ir6;
+                    dvdr = (a6 - a12) * ir2;
+                    if (ENERGY) A.eLJ += (a12 * (1.0 / 12.0) - a6 * (1.0 / 6.0)) + sShiftRow[wj & 0xff];
+                }
+                if (charged)
+                {
+                    const double kqij = kqi * sQ[(wj >> 8) & 0xff];
+                    const double ir = excl ? 0.0 : ir1;
+                    dvdr += kqij * (twoKrf - ir2 * ir);
+                    if (ENERGY) A.eEle += kqij * (ir + pc.krf * r2 - pc.crf);
+                }
+                const double fxij = -dvdr * x, fyij = -dvdr * y, fzij = -dvdr * z;
+                A.fx += fxij;
+                A.fy += fyij;
+                A.fz += fzij;
+                if (ENERGY)
+                {
+                    A.vxx += fxij * x;
+                    A.vyy += fyij * y;
+                    A.vzz += fzij * z;
+                    A.vxy += fxij * y;
+                    A.vxz += fxij * z;
+                    A.vyz += fyij * z;
+                }
+            }
+        }
+    }
+    (void)ti;
+}
+
+#define PAIR3_THREADS (2 * TILE)
+template <bool ENERGY>
+__global__ void __launch_bounds__(PAIR3_THREADS, 2)
+k_pair3(int nIon, int nPad, const int *__restrict__ tileOrder, int tileBase, const double4 *__restrict__ pos, const uint32_t *__restrict__ nbr,
+        const uint16_t *__restrict__ cum, const unsigned long long *__restrict__ dmax2, int withGhosts, const float *__restrict__ dispOfSlot,
+        const TileWin *__restrict__ tileWin, int wcap, const double2 *__restrict__ ljTab, const double *__restrict__ shiftTab,
+        const double *__restrict__ qTab, PairConst pc, double *__restrict__ fx, double *__restrict__ fy, double *__restrict__ fz,
+        double *__restrict__ accPartial)
+{
+    EXTERN_SHARED(double2, sLJ);               // ntypes*ntypes {6 c6, 12 c12}
+    const int nt2 = pc.ntypes * pc.ntypes;
+    double *sQ = (double *)(sLJ + nt2);        // 256 charges
+    double *sShift = sQ + 256;                 // ntypes*ntypes (read by the ENERGY instantiation only)
+    double2 *sA = (double2 *)(sShift + nt2 + (nt2 & 1));      // window {x, y}, 16-byte aligned
+    double2 *sB = sA + wcap;                                  // window {z, w}
+    __shared__ TileWin sWin;
+    const int tile = tileOrder ? tileOrder[tileBase + blockIdx.x] : (int)blockIdx.x;
+    for (int k = threadIdx.x; k < (int)(sizeof(TileWin) / sizeof(int)); k += blockDim.x) ((int *)&sWin)[k] = ((const int *)(tileWin + tile))[k];
+    for (int k = threadIdx.x; k < nt2; k += blockDim.x)
+    {
+        const double2 c = ljTab[k];
+        sLJ[k] = make_double2(6.0 * c.x, 12.0 * c.y);
+        sShift[k] = shiftTab[k];
+    }
+    for (int k = threadIdx.x; k < 256; k += blockDim.x) sQ[k] = qTab[k];
+    __syncthreads();
+    const bool windowed = sWin.nRuns > 0;
+    if (windowed)
+    {
+        for (int r = 0; r < sWin.nRuns; r++)
+        {
+            const int lo = sWin.lo[r], o = sWin.off[r], cnt = sWin.off[r + 1] - o;
+            for (int q = threadIdx.x; q < cnt; q += blockDim.x)
+            {
+                const double4 p = ldPos(pos + lo + q);
+                sA[o + q] = make_double2(p.x, p.y);
+                sB[o + q] = make_double2(p.z, p.w);
+            }
+        }
+        __syncthreads();
+    }
+
+    const int h = threadIdx.x & 1;
+    const int i = tile * TILE + (threadIdx.x >> 1);
+    const int ii = i < nIon ? i : 0;
+    const double4 pi = ldPos(pos + ii);
+    const uint64_t wi = (uint64_t)__double_as_longlong(pi.w);
+    const bool live = i < nIon && !(wi >> 63);
+    const int ti = (int)(wi & 0xff);
+    const double qi = sQ[(wi >> 8) & 0xff];
+    const double kqi = pc.keR * qi;
+    int binLimit = 0;
+    {
+        unsigned long long db = dmax2[0];
+        if (withGhosts) db = max(db, dmax2[1]);
+        const double dmax = sqrt(__longlong_as_double((long long)db));
+        const double di = (live && dispOfSlot) ? fmin((double)dispOfSlot[ii], dmax) : dmax;
+        const double lim = (pc.rmax + pc.listSlack + dmax + di) * (1.0 + 1e-12);
+#pragma unroll
+        for (int e = 0; e < NBINS - 1; e++) binLimit += (pc.binEdge[e] < lim) ? 1 : 0;
+    }
+    const int n = live ? (int)cum[(size_t)binLimit * nPad + ii] : 0;
+    int nmax = n;
+    for (int o = 16; o > 0; o >>= 1) nmax = max(nmax, __shfl_xor_sync(0xffffffffu, nmax, o));
+
+    PairAcc A = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+    if (windowed)
+        pairWalk3<ENERGY, true>(A, pi, ti, kqi, n, nmax, h, nbr + ii, nPad, pos, sA, sB, sLJ + ti * pc.ntypes, sQ, sShift + ti * pc.ntypes, pc);
+    else
+        pairWalk3<ENERGY, false>(A, pi, ti, kqi, n, nmax, h, nbr + ii, nPad, pos, sA, sB, sLJ + ti * pc.ntypes, sQ, sShift + ti * pc.ntypes, pc);
+    // the two halves of a row, added in a fixed order: even entries + odd entries
+    A.fx += __shfl_xor_sync(0xffffffffu, A.fx, 1);
+    A.fy += __shfl_xor_sync(0xffffffffu, A.fy, 1);
+    A.fz += __shfl_xor_sync(0xffffffffu, A.fz, 1);
+    if (live && h == 0)
+    {
+        fx[i] = A.fx;
+        fy[i] = A.fy;
+        fz[i] = A.fz;
+    }
+    if (ENERGY)
+    {
+        // every pair is visited from both ends: halve.  Self term -0.5 q_i^2 keR crf (src/bioMartini.c:1031-1035), once per bead
+        double v[8] = {0.5 * A.eLJ, 0.5 * A.eEle + ((live && h == 0) ? -0.5 * qi * qi * pc.keR * pc.crf : 0.0),
+                       0.5 * A.vxx, 0.5 * A.vyy, 0.5 * A.vzz, 0.5 * A.vxy, 0.5 * A.vxz, 0.5 * A.vyz};
+        __shared__ double red[8][PAIR3_THREADS / 32];
+#pragma unroll
+        for (int a = 0; a < 8; a++)
+        {
+            double t = v[a];
+            for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+            if ((threadIdx.x & 31) == 0) red[a][threadIdx.x >> 5] = t;
+        }
+        __syncthreads();
+        if (threadIdx.x < 8)
+        {
+            double t = 0.0;
+            for (int w = 0; w < PAIR3_THREADS / 32; w++) t += red[threadIdx.x][w];
+            accPartial[(size_t)tile * 8 + threadIdx.x] = t;
+        }
+    }
+}
