@@ -361,9 +361,17 @@ class Simulate:
         return h
 
     def getRandom(self):
-        """current per-bead LCG64 states, input order"""
+        """current per-bead LCG64 states, input order.  On several ranks (collective call over the caller's torch.distributed
+        group) every rank's entries for its own local beads are merged: a bead's state is current only where the bead lives."""
         st = np.empty(self.deck.n, np.uint64)
         self._ck(lib().ddcb200_getRandom(self.ctx, st.size, st.ctypes.data_as(_P(C.c_uint64))))
+        if self.nranks > 1:
+            import torch.distributed as dist
+            beads = self.getLocalBeads()
+            parts = [None] * dist.get_world_size()
+            dist.all_gather_object(parts, (beads, st[beads]))
+            for b, v in parts:
+                st[b] = v
         return st
 
     def constraintFailures(self):

@@ -1809,7 +1809,9 @@ static int nglfcSteps(ddcb200_ctx *c, int nsteps, double dt, const bool baro, co
 {
     if (!c || nsteps < 0) return fail(DDCB200_ERR_ARG, "bad arguments");
     if (c->nLocal == 0) return fail(DDCB200_ERR_STATE, "no state");
-    if (c->nranks > 1) return fail(DDCB200_ERR_STATE, "LANGEVIN groups / nglfconstraint run on one GPU in this version (per-bead random streams and the box are not exchanged)");
+    // several ranks (src/nglfconstraint.c:510-574 runs on any task count): the per-bead random state travels with a migrating bead
+    // (k_rd_pack), the barostat works on the all-reduced virial so every rank scales its box and its beads alike, constraint
+    // clusters are solved on the rank that owns their molecule
     if (c->anyLangevin && !c->haveRandom) return fail(DDCB200_ERR_STATE, "LANGEVIN groups need the per-bead random state (setRandom)");
     CK(cudaSetDevice(c->device));
     int rc;

@@ -252,6 +252,12 @@ k_constraint(int nCons, const int *__restrict__ atomOffset, const int *__restric
     const int a0 = atomOffset[c], na = atomOffset[c + 1] - a0;
     const int p0 = pairOffset[c], np = pairOffset[c + 1] - p0;
     if (np == 0) return;
+    {
+        // several ranks: a cluster is solved where its molecule is local (molecules are whole on their owner); elsewhere its
+        // beads are absent or ghosts
+        const int s0 = slotOfBead[atomBead[a0]];
+        if (s0 < 0 || ((((unsigned long long)__double_as_longlong(pos[s0].w)) >> 63) != 0ull)) return;
+    }
     int slot[CONS_MAXATOM];
     double rMass[CONS_MAXATOM], r[CONS_MAXATOM][3], v[CONS_MAXATOM][3];
     double rab[CONS_MAXPAIR][3];

@@ -28,6 +28,7 @@
 #include "codata.h"
 #include "box.h"
 #include "bioCharmmParms.h"
+#include "neighbor.h"
 void charmmResidues(SYSTEM *sys, CHARMMPOT_PARMS *parms);
 #include "../include/ddcmd_b200_host.h"
 
@@ -158,12 +159,23 @@ int b200_install(SIMULATE *simulate, const char *objectFile, const char *restart
     if (ddcb200_deckLoad(objectFile, restartFile, simulate->name, &b200deck)) ck(-1, "b200_install", ddcb200_lastHostError());
     if (ddcb200_simulateBind(b200deck, device, &b200)) ck(-1, "b200_install", ddcb200_lastHostError());
     int found = 0;
+    sys->neighborTableType = 0;
     for (int i = 0; i < sys->npotential; i++)
     {
         POTENTIAL *p = sys->potential[i];
-        if (strcmp(p->type, "MARTINI") == 0) { p->eval_potential = martiniB200; found = 1; }
+        if (strcmp(p->type, "MARTINI") == 0)
+        {
+            /* what martini_parms() does when an accelerator is configured (src/bioMartini.c:1337-1345): the pair list lives on the
+             * device, so ddcUpdateAll calls constructList() - a stub in a CPU build; the library rebuilds its own list on the same
+             * schedule inside ddcb200_ddcenergy - instead of neighbors1(), and ddcMD no longer builds its CPU pair list next to ours */
+            p->eval_potential = martiniB200;
+            p->use_gpu_list = 1;
+            p->neighborTableType = NEIGHBORTABLE_GPU;
+            found = 1;
+        }
         else if (strcmp(p->type, "RESTRAINT") == 0) p->eval_potential = noPotential;
         else ck(-1, "b200_install", "only MARTINI and RESTRAINT potentials can be bound");
+        sys->neighborTableType |= p->neighborTableType;      /* system_init's rule, src/system.c:202-206 */
     }
     if (!found) ck(-1, "b200_install", "no MARTINI potential in the SYSTEM");
     if (mode == 2)

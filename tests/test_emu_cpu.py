@@ -151,6 +151,13 @@ def test_emu_four_and_eight_ranks_match_reference(emu_handle, nproc, name, latti
     assert r.returncode == 0 and "MGPU_OK" in r.stdout, r.stdout[-2000:] + r.stderr[-4000:]
 
 
+def test_emu_two_ranks_nglfconstraint(emu_handle):
+    """NGLFCONSTRAINT (LANGEVIN groups, velocity constraints, barostat) on 2 emulated ranks against the single-rank reference trace:
+    the per-bead random streams follow migrating beads bit for bit, the barostat works on the all-reduced virial."""
+    r = _torchrun(2, 29571, "mgpu_nglfc_worker.py", "ras_small", "full", env={"DDCB200_TEST_EMU": "1", "DDCB200_NGLFC_STEPS": "22"})
+    assert r.returncode == 0 and "MGPU_NGLFC_OK" in r.stdout, r.stdout[-2000:] + r.stderr[-4000:]
+
+
 def test_emu_bench_contract_two_ranks(emu_handle):
     """bench.py's multi-rank arm end to end (rank plumbing, max-over-ranks timing, one JSON line from rank 0)."""
     import json

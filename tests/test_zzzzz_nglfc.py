@@ -74,3 +74,17 @@ def test_nglf_with_langevin_groups_is_the_unconstrained_pass(golden_dir, tmp_pat
     etot = tr[9, 1] + tr[9, 2]
     assert abs((e.eion + e.rk) - etot) <= 1e-10 * max(abs(etot), abs(tr[9, 2]))
     sim.close()
+
+
+@pytest.mark.parametrize("nproc,deck,variant,lattice", [(2, "ras_small", "full", ()), (2, "waterbox", "full", ()), (4, "popc_small", "full", (2, 2, 1))])
+def test_nglfconstraint_on_several_gpus(nproc, deck, variant, lattice):
+    """The same traces with the system decomposed over 2 / 4 GPUs (tests/mgpu_nglfc_worker.py)."""
+    import subprocess
+    import sys
+    if dd.lib().ddcb200_deviceCount() < nproc:
+        pytest.skip("needs %d GPUs" % nproc)
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=%d" % nproc, "--master-addr", "127.0.0.1",
+           "--master-port", "29541", os.path.join(root, "tests", "mgpu_nglfc_worker.py"), deck, variant] + [str(x) for x in lattice]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0 and "MGPU_NGLFC_OK" in r.stdout, r.stdout[-3000:] + r.stderr[-6000:]
