@@ -50,7 +50,8 @@ k_paircorr(int nIon, const double4 *__restrict__ pos, const int *__restrict__ ce
             {
                 const int ax = ((x0 + dx) % nx + nx) % nx;
                 const int cc = ax + nx * (ay + ny * az);
-                for (int j = cellStart[cc]; j < cellStart[cc + 1]; j++)
+                for (int part = 0; part < 2; part++)      // the cell's local beads, then its ghosts
+                for (int j = cellStart[cc + part * nx * ny * nz]; j < cellStart[cc + part * nx * ny * nz + 1]; j++)
                 {
                     const double4 pj = pos[j];
                     const int bj = (int)((((uint64_t)__double_as_longlong(pj.w)) >> 32) & 0x7fffffffull);

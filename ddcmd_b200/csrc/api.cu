@@ -261,7 +261,13 @@ static int createInit(ddcb200_ctx *c)
         else c->pairVariant = -2;
         if (c->pairVariant == -2) return fail(DDCB200_ERR_ARG, "DDCB200_PAIR must be old or one of the built <pf>,<minb> pairs");
     }
-    if (const char *bm = getenv("DDCB200_BONDED")) c->bondedCapped = strcmp(bm, "capped") == 0;      // A/B: 64-register build of k_bonded
+    if (const char *bm = getenv("DDCB200_BONDED"))
+    {
+        // A/B: CTAs per SM the registers of k_bonded are capped for (1 = no cap; 8 = 64 registers, the default: the kernel is
+        // latency-bound and gains more from resident warps than it loses to the spills of its rare dihedral path)
+        c->bondedCap = atoi(bm);
+        if (c->bondedCap != 1 && c->bondedCap != 8 && c->bondedCap != 10 && c->bondedCap != 12) return fail(DDCB200_ERR_ARG, "DDCB200_BONDED must be 1, 8, 10 or 12");
+    }
     if (const char *hm = getenv("DDCB200_HALO"))
     {
         // several ranks: "overlap" (default) = the ghost halo runs on its own stream beside the pair rows that read no ghost,
@@ -641,8 +647,8 @@ static int ensureAux(ddcb200_ctx *c, int64_t nIon)
     CK(c->rank0.ensure((size_t)nPad));
     CK(c->member.ensure((size_t)nPad));
     CK(c->perm.ensure((size_t)nPad));
-    CK(c->cellCount.ensure((size_t)nIon + 8));
-    CK(c->cellStart.ensure((size_t)nIon + 8));
+    CK(c->cellCount.ensure(2 * (size_t)nIon + 16));      // local cells, then ghost cells
+    CK(c->cellStart.ensure(2 * (size_t)nIon + 16));
     CK(c->nbrCount.ensure((size_t)nPad));
     CK(c->nbrRawCount.ensure((size_t)nPad));
     CK(c->nbrCum.ensure((size_t)nPad * NBINS));
@@ -1088,7 +1094,7 @@ extern "C" int ddcb200_constructList(ddcb200_ctx *c)
     const int mmBlocks = std::min(1024, (nIon + 255) / 256);
     LAUNCH(k_minmax_partial, mmBlocks, 256, 0, st)(c->pos4[cur].p, nIon, c->box, c->mmPartial.p);
     LAUNCH(k_grid_setup, 1, 32, 0, st)(c->mmPartial.p, mmBlocks, nIon, c->box, c->grid, maxCells);
-    CK(cudaMemsetAsync(c->cellCount.p, 0, (size_t)(nIon + 8) * sizeof(int), st));
+    CK(cudaMemsetAsync(c->cellCount.p, 0, (2 * (size_t)nIon + 16) * sizeof(int), st));
     const int nb = (nIon + 255) / 256;
     LAUNCH(k_cell_count, nb, 256, 0, st)(c->pos4[cur].p, nIon, c->box, c->grid, c->cellOfSlot[cur].p, c->rank0.p, c->cellCount.p,
                                      c->beadOfSlot[cur].p, c->orderKey.p);
@@ -1140,15 +1146,17 @@ extern "C" int ddcb200_constructList(ddcb200_ctx *c)
         LAUNCH(k_scan_add, nsb, SCAN_BLOCK, 0, st)(nIon, c->bondStart.p, c->scanBlocks.p);
         CKL("k_scan_add");
     }
+    // after the cell sort the local beads are slots [0, nLocal): rows, tiles and every per-bead kernel cover that range only
+    const int tilesL = (nLocal + TILE - 1) / TILE;
     if (c->nranks > 1)
     {
-        CK(c->tileGhost.ensure((size_t)(nPad / TILE) + 1));
-        CK(c->tileOrder.ensure((size_t)(nPad / TILE) + 1));
+        CK(c->tileGhost.ensure((size_t)tilesL + 1));
+        CK(c->tileOrder.ensure((size_t)tilesL + 1));
     }
     if (c->pairWindows)
     {
-        CK(c->tileWin.ensure((size_t)(nPad / TILE) + 1));
-        LAUNCH(k_tile_window, (nPad / TILE + 3) / 4, 128, 0, st)(nIon, nPad / TILE, c->cellOfSlot[nxt].p, c->cellStart.p, c->grid, c->winMax, c->tileWin.p);
+        CK(c->tileWin.ensure((size_t)tilesL + 1));
+        LAUNCH(k_tile_window, (tilesL + 3) / 4, 128, 0, st)(nLocal, tilesL, c->cellOfSlot[nxt].p, c->cellStart.p, c->grid, c->winMax, c->tileWin.p);
         CKL("k_tile_window");
     }
     for (int attempt = 0; attempt < 4; attempt++)
@@ -1156,10 +1164,10 @@ extern "C" int ddcb200_constructList(ddcb200_ctx *c)
         CK(c->nbr.ensure((size_t)c->nbrCap * nPad));
         CK(c->nbrRaw.ensure((size_t)c->nbrCap * nPad));
         CK(cudaEventRecord(c->evList[0], st));
-        LAUNCH(k_nbr_filter, nPad / 128, 128, 0, st)(nIon, nPad, c->pos32.p, c->cellOfSlot[nxt].p, c->cellStart.p, c->box, rl2f, c->grid,
-                                                c->nbrCap, c->nbrRaw.p, c->nbrRawCount.p);
+        LAUNCH(k_nbr_filter, tilesL, 128, 0, st)(nLocal, nPad, c->pos32.p, c->cellOfSlot[nxt].p, c->cellStart.p, c->box, rl2f, c->grid,
+                                            c->nbrCap, c->nbrRaw.p, c->nbrRawCount.p);
         CKL("k_nbr_filter");
-        LAUNCH(k_nbr_exact, nPad / 128, 128, 0, st)(nIon, nPad, c->nbrCap, c->pos4[nxt].p, c->box, c->grid, c->nbrRaw.p, c->nbrRawCount.p,
+        LAUNCH(k_nbr_exact, tilesL, 128, 0, st)(nLocal, nPad, c->nbrCap, c->pos4[nxt].p, c->box, c->grid, c->nbrRaw.p, c->nbrRawCount.p,
                                                c->nbr.p, c->nbrCount.p, c->nbrCum.p, c->gidOfBead.p, c->molTypeOfBead.p,
                                                c->molTypeSingle.p, c->bpairOffset.p, c->bpairKey.p, c->haveExcl ? 1 : 0,
                                                c->nranks > 1 ? c->tileGhost.p : nullptr, c->pairWindows ? c->tileWin.p : nullptr);
@@ -1167,7 +1175,7 @@ extern "C" int ddcb200_constructList(ddcb200_ctx *c)
         CK(cudaEventRecord(c->evList[1], st));
         if (c->nranks > 1)
         {
-            LAUNCH(k_tile_order, 1, 1024, 0, st)(nPad / TILE, c->tileGhost.p, c->tileOrder.p, c->grid);
+            LAUNCH(k_tile_order, 1, 1024, 0, st)(tilesL, c->tileGhost.p, c->tileOrder.p, c->grid);
             CKL("k_tile_order");
         }
         CK(cudaMemcpyAsync(c->gridHost, c->grid, sizeof(GridDev), cudaMemcpyDeviceToHost, st));
@@ -1219,7 +1227,7 @@ extern "C" int ddcb200_constructList(ddcb200_ctx *c)
     c->lastBuildLoop = c->loop;
     c->totalEntries = (int64_t)c->gridHost->totalEntries;
     c->nPairsListed = (int64_t)(c->gridHost->totalEntries / 2);
-    c->nTilesInterior = c->nranks > 1 ? c->gridHost->nInterior : nPad / TILE;
+    c->nTilesInterior = c->nranks > 1 ? c->gridHost->nInterior : tilesL;
     c->winMaxTotal = c->gridHost->winMaxTotal;
     return DDCB200_OK;
 }
@@ -1350,8 +1358,8 @@ extern "C" int ddcb200_ddcenergy(ddcb200_ctx *c, int withEnergy)
     }
     cudaStream_t st = c->stream;
     const int cur = c->cur;
-    const int nLocal = (int)c->nIon, nPad = (int)c->nPad;
-    const int tiles = nPad / TILE;
+    const int nLocal = (int)c->nLocal, nPad = (int)c->nPad;      // local beads = slots [0, nLocal)
+    const int tiles = (nLocal + TILE - 1) / TILE;
     if (withEnergy) CK(cudaMemsetAsync(c->acc, 0, ACC_N * sizeof(double), st));
     {
         const size_t smem = pairSmemBytes(c->ntypes);
@@ -1411,9 +1419,15 @@ extern "C" int ddcb200_ddcenergy(ddcb200_ctx *c, int withEnergy)
         if (withEnergy)
             LAUNCH((k_bonded<true, 1>), bBlocks, BONDED_THREADS, 0, st)(c->nBondRec, c->bondRec.p, c->restrParm.p, c->restrOrigin, c->pos4[cur].p, c->pc,
                                                                     c->frc[0].p, c->frc[1].p, c->frc[2].p, c->bondPartial.p);
-        else if (c->bondedCapped)
+        else if (c->bondedCap == 8)
             LAUNCH((k_bonded<false, 8>), bBlocks, BONDED_THREADS, 0, st)(c->nBondRec, c->bondRec.p, c->restrParm.p, c->restrOrigin, c->pos4[cur].p, c->pc,
                                                                      c->frc[0].p, c->frc[1].p, c->frc[2].p, c->bondPartial.p);
+        else if (c->bondedCap == 10)
+            LAUNCH((k_bonded<false, 10>), bBlocks, BONDED_THREADS, 0, st)(c->nBondRec, c->bondRec.p, c->restrParm.p, c->restrOrigin, c->pos4[cur].p, c->pc,
+                                                                      c->frc[0].p, c->frc[1].p, c->frc[2].p, c->bondPartial.p);
+        else if (c->bondedCap == 12)
+            LAUNCH((k_bonded<false, 12>), bBlocks, BONDED_THREADS, 0, st)(c->nBondRec, c->bondRec.p, c->restrParm.p, c->restrOrigin, c->pos4[cur].p, c->pc,
+                                                                      c->frc[0].p, c->frc[1].p, c->frc[2].p, c->bondPartial.p);
         else
             LAUNCH((k_bonded<false, 1>), bBlocks, BONDED_THREADS, 0, st)(c->nBondRec, c->bondRec.p, c->restrParm.p, c->restrOrigin, c->pos4[cur].p, c->pc,
                                                                      c->frc[0].p, c->frc[1].p, c->frc[2].p, c->bondPartial.p);
@@ -1441,9 +1455,9 @@ static int launchIntegrate(ddcb200_ctx *c, double halfDt2, double halfDt1, doubl
 {
     ProfScope ps(c, PROF_INTEGRATE);
     const int cur = c->cur;
-    const int tiles = (int)(c->nPad / TILE);
+    const int tiles = (int)((c->nLocal + TILE - 1) / TILE);      // local beads are slots [0, nLocal)
     if (MODE & INT_KICK1_DRIFT) c->haloDirty = true;
-    LAUNCH(k_integrate<MODE>, tiles, TILE, 0, c->stream)((int)c->nIon, c->pos4[cur].p, c->vel[cur][0].p, c->vel[cur][1].p, c->vel[cur][2].p,
+    LAUNCH(k_integrate<MODE>, tiles, TILE, 0, c->stream)((int)c->nLocal, c->pos4[cur].p, c->vel[cur][0].p, c->vel[cur][1].p, c->vel[cur][2].p,
                                                      c->frc[0].p, c->frc[1].p, c->frc[2].p, c->massOfBead.p, halfDt2, halfDt1, dt, c->pc,
                                                      c->kinPartial.p, c->posBuild[0].p, c->posBuild[1].p, c->posBuild[2].p, c->dmax2, c->dispOfSlot.p);
     CKL("k_integrate");
@@ -1456,7 +1470,7 @@ static int kineticTerms(ddcb200_ctx *c)
     int rc = launchIntegrate<INT_KE>(c, 0, 0, 0);
     if (rc) return rc;
     ProfScope ps(c, PROF_REDUCE);
-    return reduceCols(c, c->kinPartial.p, (int)(c->nPad / TILE), 7, c->colMap.p + 19);
+    return reduceCols(c, c->kinPartial.p, (int)((c->nLocal + TILE - 1) / TILE), 7, c->colMap.p + 19);
 }
 
 static int nglfcSteps(ddcb200_ctx *c, int nsteps, double dt, const bool baro, const bool cons);
@@ -1492,7 +1506,7 @@ extern "C" int ddcb200_nglf(ddcb200_ctx *c, int nsteps, double dt)
         rc = launchIntegrate<INT_KICK2 | INT_KE>(c, half, 0.0, 0.0);
         if (rc) return rc;
         ProfScope ps(c, PROF_REDUCE);
-        rc = reduceCols(c, c->kinPartial.p, (int)(c->nPad / TILE), 7, c->colMap.p + 19);
+        rc = reduceCols(c, c->kinPartial.p, (int)((c->nLocal + TILE - 1) / TILE), 7, c->colMap.p + 19);
         if (rc) return rc;
         c->kineticValid = true;
     }
@@ -1756,9 +1770,9 @@ static int launchNglfc(ddcb200_ctx *c, double halfDt, double dt, const double sc
 {
     ProfScope ps(c, PROF_INTEGRATE);
     const int cur = c->cur;
-    const int tiles = (int)(c->nPad / TILE);
+    const int tiles = (int)((c->nLocal + TILE - 1) / TILE);
     if (MODE & (NC_DRIFT | NC_SCALE)) c->haloDirty = true;
-    LAUNCH(k_nglfc<MODE>, tiles, TILE, 0, c->stream)((int)c->nIon, c->pos4[cur].p, c->vel[cur][0].p, c->vel[cur][1].p, c->vel[cur][2].p,
+    LAUNCH(k_nglfc<MODE>, tiles, TILE, 0, c->stream)((int)c->nLocal, c->pos4[cur].p, c->vel[cur][0].p, c->vel[cur][1].p, c->vel[cur][2].p,
                                                  c->frc[0].p, c->frc[1].p, c->frc[2].p, c->massOfBead.p, c->groupOfBead.p, c->rngState.p,
                                                  c->rngMP.p, groupTabOf(c), halfDt, dt, scale[0], scale[1], scale[2], c->pc, c->kinPartial.p,
                                                  c->posBuild[0].p, c->posBuild[1].p, c->posBuild[2].p, c->dmax2, c->dispOfSlot.p);
@@ -1873,7 +1887,7 @@ static int nglfcSteps(ddcb200_ctx *c, int nsteps, double dt, const bool baro, co
             if (rc) return rc;
         }
         ProfScope ps(c, PROF_REDUCE);
-        rc = reduceCols(c, c->kinPartial.p, (int)(c->nPad / TILE), 7, c->colMap.p + 19);
+        rc = reduceCols(c, c->kinPartial.p, (int)((c->nLocal + TILE - 1) / TILE), 7, c->colMap.p + 19);
         if (rc) return rc;
         c->kineticValid = true;
     }
@@ -1936,7 +1950,7 @@ extern "C" int64_t ddcb200_getPairs(ddcb200_ctx *c, int64_t capacity, int *beadI
     if (!c) return fail(DDCB200_ERR_ARG, "null ctx");
     if (!c->listValid) return fail(DDCB200_ERR_STATE, "no list built");
     if (cudaSetDevice(c->device) != cudaSuccess) return fail(DDCB200_ERR_CUDA, "cudaSetDevice");
-    const int n = (int)c->nIon, nPad = (int)c->nPad;   // ghost rows are empty
+    const int n = (int)c->nLocal, nPad = (int)c->nPad;   // rows exist for the local slots [0, nLocal)
     std::vector<int> cnt(n), bead((size_t)c->nIon);
     cudaStreamSynchronize(c->stream);
     if (cudaMemcpy(cnt.data(), c->nbrCount.p, n * sizeof(int), cudaMemcpyDeviceToHost) != cudaSuccess ||
@@ -1965,7 +1979,7 @@ extern "C" int64_t ddcb200_getPairs(ddcb200_ctx *c, int64_t capacity, int *beadI
     if (c->pairWindows)
     {
         // rows of windowed tiles hold window offsets: turn them back into slots
-        win.resize((size_t)(nPad / TILE));
+        win.resize((size_t)((n + TILE - 1) / TILE));
         if (cudaMemcpy(win.data(), c->tileWin.p, win.size() * sizeof(TileWin), cudaMemcpyDeviceToHost) != cudaSuccess)
             return fail(DDCB200_ERR_CUDA, "getPairs copy");
     }
@@ -1991,7 +2005,7 @@ extern "C" int ddcb200_pairSetHash(ddcb200_ctx *c, uint64_t out[6])
     } sc;
     CK(sc.h.ensure(8));
     CK(cudaMemsetAsync(sc.h.p, 0, 8 * sizeof(unsigned long long), c->stream));
-    LAUNCH(k_pair_hash, (int)((c->nIon + 255) / 256), 256, 0, c->stream)((int)c->nIon, (int)c->nPad, c->nbr.p, c->nbrCount.p, c->beadOfSlot[c->cur].p,
+    LAUNCH(k_pair_hash, (int)((c->nLocal + 255) / 256), 256, 0, c->stream)((int)c->nLocal, (int)c->nPad, c->nbr.p, c->nbrCount.p, c->beadOfSlot[c->cur].p,
                                                                      c->gidOfBead.p, c->pairWindows ? c->tileWin.p : nullptr, sc.h.p);
     CKL("k_pair_hash");
     CK(cudaMemcpyAsync(out, sc.h.p, 6 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, c->stream));
@@ -2194,7 +2208,13 @@ extern "C" int ddcb200_ddcInit(ddcb200_ctx *c, int rank, int nranks, int lx, int
     ncclComm_t comm;
     CKN(ncclCommInitRank(&comm, nranks, u, rank));
     c->nccl = (void *)comm;
-    CK(cudaStreamCreateWithFlags(&c->streamH, cudaStreamNonBlocking));
+    {
+        // the halo stream outranks the compute stream: its small kernels (pack, NCCL's send/recv, unpack) take the next free
+        // CTA slots instead of queueing behind the pair kernel's grid, so the exchange really runs beside the interior rows
+        int least = 0, greatest = 0;
+        CK(cudaDeviceGetStreamPriorityRange(&least, &greatest));
+        CK(cudaStreamCreateWithPriority(&c->streamH, cudaStreamNonBlocking, greatest));
+    }
     CK(cudaEventCreateWithFlags(&c->evPos, cudaEventDisableTiming));
     CK(cudaEventCreateWithFlags(&c->evHalo, cudaEventDisableTiming));
     CK(cudaMalloc((void **)&c->boxes, sizeof(DdcBoxes)));

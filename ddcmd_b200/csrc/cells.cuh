@@ -167,17 +167,21 @@ __global__ void k_cell_count(const double4 *__restrict__ pos, int n, BoxConst b,
     GridDev g = *gp;
     if (g.error & 2) return;
     int sub;
-    int c = cellIndexOf(pos[i], b, g, sub);
+    const double4 p = pos[i];
+    int c = cellIndexOf(p, b, g, sub);
+    // slots are ordered by (local before ghost, cell, sub-cell, bead): the sort key is the cell index, plus the number of cells
+    // for a ghost, so [0, nLocal) are exactly the local slots and every kernel over local beads runs over a dense range
+    if ((((unsigned long long)__double_as_longlong(p.w)) >> 63) != 0ull) c += g.ncell;
     cellOf[i] = c;
     orderKey[i] = ((uint64_t)sub << 32) | (uint32_t)beadOfSlot[i];
     rank0[i] = atomicAdd(&cellCount[c], 1);
 }
 
-// ---- 4. exclusive scan of the cell counts (one block; ncell ~ nion/25) -----------------
+// ---- 4. exclusive scan of the cell counts (one block; ncell ~ nion/25; local cells, then ghost cells) -----------------
 __global__ void k_cell_scan(const int *__restrict__ cnt, int *__restrict__ start, const GridDev *__restrict__ gp)
 {
     __shared__ int sums[1024];
-    const int n = gp->ncell;
+    const int n = 2 * gp->ncell;
     const int per = (n + blockDim.x - 1) / blockDim.x;
     const int lo = min(n, (int)threadIdx.x * per), hi = min(n, lo + per);
     int s = 0;
@@ -267,13 +271,13 @@ k_nbr_filter(int nIon, int nPad, const float4 *__restrict__ pos32, const int *__
     const float4 pi = pos32[i < nIon ? i : 0];
     if (i < nIon && pi.w == 0.0f)
     {
-        const int nx = gp->n[0], ny = gp->n[1], nz = gp->n[2];
+        const int nx = gp->n[0], ny = gp->n[1], nz = gp->n[2], ncell = nx * ny * nz;
         const float Lx = (float)b.hxx, Ly = (float)b.hyy, Lz = (float)b.hzz;
         const float hx2 = 0.5f * Lx, hy2 = 0.5f * Ly, hz2 = 0.5f * Lz;
         // with >= 3 cells along an axis a wrapped stencil cell has ONE possible image: shift it;
         // with fewer the stencil is deduplicated and each pair takes its nearest image
         const bool px = nx < 3, py = ny < 3, pz = nz < 3;
-        const int c = cellOf[i];
+        const int c = cellOf[i];         // a local slot: the plain cell index
         const int cx = c % nx, cy = (c / nx) % ny, cz = c / (nx * ny);
         const int lx = nx >= 3 ? -1 : 0, hx = nx >= 2 ? 1 : 0;
         const int ly = ny >= 3 ? -1 : 0, hy = ny >= 2 ? 1 : 0;
@@ -300,19 +304,23 @@ k_nbr_filter(int nIon, int nPad, const float4 *__restrict__ pos32, const int *__
                     else if (ax >= nx) { ax -= nx; sx = Lx; }
                     const float bx = px ? pi.x : pi.x - sx;
                     const int cc = ax + nx * (ay + ny * az);
-                    const int lo = cellStart[cc], hi = cellStart[cc + 1];
-                    for (int j = lo; j < hi; j++)
+                    // the cell's local beads, then (several ranks) its ghosts
+                    for (int part = 0; part < 2; part++)
                     {
-                        const float4 pj = pos32[j];
-                        float x = bx - pj.x, y = by - pj.y, z = bz - pj.z;
-                        if (px) { if (x > hx2) x -= Lx; if (x < -hx2) x += Lx; }
-                        if (py) { if (y > hy2) y -= Ly; if (y < -hy2) y += Ly; }
-                        if (pz) { if (z > hz2) z -= Lz; if (z < -hz2) z += Lz; }
-                        const float r2 = x * x + y * y + z * z;
-                        if (r2 < rl2f && j != i)
+                        const int lo = cellStart[cc + part * ncell], hi = cellStart[cc + part * ncell + 1];
+                        for (int j = lo; j < hi; j++)
                         {
-                            if (cnt < cap) raw[(size_t)cnt * nPad + i] = (uint32_t)j;
-                            cnt++;
+                            const float4 pj = pos32[j];
+                            float x = bx - pj.x, y = by - pj.y, z = bz - pj.z;
+                            if (px) { if (x > hx2) x -= Lx; if (x < -hx2) x += Lx; }
+                            if (py) { if (y > hy2) y -= Ly; if (y < -hy2) y += Ly; }
+                            if (pz) { if (z > hz2) z -= Lz; if (z < -hz2) z += Lz; }
+                            const float r2 = x * x + y * y + z * z;
+                            if (r2 < rl2f && j != i)
+                            {
+                                if (cnt < cap) raw[(size_t)cnt * nPad + i] = (uint32_t)j;
+                                cnt++;
+                            }
                         }
                     }
                 }
@@ -365,7 +373,7 @@ k_tile_window(int nIon, int nTiles, const int *__restrict__ cellOfSlot, const in
         last = __shfl_sync(0xffffffffu, c, 31);
     }
     __syncwarp();
-    bool fits = nCells <= 32;
+    bool fits = nCells <= 16;       // 16 cells x 27 stencil cells x 2 parts <= WIN_IDS
     int nIds = 0;
     if (fits)
     {
@@ -380,8 +388,13 @@ k_tile_window(int nIon, int nTiles, const int *__restrict__ cellOfSlot, const in
             if (ay < 0) ay += ny; else if (ay >= ny) ay -= ny;
             if (az < 0) az += nz; else if (az >= nz) az -= nz;
             const unsigned mk = __ballot_sync(0xffffffffu, ok);
-            if (ok) ids[nIds + __popc(mk & lt)] = ax + nx * (ay + ny * az);
-            nIds += __popc(mk);
+            // the cell's local beads and (several ranks) its ghosts: two slot ranges
+            if (ok)
+            {
+                ids[nIds + 2 * __popc(mk & lt)] = ax + nx * (ay + ny * az);
+                ids[nIds + 2 * __popc(mk & lt) + 1] = ax + nx * (ay + ny * az) + nx * ny * nz;
+            }
+            nIds += 2 * __popc(mk);
         }
         int np2 = 32;
         while (np2 < nIds) np2 <<= 1;

@@ -398,7 +398,11 @@ __device__ __forceinline__ void pairWalk3(PairAcc &A, const double4 pi, int ti, 
 {
     const bool charged = kqi != 0.0;
     const double twoKrf = 2.0 * pc.krf;
-    // this thread's entries: k = h, h + 2, ...; two of them in flight
+    // this thread's entries: k = h, h + 2, ...: two per trip, and the entries of the next trip are already in flight (the rows
+    // stream from HBM with no reuse; without the prefetch the walk waits a memory latency per trip)
+    uint32_t eNext[2];
+#pragma unroll
+    for (int u = 0; u < 2; u++) eNext[u] = (h + 2 * u < n) ? row[(size_t)(h + 2 * u) * nPad] : 0u;
     for (int k0 = h; k0 < nmax; k0 += 4)
     {
         uint32_t e[2];
@@ -406,11 +410,9 @@ __device__ __forceinline__ void pairWalk3(PairAcc &A, const double4 pi, int ti, 
 #pragma unroll
         for (int u = 0; u < 2; u++)
         {
-            const int k = k0 + 2 * u;
-            e[u] = 0u;
-            if (k < n)
+            e[u] = eNext[u];
+            if (k0 + 2 * u < n)
             {
-                e[u] = row[(size_t)k * nPad];
                 const uint32_t idx = e[u] & 0x07ffffffu;
                 if (WIN)
                 {
@@ -420,6 +422,8 @@ __device__ __forceinline__ void pairWalk3(PairAcc &A, const double4 pi, int ti, 
                 else pj[u] = ldPos(pos + idx);
             }
         }
+#pragma unroll
+        for (int u = 0; u < 2; u++) eNext[u] = (k0 + 4 + 2 * u < n) ? row[(size_t)(k0 + 4 + 2 * u) * nPad] : 0u;
 #pragma unroll
         for (int u = 0; u < 2; u++)
         {
@@ -510,11 +514,14 @@ k_pair3(int nIon, int nPad, const int *__restrict__ tileOrder, int tileBase, con
         for (int r = 0; r < sWin.nRuns; r++)
         {
             const int lo = sWin.lo[r], o = sWin.off[r], cnt = sWin.off[r + 1] - o;
+            // four independent loads per thread in flight (plain loads: the compiler may batch them)
+            const double2 *src = (const double2 *)(pos + lo);
+#pragma unroll 4
             for (int q = threadIdx.x; q < cnt; q += blockDim.x)
             {
-                const double4 p = ldPos(pos + lo + q);
-                sA[o + q] = make_double2(p.x, p.y);
-                sB[o + q] = make_double2(p.z, p.w);
+                const double2 a = src[2 * q], b = src[2 * q + 1];
+                sA[o + q] = a;
+                sB[o + q] = b;
             }
         }
         __syncthreads();
