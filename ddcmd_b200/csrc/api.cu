@@ -263,10 +263,17 @@ static int createInit(ddcb200_ctx *c)
     }
     if (const char *bm = getenv("DDCB200_BONDED"))
     {
-        // A/B: CTAs per SM the registers of k_bonded are capped for (1 = no cap; 8 = 64 registers, the default: the kernel is
-        // latency-bound and gains more from resident warps than it loses to the spills of its rare dihedral path)
+        // A/B: CTAs per SM the registers of k_bonded are capped for (1 = no cap: 0.115 ms per step on the 1M-bead membrane; 8: 0.080;
+        // 10: 0.078; 12 = 40 registers, the default: 0.073 - the kernel is latency-bound and gains more from resident warps than it
+        // loses to spills; profiles/r02h_variants.txt)
         c->bondedCap = atoi(bm);
         if (c->bondedCap != 1 && c->bondedCap != 8 && c->bondedCap != 10 && c->bondedCap != 12) return fail(DDCB200_ERR_ARG, "DDCB200_BONDED must be 1, 8, 10 or 12");
+    }
+    if (const char *fm = getenv("DDCB200_FILTER"))
+    {
+        // A/B: candidate pass with one warp per cell (default) or one thread per bead over consecutive slots
+        if (strcmp(fm, "bead") == 0) c->filterPerCell = false;
+        else if (strcmp(fm, "cell") != 0) return fail(DDCB200_ERR_ARG, "DDCB200_FILTER must be cell or bead");
     }
     if (const char *hm = getenv("DDCB200_HALO"))
     {
@@ -1164,8 +1171,20 @@ extern "C" int ddcb200_constructList(ddcb200_ctx *c)
         CK(c->nbr.ensure((size_t)c->nbrCap * nPad));
         CK(c->nbrRaw.ensure((size_t)c->nbrCap * nPad));
         CK(cudaEventRecord(c->evList[0], st));
-        LAUNCH(k_nbr_filter, tilesL, 128, 0, st)(nLocal, nPad, c->pos32.p, c->cellOfSlot[nxt].p, c->cellStart.p, c->box, rl2f, c->grid,
-                                            c->nbrCap, c->nbrRaw.p, c->nbrRawCount.p);
+        if (c->filterPerCell)
+        {
+            // one warp per cell; the grid covers the largest cell count the grid set-up accepts (the kernel reads the real one)
+            const int cellBlocks = (maxCells + 3) / 4;
+            if (c->gridSmall)
+                LAUNCH(k_nbr_filter_cell<true>, cellBlocks, 128, 0, st)(nPad, c->pos32.p, c->cellStart.p, c->box, rl2f, c->grid, c->nbrCap, c->nbrRaw.p,
+                                                                    c->nbrRawCount.p);
+            else
+                LAUNCH(k_nbr_filter_cell<false>, cellBlocks, 128, 0, st)(nPad, c->pos32.p, c->cellStart.p, c->box, rl2f, c->grid, c->nbrCap, c->nbrRaw.p,
+                                                                     c->nbrRawCount.p);
+        }
+        else
+            LAUNCH(k_nbr_filter, tilesL, 128, 0, st)(nLocal, nPad, c->pos32.p, c->cellOfSlot[nxt].p, c->cellStart.p, c->box, rl2f, c->grid,
+                                                c->nbrCap, c->nbrRaw.p, c->nbrRawCount.p);
         CKL("k_nbr_filter");
         LAUNCH(k_nbr_exact, tilesL, 128, 0, st)(nLocal, nPad, c->nbrCap, c->pos4[nxt].p, c->box, c->grid, c->nbrRaw.p, c->nbrRawCount.p,
                                                c->nbr.p, c->nbrCount.p, c->nbrCum.p, c->gidOfBead.p, c->molTypeOfBead.p,
@@ -1181,6 +1200,22 @@ extern "C" int ddcb200_constructList(ddcb200_ctx *c)
         CK(cudaMemcpyAsync(c->gridHost, c->grid, sizeof(GridDev), cudaMemcpyDeviceToHost, st));
         CK(cudaStreamSynchronize(st));
         if (c->gridHost->error & 2) return fail(DDCB200_ERR_CAPACITY, "cell grid larger than the bead count bound");
+        {
+            // the candidate pass was compiled for the cell grid of the previous build (three or more cells along every axis, or
+            // not): if this grid is smaller than assumed, redo the passes with the general instantiation
+            const bool small = c->gridHost->n[0] < 3 || c->gridHost->n[1] < 3 || c->gridHost->n[2] < 3;
+            const bool redo = small && !c->gridSmall && c->filterPerCell;
+            c->gridSmall = small;
+            if (redo)
+            {
+                CK(cudaMemsetAsync(&c->grid->error, 0, sizeof(int), st));
+                CK(cudaMemsetAsync(&c->grid->maxCount, 0, sizeof(int), st));
+                CK(cudaMemsetAsync(&c->grid->maxRaw, 0, sizeof(int), st));
+                CK(cudaMemsetAsync(&c->grid->totalEntries, 0, sizeof(unsigned long long), st));
+                attempt--;
+                continue;
+            }
+        }
         if (!(c->gridHost->error & 1))
         {
             CK(cudaEventElapsedTime(&c->listBuildMs, c->evList[0], c->evList[1]));

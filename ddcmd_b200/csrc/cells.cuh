@@ -337,6 +337,112 @@ k_nbr_filter(int nIon, int nPad, const float4 *__restrict__ pos32, const int *__
     }
 }
 
+// ---- 8b. the same candidate pass, one warp per cell ----------------------------------------------------------------------------
+// ncu on k_nbr_filter (profiles/r02c_k_nbr_filter_ncu_full.txt): 536 M warp instructions, 22 per candidate and warp - a warp of 32
+// consecutive slots nearly always spans two cells (28 beads per cell), so its lanes walk two different stencils one after the
+// other.  Here a warp takes the beads of ONE cell (32 at a time): the stencil cell, its image shift and the candidate j are
+// the same for every lane, the candidate position is one broadcast load, and the self test (j != i) only exists in the one
+// stencil cell that is the cell itself.  Candidate order per bead (stencil cells dz, dy, dx ascending, local part then ghost
+// part, slots ascending) is the one of k_nbr_filter, so both write the same rows.  SMALL: an axis with fewer than 3 cells
+// (deduplicated stencil, per-pair minimum image).
+template <bool SMALL, bool SELF>
+__device__ __forceinline__ void filterRange(int jlo, int jhi, const float4 *__restrict__ pos32, float bx, float by, float bz, bool px, bool py,
+                                            bool pz, float Lx, float Ly, float Lz, float rl2f, bool act, int i, int nPad, int cap,
+                                            uint32_t *__restrict__ raw, int &cnt)
+{
+    for (int j0 = jlo; j0 < jhi; j0 += 4)
+    {
+        float4 pj[4];
+#pragma unroll
+        for (int u = 0; u < 4; u++) pj[u] = pos32[min(j0 + u, jhi - 1)];
+#pragma unroll
+        for (int u = 0; u < 4; u++)
+        {
+            const int j = j0 + u;
+            float x = bx - pj[u].x, y = by - pj[u].y, z = bz - pj[u].z;
+            if (SMALL)
+            {
+                if (px) { if (x > 0.5f * Lx) x -= Lx; if (x < -0.5f * Lx) x += Lx; }
+                if (py) { if (y > 0.5f * Ly) y -= Ly; if (y < -0.5f * Ly) y += Ly; }
+                if (pz) { if (z > 0.5f * Lz) z -= Lz; if (z < -0.5f * Lz) z += Lz; }
+            }
+            const float r2 = x * x + y * y + z * z;
+            if (act && j < jhi && r2 < rl2f && (!SELF || j != i))
+            {
+                if (cnt < cap) raw[(size_t)cnt * nPad + i] = (uint32_t)j;
+                cnt++;
+            }
+        }
+    }
+}
+
+template <bool SMALL>
+__global__ void __launch_bounds__(128)
+k_nbr_filter_cell(int nPad, const float4 *__restrict__ pos32, const int *__restrict__ cellStart, BoxConst b, float rl2f, GridDev *gp, int cap,
+                  uint32_t *__restrict__ raw, int *__restrict__ rawCount)
+{
+    const int lane = threadIdx.x & 31;
+    const int c = blockIdx.x * 4 + (threadIdx.x >> 5);            // one warp per (local) cell
+    const int nx = gp->n[0], ny = gp->n[1], nz = gp->n[2], ncell = nx * ny * nz;
+    if (c >= ncell) return;
+    const int lo = cellStart[c], hi = cellStart[c + 1];
+    if (lo == hi) return;
+    const float Lx = (float)b.hxx, Ly = (float)b.hyy, Lz = (float)b.hzz;
+    const bool px = nx < 3, py = ny < 3, pz = nz < 3;
+    const int cx = c % nx, cy = (c / nx) % ny, cz = c / (nx * ny);
+    const int lx = nx >= 3 ? -1 : 0, hx = nx >= 2 ? 1 : 0;
+    const int ly = ny >= 3 ? -1 : 0, hy = ny >= 2 ? 1 : 0;
+    const int lz = nz >= 3 ? -1 : 0, hz = nz >= 2 ? 1 : 0;
+    int statMax = 0;
+    for (int base = lo; base < hi; base += 32)
+    {
+        const int i = base + lane;
+        const bool act = i < hi;
+        const float4 pi = pos32[act ? i : lo];
+        int cnt = 0;
+        for (int dz = lz; dz <= hz; dz++)
+        {
+            int az = cz + dz;
+            float sz = 0.0f;
+            if (az < 0) { az += nz; sz = -Lz; }
+            else if (az >= nz) { az -= nz; sz = Lz; }
+            const float bz = pz ? pi.z : pi.z - sz;
+            for (int dy = ly; dy <= hy; dy++)
+            {
+                int ay = cy + dy;
+                float sy = 0.0f;
+                if (ay < 0) { ay += ny; sy = -Ly; }
+                else if (ay >= ny) { ay -= ny; sy = Ly; }
+                const float by = py ? pi.y : pi.y - sy;
+                for (int dx = lx; dx <= hx; dx++)
+                {
+                    int ax = cx + dx;
+                    float sx = 0.0f;
+                    if (ax < 0) { ax += nx; sx = -Lx; }
+                    else if (ax >= nx) { ax -= nx; sx = Lx; }
+                    const float bx = px ? pi.x : pi.x - sx;
+                    const int cc = ax + nx * (ay + ny * az);
+                    // the cell's local beads, then (several ranks) its ghosts
+                    if (cc == c)
+                        filterRange<SMALL, true>(cellStart[cc], cellStart[cc + 1], pos32, bx, by, bz, px, py, pz, Lx, Ly, Lz, rl2f, act, i, nPad, cap, raw, cnt);
+                    else
+                        filterRange<SMALL, false>(cellStart[cc], cellStart[cc + 1], pos32, bx, by, bz, px, py, pz, Lx, Ly, Lz, rl2f, act, i, nPad, cap, raw, cnt);
+                    filterRange<SMALL, false>(cellStart[cc + ncell], cellStart[cc + ncell + 1], pos32, bx, by, bz, px, py, pz, Lx, Ly, Lz, rl2f, act, i, nPad,
+                                              cap, raw, cnt);
+                }
+            }
+        }
+        if (act) rawCount[i] = cnt;
+        statMax = max(statMax, cnt);
+    }
+    for (int o = 16; o > 0; o >>= 1) statMax = max(statMax, __shfl_xor_sync(0xffffffffu, statMax, o));
+    if (lane == 0 && statMax > 0)
+    {
+        atomicMax(&gp->maxRaw, statMax);
+        if (statMax > cap) atomicOr(&gp->error, 1);
+    }
+}
+
 // ---- 8c. tile windows (windowed pair kernel only) -----------------------------------------------------------------------------
 // One warp per tile: the distinct cells of the tile's slots, their stencil cells (the cells k_nbr_filter walks), sorted and
 // merged into runs of consecutive slots.  A window that needs more than WIN_MAXRUNS runs or more than wmax beads is left
@@ -495,7 +601,6 @@ __device__ __forceinline__ double4 ldPos256(const double4 *p)
 
 #define RAW_REJECT 0xffffffffu
 
-// Eight 16-bit per-bin counters in two 64-bit words: bins 0-3 in A, 4-7 in B.
 __global__ void __launch_bounds__(128)
 k_nbr_exact(int nIon, int nPad, int cap, const double4 *__restrict__ pos, BoxConst b, GridDev *gp, uint32_t *__restrict__ raw,
             const int *__restrict__ rawCount, uint32_t *__restrict__ out, int *__restrict__ count, uint16_t *__restrict__ cum,
@@ -513,13 +618,15 @@ k_nbr_exact(int nIon, int nPad, int cap, const double4 *__restrict__ pos, BoxCon
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     int total = 0;
     bool ghostEntry = false;      // some entry of this row is a ghost slot (several ranks): the row waits for the halo
+    // per-bin counters, then running offsets, of this thread's row: a column of shared memory each (no two threads share one)
+    __shared__ unsigned short sBin[NBINS][128];
+#pragma unroll
+    for (int e = 0; e < NBINS; e++) sBin[e][threadIdx.x] = 0;
     if (i < nIon)
     {
-        // ghost slots have no candidates (rawCount 0): their row stays empty
         const int n = min(rawCount[i], cap);
         const double4 pi = pos[i];
         const uint64_t wi = (uint64_t)__double_as_longlong(pi.w);
-        uint64_t A = 0ull, B = 0ull;
         uint32_t jn = (0 < n) ? raw[i] : 0u;
         for (int k = 0; k < n; k++)
         {
@@ -550,42 +657,27 @@ k_nbr_exact(int nIon, int nPad, int cap, const double4 *__restrict__ pos, BoxCon
                         isPruned((int)((wi >> 32) & 0x7fffffffull), (int)((wj >> 32) & 0x7fffffffull), gid, molTypeOfBead, molTypeSingle, bpairOffset, bpairKey))
                         ent |= EXCL_BIT;
                 }
-                const uint64_t one = 1ull << (16 * (bin & 3));
-                if (bin < 4) A += one;
-                else B += one;
+                sBin[bin][threadIdx.x]++;
                 total++;
             }
             raw[(size_t)k * nPad + i] = ent;
         }
-        // exclusive prefix over the eight counters
-        const uint64_t totA = (A * 0x0001000100010001ull) >> 48;
-        uint64_t offA = A * 0x0001000100010000ull;
-        uint64_t offB = B * 0x0001000100010000ull + totA * 0x0001000100010001ull;
-        // cumulative counts at every bin boundary: entries of bins 0..bnd
+        // cumulative counts at every bin boundary (entries of bins 0..bnd); the counters become the running write offsets
+        int run = 0;
 #pragma unroll
         for (int bnd = 0; bnd < NBINS; bnd++)
         {
-            const uint64_t off = bnd < 4 ? offA : offB, cnt = bnd < 4 ? A : B;
-            const int sh = 16 * (bnd & 3);
-            cum[(size_t)bnd * nPad + i] = (uint16_t)(((off >> sh) & 0xffffull) + ((cnt >> sh) & 0xffffull));
+            const int cnt = sBin[bnd][threadIdx.x];
+            sBin[bnd][threadIdx.x] = (unsigned short)run;
+            run += cnt;
+            cum[(size_t)bnd * nPad + i] = (uint16_t)run;
         }
         for (int k = 0; k < n; k++)
         {
             const uint32_t e = raw[(size_t)k * nPad + i];
             if (e == RAW_REJECT) continue;
             const int bin = (e >> 27) & 7;
-            const int sh = 16 * (bin & 3);
-            int dst;
-            if (bin < 4)
-            {
-                dst = (int)((offA >> sh) & 0xffffull);
-                offA += 1ull << sh;
-            }
-            else
-            {
-                dst = (int)((offB >> sh) & 0xffffull);
-                offB += 1ull << sh;
-            }
+            const int dst = sBin[bin][threadIdx.x]++;
             uint32_t idx = e & 0x07ffffffu;
             if (tileWin && sWin.nRuns > 0)
             {

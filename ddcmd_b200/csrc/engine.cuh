@@ -240,7 +240,9 @@ struct ddcb200_ctx
     unsigned long long *dmax2 = nullptr;   // device: [0] bits of the max squared displacement of a LOCAL bead since the build, [1] of a ghost
     bool walkPerBead = true;      // DDCB200_WALK
     int pairVariant = 2;          // DDCB200_PAIR
-    int bondedCap = 8;            // DDCB200_BONDED
+    int bondedCap = 12;           // DDCB200_BONDED
+    bool filterPerCell = true;    // DDCB200_FILTER
+    bool gridSmall = true;        // an axis of the last cell grid had fewer than 3 cells (known after the first build)
     bool pairWindows = false;     // DDCB200_PAIR=win: rows hold window offsets, k_pair3 gathers from shared memory
     int winMax = 0;               // beads a window may hold (from the shared memory of the device)
     DevBuf<TileWin> tileWin;
