@@ -193,7 +193,8 @@ static int setupBox(ddcb200_ctx *c)
 // The k_pair2 instantiations (gathers in flight per thread, CTAs per SM the register allocation is capped for): A/B-ed on the
 // B200 through DDCB200_PAIR=<pf>,<minb> | old
 typedef void (*PairKernel)(int, int, const int *, int, const double4 *, const uint32_t *, const uint16_t *, const unsigned long long *, int,
-                           const float *, const double2 *, const double *, const double *, PairConst, double *, double *, double *, double *);
+                           const float *, const double2 *, const double *, const double *, PairConst, double *, double *, double *, double *,
+                           const unsigned long long *, const int *);
 struct PairVariant
 {
     int pf, minb;
@@ -232,10 +233,12 @@ static int createInit(ddcb200_ctx *c)
     CK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
     if (const char *wk = getenv("DDCB200_WALK"))
     {
-        // list-walk bound: "bead" (default) = rmax + dmax + this bead's own displacement, "global" = rmax + 2 dmax.
-        // Both are exact and give bitwise equal forces; "global" walks more entries (A/B knob)
-        if (strcmp(wk, "global") == 0) c->walkPerBead = false;
-        else if (strcmp(wk, "bead") != 0) return fail(DDCB200_ERR_ARG, "DDCB200_WALK must be bead or global");
+        // list-walk bound rmax + d_i + d_j: "cell" (default) = this bead's own displacement + the largest in its stencil cells,
+        // "bead" = own + the largest of any resident bead, "global" = twice the latter.  All exact, bitwise equal forces; the
+        // looser ones walk more entries (A/B knob)
+        if (strcmp(wk, "global") == 0) c->walkPerBead = c->walkPerCell = false;
+        else if (strcmp(wk, "bead") == 0) c->walkPerCell = false;
+        else if (strcmp(wk, "cell") != 0) return fail(DDCB200_ERR_ARG, "DDCB200_WALK must be cell, bead or global");
     }
     CK(cudaMalloc((void **)&c->grid, sizeof(GridDev)));
     CK(cudaMemset(c->grid, 0, sizeof(GridDev)));
@@ -268,12 +271,6 @@ static int createInit(ddcb200_ctx *c)
         // loses to spills; profiles/r02h_variants.txt)
         c->bondedCap = atoi(bm);
         if (c->bondedCap != 1 && c->bondedCap != 8 && c->bondedCap != 10 && c->bondedCap != 12) return fail(DDCB200_ERR_ARG, "DDCB200_BONDED must be 1, 8, 10 or 12");
-    }
-    if (const char *fm = getenv("DDCB200_FILTER"))
-    {
-        // A/B: candidate pass with one warp per cell (default) or one thread per bead over consecutive slots
-        if (strcmp(fm, "bead") == 0) c->filterPerCell = false;
-        else if (strcmp(fm, "cell") != 0) return fail(DDCB200_ERR_ARG, "DDCB200_FILTER must be cell or bead");
     }
     if (const char *hm = getenv("DDCB200_HALO"))
     {
@@ -346,7 +343,7 @@ extern "C" void ddcb200_destroy(ddcb200_ctx *c)
     if (c->streamH) { cudaStreamSynchronize(c->streamH); cudaStreamDestroy(c->streamH); }
     if (c->evPos) cudaEventDestroy(c->evPos);
     if (c->evHalo) cudaEventDestroy(c->evHalo);
-    c->tileGhost.release(); c->tileOrder.release(); c->tileWin.release();
+    c->tileGhost.release(); c->tileOrder.release(); c->tileWin.release(); c->cellDmax.release(); c->nbrDmax.release();
     if (c->ddcWork) cudaFree(c->ddcWork);
     if (c->ddcWorkInit) cudaFreeHost(c->ddcWorkInit);
     if (c->ddcRow) cudaFree(c->ddcRow);
@@ -710,6 +707,7 @@ extern "C" int ddcb200_sendState(ddcb200_ctx *c, int64_t nLocal, const int *bead
     c->loop = loop;
     c->time = time;
     c->listValid = false;
+    c->nCellsBuilt = 0;       // the cells of the last build say nothing about the new slots
     c->forcesValid = false;
     c->energyValid = false;
     c->haloDirty = false;
@@ -747,7 +745,8 @@ extern "C" int ddcb200_updateState(ddcb200_ctx *c, int64_t nLocal, const int *be
     LAUNCH(k_update_state, (int)((nLocal + 255) / 256), 256, 0, c->stream)((int)nLocal, bead ? c->stageI.p : nullptr, c->slotOfBead.p, s, s + nLocal,
                                                                        s + 2 * nLocal, s + 3 * nLocal, s + 4 * nLocal, s + 5 * nLocal, c->pos4[cur].p,
                                                                        c->vel[cur][0].p, c->vel[cur][1].p, c->vel[cur][2].p, c->pc, c->posBuild[0].p,
-                                                                       c->posBuild[1].p, c->posBuild[2].p, c->dmax2, c->dispOfSlot.p);
+                                                                       c->posBuild[1].p, c->posBuild[2].p, c->dmax2, c->dispOfSlot.p,
+                                                                       c->nCellsBuilt > 0 ? c->cellDmax.p : nullptr, c->cellOfSlot[cur].p);
     CKL("k_update_state");
     c->loop = loop;
     c->time = time;
@@ -1028,7 +1027,8 @@ static int haloExchange(ddcb200_ctx *c, cudaStream_t st)
     if (c->nRecvTot)
     {
         LAUNCH(k_halo_unpack, (c->nRecvTot + 255) / 256, 256, 0, st)(c->nRecvTot, c->recvSlot.p, c->recvBuf.p, c->pos4[cur].p, c->posBuild[0].p,
-                                                                 c->posBuild[1].p, c->posBuild[2].p, c->pc, c->dmax2);
+                                                                 c->posBuild[1].p, c->posBuild[2].p, c->pc, c->dmax2,
+                                                                 c->nCellsBuilt > 0 ? c->cellDmax.p : nullptr, c->cellOfSlot[cur].p);
         CKL("k_halo_unpack");
     }
     c->haloDirty = false;
@@ -1171,20 +1171,8 @@ extern "C" int ddcb200_constructList(ddcb200_ctx *c)
         CK(c->nbr.ensure((size_t)c->nbrCap * nPad));
         CK(c->nbrRaw.ensure((size_t)c->nbrCap * nPad));
         CK(cudaEventRecord(c->evList[0], st));
-        if (c->filterPerCell)
-        {
-            // one warp per cell; the grid covers the largest cell count the grid set-up accepts (the kernel reads the real one)
-            const int cellBlocks = (maxCells + 3) / 4;
-            if (c->gridSmall)
-                LAUNCH(k_nbr_filter_cell<true>, cellBlocks, 128, 0, st)(nPad, c->pos32.p, c->cellStart.p, c->box, rl2f, c->grid, c->nbrCap, c->nbrRaw.p,
-                                                                    c->nbrRawCount.p);
-            else
-                LAUNCH(k_nbr_filter_cell<false>, cellBlocks, 128, 0, st)(nPad, c->pos32.p, c->cellStart.p, c->box, rl2f, c->grid, c->nbrCap, c->nbrRaw.p,
-                                                                     c->nbrRawCount.p);
-        }
-        else
-            LAUNCH(k_nbr_filter, tilesL, 128, 0, st)(nLocal, nPad, c->pos32.p, c->cellOfSlot[nxt].p, c->cellStart.p, c->box, rl2f, c->grid,
-                                                c->nbrCap, c->nbrRaw.p, c->nbrRawCount.p);
+        LAUNCH(k_nbr_filter, tilesL, 128, 0, st)(nLocal, nPad, c->pos32.p, c->cellOfSlot[nxt].p, c->cellStart.p, c->box, rl2f, c->grid,
+                                            c->nbrCap, c->nbrRaw.p, c->nbrRawCount.p);
         CKL("k_nbr_filter");
         LAUNCH(k_nbr_exact, tilesL, 128, 0, st)(nLocal, nPad, c->nbrCap, c->pos4[nxt].p, c->box, c->grid, c->nbrRaw.p, c->nbrRawCount.p,
                                                c->nbr.p, c->nbrCount.p, c->nbrCum.p, c->gidOfBead.p, c->molTypeOfBead.p,
@@ -1200,22 +1188,6 @@ extern "C" int ddcb200_constructList(ddcb200_ctx *c)
         CK(cudaMemcpyAsync(c->gridHost, c->grid, sizeof(GridDev), cudaMemcpyDeviceToHost, st));
         CK(cudaStreamSynchronize(st));
         if (c->gridHost->error & 2) return fail(DDCB200_ERR_CAPACITY, "cell grid larger than the bead count bound");
-        {
-            // the candidate pass was compiled for the cell grid of the previous build (three or more cells along every axis, or
-            // not): if this grid is smaller than assumed, redo the passes with the general instantiation
-            const bool small = c->gridHost->n[0] < 3 || c->gridHost->n[1] < 3 || c->gridHost->n[2] < 3;
-            const bool redo = small && !c->gridSmall && c->filterPerCell;
-            c->gridSmall = small;
-            if (redo)
-            {
-                CK(cudaMemsetAsync(&c->grid->error, 0, sizeof(int), st));
-                CK(cudaMemsetAsync(&c->grid->maxCount, 0, sizeof(int), st));
-                CK(cudaMemsetAsync(&c->grid->maxRaw, 0, sizeof(int), st));
-                CK(cudaMemsetAsync(&c->grid->totalEntries, 0, sizeof(unsigned long long), st));
-                attempt--;
-                continue;
-            }
-        }
         if (!(c->gridHost->error & 1))
         {
             CK(cudaEventElapsedTime(&c->listBuildMs, c->evList[0], c->evList[1]));
@@ -1263,6 +1235,11 @@ extern "C" int ddcb200_constructList(ddcb200_ctx *c)
     c->totalEntries = (int64_t)c->gridHost->totalEntries;
     c->nPairsListed = (int64_t)(c->gridHost->totalEntries / 2);
     c->nTilesInterior = c->nranks > 1 ? c->gridHost->nInterior : tilesL;
+    // per-cell displacement maxima start at zero with the new list
+    c->nCellsBuilt = c->gridHost->ncell;
+    CK(c->cellDmax.ensure(2 * (size_t)c->nCellsBuilt + 2));
+    CK(c->nbrDmax.ensure(2 * (size_t)c->nCellsBuilt + 2));
+    CK(cudaMemsetAsync(c->cellDmax.p, 0, 2 * (size_t)c->nCellsBuilt * sizeof(unsigned long long), st));
     c->winMaxTotal = c->gridHost->winMaxTotal;
     return DDCB200_OK;
 }
@@ -1372,6 +1349,13 @@ extern "C" int ddcb200_ddcenergy(ddcb200_ctx *c, int withEnergy)
             CK(cudaStreamWaitEvent(c->streamH, c->evPos, 0));
             rc = haloExchange(c, c->streamH);
             if (rc) return rc;
+            if (c->walkPerCell && c->walkPerBead && c->pairVariant >= 0 && !c->pairWindows && c->nCellsBuilt > 0)
+            {
+                // the neighbourhood bounds that include the ghosts' displacements, for the rows that wait for the halo.  (The
+                // local parts of cellDmax are complete: this stream waited for the integrator's event.)
+                LAUNCH(k_nbr_dmax, (c->nCellsBuilt + 127) / 128, 128, 0, c->streamH)(c->grid, c->cellDmax.p, 1, c->nbrDmax.p + c->nCellsBuilt);
+                CKL("k_nbr_dmax");
+            }
             CK(cudaEventRecord(c->evHalo, c->streamH));
             overlapped = true;
         }
@@ -1419,9 +1403,10 @@ extern "C" int ddcb200_ddcenergy(ddcb200_ctx *c, int withEnergy)
             {
                 const PairVariant &pv = g_pairVariants[c->pairVariant];
                 const PairKernel kern = withEnergy ? pv.energy : pv.force;
-                LAUNCH(kern, nTiles, TILE, smem, st)(nLocal, nPad, order, base, c->pos4[cur].p, c->nbr.p, c->nbrCum.p,
-                                                                                 c->dmax2, withGhosts, disp, c->ljTab.p, c->shiftTab.p, c->qTab.p,
-                                                                                 c->pc, c->frc[0].p, c->frc[1].p, c->frc[2].p, c->pairPartial.p);
+                const bool cellWalk = c->walkPerCell && c->walkPerBead && c->nCellsBuilt > 0;
+                LAUNCH(kern, nTiles, TILE, smem, st)(nLocal, nPad, order, base, c->pos4[cur].p, c->nbr.p, c->nbrCum.p, c->dmax2, withGhosts, disp, c->ljTab.p,
+                                                     c->shiftTab.p, c->qTab.p, c->pc, c->frc[0].p, c->frc[1].p, c->frc[2].p, c->pairPartial.p,
+                                                     cellWalk ? c->nbrDmax.p + (withGhosts ? c->nCellsBuilt : 0) : nullptr, c->cellOfSlot[cur].p);
             }
             else if (withEnergy)
                 LAUNCH(k_pair<true>, nTiles, TILE, smem, st)(nLocal, nPad, order, base, c->pos4[cur].p, c->nbr.p, c->nbrCum.p, c->dmax2, withGhosts, disp,
@@ -1434,6 +1419,18 @@ extern "C" int ddcb200_ddcenergy(ddcb200_ctx *c, int withEnergy)
             CKL("k_pair");
             return DDCB200_OK;
         };
+        const bool cellWalk = c->walkPerCell && c->walkPerBead && c->pairVariant >= 0 && !c->pairWindows && c->nCellsBuilt > 0;
+        if (cellWalk)
+        {
+            // the displacement bound of every cell's neighbourhood, from the local beads (complete since the integrator ran)
+            LAUNCH(k_nbr_dmax, (c->nCellsBuilt + 127) / 128, 128, 0, st)(c->grid, c->cellDmax.p, 0, c->nbrDmax.p);
+            CKL("k_nbr_dmax");
+            if (c->nranks > 1 && !overlapped)
+            {
+                LAUNCH(k_nbr_dmax, (c->nCellsBuilt + 127) / 128, 128, 0, st)(c->grid, c->cellDmax.p, 1, c->nbrDmax.p + c->nCellsBuilt);
+                CKL("k_nbr_dmax");
+            }
+        }
         if (c->nranks > 1)
         {
             rc = launchPair(c->nTilesInterior, c->tileOrder.p, 0, 0);
@@ -1494,7 +1491,8 @@ static int launchIntegrate(ddcb200_ctx *c, double halfDt2, double halfDt1, doubl
     if (MODE & INT_KICK1_DRIFT) c->haloDirty = true;
     LAUNCH(k_integrate<MODE>, tiles, TILE, 0, c->stream)((int)c->nLocal, c->pos4[cur].p, c->vel[cur][0].p, c->vel[cur][1].p, c->vel[cur][2].p,
                                                      c->frc[0].p, c->frc[1].p, c->frc[2].p, c->massOfBead.p, halfDt2, halfDt1, dt, c->pc,
-                                                     c->kinPartial.p, c->posBuild[0].p, c->posBuild[1].p, c->posBuild[2].p, c->dmax2, c->dispOfSlot.p);
+                                                     c->kinPartial.p, c->posBuild[0].p, c->posBuild[1].p, c->posBuild[2].p, c->dmax2, c->dispOfSlot.p,
+                                                     c->nCellsBuilt > 0 ? c->cellDmax.p : nullptr, c->cellOfSlot[cur].p);
     CKL("k_integrate");
     return DDCB200_OK;
 }
@@ -1810,7 +1808,8 @@ static int launchNglfc(ddcb200_ctx *c, double halfDt, double dt, const double sc
     LAUNCH(k_nglfc<MODE>, tiles, TILE, 0, c->stream)((int)c->nLocal, c->pos4[cur].p, c->vel[cur][0].p, c->vel[cur][1].p, c->vel[cur][2].p,
                                                  c->frc[0].p, c->frc[1].p, c->frc[2].p, c->massOfBead.p, c->groupOfBead.p, c->rngState.p,
                                                  c->rngMP.p, groupTabOf(c), halfDt, dt, scale[0], scale[1], scale[2], c->pc, c->kinPartial.p,
-                                                 c->posBuild[0].p, c->posBuild[1].p, c->posBuild[2].p, c->dmax2, c->dispOfSlot.p);
+                                                 c->posBuild[0].p, c->posBuild[1].p, c->posBuild[2].p, c->dmax2, c->dispOfSlot.p,
+                                                 c->nCellsBuilt > 0 ? c->cellDmax.p : nullptr, c->cellOfSlot[cur].p);
     CKL("k_nglfc");
     return DDCB200_OK;
 }

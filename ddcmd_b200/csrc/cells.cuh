@@ -337,112 +337,6 @@ k_nbr_filter(int nIon, int nPad, const float4 *__restrict__ pos32, const int *__
     }
 }
 
-// ---- 8b. the same candidate pass, one warp per cell ----------------------------------------------------------------------------
-// ncu on k_nbr_filter (profiles/r02c_k_nbr_filter_ncu_full.txt): 536 M warp instructions, 22 per candidate and warp - a warp of 32
-// consecutive slots nearly always spans two cells (28 beads per cell), so its lanes walk two different stencils one after the
-// other.  Here a warp takes the beads of ONE cell (32 at a time): the stencil cell, its image shift and the candidate j are
-// the same for every lane, the candidate position is one broadcast load, and the self test (j != i) only exists in the one
-// stencil cell that is the cell itself.  Candidate order per bead (stencil cells dz, dy, dx ascending, local part then ghost
-// part, slots ascending) is the one of k_nbr_filter, so both write the same rows.  SMALL: an axis with fewer than 3 cells
-// (deduplicated stencil, per-pair minimum image).
-template <bool SMALL, bool SELF>
-__device__ __forceinline__ void filterRange(int jlo, int jhi, const float4 *__restrict__ pos32, float bx, float by, float bz, bool px, bool py,
-                                            bool pz, float Lx, float Ly, float Lz, float rl2f, bool act, int i, int nPad, int cap,
-                                            uint32_t *__restrict__ raw, int &cnt)
-{
-    for (int j0 = jlo; j0 < jhi; j0 += 4)
-    {
-        float4 pj[4];
-#pragma unroll
-        for (int u = 0; u < 4; u++) pj[u] = pos32[min(j0 + u, jhi - 1)];
-#pragma unroll
-        for (int u = 0; u < 4; u++)
-        {
-            const int j = j0 + u;
-            float x = bx - pj[u].x, y = by - pj[u].y, z = bz - pj[u].z;
-            if (SMALL)
-            {
-                if (px) { if (x > 0.5f * Lx) x -= Lx; if (x < -0.5f * Lx) x += Lx; }
-                if (py) { if (y > 0.5f * Ly) y -= Ly; if (y < -0.5f * Ly) y += Ly; }
-                if (pz) { if (z > 0.5f * Lz) z -= Lz; if (z < -0.5f * Lz) z += Lz; }
-            }
-            const float r2 = x * x + y * y + z * z;
-            if (act && j < jhi && r2 < rl2f && (!SELF || j != i))
-            {
-                if (cnt < cap) raw[(size_t)cnt * nPad + i] = (uint32_t)j;
-                cnt++;
-            }
-        }
-    }
-}
-
-template <bool SMALL>
-__global__ void __launch_bounds__(128)
-k_nbr_filter_cell(int nPad, const float4 *__restrict__ pos32, const int *__restrict__ cellStart, BoxConst b, float rl2f, GridDev *gp, int cap,
-                  uint32_t *__restrict__ raw, int *__restrict__ rawCount)
-{
-    const int lane = threadIdx.x & 31;
-    const int c = blockIdx.x * 4 + (threadIdx.x >> 5);            // one warp per (local) cell
-    const int nx = gp->n[0], ny = gp->n[1], nz = gp->n[2], ncell = nx * ny * nz;
-    if (c >= ncell) return;
-    const int lo = cellStart[c], hi = cellStart[c + 1];
-    if (lo == hi) return;
-    const float Lx = (float)b.hxx, Ly = (float)b.hyy, Lz = (float)b.hzz;
-    const bool px = nx < 3, py = ny < 3, pz = nz < 3;
-    const int cx = c % nx, cy = (c / nx) % ny, cz = c / (nx * ny);
-    const int lx = nx >= 3 ? -1 : 0, hx = nx >= 2 ? 1 : 0;
-    const int ly = ny >= 3 ? -1 : 0, hy = ny >= 2 ? 1 : 0;
-    const int lz = nz >= 3 ? -1 : 0, hz = nz >= 2 ? 1 : 0;
-    int statMax = 0;
-    for (int base = lo; base < hi; base += 32)
-    {
-        const int i = base + lane;
-        const bool act = i < hi;
-        const float4 pi = pos32[act ? i : lo];
-        int cnt = 0;
-        for (int dz = lz; dz <= hz; dz++)
-        {
-            int az = cz + dz;
-            float sz = 0.0f;
-            if (az < 0) { az += nz; sz = -Lz; }
-            else if (az >= nz) { az -= nz; sz = Lz; }
-            const float bz = pz ? pi.z : pi.z - sz;
-            for (int dy = ly; dy <= hy; dy++)
-            {
-                int ay = cy + dy;
-                float sy = 0.0f;
-                if (ay < 0) { ay += ny; sy = -Ly; }
-                else if (ay >= ny) { ay -= ny; sy = Ly; }
-                const float by = py ? pi.y : pi.y - sy;
-                for (int dx = lx; dx <= hx; dx++)
-                {
-                    int ax = cx + dx;
-                    float sx = 0.0f;
-                    if (ax < 0) { ax += nx; sx = -Lx; }
-                    else if (ax >= nx) { ax -= nx; sx = Lx; }
-                    const float bx = px ? pi.x : pi.x - sx;
-                    const int cc = ax + nx * (ay + ny * az);
-                    // the cell's local beads, then (several ranks) its ghosts
-                    if (cc == c)
-                        filterRange<SMALL, true>(cellStart[cc], cellStart[cc + 1], pos32, bx, by, bz, px, py, pz, Lx, Ly, Lz, rl2f, act, i, nPad, cap, raw, cnt);
-                    else
-                        filterRange<SMALL, false>(cellStart[cc], cellStart[cc + 1], pos32, bx, by, bz, px, py, pz, Lx, Ly, Lz, rl2f, act, i, nPad, cap, raw, cnt);
-                    filterRange<SMALL, false>(cellStart[cc + ncell], cellStart[cc + ncell + 1], pos32, bx, by, bz, px, py, pz, Lx, Ly, Lz, rl2f, act, i, nPad,
-                                              cap, raw, cnt);
-                }
-            }
-        }
-        if (act) rawCount[i] = cnt;
-        statMax = max(statMax, cnt);
-    }
-    for (int o = 16; o > 0; o >>= 1) statMax = max(statMax, __shfl_xor_sync(0xffffffffu, statMax, o));
-    if (lane == 0 && statMax > 0)
-    {
-        atomicMax(&gp->maxRaw, statMax);
-        if (statMax > cap) atomicOr(&gp->error, 1);
-    }
-}
-
 // ---- 8c. tile windows (windowed pair kernel only) -----------------------------------------------------------------------------
 // One warp per tile: the distinct cells of the tile's slots, their stencil cells (the cells k_nbr_filter walks), sorted and
 // merged into runs of consecutive slots.  A window that needs more than WIN_MAXRUNS runs or more than wmax beads is left
@@ -747,4 +641,42 @@ k_tile_order(int nTiles, const int *__restrict__ tileGhost, int *__restrict__ or
         else order[ni++] = t;
     }
     if (threadIdx.x == 0) gp->nInterior = totalInterior;
+}
+
+
+// ---- per step: the displacement bound of every cell's neighbourhood ---------------------------------------------------------------
+// out[c] = largest squared displacement since the build of any bead in the stencil cells of cell c (its local beads, and with
+// withGhosts also its ghosts).  A partner j of a bead of cell c was in one of those cells at the build (that is how the list
+// is made), so d_j is at most the square root of this: k_pair's walk bound no longer pays for the fastest bead of the whole
+// system (the maximum over a million beads is about 5.5 sigma, over the ~750 of a neighbourhood about 4 sigma).
+__global__ void __launch_bounds__(128)
+k_nbr_dmax(const GridDev *__restrict__ gp, const unsigned long long *__restrict__ cellDmax, int withGhosts, unsigned long long *__restrict__ out)
+{
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    const int nx = gp->n[0], ny = gp->n[1], nz = gp->n[2], ncell = nx * ny * nz;
+    if (c >= ncell) return;
+    const int cx = c % nx, cy = (c / nx) % ny, cz = c / (nx * ny);
+    const int lx = nx >= 3 ? -1 : 0, hx = nx >= 2 ? 1 : 0;
+    const int ly = ny >= 3 ? -1 : 0, hy = ny >= 2 ? 1 : 0;
+    const int lz = nz >= 3 ? -1 : 0, hz = nz >= 2 ? 1 : 0;
+    unsigned long long m = 0ull;
+    for (int dz = lz; dz <= hz; dz++)
+    {
+        int az = cz + dz;
+        if (az < 0) az += nz; else if (az >= nz) az -= nz;
+        for (int dy = ly; dy <= hy; dy++)
+        {
+            int ay = cy + dy;
+            if (ay < 0) ay += ny; else if (ay >= ny) ay -= ny;
+            for (int dx = lx; dx <= hx; dx++)
+            {
+                int ax = cx + dx;
+                if (ax < 0) ax += nx; else if (ax >= nx) ax -= nx;
+                const int cc = ax + nx * (ay + ny * az);
+                m = max(m, cellDmax[cc]);
+                if (withGhosts) m = max(m, cellDmax[cc + ncell]);
+            }
+        }
+    }
+    out[c] = m;
 }

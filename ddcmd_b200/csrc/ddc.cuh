@@ -374,7 +374,8 @@ __global__ void k_halo_pack(int n, const int *__restrict__ slot, const double4 *
 
 __global__ void k_halo_unpack(int n, const int *__restrict__ slot, const double *__restrict__ buf, double4 *__restrict__ pos,
                               const double *__restrict__ bx, const double *__restrict__ by, const double *__restrict__ bz, PairConst pc,
-                              unsigned long long *__restrict__ dmax2)
+                              unsigned long long *__restrict__ dmax2, unsigned long long *__restrict__ cellDmax,
+                              const int *__restrict__ cellOfSlot)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     double disp2 = 0.0;
@@ -388,6 +389,7 @@ __global__ void k_halo_unpack(int n, const int *__restrict__ slot, const double 
         // ghosts move too: their displacement since the build enters the same bound as the locals'
         double dx = ddcMinImg(x - bx[s], pc.hxx, pc.hhx), dy = ddcMinImg(y - by[s], pc.hyy, pc.hhy), dz = ddcMinImg(z - bz[s], pc.hzz, pc.hhz);
         disp2 = dx * dx + dy * dy + dz * dz;
+        trackCellDisp(cellDmax, cellOfSlot, s, disp2);      // the ghost part of the bead's cell
     }
     for (int o = 16; o > 0; o >>= 1) disp2 = fmax(disp2, __shfl_xor_sync(0xffffffffu, disp2, o));
     if ((threadIdx.x & 31) == 0)

@@ -239,10 +239,12 @@ struct ddcb200_ctx
     DevBuf<double> posBuild[3];   // build-time positions, slot order (displacement bound)
     unsigned long long *dmax2 = nullptr;   // device: [0] bits of the max squared displacement of a LOCAL bead since the build, [1] of a ghost
     bool walkPerBead = true;      // DDCB200_WALK
+    bool walkPerCell = true;      // DDCB200_WALK=cell (default): d_j bounded by the bead's stencil cells instead of the whole system
+    DevBuf<unsigned long long> cellDmax;   // [2 ncell]: largest squared displacement since the build per cell (local part, ghost part)
+    DevBuf<unsigned long long> nbrDmax;    // [2][ncell]: the maximum over each cell's stencil, without / with the ghost parts
+    int nCellsBuilt = 0;
     int pairVariant = 2;          // DDCB200_PAIR
     int bondedCap = 12;           // DDCB200_BONDED
-    bool filterPerCell = true;    // DDCB200_FILTER
-    bool gridSmall = true;        // an axis of the last cell grid had fewer than 3 cells (known after the first build)
     bool pairWindows = false;     // DDCB200_PAIR=win: rows hold window offsets, k_pair3 gathers from shared memory
     int winMax = 0;               // beads a window may hold (from the shared memory of the device)
     DevBuf<TileWin> tileWin;

@@ -14,13 +14,23 @@
 #define INT_KE 2
 #define INT_KICK1_DRIFT 4
 
+// largest squared displacement since the build of any bead of a cell (k_pair's walk bound uses the maximum over a bead's stencil
+// cells, k_nbr_dmax): non-negative doubles order like their bit patterns; the running maximum is read first, so atomics are rare
+__device__ __forceinline__ void trackCellDisp(unsigned long long *__restrict__ cellDmax, const int *__restrict__ cellOfSlot, int slot, double disp2)
+{
+    if (!cellDmax) return;
+    unsigned long long *p = cellDmax + cellOfSlot[slot];
+    const unsigned long long bits = (unsigned long long)__double_as_longlong(disp2);
+    if (bits > *(volatile unsigned long long *)p) atomicMax(p, bits);
+}
+
 template <int MODE>
 __global__ void __launch_bounds__(TILE)
 k_integrate(int nIon, double4 *__restrict__ pos, double *__restrict__ vx, double *__restrict__ vy, double *__restrict__ vz,
             const double *__restrict__ fx, const double *__restrict__ fy, const double *__restrict__ fz,
             const double *__restrict__ massOfBead, double halfDt2, double halfDt1, double dt, PairConst pc, double *__restrict__ partial,
             const double *__restrict__ bx, const double *__restrict__ by, const double *__restrict__ bz, unsigned long long *__restrict__ dmax2,
-            float *__restrict__ dispOfSlot)
+            float *__restrict__ dispOfSlot, unsigned long long *__restrict__ cellDmax, const int *__restrict__ cellOfSlot)
 {
     const int i = blockIdx.x * TILE + threadIdx.x;
     double ke[7] = {0, 0, 0, 0, 0, 0, 0};
@@ -78,6 +88,7 @@ k_integrate(int nIon, double4 *__restrict__ pos, double *__restrict__ vx, double
             if (dz < -pc.hhz) dz += pc.hzz;
             disp2 = dx * dx + dy * dy + dz * dz;
             dispOfSlot[i] = __double2float_ru(sqrt(disp2));     // this bead's own displacement, rounded up: k_pair's per-bead walk bound
+            trackCellDisp(cellDmax, cellOfSlot, i, disp2);
         }
         if (MODE & (INT_KICK2 | INT_KICK1_DRIFT))
         {
@@ -230,7 +241,8 @@ __global__ void k_update_state(int n, const int *__restrict__ bead, const int *_
                                const double *__restrict__ vyi, const double *__restrict__ vzi, double4 *__restrict__ pos,
                                double *__restrict__ vx, double *__restrict__ vy, double *__restrict__ vz, PairConst pc,
                                const double *__restrict__ bx, const double *__restrict__ by, const double *__restrict__ bz,
-                               unsigned long long *__restrict__ dmax2, float *__restrict__ dispOfSlot)
+                               unsigned long long *__restrict__ dmax2, float *__restrict__ dispOfSlot, unsigned long long *__restrict__ cellDmax,
+                               const int *__restrict__ cellOfSlot)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     double disp2 = 0.0;
@@ -254,6 +266,7 @@ __global__ void k_update_state(int n, const int *__restrict__ bead, const int *_
         if (dz < -pc.hhz) dz += pc.hzz;
         disp2 = dx * dx + dy * dy + dz * dz;
         dispOfSlot[s] = __double2float_ru(sqrt(disp2));
+        trackCellDisp(cellDmax, cellOfSlot, s, disp2);
     }
     // one atomicMax per warp, and only when it can raise the running maximum (as k_integrate)
     for (int o = 16; o > 0; o >>= 1) disp2 = fmax(disp2, __shfl_xor_sync(0xffffffffu, disp2, o));

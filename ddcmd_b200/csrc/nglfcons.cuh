@@ -77,7 +77,8 @@ k_nglfc(int nIon, double4 *__restrict__ pos, double *__restrict__ vx, double *__
         const double *__restrict__ massOfBead, const unsigned char *__restrict__ groupOfBead, uint64_t *__restrict__ rngState,
         const uint2 *__restrict__ rngMP, GroupTab g, double halfDt, double dt, double sx, double sy, double sz, PairConst pc,
         double *__restrict__ partial, const double *__restrict__ bx, const double *__restrict__ by, const double *__restrict__ bz,
-        unsigned long long *__restrict__ dmax2, float *__restrict__ dispOfSlot)
+        unsigned long long *__restrict__ dmax2, float *__restrict__ dispOfSlot, unsigned long long *__restrict__ cellDmax,
+        const int *__restrict__ cellOfSlot)
 {
     const int i = blockIdx.x * TILE + threadIdx.x;
     double ke[7] = {0, 0, 0, 0, 0, 0, 0};
@@ -192,6 +193,7 @@ k_nglfc(int nIon, double4 *__restrict__ pos, double *__restrict__ vx, double *__
             if (dz < -pc.hhz) dz += pc.hzz;
             disp2 = dx * dx + dy * dy + dz * dz;
             dispOfSlot[i] = __double2float_ru(sqrt(disp2));
+            trackCellDisp(cellDmax, cellOfSlot, i, disp2);
         }
         if (MODE & (NC_SCALE | NC_DRIFT)) pos[i] = p;
         if (MODE & (NC_BACK | NC_FRONT))

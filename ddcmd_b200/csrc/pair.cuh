@@ -230,7 +230,8 @@ __global__ void __launch_bounds__(TILE, MINB)
 k_pair2(int nIon, int nPad, const int *__restrict__ tileOrder, int tileBase, const double4 *__restrict__ pos, const uint32_t *__restrict__ nbr,
         const uint16_t *__restrict__ cum, const unsigned long long *__restrict__ dmax2, int withGhosts, const float *__restrict__ dispOfSlot,
         const double2 *__restrict__ ljTab, const double *__restrict__ shiftTab, const double *__restrict__ qTab, PairConst pc,
-        double *__restrict__ fx, double *__restrict__ fy, double *__restrict__ fz, double *__restrict__ accPartial)
+        double *__restrict__ fx, double *__restrict__ fy, double *__restrict__ fz, double *__restrict__ accPartial,
+        const unsigned long long *__restrict__ nbrDmax, const int *__restrict__ cellOfSlot)
 {
     EXTERN_SHARED(double2, sLJ);               // ntypes*ntypes {6 c6, 12 c12}
     double *sQ = (double *)(sLJ + pc.ntypes * pc.ntypes);   // 256 charges
@@ -257,10 +258,24 @@ k_pair2(int nIon, int nPad, const int *__restrict__ tileOrder, int tileBase, con
     const double2 *ljRow = sLJ + ti * pc.ntypes;
     int binLimit = 0;
     {
-        unsigned long long db = dmax2[0];
-        if (withGhosts) db = max(db, dmax2[1]);
+        // d_j: the largest displacement in this bead's stencil cells (k_nbr_dmax; the launch over the rows with ghost entries
+        // gets the table that includes the ghosts), or - DDCB200_WALK=bead / global - of any resident bead
+        unsigned long long db;
+        if (nbrDmax) db = nbrDmax[cellOfSlot[ii]];
+        else
+        {
+            db = dmax2[0];
+            if (withGhosts) db = max(db, dmax2[1]);
+        }
         const double dmax = sqrt(__longlong_as_double((long long)db));
-        const double di = (live && dispOfSlot) ? fmin((double)dispOfSlot[ii], dmax) : dmax;
+        double di = dmax;
+        if (live && dispOfSlot)
+        {
+            // this bead's own displacement; never more than the global maximum, which the DDCB200_WALK=bead bound is capped with
+            unsigned long long dg = dmax2[0];
+            if (withGhosts) dg = max(dg, dmax2[1]);
+            di = fmin((double)dispOfSlot[ii], sqrt(__longlong_as_double((long long)dg)));
+        }
         const double lim = (pc.rmax + pc.listSlack + dmax + di) * (1.0 + 1e-12);
 #pragma unroll
         for (int e = 0; e < NBINS - 1; e++) binLimit += (pc.binEdge[e] < lim) ? 1 : 0;

@@ -42,10 +42,11 @@ def test_bin_edges_knob_keeps_the_pair_set(golden_dir, monkeypatch):
 
 @pytest.mark.parametrize("name", ["popc_small", "ras_small"])
 def test_per_bead_walk_bound_is_bitwise_neutral(golden_dir, name, monkeypatch):
-    """k_pair stops each row at rmax + dmax + the bead's own displacement instead of rmax + 2 dmax: the entries it no longer visits
-    would have added exact zeros, so 45 steps (two rebuilds, growing displacements) are bitwise the same with either bound."""
+    """k_pair stops each row at rmax + the bead's own displacement + the largest displacement in its stencil cells (or, "bead", of
+    any resident bead) instead of rmax + 2 dmax: the entries it no longer visits would have added exact zeros, so 45 steps (two
+    rebuilds, growing displacements) are bitwise the same with every bound."""
     out = {}
-    for mode in ("global", "bead"):
+    for mode in ("global", "bead", "cell"):
         monkeypatch.setenv("DDCB200_WALK", mode)
         sim, _ = _load(golden_dir, name)
         sim.nglf(45)
@@ -53,10 +54,11 @@ def test_per_bead_walk_bound_is_bitwise_neutral(golden_dir, name, monkeypatch):
         st = sim.getState()
         out[mode] = (st, e.eion, e.rk, np.array(e.virial[:]))
         sim.close()
-    a, b = out["global"], out["bead"]
-    for k in ("rx", "ry", "rz", "vx", "vy", "vz", "fx", "fy", "fz"):
-        assert np.array_equal(a[0][k], b[0][k]), k
-    assert a[1] == b[1] and a[2] == b[2] and np.array_equal(a[3], b[3])
+    a = out["global"]
+    for b in (out["bead"], out["cell"]):
+        for k in ("rx", "ry", "rz", "vx", "vy", "vz", "fx", "fy", "fz"):
+            assert np.array_equal(a[0][k], b[0][k]), k
+        assert a[1] == b[1] and a[2] == b[2] and np.array_equal(a[3], b[3])
 
 
 def test_row_capacity_regrow(golden_dir, monkeypatch):
