@@ -341,6 +341,8 @@ extern "C" void ddcb200_destroy(ddcb200_ctx *c)
     c->ddcList.release(); c->sendSlot.release(); c->recvSlot.release();
     c->sendBuf.release(); c->recvBuf.release(); c->accG.release();
     if (c->streamH) { cudaStreamSynchronize(c->streamH); cudaStreamDestroy(c->streamH); }
+    if (c->streamB) { cudaStreamSynchronize(c->streamB); cudaStreamDestroy(c->streamB); }
+    if (c->evBoundary) cudaEventDestroy(c->evBoundary);
     if (c->evPos) cudaEventDestroy(c->evPos);
     if (c->evHalo) cudaEventDestroy(c->evHalo);
     c->tileGhost.release(); c->tileOrder.release(); c->tileWin.release(); c->cellDmax.release(); c->nbrDmax.release();
@@ -1383,9 +1385,11 @@ extern "C" int ddcb200_ddcenergy(ddcb200_ctx *c, int withEnergy)
     {
         const size_t smem = pairSmemBytes(c->ntypes);
         const float *disp = c->walkPerBead ? c->dispOfSlot.p : nullptr;
+        cudaStream_t pst = st;      // the stream of the next pair launch
         auto launchPair = [&](int nTiles, const int *order, int base, int withGhosts) -> int {
             if (nTiles <= 0) return DDCB200_OK;
-            ProfScope ps(c, PROF_PAIR);
+            cudaStream_t st = pst;
+            ProfScope ps(c, PROF_PAIR, st);
             if (c->pairWindows)
             {
                 const int wcap = (c->winMaxTotal + 7) & ~7;
@@ -1431,15 +1435,26 @@ extern "C" int ddcb200_ddcenergy(ddcb200_ctx *c, int withEnergy)
                 CKL("k_nbr_dmax");
             }
         }
-        if (c->nranks > 1)
+        if (c->nranks > 1 && overlapped)
         {
+            // the rows that read no ghost run now; the others wait for the halo on a stream of their own, so that their CTAs
+            // fill the slots the first launch leaves idle in its last wave (two launches in one stream would each pay a tail)
             rc = launchPair(c->nTilesInterior, c->tileOrder.p, 0, 0);
             if (rc) return rc;
-            if (overlapped) CK(cudaStreamWaitEvent(st, c->evHalo, 0));
-            rc = launchPair(tiles - c->nTilesInterior, c->tileOrder.p, c->nTilesInterior, 1);
+            if (tiles - c->nTilesInterior > 0)
+            {
+                CK(cudaStreamWaitEvent(c->streamB, c->evHalo, 0));
+                pst = c->streamB;
+                rc = launchPair(tiles - c->nTilesInterior, c->tileOrder.p, c->nTilesInterior, 1);
+                if (rc) return rc;
+                CK(cudaEventRecord(c->evBoundary, c->streamB));
+                CK(cudaStreamWaitEvent(st, c->evBoundary, 0));
+            }
+            else
+                CK(cudaStreamWaitEvent(st, c->evHalo, 0));
         }
         else
-            rc = launchPair(tiles, nullptr, 0, 0);
+            rc = launchPair(tiles, nullptr, 0, c->nranks > 1 ? 1 : 0);      // one launch over every row (ghost positions are in place)
         if (rc) return rc;
     }
     int bBlocks = 0;
@@ -2251,6 +2266,8 @@ extern "C" int ddcb200_ddcInit(ddcb200_ctx *c, int rank, int nranks, int lx, int
     }
     CK(cudaEventCreateWithFlags(&c->evPos, cudaEventDisableTiming));
     CK(cudaEventCreateWithFlags(&c->evHalo, cudaEventDisableTiming));
+    CK(cudaEventCreateWithFlags(&c->evBoundary, cudaEventDisableTiming));
+    CK(cudaStreamCreateWithFlags(&c->streamB, cudaStreamNonBlocking));
     CK(cudaMalloc((void **)&c->boxes, sizeof(DdcBoxes)));
     CK(cudaMalloc((void **)&c->ddcWork, sizeof(DdcWork)));
     CK(cudaMallocHost((void **)&c->ddcWorkInit, sizeof(DdcWork)));

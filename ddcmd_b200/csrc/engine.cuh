@@ -320,7 +320,8 @@ struct ddcb200_ctx
     int nSendTot = 0, nRecvTot = 0;
     bool haloDirty = false, localsDirty = false;
     cudaStream_t streamH = nullptr;         // the halo runs here, beside the pair work of the rows that read no ghost
-    cudaEvent_t evPos = nullptr, evHalo = nullptr;
+    cudaStream_t streamB = nullptr;         // the pair rows that wait for the halo: beside the tail of the other rows' launch
+    cudaEvent_t evPos = nullptr, evHalo = nullptr, evBoundary = nullptr;
     DevBuf<int> tileGhost, tileOrder;
     int nTilesInterior = 0;
     bool haloOverlap = true;                // DDCB200_HALO=overlap|inline
