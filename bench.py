@@ -63,7 +63,7 @@ class ClockSampler(threading.Thread):
         q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.device), "--query-gpu=" + q, "--format=csv,noheader,nounits", "-lms", "100"],
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.device), "--query-gpu=" + q, "--format=csv,noheader,nounits", "-lms", "200"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             for line in self.proc.stdout:
                 if self.stop_flag:
@@ -310,8 +310,12 @@ def main():
         sim.nglf(W)
         sim.sync()
         l0 = sim.kernelLaunches()
-        clocks = ClockSampler(local)
-        clocks.start()
+        # clocks and throttle reasons under load: one sampler (rank 0's GPU; every GPU of the box runs the same step), kept running
+        # through the long window below so that most samples fall under load.  (One nvidia-smi poller per rank at 100 ms was seen
+        # to stall the timed window of 2-GPU runs by up to 2x.)
+        clocks = ClockSampler(local) if rank == 0 else None
+        if clocks:
+            clocks.start()
         time.sleep(0.3)
         barrier()
         sim.sync()
@@ -322,7 +326,6 @@ def main():
         barrier()
         ms = max_over_ranks(sim.timerElapsed(0, 1))      # device time on the launching stream, max over ranks
         out["launches"] = sim.kernelLaunches() - l0
-        out["clocks"] = clocks.finish()
         out["ms"] = ms
         out["steps_per_s"] = K / (ms * 1e-3)
         e = sim.energyInfo()
@@ -341,6 +344,7 @@ def main():
             barrier()
             ms_long = max_over_ranks(sim.timerElapsed(2, 3))
             out["long_run"] = {"steps": 400, "steps_per_s": 400 / (ms_long * 1e-3), "ms_per_step": ms_long / 400}
+        out["clocks"] = clocks.finish() if clocks else None
         return sim, deck, out, e
 
     K, W = args.steps, max(3, args.warmup)

@@ -130,7 +130,7 @@ struct DevBuf
         if (p) cudaFree(p);
         p = nullptr;
         cap = 0;
-        size_t want = n + n / 8 + 256;
+        size_t want = n + n / 4 + 256;      // a quarter of headroom: bead and ghost counts drift from one re-domain to the next
         cudaError_t e = cudaMalloc((void **)&p, want * sizeof(T));
         if (e == cudaSuccess) cap = want;
         return e;
@@ -139,7 +139,7 @@ struct DevBuf
     cudaError_t grow(size_t n, cudaStream_t st)
     {
         if (n <= cap) return cudaSuccess;
-        const size_t want = n + n / 8 + 256;
+        const size_t want = n + n / 4 + 256;
         T *q = nullptr;
         cudaError_t e = cudaMalloc((void **)&q, want * sizeof(T));
         if (e != cudaSuccess) return e;
