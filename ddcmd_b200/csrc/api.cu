@@ -270,7 +270,7 @@ static int createInit(ddcb200_ctx *c)
         // 10: 0.078; 12 = 40 registers, the default: 0.073 - the kernel is latency-bound and gains more from resident warps than it
         // loses to spills; profiles/r02h_variants.txt)
         c->bondedCap = atoi(bm);
-        if (c->bondedCap != 1 && c->bondedCap != 8 && c->bondedCap != 10 && c->bondedCap != 12) return fail(DDCB200_ERR_ARG, "DDCB200_BONDED must be 1, 8, 10 or 12");
+        if (c->bondedCap != 1 && c->bondedCap != 8 && c->bondedCap != 12) return fail(DDCB200_ERR_ARG, "DDCB200_BONDED must be 1, 8 or 12");
     }
     if (const char *hm = getenv("DDCB200_HALO"))
     {
@@ -315,7 +315,8 @@ extern "C" void ddcb200_destroy(ddcb200_ctx *c)
     if (c->stream) cudaStreamSynchronize(c->stream);
     c->ljTab.release(); c->shiftTab.release(); c->qTab.release(); c->massOfBead.release(); c->wOfBead.release();
     c->gidOfBead.release(); c->molTypeOfBead.release(); c->molTypeSingle.release(); c->bpairOffset.release();
-    c->bpairKey.release(); c->termsBead.release(); c->restrBead.release(); c->bondCsrOff.release(); c->bondEnt.release(); c->bondRec.release(); c->bondCount.release(); c->bondStart.release(); c->scanBlocks.release();
+    c->bpairKey.release(); c->termsBead.release(); c->restrBead.release(); c->bondCsrOff.release(); c->bondEnt.release(); c->bondRec.release(); c->bondCount.release(); c->bondStart.release(); c->scanBlocks.release(); c->bondCount0.release(); c->bondStart0.release();
+    c->termMap.release(); c->bondStageIdx.release(); c->bondStage.release();
     c->restrParm.release(); c->molOffset.release(); c->molBeads.release();
     for (int k = 0; k < 2; k++)
     {
@@ -1062,9 +1063,6 @@ static int ensureBondCsr(ddcb200_ctx *c)
     }
     for (int64_t b = 0; b < nG; b++) off[(size_t)b + 1] += off[(size_t)b];
     if ((int64_t)off[(size_t)nG] < 0) return fail(DDCB200_ERR_CAPACITY, "too many bonded term entries");
-    for (int64_t b = 0; b < nG; b++)
-        if (off[(size_t)b + 1] - off[(size_t)b] > BONDED_SPILL)
-            return fail(DDCB200_ERR_CAPACITY, "a bead takes part in more than 256 bonded terms");
     std::vector<uint32_t> ent((size_t)off[(size_t)nG] + 1);
     std::vector<int> fill(off.begin(), off.end() - 1);
     for (size_t t = 0; t < c->hTerms.size(); t++)
@@ -1144,16 +1142,24 @@ extern "C" int ddcb200_constructList(ddcb200_ctx *c)
         if (rcb) return rcb;
         CK(c->bondCount.ensure((size_t)nPad));
         CK(c->bondStart.ensure((size_t)nPad));
-        LAUNCH(k_bond_count, (nIon + 255) / 256, 256, 0, st)(nIon, c->pos4[nxt].p, c->bondCsrOff.p, c->bondCount.p);
+        CK(c->bondCount0.ensure((size_t)nPad));
+        CK(c->bondStart0.ensure((size_t)nPad));
+        LAUNCH(k_bond_count, (nLocal + 255) / 256, 256, 0, st)(nLocal, c->pos4[nxt].p, c->bondCsrOff.p, c->bondEnt.p, c->bondCount.p, c->bondCount0.p);
         CKL("k_bond_count");
-        const int nsb = (nIon + SCAN_BLOCK - 1) / SCAN_BLOCK;
+        const int nsb = (nLocal + SCAN_BLOCK - 1) / SCAN_BLOCK;
         CK(c->scanBlocks.ensure((size_t)nsb + 1));
-        LAUNCH(k_scan_local, nsb, SCAN_BLOCK, 0, st)(nIon, c->bondCount.p, c->bondStart.p, c->scanBlocks.p);
-        CKL("k_scan_local");
-        LAUNCH(k_scan_blocks, 1, 1024, 0, st)(nsb, c->scanBlocks.p, &c->grid->bondTotal);
-        CKL("k_scan_blocks");
-        LAUNCH(k_scan_add, nsb, SCAN_BLOCK, 0, st)(nIon, c->bondStart.p, c->scanBlocks.p);
-        CKL("k_scan_add");
+        for (int which = 0; which < 2; which++)
+        {
+            // entries per bead -> where the bead's run starts; role-0 entries per bead -> the bead's first local term
+            const int *cnt = which ? c->bondCount0.p : c->bondCount.p;
+            int *start = which ? c->bondStart0.p : c->bondStart.p;
+            LAUNCH(k_scan_local, nsb, SCAN_BLOCK, 0, st)(nLocal, cnt, start, c->scanBlocks.p);
+            CKL("k_scan_local");
+            LAUNCH(k_scan_blocks, 1, 1024, 0, st)(nsb, c->scanBlocks.p, which ? &c->grid->bondTerms : &c->grid->bondTotal);
+            CKL("k_scan_blocks");
+            LAUNCH(k_scan_add, nsb, SCAN_BLOCK, 0, st)(nLocal, start, c->scanBlocks.p);
+            CKL("k_scan_add");
+        }
     }
     // after the cell sort the local beads are slots [0, nLocal): rows, tiles and every per-bead kernel cover that range only
     const int tilesL = (nLocal + TILE - 1) / TILE;
@@ -1206,10 +1212,19 @@ extern "C" int ddcb200_constructList(ddcb200_ctx *c)
     if (haveBonded)
     {
         c->nBondRec = c->gridHost->bondTotal;
-        CK(c->bondRec.ensure((size_t)c->nBondRec + 1));
-        LAUNCH(k_bond_resolve, (nIon + 255) / 256, 256, 0, st)(nIon, c->pos4[nxt].p, c->bondCsrOff.p, c->bondEnt.p, c->nTerms, c->termsBead.p,
-                                                           c->restrParm.p, c->slotOfBead.p, c->bondStart.p, c->bondCount.p, c->bondRec.p);
-        CKL("k_bond_resolve");
+        c->nBondTerms = c->gridHost->bondTerms;
+        const size_t nAll = (size_t)(c->nTerms + c->nRestr);
+        CK(c->bondRec.ensure((size_t)c->nBondTerms + 1));
+        CK(c->bondStageIdx.ensure((size_t)c->nBondRec + 1));
+        CK(c->bondStage.ensure(12 * (size_t)c->nBondTerms + 12));
+        CK(c->termMap.ensure(nAll + 1));
+        CK(cudaMemsetAsync(c->termMap.p, 0xff, nAll * sizeof(int), st));
+        LAUNCH(k_bond_resolve_terms, (nLocal + 255) / 256, 256, 0, st)(nLocal, c->pos4[nxt].p, c->bondCsrOff.p, c->bondEnt.p, c->nTerms, c->termsBead.p,
+                                                                   c->slotOfBead.p, c->bondStart0.p, c->bondCount0.p, c->bondRec.p, c->termMap.p);
+        CKL("k_bond_resolve_terms");
+        LAUNCH(k_bond_resolve_beads, (nLocal + 255) / 256, 256, 0, st)(nLocal, c->pos4[nxt].p, c->bondCsrOff.p, c->bondEnt.p, c->termMap.p,
+                                                                   c->bondStart.p, c->bondCount.p, c->bondStageIdx.p);
+        CKL("k_bond_resolve_beads");
     }
     if (c->nranks > 1)
     {
@@ -1458,27 +1473,28 @@ extern "C" int ddcb200_ddcenergy(ddcb200_ctx *c, int withEnergy)
         if (rc) return rc;
     }
     int bBlocks = 0;
-    if (c->nTerms + c->nRestr > 0 && c->nBondRec > 0)
+    if (c->nTerms + c->nRestr > 0 && c->nBondTerms > 0)
     {
         ProfScope ps(c, PROF_BONDED);
-        bBlocks = (c->nBondRec + BONDED_THREADS - 1) / BONDED_THREADS;
+        bBlocks = (c->nBondTerms + BONDED_THREADS - 1) / BONDED_THREADS;
         CK(c->bondPartial.ensure((size_t)bBlocks * BONDED_ACC + 8));
+        V3 *stage = (V3 *)c->bondStage.p;
         if (withEnergy)
-            LAUNCH((k_bonded<true, 1>), bBlocks, BONDED_THREADS, 0, st)(c->nBondRec, c->bondRec.p, c->restrParm.p, c->restrOrigin, c->pos4[cur].p, c->pc,
-                                                                    c->frc[0].p, c->frc[1].p, c->frc[2].p, c->bondPartial.p);
+            LAUNCH((k_bonded<true, 1>), bBlocks, BONDED_THREADS, 0, st)(c->nBondTerms, c->bondRec.p, c->restrParm.p, c->restrOrigin, c->pos4[cur].p, c->pc,
+                                                                    stage, c->bondPartial.p);
         else if (c->bondedCap == 8)
-            LAUNCH((k_bonded<false, 8>), bBlocks, BONDED_THREADS, 0, st)(c->nBondRec, c->bondRec.p, c->restrParm.p, c->restrOrigin, c->pos4[cur].p, c->pc,
-                                                                     c->frc[0].p, c->frc[1].p, c->frc[2].p, c->bondPartial.p);
-        else if (c->bondedCap == 10)
-            LAUNCH((k_bonded<false, 10>), bBlocks, BONDED_THREADS, 0, st)(c->nBondRec, c->bondRec.p, c->restrParm.p, c->restrOrigin, c->pos4[cur].p, c->pc,
-                                                                      c->frc[0].p, c->frc[1].p, c->frc[2].p, c->bondPartial.p);
+            LAUNCH((k_bonded<false, 8>), bBlocks, BONDED_THREADS, 0, st)(c->nBondTerms, c->bondRec.p, c->restrParm.p, c->restrOrigin, c->pos4[cur].p, c->pc,
+                                                                     stage, c->bondPartial.p);
         else if (c->bondedCap == 12)
-            LAUNCH((k_bonded<false, 12>), bBlocks, BONDED_THREADS, 0, st)(c->nBondRec, c->bondRec.p, c->restrParm.p, c->restrOrigin, c->pos4[cur].p, c->pc,
-                                                                      c->frc[0].p, c->frc[1].p, c->frc[2].p, c->bondPartial.p);
+            LAUNCH((k_bonded<false, 12>), bBlocks, BONDED_THREADS, 0, st)(c->nBondTerms, c->bondRec.p, c->restrParm.p, c->restrOrigin, c->pos4[cur].p, c->pc,
+                                                                      stage, c->bondPartial.p);
         else
-            LAUNCH((k_bonded<false, 1>), bBlocks, BONDED_THREADS, 0, st)(c->nBondRec, c->bondRec.p, c->restrParm.p, c->restrOrigin, c->pos4[cur].p, c->pc,
-                                                                     c->frc[0].p, c->frc[1].p, c->frc[2].p, c->bondPartial.p);
+            LAUNCH((k_bonded<false, 1>), bBlocks, BONDED_THREADS, 0, st)(c->nBondTerms, c->bondRec.p, c->restrParm.p, c->restrOrigin, c->pos4[cur].p, c->pc,
+                                                                     stage, c->bondPartial.p);
         CKL("k_bonded");
+        LAUNCH(k_bonded_sum, (nLocal + BONDED_THREADS - 1) / BONDED_THREADS, BONDED_THREADS, 0, st)(nLocal, c->bondStart.p, c->bondCount.p, c->bondStageIdx.p,
+                                                                                                stage, c->frc[0].p, c->frc[1].p, c->frc[2].p);
+        CKL("k_bonded_sum");
     }
     if (withEnergy)
     {

@@ -77,28 +77,32 @@ __device__ __forceinline__ void dihedral(V3 vij, V3 vjk, V3 vkl, double &ang, do
 #define BONDED_THREADS 128
 #define BONDED_ACC 11   // 0..5 virial (xx yy zz xy xz yz), 6 bond, 7 angle, 8 torsion, 9 improper, 10 restraint
 
-// Forces are GATHERED, not scattered: every resident local bead has the (static) list of bonded terms it takes part in -
-// entry = (term << 2 | role of this bead in the term), ascending term order; each entry is evaluated for the force on that
-// one bead only, and a bead's entries are added up in their fixed order.  A bond is therefore evaluated twice, an angle three times, a dihedral four times;
-// in exchange there is no atomic and the summation order of every bead's force is fixed, so forces and energies are
-// bitwise reproducible run to run (the reference accumulates in owner order too, src/bioCharmmCovalent.c:95-251).
-// Energy and virial of a term are counted by the thread of its role-0 bead only.  At every list build the entries of the
-// resident local beads are resolved into records in slot order (endpoint slots + parameters), so a step reads one record
-// and the partners' positions per entry.  A term with an endpoint that is not resident here is skipped (molecules are
-// whole on their owner rank, src/ddcRuleMolecule.c:43, so that never happens for a local bead of a Martini deck).
-// ---- at every list build: the records of the resident local beads, in slot order -------------------------------------
-__global__ void k_bond_count(int nIon, const double4 *__restrict__ pos, const int *__restrict__ csrOff, int *__restrict__ cnt)
+// No atomics, fixed summation order: every resident local bead has the (static) list of bonded terms it takes part in - entry =
+// (term << 2 | role of this bead in the term), ascending term order.  Every term is evaluated once, by the thread of its
+// role-0 entry's term record, which stages the forces on all of the term's beads; a second kernel adds up each bead's
+// entries from the stage in their fixed order.  Forces and energies are bitwise reproducible run to run (the reference
+// accumulates in owner order too, src/bioCharmmCovalent.c:95-251).  Term records (endpoint slots + parameters) and the
+// per-bead stage indices are rebuilt at every list build for the local beads only.  A term with an endpoint that is not
+// resident here is skipped, and so is a bead's entry whose term has its role-0 bead on another rank (molecules are whole
+// on their owner rank, src/ddcRuleMolecule.c:43, so neither happens for a Martini deck).
+// ---- at every list build: the terms and the per-bead contribution lists of the resident local beads, in slot order -----------------
+// cnt[s] = entries of slot s (its contributions), cnt0[s] = those with role 0 (the terms this bead "owns": each term has exactly one)
+__global__ void k_bond_count(int nIon, const double4 *__restrict__ pos, const int *__restrict__ csrOff, const uint32_t *__restrict__ ent,
+                             int *__restrict__ cnt, int *__restrict__ cnt0)
 {
     const int s = blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= nIon) return;
     const unsigned long long w = (unsigned long long)__double_as_longlong(pos[s].w);
-    int n = 0;
+    int n = 0, n0 = 0;
     if (!(w >> 63))
     {
         const int b = (int)((w >> 32) & 0x7fffffffull);
-        n = csrOff[b + 1] - csrOff[b];
+        const int lo = csrOff[b];
+        n = csrOff[b + 1] - lo;
+        for (int q = 0; q < n; q++) n0 += ((ent[lo + q] & 3u) == 0u) ? 1 : 0;
     }
     cnt[s] = n;
+    cnt0[s] = n0;
 }
 
 // exclusive scan of n ints (n = resident beads): per-block scans, a scan of the block totals by one block, then the offsets
@@ -168,30 +172,31 @@ k_scan_add(int n, int *__restrict__ out, const int *__restrict__ blockSum)
     if (i < n) out[i] += blockSum[blockIdx.x];
 }
 
-__global__ void k_bond_resolve(int nIon, const double4 *__restrict__ pos, const int *__restrict__ csrOff, const uint32_t *__restrict__ ent,
-                               int64_t nTerms, const Term *__restrict__ terms, const double *__restrict__ restrParm,
-                               const int *__restrict__ slotOfBead, const int *__restrict__ start, const int *__restrict__ cnt,
-                               BondRec *__restrict__ recs)
+// the local terms: one record per term, written by the slot of its role-0 bead; termMap[t] = index of term t here
+__global__ void k_bond_resolve_terms(int nIon, const double4 *__restrict__ pos, const int *__restrict__ csrOff, const uint32_t *__restrict__ ent,
+                                     int64_t nTerms, const Term *__restrict__ terms, const int *__restrict__ slotOfBead,
+                                     const int *__restrict__ start0, const int *__restrict__ cnt0, BondRec *__restrict__ recs,
+                                     int *__restrict__ termMap)
 {
     const int s = blockIdx.x * blockDim.x + threadIdx.x;
-    if (s >= nIon) return;
-    const int n = cnt[s], lo = start[s];
-    if (n == 0) return;
+    if (s >= nIon || cnt0[s] == 0) return;
     const unsigned long long w = (unsigned long long)__double_as_longlong(pos[s].w);
-    const int elo = csrOff[(int)((w >> 32) & 0x7fffffffull)];
+    const int b = (int)((w >> 32) & 0x7fffffffull);
+    const int elo = csrOff[b], n = csrOff[b + 1] - elo;
+    int lt = start0[s];
     for (int q = 0; q < n; q++)
     {
         const uint32_t e = ent[elo + q];
+        if ((e & 3u) != 0u) continue;
         const int64_t t = (int64_t)(e >> 2);
         BondRec r;
-        r.role = (short)(e & 3u);
-        r.q = (unsigned short)q;
-        r.n = (unsigned short)n;
+        r.role = 0;
+        r.q = 0;
         if (t >= nTerms)
         {
-            // restraint (src/restraint.c:287-357): frac0[3] in p0..p2 is not enough room for its 7 parameters, so the record
-            // keeps the restraint's index in s[1] and the kernel reads the table
+            // restraint (src/restraint.c:287-357): its 7 parameters stay in the table, the record keeps its index in s[1]
             r.kind = 6;
+            r.n = 1;
             r.s[0] = s; r.s[1] = (int)(t - nTerms); r.s[2] = 0; r.s[3] = 0;
             r.p0 = r.p1 = r.p2 = 0.0;
         }
@@ -204,20 +209,41 @@ __global__ void k_bond_resolve(int nIon, const double4 *__restrict__ pos, const 
             r.s[3] = tm.l >= 0 ? slotOfBead[tm.l] : 0;
             r.p0 = tm.p0; r.p1 = tm.p1; r.p2 = tm.p2;
             r.kind = (short)(((r.s[0] | r.s[1] | r.s[2] | r.s[3]) < 0) ? -1 : tm.kind);      // an endpoint is not resident on this rank
+            r.n = (unsigned short)(tm.kind == 0 ? 2 : (tm.kind <= 3 ? 3 : 4));
         }
-        recs[lo + q] = r;
+        recs[lt] = r;
+        termMap[t] = lt;
+        lt++;
     }
-    (void)restrParm;
 }
 
-// force of one record on its own bead (and, for the role-0 record of a term, the term's energy and virial into acc)
-template <bool ENERGY>
-__device__ __forceinline__ V3 bondedEval(const BondRec &tm, const double *__restrict__ restrParm, int restrOrigin, const double4 *__restrict__ pos,
-                                         const PairConst &pc, double *acc)
+// the contributions of every local bead: where the force of (term, role) is staged, in the bead's fixed entry order
+__global__ void k_bond_resolve_beads(int nIon, const double4 *__restrict__ pos, const int *__restrict__ csrOff, const uint32_t *__restrict__ ent,
+                                     const int *__restrict__ termMap, const int *__restrict__ start, const int *__restrict__ cnt,
+                                     int *__restrict__ stageIdx)
 {
-            const int role = tm.role;
-            const bool count = ENERGY && role == 0;
-            if (tm.kind < 0) return V3{0.0, 0.0, 0.0};
+    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= nIon) return;
+    const int n = cnt[s], lo = start[s];
+    if (n == 0) return;
+    const unsigned long long w = (unsigned long long)__double_as_longlong(pos[s].w);
+    const int elo = csrOff[(int)((w >> 32) & 0x7fffffffull)];
+    for (int q = 0; q < n; q++)
+    {
+        const uint32_t e = ent[elo + q];
+        const int lt = termMap[e >> 2];      // -1: the term's role-0 bead is not local here (cannot happen for whole molecules)
+        stageIdx[lo + q] = lt >= 0 ? 4 * lt + (int)(e & 3u) : -1;
+    }
+}
+
+// forces of one term on its (up to four) beads, and its energy and virial into acc
+template <bool ENERGY>
+__device__ __forceinline__ void bondedEval(const BondRec &tm, const double *__restrict__ restrParm, int restrOrigin, const double4 *__restrict__ pos,
+                                           const PairConst &pc, double *acc, V3 fo[4])
+{
+            const bool count = ENERGY;
+            fo[0] = fo[1] = fo[2] = fo[3] = V3{0.0, 0.0, 0.0};
+            if (tm.kind < 0) return;
             if (tm.kind == 6)
             {
                 // restraint (src/restraint.c:287-357)
@@ -241,10 +267,10 @@ __device__ __forceinline__ V3 bondedEval(const BondRec &tm, const double *__rest
                     acc[0] += f.x * cd.x; acc[1] += f.y * cd.y; acc[2] += f.z * cd.z;
                     acc[3] += f.x * cd.y; acc[4] += f.x * cd.z; acc[5] += f.y * cd.z;
                 }
-                return f;
+                fo[0] = f;
+                return;
             }
             const int si = tm.s[0], sj = tm.s[1], sk = tm.s[2], sl = tm.s[3];
-            V3 f;
             if (tm.kind == 0)
             {
                 // resBondSorted (src/bioCharmmCovalentEnergiesSorted.c:18-116)
@@ -253,7 +279,8 @@ __device__ __forceinline__ V3 bondedEval(const BondRec &tm, const double *__rest
                 const double dl = len - tm.p1;
                 const double kf = -2.0 * tm.p0 * dl / len;
                 const V3 fi = vscale(b, kf);
-                f = role == 0 ? fi : V3{-fi.x, -fi.y, -fi.z};
+                fo[0] = fi;
+                fo[1] = V3{-fi.x, -fi.y, -fi.z};
                 if (count)
                 {
                     acc[6] += tm.p0 * dl * dl;
@@ -292,7 +319,9 @@ __device__ __forceinline__ V3 bondedEval(const BondRec &tm, const double *__rest
                 const double ci = coef * ibij, ck = coef * ibkj;
                 const V3 fi = V3{ci * (ukj.x - uij.x * c), ci * (ukj.y - uij.y * c), ci * (ukj.z - uij.z * c)};
                 const V3 fk = V3{ck * (uij.x - ukj.x * c), ck * (uij.y - ukj.y * c), ck * (uij.z - ukj.z * c)};
-                f = role == 0 ? fi : (role == 2 ? fk : V3{-(fi.x + fk.x), -(fi.y + fk.y), -(fi.z + fk.z)});
+                fo[0] = fi;
+                fo[1] = V3{-(fi.x + fk.x), -(fi.y + fk.y), -(fi.z + fk.z)};
+                fo[2] = fk;
                 if (count)
                 {
                     acc[7] += en;
@@ -337,8 +366,10 @@ __device__ __forceinline__ V3 bondedEval(const BondRec &tm, const double *__rest
                         kf = -2.0 * kpsi / (1 - X2 / 6 + X2 * X2 / 120 - X2 * X2 * X2 / 5040 + X2 * X2 * X2 * X2 / 362880 - X2 * X2 * X2 * X2 * X2 / 39916800);
                     }
                 }
-                const V3 dd = role == 0 ? dI : (role == 1 ? dJ : (role == 2 ? dK : dL));
-                f = vscale(dd, -kf);
+                fo[0] = vscale(dI, -kf);
+                fo[1] = vscale(dJ, -kf);
+                fo[2] = vscale(dK, -kf);
+                fo[3] = vscale(dL, -kf);
                 if (count)
                 {
                     acc[tm.kind == 4 ? 8 : 9] += en;
@@ -346,75 +377,34 @@ __device__ __forceinline__ V3 bondedEval(const BondRec &tm, const double *__rest
                     for (int a = 0; a < 6; a++) acc[a] += vir[a] * kf;
                 }
             }
-            return f;
 }
 
 // One thread per RECORD (records of a bead are consecutive, beads in slot order): every thread evaluates its record, the forces
 // are staged in shared memory, and the thread of a bead's first record adds the bead's records up in their fixed order and
 // adds the sum to the slot's pair force - no atomic, one writer per slot.  A bead belongs to the CTA that holds its first
 // record; a CTA therefore also evaluates the up to BONDED_SPILL records of its last beads that lie beyond its 128.
-#define BONDED_SPILL 256
+// Every term is evaluated ONCE, by one thread, which stages the forces on the term's beads (stage[4 term + role], coalesced);
+// k_bonded_sum then adds, per local bead, the bead's contributions in their fixed order and adds the sum to the slot's pair
+// force - no atomic, one writer per slot, the same order every run.
 template <bool ENERGY, int MINB>
 __global__ void __launch_bounds__(BONDED_THREADS, MINB)
-k_bonded(int nRec, const BondRec *__restrict__ recs, const double *__restrict__ restrParm, int restrOrigin, const double4 *__restrict__ pos,
-         PairConst pc, double *__restrict__ fx, double *__restrict__ fy, double *__restrict__ fz, double *__restrict__ partial)
+k_bonded(int nTermsLocal, const BondRec *__restrict__ recs, const double *__restrict__ restrParm, int restrOrigin, const double4 *__restrict__ pos,
+         PairConst pc, V3 *__restrict__ stage, double *__restrict__ partial)
 {
-    __shared__ double sF[3][BONDED_THREADS + BONDED_SPILL];
-    __shared__ int sEnd;
-    const int base = blockIdx.x * BONDED_THREADS;
-    if (threadIdx.x == 0) sEnd = 0;
-    __syncthreads();
+    const int lt = blockIdx.x * blockDim.x + threadIdx.x;
     double acc[BONDED_ACC];
 #pragma unroll
     for (int a = 0; a < BONDED_ACC; a++) acc[a] = 0.0;
-    int myHeadN = 0, myHeadSlot = -1;
+    if (lt < nTermsLocal)
     {
-        // first pass: this CTA's own 128 records; the heads among them tell how far the CTA's last bead reaches
-        const int idx = threadIdx.x, k = base + idx;
-        V3 f = V3{0.0, 0.0, 0.0};
-        if (k < nRec)
-        {
-            const BondRec tm = recs[k];
-            if (k - (int)tm.q >= base)                    // the bead's first record is mine too
-            {
-                f = bondedEval<ENERGY>(tm, restrParm, restrOrigin, pos, pc, acc);
-                if (tm.q == 0)
-                {
-                    myHeadN = (int)tm.n;
-                    myHeadSlot = tm.s[tm.role];
-                    atomicMax(&sEnd, k + (int)tm.n);
-                }
-            }
-        }
-        sF[0][idx] = f.x; sF[1][idx] = f.y; sF[2][idx] = f.z;
+        const BondRec tm = recs[lt];
+        V3 fo[4];
+        bondedEval<ENERGY>(tm, restrParm, restrOrigin, pos, pc, acc, fo);
+        const int need = (int)tm.n;
+#pragma unroll
+        for (int r = 0; r < 4; r++)
+            if (r < need) stage[4 * (size_t)lt + r] = fo[r];
     }
-    __syncthreads();
-    const int end = min(min(sEnd, nRec), base + BONDED_THREADS + BONDED_SPILL);     // uniform over the CTA
-    for (int idx = BONDED_THREADS + threadIdx.x; base + idx < end; idx += BONDED_THREADS)
-    {
-        // records beyond the CTA's 128 that still belong to one of its beads (first record inside the 128)
-        const int k = base + idx;
-        const BondRec tm = recs[k];
-        V3 f = V3{0.0, 0.0, 0.0};
-        if (k - (int)tm.q < base + BONDED_THREADS) f = bondedEval<ENERGY>(tm, restrParm, restrOrigin, pos, pc, acc);
-        sF[0][idx] = f.x; sF[1][idx] = f.y; sF[2][idx] = f.z;
-    }
-    __syncthreads();
-    if (myHeadSlot >= 0)
-    {
-        V3 fs = V3{0.0, 0.0, 0.0};
-        for (int j = 0; j < myHeadN; j++)
-        {
-            fs.x += sF[0][threadIdx.x + j];
-            fs.y += sF[1][threadIdx.x + j];
-            fs.z += sF[2][threadIdx.x + j];
-        }
-        // k_pair has written this slot's pair force: the bonded sum is added to it by the only thread that owns the slot
-        fx[myHeadSlot] += fs.x;
-        fy[myHeadSlot] += fs.y;
-        fz[myHeadSlot] += fs.z;
-    }
-
     if (ENERGY)
     {
         __shared__ double red[BONDED_ACC][BONDED_THREADS / 32];
@@ -433,4 +423,29 @@ k_bonded(int nRec, const BondRec *__restrict__ recs, const double *__restrict__ 
             partial[(size_t)blockIdx.x * BONDED_ACC + threadIdx.x] = v;
         }
     }
+}
+
+__global__ void __launch_bounds__(BONDED_THREADS)
+k_bonded_sum(int nLocal, const int *__restrict__ start, const int *__restrict__ cnt, const int *__restrict__ stageIdx, const V3 *__restrict__ stage,
+             double *__restrict__ fx, double *__restrict__ fy, double *__restrict__ fz)
+{
+    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= nLocal) return;
+    const int n = cnt[s];
+    if (n == 0) return;
+    const int lo = start[s];
+    V3 fs = V3{0.0, 0.0, 0.0};
+    for (int q = 0; q < n; q++)
+    {
+        const int k = stageIdx[lo + q];
+        if (k < 0) continue;
+        const V3 f = stage[k];
+        fs.x += f.x;
+        fs.y += f.y;
+        fs.z += f.z;
+    }
+    // k_pair has written this slot's pair force: the bonded sum is added to it by the only thread that owns the slot
+    fx[s] += fs.x;
+    fy[s] += fs.y;
+    fz[s] += fs.z;
 }

@@ -53,7 +53,8 @@ struct GridDev
     int maxCount;    // max full-list length over beads
     int maxRaw;      // max candidate count over beads (fp32 filter pass)
     int nInterior;   // several ranks: k_pair tiles whose rows touch no ghost slot
-    int bondTotal;   // bonded (term, endpoint) records of the resident local beads
+    int bondTotal;   // bonded (term, endpoint) entries of the resident local beads
+    int bondTerms;   // bonded terms (and restraints) whose role-0 bead is local
     int winMaxTotal; // largest tile window (beads)
     int winGlobal;   // tiles whose window did not fit
     unsigned long long totalEntries;
@@ -105,13 +106,13 @@ struct Term
     int kind, pad;
 };
 
-struct alignas(16) BondRec   // one (term, endpoint) of a resident local bead, endpoints resolved to slots at the list build
+struct alignas(16) BondRec   // one local bonded term, endpoints resolved to slots at the list build
 {
     int s[4];            // slots of the term's beads (unused: 0)
     double p0, p1, p2;
     short kind;          // term kind 0..5, 6 = restraint, -1 = an endpoint is not resident: skip
-    short role;          // which of s[] is this slot
-    unsigned short q, n; // this is record q of the n records of its bead (consecutive)
+    short role;          // 0
+    unsigned short q, n; // n = number of beads of the term (forces staged)
 };
 
 enum { PROF_INTEGRATE = 0, PROF_PAIR, PROF_BONDED, PROF_LIST, PROF_REDUCE, PROF_HALO, PROF_N = 8 };
@@ -211,9 +212,12 @@ struct ddcb200_ctx
     bool bondCsrDirty = true;
     DevBuf<int> bondCsrOff;       // nGlobal + 1: entries of bead b = bondEnt[bondCsrOff[b] .. bondCsrOff[b + 1])
     DevBuf<uint32_t> bondEnt;     // (term << 2) | role of the bead in the term; term >= nTerms = restraint term - nTerms
-    DevBuf<BondRec> bondRec;      // slot order, refreshed at every list build
-    DevBuf<int> bondCount, bondStart, scanBlocks;
-    int nBondRec = 0;             // records of the resident local beads (set at the list build)
+    DevBuf<BondRec> bondRec;      // the local terms in the slot order of their role-0 beads, refreshed at every list build
+    DevBuf<int> bondCount, bondStart, bondCount0, bondStart0, scanBlocks;
+    DevBuf<int> termMap;          // term (restraint: nTerms + index) -> local term index, -1 elsewhere
+    DevBuf<int> bondStageIdx;     // per local bead entry: 4 * local term + role
+    DevBuf<double> bondStage;     // forces of every local term on its (up to 4) beads: 12 doubles per term
+    int nBondRec = 0, nBondTerms = 0;   // entries / terms of the resident local beads (set at the list build)
     DevBuf<double> restrParm;     // 7 doubles: frac0[3], kb, fc[3]
     int restrOrigin = 0;
 
