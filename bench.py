@@ -368,7 +368,8 @@ def main():
             print(json.dumps({"steps_per_s": sps, "ms_per_step": ms / K, "gpu_launches": int(launches), "clocks": clk,
                               "variant": os.environ.get("DDCB200_PAIR", "default"), "T_K": res["T_K"], "long_run": res.get("long_run"),
                               "per_kernel_ms_per_step": {k: v[0] / 40 for k, v in prof.items()},
-                              "list_build_ms": sim.listBuildInfo()[1][0]}))
+                              "list_build_ms": sim.listBuildInfo()[1][0], "prune": sim.pruneInfo(),
+                              "env": {k: v for k, v in os.environ.items() if k.startswith("DDCB200_")}}))
         sim.close()
         return
 
@@ -399,7 +400,7 @@ def main():
                 "achieved_stored": stored_bytes / (pair_ms * 1e-3) / 1e9, "kernel_ms": pair_ms,
                 "kernel_share_of_step": prof["pair"][0] / total_prof,
                 "per_kernel_ms_per_step": {k: v[0] / KP for k, v in prof.items()},
-                "list_build": {"last_build_ms": lb_ms[0]}}
+                "list_build": {"last_build_ms": lb_ms[0]}, "pruned_rows": sim.pruneInfo()}
 
     # ---- end to end through the reference-facing calls with host buffers ---------------------
     import torch

@@ -154,6 +154,7 @@ def _declare(L):
         "ddcb200_kernelLaunches": (i64, [vp]),
         "ddcb200_lastListBuild": (i64, [vp]),
         "ddcb200_listBuildInfo": (i32, [vp, pi, pd]),
+        "ddcb200_pruneInfo": (i32, [vp, _P(C.c_int64)]),
         "ddcb200_kineticByClass": (i32, [vp, i32, i32, pd]),
         "ddcb200_pairCorrelation": (i32, [vp, i32, dbl, dbl, i32, dbl, _P(C.c_uint64), _P(C.c_uint64)]),
         "ddcb200_pairCorrelationWrite": (i32, [_P(DeckStruct), i32, C.c_char_p, i64, dbl, pd, i32]),
@@ -189,7 +190,7 @@ EXPORTS = ["ddcb200_lastError", "ddcb200_deviceCount", "ddcb200_create", "ddcb20
            "ddcb200_nglfconstraintParms", "ddcb200_nglfconstraint", "ddcb200_getBox", "ddcb200_setBox", "ddcb200_constraintFailures", "ddcb200_getCells", "ddcb200_getPairs", "ddcb200_profile",
            "ddcb200_profileRead", "ddcb200_timerRecord", "ddcb200_timerElapsed", "ddcb200_kernelLaunches", "ddcb200_lastListBuild", "ddcb200_ncclUniqueId", "ddcb200_ddcInit", "ddcb200_ddcPlan", "ddcb200_deckLoad", "ddcb200_deckFree",
            "ddcb200_lastHostError", "ddcb200_simulateBind", "ddcb200_simulateBindRank", "ddcb200_printinfoLine", "ddcb200_unitsConvert",
-           "ddcb200_printinfoHeader", "ddcb200_writeRestart", "ddcb200_readCMDS", "ddcb200_simulateMaster", "ddcb200_listBuildInfo", "ddcb200_subsetWrite", "ddcb200_writeBXYZ", "ddcb200_pairCorrelation",
+           "ddcb200_printinfoHeader", "ddcb200_writeRestart", "ddcb200_readCMDS", "ddcb200_simulateMaster", "ddcb200_listBuildInfo", "ddcb200_pruneInfo", "ddcb200_subsetWrite", "ddcb200_writeBXYZ", "ddcb200_pairCorrelation",
            "ddcb200_pairCorrelationWrite", "ddcb200_kineticByClass", "ddcb200_pairSetHash"]
 
 
@@ -538,6 +539,12 @@ class Simulate:
         ms = (C.c_double * 2)()
         self._ck(lib().ddcb200_listBuildInfo(self.ctx, C.byref(v), ms))
         return int(v.value), [ms[0], ms[1]]
+
+    def pruneInfo(self):
+        """Pruned rows of the pair walk: dict(every, since, walk_next, beads_pruned, pruned_entries, full_entries) - ddcb200_pruneInfo"""
+        a = (C.c_int64 * 6)()
+        self._ck(lib().ddcb200_pruneInfo(self.ctx, a))
+        return dict(zip(("every", "since", "walk_next", "beads_pruned", "pruned_entries", "full_entries"), [int(x) for x in a]))
 
     def printinfo(self, e=None):
         e = e or self.energyInfo()

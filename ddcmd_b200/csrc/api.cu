@@ -194,13 +194,15 @@ static int setupBox(ddcb200_ctx *c)
 // B200 through DDCB200_PAIR=<pf>,<minb> | old
 typedef void (*PairKernel)(int, int, const int *, int, const double4 *, const uint32_t *, const uint16_t *, const unsigned long long *, int,
                            const float *, const double2 *, const double *, const double *, PairConst, double *, double *, double *, double *,
-                           const unsigned long long *, const int *);
+                           const unsigned long long *, const int *, PruneArgs);
 struct PairVariant
 {
     int pf, minb;
-    PairKernel force, energy;
+    PairKernel force[3], energy[3];      // [MODE]: 0 plain, 1 walk + write the pruned rows, 2 walk the pruned rows
 };
-#define PV(P, M) {P, M, k_pair2<false, P, M>, k_pair2<true, P, 1>}      // the energy instantiation needs more registers: never capped
+// the energy instantiation needs more registers: never capped
+#define PV(P, M) {P, M, {k_pair2<false, P, M, 0>, k_pair2<false, P, M, 1>, k_pair2<false, P, M, 2>}, \
+                        {k_pair2<true, P, 1, 0>, k_pair2<true, P, 1, 1>, k_pair2<true, P, 1, 2>}}
 static const PairVariant g_pairVariants[] = {PV(1, 1), PV(2, 1), PV(2, 8), PV(3, 8), PV(4, 1)};      // measured: profiles/r02d_pair_variants.txt
 #undef PV
 static const int g_nPairVariants = (int)(sizeof(g_pairVariants) / sizeof(g_pairVariants[0]));
@@ -248,8 +250,20 @@ static int createInit(ddcb200_ctx *c)
     CK(cudaMallocHost((void **)&c->accHost, (ACC_N + 8) * sizeof(double)));
     CK(cudaMallocHost((void **)&c->ddcHost, 64 * sizeof(int)));
     CK(cudaMalloc((void **)&c->ddcCounters, 8 * sizeof(int)));
-    CK(cudaMalloc((void **)&c->dmax2, 2 * sizeof(unsigned long long)));
-    CK(cudaMemset(c->dmax2, 0, 2 * sizeof(unsigned long long)));
+    CK(cudaMalloc((void **)&c->dmax2, 4 * sizeof(unsigned long long)));
+    CK(cudaMemset(c->dmax2, 0, 4 * sizeof(unsigned long long)));
+    if (const char *ph = getenv("DDCB200_PAIRHINT")) c->pairHint = atoi(ph) & 7;      // cache-policy bits of the pair walk (pair.cuh: ldRow, ldPosH)
+    if (const char *pe = getenv("DDCB200_PRUNE"))
+    {
+        // pruned rows: <every>[,<margin>] - rewritten every <every> force evaluations from the entries closer than rmax + <margin>
+        // (length units; default deltaR * every / updateRate); 0 = off.  Results are bitwise those of the full walk (pair.cuh)
+        int every = 0;
+        double margin = 0.0;
+        const int got = sscanf(pe, "%d,%lf", &every, &margin);
+        if (got < 1 || every < 0 || every > 1000 || (got == 2 && !(margin > 0.0))) return fail(DDCB200_ERR_ARG, "DDCB200_PRUNE must be <every>[,<margin>]");
+        c->pruneEvery = every;
+        c->pruneMargin = got == 2 ? margin : 0.0;
+    }
     if (const char *pv = getenv("DDCB200_PAIR"))
     {
         int pf = 0, mb = 0;
@@ -331,7 +345,7 @@ extern "C" void ddcb200_destroy(ddcb200_ctx *c)
     c->colMap.release(); c->stage.release(); c->stageI.release();
     c->orderKey.release(); c->pos32.release(); c->nbrRawCount.release(); c->nbrCum.release();
     for (int a = 0; a < 3; a++) c->posBuild[a].release();
-    c->dispOfSlot.release();
+    c->dispOfSlot.release(); c->pruneCount.release();
     if (c->dmax2) cudaFree(c->dmax2);
     c->groupOfBead.release(); c->rngState.release(); c->rngMP.release(); c->consAtomOff.release(); c->consAtomBead.release();
     c->consPairOff.release(); c->consPairA.release(); c->consPairB.release(); c->consPairDist.release();
@@ -418,8 +432,11 @@ extern "C" int ddcb200_martiniNonBondParms(ddcb200_ctx *c, int ntypes, const dou
     CK(cudaFuncSetAttribute(k_pair<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     for (int v = 0; v < g_nPairVariants; v++)
     {
-        CK(cudaFuncSetAttribute(g_pairVariants[v].force, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        CK(cudaFuncSetAttribute(g_pairVariants[v].energy, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        for (int m = 0; m < 3; m++)
+        {
+            CK(cudaFuncSetAttribute(g_pairVariants[v].force[m], cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            CK(cudaFuncSetAttribute(g_pairVariants[v].energy[m], cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        }
     }
     {
         // windowed kernel: two CTAs per SM at the largest window it accepts; smaller windows leave room for more
@@ -751,6 +768,7 @@ extern "C" int ddcb200_updateState(ddcb200_ctx *c, int64_t nLocal, const int *be
                                                                        c->posBuild[1].p, c->posBuild[2].p, c->dmax2, c->dispOfSlot.p,
                                                                        c->nCellsBuilt > 0 ? c->cellDmax.p : nullptr, c->cellOfSlot[cur].p);
     CKL("k_update_state");
+    c->movedSinceRef = true;
     c->loop = loop;
     c->time = time;
     c->forcesValid = false;
@@ -1114,7 +1132,11 @@ extern "C" int ddcb200_constructList(ddcb200_ctx *c)
                                  c->pos32.p, c->posBuild[0].p, c->posBuild[1].p, c->posBuild[2].p);
     CKL("cell sort");
     c->cur = nxt;
-    CK(cudaMemsetAsync(c->dmax2, 0, 2 * sizeof(unsigned long long), st));
+    CK(cudaMemsetAsync(c->dmax2, 0, 4 * sizeof(unsigned long long), st));
+    c->pruneValid = false;      // the candidate buffer the pruned rows live in is overwritten by the build
+    c->rebased = false;
+    c->movedSinceRef = false;
+    c->sincePrune = 0;
     CK(c->dispOfSlot.ensure((size_t)nPad));
     CK(cudaMemsetAsync(c->dispOfSlot.p, 0, (size_t)nPad * sizeof(float), st));
 
@@ -1262,6 +1284,21 @@ extern "C" int ddcb200_constructList(ddcb200_ctx *c)
 }
 
 // ---- force evaluation -------------------------------------------------------------------
+// the pruned rows of this context (pair.cuh): where they live and the margin they are cut with
+static double pruneArgsOf(const ddcb200_ctx *c, PruneArgs &pr)
+{
+    const double deltaR = sqrt(c->box.rlist2) - c->pc.rmax;
+    double margin = c->pruneMargin > 0.0 ? c->pruneMargin : deltaR * c->pruneEvery / std::max(1, c->prm.updateRate);
+    margin = std::min(margin, deltaR);
+    pr.rows = c->nbrRaw.p;
+    pr.count = c->pruneCount.p;
+    pr.keep2 = (c->pc.rmax + margin) * (c->pc.rmax + margin) * (1.0 + 1e-12);
+    pr.walkLim = 1e300;
+    pr.useLim = c->pc.rmax + margin;
+    pr.hint = c->pairHint;
+    return margin;
+}
+
 static int reduceCols(ddcb200_ctx *c, const double *partial, int nblocks, int ncol, const int *map)
 {
     // column map lives in a small device table: [0..7] pair, [8..18] bonded, [19..25] kinetic
@@ -1358,9 +1395,13 @@ extern "C" int ddcb200_ddcenergy(ddcb200_ctx *c, int withEnergy)
     // ddcUpdate (src/ddcUpdate.c:40-88).  With a fixed rebuild rate the halo goes to its own stream: the pair rows that read no
     // ghost position run meanwhile, the others wait for it.  (updateRate = 0: neighborCheck needs the ghosts first)
     bool overlapped = false;
+    // pruned rows (pair.cuh): this evaluation writes them if it follows a build or the last prune is pruneEvery evaluations old
+    const bool pruneCfg = c->pruneEvery > 0 && c->prm.updateRate > 0 && c->pairVariant >= 0 && !c->pairWindows && c->pc.listSlack == 0.0;
+    const bool pruneStep = pruneCfg && (!c->listValid || due || !c->pruneValid || c->sincePrune + 1 >= c->pruneEvery);
     if (c->listValid && !due && c->nranks > 1 && c->haloDirty)
     {
-        if (c->haloOverlap && c->prm.updateRate > 0)
+        // (a prune step takes the reference positions of the ghosts after the halo: in line)
+        if (c->haloOverlap && c->prm.updateRate > 0 && !pruneStep)
         {
             CK(cudaEventRecord(c->evPos, c->stream));
             CK(cudaStreamWaitEvent(c->streamH, c->evPos, 0));
@@ -1397,6 +1438,33 @@ extern "C" int ddcb200_ddcenergy(ddcb200_ctx *c, int withEnergy)
     const int nLocal = (int)c->nLocal, nPad = (int)c->nPad;      // local beads = slots [0, nLocal)
     const int tiles = (nLocal + TILE - 1) / TILE;
     if (withEnergy) CK(cudaMemsetAsync(c->acc, 0, ACC_N * sizeof(double), st));
+    int pruneMode = 0;
+    PruneArgs pr = {nullptr, nullptr, 0.0, 0.0, 0.0, c->pairHint};
+    PairConst pcl = c->pc;
+    if (pruneCfg)
+    {
+        CK(c->pruneCount.ensure((size_t)nPad));
+        const double margin = pruneArgsOf(c, pr);
+        if (pruneStep)
+        {
+            if (c->movedSinceRef)
+            {
+                // the positions of this evaluation (ghosts included: the halo ran in line) become the reference of the displacement bounds
+                const int nIon = (int)c->nIon;
+                LAUNCH(k_rebase, (nIon + 255) / 256, 256, 0, st)(nIon, c->pos4[cur].p, c->posBuild[0].p, c->posBuild[1].p, c->posBuild[2].p,
+                                                              c->dispOfSlot.p, c->dmax2);
+                CKL("k_rebase");
+                if (c->nCellsBuilt > 0) CK(cudaMemsetAsync(c->cellDmax.p, 0, 2 * (size_t)c->nCellsBuilt * sizeof(unsigned long long), st));
+                c->rebased = true;
+                c->movedSinceRef = false;
+            }
+            // right after a build the rows are ordered by the distances of these very positions: the walk can stop at rmax + margin
+            if (!c->rebased) pr.walkLim = (c->pc.rmax + margin) * (1.0 + 1e-12);
+            pruneMode = 1;
+        }
+        else pruneMode = 2;
+    }
+    else if (c->rebased) pcl.listSlack = 1e30;      // no bin-limited walk against reference positions that are not the build's
     {
         const size_t smem = pairSmemBytes(c->ntypes);
         const float *disp = c->walkPerBead ? c->dispOfSlot.p : nullptr;
@@ -1421,11 +1489,11 @@ extern "C" int ddcb200_ddcenergy(ddcb200_ctx *c, int withEnergy)
             else if (c->pairVariant >= 0)
             {
                 const PairVariant &pv = g_pairVariants[c->pairVariant];
-                const PairKernel kern = withEnergy ? pv.energy : pv.force;
+                const PairKernel kern = withEnergy ? pv.energy[pruneMode] : pv.force[pruneMode];
                 const bool cellWalk = c->walkPerCell && c->walkPerBead && c->nCellsBuilt > 0;
                 LAUNCH(kern, nTiles, TILE, smem, st)(nLocal, nPad, order, base, c->pos4[cur].p, c->nbr.p, c->nbrCum.p, c->dmax2, withGhosts, disp, c->ljTab.p,
-                                                     c->shiftTab.p, c->qTab.p, c->pc, c->frc[0].p, c->frc[1].p, c->frc[2].p, c->pairPartial.p,
-                                                     cellWalk ? c->nbrDmax.p + (withGhosts ? c->nCellsBuilt : 0) : nullptr, c->cellOfSlot[cur].p);
+                                                     c->shiftTab.p, c->qTab.p, pcl, c->frc[0].p, c->frc[1].p, c->frc[2].p, c->pairPartial.p,
+                                                     cellWalk ? c->nbrDmax.p + (withGhosts ? c->nCellsBuilt : 0) : nullptr, c->cellOfSlot[cur].p, pr);
             }
             else if (withEnergy)
                 LAUNCH(k_pair<true>, nTiles, TILE, smem, st)(nLocal, nPad, order, base, c->pos4[cur].p, c->nbr.p, c->nbrCum.p, c->dmax2, withGhosts, disp,
@@ -1471,6 +1539,12 @@ extern "C" int ddcb200_ddcenergy(ddcb200_ctx *c, int withEnergy)
         else
             rc = launchPair(tiles, nullptr, 0, c->nranks > 1 ? 1 : 0);      // one launch over every row (ghost positions are in place)
         if (rc) return rc;
+        if (pruneMode == 1)
+        {
+            c->pruneValid = true;
+            c->sincePrune = 0;
+        }
+        else if (pruneMode == 2) c->sincePrune++;
     }
     int bBlocks = 0;
     if (c->nTerms + c->nRestr > 0 && c->nBondTerms > 0)
@@ -1519,7 +1593,7 @@ static int launchIntegrate(ddcb200_ctx *c, double halfDt2, double halfDt1, doubl
     ProfScope ps(c, PROF_INTEGRATE);
     const int cur = c->cur;
     const int tiles = (int)((c->nLocal + TILE - 1) / TILE);      // local beads are slots [0, nLocal)
-    if (MODE & INT_KICK1_DRIFT) c->haloDirty = true;
+    if (MODE & INT_KICK1_DRIFT) c->haloDirty = c->movedSinceRef = true;
     LAUNCH(k_integrate<MODE>, tiles, TILE, 0, c->stream)((int)c->nLocal, c->pos4[cur].p, c->vel[cur][0].p, c->vel[cur][1].p, c->vel[cur][2].p,
                                                      c->frc[0].p, c->frc[1].p, c->frc[2].p, c->massOfBead.p, halfDt2, halfDt1, dt, c->pc,
                                                      c->kinPartial.p, c->posBuild[0].p, c->posBuild[1].p, c->posBuild[2].p, c->dmax2, c->dispOfSlot.p,
@@ -1835,7 +1909,7 @@ static int launchNglfc(ddcb200_ctx *c, double halfDt, double dt, const double sc
     ProfScope ps(c, PROF_INTEGRATE);
     const int cur = c->cur;
     const int tiles = (int)((c->nLocal + TILE - 1) / TILE);
-    if (MODE & (NC_DRIFT | NC_SCALE)) c->haloDirty = true;
+    if (MODE & (NC_DRIFT | NC_SCALE)) c->haloDirty = c->movedSinceRef = true;
     LAUNCH(k_nglfc<MODE>, tiles, TILE, 0, c->stream)((int)c->nLocal, c->pos4[cur].p, c->vel[cur][0].p, c->vel[cur][1].p, c->vel[cur][2].p,
                                                  c->frc[0].p, c->frc[1].p, c->frc[2].p, c->massOfBead.p, c->groupOfBead.p, c->rngState.p,
                                                  c->rngMP.p, groupTabOf(c), halfDt, dt, scale[0], scale[1], scale[2], c->pc, c->kinPartial.p,
@@ -2158,14 +2232,15 @@ extern "C" int ddcb200_pairCorrelation(ddcb200_ctx *c, int nBins, double rmin, d
     cudaStream_t st = c->stream;
     // candidates: the cells within `reach` cells of a bead's build-time cell.  A pair with r < rmax now was within
     // rmax + 2 dmax + box slack at the build, and a cell is at least d_min wide: reach = ceil of that over d_min
-    unsigned long long dbits2[2] = {0, 0};
+    unsigned long long dbits2[3] = {0, 0, 0};      // [2]: a bound of the displacement between the build and the last prune (k_rebase)
     CK(cudaMemcpyAsync(dbits2, c->dmax2, sizeof dbits2, cudaMemcpyDeviceToHost, st));
     CK(cudaMemcpyAsync(c->gridHost, c->grid, sizeof(GridDev), cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
     const unsigned long long dbits = std::max(dbits2[0], dbits2[1]);     // locals and ghosts
-    double d2;
+    double d2, dBase;
     memcpy(&d2, &dbits, sizeof d2);
-    const double need = (rmax + 2.0 * sqrt(d2) + c->pc.listSlack) * (1.0 + 1e-9);
+    memcpy(&dBase, &dbits2[2], sizeof dBase);
+    const double need = (rmax + 2.0 * (sqrt(d2) + dBase) + c->pc.listSlack) * (1.0 + 1e-9);
     // cell edges in length units: d (fraction of the box span) x span
     const double edge[3] = {c->gridHost->d[0] * c->box.spanx, c->gridHost->d[1] * c->box.spany, c->gridHost->d[2] * c->box.spanz};
     const double dmin = std::min(edge[0], std::min(edge[1], edge[2]));
@@ -2197,6 +2272,48 @@ extern "C" int ddcb200_pairCorrelation(ddcb200_ctx *c, int nBins, double rmin, d
     CK(cudaMemcpyAsync(counts, hist.p, nh * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
     CK(cudaMemcpyAsync(nAtoms, hist.p + nh, (size_t)ns * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
+    return DDCB200_OK;
+}
+
+// measurement hook: the state of the pruned rows and what the walk of the next force evaluation at the current positions would visit
+extern "C" int ddcb200_pruneInfo(ddcb200_ctx *c, int64_t info[6])
+{
+    if (!c || !info) return fail(DDCB200_ERR_ARG, "bad arguments");
+    info[0] = c->pruneEvery;
+    info[1] = c->pruneValid ? c->sincePrune : -1;
+    info[2] = info[3] = info[4] = 0;
+    info[5] = c->totalEntries;
+    if (!c->pruneValid || !c->listValid || c->pruneEvery <= 0) return DDCB200_OK;
+    CK(cudaSetDevice(c->device));
+    cudaStream_t st = c->stream;
+    PruneArgs pr;
+    pruneArgsOf(c, pr);
+    unsigned long long *d = nullptr, h[3] = {0, 0, 0};
+    CK(cudaMalloc((void **)&d, sizeof h));
+    cudaError_t e = cudaMemsetAsync(d, 0, sizeof h, st);
+    if (e == cudaSuccess)
+    {
+        const int nLocal = (int)c->nLocal, cur = c->cur;
+        const bool cellWalk = c->walkPerCell && c->walkPerBead && c->nCellsBuilt > 0;
+        const int withGhosts = c->nranks > 1 ? 1 : 0;
+        if (cellWalk)
+        {
+            LAUNCH(k_nbr_dmax, (c->nCellsBuilt + 127) / 128, 128, 0, st)(c->grid, c->cellDmax.p, 0, c->nbrDmax.p);
+            if (withGhosts) LAUNCH(k_nbr_dmax, (c->nCellsBuilt + 127) / 128, 128, 0, st)(c->grid, c->cellDmax.p, 1, c->nbrDmax.p + c->nCellsBuilt);
+        }
+        LAUNCH(k_prune_stats, (nLocal + TILE - 1) / TILE, TILE, 0, st)(nLocal, (int)c->nPad, c->pos4[cur].p, c->nbrCum.p, c->dmax2, withGhosts,
+                                                                 c->walkPerBead ? c->dispOfSlot.p : nullptr, c->pc,
+                                                                 cellWalk ? c->nbrDmax.p + (withGhosts ? c->nCellsBuilt : 0) : nullptr,
+                                                                 c->cellOfSlot[cur].p, pr, d);
+        e = cudaGetLastError();
+    }
+    if (e == cudaSuccess) e = cudaMemcpyAsync(h, d, sizeof h, cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    cudaFree(d);
+    CK(e);
+    info[2] = (int64_t)h[0];
+    info[3] = (int64_t)h[1];
+    info[4] = (int64_t)h[2];
     return DDCB200_OK;
 }
 

@@ -644,6 +644,32 @@ k_tile_order(int nTiles, const int *__restrict__ tileGhost, int *__restrict__ or
 }
 
 
+// ---- at a prune step: the current positions become the reference of the displacement bounds ------------------------------------------
+// (k_pair2 MODE 1 writes the pruned rows from the same positions.)  dmax2[2] keeps a bound of the displacement since the BUILD
+// for the callers that still need one (the pair correlation's cell walk): the sum of the maxima of the intervals between prunes.
+__global__ void __launch_bounds__(256)
+k_rebase(int nIon, const double4 *__restrict__ pos, double *__restrict__ bx, double *__restrict__ by, double *__restrict__ bz,
+         float *__restrict__ dispOfSlot, unsigned long long *__restrict__ dmax2)
+{
+    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s < nIon)
+    {
+        const double4 p = pos[s];
+        bx[s] = p.x;
+        by[s] = p.y;
+        bz[s] = p.z;
+        dispOfSlot[s] = 0.0f;
+    }
+    if (s == 0)
+    {
+        const unsigned long long m = max(dmax2[0], dmax2[1]);
+        const double base = __longlong_as_double((long long)dmax2[2]) + sqrt(__longlong_as_double((long long)m)) * (1.0 + 1e-12);
+        dmax2[2] = (unsigned long long)__double_as_longlong(base);
+        dmax2[0] = 0ull;
+        dmax2[1] = 0ull;
+    }
+}
+
 // ---- per step: the displacement bound of every cell's neighbourhood ---------------------------------------------------------------
 // out[c] = largest squared displacement since the build of any bead in the stencil cells of cell c (its local beads, and with
 // withGhosts also its ghosts).  A partner j of a bead of cell c was in one of those cells at the build (that is how the list

@@ -241,7 +241,17 @@ struct ddcb200_ctx
     DevBuf<uint64_t> orderKey;    // (sub-cell Morton key, bead) : slot order inside a cell
     DevBuf<float4> pos32;         // fp32 copy of the build-time positions (candidate filter)
     DevBuf<double> posBuild[3];   // build-time positions, slot order (displacement bound)
-    unsigned long long *dmax2 = nullptr;   // device: [0] bits of the max squared displacement of a LOCAL bead since the build, [1] of a ghost
+    unsigned long long *dmax2 = nullptr;   // device: [0] bits of the max squared displacement of a LOCAL bead since the build (or the last
+                                           // prune), [1] of a ghost, [2] bits of a bound of the displacement between the build and the last prune
+    // pruned rows (k_pair2 MODE 1 / 2, DDCB200_PRUNE=<every>[,<margin>]; 0 = off)
+    int pairHint = 0;             // DDCB200_PAIRHINT
+    int pruneEvery = 0;           // steps between prunes
+    double pruneMargin = 0.0;     // entries closer than rmax + margin are kept (0: deltaR * pruneEvery / updateRate)
+    int sincePrune = 0;           // force evaluations since the pruned rows were written
+    bool pruneValid = false;      // the pruned rows belong to the current list and reference positions
+    bool rebased = false;         // the reference positions are no longer those of the build (bin-limited walks are off until the next build)
+    bool movedSinceRef = false;   // positions changed since the reference positions were taken
+    DevBuf<uint16_t> pruneCount;  // entries per pruned row
     bool walkPerBead = true;      // DDCB200_WALK
     bool walkPerCell = true;      // DDCB200_WALK=cell (default): d_j bounded by the bead's stencil cells instead of the whole system
     DevBuf<unsigned long long> cellDmax;   // [2 ncell]: largest squared displacement since the build per cell (local part, ghost part)

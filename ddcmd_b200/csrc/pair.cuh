@@ -24,6 +24,33 @@ __device__ __forceinline__ double4 ldPos(const double4 *p)
 #endif
 }
 
+// cache-policy A/B of the walk (DDCB200_PAIRHINT, PruneArgs::hint): the rows stream through once (bit 0: L1::no_allocate, bit 1:
+// L1::evict_first) while the gathered positions are re-read by neighbouring beads (bit 2: L1::evict_last)
+__device__ __forceinline__ uint32_t ldRow(const uint32_t *p, int hint)
+{
+#ifdef DDCB200_EMU
+    return *p;
+#else
+    uint32_t v;
+    if (hint & 1) asm volatile("ld.global.nc.L1::no_allocate.u32 %0, [%1];" : "=r"(v) : "l"(p));
+    else if (hint & 2) asm volatile("ld.global.nc.L1::evict_first.u32 %0, [%1];" : "=r"(v) : "l"(p));
+    else v = __ldg(p);
+    return v;
+#endif
+}
+
+__device__ __forceinline__ double4 ldPosH(const double4 *p, int hint)
+{
+#ifdef DDCB200_EMU
+    return *p;
+#else
+    double4 r;
+    if (hint & 4) asm volatile("ld.global.nc.L1::evict_last.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(r.x), "=d"(r.y), "=d"(r.z), "=d"(r.w) : "l"(p));
+    else asm volatile("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(r.x), "=d"(r.y), "=d"(r.z), "=d"(r.w) : "l"(p));
+    return r;
+#endif
+}
+
 #define PF 4   // gathers in flight per thread
 
 template <bool ENERGY>
@@ -225,13 +252,57 @@ __device__ __forceinline__ double rsqrtFast(double x)
 #endif
 }
 
-template <bool ENERGY, int NPF, int MINB>
+// The pruned rows (MODE): the list radius is rmax + deltaR for a rebuild every updateRate steps, but over a few steps the beads move
+// a fraction of deltaR only.  Every pruneEvery steps the walk therefore also WRITES a second, shorter row per bead (MODE 1): the
+// entries now closer than rmax + margin, in the order of the full row, and the positions of that step become the reference of the
+// displacement bounds (k_rebase).  On the steps in between (MODE 2) a bead walks its pruned row as long as its own displacement
+// plus the largest in its stencil cells since the prune stays within the margin - every skipped entry is then provably outside
+// the cutoff and would have added an exact zero, so forces and energies are bitwise those of the full walk - and its full row
+// otherwise.  The same idea as the rolling pruning of a dual pair list; here it is exact by construction, not by a drift estimate.
+// The distance (at the time the reference positions were taken: the build, or the last prune) beyond which an entry of bead ii's
+// row cannot be inside the cutoff now: rmax + its own displacement + the largest displacement of a possible partner.
+__device__ __forceinline__ double pairWalkLim(int ii, bool live, const unsigned long long *__restrict__ nbrDmax, const int *__restrict__ cellOfSlot,
+                                              const unsigned long long *__restrict__ dmax2, int withGhosts, const float *__restrict__ dispOfSlot,
+                                              const PairConst &pc)
+{
+    // d_j: the largest displacement in this bead's stencil cells (k_nbr_dmax; the launch over the rows with ghost entries
+    // gets the table that includes the ghosts), or - DDCB200_WALK=bead / global - of any resident bead
+    unsigned long long db;
+    if (nbrDmax) db = nbrDmax[cellOfSlot[ii]];
+    else
+    {
+        db = dmax2[0];
+        if (withGhosts) db = max(db, dmax2[1]);
+    }
+    const double dmax = sqrt(__longlong_as_double((long long)db));
+    double di = dmax;
+    if (live && dispOfSlot)
+    {
+        // this bead's own displacement; never more than the global maximum, which the DDCB200_WALK=bead bound is capped with
+        unsigned long long dg = dmax2[0];
+        if (withGhosts) dg = max(dg, dmax2[1]);
+        di = fmin((double)dispOfSlot[ii], sqrt(__longlong_as_double((long long)dg)));
+    }
+    return (pc.rmax + pc.listSlack + dmax + di) * (1.0 + 1e-12);
+}
+
+struct PruneArgs
+{
+    uint32_t *rows;      // pruned rows, transposed like the full rows (the candidate buffer of the list build, idle between builds)
+    uint16_t *count;     // entries per pruned row
+    double keep2;        // MODE 1: (rmax + margin)^2
+    double walkLim;      // MODE 1: the full row is walked up to this build-time distance (rmax + margin right after a build, else all)
+    double useLim;       // MODE 2: a bead may use its pruned row while rmax + its displacement bound <= rmax + margin
+    int hint;            // cache-policy bits of the row / position loads (ldRow, ldPosH)
+};
+
+template <bool ENERGY, int NPF, int MINB, int MODE>
 __global__ void __launch_bounds__(TILE, MINB)
 k_pair2(int nIon, int nPad, const int *__restrict__ tileOrder, int tileBase, const double4 *__restrict__ pos, const uint32_t *__restrict__ nbr,
         const uint16_t *__restrict__ cum, const unsigned long long *__restrict__ dmax2, int withGhosts, const float *__restrict__ dispOfSlot,
         const double2 *__restrict__ ljTab, const double *__restrict__ shiftTab, const double *__restrict__ qTab, PairConst pc,
         double *__restrict__ fx, double *__restrict__ fy, double *__restrict__ fz, double *__restrict__ accPartial,
-        const unsigned long long *__restrict__ nbrDmax, const int *__restrict__ cellOfSlot)
+        const unsigned long long *__restrict__ nbrDmax, const int *__restrict__ cellOfSlot, PruneArgs pr)
 {
     EXTERN_SHARED(double2, sLJ);               // ntypes*ntypes {6 c6, 12 c12}
     double *sQ = (double *)(sLJ + pc.ntypes * pc.ntypes);   // 256 charges
@@ -257,30 +328,20 @@ k_pair2(int nIon, int nPad, const int *__restrict__ tileOrder, int tileBase, con
     const bool charged = kqi != 0.0;
     const double2 *ljRow = sLJ + ti * pc.ntypes;
     int binLimit = 0;
+    bool usePruned = false;
     {
-        // d_j: the largest displacement in this bead's stencil cells (k_nbr_dmax; the launch over the rows with ghost entries
-        // gets the table that includes the ghosts), or - DDCB200_WALK=bead / global - of any resident bead
-        unsigned long long db;
-        if (nbrDmax) db = nbrDmax[cellOfSlot[ii]];
-        else
+        double lim = pairWalkLim(ii, live, nbrDmax, cellOfSlot, dmax2, withGhosts, dispOfSlot, pc);
+        if (MODE == 1) lim = pr.walkLim;
+        if (MODE == 2)
         {
-            db = dmax2[0];
-            if (withGhosts) db = max(db, dmax2[1]);
+            usePruned = lim <= pr.useLim;
+            lim = 1e300;      // the displacements are those since the prune, not since the build: a full row is walked to its end
         }
-        const double dmax = sqrt(__longlong_as_double((long long)db));
-        double di = dmax;
-        if (live && dispOfSlot)
-        {
-            // this bead's own displacement; never more than the global maximum, which the DDCB200_WALK=bead bound is capped with
-            unsigned long long dg = dmax2[0];
-            if (withGhosts) dg = max(dg, dmax2[1]);
-            di = fmin((double)dispOfSlot[ii], sqrt(__longlong_as_double((long long)dg)));
-        }
-        const double lim = (pc.rmax + pc.listSlack + dmax + di) * (1.0 + 1e-12);
 #pragma unroll
         for (int e = 0; e < NBINS - 1; e++) binLimit += (pc.binEdge[e] < lim) ? 1 : 0;
     }
-    const int n = live ? (int)cum[(size_t)binLimit * nPad + ii] : 0;
+    int n = 0;
+    if (live) n = (MODE == 2 && usePruned) ? (int)pr.count[ii] : (int)cum[(size_t)binLimit * nPad + ii];
     int nmax = n;
     for (int o = 16; o > 0; o >>= 1) nmax = max(nmax, __shfl_xor_sync(0xffffffffu, nmax, o));
 
@@ -288,10 +349,11 @@ k_pair2(int nIon, int nPad, const int *__restrict__ tileOrder, int tileBase, con
     double eLJ = 0.0, eEle = 0.0, vxx = 0.0, vyy = 0.0, vzz = 0.0, vxy = 0.0, vxz = 0.0, vyz = 0.0;
     const double twoKrf = 2.0 * pc.krf;
 
-    const uint32_t *row = nbr + ii;
+    const uint32_t *row = ((MODE == 2 && usePruned) ? pr.rows : nbr) + ii;
+    int nKept = 0;      // MODE 1: entries written to the pruned row so far
     uint32_t eNext[NPF];
 #pragma unroll
-    for (int u = 0; u < NPF; u++) eNext[u] = (u < n) ? row[(size_t)u * nPad] : 0u;
+    for (int u = 0; u < NPF; u++) eNext[u] = (u < n) ? ldRow(row + (size_t)u * nPad, pr.hint) : 0u;
     for (int k0 = 0; k0 < nmax; k0 += NPF)
     {
         uint32_t eCur[NPF];
@@ -301,10 +363,10 @@ k_pair2(int nIon, int nPad, const int *__restrict__ tileOrder, int tileBase, con
         {
             eCur[u] = eNext[u];
             // lanes past the end of their own row issue no load at all (a dummy gather would still cost an L1 tag lookup)
-            if (k0 + u < n) pCur[u] = ldPos(pos + (eCur[u] & 0x07ffffffu));
+            if (k0 + u < n) pCur[u] = ldPosH(pos + (eCur[u] & 0x07ffffffu), pr.hint);
         }
 #pragma unroll
-        for (int u = 0; u < NPF; u++) eNext[u] = (k0 + NPF + u < n) ? row[(size_t)(k0 + NPF + u) * nPad] : 0u;
+        for (int u = 0; u < NPF; u++) eNext[u] = (k0 + NPF + u < n) ? ldRow(row + (size_t)(k0 + NPF + u) * nPad, pr.hint) : 0u;
 #pragma unroll
         for (int u = 0; u < NPF; u++)
         {
@@ -322,6 +384,11 @@ k_pair2(int nIon, int nPad, const int *__restrict__ tileOrder, int tileBase, con
                 if (z > pc.hhz) z -= pc.hzz;
                 if (z < -pc.hhz) z += pc.hzz;
                 r2 = x * x + y * y + z * z;
+            }
+            if (MODE == 1 && have && r2 < pr.keep2)
+            {
+                pr.rows[(size_t)nKept * nPad + ii] = eCur[u];
+                nKept++;
             }
             if (have && r2 < pc.rc2)
             {
@@ -368,6 +435,7 @@ k_pair2(int nIon, int nPad, const int *__restrict__ tileOrder, int tileBase, con
         fx[i] = fxi;
         fy[i] = fyi;
         fz[i] = fzi;
+        if (MODE == 1) pr.count[i] = (uint16_t)nKept;
     }
     if (ENERGY)
     {
@@ -388,6 +456,38 @@ k_pair2(int nIon, int nPad, const int *__restrict__ tileOrder, int tileBase, con
             for (int w = 0; w < TILE / 32; w++) t += red[threadIdx.x][w];
             accPartial[(size_t)tile * 8 + threadIdx.x] = t;
         }
+    }
+}
+
+
+// what the walk of the next force evaluation would visit (ddcb200_pruneInfo; a measurement hook, not part of a step):
+// out[0] = entries of the rows the beads would walk, out[1] = beads that would walk their pruned row, out[2] = entries of all pruned rows
+__global__ void __launch_bounds__(TILE)
+k_prune_stats(int nIon, int nPad, const double4 *__restrict__ pos, const uint16_t *__restrict__ cum, const unsigned long long *__restrict__ dmax2,
+              int withGhosts, const float *__restrict__ dispOfSlot, PairConst pc, const unsigned long long *__restrict__ nbrDmax,
+              const int *__restrict__ cellOfSlot, PruneArgs pr, unsigned long long *__restrict__ out)
+{
+    const int i = blockIdx.x * TILE + threadIdx.x;
+    unsigned long long walked = 0ull, pruned = 0ull, kept = 0ull;
+    if (i < nIon && !(((uint64_t)__double_as_longlong(pos[i].w)) >> 63))
+    {
+        const double lim = pairWalkLim(i, true, nbrDmax, cellOfSlot, dmax2, withGhosts, dispOfSlot, pc);
+        const bool usePruned = lim <= pr.useLim;
+        walked = usePruned ? pr.count[i] : cum[(size_t)(NBINS - 1) * nPad + i];
+        pruned = usePruned ? 1ull : 0ull;
+        kept = pr.count[i];
+    }
+    for (int o = 16; o > 0; o >>= 1)
+    {
+        walked += __shfl_xor_sync(0xffffffffu, walked, o);
+        pruned += __shfl_xor_sync(0xffffffffu, pruned, o);
+        kept += __shfl_xor_sync(0xffffffffu, kept, o);
+    }
+    if ((threadIdx.x & 31) == 0)
+    {
+        atomicAdd(out, walked);
+        atomicAdd(out + 1, pruned);
+        atomicAdd(out + 2, kept);
     }
 }
 

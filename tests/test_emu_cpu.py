@@ -56,6 +56,11 @@ def test_emu_per_bead_walk_bound(emu, golden_dir, name, monkeypatch):
     tv.test_per_bead_walk_bound_is_bitwise_neutral(golden_dir, name, monkeypatch)
 
 
+@pytest.mark.parametrize("name", ["popc_small"])
+def test_emu_pruned_rows(emu, golden_dir, name, monkeypatch):
+    tv.test_pruned_rows_are_bitwise_neutral(golden_dir, name, monkeypatch)
+
+
 def test_emu_row_capacity_regrow(emu, golden_dir, monkeypatch):
     tv.test_row_capacity_regrow(golden_dir, monkeypatch)
 

@@ -61,6 +61,44 @@ def test_per_bead_walk_bound_is_bitwise_neutral(golden_dir, name, monkeypatch):
         assert a[1] == b[1] and a[2] == b[2] and np.array_equal(a[3], b[3])
 
 
+@pytest.mark.parametrize("name", ["popc_small", "ras_small"])
+def test_pruned_rows_are_bitwise_neutral(golden_dir, name, monkeypatch):
+    """DDCB200_PRUNE: every few steps the pair walk also writes a shorter row per bead (entries closer than rmax + margin) and the
+    steps in between walk that row while the displacement bounds since the prune stay within the margin, the full row otherwise.
+    Every skipped entry is outside the cutoff, so 45 steps (two rebuilds) are bitwise the same - with a margin that holds, with
+    one so small that beads fall back to their full rows, and with energies evaluated on prune steps and on steps in between."""
+    out = {}
+    for tag, prune in (("off", "0"), ("p4", "4"), ("p5wide", "5,1.5"), ("p3tiny", "3,0.05"), ("p2", "2,0.4")):
+        monkeypatch.setenv("DDCB200_PRUNE", prune)
+        sim, _ = _load(golden_dir, name)
+        trace = []
+        for n in (7, 6, 12, 20):                  # energies at steps 7, 13, 25, 45: prune steps and steps in between
+            sim.nglf(n)
+            e = sim.energyInfo()
+            trace.append((e.eion, e.rk, tuple(e.virial[:])))
+        st = sim.getState()
+        info = sim.pruneInfo()
+        out[tag] = (st, trace, info)
+        sim.close()
+    # the pruned rows really are in use: with a margin that holds nearly every bead would walk its short row, with the tiny one none
+    i4, itiny = out["p4"][2], out["p3tiny"][2]
+    n = len(out["off"][0]["rx"])
+    assert out["off"][2]["every"] == 0 and out["off"][2]["since"] == -1
+    assert i4["every"] == 4 and 0 <= i4["since"] < 4 and i4["full_entries"] > 0
+    assert 0 < i4["pruned_entries"] < 0.8 * i4["full_entries"]
+    assert i4["beads_pruned"] > 0.5 * n and i4["walk_next"] < 0.9 * i4["full_entries"]
+    assert itiny["beads_pruned"] < 0.5 * n
+    a = out["off"]
+    for tag in ("p4", "p5wide", "p3tiny", "p2"):
+        b = out[tag]
+        for k in ("rx", "ry", "rz", "vx", "vy", "vz", "fx", "fy", "fz"):
+            assert np.array_equal(a[0][k], b[0][k]), (tag, k)
+        assert a[1] == b[1], tag
+    monkeypatch.setenv("DDCB200_PRUNE", "-1")
+    with pytest.raises(dd.DdcError):
+        _load(golden_dir, name)
+
+
 def test_row_capacity_regrow(golden_dir, monkeypatch):
     """A first build whose rows overflow the allocated capacity (forced small here) regrows from the measured maximum and repeats:
     same pairs, same forces as with the default capacity."""
