@@ -470,7 +470,7 @@ class Simulate:
         ms = (C.c_double * 8)()
         ln = (C.c_int64 * 8)()
         self._ck(lib().ddcb200_profileRead(self.ctx, ms, ln, int(reset)))
-        names = ("integrate", "pair", "bonded", "list", "reduce", "halo")
+        names = ("integrate", "pair", "bonded", "list", "reduce", "halo", "pair_prune")
         return {k: (ms[i], int(ln[i])) for i, k in enumerate(names)}
 
     def timerRecord(self, which):

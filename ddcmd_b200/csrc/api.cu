@@ -252,15 +252,23 @@ static int createInit(ddcb200_ctx *c)
     CK(cudaMalloc((void **)&c->ddcCounters, 8 * sizeof(int)));
     CK(cudaMalloc((void **)&c->dmax2, 4 * sizeof(unsigned long long)));
     CK(cudaMemset(c->dmax2, 0, 4 * sizeof(unsigned long long)));
-    if (const char *ph = getenv("DDCB200_PAIRHINT")) c->pairHint = atoi(ph) & 7;      // cache-policy bits of the pair walk (pair.cuh: ldRow, ldPosH)
+    if (const char *lb = getenv("DDCB200_LISTBUILD"))
+    {
+        // A/B: "fused" = one pass (k_nbr_build: rows in stencil order), "twopass" = candidate pass + exact pass (rows ordered by distance bin)
+        if (strcmp(lb, "fused") == 0) c->listFused = true;
+        else if (strcmp(lb, "twopass") == 0) c->listFused = false;
+        else return fail(DDCB200_ERR_ARG, "DDCB200_LISTBUILD must be fused or twopass");
+    }
     if (const char *pe = getenv("DDCB200_PRUNE"))
     {
-        // pruned rows: <every>[,<margin>] - rewritten every <every> force evaluations from the entries closer than rmax + <margin>
-        // (length units; default deltaR * every / updateRate); 0 = off.  Results are bitwise those of the full walk (pair.cuh)
+        // pruned rows: <every>[,<margin>] - rewritten every <every> force evaluations from the entries closer than rmax + <margin> x deltaR
+        // (default margin 1.4 x every / updateRate: a bead and its fastest neighbour move about 0.07 deltaR per step at 310 K);
+        // 0 = off.  Results are bitwise those of the full walk whatever the values (pair.cuh)
         int every = 0;
         double margin = 0.0;
         const int got = sscanf(pe, "%d,%lf", &every, &margin);
-        if (got < 1 || every < 0 || every > 1000 || (got == 2 && !(margin > 0.0))) return fail(DDCB200_ERR_ARG, "DDCB200_PRUNE must be <every>[,<margin>]");
+        if (got < 1 || every < 0 || every > 1000 || (got == 2 && !(margin > 0.0 && margin <= 1.0)))
+            return fail(DDCB200_ERR_ARG, "DDCB200_PRUNE must be <every>[,<margin as a fraction of deltaR>]");
         c->pruneEvery = every;
         c->pruneMargin = got == 2 ? margin : 0.0;
     }
@@ -1201,14 +1209,25 @@ extern "C" int ddcb200_constructList(ddcb200_ctx *c)
         CK(c->nbr.ensure((size_t)c->nbrCap * nPad));
         CK(c->nbrRaw.ensure((size_t)c->nbrCap * nPad));
         CK(cudaEventRecord(c->evList[0], st));
-        LAUNCH(k_nbr_filter, tilesL, 128, 0, st)(nLocal, nPad, c->pos32.p, c->cellOfSlot[nxt].p, c->cellStart.p, c->box, rl2f, c->grid,
-                                            c->nbrCap, c->nbrRaw.p, c->nbrRawCount.p);
-        CKL("k_nbr_filter");
-        LAUNCH(k_nbr_exact, tilesL, 128, 0, st)(nLocal, nPad, c->nbrCap, c->pos4[nxt].p, c->box, c->grid, c->nbrRaw.p, c->nbrRawCount.p,
-                                               c->nbr.p, c->nbrCount.p, c->nbrCum.p, c->gidOfBead.p, c->molTypeOfBead.p,
-                                               c->molTypeSingle.p, c->bpairOffset.p, c->bpairKey.p, c->haveExcl ? 1 : 0,
-                                               c->nranks > 1 ? c->tileGhost.p : nullptr, c->pairWindows ? c->tileWin.p : nullptr);
-        CKL("k_nbr_exact");
+        if (c->listFused && !c->pairWindows)
+        {
+            LAUNCH(k_nbr_build, tilesL, 128, 0, st)(nLocal, nPad, c->nbrCap, c->pos32.p, c->pos4[nxt].p, c->cellOfSlot[nxt].p, c->cellStart.p, c->box, rl2f,
+                                                   c->grid, c->nbr.p, c->nbrCount.p, c->nbrCum.p, c->gidOfBead.p, c->molTypeOfBead.p,
+                                                   c->molTypeSingle.p, c->bpairOffset.p, c->bpairKey.p, c->haveExcl ? 1 : 0,
+                                                   c->nranks > 1 ? c->tileGhost.p : nullptr);
+            CKL("k_nbr_build");
+        }
+        else
+        {
+            LAUNCH(k_nbr_filter, tilesL, 128, 0, st)(nLocal, nPad, c->pos32.p, c->cellOfSlot[nxt].p, c->cellStart.p, c->box, rl2f, c->grid,
+                                                c->nbrCap, c->nbrRaw.p, c->nbrRawCount.p);
+            CKL("k_nbr_filter");
+            LAUNCH(k_nbr_exact, tilesL, 128, 0, st)(nLocal, nPad, c->nbrCap, c->pos4[nxt].p, c->box, c->grid, c->nbrRaw.p, c->nbrRawCount.p,
+                                                   c->nbr.p, c->nbrCount.p, c->nbrCum.p, c->gidOfBead.p, c->molTypeOfBead.p,
+                                                   c->molTypeSingle.p, c->bpairOffset.p, c->bpairKey.p, c->haveExcl ? 1 : 0,
+                                                   c->nranks > 1 ? c->tileGhost.p : nullptr, c->pairWindows ? c->tileWin.p : nullptr);
+            CKL("k_nbr_exact");
+        }
         CK(cudaEventRecord(c->evList[1], st));
         if (c->nranks > 1)
         {
@@ -1288,14 +1307,13 @@ extern "C" int ddcb200_constructList(ddcb200_ctx *c)
 static double pruneArgsOf(const ddcb200_ctx *c, PruneArgs &pr)
 {
     const double deltaR = sqrt(c->box.rlist2) - c->pc.rmax;
-    double margin = c->pruneMargin > 0.0 ? c->pruneMargin : deltaR * c->pruneEvery / std::max(1, c->prm.updateRate);
-    margin = std::min(margin, deltaR);
+    const double frac = c->pruneMargin > 0.0 ? c->pruneMargin : 1.4 * c->pruneEvery / std::max(1, c->prm.updateRate);
+    const double margin = deltaR * std::min(frac, 1.0);
     pr.rows = c->nbrRaw.p;
     pr.count = c->pruneCount.p;
     pr.keep2 = (c->pc.rmax + margin) * (c->pc.rmax + margin) * (1.0 + 1e-12);
     pr.walkLim = 1e300;
     pr.useLim = c->pc.rmax + margin;
-    pr.hint = c->pairHint;
     return margin;
 }
 
@@ -1439,7 +1457,7 @@ extern "C" int ddcb200_ddcenergy(ddcb200_ctx *c, int withEnergy)
     const int tiles = (nLocal + TILE - 1) / TILE;
     if (withEnergy) CK(cudaMemsetAsync(c->acc, 0, ACC_N * sizeof(double), st));
     int pruneMode = 0;
-    PruneArgs pr = {nullptr, nullptr, 0.0, 0.0, 0.0, c->pairHint};
+    PruneArgs pr = {nullptr, nullptr, 0.0, 0.0, 0.0};
     PairConst pcl = c->pc;
     if (pruneCfg)
     {
@@ -1472,7 +1490,7 @@ extern "C" int ddcb200_ddcenergy(ddcb200_ctx *c, int withEnergy)
         auto launchPair = [&](int nTiles, const int *order, int base, int withGhosts) -> int {
             if (nTiles <= 0) return DDCB200_OK;
             cudaStream_t st = pst;
-            ProfScope ps(c, PROF_PAIR, st);
+            ProfScope ps(c, pruneMode == 1 ? PROF_PAIR_PRUNE : PROF_PAIR, st);
             if (c->pairWindows)
             {
                 const int wcap = (c->winMaxTotal + 7) & ~7;

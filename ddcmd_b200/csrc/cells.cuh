@@ -611,6 +611,192 @@ k_nbr_exact(int nIon, int nPad, int cap, const double4 *__restrict__ pos, BoxCon
     }
 }
 
+// ---- 9b. the list build in one pass ---------------------------------------------------------------------------------------------
+// One thread per local slot.  The fp32 scan of the stencil (the conservative filter of k_nbr_filter; x-adjacent cells are one run
+// of consecutive slots, so a bead scans 9 long runs instead of 27 short ones) pushes its survivors on a per-lane queue in shared
+// memory; the warp pops the queues together - one candidate per lane per round, while every lane has one or a queue fills up - and
+// takes pairlist1's decision in fp64 exactly as k_nbr_exact does (same arithmetic, bit for bit the same membership).  Compacting
+// through the queues keeps the expensive exact block converged (16 % of the scanned candidates survive: without the queues nearly
+// every scan iteration would enter it with a handful of lanes), and because the lanes pop in step their rows grow in step, so the
+// transposed row stores of a warp fall into one or two lines.  No candidate buffer, no second sweep; rows are in stencil order (no
+// distance bins: the pruned rows of the pair walk do that job, pair.cuh).
+#define NBQ 32          // queue slots per lane
+#define NBQ_HEAD 12     // a lane's queue this close to full makes the warp pop
+__global__ void __launch_bounds__(128)
+k_nbr_build(int nIon, int nPad, int cap, const float4 *__restrict__ pos32, const double4 *__restrict__ pos, const int *__restrict__ cellOf,
+            const int *__restrict__ cellStart, BoxConst b, float rl2f, GridDev *gp, uint32_t *__restrict__ out, int *__restrict__ count,
+            uint16_t *__restrict__ cum, const uint64_t *__restrict__ gid, const int *__restrict__ molTypeOfBead,
+            const int *__restrict__ molTypeSingle, const int *__restrict__ bpairOffset, const uint32_t *__restrict__ bpairKey, int haveExcl,
+            int *__restrict__ tileGhost)
+{
+    __shared__ uint32_t sQ[4][NBQ][32];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const float4 pi = pos32[i < nIon ? i : 0];
+    const bool act = i < nIon && pi.w == 0.0f;
+    const double4 pd = pos[i < nIon ? i : 0];
+    const uint64_t wi = (uint64_t)__double_as_longlong(pd.w);
+    int head = 0, tail = 0, total = 0;
+    bool ghostEntry = false;      // some entry of this row is a ghost slot (several ranks): the row waits for the halo
+
+    // one queued candidate of this lane: pairlist1's test (src/pairlist.c:280-288), reOrgPairs' pruning flag, the row store
+    auto popOne = [&]() {
+        const uint32_t j = sQ[wib][head & (NBQ - 1)][lane];
+        head++;
+        const double4 pj = ldPos256(pos + j);
+        double x = __dadd_rn(pd.x, -pj.x), y = __dadd_rn(pd.y, -pj.y), z = __dadd_rn(pd.z, -pj.z);
+        double r2 = exactR2(x, y, z);
+        if (r2 > b.R2cut)
+        {
+            wrapOnce(x, y, z, b);
+            r2 = exactR2(x, y, z);
+        }
+        if (r2 < b.rlist2)
+        {
+            uint32_t ent = j;
+            const uint64_t wj = (uint64_t)__double_as_longlong(pj.w);
+            ghostEntry |= (wj >> 63) != 0ull;
+            if (haveExcl)
+            {
+                // same molecule? bits 16..31 of w carry the low 16 bits of gid>>32: cheap reject before the gid gathers
+                if (((wi ^ wj) & 0xffff0000ull) == 0ull &&
+                    isPruned((int)((wi >> 32) & 0x7fffffffull), (int)((wj >> 32) & 0x7fffffffull), gid, molTypeOfBead, molTypeSingle, bpairOffset, bpairKey))
+                    ent |= EXCL_BIT;
+            }
+            if (total < cap) out[(size_t)total * nPad + i] = ent;
+            total++;
+        }
+    };
+    // mode 0: pop while every scanning lane has a candidate or some queue is nearly full; 1: one round (a lane is blocked on a
+    // full queue); 2: until every queue is empty.  Warp-uniform: every lane of the warp calls it at the same places.
+    auto drain = [&](int mode) {
+        for (;;)
+        {
+            const int q = tail - head;
+            const int mx = __reduce_max_sync(0xffffffffu, q);
+            if (mx == 0) break;
+            const int mn = __reduce_min_sync(0xffffffffu, act ? q : 0x7fffffff);
+            if (mode == 0 && !(mn >= 1 || mx > NBQ - NBQ_HEAD)) break;
+            if (q > 0) popOne();
+            if (mode == 1) break;
+        }
+    };
+
+    const int nx = gp->n[0], ny = gp->n[1], nz = gp->n[2], ncell = nx * ny * nz;
+    const float Lx = (float)b.hxx, Ly = (float)b.hyy, Lz = (float)b.hzz;
+    const float hx2 = 0.5f * Lx, hy2 = 0.5f * Ly, hz2 = 0.5f * Lz;
+    // with >= 3 cells along an axis a wrapped stencil cell has ONE possible image: shift it;
+    // with fewer the stencil is deduplicated and each pair takes its nearest image
+    const bool px = nx < 3, py = ny < 3, pz = nz < 3;
+    const int c = act ? cellOf[i] : 0;
+    const int cx = c % nx, cy = (c / nx) % ny, cz = c / (nx * ny);
+    const int ly = ny >= 3 ? -1 : 0, hy = ny >= 2 ? 1 : 0;
+    const int lz = nz >= 3 ? -1 : 0, hz = nz >= 2 ? 1 : 0;
+    // runs along x (uniform count for the warp): nx >= 3: the run of the cells cx-1 .. cx+1 clipped to the row + the one cell
+    // that wraps around (empty for most beads); nx < 3: the one or two cells of the row, pairs take their nearest image
+    const int nseg = 2;
+    for (int dz = lz; dz <= hz; dz++)
+    {
+        int az = cz + dz;
+        float sz = 0.0f;
+        if (az < 0) { az += nz; sz = -Lz; }
+        else if (az >= nz) { az -= nz; sz = Lz; }
+        const float bz = pz ? pi.z : pi.z - sz;
+        for (int dy = ly; dy <= hy; dy++)
+        {
+            int ay = cy + dy;
+            float sy = 0.0f;
+            if (ay < 0) { ay += ny; sy = -Ly; }
+            else if (ay >= ny) { ay -= ny; sy = Ly; }
+            const float by = py ? pi.y : pi.y - sy;
+            const int rowBase = nx * (ay + ny * az);
+            for (int sg = 0; sg < nseg; sg++)
+            {
+                int c0, c1;      // cells c0 .. c1 of the row; c1 < c0: nothing
+                float sx = 0.0f;
+                if (!px)
+                {
+                    if (sg == 0) { c0 = max(cx - 1, 0); c1 = min(cx + 1, nx - 1); }
+                    else if (cx == 0) { c0 = c1 = nx - 1; sx = -Lx; }
+                    else if (cx == nx - 1) { c0 = c1 = 0; sx = Lx; }
+                    else { c0 = 1; c1 = 0; }
+                }
+                else
+                {
+                    // one or two cells: sg = 0 the bead's own, sg = 1 the other one (nx = 2)
+                    if (sg == 0) c0 = c1 = cx;
+                    else if (nx == 2) c0 = c1 = 1 - cx;
+                    else { c0 = 1; c1 = 0; }
+                }
+                const float bx = px ? pi.x : pi.x - sx;
+                // the cells' local beads, then (several ranks) their ghosts
+                for (int part = 0; part < 2; part++)
+                {
+                    int j = 0, hi = 0;
+                    if (act && c1 >= c0)
+                    {
+                        j = cellStart[part * ncell + rowBase + c0];
+                        hi = cellStart[part * ncell + rowBase + c1 + 1];
+                    }
+                    for (;;)
+                    {
+                        // scan until the end of the run or until this lane's queue is full
+                        const int stop = min(hi, j + (NBQ - (tail - head)));
+                        for (; j < stop; j++)
+                        {
+                            const float4 pj = pos32[j];
+                            float x = bx - pj.x, y = by - pj.y, z = bz - pj.z;
+                            if (px) { if (x > hx2) x -= Lx; if (x < -hx2) x += Lx; }
+                            if (py) { if (y > hy2) y -= Ly; if (y < -hy2) y += Ly; }
+                            if (pz) { if (z > hz2) z -= Lz; if (z < -hz2) z += Lz; }
+                            const float r2 = x * x + y * y + z * z;
+                            if (r2 < rl2f && j != i)
+                            {
+                                sQ[wib][tail & (NBQ - 1)][lane] = (uint32_t)j;
+                                tail++;
+                            }
+                        }
+                        const bool blocked = j < hi;
+                        if (!__any_sync(0xffffffffu, blocked)) break;
+                        drain(1);
+                    }
+                    drain(0);
+                }
+            }
+        }
+    }
+    drain(2);
+    if (act)
+    {
+        const uint16_t t16 = (uint16_t)min(total, cap);
+#pragma unroll
+        for (int bnd = 0; bnd < NBINS; bnd++) cum[(size_t)bnd * nPad + i] = t16;      // no distance bins: every boundary is the row's end
+        count[i] = min(total, cap);
+    }
+    // statistics (maxRaw: what a row needs, for the regrow of the capacity)
+    int m = total;
+    for (int o = 16; o > 0; o >>= 1) m = max(m, __shfl_xor_sync(0xffffffffu, m, o));
+    unsigned long long t = (unsigned long long)min(total, cap);
+    for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+    if (lane == 0 && m > 0)
+    {
+        atomicMax(&gp->maxCount, m);
+        atomicMax(&gp->maxRaw, m);
+        atomicAdd(&gp->totalEntries, t);
+        if (m > cap) atomicOr(&gp->error, 1);
+    }
+    if (tileGhost)
+    {
+        // one tile of k_pair = this block (TILE threads): does any of its rows read a ghost position?
+        __shared__ int anyGhost;
+        if (threadIdx.x == 0) anyGhost = 0;
+        __syncthreads();
+        if (ghostEntry) atomicOr(&anyGhost, 1);
+        __syncthreads();
+        if (threadIdx.x == 0) tileGhost[blockIdx.x] = anyGhost;
+    }
+}
+
 // Order of the k_pair tiles on several ranks: the tiles whose rows touch no ghost first (they run while the halo is in
 // flight), then the others; ascending inside each group.  One block; nInterior goes to the grid record.
 __global__ void __launch_bounds__(1024)

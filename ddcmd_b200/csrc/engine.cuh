@@ -115,7 +115,7 @@ struct alignas(16) BondRec   // one local bonded term, endpoints resolved to slo
     unsigned short q, n; // n = number of beads of the term (forces staged)
 };
 
-enum { PROF_INTEGRATE = 0, PROF_PAIR, PROF_BONDED, PROF_LIST, PROF_REDUCE, PROF_HALO, PROF_N = 8 };
+enum { PROF_INTEGRATE = 0, PROF_PAIR, PROF_BONDED, PROF_LIST, PROF_REDUCE, PROF_HALO, PROF_PAIR_PRUNE, PROF_N = 8 };      // PAIR_PRUNE: the pair launches that also write the pruned rows
 enum { ACC_ELJ = 0, ACC_EELE, ACC_VXX, ACC_VYY, ACC_VZZ, ACC_VXY, ACC_VXZ, ACC_VYZ,
        ACC_EBOND, ACC_EANGLE, ACC_ETORS, ACC_EIMPR, ACC_EREST, ACC_RK,
        ACC_TXX, ACC_TYY, ACC_TZZ, ACC_TXY, ACC_TXZ, ACC_TYZ, ACC_MVX, ACC_MVY, ACC_MVZ, ACC_NENTRIES, ACC_N = 24 };
@@ -244,9 +244,9 @@ struct ddcb200_ctx
     unsigned long long *dmax2 = nullptr;   // device: [0] bits of the max squared displacement of a LOCAL bead since the build (or the last
                                            // prune), [1] of a ghost, [2] bits of a bound of the displacement between the build and the last prune
     // pruned rows (k_pair2 MODE 1 / 2, DDCB200_PRUNE=<every>[,<margin>]; 0 = off)
-    int pairHint = 0;             // DDCB200_PAIRHINT
+    bool listFused = true;        // DDCB200_LISTBUILD
     int pruneEvery = 0;           // steps between prunes
-    double pruneMargin = 0.0;     // entries closer than rmax + margin are kept (0: deltaR * pruneEvery / updateRate)
+    double pruneMargin = 0.0;     // entries closer than rmax + pruneMargin x deltaR are kept (0: 1.4 x pruneEvery / updateRate)
     int sincePrune = 0;           // force evaluations since the pruned rows were written
     bool pruneValid = false;      // the pruned rows belong to the current list and reference positions
     bool rebased = false;         // the reference positions are no longer those of the build (bin-limited walks are off until the next build)

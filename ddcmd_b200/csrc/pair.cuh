@@ -24,30 +24,16 @@ __device__ __forceinline__ double4 ldPos(const double4 *p)
 #endif
 }
 
-// cache-policy A/B of the walk (DDCB200_PAIRHINT, PruneArgs::hint): the rows stream through once (bit 0: L1::no_allocate, bit 1:
-// L1::evict_first) while the gathered positions are re-read by neighbouring beads (bit 2: L1::evict_last)
-__device__ __forceinline__ uint32_t ldRow(const uint32_t *p, int hint)
+// A row streams through once: its loads do not allocate in L1, which is left to the gathered positions that neighbouring beads
+// re-read (measured: -3 % on the walk; evict-last on the position loads made no difference - profiles/r02o_prune_ab.txt)
+__device__ __forceinline__ uint32_t ldRow(const uint32_t *p)
 {
 #ifdef DDCB200_EMU
     return *p;
 #else
     uint32_t v;
-    if (hint & 1) asm volatile("ld.global.nc.L1::no_allocate.u32 %0, [%1];" : "=r"(v) : "l"(p));
-    else if (hint & 2) asm volatile("ld.global.nc.L1::evict_first.u32 %0, [%1];" : "=r"(v) : "l"(p));
-    else v = __ldg(p);
+    asm("ld.global.nc.L1::no_allocate.u32 %0, [%1];" : "=r"(v) : "l"(p));
     return v;
-#endif
-}
-
-__device__ __forceinline__ double4 ldPosH(const double4 *p, int hint)
-{
-#ifdef DDCB200_EMU
-    return *p;
-#else
-    double4 r;
-    if (hint & 4) asm volatile("ld.global.nc.L1::evict_last.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(r.x), "=d"(r.y), "=d"(r.z), "=d"(r.w) : "l"(p));
-    else asm volatile("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(r.x), "=d"(r.y), "=d"(r.z), "=d"(r.w) : "l"(p));
-    return r;
 #endif
 }
 
@@ -293,7 +279,6 @@ struct PruneArgs
     double keep2;        // MODE 1: (rmax + margin)^2
     double walkLim;      // MODE 1: the full row is walked up to this build-time distance (rmax + margin right after a build, else all)
     double useLim;       // MODE 2: a bead may use its pruned row while rmax + its displacement bound <= rmax + margin
-    int hint;            // cache-policy bits of the row / position loads (ldRow, ldPosH)
 };
 
 template <bool ENERGY, int NPF, int MINB, int MODE>
@@ -353,7 +338,7 @@ k_pair2(int nIon, int nPad, const int *__restrict__ tileOrder, int tileBase, con
     int nKept = 0;      // MODE 1: entries written to the pruned row so far
     uint32_t eNext[NPF];
 #pragma unroll
-    for (int u = 0; u < NPF; u++) eNext[u] = (u < n) ? ldRow(row + (size_t)u * nPad, pr.hint) : 0u;
+    for (int u = 0; u < NPF; u++) eNext[u] = (u < n) ? ldRow(row + (size_t)u * nPad) : 0u;
     for (int k0 = 0; k0 < nmax; k0 += NPF)
     {
         uint32_t eCur[NPF];
@@ -363,10 +348,10 @@ k_pair2(int nIon, int nPad, const int *__restrict__ tileOrder, int tileBase, con
         {
             eCur[u] = eNext[u];
             // lanes past the end of their own row issue no load at all (a dummy gather would still cost an L1 tag lookup)
-            if (k0 + u < n) pCur[u] = ldPosH(pos + (eCur[u] & 0x07ffffffu), pr.hint);
+            if (k0 + u < n) pCur[u] = ldPos(pos + (eCur[u] & 0x07ffffffu));
         }
 #pragma unroll
-        for (int u = 0; u < NPF; u++) eNext[u] = (k0 + NPF + u < n) ? ldRow(row + (size_t)(k0 + NPF + u) * nPad, pr.hint) : 0u;
+        for (int u = 0; u < NPF; u++) eNext[u] = (k0 + NPF + u < n) ? ldRow(row + (size_t)(k0 + NPF + u) * nPad) : 0u;
 #pragma unroll
         for (int u = 0; u < NPF; u++)
         {

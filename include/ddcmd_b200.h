@@ -243,7 +243,7 @@ int ddcb200_pairCorrelation(ddcb200_ctx *ctx, int nBins, double rmin, double del
 int ddcb200_listBuildInfo(ddcb200_ctx *ctx, int *variant, double ms[2]);
 
 /* Pruned rows of the pair walk (measurement hook, no reference counterpart; DDCB200_PRUNE=<every>[,<margin>]): every <every> force
- * evaluations the pair kernel also writes, per bead, the entries now closer than rmax + margin; in between a bead walks that
+ * evaluations the pair kernel also writes, per bead, the entries now closer than rmax + margin x deltaR; in between a bead walks that
  * shorter row while its displacement bounds since the prune stay within the margin (bitwise the results of the full walk).
  * info[0] = <every> (0: off), [1] = evaluations since the rows were written (-1: none valid), [2] = entries the next evaluation
  * would walk at the current positions, [3] = local beads that would walk their pruned row, [4] = entries of all pruned rows,

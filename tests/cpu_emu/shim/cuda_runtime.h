@@ -370,6 +370,24 @@ static inline int __all_sync(unsigned mk, int pred)
     (void)mk;
     return 1;
 }
+static inline int __reduce_max_sync(unsigned, int v)
+{
+    uint32_t m;
+    const uint64_t *x = emu::warpPost(emu::toBits(v), m);
+    int r = v;
+    for (int l = 0; l < 32; l++)
+        if ((m >> l) & 1u) r = std::max(r, emu::fromBits<int>(x[l]));
+    return r;
+}
+static inline int __reduce_min_sync(unsigned, int v)
+{
+    uint32_t m;
+    const uint64_t *x = emu::warpPost(emu::toBits(v), m);
+    int r = v;
+    for (int l = 0; l < 32; l++)
+        if ((m >> l) & 1u) r = std::min(r, emu::fromBits<int>(x[l]));
+    return r;
+}
 static inline unsigned __activemask()
 {
     emu::Block &b = emu::blk();

@@ -15,6 +15,7 @@ pytestmark = pytest.mark.gpu
 
 def test_bin_edges_knob_keeps_the_pair_set(golden_dir, monkeypatch):
     """DDCB200_BIN_EDGES only reorders the entries of a row (here: two bins instead of eight): same pairs, forces to rounding."""
+    monkeypatch.setenv("DDCB200_LISTBUILD", "twopass")      # the build that orders rows by distance bin
     sim, ref = _load(golden_dir, "popc_small")
     sim.ddcenergy(1)
     a = sim.getState()
@@ -68,7 +69,7 @@ def test_pruned_rows_are_bitwise_neutral(golden_dir, name, monkeypatch):
     Every skipped entry is outside the cutoff, so 45 steps (two rebuilds) are bitwise the same - with a margin that holds, with
     one so small that beads fall back to their full rows, and with energies evaluated on prune steps and on steps in between."""
     out = {}
-    for tag, prune in (("off", "0"), ("p4", "4"), ("p5wide", "5,1.5"), ("p3tiny", "3,0.05"), ("p2", "2,0.4")):
+    for tag, prune in (("off", "0"), ("p4", "4"), ("p5wide", "5,0.6"), ("p3tiny", "3,0.01"), ("p2", "2,0.1")):
         monkeypatch.setenv("DDCB200_PRUNE", prune)
         sim, _ = _load(golden_dir, name)
         trace = []
