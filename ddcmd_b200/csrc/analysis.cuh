@@ -133,19 +133,19 @@ __device__ __forceinline__ unsigned long long mix64(unsigned long long x)
 }
 
 __global__ void k_pair_hash(int nIon, int nPad, const uint32_t *__restrict__ nbr, const int *__restrict__ count, const int *__restrict__ beadOfSlot,
-                            const uint64_t *__restrict__ gid, const TileWin *__restrict__ tileWin, unsigned long long *__restrict__ out)
+                            const uint64_t *__restrict__ gid, const uint16_t *__restrict__ cum, int farTop, unsigned long long *__restrict__ out)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     unsigned long long h[6] = {0, 0, 0, 0, 0, 0};
     if (i < nIon)
     {
         const int n = count[i];
+        const int nFront = farTop >= 0 ? (int)cum[i] : n;      // rows in two segments (k_nbr_tile): the second one runs down from farTop
         const uint64_t gi = gid[beadOfSlot[i]];
         for (int k = 0; k < n; k++)
         {
-            const uint32_t e = nbr[(size_t)k * nPad + i];
-            int j = (int)(e & 0x07ffffffu);
-            if (tileWin) j = winSlot(tileWin[i / TILE], j);      // rows of windowed tiles hold window offsets
+            const uint32_t e = nbr[(size_t)(k < nFront ? k : farTop - (k - nFront)) * nPad + i];
+            const int j = (int)(e & 0x07ffffffu);
             const uint64_t gj = gid[beadOfSlot[j]];
             if (gi < gj)
             {

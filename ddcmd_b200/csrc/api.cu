@@ -207,9 +207,37 @@ static const PairVariant g_pairVariants[] = {PV(1, 1), PV(2, 1), PV(2, 8), PV(3,
 #undef PV
 static const int g_nPairVariants = (int)(sizeof(g_pairVariants) / sizeof(g_pairVariants[0]));
 
+// margin of the pruned rows as a fraction of deltaR (DDCB200_PRUNE; default 1.4 x every / updateRate: a bead and its fastest
+// neighbour together move about 0.07 deltaR per step at 310 K with deltaR = 4 A)
+static double pruneFracOf(const ddcb200_ctx *c)
+{
+    const double frac = c->pruneMargin > 0.0 ? c->pruneMargin : 1.4 * c->pruneEvery / std::max(1, c->prm.updateRate);
+    return std::min(frac, 1.0);
+}
+
 // everything of ddcb200_create that can fail after the context exists: a failure is unwound by ddcb200_destroy
 static int createInit(ddcb200_ctx *c)
 {
+    if (const char *lb = getenv("DDCB200_LISTBUILD"))
+    {
+        // A/B: "fused" = one pass (k_nbr_build: rows in stencil order), "twopass" = candidate pass + exact pass (rows ordered by distance bin)
+        if (strcmp(lb, "fused") == 0) c->listFused = true;
+        else if (strcmp(lb, "twopass") == 0) c->listFused = false;
+        else return fail(DDCB200_ERR_ARG, "DDCB200_LISTBUILD must be fused or twopass");
+    }
+    if (const char *pe = getenv("DDCB200_PRUNE"))
+    {
+        // pruned rows: <every>[,<margin>] - rewritten every <every> force evaluations from the entries closer than rmax + <margin> x deltaR
+        // (default margin 1.4 x every / updateRate: a bead and its fastest neighbour move about 0.07 deltaR per step at 310 K);
+        // 0 = off.  Results are bitwise those of the full walk whatever the values (pair.cuh)
+        int every = 0;
+        double margin = 0.0;
+        const int got = sscanf(pe, "%d,%lf", &every, &margin);
+        if (got < 1 || every < 0 || every > 1000 || (got == 2 && !(margin > 0.0 && margin <= 1.0)))
+            return fail(DDCB200_ERR_ARG, "DDCB200_PRUNE must be <every>[,<margin as a fraction of deltaR>]");
+        c->pruneEvery = every;
+        c->pruneMargin = got == 2 ? margin : 0.0;
+    }
     if (const char *be = getenv("DDCB200_BIN_EDGES"))
     {
         // tuning knob: the NBINS-1 ascending edges of the row-ordering bins as fractions of deltaR around the cutoff
@@ -229,6 +257,24 @@ static int createInit(ddcb200_ctx *c)
         for (int k = 0; ok && k < NBINS - 1; k++) ok = v[k] > -1.0 && v[k] <= 1.0 && (k == 0 || v[k] >= v[k - 1]);
         if (!ok) return fail(DDCB200_ERR_ARG, "DDCB200_BIN_EDGES needs 7 ascending fractions of deltaR in (-1, 1]");
         for (int k = 0; k < NBINS - 1; k++) c->binFrac[k] = v[k];
+    }
+    if (c->listFused)
+    {
+        // the one-pass build keeps two segments per row: every bin edge is the one edge between them, rmax + 0.3 deltaR (DDCB200_NEAR) -
+        // just beyond the default margin of the pruned rows, so that the evaluation after a build finds all it needs in the first
+        // segment, and independent of it, so that the order of a row (the order of the force sums) does not depend on the pruning
+        double nearFrac = 0.3;
+        if (const char *nf = getenv("DDCB200_NEAR"))
+        {
+            nearFrac = atof(nf);
+            if (!(nearFrac > 0.0 && nearFrac <= 1.0)) return fail(DDCB200_ERR_ARG, "DDCB200_NEAR must be a fraction of deltaR in (0, 1]");
+        }
+        for (int k = 0; k < NBINS - 1; k++) c->binFrac[k] = nearFrac;
+    }
+    {
+        cudaDeviceProp prop;
+        CK(cudaGetDeviceProperties(&prop, c->device));
+        c->smemOptin = prop.sharedMemPerBlockOptin;
     }
     int rc = setupBox(c);
     if (rc != DDCB200_OK) return rc;
@@ -252,39 +298,17 @@ static int createInit(ddcb200_ctx *c)
     CK(cudaMalloc((void **)&c->ddcCounters, 8 * sizeof(int)));
     CK(cudaMalloc((void **)&c->dmax2, 4 * sizeof(unsigned long long)));
     CK(cudaMemset(c->dmax2, 0, 4 * sizeof(unsigned long long)));
-    if (const char *lb = getenv("DDCB200_LISTBUILD"))
-    {
-        // A/B: "fused" = one pass (k_nbr_build: rows in stencil order), "twopass" = candidate pass + exact pass (rows ordered by distance bin)
-        if (strcmp(lb, "fused") == 0) c->listFused = true;
-        else if (strcmp(lb, "twopass") == 0) c->listFused = false;
-        else return fail(DDCB200_ERR_ARG, "DDCB200_LISTBUILD must be fused or twopass");
-    }
-    if (const char *pe = getenv("DDCB200_PRUNE"))
-    {
-        // pruned rows: <every>[,<margin>] - rewritten every <every> force evaluations from the entries closer than rmax + <margin> x deltaR
-        // (default margin 1.4 x every / updateRate: a bead and its fastest neighbour move about 0.07 deltaR per step at 310 K);
-        // 0 = off.  Results are bitwise those of the full walk whatever the values (pair.cuh)
-        int every = 0;
-        double margin = 0.0;
-        const int got = sscanf(pe, "%d,%lf", &every, &margin);
-        if (got < 1 || every < 0 || every > 1000 || (got == 2 && !(margin > 0.0 && margin <= 1.0)))
-            return fail(DDCB200_ERR_ARG, "DDCB200_PRUNE must be <every>[,<margin as a fraction of deltaR>]");
-        c->pruneEvery = every;
-        c->pruneMargin = got == 2 ? margin : 0.0;
-    }
     if (const char *pv = getenv("DDCB200_PAIR"))
     {
         int pf = 0, mb = 0;
-        if (strcmp(pv, "old") == 0) c->pairVariant = -1;
-        else if (strcmp(pv, "win") == 0) c->pairWindows = true;
-        else if (sscanf(pv, "%d,%d", &pf, &mb) == 2)
+        if (sscanf(pv, "%d,%d", &pf, &mb) == 2)
         {
             c->pairVariant = -2;
             for (int v = 0; v < g_nPairVariants; v++)
                 if (g_pairVariants[v].pf == pf && g_pairVariants[v].minb == mb) c->pairVariant = v;
         }
         else c->pairVariant = -2;
-        if (c->pairVariant == -2) return fail(DDCB200_ERR_ARG, "DDCB200_PAIR must be old or one of the built <pf>,<minb> pairs");
+        if (c->pairVariant == -2) return fail(DDCB200_ERR_ARG, "DDCB200_PAIR must be one of the built <pf>,<minb> pairs");
     }
     if (const char *bm = getenv("DDCB200_BONDED"))
     {
@@ -368,7 +392,7 @@ extern "C" void ddcb200_destroy(ddcb200_ctx *c)
     if (c->evBoundary) cudaEventDestroy(c->evBoundary);
     if (c->evPos) cudaEventDestroy(c->evPos);
     if (c->evHalo) cudaEventDestroy(c->evHalo);
-    c->tileGhost.release(); c->tileOrder.release(); c->tileWin.release(); c->cellDmax.release(); c->nbrDmax.release();
+    c->tileGhost.release(); c->tileOrder.release(); c->cellDmax.release(); c->nbrDmax.release();
     if (c->ddcWork) cudaFree(c->ddcWork);
     if (c->ddcWorkInit) cudaFreeHost(c->ddcWorkInit);
     if (c->ddcRow) cudaFree(c->ddcRow);
@@ -406,13 +430,6 @@ extern "C" int ddcb200_sync(ddcb200_ctx *c)
     return DDCB200_OK;
 }
 
-// k_pair3: the tables, then the window ({x, y} and {z, w}, 32 bytes per bead)
-static size_t pair3TableBytes(int ntypes)
-{
-    const size_t nt2 = (size_t)ntypes * ntypes;
-    return nt2 * sizeof(double2) + 256 * sizeof(double) + (nt2 + (nt2 & 1)) * sizeof(double);
-}
-
 static size_t pairSmemBytes(int ntypes) { return (size_t)ntypes * ntypes * (sizeof(double2) + sizeof(double)) + 256 * sizeof(double); }
 
 extern "C" int ddcb200_martiniNonBondParms(ddcb200_ctx *c, int ntypes, const double *eps, const double *sigma, const double *shift)
@@ -436,8 +453,6 @@ extern "C" int ddcb200_martiniNonBondParms(ddcb200_ctx *c, int ntypes, const dou
     CK(cudaGetDeviceProperties(&prop, c->device));
     if (smem + 1024 > prop.sharedMemPerBlockOptin)
         return fail(DDCB200_ERR_CAPACITY, "too many LJ atom types for the shared-memory tables of the pair kernel (about 96 at most)");
-    CK(cudaFuncSetAttribute(k_pair<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    CK(cudaFuncSetAttribute(k_pair<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     for (int v = 0; v < g_nPairVariants; v++)
     {
         for (int m = 0; m < 3; m++)
@@ -445,19 +460,6 @@ extern "C" int ddcb200_martiniNonBondParms(ddcb200_ctx *c, int ntypes, const dou
             CK(cudaFuncSetAttribute(g_pairVariants[v].force[m], cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             CK(cudaFuncSetAttribute(g_pairVariants[v].energy[m], cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         }
-    }
-    {
-        // windowed kernel: two CTAs per SM at the largest window it accepts; smaller windows leave room for more
-        const size_t perCta = prop.sharedMemPerBlockOptin / 2 - 2048;      // static shared memory + the per-CTA reservation
-        const size_t tab = pair3TableBytes(ntypes);
-        c->winMax = perCta > tab + 32 * 256 ? (int)((perCta - tab) / 32) : 0;
-        if (c->winMax > 0)
-        {
-            CK(cudaFuncSetAttribute(k_pair3<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(tab + 32 * (size_t)c->winMax)));
-            CK(cudaFuncSetAttribute(k_pair3<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(tab + 32 * (size_t)c->winMax)));
-        }
-        else
-            c->pairWindows = false;
     }
     c->ntypes = ntypes;
     c->pc.ntypes = ntypes;
@@ -1198,24 +1200,24 @@ extern "C" int ddcb200_constructList(ddcb200_ctx *c)
         CK(c->tileGhost.ensure((size_t)tilesL + 1));
         CK(c->tileOrder.ensure((size_t)tilesL + 1));
     }
-    if (c->pairWindows)
-    {
-        CK(c->tileWin.ensure((size_t)tilesL + 1));
-        LAUNCH(k_tile_window, (tilesL + 3) / 4, 128, 0, st)(nLocal, tilesL, c->cellOfSlot[nxt].p, c->cellStart.p, c->grid, c->winMax, c->tileWin.p);
-        CKL("k_tile_window");
-    }
     for (int attempt = 0; attempt < 4; attempt++)
     {
         CK(c->nbr.ensure((size_t)c->nbrCap * nPad));
         CK(c->nbrRaw.ensure((size_t)c->nbrCap * nPad));
         CK(cudaEventRecord(c->evList[0], st));
-        if (c->listFused && !c->pairWindows)
+        if (c->listFused)
         {
-            LAUNCH(k_nbr_build, tilesL, 128, 0, st)(nLocal, nPad, c->nbrCap, c->pos32.p, c->pos4[nxt].p, c->cellOfSlot[nxt].p, c->cellStart.p, c->box, rl2f,
+            // one pass; rows in two segments around the first bin edge (all the bin edges are that one edge, setupBox)
+            const size_t smemT = (size_t)NBT_BEADS * (size_t)(c->nbrCap | 1) * sizeof(uint32_t);
+            if (smemT + 4096 > c->smemOptin) return fail(DDCB200_ERR_CAPACITY, "neighbor rows too long for the shared-memory staging of the list build");
+            CK(cudaFuncSetAttribute(k_nbr_tile, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemT));
+            if (c->nranks > 1) CK(cudaMemsetAsync(c->tileGhost.p, 0, ((size_t)tilesL + 1) * sizeof(int), st));
+            LAUNCH(k_nbr_tile, (nLocal + NBT_BEADS - 1) / NBT_BEADS, 128, smemT, st)(nLocal, nPad, c->nbrCap, c->pos32.p, c->pos4[nxt].p, c->cellOfSlot[nxt].p,
+                                                   c->cellStart.p, c->box, rl2f, c->box.binEdge2[0],
                                                    c->grid, c->nbr.p, c->nbrCount.p, c->nbrCum.p, c->gidOfBead.p, c->molTypeOfBead.p,
                                                    c->molTypeSingle.p, c->bpairOffset.p, c->bpairKey.p, c->haveExcl ? 1 : 0,
                                                    c->nranks > 1 ? c->tileGhost.p : nullptr);
-            CKL("k_nbr_build");
+            CKL("k_nbr_tile");
         }
         else
         {
@@ -1225,7 +1227,7 @@ extern "C" int ddcb200_constructList(ddcb200_ctx *c)
             LAUNCH(k_nbr_exact, tilesL, 128, 0, st)(nLocal, nPad, c->nbrCap, c->pos4[nxt].p, c->box, c->grid, c->nbrRaw.p, c->nbrRawCount.p,
                                                    c->nbr.p, c->nbrCount.p, c->nbrCum.p, c->gidOfBead.p, c->molTypeOfBead.p,
                                                    c->molTypeSingle.p, c->bpairOffset.p, c->bpairKey.p, c->haveExcl ? 1 : 0,
-                                                   c->nranks > 1 ? c->tileGhost.p : nullptr, c->pairWindows ? c->tileWin.p : nullptr);
+                                                   c->nranks > 1 ? c->tileGhost.p : nullptr);
             CKL("k_nbr_exact");
         }
         CK(cudaEventRecord(c->evList[1], st));
@@ -1298,7 +1300,6 @@ extern "C" int ddcb200_constructList(ddcb200_ctx *c)
     CK(c->cellDmax.ensure(2 * (size_t)c->nCellsBuilt + 2));
     CK(c->nbrDmax.ensure(2 * (size_t)c->nCellsBuilt + 2));
     CK(cudaMemsetAsync(c->cellDmax.p, 0, 2 * (size_t)c->nCellsBuilt * sizeof(unsigned long long), st));
-    c->winMaxTotal = c->gridHost->winMaxTotal;
     return DDCB200_OK;
 }
 
@@ -1307,13 +1308,13 @@ extern "C" int ddcb200_constructList(ddcb200_ctx *c)
 static double pruneArgsOf(const ddcb200_ctx *c, PruneArgs &pr)
 {
     const double deltaR = sqrt(c->box.rlist2) - c->pc.rmax;
-    const double frac = c->pruneMargin > 0.0 ? c->pruneMargin : 1.4 * c->pruneEvery / std::max(1, c->prm.updateRate);
-    const double margin = deltaR * std::min(frac, 1.0);
+    const double margin = deltaR * pruneFracOf(c);
     pr.rows = c->nbrRaw.p;
     pr.count = c->pruneCount.p;
     pr.keep2 = (c->pc.rmax + margin) * (c->pc.rmax + margin) * (1.0 + 1e-12);
     pr.walkLim = 1e300;
     pr.useLim = c->pc.rmax + margin;
+    pr.farTop = c->listFused ? c->nbrCap - 1 : -1;
     return margin;
 }
 
@@ -1414,7 +1415,7 @@ extern "C" int ddcb200_ddcenergy(ddcb200_ctx *c, int withEnergy)
     // ghost position run meanwhile, the others wait for it.  (updateRate = 0: neighborCheck needs the ghosts first)
     bool overlapped = false;
     // pruned rows (pair.cuh): this evaluation writes them if it follows a build or the last prune is pruneEvery evaluations old
-    const bool pruneCfg = c->pruneEvery > 0 && c->prm.updateRate > 0 && c->pairVariant >= 0 && !c->pairWindows && c->pc.listSlack == 0.0;
+    const bool pruneCfg = c->pruneEvery > 0 && c->prm.updateRate > 0 && c->pc.listSlack == 0.0;
     const bool pruneStep = pruneCfg && (!c->listValid || due || !c->pruneValid || c->sincePrune + 1 >= c->pruneEvery);
     if (c->listValid && !due && c->nranks > 1 && c->haloDirty)
     {
@@ -1425,7 +1426,7 @@ extern "C" int ddcb200_ddcenergy(ddcb200_ctx *c, int withEnergy)
             CK(cudaStreamWaitEvent(c->streamH, c->evPos, 0));
             rc = haloExchange(c, c->streamH);
             if (rc) return rc;
-            if (c->walkPerCell && c->walkPerBead && c->pairVariant >= 0 && !c->pairWindows && c->nCellsBuilt > 0)
+            if (c->walkPerCell && c->walkPerBead && c->nCellsBuilt > 0)
             {
                 // the neighbourhood bounds that include the ghosts' displacements, for the rows that wait for the halo.  (The
                 // local parts of cellDmax are complete: this stream waited for the integrator's event.)
@@ -1457,7 +1458,7 @@ extern "C" int ddcb200_ddcenergy(ddcb200_ctx *c, int withEnergy)
     const int tiles = (nLocal + TILE - 1) / TILE;
     if (withEnergy) CK(cudaMemsetAsync(c->acc, 0, ACC_N * sizeof(double), st));
     int pruneMode = 0;
-    PruneArgs pr = {nullptr, nullptr, 0.0, 0.0, 0.0};
+    PruneArgs pr = {nullptr, nullptr, 0.0, 0.0, 0.0, c->listFused ? c->nbrCap - 1 : -1};
     PairConst pcl = c->pc;
     if (pruneCfg)
     {
@@ -1491,20 +1492,6 @@ extern "C" int ddcb200_ddcenergy(ddcb200_ctx *c, int withEnergy)
             if (nTiles <= 0) return DDCB200_OK;
             cudaStream_t st = pst;
             ProfScope ps(c, pruneMode == 1 ? PROF_PAIR_PRUNE : PROF_PAIR, st);
-            if (c->pairWindows)
-            {
-                const int wcap = (c->winMaxTotal + 7) & ~7;
-                const size_t smem3 = pair3TableBytes(c->ntypes) + 32 * (size_t)wcap;
-                if (withEnergy)
-                    LAUNCH(k_pair3<true>, nTiles, PAIR3_THREADS, smem3, st)(nLocal, nPad, order, base, c->pos4[cur].p, c->nbr.p, c->nbrCum.p, c->dmax2, withGhosts,
-                                                                        disp, c->tileWin.p, wcap, c->ljTab.p, c->shiftTab.p, c->qTab.p, c->pc, c->frc[0].p,
-                                                                        c->frc[1].p, c->frc[2].p, c->pairPartial.p);
-                else
-                    LAUNCH(k_pair3<false>, nTiles, PAIR3_THREADS, smem3, st)(nLocal, nPad, order, base, c->pos4[cur].p, c->nbr.p, c->nbrCum.p, c->dmax2, withGhosts,
-                                                                         disp, c->tileWin.p, wcap, c->ljTab.p, c->shiftTab.p, c->qTab.p, c->pc, c->frc[0].p,
-                                                                         c->frc[1].p, c->frc[2].p, c->pairPartial.p);
-            }
-            else if (c->pairVariant >= 0)
             {
                 const PairVariant &pv = g_pairVariants[c->pairVariant];
                 const PairKernel kern = withEnergy ? pv.energy[pruneMode] : pv.force[pruneMode];
@@ -1513,18 +1500,10 @@ extern "C" int ddcb200_ddcenergy(ddcb200_ctx *c, int withEnergy)
                                                      c->shiftTab.p, c->qTab.p, pcl, c->frc[0].p, c->frc[1].p, c->frc[2].p, c->pairPartial.p,
                                                      cellWalk ? c->nbrDmax.p + (withGhosts ? c->nCellsBuilt : 0) : nullptr, c->cellOfSlot[cur].p, pr);
             }
-            else if (withEnergy)
-                LAUNCH(k_pair<true>, nTiles, TILE, smem, st)(nLocal, nPad, order, base, c->pos4[cur].p, c->nbr.p, c->nbrCum.p, c->dmax2, withGhosts, disp,
-                                                         c->ljTab.p, c->shiftTab.p, c->qTab.p, c->pc, c->frc[0].p, c->frc[1].p, c->frc[2].p,
-                                                         c->pairPartial.p);
-            else
-                LAUNCH(k_pair<false>, nTiles, TILE, smem, st)(nLocal, nPad, order, base, c->pos4[cur].p, c->nbr.p, c->nbrCum.p, c->dmax2, withGhosts, disp,
-                                                          c->ljTab.p, c->shiftTab.p, c->qTab.p, c->pc, c->frc[0].p, c->frc[1].p, c->frc[2].p,
-                                                          c->pairPartial.p);
             CKL("k_pair");
             return DDCB200_OK;
         };
-        const bool cellWalk = c->walkPerCell && c->walkPerBead && c->pairVariant >= 0 && !c->pairWindows && c->nCellsBuilt > 0;
+        const bool cellWalk = c->walkPerCell && c->walkPerBead && c->nCellsBuilt > 0;
         if (cellWalk)
         {
             // the displacement bound of every cell's neighbourhood, from the local beads (complete since the integrator ran)
@@ -2127,25 +2106,28 @@ extern "C" int64_t ddcb200_getPairs(ddcb200_ctx *c, int64_t capacity, int *beadI
             np++;
         }
     };
+    // rows of the one-pass build are two segments: the first cum[0] entries from the front, the others from the end of the row's
+    // allocation backwards (k_nbr_tile); rows of the two-pass build run forward
+    const int farTop = c->listFused ? c->nbrCap - 1 : -1;
     int maxc = 0;
     for (int i = 0; i < n; i++) maxc = std::max(maxc, cnt[i]);
-    std::vector<uint32_t> rows((size_t)maxc * nPad);
+    const size_t nrows = farTop >= 0 ? (size_t)c->nbrCap : (size_t)maxc;
+    std::vector<uint32_t> rows(nrows * nPad);
+    std::vector<uint16_t> nearN;
     if (maxc && cudaMemcpy(rows.data(), c->nbr.p, rows.size() * sizeof(uint32_t), cudaMemcpyDeviceToHost) != cudaSuccess)
         return fail(DDCB200_ERR_CUDA, "getPairs copy");
-    std::vector<TileWin> win;
-    if (c->pairWindows)
+    if (farTop >= 0)
     {
-        // rows of windowed tiles hold window offsets: turn them back into slots
-        win.resize((size_t)((n + TILE - 1) / TILE));
-        if (cudaMemcpy(win.data(), c->tileWin.p, win.size() * sizeof(TileWin), cudaMemcpyDeviceToHost) != cudaSuccess)
+        nearN.resize((size_t)n);
+        if (cudaMemcpy(nearN.data(), c->nbrCum.p, (size_t)n * sizeof(uint16_t), cudaMemcpyDeviceToHost) != cudaSuccess)
             return fail(DDCB200_ERR_CUDA, "getPairs copy");
     }
     for (int i = 0; i < n; i++)
         for (int k = 0; k < cnt[i]; k++)
         {
-            const uint32_t e = rows[(size_t)k * nPad + i];
-            const int idx = (int)(e & 0x07ffffffu);
-            emit(i, win.empty() ? idx : winSlot(win[(size_t)(i / TILE)], idx), (e & EXCL_BIT) != 0u);
+            const int at = (farTop >= 0 && k >= (int)nearN[(size_t)i]) ? farTop - (k - (int)nearN[(size_t)i]) : k;
+            const uint32_t e = rows[(size_t)at * nPad + i];
+            emit(i, (int)(e & 0x07ffffffu), (e & EXCL_BIT) != 0u);
         }
     return np;
 }
@@ -2163,7 +2145,7 @@ extern "C" int ddcb200_pairSetHash(ddcb200_ctx *c, uint64_t out[6])
     CK(sc.h.ensure(8));
     CK(cudaMemsetAsync(sc.h.p, 0, 8 * sizeof(unsigned long long), c->stream));
     LAUNCH(k_pair_hash, (int)((c->nLocal + 255) / 256), 256, 0, c->stream)((int)c->nLocal, (int)c->nPad, c->nbr.p, c->nbrCount.p, c->beadOfSlot[c->cur].p,
-                                                                     c->gidOfBead.p, c->pairWindows ? c->tileWin.p : nullptr, sc.h.p);
+                                                                     c->gidOfBead.p, c->nbrCum.p, c->listFused ? c->nbrCap - 1 : -1, sc.h.p);
     CKL("k_pair_hash");
     CK(cudaMemcpyAsync(out, sc.h.p, 6 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, c->stream));
     CK(cudaStreamSynchronize(c->stream));

@@ -131,8 +131,6 @@ __global__ void k_grid_setup(const double *__restrict__ partial, int nblocks, in
     g->maxCount = 0;
     g->maxRaw = 0;
     g->totalEntries = 0ull;
-    g->winMaxTotal = 0;
-    g->winGlobal = 0;
 }
 
 __device__ __forceinline__ int spread2(int v) { return (v & 1) | ((v & 2) << 2); }   // bits 0,1 -> bits 0,3
@@ -337,125 +335,6 @@ k_nbr_filter(int nIon, int nPad, const float4 *__restrict__ pos32, const int *__
     }
 }
 
-// ---- 8c. tile windows (windowed pair kernel only) -----------------------------------------------------------------------------
-// One warp per tile: the distinct cells of the tile's slots, their stencil cells (the cells k_nbr_filter walks), sorted and
-// merged into runs of consecutive slots.  A window that needs more than WIN_MAXRUNS runs or more than wmax beads is left
-// empty: that tile keeps slot entries and gathers from global memory.
-#define WIN_IDS 1024
-__global__ void __launch_bounds__(128)
-k_tile_window(int nIon, int nTiles, const int *__restrict__ cellOfSlot, const int *__restrict__ cellStart, GridDev *gp, int wmax,
-              TileWin *__restrict__ out)
-{
-    __shared__ int sIds[4][WIN_IDS];
-    __shared__ int sDc[4][32];
-    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-    const int t = blockIdx.x * 4 + wib;
-    if (t >= nTiles) return;
-    int *ids = sIds[wib], *dc = sDc[wib];
-    const int nx = gp->n[0], ny = gp->n[1], nz = gp->n[2];
-    const int lx = nx >= 3 ? -1 : 0, hx = nx >= 2 ? 1 : 0;
-    const int ly = ny >= 3 ? -1 : 0, hy = ny >= 2 ? 1 : 0;
-    const int lz = nz >= 3 ? -1 : 0, hz = nz >= 2 ? 1 : 0;
-    const unsigned lt = (1u << lane) - 1u;
-    // distinct cells of the tile (slots are sorted by cell)
-    int nCells = 0, last = -2;
-    for (int m = 0; m < TILE / 32; m++)
-    {
-        const int s = t * TILE + m * 32 + lane;
-        const int c = s < nIon ? cellOfSlot[s] : -1;
-        int prev = __shfl_up_sync(0xffffffffu, c, 1);
-        if (lane == 0) prev = last;
-        const bool isNew = c >= 0 && c != prev;
-        const unsigned mk = __ballot_sync(0xffffffffu, isNew);
-        const int p = nCells + __popc(mk & lt);
-        if (isNew && p < 32) dc[p] = c;
-        nCells += __popc(mk);
-        last = __shfl_sync(0xffffffffu, c, 31);
-    }
-    __syncwarp();
-    bool fits = nCells <= 16;       // 16 cells x 27 stencil cells x 2 parts <= WIN_IDS
-    int nIds = 0;
-    if (fits)
-    {
-        for (int d = 0; d < nCells; d++)
-        {
-            const int c = dc[d];
-            const int cx = c % nx, cy = (c / nx) % ny, cz = c / (nx * ny);
-            const int dx = lane % 3 - 1, dy = (lane / 3) % 3 - 1, dz = lane / 9 - 1;
-            const bool ok = lane < 27 && dx >= lx && dx <= hx && dy >= ly && dy <= hy && dz >= lz && dz <= hz;
-            int ax = cx + dx, ay = cy + dy, az = cz + dz;
-            if (ax < 0) ax += nx; else if (ax >= nx) ax -= nx;
-            if (ay < 0) ay += ny; else if (ay >= ny) ay -= ny;
-            if (az < 0) az += nz; else if (az >= nz) az -= nz;
-            const unsigned mk = __ballot_sync(0xffffffffu, ok);
-            // the cell's local beads and (several ranks) its ghosts: two slot ranges
-            if (ok)
-            {
-                ids[nIds + 2 * __popc(mk & lt)] = ax + nx * (ay + ny * az);
-                ids[nIds + 2 * __popc(mk & lt) + 1] = ax + nx * (ay + ny * az) + nx * ny * nz;
-            }
-            nIds += 2 * __popc(mk);
-        }
-        int np2 = 32;
-        while (np2 < nIds) np2 <<= 1;
-        for (int q = nIds + lane; q < np2; q += 32) ids[q] = 0x7fffffff;
-        __syncwarp();
-        // bitonic sort, ascending
-        for (int k = 2; k <= np2; k <<= 1)
-            for (int j = k >> 1; j > 0; j >>= 1)
-            {
-                for (int q = lane; q < np2; q += 32)
-                {
-                    const int r = q ^ j;
-                    if (r > q)
-                    {
-                        const int a = ids[q], b = ids[r];
-                        const bool up = (q & k) == 0;
-                        if ((a > b) == up) { ids[q] = b; ids[r] = a; }
-                    }
-                }
-                __syncwarp();
-            }
-    }
-    if (lane == 0)
-    {
-        TileWin w;
-        w.nRuns = 0;
-        w.total = 0;
-        w.pad = 0;
-        int prevC = -1;
-        for (int q = 0; q < nIds && fits; q++)
-        {
-            const int c = ids[q];
-            if (c == prevC) continue;
-            prevC = c;
-            const int lo = cellStart[c], n = cellStart[c + 1] - lo;
-            if (n == 0) continue;
-            if (w.nRuns > 0 && w.lo[w.nRuns - 1] + (w.total - w.off[w.nRuns - 1]) == lo) w.total += n;     // continues the last run
-            else if (w.nRuns == WIN_MAXRUNS) fits = false;
-            else
-            {
-                w.lo[w.nRuns] = lo;
-                w.off[w.nRuns] = w.total;
-                w.nRuns++;
-                w.total += n;
-            }
-            if (w.total > wmax) fits = false;
-        }
-        if (!fits)
-        {
-            w.nRuns = 0;
-            w.total = 0;
-            atomicAdd(&gp->winGlobal, 1);
-        }
-        for (int r = w.nRuns; r < WIN_MAXRUNS; r++) { w.lo[r] = 0x7fffffff; w.off[r] = w.total; }
-        w.off[WIN_MAXRUNS] = w.total;
-        if (w.nRuns > 0) w.off[w.nRuns] = w.total;
-        out[t] = w;
-        atomicMax(&gp->winMaxTotal, w.total);
-    }
-}
-
 // ---- 9. exact pass: pairlist1's test bit for bit, reOrgPairs' pruning, distance-bin order ----
 __device__ __forceinline__ bool isPruned(int bi, int bj, const uint64_t *__restrict__ gid,
                                          const int *__restrict__ molTypeOfBead, const int *__restrict__ molTypeSingle,
@@ -499,16 +378,8 @@ __global__ void __launch_bounds__(128)
 k_nbr_exact(int nIon, int nPad, int cap, const double4 *__restrict__ pos, BoxConst b, GridDev *gp, uint32_t *__restrict__ raw,
             const int *__restrict__ rawCount, uint32_t *__restrict__ out, int *__restrict__ count, uint16_t *__restrict__ cum,
             const uint64_t *__restrict__ gid, const int *__restrict__ molTypeOfBead, const int *__restrict__ molTypeSingle,
-            const int *__restrict__ bpairOffset, const uint32_t *__restrict__ bpairKey, int haveExcl, int *__restrict__ tileGhost,
-            const TileWin *__restrict__ tileWin)
+            const int *__restrict__ bpairOffset, const uint32_t *__restrict__ bpairKey, int haveExcl, int *__restrict__ tileGhost)
 {
-    // windowed pair kernel: this block is one tile; its rows hold offsets into the tile's window instead of slots
-    __shared__ TileWin sWin;
-    if (tileWin)
-    {
-        for (int k = threadIdx.x; k < (int)(sizeof(TileWin) / sizeof(int)); k += blockDim.x) ((int *)&sWin)[k] = ((const int *)(tileWin + blockIdx.x))[k];
-        __syncthreads();
-    }
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     int total = 0;
     bool ghostEntry = false;      // some entry of this row is a ghost slot (several ranks): the row waits for the halo
@@ -572,19 +443,7 @@ k_nbr_exact(int nIon, int nPad, int cap, const double4 *__restrict__ pos, BoxCon
             if (e == RAW_REJECT) continue;
             const int bin = (e >> 27) & 7;
             const int dst = sBin[bin][threadIdx.x]++;
-            uint32_t idx = e & 0x07ffffffu;
-            if (tileWin && sWin.nRuns > 0)
-            {
-                // the run that holds slot idx (runs ascend): binary search over at most WIN_MAXRUNS first slots
-                int lo = 0, hi = sWin.nRuns - 1;
-                while (lo < hi)
-                {
-                    const int mid = (lo + hi + 1) >> 1;
-                    if (sWin.lo[mid] <= (int)idx) lo = mid;
-                    else hi = mid - 1;
-                }
-                idx = (uint32_t)(sWin.off[lo] + ((int)idx - sWin.lo[lo]));
-            }
+            const uint32_t idx = e & 0x07ffffffu;
             out[(size_t)dst * nPad + i] = idx | (e & EXCL_BIT);
         }
         count[i] = total;
@@ -611,189 +470,227 @@ k_nbr_exact(int nIon, int nPad, int cap, const double4 *__restrict__ pos, BoxCon
     }
 }
 
-// ---- 9b. the list build in one pass ---------------------------------------------------------------------------------------------
-// One thread per local slot.  The fp32 scan of the stencil (the conservative filter of k_nbr_filter; x-adjacent cells are one run
-// of consecutive slots, so a bead scans 9 long runs instead of 27 short ones) pushes its survivors on a per-lane queue in shared
-// memory; the warp pops the queues together - one candidate per lane per round, while every lane has one or a queue fills up - and
-// takes pairlist1's decision in fp64 exactly as k_nbr_exact does (same arithmetic, bit for bit the same membership).  Compacting
-// through the queues keeps the expensive exact block converged (16 % of the scanned candidates survive: without the queues nearly
-// every scan iteration would enter it with a handful of lanes), and because the lanes pop in step their rows grow in step, so the
-// transposed row stores of a warp fall into one or two lines.  No candidate buffer, no second sweep; rows are in stencil order (no
-// distance bins: the pruned rows of the pair walk do that job, pair.cuh).
-#define NBQ 32          // queue slots per lane
-#define NBQ_HEAD 12     // a lane's queue this close to full makes the warp pop
+// ---- 9b. the list build in one pass: one warp per bead, lanes over candidates ----------------------------------------------------
+// A block builds the rows of 32 consecutive local slots (the beads of one warp of the pair kernel); each of its four warps takes
+// eight of them, one after the other.  For its bead the warp scans the stencil 32 candidates at a time - x-adjacent cells are one
+// run of consecutive slots, so the loads of the fp32 positions are coalesced - with the conservative fp32 filter of k_nbr_filter;
+// the survivors are compacted with a ballot into a small queue, and whenever 32 are queued the lanes take pairlist1's decision in
+// fp64 for one candidate each, with exactly the arithmetic of k_nbr_exact (bit for bit the same membership).  Entries listed
+// closer than nearEdge are appended to the front of the bead's row, the others from the end of the row's allocation backwards:
+// two segments in stencil order, no sort.  The pair walk visits the front segment first - nearly all of its entries are inside the
+// cutoff, and right after a build it is all the pruned rows need - and the far segment behind it is nearly all outside, so the
+// lanes of a warp agree on whether the force block runs.  The block's rows are staged in shared memory and written out
+// transposed, one 128-byte line per row position.  An earlier version with one thread per bead and per-lane queues ran 1.5 G warp
+// instructions and 2.1 ms against 2.8 ms for the two passes (profiles/r02q_k_nbr_build_ncu_full.txt); this one has no divergence
+// in the scan and no scattered stores.
+#define NBT_BEADS 32      // beads per block
+#define NBT_QCAP 64       // queue slots per warp
 __global__ void __launch_bounds__(128)
-k_nbr_build(int nIon, int nPad, int cap, const float4 *__restrict__ pos32, const double4 *__restrict__ pos, const int *__restrict__ cellOf,
-            const int *__restrict__ cellStart, BoxConst b, float rl2f, GridDev *gp, uint32_t *__restrict__ out, int *__restrict__ count,
-            uint16_t *__restrict__ cum, const uint64_t *__restrict__ gid, const int *__restrict__ molTypeOfBead,
-            const int *__restrict__ molTypeSingle, const int *__restrict__ bpairOffset, const uint32_t *__restrict__ bpairKey, int haveExcl,
-            int *__restrict__ tileGhost)
+k_nbr_tile(int nIon, int nPad, int cap, const float4 *__restrict__ pos32, const double4 *__restrict__ pos, const int *__restrict__ cellOf,
+           const int *__restrict__ cellStart, BoxConst b, float rl2f, double near2, GridDev *gp, uint32_t *__restrict__ out,
+           int *__restrict__ count, uint16_t *__restrict__ cum, const uint64_t *__restrict__ gid, const int *__restrict__ molTypeOfBead,
+           const int *__restrict__ molTypeSingle, const int *__restrict__ bpairOffset, const uint32_t *__restrict__ bpairKey, int haveExcl,
+           int *__restrict__ tileGhost)
 {
-    __shared__ uint32_t sQ[4][NBQ][32];
+    EXTERN_SHARED(uint32_t, sRow);               // [NBT_BEADS][rs] the rows of this block (odd stride: the transposed read-out hits 32 banks)
+    const int rs = cap | 1;
+    __shared__ uint32_t sQ[4][NBT_QCAP];
+    __shared__ int sNear[NBT_BEADS], sFar[NBT_BEADS];
+    __shared__ int sGhost;
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    const float4 pi = pos32[i < nIon ? i : 0];
-    const bool act = i < nIon && pi.w == 0.0f;
-    const double4 pd = pos[i < nIon ? i : 0];
-    const uint64_t wi = (uint64_t)__double_as_longlong(pd.w);
-    int head = 0, tail = 0, total = 0;
-    bool ghostEntry = false;      // some entry of this row is a ghost slot (several ranks): the row waits for the halo
-
-    // one queued candidate of this lane: pairlist1's test (src/pairlist.c:280-288), reOrgPairs' pruning flag, the row store
-    auto popOne = [&]() {
-        const uint32_t j = sQ[wib][head & (NBQ - 1)][lane];
-        head++;
-        const double4 pj = ldPos256(pos + j);
-        double x = __dadd_rn(pd.x, -pj.x), y = __dadd_rn(pd.y, -pj.y), z = __dadd_rn(pd.z, -pj.z);
-        double r2 = exactR2(x, y, z);
-        if (r2 > b.R2cut)
-        {
-            wrapOnce(x, y, z, b);
-            r2 = exactR2(x, y, z);
-        }
-        if (r2 < b.rlist2)
-        {
-            uint32_t ent = j;
-            const uint64_t wj = (uint64_t)__double_as_longlong(pj.w);
-            ghostEntry |= (wj >> 63) != 0ull;
-            if (haveExcl)
-            {
-                // same molecule? bits 16..31 of w carry the low 16 bits of gid>>32: cheap reject before the gid gathers
-                if (((wi ^ wj) & 0xffff0000ull) == 0ull &&
-                    isPruned((int)((wi >> 32) & 0x7fffffffull), (int)((wj >> 32) & 0x7fffffffull), gid, molTypeOfBead, molTypeSingle, bpairOffset, bpairKey))
-                    ent |= EXCL_BIT;
-            }
-            if (total < cap) out[(size_t)total * nPad + i] = ent;
-            total++;
-        }
-    };
-    // mode 0: pop while every scanning lane has a candidate or some queue is nearly full; 1: one round (a lane is blocked on a
-    // full queue); 2: until every queue is empty.  Warp-uniform: every lane of the warp calls it at the same places.
-    auto drain = [&](int mode) {
-        for (;;)
-        {
-            const int q = tail - head;
-            const int mx = __reduce_max_sync(0xffffffffu, q);
-            if (mx == 0) break;
-            const int mn = __reduce_min_sync(0xffffffffu, act ? q : 0x7fffffff);
-            if (mode == 0 && !(mn >= 1 || mx > NBQ - NBQ_HEAD)) break;
-            if (q > 0) popOne();
-            if (mode == 1) break;
-        }
-    };
-
+    const unsigned ltMask = (1u << lane) - 1u;
+    const int base = blockIdx.x * NBT_BEADS;
+    if (threadIdx.x == 0) sGhost = 0;
+    if (threadIdx.x < NBT_BEADS) { sNear[threadIdx.x] = 0; sFar[threadIdx.x] = 0; }
+    __syncthreads();
     const int nx = gp->n[0], ny = gp->n[1], nz = gp->n[2], ncell = nx * ny * nz;
     const float Lx = (float)b.hxx, Ly = (float)b.hyy, Lz = (float)b.hzz;
     const float hx2 = 0.5f * Lx, hy2 = 0.5f * Ly, hz2 = 0.5f * Lz;
     // with >= 3 cells along an axis a wrapped stencil cell has ONE possible image: shift it;
     // with fewer the stencil is deduplicated and each pair takes its nearest image
     const bool px = nx < 3, py = ny < 3, pz = nz < 3;
-    const int c = act ? cellOf[i] : 0;
-    const int cx = c % nx, cy = (c / nx) % ny, cz = c / (nx * ny);
     const int ly = ny >= 3 ? -1 : 0, hy = ny >= 2 ? 1 : 0;
     const int lz = nz >= 3 ? -1 : 0, hz = nz >= 2 ? 1 : 0;
-    // runs along x (uniform count for the warp): nx >= 3: the run of the cells cx-1 .. cx+1 clipped to the row + the one cell
-    // that wraps around (empty for most beads); nx < 3: the one or two cells of the row, pairs take their nearest image
-    const int nseg = 2;
-    for (int dz = lz; dz <= hz; dz++)
+    int maxTotal = 0;
+    bool ghostEntry = false;
+    for (int q = 0; q < NBT_BEADS / 4; q++)
     {
-        int az = cz + dz;
-        float sz = 0.0f;
-        if (az < 0) { az += nz; sz = -Lz; }
-        else if (az >= nz) { az -= nz; sz = Lz; }
-        const float bz = pz ? pi.z : pi.z - sz;
-        for (int dy = ly; dy <= hy; dy++)
-        {
-            int ay = cy + dy;
-            float sy = 0.0f;
-            if (ay < 0) { ay += ny; sy = -Ly; }
-            else if (ay >= ny) { ay -= ny; sy = Ly; }
-            const float by = py ? pi.y : pi.y - sy;
-            const int rowBase = nx * (ay + ny * az);
-            for (int sg = 0; sg < nseg; sg++)
+        const int bt = wib * (NBT_BEADS / 4) + q;      // bead of the block
+        const int i = base + bt;
+        if (i >= nIon) break;
+        const float4 pi = pos32[i];
+        if (pi.w != 0.0f) continue;                    // a ghost slot owns no row (local slots come first: never happens below nLocal)
+        const double4 pd = pos[i];
+        const uint64_t wi = (uint64_t)__double_as_longlong(pd.w);
+        uint32_t *row = sRow + (size_t)bt * rs;
+        int nNear = 0, nFar = 0, qn = 0;
+        // pairlist1's test (src/pairlist.c:280-288) and reOrgPairs' pruning flag for the first `take` queued candidates, one per lane
+        auto exactBatch = [&](int take) {
+            const bool has = lane < take;
+            const uint32_t j = has ? sQ[wib][lane] : 0u;
+            bool in = false, isNear = false;
+            uint32_t ent = j;
+            if (has)
             {
-                int c0, c1;      // cells c0 .. c1 of the row; c1 < c0: nothing
-                float sx = 0.0f;
-                if (!px)
+                const double4 pj = ldPos256(pos + j);
+                double x = __dadd_rn(pd.x, -pj.x), y = __dadd_rn(pd.y, -pj.y), z = __dadd_rn(pd.z, -pj.z);
+                double r2 = exactR2(x, y, z);
+                if (r2 > b.R2cut)
                 {
-                    if (sg == 0) { c0 = max(cx - 1, 0); c1 = min(cx + 1, nx - 1); }
-                    else if (cx == 0) { c0 = c1 = nx - 1; sx = -Lx; }
-                    else if (cx == nx - 1) { c0 = c1 = 0; sx = Lx; }
-                    else { c0 = 1; c1 = 0; }
+                    wrapOnce(x, y, z, b);
+                    r2 = exactR2(x, y, z);
                 }
-                else
+                if (r2 < b.rlist2)
                 {
-                    // one or two cells: sg = 0 the bead's own, sg = 1 the other one (nx = 2)
-                    if (sg == 0) c0 = c1 = cx;
-                    else if (nx == 2) c0 = c1 = 1 - cx;
-                    else { c0 = 1; c1 = 0; }
-                }
-                const float bx = px ? pi.x : pi.x - sx;
-                // the cells' local beads, then (several ranks) their ghosts
-                for (int part = 0; part < 2; part++)
-                {
-                    int j = 0, hi = 0;
-                    if (act && c1 >= c0)
+                    in = true;
+                    isNear = r2 < near2;
+                    const uint64_t wj = (uint64_t)__double_as_longlong(pj.w);
+                    ghostEntry |= (wj >> 63) != 0ull;
+                    if (haveExcl)
                     {
-                        j = cellStart[part * ncell + rowBase + c0];
-                        hi = cellStart[part * ncell + rowBase + c1 + 1];
+                        // same molecule? bits 16..31 of w carry the low 16 bits of gid>>32: cheap reject before the gid gathers
+                        if (((wi ^ wj) & 0xffff0000ull) == 0ull &&
+                            isPruned((int)((wi >> 32) & 0x7fffffffull), (int)((wj >> 32) & 0x7fffffffull), gid, molTypeOfBead, molTypeSingle, bpairOffset, bpairKey))
+                            ent |= EXCL_BIT;
                     }
-                    for (;;)
+                }
+            }
+            const unsigned mNear = __ballot_sync(0xffffffffu, in && isNear), mFar = __ballot_sync(0xffffffffu, in && !isNear);
+            const int cN = __popc(mNear), cF = __popc(mFar);
+            if (nNear + nFar + cN + cF <= cap)
+            {
+                if (in && isNear) row[nNear + __popc(mNear & ltMask)] = ent;
+                if (in && !isNear) row[cap - 1 - (nFar + __popc(mFar & ltMask))] = ent;
+            }
+            nNear += cN;
+            nFar += cF;
+            // the candidates behind the batch move to the front of the queue
+            __syncwarp();
+            const uint32_t keep = (lane + take < qn) ? sQ[wib][lane + take] : 0u;
+            __syncwarp();
+            if (lane + take < qn) sQ[wib][lane] = keep;
+            qn -= take;
+            __syncwarp();
+        };
+        const int c = cellOf[i];
+        const int cx = c % nx, cy = (c / nx) % ny, cz = c / (nx * ny);
+        for (int dz = lz; dz <= hz; dz++)
+        {
+            int az = cz + dz;
+            float sz = 0.0f;
+            if (az < 0) { az += nz; sz = -Lz; }
+            else if (az >= nz) { az -= nz; sz = Lz; }
+            const float bz = pz ? pi.z : pi.z - sz;
+            for (int dy = ly; dy <= hy; dy++)
+            {
+                int ay = cy + dy;
+                float sy = 0.0f;
+                if (ay < 0) { ay += ny; sy = -Ly; }
+                else if (ay >= ny) { ay -= ny; sy = Ly; }
+                const float by = py ? pi.y : pi.y - sy;
+                const int rowBase = nx * (ay + ny * az);
+                // runs along x: nx >= 3: the cells cx-1 .. cx+1 clipped to the row, then the one cell that wraps around (most beads
+                // have none); nx < 3: the bead's own cell, then the other one (nx = 2), pairs take their nearest image
+                for (int sg = 0; sg < 2; sg++)
+                {
+                    int c0, c1;      // cells c0 .. c1 of the row; c1 < c0: nothing
+                    float sx = 0.0f;
+                    if (!px)
                     {
-                        // scan until the end of the run or until this lane's queue is full
-                        const int stop = min(hi, j + (NBQ - (tail - head)));
-                        for (; j < stop; j++)
+                        if (sg == 0) { c0 = max(cx - 1, 0); c1 = min(cx + 1, nx - 1); }
+                        else if (cx == 0) { c0 = c1 = nx - 1; sx = -Lx; }
+                        else if (cx == nx - 1) { c0 = c1 = 0; sx = Lx; }
+                        else { c0 = 1; c1 = 0; }
+                    }
+                    else
+                    {
+                        if (sg == 0) c0 = c1 = cx;
+                        else if (nx == 2) c0 = c1 = 1 - cx;
+                        else { c0 = 1; c1 = 0; }
+                    }
+                    if (c1 < c0) continue;
+                    const float bx = px ? pi.x : pi.x - sx;
+                    // the cells' local beads, then (several ranks) their ghosts
+                    for (int part = 0; part < 2; part++)
+                    {
+                        const int lo = cellStart[part * ncell + rowBase + c0], hi = cellStart[part * ncell + rowBase + c1 + 1];
+                        for (int j0 = lo; j0 < hi; j0 += 32)
                         {
-                            const float4 pj = pos32[j];
-                            float x = bx - pj.x, y = by - pj.y, z = bz - pj.z;
-                            if (px) { if (x > hx2) x -= Lx; if (x < -hx2) x += Lx; }
-                            if (py) { if (y > hy2) y -= Ly; if (y < -hy2) y += Ly; }
-                            if (pz) { if (z > hz2) z -= Lz; if (z < -hz2) z += Lz; }
-                            const float r2 = x * x + y * y + z * z;
-                            if (r2 < rl2f && j != i)
+                            const int j = j0 + lane;
+                            bool pass = false;
+                            if (j < hi)
                             {
-                                sQ[wib][tail & (NBQ - 1)][lane] = (uint32_t)j;
-                                tail++;
+                                const float4 pj = pos32[j];
+                                float x = bx - pj.x, y = by - pj.y, z = bz - pj.z;
+                                if (px) { if (x > hx2) x -= Lx; if (x < -hx2) x += Lx; }
+                                if (py) { if (y > hy2) y -= Ly; if (y < -hy2) y += Ly; }
+                                if (pz) { if (z > hz2) z -= Lz; if (z < -hz2) z += Lz; }
+                                pass = (x * x + y * y + z * z < rl2f) && j != i;
                             }
+                            const unsigned m = __ballot_sync(0xffffffffu, pass);
+                            if (pass) sQ[wib][qn + __popc(m & ltMask)] = (uint32_t)j;
+                            qn += __popc(m);
+                            __syncwarp();
+                            if (qn >= 32) exactBatch(32);
                         }
-                        const bool blocked = j < hi;
-                        if (!__any_sync(0xffffffffu, blocked)) break;
-                        drain(1);
                     }
-                    drain(0);
                 }
             }
         }
+        if (qn > 0) exactBatch(qn);
+        const int total = nNear + nFar;
+        maxTotal = max(maxTotal, total);
+        if (lane == 0)
+        {
+            sNear[bt] = total <= cap ? nNear : 0;
+            sFar[bt] = total <= cap ? nFar : 0;
+        }
     }
-    drain(2);
-    if (act)
+    __syncthreads();
+    // the rows go out transposed: row position k of the block's 32 beads is one line.  Front segments from position 0 up, far
+    // segments from cap - 1 down; cum[0] = front length, cum[1..] = the whole row (the pair walk's two "bins")
     {
-        const uint16_t t16 = (uint16_t)min(total, cap);
+        const int bt = lane, i = base + bt;
+        const int nNear = sNear[bt], nFar = sFar[bt];
+        int mxN = nNear, mxF = nFar;
+        for (int o = 16; o > 0; o >>= 1)
+        {
+            mxN = max(mxN, __shfl_xor_sync(0xffffffffu, mxN, o));
+            mxF = max(mxF, __shfl_xor_sync(0xffffffffu, mxF, o));
+        }
+        const uint32_t *row = sRow + (size_t)bt * rs;
+        for (int k = wib; k < mxN; k += 4)
+            if (k < nNear) out[(size_t)k * nPad + i] = row[k];
+        for (int f = wib; f < mxF; f += 4)
+            if (f < nFar) out[(size_t)(cap - 1 - f) * nPad + i] = row[cap - 1 - f];
+        if (wib == 0 && i < nIon)
+        {
+            const int total = nNear + nFar;
+            cum[i] = (uint16_t)nNear;
 #pragma unroll
-        for (int bnd = 0; bnd < NBINS; bnd++) cum[(size_t)bnd * nPad + i] = t16;      // no distance bins: every boundary is the row's end
-        count[i] = min(total, cap);
+            for (int bnd = 1; bnd < NBINS; bnd++) cum[(size_t)bnd * nPad + i] = (uint16_t)total;
+            count[i] = total;
+        }
+        if (wib == 0)
+        {
+            unsigned long long t = (unsigned long long)(nNear + nFar);
+            for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+            if (lane == 0 && t > 0) atomicAdd(&gp->totalEntries, t);
+        }
     }
     // statistics (maxRaw: what a row needs, for the regrow of the capacity)
-    int m = total;
-    for (int o = 16; o > 0; o >>= 1) m = max(m, __shfl_xor_sync(0xffffffffu, m, o));
-    unsigned long long t = (unsigned long long)min(total, cap);
-    for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
-    if (lane == 0 && m > 0)
+    if (lane == 0 && maxTotal > 0)
     {
-        atomicMax(&gp->maxCount, m);
-        atomicMax(&gp->maxRaw, m);
-        atomicAdd(&gp->totalEntries, t);
-        if (m > cap) atomicOr(&gp->error, 1);
+        atomicMax(&gp->maxCount, maxTotal);
+        atomicMax(&gp->maxRaw, maxTotal);
+        if (maxTotal > cap) atomicOr(&gp->error, 1);
     }
     if (tileGhost)
     {
-        // one tile of k_pair = this block (TILE threads): does any of its rows read a ghost position?
-        __shared__ int anyGhost;
-        if (threadIdx.x == 0) anyGhost = 0;
+        // a tile of k_pair is TILE slots = TILE / NBT_BEADS of these blocks (the flags are zeroed before the launch)
+        if (__any_sync(0xffffffffu, ghostEntry) && lane == 0) atomicOr(&sGhost, 1);
         __syncthreads();
-        if (ghostEntry) atomicOr(&anyGhost, 1);
-        __syncthreads();
-        if (threadIdx.x == 0) tileGhost[blockIdx.x] = anyGhost;
+        if (threadIdx.x == 0 && sGhost) atomicOr(&tileGhost[base / TILE], 1);
     }
 }
 

@@ -55,8 +55,6 @@ struct GridDev
     int nInterior;   // several ranks: k_pair tiles whose rows touch no ghost slot
     int bondTotal;   // bonded (term, endpoint) entries of the resident local beads
     int bondTerms;   // bonded terms (and restraints) whose role-0 bead is local
-    int winMaxTotal; // largest tile window (beads)
-    int winGlobal;   // tiles whose window did not fit
     unsigned long long totalEntries;
 };
 
@@ -76,27 +74,6 @@ struct PairConst
 __host__ __device__ inline uint64_t packW(int lj, int qi, uint32_t mol, uint32_t bead)
 {
     return (uint64_t)(lj & 0xff) | ((uint64_t)(qi & 0xff) << 8) | ((uint64_t)(mol & 0xffff) << 16) | ((uint64_t)bead << 32);
-}
-
-// Window of one k_pair tile (TILE consecutive slots): the slot runs that hold every partner of the tile's rows (the union of the
-// stencil cells of the tile's cells), staged in shared memory by the windowed pair kernel.  Entries of a windowed tile's rows are
-// offsets into the window; nRuns = 0: the window did not fit (or windows are off) and the entries are slots.
-#define WIN_MAXRUNS 30
-struct TileWin
-{
-    int nRuns, total;
-    int lo[WIN_MAXRUNS];        // first slot of each run, ascending
-    int off[WIN_MAXRUNS + 1];   // window offset of each run's first bead; off[nRuns] = total
-    int pad;
-};
-
-// entry of a row -> slot
-__host__ __device__ inline int winSlot(const TileWin &w, int idx)
-{
-    if (w.nRuns == 0) return idx;
-    int r = 0;
-    while (r + 1 < w.nRuns && w.off[r + 1] <= idx) r++;
-    return w.lo[r] + (idx - w.off[r]);
 }
 
 struct Term
@@ -245,6 +222,7 @@ struct ddcb200_ctx
                                            // prune), [1] of a ghost, [2] bits of a bound of the displacement between the build and the last prune
     // pruned rows (k_pair2 MODE 1 / 2, DDCB200_PRUNE=<every>[,<margin>]; 0 = off)
     bool listFused = true;        // DDCB200_LISTBUILD
+    size_t smemOptin = 0;         // shared memory a block may opt in to on this device
     int pruneEvery = 0;           // steps between prunes
     double pruneMargin = 0.0;     // entries closer than rmax + pruneMargin x deltaR are kept (0: 1.4 x pruneEvery / updateRate)
     int sincePrune = 0;           // force evaluations since the pruned rows were written
@@ -257,12 +235,8 @@ struct ddcb200_ctx
     DevBuf<unsigned long long> cellDmax;   // [2 ncell]: largest squared displacement since the build per cell (local part, ghost part)
     DevBuf<unsigned long long> nbrDmax;    // [2][ncell]: the maximum over each cell's stencil, without / with the ghost parts
     int nCellsBuilt = 0;
-    int pairVariant = 2;          // DDCB200_PAIR
+    int pairVariant = 2;          // DDCB200_PAIR: index into the k_pair2 instantiations of api.cu
     int bondedCap = 12;           // DDCB200_BONDED
-    bool pairWindows = false;     // DDCB200_PAIR=win: rows hold window offsets, k_pair3 gathers from shared memory
-    int winMax = 0;               // beads a window may hold (from the shared memory of the device)
-    DevBuf<TileWin> tileWin;
-    int winMaxTotal = 0;          // largest window of the current list: index into the k_pair2 instantiations of api.cu (-1: the round-1 kernel)
     DevBuf<float> dispOfSlot;     // each local bead's own displacement since the build, rounded up (0 right after a build)
     DevBuf<double> mmPartial;
     GridDev *grid = nullptr;      // device
