@@ -140,7 +140,7 @@ __global__ void k_pair_hash(int nIon, int nPad, const uint32_t *__restrict__ nbr
     if (i < nIon)
     {
         const int n = count[i];
-        const int nFront = farTop >= 0 ? (int)cum[i] : n;      // rows in two segments (k_nbr_tile): the second one runs down from farTop
+        const int nFront = farTop >= 0 ? (int)cum[i] : n;      // rows in two segments (k_nbr_exact2): the second one runs down from farTop
         const uint64_t gi = gid[beadOfSlot[i]];
         for (int k = 0; k < n; k++)
         {

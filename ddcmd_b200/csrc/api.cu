@@ -194,7 +194,7 @@ static int setupBox(ddcb200_ctx *c)
 // B200 through DDCB200_PAIR=<pf>,<minb> | old
 typedef void (*PairKernel)(int, int, const int *, int, const double4 *, const uint32_t *, const uint16_t *, const unsigned long long *, int,
                            const float *, const double2 *, const double *, const double *, PairConst, double *, double *, double *, double *,
-                           const unsigned long long *, const int *, PruneArgs);
+                           const unsigned long long *, const int *, PruneArgs, BondAdd);
 struct PairVariant
 {
     int pf, minb;
@@ -220,10 +220,11 @@ static int createInit(ddcb200_ctx *c)
 {
     if (const char *lb = getenv("DDCB200_LISTBUILD"))
     {
-        // A/B: "fused" = one pass (k_nbr_build: rows in stencil order), "twopass" = candidate pass + exact pass (rows ordered by distance bin)
-        if (strcmp(lb, "fused") == 0) c->listFused = true;
-        else if (strcmp(lb, "twopass") == 0) c->listFused = false;
-        else return fail(DDCB200_ERR_ARG, "DDCB200_LISTBUILD must be fused or twopass");
+        // A/B of the exact pass: "twoseg" = one sweep, rows in two segments (k_nbr_exact2), "bins" = counting sweep + placing sweep, rows
+        // ordered by eight distance bins (k_nbr_exact)
+        if (strcmp(lb, "twoseg") == 0) c->listFused = true;
+        else if (strcmp(lb, "bins") == 0) c->listFused = false;
+        else return fail(DDCB200_ERR_ARG, "DDCB200_LISTBUILD must be twoseg or bins");
     }
     if (const char *pe = getenv("DDCB200_PRUNE"))
     {
@@ -390,6 +391,7 @@ extern "C" void ddcb200_destroy(ddcb200_ctx *c)
     if (c->streamH) { cudaStreamSynchronize(c->streamH); cudaStreamDestroy(c->streamH); }
     if (c->streamB) { cudaStreamSynchronize(c->streamB); cudaStreamDestroy(c->streamB); }
     if (c->evBoundary) cudaEventDestroy(c->evBoundary);
+    if (c->evBonded) cudaEventDestroy(c->evBonded);
     if (c->evPos) cudaEventDestroy(c->evPos);
     if (c->evHalo) cudaEventDestroy(c->evHalo);
     c->tileGhost.release(); c->tileOrder.release(); c->cellDmax.release(); c->nbrDmax.release();
@@ -1205,25 +1207,20 @@ extern "C" int ddcb200_constructList(ddcb200_ctx *c)
         CK(c->nbr.ensure((size_t)c->nbrCap * nPad));
         CK(c->nbrRaw.ensure((size_t)c->nbrCap * nPad));
         CK(cudaEventRecord(c->evList[0], st));
+        LAUNCH(k_nbr_filter, tilesL, 128, 0, st)(nLocal, nPad, c->pos32.p, c->cellOfSlot[nxt].p, c->cellStart.p, c->box, rl2f, c->grid,
+                                            c->nbrCap, c->nbrRaw.p, c->nbrRawCount.p);
+        CKL("k_nbr_filter");
         if (c->listFused)
         {
-            // one pass; rows in two segments around the first bin edge (all the bin edges are that one edge, setupBox)
-            const size_t smemT = (size_t)NBT_BEADS * (size_t)(c->nbrCap | 1) * sizeof(uint32_t);
-            if (smemT + 4096 > c->smemOptin) return fail(DDCB200_ERR_CAPACITY, "neighbor rows too long for the shared-memory staging of the list build");
-            CK(cudaFuncSetAttribute(k_nbr_tile, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemT));
-            if (c->nranks > 1) CK(cudaMemsetAsync(c->tileGhost.p, 0, ((size_t)tilesL + 1) * sizeof(int), st));
-            LAUNCH(k_nbr_tile, (nLocal + NBT_BEADS - 1) / NBT_BEADS, 128, smemT, st)(nLocal, nPad, c->nbrCap, c->pos32.p, c->pos4[nxt].p, c->cellOfSlot[nxt].p,
-                                                   c->cellStart.p, c->box, rl2f, c->box.binEdge2[0],
-                                                   c->grid, c->nbr.p, c->nbrCount.p, c->nbrCum.p, c->gidOfBead.p, c->molTypeOfBead.p,
-                                                   c->molTypeSingle.p, c->bpairOffset.p, c->bpairKey.p, c->haveExcl ? 1 : 0,
-                                                   c->nranks > 1 ? c->tileGhost.p : nullptr);
-            CKL("k_nbr_tile");
+            // one sweep; rows in two segments around the first bin edge (all the bin edges are that one edge, createInit)
+            LAUNCH(k_nbr_exact2, tilesL, 128, 0, st)(nLocal, nPad, c->nbrCap, c->pos4[nxt].p, c->box, c->box.binEdge2[0], c->grid, c->nbrRaw.p,
+                                                    c->nbrRawCount.p, c->nbr.p, c->nbrCount.p, c->nbrCum.p, c->gidOfBead.p, c->molTypeOfBead.p,
+                                                    c->molTypeSingle.p, c->bpairOffset.p, c->bpairKey.p, c->haveExcl ? 1 : 0,
+                                                    c->nranks > 1 ? c->tileGhost.p : nullptr);
+            CKL("k_nbr_exact2");
         }
         else
         {
-            LAUNCH(k_nbr_filter, tilesL, 128, 0, st)(nLocal, nPad, c->pos32.p, c->cellOfSlot[nxt].p, c->cellStart.p, c->box, rl2f, c->grid,
-                                                c->nbrCap, c->nbrRaw.p, c->nbrRawCount.p);
-            CKL("k_nbr_filter");
             LAUNCH(k_nbr_exact, tilesL, 128, 0, st)(nLocal, nPad, c->nbrCap, c->pos4[nxt].p, c->box, c->grid, c->nbrRaw.p, c->nbrRawCount.p,
                                                    c->nbr.p, c->nbrCount.p, c->nbrCum.p, c->gidOfBead.p, c->molTypeOfBead.p,
                                                    c->molTypeSingle.p, c->bpairOffset.p, c->bpairKey.p, c->haveExcl ? 1 : 0,
@@ -1457,6 +1454,33 @@ extern "C" int ddcb200_ddcenergy(ddcb200_ctx *c, int withEnergy)
     const int nLocal = (int)c->nLocal, nPad = (int)c->nPad;      // local beads = slots [0, nLocal)
     const int tiles = (nLocal + TILE - 1) / TILE;
     if (withEnergy) CK(cudaMemsetAsync(c->acc, 0, ACC_N * sizeof(double), st));
+    // the bonded terms first: every term once, its forces staged; the pair kernel adds each bead's staged forces to its pair force
+    int bBlocks = 0;
+    BondAdd ba = {nullptr, nullptr, nullptr, nullptr};
+    if (c->nTerms + c->nRestr > 0 && c->nBondTerms > 0)
+    {
+        ba.start = c->bondStart.p;
+        ba.count = c->bondCount.p;
+        ba.stageIdx = c->bondStageIdx.p;
+        ba.stage = c->bondStage.p;
+        ProfScope ps(c, PROF_BONDED);
+        bBlocks = (c->nBondTerms + BONDED_THREADS - 1) / BONDED_THREADS;
+        CK(c->bondPartial.ensure((size_t)bBlocks * BONDED_ACC + 8));
+        V3 *stage = (V3 *)c->bondStage.p;
+        if (withEnergy)
+            LAUNCH((k_bonded<true, 1>), bBlocks, BONDED_THREADS, 0, st)(c->nBondTerms, c->bondRec.p, c->restrParm.p, c->restrOrigin, c->pos4[cur].p, c->pc,
+                                                                    stage, c->bondPartial.p);
+        else if (c->bondedCap == 8)
+            LAUNCH((k_bonded<false, 8>), bBlocks, BONDED_THREADS, 0, st)(c->nBondTerms, c->bondRec.p, c->restrParm.p, c->restrOrigin, c->pos4[cur].p, c->pc,
+                                                                     stage, c->bondPartial.p);
+        else if (c->bondedCap == 12)
+            LAUNCH((k_bonded<false, 12>), bBlocks, BONDED_THREADS, 0, st)(c->nBondTerms, c->bondRec.p, c->restrParm.p, c->restrOrigin, c->pos4[cur].p, c->pc,
+                                                                      stage, c->bondPartial.p);
+        else
+            LAUNCH((k_bonded<false, 1>), bBlocks, BONDED_THREADS, 0, st)(c->nBondTerms, c->bondRec.p, c->restrParm.p, c->restrOrigin, c->pos4[cur].p, c->pc,
+                                                                     stage, c->bondPartial.p);
+        CKL("k_bonded");
+    }
     int pruneMode = 0;
     PruneArgs pr = {nullptr, nullptr, 0.0, 0.0, 0.0, c->listFused ? c->nbrCap - 1 : -1};
     PairConst pcl = c->pc;
@@ -1498,7 +1522,7 @@ extern "C" int ddcb200_ddcenergy(ddcb200_ctx *c, int withEnergy)
                 const bool cellWalk = c->walkPerCell && c->walkPerBead && c->nCellsBuilt > 0;
                 LAUNCH(kern, nTiles, TILE, smem, st)(nLocal, nPad, order, base, c->pos4[cur].p, c->nbr.p, c->nbrCum.p, c->dmax2, withGhosts, disp, c->ljTab.p,
                                                      c->shiftTab.p, c->qTab.p, pcl, c->frc[0].p, c->frc[1].p, c->frc[2].p, c->pairPartial.p,
-                                                     cellWalk ? c->nbrDmax.p + (withGhosts ? c->nCellsBuilt : 0) : nullptr, c->cellOfSlot[cur].p, pr);
+                                                     cellWalk ? c->nbrDmax.p + (withGhosts ? c->nCellsBuilt : 0) : nullptr, c->cellOfSlot[cur].p, pr, ba);
             }
             CKL("k_pair");
             return DDCB200_OK;
@@ -1524,6 +1548,12 @@ extern "C" int ddcb200_ddcenergy(ddcb200_ctx *c, int withEnergy)
             if (tiles - c->nTilesInterior > 0)
             {
                 CK(cudaStreamWaitEvent(c->streamB, c->evHalo, 0));
+                if (bBlocks)
+                {
+                    // the boundary rows add the staged bonded forces too: their stream waits for k_bonded
+                    CK(cudaEventRecord(c->evBonded, st));
+                    CK(cudaStreamWaitEvent(c->streamB, c->evBonded, 0));
+                }
                 pst = c->streamB;
                 rc = launchPair(tiles - c->nTilesInterior, c->tileOrder.p, c->nTilesInterior, 1);
                 if (rc) return rc;
@@ -1542,30 +1572,6 @@ extern "C" int ddcb200_ddcenergy(ddcb200_ctx *c, int withEnergy)
             c->sincePrune = 0;
         }
         else if (pruneMode == 2) c->sincePrune++;
-    }
-    int bBlocks = 0;
-    if (c->nTerms + c->nRestr > 0 && c->nBondTerms > 0)
-    {
-        ProfScope ps(c, PROF_BONDED);
-        bBlocks = (c->nBondTerms + BONDED_THREADS - 1) / BONDED_THREADS;
-        CK(c->bondPartial.ensure((size_t)bBlocks * BONDED_ACC + 8));
-        V3 *stage = (V3 *)c->bondStage.p;
-        if (withEnergy)
-            LAUNCH((k_bonded<true, 1>), bBlocks, BONDED_THREADS, 0, st)(c->nBondTerms, c->bondRec.p, c->restrParm.p, c->restrOrigin, c->pos4[cur].p, c->pc,
-                                                                    stage, c->bondPartial.p);
-        else if (c->bondedCap == 8)
-            LAUNCH((k_bonded<false, 8>), bBlocks, BONDED_THREADS, 0, st)(c->nBondTerms, c->bondRec.p, c->restrParm.p, c->restrOrigin, c->pos4[cur].p, c->pc,
-                                                                     stage, c->bondPartial.p);
-        else if (c->bondedCap == 12)
-            LAUNCH((k_bonded<false, 12>), bBlocks, BONDED_THREADS, 0, st)(c->nBondTerms, c->bondRec.p, c->restrParm.p, c->restrOrigin, c->pos4[cur].p, c->pc,
-                                                                      stage, c->bondPartial.p);
-        else
-            LAUNCH((k_bonded<false, 1>), bBlocks, BONDED_THREADS, 0, st)(c->nBondTerms, c->bondRec.p, c->restrParm.p, c->restrOrigin, c->pos4[cur].p, c->pc,
-                                                                     stage, c->bondPartial.p);
-        CKL("k_bonded");
-        LAUNCH(k_bonded_sum, (nLocal + BONDED_THREADS - 1) / BONDED_THREADS, BONDED_THREADS, 0, st)(nLocal, c->bondStart.p, c->bondCount.p, c->bondStageIdx.p,
-                                                                                                stage, c->frc[0].p, c->frc[1].p, c->frc[2].p);
-        CKL("k_bonded_sum");
     }
     if (withEnergy)
     {
@@ -2107,7 +2113,7 @@ extern "C" int64_t ddcb200_getPairs(ddcb200_ctx *c, int64_t capacity, int *beadI
         }
     };
     // rows of the one-pass build are two segments: the first cum[0] entries from the front, the others from the end of the row's
-    // allocation backwards (k_nbr_tile); rows of the two-pass build run forward
+    // allocation backwards (k_nbr_exact2); rows of k_nbr_exact run forward
     const int farTop = c->listFused ? c->nbrCap - 1 : -1;
     int maxc = 0;
     for (int i = 0; i < n; i++) maxc = std::max(maxc, cnt[i]);
@@ -2400,6 +2406,7 @@ extern "C" int ddcb200_ddcInit(ddcb200_ctx *c, int rank, int nranks, int lx, int
     CK(cudaEventCreateWithFlags(&c->evPos, cudaEventDisableTiming));
     CK(cudaEventCreateWithFlags(&c->evHalo, cudaEventDisableTiming));
     CK(cudaEventCreateWithFlags(&c->evBoundary, cudaEventDisableTiming));
+    CK(cudaEventCreateWithFlags(&c->evBonded, cudaEventDisableTiming));
     CK(cudaStreamCreateWithFlags(&c->streamB, cudaStreamNonBlocking));
     CK(cudaMalloc((void **)&c->boxes, sizeof(DdcBoxes)));
     CK(cudaMalloc((void **)&c->ddcWork, sizeof(DdcWork)));

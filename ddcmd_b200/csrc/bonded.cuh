@@ -384,8 +384,8 @@ __device__ __forceinline__ void bondedEval(const BondRec &tm, const double *__re
 // adds the sum to the slot's pair force - no atomic, one writer per slot.  A bead belongs to the CTA that holds its first
 // record; a CTA therefore also evaluates the up to BONDED_SPILL records of its last beads that lie beyond its 128.
 // Every term is evaluated ONCE, by one thread, which stages the forces on the term's beads (stage[4 term + role], coalesced);
-// k_bonded_sum then adds, per local bead, the bead's contributions in their fixed order and adds the sum to the slot's pair
-// force - no atomic, one writer per slot, the same order every run.
+// the pair kernel, which runs after this one, adds per local bead the bead's contributions in their fixed order to the bead's
+// pair force before it stores it (BondAdd, pair.cuh) - no atomic, one writer per slot, the same order every run.
 template <bool ENERGY, int MINB>
 __global__ void __launch_bounds__(BONDED_THREADS, MINB)
 k_bonded(int nTermsLocal, const BondRec *__restrict__ recs, const double *__restrict__ restrParm, int restrOrigin, const double4 *__restrict__ pos,
@@ -423,29 +423,4 @@ k_bonded(int nTermsLocal, const BondRec *__restrict__ recs, const double *__rest
             partial[(size_t)blockIdx.x * BONDED_ACC + threadIdx.x] = v;
         }
     }
-}
-
-__global__ void __launch_bounds__(BONDED_THREADS)
-k_bonded_sum(int nLocal, const int *__restrict__ start, const int *__restrict__ cnt, const int *__restrict__ stageIdx, const V3 *__restrict__ stage,
-             double *__restrict__ fx, double *__restrict__ fy, double *__restrict__ fz)
-{
-    const int s = blockIdx.x * blockDim.x + threadIdx.x;
-    if (s >= nLocal) return;
-    const int n = cnt[s];
-    if (n == 0) return;
-    const int lo = start[s];
-    V3 fs = V3{0.0, 0.0, 0.0};
-    for (int q = 0; q < n; q++)
-    {
-        const int k = stageIdx[lo + q];
-        if (k < 0) continue;
-        const V3 f = stage[k];
-        fs.x += f.x;
-        fs.y += f.y;
-        fs.z += f.z;
-    }
-    // k_pair has written this slot's pair force: the bonded sum is added to it by the only thread that owns the slot
-    fx[s] += fs.x;
-    fy[s] += fs.y;
-    fz[s] += fs.z;
 }

@@ -470,70 +470,49 @@ k_nbr_exact(int nIon, int nPad, int cap, const double4 *__restrict__ pos, BoxCon
     }
 }
 
-// ---- 9b. the list build in one pass: one warp per bead, lanes over candidates ----------------------------------------------------
-// A block builds the rows of 32 consecutive local slots (the beads of one warp of the pair kernel); each of its four warps takes
-// eight of them, one after the other.  For its bead the warp scans the stencil 32 candidates at a time - x-adjacent cells are one
-// run of consecutive slots, so the loads of the fp32 positions are coalesced - with the conservative fp32 filter of k_nbr_filter;
-// the survivors are compacted with a ballot into a small queue, and whenever 32 are queued the lanes take pairlist1's decision in
-// fp64 for one candidate each, with exactly the arithmetic of k_nbr_exact (bit for bit the same membership).  Entries listed
-// closer than nearEdge are appended to the front of the bead's row, the others from the end of the row's allocation backwards:
-// two segments in stencil order, no sort.  The pair walk visits the front segment first - nearly all of its entries are inside the
-// cutoff, and right after a build it is all the pruned rows need - and the far segment behind it is nearly all outside, so the
-// lanes of a warp agree on whether the force block runs.  The block's rows are staged in shared memory and written out
-// transposed, one 128-byte line per row position.  An earlier version with one thread per bead and per-lane queues ran 1.5 G warp
-// instructions and 2.1 ms against 2.8 ms for the two passes (profiles/r02q_k_nbr_build_ncu_full.txt); this one has no divergence
-// in the scan and no scattered stores.
-#define NBT_BEADS 32      // beads per block
-#define NBT_QCAP 64       // queue slots per warp
+// ---- 9b. exact pass in one sweep, rows in two segments ----------------------------------------------------------------------------
+// The same decision as k_nbr_exact for every candidate, but each entry is written once, straight to its place: the entries listed
+// closer than nearEdge go to the front of the bead's row, the others from the end of the row's allocation backwards - two segments
+// in candidate order instead of eight sorted bins, so there is no counting sweep, no write-back of the candidates and no second
+// read (k_nbr_exact moves 2.6 GB for 0.9 GB of rows and candidates).  The lanes of a warp accept nearly every candidate (the fp32
+// filter is tight), so their cursors advance together and a warp's stores fall into a few lines.  The pair walk visits the front
+// segment first: nearly all of it is inside the cutoff and right after a build it is all the pruned rows need, while the far
+// segment is nearly all outside - the lanes of a warp agree on whether the force block runs, which is what the bins were for.
+// Two one-warp-per-bead builds that fused the candidate scan into this pass were measured and lost (1.5 G and 3.2 G warp
+// instructions against 1.2 G for the two passes; profiles/r02q_k_nbr_build_ncu_full.txt, r02s_k_nbr_tile_ncu_full.txt).
 __global__ void __launch_bounds__(128)
-k_nbr_tile(int nIon, int nPad, int cap, const float4 *__restrict__ pos32, const double4 *__restrict__ pos, const int *__restrict__ cellOf,
-           const int *__restrict__ cellStart, BoxConst b, float rl2f, double near2, GridDev *gp, uint32_t *__restrict__ out,
-           int *__restrict__ count, uint16_t *__restrict__ cum, const uint64_t *__restrict__ gid, const int *__restrict__ molTypeOfBead,
-           const int *__restrict__ molTypeSingle, const int *__restrict__ bpairOffset, const uint32_t *__restrict__ bpairKey, int haveExcl,
-           int *__restrict__ tileGhost)
+k_nbr_exact2(int nIon, int nPad, int cap, const double4 *__restrict__ pos, BoxConst b, double near2, GridDev *gp, const uint32_t *__restrict__ raw,
+             const int *__restrict__ rawCount, uint32_t *__restrict__ out, int *__restrict__ count, uint16_t *__restrict__ cum,
+             const uint64_t *__restrict__ gid, const int *__restrict__ molTypeOfBead, const int *__restrict__ molTypeSingle,
+             const int *__restrict__ bpairOffset, const uint32_t *__restrict__ bpairKey, int haveExcl, int *__restrict__ tileGhost)
 {
-    EXTERN_SHARED(uint32_t, sRow);               // [NBT_BEADS][rs] the rows of this block (odd stride: the transposed read-out hits 32 banks)
-    const int rs = cap | 1;
-    __shared__ uint32_t sQ[4][NBT_QCAP];
-    __shared__ int sNear[NBT_BEADS], sFar[NBT_BEADS];
-    __shared__ int sGhost;
-    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-    const unsigned ltMask = (1u << lane) - 1u;
-    const int base = blockIdx.x * NBT_BEADS;
-    if (threadIdx.x == 0) sGhost = 0;
-    if (threadIdx.x < NBT_BEADS) { sNear[threadIdx.x] = 0; sFar[threadIdx.x] = 0; }
-    __syncthreads();
-    const int nx = gp->n[0], ny = gp->n[1], nz = gp->n[2], ncell = nx * ny * nz;
-    const float Lx = (float)b.hxx, Ly = (float)b.hyy, Lz = (float)b.hzz;
-    const float hx2 = 0.5f * Lx, hy2 = 0.5f * Ly, hz2 = 0.5f * Lz;
-    // with >= 3 cells along an axis a wrapped stencil cell has ONE possible image: shift it;
-    // with fewer the stencil is deduplicated and each pair takes its nearest image
-    const bool px = nx < 3, py = ny < 3, pz = nz < 3;
-    const int ly = ny >= 3 ? -1 : 0, hy = ny >= 2 ? 1 : 0;
-    const int lz = nz >= 3 ? -1 : 0, hz = nz >= 2 ? 1 : 0;
-    int maxTotal = 0;
-    bool ghostEntry = false;
-    for (int q = 0; q < NBT_BEADS / 4; q++)
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    int nNear = 0, nFar = 0;
+    bool ghostEntry = false;      // some entry of this row is a ghost slot (several ranks): the row waits for the halo
+    if (i < nIon)
     {
-        const int bt = wib * (NBT_BEADS / 4) + q;      // bead of the block
-        const int i = base + bt;
-        if (i >= nIon) break;
-        const float4 pi = pos32[i];
-        if (pi.w != 0.0f) continue;                    // a ghost slot owns no row (local slots come first: never happens below nLocal)
-        const double4 pd = pos[i];
-        const uint64_t wi = (uint64_t)__double_as_longlong(pd.w);
-        uint32_t *row = sRow + (size_t)bt * rs;
-        int nNear = 0, nFar = 0, qn = 0;
-        // pairlist1's test (src/pairlist.c:280-288) and reOrgPairs' pruning flag for the first `take` queued candidates, one per lane
-        auto exactBatch = [&](int take) {
-            const bool has = lane < take;
-            const uint32_t j = has ? sQ[wib][lane] : 0u;
-            bool in = false, isNear = false;
-            uint32_t ent = j;
-            if (has)
+        const int n = min(rawCount[i], cap);
+        const double4 pi = pos[i];
+        const uint64_t wi = (uint64_t)__double_as_longlong(pi.w);
+        // two candidates in flight: the gathers of a pair of candidates are issued before either is tested
+        uint32_t jn0 = (0 < n) ? raw[i] : 0u, jn1 = (1 < n) ? raw[(size_t)nPad + i] : 0u;
+        for (int k = 0; k < n; k += 2)
+        {
+            const uint32_t j0 = jn0, j1 = jn1;
+            const bool has1 = k + 1 < n;
+            const double4 p0 = ldPos256(pos + j0);
+            double4 p1 = p0;
+            if (has1) p1 = ldPos256(pos + j1);
+            if (k + 2 < n) jn0 = raw[(size_t)(k + 2) * nPad + i];
+            if (k + 3 < n) jn1 = raw[(size_t)(k + 3) * nPad + i];
+#pragma unroll
+            for (int u = 0; u < 2; u++)
             {
-                const double4 pj = ldPos256(pos + j);
-                double x = __dadd_rn(pd.x, -pj.x), y = __dadd_rn(pd.y, -pj.y), z = __dadd_rn(pd.z, -pj.z);
+                if (u == 1 && !has1) break;
+                const uint32_t j = u ? j1 : j0;
+                const double4 pj = u ? p1 : p0;
+                // pairlist1, src/pairlist.c:280-288
+                double x = __dadd_rn(pi.x, -pj.x), y = __dadd_rn(pi.y, -pj.y), z = __dadd_rn(pi.z, -pj.z);
                 double r2 = exactR2(x, y, z);
                 if (r2 > b.R2cut)
                 {
@@ -542,8 +521,7 @@ k_nbr_tile(int nIon, int nPad, int cap, const float4 *__restrict__ pos32, const 
                 }
                 if (r2 < b.rlist2)
                 {
-                    in = true;
-                    isNear = r2 < near2;
+                    uint32_t ent = j;
                     const uint64_t wj = (uint64_t)__double_as_longlong(pj.w);
                     ghostEntry |= (wj >> 63) != 0ull;
                     if (haveExcl)
@@ -553,144 +531,46 @@ k_nbr_tile(int nIon, int nPad, int cap, const float4 *__restrict__ pos32, const 
                             isPruned((int)((wi >> 32) & 0x7fffffffull), (int)((wj >> 32) & 0x7fffffffull), gid, molTypeOfBead, molTypeSingle, bpairOffset, bpairKey))
                             ent |= EXCL_BIT;
                     }
-                }
-            }
-            const unsigned mNear = __ballot_sync(0xffffffffu, in && isNear), mFar = __ballot_sync(0xffffffffu, in && !isNear);
-            const int cN = __popc(mNear), cF = __popc(mFar);
-            if (nNear + nFar + cN + cF <= cap)
-            {
-                if (in && isNear) row[nNear + __popc(mNear & ltMask)] = ent;
-                if (in && !isNear) row[cap - 1 - (nFar + __popc(mFar & ltMask))] = ent;
-            }
-            nNear += cN;
-            nFar += cF;
-            // the candidates behind the batch move to the front of the queue
-            __syncwarp();
-            const uint32_t keep = (lane + take < qn) ? sQ[wib][lane + take] : 0u;
-            __syncwarp();
-            if (lane + take < qn) sQ[wib][lane] = keep;
-            qn -= take;
-            __syncwarp();
-        };
-        const int c = cellOf[i];
-        const int cx = c % nx, cy = (c / nx) % ny, cz = c / (nx * ny);
-        for (int dz = lz; dz <= hz; dz++)
-        {
-            int az = cz + dz;
-            float sz = 0.0f;
-            if (az < 0) { az += nz; sz = -Lz; }
-            else if (az >= nz) { az -= nz; sz = Lz; }
-            const float bz = pz ? pi.z : pi.z - sz;
-            for (int dy = ly; dy <= hy; dy++)
-            {
-                int ay = cy + dy;
-                float sy = 0.0f;
-                if (ay < 0) { ay += ny; sy = -Ly; }
-                else if (ay >= ny) { ay -= ny; sy = Ly; }
-                const float by = py ? pi.y : pi.y - sy;
-                const int rowBase = nx * (ay + ny * az);
-                // runs along x: nx >= 3: the cells cx-1 .. cx+1 clipped to the row, then the one cell that wraps around (most beads
-                // have none); nx < 3: the bead's own cell, then the other one (nx = 2), pairs take their nearest image
-                for (int sg = 0; sg < 2; sg++)
-                {
-                    int c0, c1;      // cells c0 .. c1 of the row; c1 < c0: nothing
-                    float sx = 0.0f;
-                    if (!px)
+                    if (r2 < near2)
                     {
-                        if (sg == 0) { c0 = max(cx - 1, 0); c1 = min(cx + 1, nx - 1); }
-                        else if (cx == 0) { c0 = c1 = nx - 1; sx = -Lx; }
-                        else if (cx == nx - 1) { c0 = c1 = 0; sx = Lx; }
-                        else { c0 = 1; c1 = 0; }
+                        out[(size_t)nNear * nPad + i] = ent;
+                        nNear++;
                     }
                     else
                     {
-                        if (sg == 0) c0 = c1 = cx;
-                        else if (nx == 2) c0 = c1 = 1 - cx;
-                        else { c0 = 1; c1 = 0; }
-                    }
-                    if (c1 < c0) continue;
-                    const float bx = px ? pi.x : pi.x - sx;
-                    // the cells' local beads, then (several ranks) their ghosts
-                    for (int part = 0; part < 2; part++)
-                    {
-                        const int lo = cellStart[part * ncell + rowBase + c0], hi = cellStart[part * ncell + rowBase + c1 + 1];
-                        for (int j0 = lo; j0 < hi; j0 += 32)
-                        {
-                            const int j = j0 + lane;
-                            bool pass = false;
-                            if (j < hi)
-                            {
-                                const float4 pj = pos32[j];
-                                float x = bx - pj.x, y = by - pj.y, z = bz - pj.z;
-                                if (px) { if (x > hx2) x -= Lx; if (x < -hx2) x += Lx; }
-                                if (py) { if (y > hy2) y -= Ly; if (y < -hy2) y += Ly; }
-                                if (pz) { if (z > hz2) z -= Lz; if (z < -hz2) z += Lz; }
-                                pass = (x * x + y * y + z * z < rl2f) && j != i;
-                            }
-                            const unsigned m = __ballot_sync(0xffffffffu, pass);
-                            if (pass) sQ[wib][qn + __popc(m & ltMask)] = (uint32_t)j;
-                            qn += __popc(m);
-                            __syncwarp();
-                            if (qn >= 32) exactBatch(32);
-                        }
+                        out[(size_t)(cap - 1 - nFar) * nPad + i] = ent;
+                        nFar++;
                     }
                 }
             }
         }
-        if (qn > 0) exactBatch(qn);
+        // cum[0] = the front segment, cum[1..] = the whole row: the pair walk's two "bins" (every bin edge is nearEdge)
         const int total = nNear + nFar;
-        maxTotal = max(maxTotal, total);
-        if (lane == 0)
-        {
-            sNear[bt] = total <= cap ? nNear : 0;
-            sFar[bt] = total <= cap ? nFar : 0;
-        }
-    }
-    __syncthreads();
-    // the rows go out transposed: row position k of the block's 32 beads is one line.  Front segments from position 0 up, far
-    // segments from cap - 1 down; cum[0] = front length, cum[1..] = the whole row (the pair walk's two "bins")
-    {
-        const int bt = lane, i = base + bt;
-        const int nNear = sNear[bt], nFar = sFar[bt];
-        int mxN = nNear, mxF = nFar;
-        for (int o = 16; o > 0; o >>= 1)
-        {
-            mxN = max(mxN, __shfl_xor_sync(0xffffffffu, mxN, o));
-            mxF = max(mxF, __shfl_xor_sync(0xffffffffu, mxF, o));
-        }
-        const uint32_t *row = sRow + (size_t)bt * rs;
-        for (int k = wib; k < mxN; k += 4)
-            if (k < nNear) out[(size_t)k * nPad + i] = row[k];
-        for (int f = wib; f < mxF; f += 4)
-            if (f < nFar) out[(size_t)(cap - 1 - f) * nPad + i] = row[cap - 1 - f];
-        if (wib == 0 && i < nIon)
-        {
-            const int total = nNear + nFar;
-            cum[i] = (uint16_t)nNear;
+        cum[i] = (uint16_t)nNear;
 #pragma unroll
-            for (int bnd = 1; bnd < NBINS; bnd++) cum[(size_t)bnd * nPad + i] = (uint16_t)total;
-            count[i] = total;
-        }
-        if (wib == 0)
-        {
-            unsigned long long t = (unsigned long long)(nNear + nFar);
-            for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
-            if (lane == 0 && t > 0) atomicAdd(&gp->totalEntries, t);
-        }
+        for (int bnd = 1; bnd < NBINS; bnd++) cum[(size_t)bnd * nPad + i] = (uint16_t)total;
+        count[i] = total;
     }
-    // statistics (maxRaw: what a row needs, for the regrow of the capacity)
-    if (lane == 0 && maxTotal > 0)
+    // statistics
+    const int total = nNear + nFar;
+    int m = total;
+    for (int o = 16; o > 0; o >>= 1) m = max(m, __shfl_xor_sync(0xffffffffu, m, o));
+    unsigned long long t = (unsigned long long)total;
+    for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+    if ((threadIdx.x & 31) == 0 && m > 0)
     {
-        atomicMax(&gp->maxCount, maxTotal);
-        atomicMax(&gp->maxRaw, maxTotal);
-        if (maxTotal > cap) atomicOr(&gp->error, 1);
+        atomicMax(&gp->maxCount, m);
+        atomicAdd(&gp->totalEntries, t);
     }
     if (tileGhost)
     {
-        // a tile of k_pair is TILE slots = TILE / NBT_BEADS of these blocks (the flags are zeroed before the launch)
-        if (__any_sync(0xffffffffu, ghostEntry) && lane == 0) atomicOr(&sGhost, 1);
+        // one tile of k_pair = this block (TILE threads): does any of its rows read a ghost position?
+        __shared__ int anyGhost;
+        if (threadIdx.x == 0) anyGhost = 0;
         __syncthreads();
-        if (threadIdx.x == 0 && sGhost) atomicOr(&tileGhost[base / TILE], 1);
+        if (ghostEntry) atomicOr(&anyGhost, 1);
+        __syncthreads();
+        if (threadIdx.x == 0) tileGhost[blockIdx.x] = anyGhost;
     }
 }
 

@@ -221,9 +221,9 @@ struct ddcb200_ctx
     unsigned long long *dmax2 = nullptr;   // device: [0] bits of the max squared displacement of a LOCAL bead since the build (or the last
                                            // prune), [1] of a ghost, [2] bits of a bound of the displacement between the build and the last prune
     // pruned rows (k_pair2 MODE 1 / 2, DDCB200_PRUNE=<every>[,<margin>]; 0 = off)
-    bool listFused = true;        // DDCB200_LISTBUILD
+    bool listFused = true;        // DDCB200_LISTBUILD: rows in two segments (k_nbr_exact2) instead of eight bins
     size_t smemOptin = 0;         // shared memory a block may opt in to on this device
-    int pruneEvery = 0;           // steps between prunes
+    int pruneEvery = 4;           // steps between prunes (measured best with its default margin: profiles/r02p_prune_ab.jsonl)
     double pruneMargin = 0.0;     // entries closer than rmax + pruneMargin x deltaR are kept (0: 1.4 x pruneEvery / updateRate)
     int sincePrune = 0;           // force evaluations since the pruned rows were written
     bool pruneValid = false;      // the pruned rows belong to the current list and reference positions
@@ -309,7 +309,7 @@ struct ddcb200_ctx
     bool haloDirty = false, localsDirty = false;
     cudaStream_t streamH = nullptr;         // the halo runs here, beside the pair work of the rows that read no ghost
     cudaStream_t streamB = nullptr;         // the pair rows that wait for the halo: beside the tail of the other rows' launch
-    cudaEvent_t evPos = nullptr, evHalo = nullptr, evBoundary = nullptr;
+    cudaEvent_t evPos = nullptr, evHalo = nullptr, evBoundary = nullptr, evBonded = nullptr;
     DevBuf<int> tileGhost, tileOrder;
     int nTilesInterior = 0;
     bool haloOverlap = true;                // DDCB200_HALO=overlap|inline

@@ -102,7 +102,16 @@ struct PruneArgs
     double keep2;        // MODE 1: (rmax + margin)^2
     double walkLim;      // MODE 1: the full row is walked up to this build-time distance (rmax + margin right after a build, else all)
     double useLim;       // MODE 2: a bead may use its pruned row while rmax + its displacement bound <= rmax + margin
-    int farTop;          // full rows in two segments (k_nbr_tile): entry k >= nNear of a row sits at farTop - (k - nNear); -1: rows run forward
+    int farTop;          // full rows in two segments (k_nbr_exact2): entry k >= nNear of a row sits at farTop - (k - nNear); -1: rows run forward
+};
+
+// The bonded forces of the step (k_bonded has staged them, one entry per term and endpoint) are added up per bead, in the bead's
+// fixed entry order, by the thread that owns the bead's pair force, and the total goes out in one store: no pass of its own over
+// the force arrays.  start == nullptr: no bonded terms.
+struct BondAdd
+{
+    const int *start, *count, *stageIdx;     // per local slot: its run of entries; per entry: where the force on this bead is staged (-1: none)
+    const double *stage;                     // 3 doubles per (term, endpoint)
 };
 
 template <bool ENERGY, int NPF, int MINB, int MODE>
@@ -111,7 +120,7 @@ k_pair2(int nIon, int nPad, const int *__restrict__ tileOrder, int tileBase, con
         const uint16_t *__restrict__ cum, const unsigned long long *__restrict__ dmax2, int withGhosts, const float *__restrict__ dispOfSlot,
         const double2 *__restrict__ ljTab, const double *__restrict__ shiftTab, const double *__restrict__ qTab, PairConst pc,
         double *__restrict__ fx, double *__restrict__ fy, double *__restrict__ fz, double *__restrict__ accPartial,
-        const unsigned long long *__restrict__ nbrDmax, const int *__restrict__ cellOfSlot, PruneArgs pr)
+        const unsigned long long *__restrict__ nbrDmax, const int *__restrict__ cellOfSlot, PruneArgs pr, BondAdd ba)
 {
     EXTERN_SHARED(double2, sLJ);               // ntypes*ntypes {6 c6, 12 c12}
     double *sQ = (double *)(sLJ + pc.ntypes * pc.ntypes);   // 256 charges
@@ -251,9 +260,22 @@ k_pair2(int nIon, int nPad, const int *__restrict__ tileOrder, int tileBase, con
 #undef ROWAT
     if (live)
     {
-        fx[i] = fxi;
-        fy[i] = fyi;
-        fz[i] = fzi;
+        double bfx = 0.0, bfy = 0.0, bfz = 0.0;
+        if (ba.start)
+        {
+            const int nb = ba.count[i], lo = ba.start[i];
+            for (int q = 0; q < nb; q++)
+            {
+                const int k = ba.stageIdx[lo + q];
+                if (k < 0) continue;
+                bfx += ba.stage[3 * (size_t)k];
+                bfy += ba.stage[3 * (size_t)k + 1];
+                bfz += ba.stage[3 * (size_t)k + 2];
+            }
+        }
+        fx[i] = fxi + bfx;
+        fy[i] = fyi + bfy;
+        fz[i] = fzi + bfz;
         if (MODE == 1) pr.count[i] = (uint16_t)nKept;
     }
     if (ENERGY)

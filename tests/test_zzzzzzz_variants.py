@@ -15,7 +15,7 @@ pytestmark = pytest.mark.gpu
 
 def test_bin_edges_knob_keeps_the_pair_set(golden_dir, monkeypatch):
     """DDCB200_BIN_EDGES only reorders the entries of a row (here: two bins instead of eight): same pairs, forces to rounding."""
-    monkeypatch.setenv("DDCB200_LISTBUILD", "twopass")      # the build that orders rows by distance bin
+    monkeypatch.setenv("DDCB200_LISTBUILD", "bins")      # the exact pass that orders rows by distance bin
     sim, ref = _load(golden_dir, "popc_small")
     sim.ddcenergy(1)
     a = sim.getState()
