@@ -211,21 +211,14 @@ static const int g_nPairVariants = (int)(sizeof(g_pairVariants) / sizeof(g_pairV
 // neighbour together move about 0.07 deltaR per step at 310 K with deltaR = 4 A)
 static double pruneFracOf(const ddcb200_ctx *c)
 {
-    const double frac = c->pruneMargin > 0.0 ? c->pruneMargin : 1.4 * c->pruneEvery / std::max(1, c->prm.updateRate);
+    // (updateRate = 0, rebuilds triggered by the displacements: the margin of a 20-step schedule)
+    const double frac = c->pruneMargin > 0.0 ? c->pruneMargin : 1.4 * c->pruneEvery / (c->prm.updateRate > 0 ? c->prm.updateRate : 20);
     return std::min(frac, 1.0);
 }
 
 // everything of ddcb200_create that can fail after the context exists: a failure is unwound by ddcb200_destroy
 static int createInit(ddcb200_ctx *c)
 {
-    if (const char *lb = getenv("DDCB200_LISTBUILD"))
-    {
-        // A/B of the exact pass: "twoseg" = one sweep, rows in two segments (k_nbr_exact2), "bins" = counting sweep + placing sweep, rows
-        // ordered by eight distance bins (k_nbr_exact)
-        if (strcmp(lb, "twoseg") == 0) c->listFused = true;
-        else if (strcmp(lb, "bins") == 0) c->listFused = false;
-        else return fail(DDCB200_ERR_ARG, "DDCB200_LISTBUILD must be twoseg or bins");
-    }
     if (const char *pe = getenv("DDCB200_PRUNE"))
     {
         // pruned rows: <every>[,<margin>] - rewritten every <every> force evaluations from the entries closer than rmax + <margin> x deltaR
@@ -239,31 +232,10 @@ static int createInit(ddcb200_ctx *c)
         c->pruneEvery = every;
         c->pruneMargin = got == 2 ? margin : 0.0;
     }
-    if (const char *be = getenv("DDCB200_BIN_EDGES"))
     {
-        // tuning knob: the NBINS-1 ascending edges of the row-ordering bins as fractions of deltaR around the cutoff
-        // (equal values merge bins).  Any choice gives the same pair set; only the order of the entries in a row changes.
-        double v[NBINS - 1];
-        int n = 0;
-        const char *q = be;
-        while (n < NBINS - 1)
-        {
-            char *end;
-            v[n] = strtod(q, &end);
-            if (end == q) break;
-            n++;
-            q = (*end == ',') ? end + 1 : end;
-        }
-        bool ok = n == NBINS - 1;
-        for (int k = 0; ok && k < NBINS - 1; k++) ok = v[k] > -1.0 && v[k] <= 1.0 && (k == 0 || v[k] >= v[k - 1]);
-        if (!ok) return fail(DDCB200_ERR_ARG, "DDCB200_BIN_EDGES needs 7 ascending fractions of deltaR in (-1, 1]");
-        for (int k = 0; k < NBINS - 1; k++) c->binFrac[k] = v[k];
-    }
-    if (c->listFused)
-    {
-        // the one-pass build keeps two segments per row: every bin edge is the one edge between them, rmax + 0.3 deltaR (DDCB200_NEAR) -
-        // just beyond the default margin of the pruned rows, so that the evaluation after a build finds all it needs in the first
-        // segment, and independent of it, so that the order of a row (the order of the force sums) does not depend on the pruning
+        // a row is two segments around one edge, rmax + 0.3 deltaR (DDCB200_NEAR): just beyond the default margin of the pruned rows, so
+        // that the evaluation after a build finds all it needs in the first segment, and independent of that margin, so that the
+        // order of a row (the order of the force sums) does not depend on the pruning
         double nearFrac = 0.3;
         if (const char *nf = getenv("DDCB200_NEAR"))
         {
@@ -271,11 +243,6 @@ static int createInit(ddcb200_ctx *c)
             if (!(nearFrac > 0.0 && nearFrac <= 1.0)) return fail(DDCB200_ERR_ARG, "DDCB200_NEAR must be a fraction of deltaR in (0, 1]");
         }
         for (int k = 0; k < NBINS - 1; k++) c->binFrac[k] = nearFrac;
-    }
-    {
-        cudaDeviceProp prop;
-        CK(cudaGetDeviceProperties(&prop, c->device));
-        c->smemOptin = prop.sharedMemPerBlockOptin;
     }
     int rc = setupBox(c);
     if (rc != DDCB200_OK) return rc;
@@ -378,6 +345,7 @@ extern "C" void ddcb200_destroy(ddcb200_ctx *c)
     c->colMap.release(); c->stage.release(); c->stageI.release();
     c->orderKey.release(); c->pos32.release(); c->nbrRawCount.release(); c->nbrCum.release();
     for (int a = 0; a < 3; a++) c->posBuild[a].release();
+    for (int a = 0; a < 3; a++) c->posCheck[a].release();
     c->dispOfSlot.release(); c->pruneCount.release();
     if (c->dmax2) cudaFree(c->dmax2);
     c->groupOfBead.release(); c->rngState.release(); c->rngMP.release(); c->consAtomOff.release(); c->consAtomBead.release();
@@ -1176,22 +1144,25 @@ extern "C" int ddcb200_constructList(ddcb200_ctx *c)
         if (rcb) return rcb;
         CK(c->bondCount.ensure((size_t)nPad));
         CK(c->bondStart.ensure((size_t)nPad));
-        CK(c->bondCount0.ensure((size_t)nPad));
-        CK(c->bondStart0.ensure((size_t)nPad));
-        LAUNCH(k_bond_count, (nLocal + 255) / 256, 256, 0, st)(nLocal, c->pos4[nxt].p, c->bondCsrOff.p, c->bondEnt.p, c->bondCount.p, c->bondCount0.p);
+        CK(c->bondCount0.ensure((size_t)BOND_GROUPS * nPad));
+        CK(c->bondStart0.ensure((size_t)BOND_GROUPS * nPad));
+        LAUNCH(k_bond_count, (nLocal + 255) / 256, 256, 0, st)(nLocal, c->pos4[nxt].p, c->bondCsrOff.p, c->bondEnt.p, c->nTerms, c->termsBead.p,
+                                                           c->bondCount.p, c->bondCount0.p);
         CKL("k_bond_count");
-        const int nsb = (nLocal + SCAN_BLOCK - 1) / SCAN_BLOCK;
-        CK(c->scanBlocks.ensure((size_t)nsb + 1));
         for (int which = 0; which < 2; which++)
         {
-            // entries per bead -> where the bead's run starts; role-0 entries per bead -> the bead's first local term
+            // entries per bead -> where the bead's run starts; owned terms per (kind group, bead) -> the place of the bead's first term
+            // of that group in the kind-grouped numbering of the local terms
+            const int n = which ? BOND_GROUPS * nLocal : nLocal;
+            const int nsb = (n + SCAN_BLOCK - 1) / SCAN_BLOCK;
+            CK(c->scanBlocks.ensure((size_t)nsb + 1));
             const int *cnt = which ? c->bondCount0.p : c->bondCount.p;
             int *start = which ? c->bondStart0.p : c->bondStart.p;
-            LAUNCH(k_scan_local, nsb, SCAN_BLOCK, 0, st)(nLocal, cnt, start, c->scanBlocks.p);
+            LAUNCH(k_scan_local, nsb, SCAN_BLOCK, 0, st)(n, cnt, start, c->scanBlocks.p);
             CKL("k_scan_local");
             LAUNCH(k_scan_blocks, 1, 1024, 0, st)(nsb, c->scanBlocks.p, which ? &c->grid->bondTerms : &c->grid->bondTotal);
             CKL("k_scan_blocks");
-            LAUNCH(k_scan_add, nsb, SCAN_BLOCK, 0, st)(nLocal, start, c->scanBlocks.p);
+            LAUNCH(k_scan_add, nsb, SCAN_BLOCK, 0, st)(n, start, c->scanBlocks.p);
             CKL("k_scan_add");
         }
     }
@@ -1210,23 +1181,12 @@ extern "C" int ddcb200_constructList(ddcb200_ctx *c)
         LAUNCH(k_nbr_filter, tilesL, 128, 0, st)(nLocal, nPad, c->pos32.p, c->cellOfSlot[nxt].p, c->cellStart.p, c->box, rl2f, c->grid,
                                             c->nbrCap, c->nbrRaw.p, c->nbrRawCount.p);
         CKL("k_nbr_filter");
-        if (c->listFused)
-        {
-            // one sweep; rows in two segments around the first bin edge (all the bin edges are that one edge, createInit)
-            LAUNCH(k_nbr_exact2, tilesL, 128, 0, st)(nLocal, nPad, c->nbrCap, c->pos4[nxt].p, c->box, c->box.binEdge2[0], c->grid, c->nbrRaw.p,
-                                                    c->nbrRawCount.p, c->nbr.p, c->nbrCount.p, c->nbrCum.p, c->gidOfBead.p, c->molTypeOfBead.p,
-                                                    c->molTypeSingle.p, c->bpairOffset.p, c->bpairKey.p, c->haveExcl ? 1 : 0,
-                                                    c->nranks > 1 ? c->tileGhost.p : nullptr);
-            CKL("k_nbr_exact2");
-        }
-        else
-        {
-            LAUNCH(k_nbr_exact, tilesL, 128, 0, st)(nLocal, nPad, c->nbrCap, c->pos4[nxt].p, c->box, c->grid, c->nbrRaw.p, c->nbrRawCount.p,
-                                                   c->nbr.p, c->nbrCount.p, c->nbrCum.p, c->gidOfBead.p, c->molTypeOfBead.p,
-                                                   c->molTypeSingle.p, c->bpairOffset.p, c->bpairKey.p, c->haveExcl ? 1 : 0,
-                                                   c->nranks > 1 ? c->tileGhost.p : nullptr);
-            CKL("k_nbr_exact");
-        }
+        // one sweep; rows in two segments around the bin edge
+        LAUNCH(k_nbr_exact2, tilesL, 128, 0, st)(nLocal, nPad, c->nbrCap, c->pos4[nxt].p, c->box, c->box.binEdge2[0], c->grid, c->nbrRaw.p,
+                                                c->nbrRawCount.p, c->nbr.p, c->nbrCount.p, c->nbrCum.p, c->gidOfBead.p, c->molTypeOfBead.p,
+                                                c->molTypeSingle.p, c->bpairOffset.p, c->bpairKey.p, c->haveExcl ? 1 : 0,
+                                                c->nranks > 1 ? c->tileGhost.p : nullptr);
+        CKL("k_nbr_exact2");
         CK(cudaEventRecord(c->evList[1], st));
         if (c->nranks > 1)
         {
@@ -1260,7 +1220,7 @@ extern "C" int ddcb200_constructList(ddcb200_ctx *c)
         CK(c->termMap.ensure(nAll + 1));
         CK(cudaMemsetAsync(c->termMap.p, 0xff, nAll * sizeof(int), st));
         LAUNCH(k_bond_resolve_terms, (nLocal + 255) / 256, 256, 0, st)(nLocal, c->pos4[nxt].p, c->bondCsrOff.p, c->bondEnt.p, c->nTerms, c->termsBead.p,
-                                                                   c->slotOfBead.p, c->bondStart0.p, c->bondCount0.p, c->bondRec.p, c->termMap.p);
+                                                                   c->slotOfBead.p, c->bondStart0.p, c->bondRec.p, c->termMap.p);
         CKL("k_bond_resolve_terms");
         LAUNCH(k_bond_resolve_beads, (nLocal + 255) / 256, 256, 0, st)(nLocal, c->pos4[nxt].p, c->bondCsrOff.p, c->bondEnt.p, c->termMap.p,
                                                                    c->bondStart.p, c->bondCount.p, c->bondStageIdx.p);
@@ -1282,11 +1242,18 @@ extern "C" int ddcb200_constructList(ddcb200_ctx *c)
     }
     if (c->prm.updateRate == 0)
     {
+        // neighborCheck compares with the positions of the build; posBuild is re-based by the prunes of the pair walk
+        for (int a = 0; a < 3; a++)
+        {
+            CK(c->posCheck[a].ensure((size_t)nPad));
+            CK(cudaMemcpyAsync(c->posCheck[a].p, c->posBuild[a].p, (size_t)nIon * sizeof(double), cudaMemcpyDeviceToDevice, st));
+        }
         int rcs = localSums(c, 1);   // neighborRef: rbar at the build
         if (rcs) return rcs;
     }
     c->listValid = true;
     c->hBuild[0] = c->box.hxx; c->hBuild[1] = c->box.hyy; c->hBuild[2] = c->box.hzz;
+    for (int a = 0; a < 3; a++) c->hCheck[a] = c->hBuild[a];
     c->pc.listSlack = 0.0;
     c->lastBuildLoop = c->loop;
     c->totalEntries = (int64_t)c->gridHost->totalEntries;
@@ -1311,7 +1278,7 @@ static double pruneArgsOf(const ddcb200_ctx *c, PruneArgs &pr)
     pr.keep2 = (c->pc.rmax + margin) * (c->pc.rmax + margin) * (1.0 + 1e-12);
     pr.walkLim = 1e300;
     pr.useLim = c->pc.rmax + margin;
-    pr.farTop = c->listFused ? c->nbrCap - 1 : -1;
+    pr.farTop = c->nbrCap - 1;
     return margin;
 }
 
@@ -1374,8 +1341,8 @@ static int neighborCheck(ddcb200_ctx *c, bool *update)
     int rc = localSums(c, 0);
     if (rc) return rc;
     CK(cudaMemsetAsync(c->chk.p + 6, 0, sizeof(double), st));
-    LAUNCH(k_nbr_check, (int)(c->nPad / TILE), TILE, 0, st)((int)c->nIon, (int)c->nLocal, c->pos4[c->cur].p, c->posBuild[0].p,
-                                                             c->posBuild[1].p, c->posBuild[2].p, c->pc, c->chk.p);
+    LAUNCH(k_nbr_check, (int)(c->nPad / TILE), TILE, 0, st)((int)c->nIon, (int)c->nLocal, c->pos4[c->cur].p, c->posCheck[0].p,
+                                                             c->posCheck[1].p, c->posCheck[2].p, c->pc, c->chk.p);
     CKL("k_nbr_check");
     if (c->nranks > 1)   // check4updateNeighbor's MPI_Allreduce of the flags (src/ddcUpdateAll.c:48-62) = max of d^2
         CKN(ncclAllReduce(c->chk.p + 6, c->chk.p + 6, 1, ncclDouble, ncclMax, (ncclComm_t)c->nccl, st));
@@ -1385,7 +1352,7 @@ static int neighborCheck(ddcb200_ctx *c, bool *update)
     const double *hi = c->box.hinv;
     double h[9];
     memcpy(h, c->prm.h, sizeof(h));
-    if (c->hBuild[0] != 0.0) { h[0] = c->hBuild[0]; h[4] = c->hBuild[1]; h[8] = c->hBuild[2]; }
+    if (c->hCheck[0] != 0.0) { h[0] = c->hCheck[0]; h[4] = c->hCheck[1]; h[8] = c->hCheck[2]; }
     const double ux = hi[0] + hi[1] + hi[2], uy = hi[3] + hi[4] + hi[5], uz = hi[6] + hi[7] + hi[8];
     const double sx = fabs(1.0 - (h[0] * ux + h[1] * uy + h[2] * uz)), sy = fabs(1.0 - (h[3] * ux + h[4] * uy + h[5] * uz)),
                  sz = fabs(1.0 - (h[6] * ux + h[7] * uy + h[8] * uz));
@@ -1412,8 +1379,8 @@ extern "C" int ddcb200_ddcenergy(ddcb200_ctx *c, int withEnergy)
     // ghost position run meanwhile, the others wait for it.  (updateRate = 0: neighborCheck needs the ghosts first)
     bool overlapped = false;
     // pruned rows (pair.cuh): this evaluation writes them if it follows a build or the last prune is pruneEvery evaluations old
-    const bool pruneCfg = c->pruneEvery > 0 && c->prm.updateRate > 0 && c->pc.listSlack == 0.0;
-    const bool pruneStep = pruneCfg && (!c->listValid || due || !c->pruneValid || c->sincePrune + 1 >= c->pruneEvery);
+    const bool pruneCfg = c->pruneEvery > 0;
+    bool pruneStep = pruneCfg && (!c->listValid || due || !c->pruneValid || c->sincePrune + 1 >= c->pruneEvery);
     if (c->listValid && !due && c->nranks > 1 && c->haloDirty)
     {
         // (a prune step takes the reference positions of the ghosts after the halo: in line)
@@ -1449,6 +1416,7 @@ extern "C" int ddcb200_ddcenergy(ddcb200_ctx *c, int withEnergy)
         rc = ddcb200_constructList(c);
         if (rc) return rc;
     }
+    pruneStep = pruneCfg && (pruneStep || !c->pruneValid);      // (updateRate = 0: neighborCheck may just have asked for the build)
     cudaStream_t st = c->stream;
     const int cur = c->cur;
     const int nLocal = (int)c->nLocal, nPad = (int)c->nPad;      // local beads = slots [0, nLocal)
@@ -1482,7 +1450,7 @@ extern "C" int ddcb200_ddcenergy(ddcb200_ctx *c, int withEnergy)
         CKL("k_bonded");
     }
     int pruneMode = 0;
-    PruneArgs pr = {nullptr, nullptr, 0.0, 0.0, 0.0, c->listFused ? c->nbrCap - 1 : -1};
+    PruneArgs pr = {nullptr, nullptr, 0.0, 0.0, 0.0, c->nbrCap - 1};
     PairConst pcl = c->pc;
     if (pruneCfg)
     {
@@ -1500,6 +1468,10 @@ extern "C" int ddcb200_ddcenergy(ddcb200_ctx *c, int withEnergy)
                 if (c->nCellsBuilt > 0) CK(cudaMemsetAsync(c->cellDmax.p, 0, 2 * (size_t)c->nCellsBuilt * sizeof(unsigned long long), st));
                 c->rebased = true;
                 c->movedSinceRef = false;
+                // the box of the reference positions: a barostat's change of the box edges counts from here (PairConst::listSlack)
+                c->hBuild[0] = c->box.hxx; c->hBuild[1] = c->box.hyy; c->hBuild[2] = c->box.hzz;
+                c->pc.listSlack = 0.0;
+                pcl.listSlack = 0.0;
             }
             // right after a build the rows are ordered by the distances of these very positions: the walk can stop at rmax + margin
             if (!c->rebased) pr.walkLim = (c->pc.rmax + margin) * (1.0 + 1e-12);
@@ -2114,7 +2086,7 @@ extern "C" int64_t ddcb200_getPairs(ddcb200_ctx *c, int64_t capacity, int *beadI
     };
     // rows of the one-pass build are two segments: the first cum[0] entries from the front, the others from the end of the row's
     // allocation backwards (k_nbr_exact2); rows of k_nbr_exact run forward
-    const int farTop = c->listFused ? c->nbrCap - 1 : -1;
+    const int farTop = c->nbrCap - 1;
     int maxc = 0;
     for (int i = 0; i < n; i++) maxc = std::max(maxc, cnt[i]);
     const size_t nrows = farTop >= 0 ? (size_t)c->nbrCap : (size_t)maxc;
@@ -2151,7 +2123,7 @@ extern "C" int ddcb200_pairSetHash(ddcb200_ctx *c, uint64_t out[6])
     CK(sc.h.ensure(8));
     CK(cudaMemsetAsync(sc.h.p, 0, 8 * sizeof(unsigned long long), c->stream));
     LAUNCH(k_pair_hash, (int)((c->nLocal + 255) / 256), 256, 0, c->stream)((int)c->nLocal, (int)c->nPad, c->nbr.p, c->nbrCount.p, c->beadOfSlot[c->cur].p,
-                                                                     c->gidOfBead.p, c->nbrCum.p, c->listFused ? c->nbrCap - 1 : -1, sc.h.p);
+                                                                     c->gidOfBead.p, c->nbrCum.p, c->nbrCap - 1, sc.h.p);
     CKL("k_pair_hash");
     CK(cudaMemcpyAsync(out, sc.h.p, 6 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, c->stream));
     CK(cudaStreamSynchronize(c->stream));

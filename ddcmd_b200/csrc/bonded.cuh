@@ -86,23 +86,37 @@ __device__ __forceinline__ void dihedral(V3 vij, V3 vjk, V3 vkl, double &ang, do
 // resident here is skipped, and so is a bead's entry whose term has its role-0 bead on another rank (molecules are whole
 // on their owner rank, src/ddcRuleMolecule.c:43, so neither happens for a Martini deck).
 // ---- at every list build: the terms and the per-bead contribution lists of the resident local beads, in slot order -----------------
-// cnt[s] = entries of slot s (its contributions), cnt0[s] = those with role 0 (the terms this bead "owns": each term has exactly one)
+// cnt[s] = entries of slot s (its contributions); cntK[g * nIon + s] = the terms this bead "owns" (its role-0 entries: each term
+// has exactly one) of kind group g - the local terms are numbered group by group (bonds, the three angle forms, torsions,
+// impropers, restraints) and by slot inside a group, so that the threads of a warp of k_bonded evaluate the same kind of term
+#define BOND_GROUPS 7
 __global__ void k_bond_count(int nIon, const double4 *__restrict__ pos, const int *__restrict__ csrOff, const uint32_t *__restrict__ ent,
-                             int *__restrict__ cnt, int *__restrict__ cnt0)
+                             int64_t nTerms, const Term *__restrict__ terms, int *__restrict__ cnt, int *__restrict__ cntK)
 {
     const int s = blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= nIon) return;
     const unsigned long long w = (unsigned long long)__double_as_longlong(pos[s].w);
-    int n = 0, n0 = 0;
+    int n = 0, nk[BOND_GROUPS];
+#pragma unroll
+    for (int g = 0; g < BOND_GROUPS; g++) nk[g] = 0;
     if (!(w >> 63))
     {
         const int b = (int)((w >> 32) & 0x7fffffffull);
         const int lo = csrOff[b];
         n = csrOff[b + 1] - lo;
-        for (int q = 0; q < n; q++) n0 += ((ent[lo + q] & 3u) == 0u) ? 1 : 0;
+        for (int q = 0; q < n; q++)
+        {
+            const uint32_t e = ent[lo + q];
+            if ((e & 3u) != 0u) continue;
+            const int64_t t = (int64_t)(e >> 2);
+            const int kind = t >= nTerms ? 6 : terms[t].kind;
+#pragma unroll
+            for (int g = 0; g < BOND_GROUPS; g++) nk[g] += (kind == g) ? 1 : 0;
+        }
     }
     cnt[s] = n;
-    cnt0[s] = n0;
+#pragma unroll
+    for (int g = 0; g < BOND_GROUPS; g++) cntK[(size_t)g * nIon + s] = nk[g];
 }
 
 // exclusive scan of n ints (n = resident beads): per-block scans, a scan of the block totals by one block, then the offsets
@@ -172,23 +186,31 @@ k_scan_add(int n, int *__restrict__ out, const int *__restrict__ blockSum)
     if (i < n) out[i] += blockSum[blockIdx.x];
 }
 
-// the local terms: one record per term, written by the slot of its role-0 bead; termMap[t] = index of term t here
+// the local terms: one record per term, written by the slot of its role-0 bead at the term's place in the kind-grouped numbering;
+// termMap[t] = index of term t here
 __global__ void k_bond_resolve_terms(int nIon, const double4 *__restrict__ pos, const int *__restrict__ csrOff, const uint32_t *__restrict__ ent,
                                      int64_t nTerms, const Term *__restrict__ terms, const int *__restrict__ slotOfBead,
-                                     const int *__restrict__ start0, const int *__restrict__ cnt0, BondRec *__restrict__ recs,
-                                     int *__restrict__ termMap)
+                                     const int *__restrict__ startK, BondRec *__restrict__ recs, int *__restrict__ termMap)
 {
     const int s = blockIdx.x * blockDim.x + threadIdx.x;
-    if (s >= nIon || cnt0[s] == 0) return;
+    if (s >= nIon) return;
     const unsigned long long w = (unsigned long long)__double_as_longlong(pos[s].w);
+    if (w >> 63) return;
     const int b = (int)((w >> 32) & 0x7fffffffull);
     const int elo = csrOff[b], n = csrOff[b + 1] - elo;
-    int lt = start0[s];
+    int next[BOND_GROUPS];      // where this bead's next term of each kind group goes
+#pragma unroll
+    for (int g = 0; g < BOND_GROUPS; g++) next[g] = startK[(size_t)g * nIon + s];
     for (int q = 0; q < n; q++)
     {
         const uint32_t e = ent[elo + q];
         if ((e & 3u) != 0u) continue;
         const int64_t t = (int64_t)(e >> 2);
+        const int group = t >= nTerms ? 6 : terms[t].kind;
+        int lt = 0;
+#pragma unroll
+        for (int g = 0; g < BOND_GROUPS; g++)
+            if (group == g) lt = next[g]++;
         BondRec r;
         r.role = 0;
         r.q = 0;
@@ -213,7 +235,6 @@ __global__ void k_bond_resolve_terms(int nIon, const double4 *__restrict__ pos, 
         }
         recs[lt] = r;
         termMap[t] = lt;
-        lt++;
     }
 }
 

@@ -259,6 +259,33 @@ __global__ void k_gather(int n, const int *__restrict__ perm, const int *__restr
 // single-precision distance is below (rcut+skin)^2 times a safety margin covering the fp32
 // rounding of the coordinates.  It only shrinks the work of the exact pass below; every list
 // decision is taken there in fp64 with the reference's own arithmetic.
+// The x-adjacent cells of a stencil row are one run of consecutive slots, so a bead scans 9 long runs (plus the rare cell that
+// wraps around) instead of 27 short ones, and the nearest-image arithmetic of boxes with fewer than three cells along an axis
+// lives in a loop of its own: the common loop is a load, seven flops, two compares.
+template <bool IMAGE>
+__device__ __forceinline__ void filterRun(int lo, int hi, int i, float bx, float by, float bz, bool px, bool py, bool pz, float Lx, float Ly, float Lz,
+                                          float rl2f, const float4 *__restrict__ pos32, int nPad, int cap, uint32_t *__restrict__ raw, int &cnt)
+{
+    const float hx2 = 0.5f * Lx, hy2 = 0.5f * Ly, hz2 = 0.5f * Lz;
+    for (int j = lo; j < hi; j++)
+    {
+        const float4 pj = pos32[j];
+        float x = bx - pj.x, y = by - pj.y, z = bz - pj.z;
+        if (IMAGE)
+        {
+            if (px) { if (x > hx2) x -= Lx; if (x < -hx2) x += Lx; }
+            if (py) { if (y > hy2) y -= Ly; if (y < -hy2) y += Ly; }
+            if (pz) { if (z > hz2) z -= Lz; if (z < -hz2) z += Lz; }
+        }
+        const float r2 = x * x + y * y + z * z;
+        if (r2 < rl2f && j != i)
+        {
+            if (cnt < cap) raw[(size_t)cnt * nPad + i] = (uint32_t)j;
+            cnt++;
+        }
+    }
+}
+
 __global__ void __launch_bounds__(128)
 k_nbr_filter(int nIon, int nPad, const float4 *__restrict__ pos32, const int *__restrict__ cellOf,
              const int *__restrict__ cellStart, BoxConst b, float rl2f, GridDev *gp, int cap, uint32_t *__restrict__ raw,
@@ -271,13 +298,12 @@ k_nbr_filter(int nIon, int nPad, const float4 *__restrict__ pos32, const int *__
     {
         const int nx = gp->n[0], ny = gp->n[1], nz = gp->n[2], ncell = nx * ny * nz;
         const float Lx = (float)b.hxx, Ly = (float)b.hyy, Lz = (float)b.hzz;
-        const float hx2 = 0.5f * Lx, hy2 = 0.5f * Ly, hz2 = 0.5f * Lz;
         // with >= 3 cells along an axis a wrapped stencil cell has ONE possible image: shift it;
         // with fewer the stencil is deduplicated and each pair takes its nearest image
         const bool px = nx < 3, py = ny < 3, pz = nz < 3;
+        const bool anyImage = px || py || pz;
         const int c = cellOf[i];         // a local slot: the plain cell index
         const int cx = c % nx, cy = (c / nx) % ny, cz = c / (nx * ny);
-        const int lx = nx >= 3 ? -1 : 0, hx = nx >= 2 ? 1 : 0;
         const int ly = ny >= 3 ? -1 : 0, hy = ny >= 2 ? 1 : 0;
         const int lz = nz >= 3 ? -1 : 0, hz = nz >= 2 ? 1 : 0;
         for (int dz = lz; dz <= hz; dz++)
@@ -294,32 +320,34 @@ k_nbr_filter(int nIon, int nPad, const float4 *__restrict__ pos32, const int *__
                 if (ay < 0) { ay += ny; sy = -Ly; }
                 else if (ay >= ny) { ay -= ny; sy = Ly; }
                 const float by = py ? pi.y : pi.y - sy;
-                for (int dx = lx; dx <= hx; dx++)
+                const int rowBase = nx * (ay + ny * az);
+                // runs along x.  nx >= 3: the cells cx-1 .. cx+1 clipped to the row, then the one cell that wraps around (most beads have
+                // none); nx < 3: the bead's own cell, then the other one (nx = 2), pairs take their nearest image
+                for (int sg = 0; sg < 2; sg++)
                 {
-                    int ax = cx + dx;
+                    int c0, c1;      // cells c0 .. c1 of the row; c1 < c0: nothing
                     float sx = 0.0f;
-                    if (ax < 0) { ax += nx; sx = -Lx; }
-                    else if (ax >= nx) { ax -= nx; sx = Lx; }
+                    if (!px)
+                    {
+                        if (sg == 0) { c0 = max(cx - 1, 0); c1 = min(cx + 1, nx - 1); }
+                        else if (cx == 0) { c0 = c1 = nx - 1; sx = -Lx; }
+                        else if (cx == nx - 1) { c0 = c1 = 0; sx = Lx; }
+                        else { c0 = 1; c1 = 0; }
+                    }
+                    else
+                    {
+                        if (sg == 0) c0 = c1 = cx;
+                        else if (nx == 2) c0 = c1 = 1 - cx;
+                        else { c0 = 1; c1 = 0; }
+                    }
+                    if (c1 < c0) continue;
                     const float bx = px ? pi.x : pi.x - sx;
-                    const int cc = ax + nx * (ay + ny * az);
-                    // the cell's local beads, then (several ranks) its ghosts
+                    // the cells' local beads, then (several ranks) their ghosts
                     for (int part = 0; part < 2; part++)
                     {
-                        const int lo = cellStart[cc + part * ncell], hi = cellStart[cc + part * ncell + 1];
-                        for (int j = lo; j < hi; j++)
-                        {
-                            const float4 pj = pos32[j];
-                            float x = bx - pj.x, y = by - pj.y, z = bz - pj.z;
-                            if (px) { if (x > hx2) x -= Lx; if (x < -hx2) x += Lx; }
-                            if (py) { if (y > hy2) y -= Ly; if (y < -hy2) y += Ly; }
-                            if (pz) { if (z > hz2) z -= Lz; if (z < -hz2) z += Lz; }
-                            const float r2 = x * x + y * y + z * z;
-                            if (r2 < rl2f && j != i)
-                            {
-                                if (cnt < cap) raw[(size_t)cnt * nPad + i] = (uint32_t)j;
-                                cnt++;
-                            }
-                        }
+                        const int lo = cellStart[part * ncell + rowBase + c0], hi = cellStart[part * ncell + rowBase + c1 + 1];
+                        if (anyImage) filterRun<true>(lo, hi, i, bx, by, bz, px, py, pz, Lx, Ly, Lz, rl2f, pos32, nPad, cap, raw, cnt);
+                        else filterRun<false>(lo, hi, i, bx, by, bz, px, py, pz, Lx, Ly, Lz, rl2f, pos32, nPad, cap, raw, cnt);
                     }
                 }
             }
@@ -335,7 +363,7 @@ k_nbr_filter(int nIon, int nPad, const float4 *__restrict__ pos32, const int *__
     }
 }
 
-// ---- 9. exact pass: pairlist1's test bit for bit, reOrgPairs' pruning, distance-bin order ----
+// ---- 9. exact pass: pairlist1's test bit for bit, reOrgPairs' pruning ----
 __device__ __forceinline__ bool isPruned(int bi, int bj, const uint64_t *__restrict__ gid,
                                          const int *__restrict__ molTypeOfBead, const int *__restrict__ molTypeSingle,
                                          const int *__restrict__ bpairOffset, const uint32_t *__restrict__ bpairKey)
@@ -372,109 +400,12 @@ __device__ __forceinline__ double4 ldPos256(const double4 *p)
 #endif
 }
 
-#define RAW_REJECT 0xffffffffu
-
-__global__ void __launch_bounds__(128)
-k_nbr_exact(int nIon, int nPad, int cap, const double4 *__restrict__ pos, BoxConst b, GridDev *gp, uint32_t *__restrict__ raw,
-            const int *__restrict__ rawCount, uint32_t *__restrict__ out, int *__restrict__ count, uint16_t *__restrict__ cum,
-            const uint64_t *__restrict__ gid, const int *__restrict__ molTypeOfBead, const int *__restrict__ molTypeSingle,
-            const int *__restrict__ bpairOffset, const uint32_t *__restrict__ bpairKey, int haveExcl, int *__restrict__ tileGhost)
-{
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    int total = 0;
-    bool ghostEntry = false;      // some entry of this row is a ghost slot (several ranks): the row waits for the halo
-    // per-bin counters, then running offsets, of this thread's row: a column of shared memory each (no two threads share one)
-    __shared__ unsigned short sBin[NBINS][128];
-#pragma unroll
-    for (int e = 0; e < NBINS; e++) sBin[e][threadIdx.x] = 0;
-    if (i < nIon)
-    {
-        const int n = min(rawCount[i], cap);
-        const double4 pi = pos[i];
-        const uint64_t wi = (uint64_t)__double_as_longlong(pi.w);
-        uint32_t jn = (0 < n) ? raw[i] : 0u;
-        for (int k = 0; k < n; k++)
-        {
-            const uint32_t j = jn;
-            if (k + 1 < n) jn = raw[(size_t)(k + 1) * nPad + i];
-            const double4 pj = ldPos256(pos + j);
-            // pairlist1, src/pairlist.c:280-288
-            double x = __dadd_rn(pi.x, -pj.x), y = __dadd_rn(pi.y, -pj.y), z = __dadd_rn(pi.z, -pj.z);
-            double r2 = exactR2(x, y, z);
-            if (r2 > b.R2cut)
-            {
-                wrapOnce(x, y, z, b);
-                r2 = exactR2(x, y, z);
-            }
-            uint32_t ent = RAW_REJECT;
-            if (r2 < b.rlist2)
-            {
-                int bin = 0;
-#pragma unroll
-                for (int e = 0; e < NBINS - 1; e++) bin += (r2 >= b.binEdge2[e]) ? 1 : 0;
-                ent = j | ((uint32_t)bin << 27);
-                const uint64_t wj = (uint64_t)__double_as_longlong(pj.w);
-                ghostEntry |= (wj >> 63) != 0ull;
-                if (haveExcl)
-                {
-                    // same molecule? bits 16..31 of w carry the low 16 bits of gid>>32: cheap reject before the gid gathers
-                    if (((wi ^ wj) & 0xffff0000ull) == 0ull &&
-                        isPruned((int)((wi >> 32) & 0x7fffffffull), (int)((wj >> 32) & 0x7fffffffull), gid, molTypeOfBead, molTypeSingle, bpairOffset, bpairKey))
-                        ent |= EXCL_BIT;
-                }
-                sBin[bin][threadIdx.x]++;
-                total++;
-            }
-            raw[(size_t)k * nPad + i] = ent;
-        }
-        // cumulative counts at every bin boundary (entries of bins 0..bnd); the counters become the running write offsets
-        int run = 0;
-#pragma unroll
-        for (int bnd = 0; bnd < NBINS; bnd++)
-        {
-            const int cnt = sBin[bnd][threadIdx.x];
-            sBin[bnd][threadIdx.x] = (unsigned short)run;
-            run += cnt;
-            cum[(size_t)bnd * nPad + i] = (uint16_t)run;
-        }
-        for (int k = 0; k < n; k++)
-        {
-            const uint32_t e = raw[(size_t)k * nPad + i];
-            if (e == RAW_REJECT) continue;
-            const int bin = (e >> 27) & 7;
-            const int dst = sBin[bin][threadIdx.x]++;
-            const uint32_t idx = e & 0x07ffffffu;
-            out[(size_t)dst * nPad + i] = idx | (e & EXCL_BIT);
-        }
-        count[i] = total;
-    }
-    // statistics
-    int m = total;
-    for (int o = 16; o > 0; o >>= 1) m = max(m, __shfl_xor_sync(0xffffffffu, m, o));
-    unsigned long long t = (unsigned long long)total;
-    for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
-    if ((threadIdx.x & 31) == 0 && m > 0)
-    {
-        atomicMax(&gp->maxCount, m);
-        atomicAdd(&gp->totalEntries, t);
-    }
-    if (tileGhost)
-    {
-        // one tile of k_pair = this block (TILE threads): does any of its rows read a ghost position?
-        __shared__ int anyGhost;
-        if (threadIdx.x == 0) anyGhost = 0;
-        __syncthreads();
-        if (ghostEntry) atomicOr(&anyGhost, 1);
-        __syncthreads();
-        if (threadIdx.x == 0) tileGhost[blockIdx.x] = anyGhost;
-    }
-}
-
 // ---- 9b. exact pass in one sweep, rows in two segments ----------------------------------------------------------------------------
-// The same decision as k_nbr_exact for every candidate, but each entry is written once, straight to its place: the entries listed
-// closer than nearEdge go to the front of the bead's row, the others from the end of the row's allocation backwards - two segments
-// in candidate order instead of eight sorted bins, so there is no counting sweep, no write-back of the candidates and no second
-// read (k_nbr_exact moves 2.6 GB for 0.9 GB of rows and candidates).  The lanes of a warp accept nearly every candidate (the fp32
+// pairlist1's decision for every candidate (src/pairlist.c:280-288, the reference's arithmetic without FMA: bit-exact membership) and
+// reOrgPairs' pruning flag; each entry is written once, straight to its place: the entries listed closer than nearEdge go to the
+// front of the bead's row, the others from the end of the row's allocation backwards - two segments in candidate order.  (Until
+// round 2 an exact pass k_nbr_exact sorted each row into eight distance bins with a counting sweep and a placing sweep: 1.56 ms and
+// 2.6 GB moved for 0.9 GB of rows and candidates against 0.84 ms here; profiles/r02c_k_nbr_exact_ncu_full.txt, r02t_*.)  The lanes of a warp accept nearly every candidate (the fp32
 // filter is tight), so their cursors advance together and a warp's stores fall into a few lines.  The pair walk visits the front
 // segment first: nearly all of it is inside the cutoff and right after a build it is all the pruned rows need, while the far
 // segment is nearly all outside - the lanes of a warp agree on whether the force block runs, which is what the bins were for.

@@ -26,7 +26,7 @@
 #endif
 
 #define TILE 128           // beads per CTA in the per-step kernels
-#define NBINS 8            // build-time distance bins used to order each bead's list
+#define NBINS 2            // segments of a row: listed closer / farther than the near edge (PairConst::binEdge)
 #define EXCL_BIT 0x80000000u
 
 struct BoxConst
@@ -221,8 +221,6 @@ struct ddcb200_ctx
     unsigned long long *dmax2 = nullptr;   // device: [0] bits of the max squared displacement of a LOCAL bead since the build (or the last
                                            // prune), [1] of a ghost, [2] bits of a bound of the displacement between the build and the last prune
     // pruned rows (k_pair2 MODE 1 / 2, DDCB200_PRUNE=<every>[,<margin>]; 0 = off)
-    bool listFused = true;        // DDCB200_LISTBUILD: rows in two segments (k_nbr_exact2) instead of eight bins
-    size_t smemOptin = 0;         // shared memory a block may opt in to on this device
     int pruneEvery = 4;           // steps between prunes (measured best with its default margin: profiles/r02p_prune_ab.jsonl)
     double pruneMargin = 0.0;     // entries closer than rmax + pruneMargin x deltaR are kept (0: 1.4 x pruneEvery / updateRate)
     int sincePrune = 0;           // force evaluations since the pruned rows were written
@@ -249,7 +247,7 @@ struct ddcb200_ctx
     int nbrCap = 0;               // entries per bead allocated
     bool listValid = false;
     int64_t lastBuildLoop = -1;
-    double binFrac[NBINS - 1] = {-0.25, -0.125, 0.0, 0.125, 0.25, 0.375, 0.625};   // ordering-bin edges, fractions of deltaR (DDCB200_BIN_EDGES)
+    double binFrac[NBINS - 1] = {0.3};   // the edge between the two segments of a row, as a fraction of deltaR beyond rmax (DDCB200_NEAR)
     float listBuildMs = 0.f;         // device time of the last list build (filter + exact pass), for ddcb200_listBuildInfo
     cudaEvent_t evList[2] = {nullptr, nullptr};
     // displacement-triggered rebuild (updateRate == 0, nbrcheck.cuh)
@@ -329,5 +327,7 @@ struct ddcb200_ctx
     DevBuf<double> consPairDist;
     int *consFlag = nullptr;             // device: clusters that hit the iteration cap
     double ncKBT = 0.0, ncP0 = 0.0, ncBeta = 0.0, ncTau = 0.0;   // nglfconstraint_parms: kB*T, P0, beta, tauBarostat
-    double hBuild[3] = {0, 0, 0};        // box edges at the last list build (nbr->h0, src/neighbor.c:231)
+    double hBuild[3] = {0, 0, 0};        // box edges when the reference positions of the displacement bounds were taken (the last build or prune)
+    double hCheck[3] = {0, 0, 0};        // box edges at the last list build (nbr->h0, src/neighbor.c:231): neighborCheck
+    DevBuf<double> posCheck[3];          // updateRate = 0: the positions at the last list build (neighborCheck; posBuild moves on with the prunes)
 };

@@ -61,12 +61,17 @@ def test_emu_pruned_rows(emu, golden_dir, name, monkeypatch):
     tv.test_pruned_rows_are_bitwise_neutral(golden_dir, name, monkeypatch)
 
 
+@pytest.mark.parametrize("mode", ["barostat", "ur0"])
+def test_emu_pruned_rows_other_modes(emu, golden_dir, mode, tmp_path, monkeypatch):
+    tv.test_pruned_rows_with_barostat_and_displacement_rebuilds(golden_dir, mode, tmp_path, monkeypatch)
+
+
 def test_emu_row_capacity_regrow(emu, golden_dir, monkeypatch):
     tv.test_row_capacity_regrow(golden_dir, monkeypatch)
 
 
-def test_emu_bin_edges_knob(emu, golden_dir, monkeypatch):
-    tv.test_bin_edges_knob_keeps_the_pair_set(golden_dir, monkeypatch)
+def test_emu_near_edge_knob(emu, golden_dir, monkeypatch):
+    tv.test_near_edge_knob_keeps_the_pair_set(golden_dir, monkeypatch)
 
 
 @pytest.mark.parametrize("name", SMALL)

@@ -1,9 +1,12 @@
 """Walk / row-order variants that must not change a result:
 
   * the per-bead list-walk bound against the global one: bitwise equal trajectories;
-  * DDCB200_BIN_EDGES: another row order, same pair set, forces to rounding;
+  * DDCB200_NEAR: another row order, same pair set, forces to rounding;
+  * DDCB200_PRUNE: the pruned rows of the pair walk, bitwise the results of the full walk, in every integrator / rebuild mode;
   * a first build whose rows overflow the allocated capacity regrows and repeats.
 """
+import os
+
 import numpy as np
 import pytest
 
@@ -13,15 +16,14 @@ from test_gpu_parity import F_TOL, _force_err, _load, _pairkey
 pytestmark = pytest.mark.gpu
 
 
-def test_bin_edges_knob_keeps_the_pair_set(golden_dir, monkeypatch):
-    """DDCB200_BIN_EDGES only reorders the entries of a row (here: two bins instead of eight): same pairs, forces to rounding."""
-    monkeypatch.setenv("DDCB200_LISTBUILD", "bins")      # the exact pass that orders rows by distance bin
+def test_near_edge_knob_keeps_the_pair_set(golden_dir, monkeypatch):
+    """DDCB200_NEAR moves the edge between the two segments of a row: same pairs, another order inside the rows, forces to rounding."""
     sim, ref = _load(golden_dir, "popc_small")
     sim.ddcenergy(1)
     a = sim.getState()
     pa = sim.getPairs()
     sim.close()
-    monkeypatch.setenv("DDCB200_BIN_EDGES", "-0.25,-0.25,-0.25,0.25,0.25,0.25,0.25")
+    monkeypatch.setenv("DDCB200_NEAR", "0.6")
     sim, _ = _load(golden_dir, "popc_small")
     sim.ddcenergy(1)
     b = sim.getState()
@@ -30,13 +32,13 @@ def test_bin_edges_knob_keeps_the_pair_set(golden_dir, monkeypatch):
     assert np.array_equal(np.sort(_pairkey(pa[0], pa[1])), np.sort(_pairkey(pb[0], pb[1])))
     assert not np.array_equal(pa[1], pb[1])              # the rows really are in a different order
     assert np.abs(a["fx"] - b["fx"]).max() <= 1e-10 * np.abs(a["fx"]).max()
-    sim.nglf(25)                                         # displacement-bounded walk across a rebuild with the merged bins
+    sim.nglf(25)                                         # across a rebuild and several prunes
     tr = ref["trace"].reshape(-1, 16)
     e = sim.energyInfo()
     etot = tr[24, 1] + tr[24, 2]
     assert abs((e.eion + e.rk) - etot) <= 1e-9 * max(abs(etot), abs(tr[24, 2]))
     sim.close()
-    monkeypatch.setenv("DDCB200_BIN_EDGES", "0.5,0.1")
+    monkeypatch.setenv("DDCB200_NEAR", "1.5")
     with pytest.raises(dd.DdcError):
         _load(golden_dir, "popc_small")
 
@@ -98,6 +100,39 @@ def test_pruned_rows_are_bitwise_neutral(golden_dir, name, monkeypatch):
     monkeypatch.setenv("DDCB200_PRUNE", "-1")
     with pytest.raises(dd.DdcError):
         _load(golden_dir, name)
+
+
+@pytest.mark.parametrize("mode", ["barostat", "ur0"])
+def test_pruned_rows_with_barostat_and_displacement_rebuilds(golden_dir, mode, tmp_path, monkeypatch):
+    """The pruned rows also serve NGLFCONSTRAINT with the barostat (the box the displacement bounds refer to is the one of the last
+    prune) and DDC updateRate = 0 (neighborCheck keeps the positions of the build, the prunes move their own reference on):
+    30 steps bitwise equal with and without them, same rebuild loops."""
+    import nglfc_decks
+    from test_zzzz_ur0 import ur0_deck
+    out = {}
+    for prune in ("0", "4", "3,0.05"):
+        monkeypatch.setenv("DDCB200_PRUNE", prune)
+        if mode == "barostat":
+            d = nglfc_decks.make_variant(golden_dir, "popc_small", "full", tmp_path / ("b" + prune.replace(",", "_")))
+            sim = dd.simulate_init(os.path.join(d, "object.data"))
+        else:
+            sim = dd.simulate_init(ur0_deck(golden_dir, "popc_small", tmp_path / ("u" + prune.replace(",", "_"))))
+        sim.ddcenergy(1)
+        builds, es = [], []
+        for _ in range(30):
+            sim.eval_integrator(1)
+            e = sim.energyInfo()
+            builds.append(sim.lastListBuild())
+            es.append((e.eion, e.rk, tuple(e.virial[:])))
+        out[prune] = (sim.getState(), builds, es, tuple(sim.getBox()), sim.pruneInfo())
+        sim.close()
+    a = out["0"]
+    assert out["4"][4]["every"] == 4 and out["4"][4]["pruned_entries"] > 0
+    for tag in ("4", "3,0.05"):
+        b = out[tag]
+        assert a[1] == b[1] and a[2] == b[2] and a[3] == b[3], tag
+        for k in ("rx", "ry", "rz", "vx", "vy", "vz", "fx", "fy", "fz"):
+            assert np.array_equal(a[0][k], b[0][k]), (tag, k)
 
 
 def test_row_capacity_regrow(golden_dir, monkeypatch):
