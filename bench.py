@@ -357,7 +357,7 @@ def main():
                 "parallelism": "ddc bricks %dx%dx%d, one process per GPU; migration + ghost lists every 20 steps and the per-step ghost halo "
                                "over NCCL (halo on its own stream beside the rows that read no ghost)" % lattice if world > 1 else "single GPU"}
     if os.environ.get("DDCB200_BENCH_RETRY"):
-        run_info["fallback"] = "first attempt failed; this run uses DDCB200_PAIR=old DDCB200_WALK=global"
+        run_info["fallback"] = "first attempt failed; this run uses DDCB200_PRUNE=0 DDCB200_WALK=global DDCB200_PAIR=1,1"
 
     if args.kernels_only:
         sim.profile(True)
@@ -422,16 +422,20 @@ def main():
     t0 = time.perf_counter()
     sim.sendState(host[0], host[1], host[2], host[3], host[4], host[5], loop=int(ee.loop), time=float(ee.time),
                   bead=beads if world > 1 else None)
+    sim.sync()
+    ta = time.perf_counter()
     for _ in range(KE):
         sim.nglf(1)
         ee = sim.energyInfo()
+    tb = time.perf_counter()
     nl2 = sim.numLocal()
     st2 = sim.getState(out=host_flat[:9 * nl2].reshape(9, nl2))
     barrier()
     t1 = time.perf_counter()
     e2e_sps = KE / max_over_ranks(t1 - t0)
+    e2e_parts = {"sendState_ms": (ta - t0) * 1e3, "steps_ms": (tb - ta) * 1e3, "getState_ms": (t1 - tb) * 1e3}
     e2e = {"value": e2e_sps, "unit": "steps/s", "h2d_bytes_per_step": 6 * 8 * n / KE, "d2h_bytes_per_step": 9 * 8 * n / KE + 24 * 8 * world,
-           "steps": KE, "note": "sendState(H2D, pinned) + per step [nglf(1) + energyInfo D2H] (printrate=1) + getState(D2H); bytes summed over ranks; "
+           "steps": KE, "parts_rank0": e2e_parts, "note": "sendState(H2D, pinned) + per step [nglf(1) + energyInfo D2H] (printrate=1) + getState(D2H); bytes summed over ranks; "
                                 "MD keeps the state on the device between prints, so the state copies are per run; plugin_seam has them per step"}
     # ---- the same through the plug-in seam of a host-side integrator (eval_potential, integration/ddcmd_shim.c mode 1): every step
     # uploads positions and velocities from pinned host memory, evaluates forces + energies, reads the forces and energyInfo back
@@ -505,8 +509,8 @@ if __name__ == "__main__":
         if int(os.environ.get("WORLD_SIZE", "1")) == 1 and "--impl" not in " ".join(sys.argv) and not os.environ.get("DDCB200_BENCH_RETRY"):
             import traceback
             traceback.print_exc()
-            log("[bench] run failed (%s); repeating once with DDCB200_PAIR=old DDCB200_WALK=global" % ex)
-            env = dict(os.environ, DDCB200_BENCH_RETRY="1", DDCB200_PAIR="old", DDCB200_WALK="global")
+            log("[bench] run failed (%s); repeating once with DDCB200_PRUNE=0 DDCB200_WALK=global DDCB200_PAIR=1,1" % ex)
+            env = dict(os.environ, DDCB200_BENCH_RETRY="1", DDCB200_PRUNE="0", DDCB200_WALK="global", DDCB200_PAIR="1,1")
             sys.stdout.flush()
             os.execve(sys.executable, [sys.executable] + sys.argv, env)
         raise

@@ -197,13 +197,13 @@ typedef void (*PairKernel)(int, int, const int *, int, const double4 *, const ui
                            const unsigned long long *, const int *, PruneArgs, BondAdd);
 struct PairVariant
 {
-    int pf, minb;
+    int pf, minb, eminb;
     PairKernel force[3], energy[3];      // [MODE]: 0 plain, 1 walk + write the pruned rows, 2 walk the pruned rows
 };
-// the energy instantiation needs more registers: never capped
-#define PV(P, M) {P, M, {k_pair2<false, P, M, 0>, k_pair2<false, P, M, 1>, k_pair2<false, P, M, 2>}, \
-                        {k_pair2<true, P, 1, 0>, k_pair2<true, P, 1, 1>, k_pair2<true, P, 1, 2>}}
-static const PairVariant g_pairVariants[] = {PV(1, 1), PV(2, 1), PV(2, 8), PV(3, 8), PV(4, 1)};      // measured: profiles/r02d_pair_variants.txt
+// the energy instantiation carries eight more accumulators: its register cap (E CTAs per SM, 1 = none) is chosen apart
+#define PV(P, M, E) {P, M, E, {k_pair2<false, P, M, 0>, k_pair2<false, P, M, 1>, k_pair2<false, P, M, 2>}, \
+                              {k_pair2<true, P, E, 0>, k_pair2<true, P, E, 1>, k_pair2<true, P, E, 2>}}
+static const PairVariant g_pairVariants[] = {PV(1, 1, 1), PV(2, 1, 1), PV(2, 8, 1), PV(3, 8, 1), PV(4, 1, 1), PV(2, 8, 6), PV(2, 8, 5)};      // measured: profiles/r02d_pair_variants.txt
 #undef PV
 static const int g_nPairVariants = (int)(sizeof(g_pairVariants) / sizeof(g_pairVariants[0]));
 
@@ -268,15 +268,15 @@ static int createInit(ddcb200_ctx *c)
     CK(cudaMemset(c->dmax2, 0, 4 * sizeof(unsigned long long)));
     if (const char *pv = getenv("DDCB200_PAIR"))
     {
-        int pf = 0, mb = 0;
-        if (sscanf(pv, "%d,%d", &pf, &mb) == 2)
+        int pf = 0, mb = 0, eb = 1;
+        if (sscanf(pv, "%d,%d,%d", &pf, &mb, &eb) >= 2)
         {
             c->pairVariant = -2;
             for (int v = 0; v < g_nPairVariants; v++)
-                if (g_pairVariants[v].pf == pf && g_pairVariants[v].minb == mb) c->pairVariant = v;
+                if (g_pairVariants[v].pf == pf && g_pairVariants[v].minb == mb && g_pairVariants[v].eminb == eb) c->pairVariant = v;
         }
         else c->pairVariant = -2;
-        if (c->pairVariant == -2) return fail(DDCB200_ERR_ARG, "DDCB200_PAIR must be one of the built <pf>,<minb> pairs");
+        if (c->pairVariant == -2) return fail(DDCB200_ERR_ARG, "DDCB200_PAIR must be one of the built <pf>,<minb>[,<minb of the energy kernel>] combinations");
     }
     if (const char *bm = getenv("DDCB200_BONDED"))
     {
