@@ -203,7 +203,9 @@ struct PairVariant
 // the energy instantiation carries eight more accumulators: its register cap (E CTAs per SM, 1 = none) is chosen apart
 #define PV(P, M, E) {P, M, E, {k_pair2<false, P, M, 0>, k_pair2<false, P, M, 1>, k_pair2<false, P, M, 2>}, \
                               {k_pair2<true, P, E, 0>, k_pair2<true, P, E, 1>, k_pair2<true, P, E, 2>}}
-static const PairVariant g_pairVariants[] = {PV(1, 1, 1), PV(2, 1, 1), PV(2, 8, 1), PV(3, 8, 1), PV(4, 1, 1), PV(2, 8, 6), PV(2, 8, 5)};      // measured: profiles/r02d_pair_variants.txt
+// measured: profiles/r02d_pair_variants.txt (force kernel), r02w_e2e_energy_caps.jsonl (energy kernel: 96 registers uncapped = 5 CTAs
+// per SM; capped for 6 = 80 registers, 8 bytes spilled: the per-step energy evaluation of the end-to-end loop 12 % faster)
+static const PairVariant g_pairVariants[] = {PV(1, 1, 1), PV(2, 1, 1), PV(2, 8, 6), PV(3, 8, 1), PV(4, 1, 1), PV(2, 8, 1), PV(2, 8, 5)};
 #undef PV
 static const int g_nPairVariants = (int)(sizeof(g_pairVariants) / sizeof(g_pairVariants[0]));
 
@@ -268,12 +270,13 @@ static int createInit(ddcb200_ctx *c)
     CK(cudaMemset(c->dmax2, 0, 4 * sizeof(unsigned long long)));
     if (const char *pv = getenv("DDCB200_PAIR"))
     {
-        int pf = 0, mb = 0, eb = 1;
+        int pf = 0, mb = 0, eb = 0;
         if (sscanf(pv, "%d,%d,%d", &pf, &mb, &eb) >= 2)
         {
+            // without the third number: the first built combination with that force kernel
             c->pairVariant = -2;
-            for (int v = 0; v < g_nPairVariants; v++)
-                if (g_pairVariants[v].pf == pf && g_pairVariants[v].minb == mb && g_pairVariants[v].eminb == eb) c->pairVariant = v;
+            for (int v = g_nPairVariants - 1; v >= 0; v--)
+                if (g_pairVariants[v].pf == pf && g_pairVariants[v].minb == mb && (eb == 0 || g_pairVariants[v].eminb == eb)) c->pairVariant = v;
         }
         else c->pairVariant = -2;
         if (c->pairVariant == -2) return fail(DDCB200_ERR_ARG, "DDCB200_PAIR must be one of the built <pf>,<minb>[,<minb of the energy kernel>] combinations");

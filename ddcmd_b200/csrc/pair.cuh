@@ -54,9 +54,9 @@ __device__ __forceinline__ double rsqrtFast(double x)
 #else
     double y;
     asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));      // MUFU.RSQ64H: about 2^-22 relative
-    const double h = 0.5 * x;
-    y = y * fma(-h * y, y, 1.5);
-    y = y * fma(-h * y, y, 1.5);
+    const double h = __dmul_rn(0.5, x);
+    y = __dmul_rn(y, __fma_rn(__dmul_rn(-h, y), y, 1.5));
+    y = __dmul_rn(y, __fma_rn(__dmul_rn(-h, y), y, 1.5));
     return y;
 #endif
 }
@@ -199,8 +199,10 @@ k_pair2(int nIon, int nPad, const int *__restrict__ tileOrder, int tileBase, con
         {
             const bool have = k0 + u < n;
             const double4 pj = pCur[u];
+            // The arithmetic of a pair is spelled out (no contraction left to the compiler): the instantiations of this kernel - with
+            // and without energies, over full and pruned rows - must give a pair the same force bit for bit, whichever of them meets it
             double x = pi.x - pj.x, y = pi.y - pj.y, z = pi.z - pj.z;
-            double r2 = x * x + y * y + z * z;
+            double r2 = __fma_rn(z, z, __fma_rn(y, y, __dmul_rn(x, x)));
             if (have && r2 > pc.R2cut)
             {
                 // nearestImage_fast: one lattice reduction per component (src/preduce.c:147-160)
@@ -210,7 +212,7 @@ k_pair2(int nIon, int nPad, const int *__restrict__ tileOrder, int tileBase, con
                 if (y < -pc.hhy) y += pc.hyy;
                 if (z > pc.hhz) z -= pc.hzz;
                 if (z < -pc.hhz) z += pc.hzz;
-                r2 = x * x + y * y + z * z;
+                r2 = __fma_rn(z, z, __fma_rn(y, y, __dmul_rn(x, x)));
             }
             if (MODE == 1 && have && r2 < pr.keep2)
             {
@@ -222,31 +224,32 @@ k_pair2(int nIon, int nPad, const int *__restrict__ tileOrder, int tileBase, con
                 const uint64_t wj = (uint64_t)__double_as_longlong(pj.w);
                 const bool excl = (eCur[u] & EXCL_BIT) != 0u;
                 const double ir1 = rsqrtFast(r2);
-                const double ir2 = ir1 * ir1;
+                const double ir2 = __dmul_rn(ir1, ir1);
                 double dvdr = 0.0;
                 if (!excl)
                 {
                     // Lennard-Jones: 4 eps (s12 - s6) + shift ; dvdr = 24 eps (s6 - 2 s12)/r^2 (src/bioMartini.c:1073-1080)
                     const double2 cc = ljRow[wj & 0xff];
-                    const double ir6 = ir2 * ir2 * ir2;
-                    const double a6 = cc.x * ir6, a12 = cc.y * ir6 * ir6;
-                    dvdr = (a6 - a12) * ir2;
+                    const double ir6 = __dmul_rn(__dmul_rn(ir2, ir2), ir2);
+                    const double a6 = __dmul_rn(cc.x, ir6), a12 = __dmul_rn(__dmul_rn(cc.y, ir6), ir6);
+                    dvdr = __dmul_rn(__dadd_rn(a6, -a12), ir2);
                     if (ENERGY) eLJ += (a12 * (1.0 / 12.0) - a6 * (1.0 / 6.0)) + sShift[ti * pc.ntypes + (int)(wj & 0xff)];
                 }
                 if (charged)
                 {
-                    const double kqij = kqi * sQ[(wj >> 8) & 0xff];
+                    const double kqij = __dmul_rn(kqi, sQ[(wj >> 8) & 0xff]);
                     // reaction field (src/bioMartini.c:1082-1085); pruned pairs keep only krf r^2 - crf (:1172-1174)
                     const double ir = excl ? 0.0 : ir1;
-                    dvdr += kqij * (twoKrf - ir2 * ir);
+                    dvdr = __fma_rn(kqij, __fma_rn(-ir2, ir, twoKrf), dvdr);
                     if (ENERGY) eEle += kqij * (ir + pc.krf * r2 - pc.crf);
                 }
-                const double fxij = -dvdr * x, fyij = -dvdr * y, fzij = -dvdr * z;
-                fxi += fxij;
-                fyi += fyij;
-                fzi += fzij;
+                const double ndv = -dvdr;
+                fxi = __fma_rn(ndv, x, fxi);
+                fyi = __fma_rn(ndv, y, fyi);
+                fzi = __fma_rn(ndv, z, fzi);
                 if (ENERGY)
                 {
+                    const double fxij = __dmul_rn(ndv, x), fyij = __dmul_rn(ndv, y), fzij = __dmul_rn(ndv, z);
                     vxx += fxij * x;
                     vyy += fyij * y;
                     vzz += fzij * z;
