@@ -9,7 +9,7 @@ integrate.  Before the warm-up the deck is brought to 310 K (untimed set-up).  `
 stream the kernels are launched on; `e2e` = the same through the reference-facing call
 sequence with HOST buffers (sendState H2D from pinned memory, then nglf(1) + energyInfo D2H
 every step = the shipped deck's printrate=1, then getState D2H).  The `roofline` object is
-for the dominant kernel (k_pair); `cpu_baseline` times the UNMODIFIED reference CPU path
+for the dominant kernel (k_pair2); `cpu_baseline` times the UNMODIFIED reference CPU path
 (oracle/_ref) on a bounded sample of the same membrane.
 
 --impl reference times only the reference CPU path (no GPU work): the same full deck, one single-rank

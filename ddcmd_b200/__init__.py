@@ -534,7 +534,7 @@ class Simulate:
         return counts.reshape(npair, int(nbins)), natoms
 
     def listBuildInfo(self):
-        """(variant in use: 0 undecided / 1 two-pass / 2 one-pass cell build, [ms of the timed two-pass build, ms of the timed cell build])"""
+        """(1, [device ms of the last list build (candidate pass + exact pass), 0.0])"""
         v = C.c_int()
         ms = (C.c_double * 2)()
         self._ck(lib().ddcb200_listBuildInfo(self.ctx, C.byref(v), ms))

@@ -236,10 +236,8 @@ int ddcb200_kineticByClass(ddcb200_ctx *ctx, int bySpecies, int nClasses, double
 int ddcb200_pairCorrelation(ddcb200_ctx *ctx, int nBins, double rmin, double delta, int logScale, double rmax,
                             unsigned long long *counts, unsigned long long *nAtoms);
 
-/* Which list build runs: 1 = two passes (fp32 candidate filter, then the exact pairlist1 test over the candidates),
- * 2 = one pass (one warp per cell, exact test on every stencil candidate), 0 = not decided yet.  Both write the same
- * rows bit for bit.  Unless DDCB200_LISTBUILD=twopass|cell fixes it, the first four rebuilds alternate between the
- * variants under CUDA events and the faster is kept; ms[0], ms[1] are the best device time of each. */
+/* The list build (measurement hook): *variant = 1 (there is one build: fp32 candidate pass, then the exact pairlist1 test over the
+ * candidates in one sweep); ms[0] = device time of the last build's two passes, ms[1] = 0. */
 int ddcb200_listBuildInfo(ddcb200_ctx *ctx, int *variant, double ms[2]);
 
 /* Pruned rows of the pair walk (measurement hook, no reference counterpart; DDCB200_PRUNE=<every>[,<margin>]): every <every> force
