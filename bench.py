@@ -395,7 +395,17 @@ def main():
     stored_bytes = 56 * n_loc + 8 * pairs
     peak, peak_kind = measured_peaks()
     achieved = alg_bytes / (pair_ms * 1e-3) / 1e9
-    traffic = ncu_traffic("k_pair2") if (args.workload == "membrane_1m" and world == 1) else None
+    # measured DRAM traffic per launch: the launches over the pruned rows and the ones over the full rows (which also write the pruned
+    # rows) were captured apart; the figure is their mean weighted by how often each ran in the profiled steps
+    traffic = None
+    if args.workload == "membrane_1m" and world == 1:
+        t2, t1 = ncu_traffic("k_pair2_mode2"), ncu_traffic("k_pair2_mode1")
+        n2, n1 = prof["pair"][1], prof["pair_prune"][1]
+        if t2 and t1 and n1 + n2 > 0:
+            traffic = {"bytes_per_launch": (n2 * t2["bytes_per_launch"] + n1 * t1["bytes_per_launch"]) / (n1 + n2),
+                       "source": "%s (x%d), %s (x%d)" % (t2["source"], n2, t1["source"], n1)}
+        else:
+            traffic = t2 or ncu_traffic("k_pair2")
     roofline = {"bound": "hbm", "kernel": "k_pair2", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": traffic["bytes_per_launch"] if traffic else None, "traffic_source": traffic["source"] if traffic else None,
                 "peak_kind": peak_kind, "algorithmic_bytes_per_launch": alg_bytes, "stored_bytes_per_launch": stored_bytes,

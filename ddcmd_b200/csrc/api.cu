@@ -283,9 +283,10 @@ static int createInit(ddcb200_ctx *c)
     }
     if (const char *bm = getenv("DDCB200_BONDED"))
     {
-        // A/B: CTAs per SM the registers of k_bonded are capped for (1 = no cap: 0.115 ms per step on the 1M-bead membrane; 8: 0.080;
-        // 10: 0.078; 12 = 40 registers, the default: 0.073 - the kernel is latency-bound and gains more from resident warps than it
-        // loses to spills; profiles/r02h_variants.txt)
+        // A/B: CTAs per SM the registers of k_bonded are capped for.  With one thread per (term, endpoint) record the 40-register
+        // build (12) won: 0.073 ms against 0.115 uncapped (profiles/r02h_variants.txt).  Since a thread evaluates a whole term and
+        // stages up to four forces the caps only spill: uncapped (1, the default) 0.037 ms, 8: 0.040, 12: 0.046
+        // (profiles/r02aa_bonded_filter_ab.jsonl)
         c->bondedCap = atoi(bm);
         if (c->bondedCap != 1 && c->bondedCap != 8 && c->bondedCap != 12) return fail(DDCB200_ERR_ARG, "DDCB200_BONDED must be 1, 8 or 12");
     }

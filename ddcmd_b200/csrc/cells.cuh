@@ -262,13 +262,15 @@ __global__ void k_gather(int n, const int *__restrict__ perm, const int *__restr
 // The x-adjacent cells of a stencil row are one run of consecutive slots, so a bead scans 9 long runs (plus the rare cell that
 // wraps around) instead of 27 short ones, and the nearest-image arithmetic of boxes with fewer than three cells along an axis
 // lives in a loop of its own: the common loop is a load, seven flops, two compares.
+// One run of consecutive candidate slots, 32 at a time: the distance tests of a chunk only set bits of a mask (eight loads in flight,
+// no store and no branch between them), then the set bits are turned into row entries.  Interleaving test and store cost 24
+// instructions per candidate, 10 of them the store path that some lane of the warp takes in nearly every iteration.
 template <bool IMAGE>
 __device__ __forceinline__ void filterRun(int lo, int hi, int i, float bx, float by, float bz, bool px, bool py, bool pz, float Lx, float Ly, float Lz,
                                           float rl2f, const float4 *__restrict__ pos32, int nPad, int cap, uint32_t *__restrict__ raw, int &cnt)
 {
     const float hx2 = 0.5f * Lx, hy2 = 0.5f * Ly, hz2 = 0.5f * Lz;
-    for (int j = lo; j < hi; j++)
-    {
+    auto inside = [&](int j) {
         const float4 pj = pos32[j];
         float x = bx - pj.x, y = by - pj.y, z = bz - pj.z;
         if (IMAGE)
@@ -277,10 +279,23 @@ __device__ __forceinline__ void filterRun(int lo, int hi, int i, float bx, float
             if (py) { if (y > hy2) y -= Ly; if (y < -hy2) y += Ly; }
             if (pz) { if (z > hz2) z -= Lz; if (z < -hz2) z += Lz; }
         }
-        const float r2 = x * x + y * y + z * z;
-        if (r2 < rl2f && j != i)
+        return x * x + y * y + z * z < rl2f;
+    };
+    for (int j0 = lo; j0 < hi; j0 += 32)
+    {
+        // one code path for whole and partial chunks (slots past the end of the run re-test its last candidate and are masked off):
+        // the lanes of a warp sit in two cells with different runs, and two paths would be executed one after the other
+        unsigned mask = 0u;
+        const int last = hi - 1;
+#pragma unroll
+        for (int q = 0; q < 32; q++) mask |= inside(min(j0 + q, last)) ? (1u << q) : 0u;      // bit positions are compile-time constants
+        if (hi - j0 < 32) mask &= (1u << (hi - j0)) - 1u;
+        if ((unsigned)(i - j0) < 32u) mask &= ~(1u << (i - j0));      // the bead itself
+        while (mask)
         {
-            if (cnt < cap) raw[(size_t)cnt * nPad + i] = (uint32_t)j;
+            const int q = __ffs(mask) - 1;
+            mask &= mask - 1u;
+            if (cnt < cap) raw[(size_t)cnt * nPad + i] = (uint32_t)(j0 + q);
             cnt++;
         }
     }

@@ -234,7 +234,7 @@ struct ddcb200_ctx
     DevBuf<unsigned long long> nbrDmax;    // [2][ncell]: the maximum over each cell's stencil, without / with the ghost parts
     int nCellsBuilt = 0;
     int pairVariant = 2;          // DDCB200_PAIR: index into the k_pair2 instantiations of api.cu
-    int bondedCap = 12;           // DDCB200_BONDED
+    int bondedCap = 1;            // DDCB200_BONDED: register cap of k_bonded as CTAs per SM; 1 = none (84 registers): best since a thread evaluates a whole term
     DevBuf<float> dispOfSlot;     // each local bead's own displacement since the build, rounded up (0 right after a build)
     DevBuf<double> mmPartial;
     GridDev *grid = nullptr;      // device
