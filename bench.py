@@ -72,6 +72,14 @@ class ClockSampler(threading.Thread):
         except Exception:
             pass
 
+    def wait_first(self, timeout=5.0):
+        """block until nvidia-smi has loaded and delivered its first sample: its start-up enumerates every GPU of the box through the
+        driver and was seen to stall the kernel launches of all ranks for milliseconds - inside a 20-step window of an 8-GPU run
+        (3 ms of work) that tripled the measured time.  The start-up now happens before the warm-up steps."""
+        t0 = time.time()
+        while not self.samples and time.time() - t0 < timeout:
+            time.sleep(0.05)
+
     def finish(self):
         self.stop_flag = True
         if self.proc:
@@ -307,16 +315,17 @@ def main():
         if not args.no_equilibration:
             temps = equilibrate(sim, dd, args.equil_rounds, args.equil_steps)
             out["equilibration_T_K"] = [round(x, 1) for x in temps]
-        sim.nglf(W)
-        sim.sync()
-        l0 = sim.kernelLaunches()
         # clocks and throttle reasons under load: one sampler (rank 0's GPU; every GPU of the box runs the same step), kept running
         # through the long window below so that most samples fall under load.  (One nvidia-smi poller per rank at 100 ms was seen
-        # to stall the timed window of 2-GPU runs by up to 2x.)
+        # to stall the timed window of 2-GPU runs by up to 2x.)  It is started, and its first sample awaited, before the warm-up.
         clocks = ClockSampler(local) if rank == 0 else None
         if clocks:
             clocks.start()
-        time.sleep(0.3)
+            clocks.wait_first()
+        barrier()
+        sim.nglf(W)
+        sim.sync()
+        l0 = sim.kernelLaunches()
         barrier()
         sim.sync()
         sim.timerRecord(0)
