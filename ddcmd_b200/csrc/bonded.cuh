@@ -5,8 +5,9 @@
 // Replaces charmmConvalent + connectiveEnergy + res*Sorted (src/bioCharmmCovalent.c:95-251,
 // src/bioCharmmCovalentEnergies.c:266-351,754-794, src/bioCharmmCovalentEnergiesSorted.c)
 // and bondedGPU.cu's seven kernels, and restraint() (src/restraint.c:259-361).
-// One thread per resident local bead gathers the force of every term the bead takes part in (no atomics: bitwise
-// reproducible); terms are sorted by kind on the host, so the lanes of a warp mostly run the same formula.
+// One thread per local term evaluates it once and stages the forces on its beads; the pair kernel adds each bead's staged forces
+// in the bead's fixed entry order (no atomics: bitwise reproducible).  The local terms are numbered kind by kind at every list
+// build, so the lanes of a warp mostly run the same formula.
 #pragma once
 #include "engine.cuh"
 
@@ -400,10 +401,6 @@ __device__ __forceinline__ void bondedEval(const BondRec &tm, const double *__re
             }
 }
 
-// One thread per RECORD (records of a bead are consecutive, beads in slot order): every thread evaluates its record, the forces
-// are staged in shared memory, and the thread of a bead's first record adds the bead's records up in their fixed order and
-// adds the sum to the slot's pair force - no atomic, one writer per slot.  A bead belongs to the CTA that holds its first
-// record; a CTA therefore also evaluates the up to BONDED_SPILL records of its last beads that lie beyond its 128.
 // Every term is evaluated ONCE, by one thread, which stages the forces on the term's beads (stage[4 term + role], coalesced);
 // the pair kernel, which runs after this one, adds per local bead the bead's contributions in their fixed order to the bead's
 // pair force before it stores it (BondAdd, pair.cuh) - no atomic, one writer per slot, the same order every run.
