@@ -214,7 +214,8 @@ static const int g_nPairVariants = (int)(sizeof(g_pairVariants) / sizeof(g_pairV
 static double pruneFracOf(const ddcb200_ctx *c)
 {
     // (updateRate = 0, rebuilds triggered by the displacements: the margin of a 20-step schedule)
-    const double frac = c->pruneMargin > 0.0 ? c->pruneMargin : 1.4 * c->pruneEvery / (c->prm.updateRate > 0 ? c->prm.updateRate : 20);
+    // (a deck that rebuilds rarely for its skin would get a margin no bead can keep: at least a fifth of the skin)
+    const double frac = c->pruneMargin > 0.0 ? c->pruneMargin : std::max(0.2, 1.4 * c->pruneEvery / (c->prm.updateRate > 0 ? c->prm.updateRate : 20));
     return std::min(frac, 1.0);
 }
 
