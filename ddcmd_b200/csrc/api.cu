@@ -1384,7 +1384,7 @@ extern "C" int ddcb200_ddcenergy(ddcb200_ctx *c, int withEnergy)
     // ghost position run meanwhile, the others wait for it.  (updateRate = 0: neighborCheck needs the ghosts first)
     bool overlapped = false;
     // pruned rows (pair.cuh): this evaluation writes them if it follows a build or the last prune is pruneEvery evaluations old
-    const bool pruneCfg = c->pruneEvery > 0;
+    const bool pruneCfg = c->pruneEvery > 0 && pruneFracOf(c) < 0.8;      // (a margin near the whole skin prunes nothing: e.g. a deck that rebuilds every 5 steps)
     bool pruneStep = pruneCfg && (!c->listValid || due || !c->pruneValid || c->sincePrune + 1 >= c->pruneEvery);
     if (c->listValid && !due && c->nranks > 1 && c->haloDirty)
     {
